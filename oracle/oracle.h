@@ -1,0 +1,151 @@
+/*
+ * oracle/oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C) of the simulation (playout) phase of thomasmarsh/mcts:
+ * the five bitboard games, the playout loop and its three in-scope policies, and the
+ * statistics a playout feeds into backprop.  It exists to CHECK the CUDA path
+ * (tests/, __graft_entry__.smoke()) and to be TIMED as the CPU baseline
+ * (bench.py cpu_baseline / --impl reference).  The product (mcts_b200/, include/)
+ * never links, imports or calls anything in this directory.
+ *
+ * Pinning status: the reference is a Rust workspace and no Rust toolchain exists in
+ * this image, so the reference itself cannot be run here (no oracle/_ref).  The
+ * restatement is pinned against every golden vector / known-answer test the
+ * reference's own tests hold for this path (tests/test_oracle_golden.py lists them
+ * with file:line), and against restatements of the reference tests' own naive
+ * array-board oracles (oracle/naive_ref.c).  NOT pinned by any reference test, and
+ * therefore pinned only by reading code: the ORDER of generate_actions output, the
+ * random_best visiting order, DecisiveMove's Win-mode fallback, "no actions => draw".
+ * The RNG stream is deliberately NOT the reference's (rand 0.8 SmallRng, a crates.io
+ * dependency absent from /root/reference): both this oracle and the CUDA kernels
+ * use the counter-based Philox4x32-10 draw discipline documented in DESIGN.md.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_CONNECT4 = 0, ORC_BREAKTHROUGH = 1, ORC_KNIGHTTHROUGH = 2, ORC_OTHELLO = 3, ORC_HEX11 = 4, ORC_NUM_GAMES = 5 };
+enum { ORC_UNIFORM = 0, ORC_EPS_MAST = 1, ORC_DECISIVE_WIN = 2 };
+enum { ORC_NOT_TERMINAL = 0, ORC_DRAW = 1, ORC_WINNER_P0 = 2, ORC_WINNER_P1 = 3 };
+enum { ORC_END_TERMINAL = 0, ORC_END_TURN_LIMIT = 1, ORC_END_NO_ACTIONS = 2 };
+
+#define ORC_MAX_ACTIONS 256
+#define ORC_OTHELLO_PASS 64
+
+/* Same byte layout as include/mcts_rollout.h's mr_leaf (declared separately on
+ * purpose: the oracle shares no header with the product).
+ *   Connect4/Breakthrough/Knightthrough/Othello: board[0]=black, board[1]=white in the
+ *     reference's row-major layout (idx = row*cols + col, row 0 = south/bottom).
+ *   Hex 11x11: board[0..1] = P0 words (low word first), board[2..3] = P1 words.
+ *   turn: player to move (0 = Black / P0).
+ *   flag: Connect4/Breakthrough/Knightthrough `winner`; Othello `last_pass`. */
+typedef struct {
+    uint64_t board[4];
+    uint8_t turn;
+    uint8_t flag;
+    uint8_t pad[6];
+} orc_state;
+
+typedef struct {
+    uint32_t wins[2];
+    uint32_t draws;   /* every zero-utility ending: terminal draw, depth cutoff, no-actions */
+    uint32_t cutoffs; /* the subset of `draws` that ended by max_playout_depth */
+    uint64_t sum_depth;
+} orc_leaf_result;
+
+typedef struct {
+    uint32_t visits;
+    int32_t score;
+} orc_action_stat;
+
+typedef struct {
+    uint32_t depth;
+    uint8_t outcome;  /* ORC_DRAW / ORC_WINNER_P0 / ORC_WINNER_P1 as utilities see it; NOT_TERMINAL endings map to ORC_DRAW */
+    uint8_t end_type; /* ORC_END_* */
+    uint8_t pad[2];
+} orc_playout_record;
+
+/* ---- rules (games.c) ---- */
+void orc_initial_state(int game, orc_state *out);
+int orc_num_actions(int game); /* size of the dense action-id space (MAST/AMAF tables) */
+int orc_generate_actions(int game, const orc_state *s, uint16_t *out);
+void orc_apply(int game, orc_state *s, uint16_t action);
+int orc_is_terminal(int game, const orc_state *s);
+int orc_winner(int game, const orc_state *s); /* -1 none, else player index */
+int orc_terminal_status(int game, const orc_state *s);
+int orc_player_to_move(int game, const orc_state *s);
+uint64_t orc_hex_flood_iterations(void); /* instrumentation: flood6 fix-point iterations since reset */
+void orc_hex_flood_iterations_reset(void);
+/* generic-size Connect4 (the reference's 4x5 draw test, connect4/lib.rs:534-553) */
+int orc_c4_generic_random_game(int rows, int cols, uint64_t seed, int *out_plies, int *out_has_winner);
+/* bare Othello bitboard functions for the KATs (othello/lib.rs:132-234) */
+uint64_t orc_othello_generate_moves(uint64_t player, uint64_t opponent);
+uint64_t orc_othello_get_flips(uint64_t player, uint64_t opponent, uint64_t move_mask);
+
+/* ---- Philox4x32-10 and the draw discipline (playout.c) ---- */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+uint32_t orc_draw(uint64_t seed, uint32_t leaf_id, uint32_t playout_id, uint32_t ply, uint32_t stream);
+
+/* ---- playouts (playout.c) ---- */
+typedef struct {
+    int game;
+    int policy;
+    uint64_t eps_threshold; /* floor(eps * 2^32), in [0, 2^32] */
+    uint32_t max_playout_depth; /* 0 = unlimited */
+    uint64_t seed;
+    uint32_t leaf_id_base;
+    uint32_t playouts_per_leaf;
+    uint32_t max_trace; /* u16 slots per playout in trace_out */
+} orc_batch_desc;
+
+/* One playout.  trace (nullable) receives up to max_trace action ids.  final_state nullable. */
+void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_id, uint32_t playout_id,
+                 const orc_action_stat *mast /* [2][num_actions], nullable */, uint16_t *trace, orc_playout_record *rec,
+                 orc_state *final_state);
+
+/* A whole batch, optionally multi-threaded (pthreads).  All outputs nullable except results.
+ *   amaf_out / mast_delta_out are ADDED to (caller zeroes).
+ *   amaf_out:       [n_leaves][2][num_actions]
+ *   mast_delta_out: [2][num_actions]
+ *   trace_out:      [n_leaves*k][max_trace] u16,  rec_out / final_out: [n_leaves*k] */
+int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t n_leaves, const orc_action_stat *mast,
+                      orc_leaf_result *results, orc_action_stat *amaf_out, orc_action_stat *mast_delta_out,
+                      uint16_t *trace_out, orc_playout_record *rec_out, orc_state *final_out, int n_threads);
+
+/* Random-play openings: `plies` uniformly random plies from the initial position (draws from
+ * stream 0 of leaf_id = index, playout 0); terminal-before-`plies` games are re-drawn with the
+ * next playout id.  Used to build synthetic positions for tests and the CPU baseline. */
+void orc_random_positions(int game, uint64_t seed, uint32_t plies, uint32_t n, orc_state *out);
+
+/* ---- restated reference TEST oracles (naive_ref.c) ---- */
+uint64_t orc_naive_othello_generate_moves(uint64_t player, uint64_t opponent);
+uint64_t orc_naive_othello_get_flips(uint64_t player, uint64_t opponent, uint64_t move_mask);
+int orc_naive_breakthrough_moves(const int8_t board[64], int turn, uint16_t *out);
+int orc_naive_knightthrough_moves(const int8_t board[64], int turn, uint16_t *out);
+int orc_naive_hex_winner(const uint8_t occ0[121], const uint8_t occ1[121], int last_mover);
+/* the reference's own stress sweeps, restated (mcts-tests/tests/stress.rs); return 0 on agreement,
+ * otherwise a non-zero code identifying the first mismatch */
+int orc_stress_othello(uint64_t num_games, uint64_t *games_done, uint64_t *plies_done);
+int orc_stress_through(int game, uint64_t num_games, uint64_t *goal_wins, uint64_t *stuck_games);
+
+/* ---- config-1 CPU search (search.c): UCB1 + uniform rollouts, single thread ---- */
+typedef struct {
+    uint32_t iterations;
+    double exploration_c; /* sqrt(2) default (select/ucb.rs:22-27) */
+    uint32_t expand_threshold;
+    uint64_t seed;
+} orc_search_desc;
+int orc_uct_search(int game, const orc_state *root, const orc_search_desc *d, uint16_t *best_action,
+                   uint32_t *root_visits /* [n_root_children] */, uint16_t *root_actions, uint32_t *n_children,
+                   uint64_t *total_playout_plies);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

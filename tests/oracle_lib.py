@@ -1,0 +1,221 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liboracle.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (mcts_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+LIB_PATH = ORACLE_DIR / "_build" / "liboracle.so"
+
+CONNECT4, BREAKTHROUGH, KNIGHTTHROUGH, OTHELLO, HEX11 = range(5)
+GAME_NAMES = ["connect4", "breakthrough", "knightthrough", "othello", "hex11"]
+UNIFORM, EPS_MAST, DECISIVE_WIN = range(3)
+NOT_TERMINAL, DRAW, WINNER_P0, WINNER_P1 = range(4)
+END_TERMINAL, END_TURN_LIMIT, END_NO_ACTIONS = range(3)
+OTHELLO_PASS = 64
+MAX_ACTIONS = 256
+
+STATE_DTYPE = np.dtype(
+    [("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("pad", "u1", (6,))], align=False
+)
+RESULT_DTYPE = np.dtype([("wins", "<u4", (2,)), ("draws", "<u4"), ("cutoffs", "<u4"), ("sum_depth", "<u8")])
+STAT_DTYPE = np.dtype([("visits", "<u4"), ("score", "<i4")])
+RECORD_DTYPE = np.dtype([("depth", "<u4"), ("outcome", "u1"), ("end_type", "u1"), ("pad", "u1", (2,))])
+assert STATE_DTYPE.itemsize == 40 and RESULT_DTYPE.itemsize == 24 and RECORD_DTYPE.itemsize == 8
+
+
+class BatchDesc(C.Structure):
+    _fields_ = [
+        ("game", C.c_int),
+        ("policy", C.c_int),
+        ("eps_threshold", C.c_uint64),
+        ("max_playout_depth", C.c_uint32),
+        ("seed", C.c_uint64),
+        ("leaf_id_base", C.c_uint32),
+        ("playouts_per_leaf", C.c_uint32),
+        ("max_trace", C.c_uint32),
+    ]
+
+
+class SearchDesc(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_uint32),
+        ("exploration_c", C.c_double),
+        ("expand_threshold", C.c_uint32),
+        ("seed", C.c_uint64),
+    ]
+
+
+def build(force: bool = False) -> Path:
+    """Compile the oracle with its own Makefile (gcc).  Idempotent."""
+    srcs = list(ORACLE_DIR.glob("*.c")) + list(ORACLE_DIR.glob("*.h")) + [ORACLE_DIR / "Makefile"]
+    stale = (not LIB_PATH.exists()) or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", str(ORACLE_DIR)], check=True, capture_output=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB_PATH))
+        vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+        L.orc_initial_state.argtypes = [i32, vp]
+        L.orc_num_actions.argtypes = [i32]
+        L.orc_generate_actions.argtypes = [i32, vp, vp]
+        L.orc_apply.argtypes = [i32, vp, C.c_uint16]
+        L.orc_is_terminal.argtypes = [i32, vp]
+        L.orc_winner.argtypes = [i32, vp]
+        L.orc_terminal_status.argtypes = [i32, vp]
+        L.orc_hex_flood_iterations.restype = u64
+        L.orc_c4_generic_random_game.argtypes = [i32, i32, u64, vp, vp]
+        L.orc_othello_generate_moves.argtypes = [u64, u64]
+        L.orc_othello_generate_moves.restype = u64
+        L.orc_othello_get_flips.argtypes = [u64, u64, u64]
+        L.orc_othello_get_flips.restype = u64
+        L.orc_naive_othello_generate_moves.argtypes = [u64, u64]
+        L.orc_naive_othello_generate_moves.restype = u64
+        L.orc_naive_othello_get_flips.argtypes = [u64, u64, u64]
+        L.orc_naive_othello_get_flips.restype = u64
+        L.orc_philox4x32_10.argtypes = [vp, vp, vp]
+        L.orc_draw.argtypes = [u64, u32, u32, u32, u32]
+        L.orc_draw.restype = u32
+        L.orc_playout_batch.argtypes = [C.POINTER(BatchDesc), vp, u32, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_random_positions.argtypes = [i32, u64, u32, u32, vp]
+        L.orc_stress_othello.argtypes = [u64, vp, vp]
+        L.orc_stress_through.argtypes = [i32, u64, vp, vp]
+        L.orc_naive_hex_winner.argtypes = [vp, vp, i32]
+        if hasattr(L, "orc_uct_search"):
+            L.orc_uct_search.argtypes = [i32, vp, C.POINTER(SearchDesc), vp, vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_state(board=(0, 0, 0, 0), turn=0, flag=0) -> np.ndarray:
+    s = np.zeros(1, dtype=STATE_DTYPE)
+    b = list(board) + [0] * (4 - len(board))
+    s["board"][0] = np.array(b, dtype=np.uint64)
+    s["turn"] = turn
+    s["flag"] = flag
+    return s
+
+
+def initial_state(game: int) -> np.ndarray:
+    s = np.zeros(1, dtype=STATE_DTYPE)
+    lib().orc_initial_state(game, _p(s))
+    return s
+
+
+def num_actions(game: int) -> int:
+    return lib().orc_num_actions(game)
+
+
+def generate_actions(game: int, state: np.ndarray) -> list[int]:
+    out = np.zeros(MAX_ACTIONS, dtype=np.uint16)
+    n = lib().orc_generate_actions(game, _p(state), _p(out))
+    return [int(x) for x in out[:n]]
+
+
+def apply(game: int, state: np.ndarray, action: int) -> np.ndarray:
+    s = state.copy()
+    lib().orc_apply(game, _p(s), int(action))
+    return s
+
+
+def is_terminal(game: int, state: np.ndarray) -> bool:
+    return bool(lib().orc_is_terminal(game, _p(state)))
+
+
+def winner(game: int, state: np.ndarray) -> int:
+    return lib().orc_winner(game, _p(state))
+
+
+def terminal_status(game: int, state: np.ndarray) -> int:
+    return lib().orc_terminal_status(game, _p(state))
+
+
+def philox(ctr, key) -> list[int]:
+    c = np.array(ctr, dtype=np.uint32)
+    k = np.array(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(_p(c), _p(k), _p(o))
+    return [int(x) for x in o]
+
+
+def draw(seed, leaf_id, playout_id, ply, stream=0) -> int:
+    return lib().orc_draw(seed, leaf_id, playout_id, ply, stream)
+
+
+def eps_threshold(eps: float) -> int:
+    return max(0, min(1 << 32, int(eps * 4294967296.0)))
+
+
+def playout_batch(
+    game,
+    leaves: np.ndarray,
+    k: int,
+    *,
+    policy=UNIFORM,
+    eps=0.1,
+    max_depth=0,
+    seed=0,
+    leaf_id_base=0,
+    mast: np.ndarray | None = None,
+    want_amaf=False,
+    want_mast_delta=False,
+    want_trace=False,
+    max_trace=0,
+    want_final=False,
+    threads=1,
+):
+    """Runs n_leaves*k playouts.  Returns a dict with results (+ optional amaf / mast_delta / trace /
+    records / final)."""
+    leaves = np.ascontiguousarray(leaves, dtype=STATE_DTYPE)
+    n = len(leaves)
+    na = num_actions(game)
+    d = BatchDesc(game, policy, eps_threshold(eps), max_depth, seed, leaf_id_base, k, max_trace if want_trace else 0)
+    results = np.zeros(n, dtype=RESULT_DTYPE)
+    amaf = np.zeros((n, 2, na), dtype=STAT_DTYPE) if want_amaf else None
+    delta = np.zeros((2, na), dtype=STAT_DTYPE) if want_mast_delta else None
+    trace = np.zeros((n * k, max_trace), dtype=np.uint16) if want_trace else None
+    rec = np.zeros(n * k, dtype=RECORD_DTYPE) if (want_trace or want_final) else None
+    final = np.zeros(n * k, dtype=STATE_DTYPE) if want_final else None
+    if mast is not None:
+        mast = np.ascontiguousarray(mast, dtype=STAT_DTYPE)
+        assert mast.shape == (2, na)
+    rc = lib().orc_playout_batch(
+        C.byref(d), _p(leaves), n, _p(mast), _p(results), _p(amaf), _p(delta), _p(trace), _p(rec), _p(final), threads
+    )
+    if rc != 0:
+        raise RuntimeError(f"orc_playout_batch failed: {rc}")
+    return {"results": results, "amaf": amaf, "mast_delta": delta, "trace": trace, "records": rec, "final": final}
+
+
+def random_positions(game: int, seed: int, plies: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=STATE_DTYPE)
+    lib().orc_random_positions(game, seed, plies, n, _p(out))
+    return out
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
