@@ -1,0 +1,211 @@
+/*
+ * mcts_rollout.h -- C ABI of the B200-native rollout engine (libmcts_b200.so).
+ *
+ * This is the drop-in boundary for the SIMULATION PHASE of thomasmarsh/mcts.  The reference has no
+ * FFI of its own: its plug-in surface for this path is the Rust trait
+ *     SimulateStrategy<G>::playout(state, max_playout_depth, &TreeStats, prev_action, rng) -> Trial<G>
+ *         (mcts/src/strategies/mcts/simulate.rs:48-155)
+ * called from simulate_step (mcts/src/strategies/mcts/search/shared.rs:763-778) by
+ * TreeSearch::simulate / simulate_many (search/core.rs:201-258) and the tree-parallel workers
+ * (search/parallel.rs:237-249).  The entry points below are what a Rust
+ * `GpuRollout<G>: SimulateStrategy<G>` plus a batched leaf-gather driver bind (the `extern "C"`
+ * block is shown in INTEGRATION.md).  Plain C structs, caller-owned buffers, integer return codes,
+ * nothing unwinds across the boundary, no torch types.
+ *
+ * Semantics of one batch: for every leaf i in [0, n_leaves) run `playouts_per_leaf` playouts of the
+ * named game and policy from `leaves[i]`, exactly as the reference's playout loop would
+ * (simulate.rs:84-143 / 173-216), with every random choice drawn from the counter-based Philox4x32-10
+ * stream keyed by (seed, leaf_id_base + i, playout index, ply) -- see DESIGN.md "Draw discipline".
+ * What comes back is the AGGREGATE the reference's backprop would have accumulated from those
+ * Trials (backprop.rs:644-964, node.rs:673-681): per leaf {wins[2], draws, cutoffs, sum_depth}; optionally
+ * the per-leaf AMAF/GRAVE occurrence table (backprop.rs:565-640) and the batch-wide MAST (GLOBAL) delta
+ * (backprop.rs:857-870); optionally, for parity checking, every playout's move trace, outcome record and
+ * final state.
+ *
+ * Threading: one mr_ctx per driving host thread; calls on one ctx are not thread-safe.
+ * There is NO CPU fallback: every entry point fails with MR_ERR_NO_DEVICE / MR_ERR_CUDA when no
+ * usable sm_100 device is present.
+ */
+#ifndef MCTS_ROLLOUT_H
+#define MCTS_ROLLOUT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_ABI_VERSION 1
+#define MR_NUM_SLOTS 2 /* double buffering: submit batch N+1 while batch N runs */
+
+typedef struct mr_ctx mr_ctx;
+
+enum mr_status {
+    MR_OK = 0,
+    MR_ERR_INVALID = 1,     /* bad argument / unsupported combination; mr_last_error() says which */
+    MR_ERR_CUDA = 2,        /* a CUDA runtime call failed */
+    MR_ERR_NO_DEVICE = 3,   /* no CUDA device, or not compute capability 10.x */
+    MR_ERR_BUSY = 4,        /* slot already has a batch in flight */
+    MR_ERR_UNSUPPORTED = 5, /* game/policy/flag combination not built */
+    MR_ERR_COMM = 6         /* multi-process communicator failure */
+};
+
+/* Games on the path.  Leaf layout per game is documented at mr_leaf. */
+enum mr_game {
+    MR_CONNECT4 = 0,      /* games/connect4/src/lib.rs      Connect4<6,7> */
+    MR_BREAKTHROUGH = 1,  /* games/breakthrough/src/lib.rs  Breakthrough<8,8> */
+    MR_KNIGHTTHROUGH = 2, /* games/knightthrough/src/lib.rs Knightthrough<8,8> */
+    MR_OTHELLO = 3,       /* games/othello/src/lib.rs */
+    MR_HEX11 = 4,         /* games/hex-gen/src/lib.rs       Hex<11,2> */
+    MR_NUM_GAMES = 5
+};
+
+/* Simulation policies (the SimulateStrategy implementors in scope). */
+enum mr_policy {
+    MR_UNIFORM = 0,     /* simulate.rs:157-216  Uniform */
+    MR_EPS_MAST = 1,    /* simulate.rs:485-570 + 819-848  EpsilonGreedy<G, Mast> */
+    MR_DECISIVE_WIN = 2 /* simulate.rs:573-760  DecisiveMove<G, Uniform>, mode Win */
+};
+
+enum mr_flags {
+    MR_WANT_AMAF = 1,        /* per-leaf AMAF/GRAVE occurrence table (Hex 11x11, Connect4, Othello) */
+    MR_WANT_MAST_DELTA = 2,  /* batch-wide MAST (GLOBAL) table delta */
+    MR_WANT_TRACE = 4,       /* parity/debug: per-playout move trace + record */
+    MR_WANT_FINAL_STATE = 8  /* parity/debug: per-playout final state */
+};
+
+/* TerminalStatus as utilities see it (mcts/src/game.rs:117-141). */
+enum mr_outcome { MR_NOT_TERMINAL = 0, MR_DRAW = 1, MR_WINNER_P0 = 2, MR_WINNER_P1 = 3 };
+/* EndType (simulate.rs:15-20) plus the "no actions but not terminal" ending (simulate.rs:112-116). */
+enum mr_end_type { MR_END_TERMINAL = 0, MR_END_TURN_LIMIT = 1, MR_END_NO_ACTIONS = 2 };
+
+/*
+ * One leaf state: a 40-byte POD record, the playout-relevant fields of the reference's G::S.
+ *   Connect4 / Breakthrough / Knightthrough / Othello:
+ *       board[0] = black, board[1] = white, in the reference's row-major layout
+ *       (bit idx = row*cols + col, row 0 = south/bottom; bitboard/src/board.rs:76-104)
+ *   Hex 11x11: board[0..1] = occupied[P0] words (low word first), board[2..3] = occupied[P1] words
+ *   turn: player to move (0 = Black / P0, 1 = White / P1)
+ *   flag: Connect4 / Breakthrough / Knightthrough `winner`; Othello `last_pass`; Hex unused
+ * Zobrist hashes carried by the reference structs are tree-side state and are not part of the record.
+ */
+typedef struct {
+    uint64_t board[4];
+    uint8_t turn;
+    uint8_t flag;
+    uint8_t pad[6];
+} mr_leaf;
+
+/* Aggregate of one leaf's playouts; what k calls of ChildArray::update / NodeStats::update need:
+ *   num_visits += k; score[p] += wins[p] - (k - draws - wins[p]); sum_sq[p] += k - draws   (node.rs:295-302, 673-681)
+ *   accum_depth += sum_depth (+ k * (stack.len() - 1) added by the host; shared.rs:814-818) */
+typedef struct {
+    uint32_t wins[2];
+    uint32_t draws;   /* every zero-utility ending: terminal draw, depth cutoff, no-actions */
+    uint32_t cutoffs; /* the subset of draws that ended by max_playout_depth (EndType::TurnLimit) */
+    uint64_t sum_depth;
+} mr_leaf_result;
+
+/* node.rs:51-55 ActionStats; score is the integer sum of +1/0/-1 utilities */
+typedef struct {
+    uint32_t visits;
+    int32_t score;
+} mr_action_stat;
+
+typedef struct {
+    uint32_t depth;
+    uint8_t outcome;  /* mr_outcome; non-terminal endings are reported as MR_DRAW */
+    uint8_t end_type; /* mr_end_type */
+    uint8_t pad[2];
+} mr_playout_record;
+
+typedef struct {
+    uint32_t game;              /* mr_game */
+    uint32_t policy;            /* mr_policy */
+    uint32_t n_leaves;
+    uint32_t playouts_per_leaf; /* k */
+    uint32_t max_playout_depth; /* SearchConfig.max_playout_depth (config.rs:440); 0 = unlimited */
+    uint32_t flags;             /* mr_flags */
+    uint64_t seed;              /* Philox key */
+    uint32_t leaf_id_base;      /* Philox counter word 0 of leaf i is leaf_id_base + i */
+    uint32_t max_trace;         /* u16 slots per playout in trace_out (MR_WANT_TRACE) */
+    double epsilon;             /* EpsilonGreedy.epsilon (simulate.rs:525 default 0.1); MR_EPS_MAST only */
+} mr_batch_desc;
+
+/* Dense action-id space of a game (the index into MAST / AMAF tables):
+ *   Connect4 7 (column); Othello 65 (square, 64 = PASS); Hex 121 (cell);
+ *   Breakthrough / Knightthrough 4096 (src*64 + dst).
+ * Trace entries use the compact u16 action code: (src << 8) | dst for Breakthrough / Knightthrough,
+ * the action id itself for the other games. */
+int mr_num_actions(int game);
+int mr_abi_version(void);
+
+/* Creates a context driving `n_devices` GPUs of this process (one stream pair, pinned staging and
+ * device buffers per GPU; batches are sharded across them by playout range with no data-path
+ * collective).  device_ids == NULL means devices 0..n_devices-1. */
+int mr_init(const int *device_ids, int n_devices, mr_ctx **out);
+void mr_destroy(mr_ctx *ctx);
+const char *mr_last_error(const mr_ctx *ctx); /* valid until the next call on ctx; ctx may be NULL */
+int mr_num_devices(const mr_ctx *ctx);
+
+/* Asynchronous batch: copies `leaves` (and the MAST snapshot, mast_in = [2][mr_num_actions], required
+ * for MR_EPS_MAST) into pinned staging before returning, enqueues H2D + kernels + D2H on the slot's
+ * streams.  Replaces one `simulate_many` fan-out (search/core.rs:218-258) per leaf of the batch. */
+int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *leaves,
+              const mr_action_stat *mast_in);
+
+/* Blocks until the slot's batch is done and copies the results out.  Every pointer except `out` is
+ * nullable and must be non-NULL only if the matching flag was set at submit:
+ *   out            [n_leaves]
+ *   amaf_out       [n_leaves][2][mr_num_actions]   (MR_WANT_AMAF; playout-trace occurrences only, the
+ *                                                   tree-path suffix is added by the host, backprop.rs:833-854)
+ *   mast_delta_out [2][mr_num_actions]             (MR_WANT_MAST_DELTA)
+ *   trace_out      [n_leaves*k][max_trace] u16, rec_out [n_leaves*k]   (MR_WANT_TRACE)
+ *   final_out      [n_leaves*k]                    (MR_WANT_FINAL_STATE) */
+int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out, mr_action_stat *mast_delta_out,
+            uint16_t *trace_out, mr_playout_record *rec_out, mr_leaf *final_out);
+
+/* mr_submit + mr_wait on slot 0. */
+int mr_playout_batch(mr_ctx *ctx, const mr_batch_desc *desc, const mr_leaf *leaves, const mr_action_stat *mast_in,
+                     mr_leaf_result *out, mr_action_stat *amaf_out, mr_action_stat *mast_delta_out,
+                     uint16_t *trace_out, mr_playout_record *rec_out, mr_leaf *final_out);
+
+/* Device-resident variant for hosts that keep leaves in HBM (and for kernel-only timing): the leaf and
+ * result arrays are caller-owned DEVICE pointers on device `device_index` of the ctx, the launch goes to
+ * `stream` (a cudaStream_t passed as void*, NULL = the ctx's own stream) and nothing is copied.
+ * d_results must be zeroed by the caller (results are accumulated with atomics).  d_amaf / d_mast_delta
+ * are nullable device pointers matching desc->flags.  The MAST snapshot is the one last uploaded with
+ * mr_set_mast. */
+int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, const void *d_leaves, void *d_results,
+                     void *d_amaf, void *d_mast_delta, void *stream);
+int mr_set_mast(mr_ctx *ctx, int game, const mr_action_stat *mast_in);
+
+/* Kernel time of the last completed batch on `slot` (max over the ctx's devices), measured with CUDA
+ * events on the launching stream; and the number of rollout-kernel launches the ctx has issued. */
+int mr_last_kernel_ms(mr_ctx *ctx, int slot, float *ms);
+uint64_t mr_kernel_launches(const mr_ctx *ctx);
+
+/* Sums `n` int32 values element-wise across the devices/ranks of the search (the per-root-child
+ * visit/score arrays of root-parallel search, search/parallel.rs:94-105).  Within one process it is a
+ * host-side sum over the ctx's per-device partial arrays: bufs[d] points at device d's `n` values and
+ * every bufs[d] receives the total.  Across processes use mr_comm_*. */
+int mr_allreduce_root(mr_ctx *ctx, int32_t *const *bufs, int n_bufs, size_t n);
+
+/* Multi-process (one rank per GPU) root-statistics merge over NCCL.  The unique id is created on rank 0
+ * with mr_comm_unique_id, broadcast by the host's own means, and passed to every rank's mr_comm_init.
+ * mr_comm_allreduce_i32 sums a DEVICE buffer in place on the ctx's stream (ncclAllReduce, ncclSum). */
+#define MR_COMM_ID_BYTES 128
+int mr_comm_unique_id(uint8_t id[MR_COMM_ID_BYTES]);
+int mr_comm_init(mr_ctx *ctx, const uint8_t id[MR_COMM_ID_BYTES], int rank, int world_size);
+int mr_comm_allreduce_i32(mr_ctx *ctx, void *d_buf, size_t n, void *stream);
+
+/* Integer-issue micro-benchmark used as the roofline denominator (DESIGN.md "Roofline"): runs a
+ * dependent-chain kernel of `kind` (0 = LOP3, 1 = IADD3, 2 = SHF, 3 = IMAD, 4 = POPC, 5 = LOP3+IMAD mix)
+ * on every SM and returns thread-level operations per second. */
+int mr_measure_int_peak(mr_ctx *ctx, int device_index, int kind, double *ops_per_second, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCTS_ROLLOUT_H */

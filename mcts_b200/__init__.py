@@ -1,0 +1,28 @@
+"""mcts_b200 -- B200-native rollout engine: a drop-in for the simulation phase of thomasmarsh/mcts.
+
+The compute path is hand-written sm_100a CUDA behind the C ABI in include/mcts_rollout.h
+(libmcts_b200.so, built in-tree by mcts_b200.build).  There is no CPU fallback.
+"""
+from ._lib import LEAF_DTYPE, RECORD_DTYPE, RESULT_DTYPE, STAT_DTYPE, EXPORTS, RolloutError, load
+from .rollout import (
+    BatchResult,
+    DecisiveMoveWin,
+    EndType,
+    EpsilonGreedyMast,
+    Game,
+    GpuRollout,
+    MastTable,
+    Outcome,
+    Policy,
+    Trial,
+    Uniform,
+    initial_state,
+    make_leaf,
+    num_actions,
+)
+
+__all__ = [
+    "BatchResult", "DecisiveMoveWin", "EndType", "EpsilonGreedyMast", "Game", "GpuRollout", "MastTable", "Outcome",
+    "Policy", "Trial", "Uniform", "initial_state", "make_leaf", "num_actions", "LEAF_DTYPE", "RECORD_DTYPE",
+    "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load",
+]

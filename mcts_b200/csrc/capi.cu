@@ -1,0 +1,761 @@
+// capi.cu -- host side of the C ABI declared in include/mcts_rollout.h.
+//
+// One mr_ctx drives one or more GPUs of this process.  Per GPU: one stream, one task-queue counter per
+// slot, grow-on-demand device buffers and pinned host staging.  A batch is cut into tasks
+// (leaf, chunk-of-playouts); the task range is split evenly over the ctx's GPUs (no data-path
+// collective: every playout is independent given (leaf state, Philox key)); per-leaf results are summed
+// on the host.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "int_peak.cuh"
+#include "rollout_kernel.cuh"
+
+using namespace mr;
+
+namespace {
+
+thread_local std::string g_global_error;
+
+struct GameInfo {
+    int num_actions;
+    uint32_t depth_bound; // longest possible playout; 0 = unbounded
+};
+const GameInfo kGames[MR_NUM_GAMES] = {
+    {7, 42},    // Connect4: 42 cells
+    {4096, 256}, // Breakthrough: pawns only advance: <= 2 * 16 * 7 = 224 plies
+    {4096, 0},   // Knightthrough: knights also jump backwards: unbounded
+    {65, 128},   // Othello: 60 placements + at most one pass between placements
+    {121, 121},  // Hex 11x11
+};
+
+template <class T>
+struct DevBuf {
+    T *d = nullptr;
+    T *h = nullptr; // pinned
+    size_t cap = 0;
+    cudaError_t reserve(size_t n, bool want_host) {
+        if (n <= cap && (!want_host || h)) return cudaSuccess;
+        size_t ncap = std::max(n, cap);
+        if (n > cap) {
+            if (d) cudaFree(d);
+            d = nullptr;
+            cudaError_t e = cudaMalloc(&d, ncap * sizeof(T));
+            if (e != cudaSuccess) return e;
+        }
+        if (want_host && (n > cap || !h)) {
+            if (h) cudaFreeHost(h);
+            h = nullptr;
+            cudaError_t e = cudaMallocHost(&h, ncap * sizeof(T));
+            if (e != cudaSuccess) return e;
+        }
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (d) cudaFree(d);
+        if (h) cudaFreeHost(h);
+        d = nullptr;
+        h = nullptr;
+        cap = 0;
+    }
+};
+
+struct SlotDev {
+    DevBuf<mr_leaf> leaves;
+    DevBuf<mr_leaf_result> results;
+    DevBuf<mr_action_stat> amaf;
+    DevBuf<mr_action_stat> mast_delta;
+    DevBuf<uint16_t> trace;
+    DevBuf<mr_playout_record> rec;
+    DevBuf<mr_leaf> final_state;
+    uint32_t *d_counter = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // what this device covers for the batch in flight
+    uint32_t task_begin = 0, task_end = 0;
+    uint64_t g_begin = 0, g_end = 0; // global playout index range
+};
+
+struct Device {
+    int id = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    SlotDev slot[MR_NUM_SLOTS];
+    DevBuf<uint16_t> mast_rank; // [2][NA]
+    int mast_game = -1;
+    DevBuf<uint16_t> scratch;
+    uint32_t *d_counter_ext = nullptr; // task counter for mr_launch_device
+};
+
+struct SlotState {
+    bool busy = false;
+    mr_batch_desc desc{};
+    uint32_t chunk = 0, chunks_per_leaf = 0, n_tasks = 0;
+    float kernel_ms = 0.f;
+};
+
+typedef void (*kernel_fn)(const KernelParams);
+
+} // namespace
+
+struct mr_ctx {
+    std::vector<Device> dev;
+    SlotState slot[MR_NUM_SLOTS];
+    std::string error;
+    uint64_t launches = 0;
+    // NCCL (loaded lazily with dlopen; see mr_comm_*)
+    void *nccl_lib = nullptr;
+    void *nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+};
+
+namespace {
+
+int fail(mr_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    g_global_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(ctx, MR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- kernel table: (game, policy, flag variant) -> instantiation ----
+// flag variants: 0 = none, 1 = AMAF, 2 = MAST delta, 3 = AMAF|MAST, 4 = everything (debug / parity outputs)
+constexpr int kFlagVariant[5] = {0, MR_WANT_AMAF, MR_WANT_MAST_DELTA, MR_WANT_AMAF | MR_WANT_MAST_DELTA,
+                                 MR_WANT_AMAF | MR_WANT_MAST_DELTA | MR_WANT_TRACE | MR_WANT_FINAL_STATE};
+
+int flag_variant(uint32_t flags) {
+    if (flags & (MR_WANT_TRACE | MR_WANT_FINAL_STATE)) return 4;
+    return (int)(flags & 3u);
+}
+
+template <class G, int POLICY>
+kernel_fn pick_variant(int v) {
+    switch (v) {
+    case 0: return rollout_kernel<G, POLICY, kFlagVariant[0]>;
+    case 1: return rollout_kernel<G, POLICY, kFlagVariant[1]>;
+    case 2: return rollout_kernel<G, POLICY, kFlagVariant[2]>;
+    case 3: return rollout_kernel<G, POLICY, kFlagVariant[3]>;
+    default: return rollout_kernel<G, POLICY, kFlagVariant[4]>;
+    }
+}
+
+kernel_fn pick_kernel(int game, int policy, int v) {
+    switch (game) {
+    case MR_CONNECT4:
+        if (policy == MR_UNIFORM) return pick_variant<Connect4, MR_UNIFORM>(v);
+        if (policy == MR_DECISIVE_WIN) return pick_variant<Connect4, MR_DECISIVE_WIN>(v);
+        return nullptr;
+    case MR_BREAKTHROUGH:
+        if (policy == MR_UNIFORM) return pick_variant<Breakthrough, MR_UNIFORM>(v);
+        if (policy == MR_EPS_MAST) return pick_variant<Breakthrough, MR_EPS_MAST>(v);
+        return nullptr;
+    case MR_KNIGHTTHROUGH:
+        if (policy == MR_UNIFORM) return pick_variant<Knightthrough, MR_UNIFORM>(v);
+        if (policy == MR_EPS_MAST) return pick_variant<Knightthrough, MR_EPS_MAST>(v);
+        return nullptr;
+    case MR_OTHELLO:
+        // DecisiveMove<Win> provably never changes an Othello pick, so it shares the kernel
+        if (policy == MR_UNIFORM || policy == MR_DECISIVE_WIN) return pick_variant<Othello, MR_UNIFORM>(v);
+        return nullptr;
+    case MR_HEX11:
+        if (policy == MR_UNIFORM) return pick_variant<Hex11, MR_UNIFORM>(v);
+        return nullptr;
+    }
+    return nullptr;
+}
+
+// ---- MAST snapshot -> order-preserving dense ranks ----
+// Mast::select_move compares unigram scores score/visits as f64, unvisited => 1.0 (simulate.rs:806-848).
+// score is an integer sum of +-1 utilities, so for visits < 2^26 the f64 comparison equals the exact
+// rational comparison score_a * visits_b <=> score_b * visits_a.  Ranks keep order and ties exactly.
+struct Rational {
+    int64_t num;
+    int64_t den;
+};
+inline bool rat_less(const Rational &a, const Rational &b) { return (__int128)a.num * b.den < (__int128)b.num * a.den; }
+inline bool rat_eq(const Rational &a, const Rational &b) { return (__int128)a.num * b.den == (__int128)b.num * a.den; }
+
+int compute_mast_ranks(mr_ctx *ctx, int na, const mr_action_stat *mast, uint16_t *out) {
+    for (int pl = 0; pl < 2; ++pl) {
+        const mr_action_stat *tab = mast + (size_t)pl * na;
+        std::vector<Rational> vals;
+        vals.push_back({1, 1});
+        for (int a = 0; a < na; ++a) {
+            if (tab[a].visits >= (1u << 26))
+                return fail(ctx, MR_ERR_INVALID, "MAST visits %u >= 2^26: exact score comparison not guaranteed", tab[a].visits);
+            if (tab[a].visits > 0) vals.push_back({(int64_t)tab[a].score, (int64_t)tab[a].visits});
+        }
+        std::sort(vals.begin(), vals.end(), rat_less);
+        std::vector<Rational> uniq;
+        for (const Rational &v : vals)
+            if (uniq.empty() || !rat_eq(uniq.back(), v)) uniq.push_back(v);
+        if (uniq.size() > 65535) return fail(ctx, MR_ERR_INVALID, "too many distinct MAST values");
+        auto rank_of = [&](Rational v) {
+            return (uint16_t)(std::lower_bound(uniq.begin(), uniq.end(), v, rat_less) - uniq.begin());
+        };
+        const uint16_t unvisited = rank_of({1, 1});
+        for (int a = 0; a < na; ++a)
+            out[(size_t)pl * na + a] =
+                tab[a].visits > 0 ? rank_of({(int64_t)tab[a].score, (int64_t)tab[a].visits}) : unvisited;
+    }
+    return MR_OK;
+}
+
+int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_out, uint32_t *trace_cap_out) {
+    if (!d) return fail(ctx, MR_ERR_INVALID, "null batch descriptor");
+    if (d->game >= MR_NUM_GAMES) return fail(ctx, MR_ERR_INVALID, "unknown game %u", d->game);
+    if (d->n_leaves == 0 || d->playouts_per_leaf == 0)
+        return fail(ctx, MR_ERR_INVALID, "empty batch (n_leaves=%u, playouts_per_leaf=%u)", d->n_leaves, d->playouts_per_leaf);
+    if (d->flags & ~15u) return fail(ctx, MR_ERR_INVALID, "unknown flags 0x%x", d->flags);
+    kernel_fn fn = pick_kernel((int)d->game, (int)d->policy, flag_variant(d->flags));
+    if (!fn) return fail(ctx, MR_ERR_UNSUPPORTED, "policy %u is not built for game %u", d->policy, d->game);
+    if (d->policy == MR_EPS_MAST) {
+        if (!has_mast) return fail(ctx, MR_ERR_INVALID, "MR_EPS_MAST needs a MAST snapshot (mast_in / mr_set_mast)");
+        if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
+    }
+    if ((d->flags & MR_WANT_TRACE) && d->max_trace == 0) return fail(ctx, MR_ERR_INVALID, "MR_WANT_TRACE needs max_trace > 0");
+    uint32_t cap = 0;
+    if (d->flags & (MR_WANT_AMAF | MR_WANT_MAST_DELTA)) {
+        const uint32_t bound = kGames[d->game].depth_bound;
+        cap = d->max_playout_depth ? d->max_playout_depth : bound;
+        if (bound && cap > bound) cap = bound;
+        if (cap == 0)
+            return fail(ctx, MR_ERR_INVALID, "AMAF / MAST-delta need a bounded playout: set max_playout_depth for game %u", d->game);
+        if (cap > 4096) return fail(ctx, MR_ERR_INVALID, "max_playout_depth %u too large for AMAF / MAST-delta (limit 4096)", cap);
+    }
+    if ((uint64_t)d->n_leaves * d->playouts_per_leaf > (1ull << 40)) return fail(ctx, MR_ERR_INVALID, "batch too large");
+    *fn_out = fn;
+    *trace_cap_out = cap;
+    return MR_OK;
+}
+
+struct LaunchPlan {
+    uint32_t chunk, chunks_per_leaf, n_tasks;
+    int blocks_per_sm;
+};
+
+int plan_launch(mr_ctx *ctx, const Device &dv, kernel_fn fn, const mr_batch_desc *d, int n_devices, LaunchPlan *lp) {
+    int bps = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, THREADS_PER_BLOCK, 0));
+    if (bps < 1) return fail(ctx, MR_ERR_CUDA, "kernel does not fit on an SM");
+    const uint64_t resident_warps = (uint64_t)dv.num_sms * bps * WARPS_PER_BLOCK * n_devices;
+    const uint64_t total = (uint64_t)d->n_leaves * d->playouts_per_leaf;
+    // enough tasks for ~8 per resident warp, 32..1024 playouts each, never more than one leaf's worth
+    uint64_t want = total / (resident_warps * 8);
+    uint32_t chunk = 32;
+    while (chunk < 1024 && (uint64_t)chunk * 2 <= want) chunk *= 2;
+    if (chunk > d->playouts_per_leaf) chunk = d->playouts_per_leaf;
+    const uint64_t cpl = (d->playouts_per_leaf + chunk - 1) / chunk;
+    const uint64_t n_tasks = cpl * d->n_leaves;
+    if (n_tasks >= 0xffff0000ull) return fail(ctx, MR_ERR_INVALID, "too many tasks");
+    lp->chunk = chunk;
+    lp->chunks_per_leaf = (uint32_t)cpl;
+    lp->n_tasks = (uint32_t)n_tasks;
+    lp->blocks_per_sm = bps;
+    return MR_OK;
+}
+
+void fill_params(KernelParams &kp, const mr_batch_desc *d, const LaunchPlan &lp, uint32_t trace_cap) {
+    memset(&kp, 0, sizeof kp);
+    kp.n_leaves = d->n_leaves;
+    kp.k = d->playouts_per_leaf;
+    kp.chunk = lp.chunk;
+    kp.chunks_per_leaf = lp.chunks_per_leaf;
+    kp.max_depth = d->max_playout_depth ? d->max_playout_depth : 0xffffffffu;
+    kp.seed_lo = (uint32_t)d->seed;
+    kp.seed_hi = (uint32_t)(d->seed >> 32);
+    kp.leaf_id_base = d->leaf_id_base;
+    // explore iff x1 < floor(eps * 2^32)
+    double t = d->epsilon * 4294967296.0;
+    uint64_t thr = t <= 0.0 ? 0 : (t >= 4294967296.0 ? (1ull << 32) : (uint64_t)t);
+    kp.eps_enable = thr > 0;
+    kp.eps_thr_m1 = thr > 0 ? (uint32_t)(thr - 1) : 0;
+    kp.max_trace = d->max_trace;
+    kp.trace_cap = trace_cap;
+}
+
+int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const LaunchPlan &lp, cudaStream_t stream,
+              uint32_t *d_counter) {
+    const uint32_t my_tasks = kp.task_end - kp.task_begin;
+    if (my_tasks == 0) return MR_OK;
+    uint32_t blocks = (uint32_t)dv.num_sms * lp.blocks_per_sm;
+    const uint32_t need_blocks = (my_tasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    if (blocks > need_blocks) blocks = need_blocks;
+    if (kp.trace_cap) {
+        const size_t need = (size_t)blocks * WARPS_PER_BLOCK * kp.trace_cap * 32u;
+        CUDA_TRY(ctx, dv.scratch.reserve(need, false));
+        kp.trace_scratch = dv.scratch.d;
+    }
+    kp.task_counter = d_counter;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), stream));
+    fn<<<blocks, THREADS_PER_BLOCK, 0, stream>>>(kp);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return MR_OK;
+}
+
+int upload_mast(mr_ctx *ctx, Device &dv, int game, const mr_action_stat *mast_in) {
+    const int na = kGames[game].num_actions;
+    CUDA_TRY(ctx, dv.mast_rank.reserve((size_t)2 * na, true));
+    int rc = compute_mast_ranks(ctx, na, mast_in, dv.mast_rank.h);
+    if (rc != MR_OK) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dv.mast_rank.d, dv.mast_rank.h, sizeof(uint16_t) * 2 * na, cudaMemcpyHostToDevice, dv.stream));
+    dv.mast_game = game;
+    return MR_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int mr_abi_version(void) { return MR_ABI_VERSION; }
+
+int mr_num_actions(int game) {
+    if (game < 0 || game >= MR_NUM_GAMES) return 0;
+    return kGames[game].num_actions;
+}
+
+const char *mr_last_error(const mr_ctx *ctx) { return ctx ? ctx->error.c_str() : g_global_error.c_str(); }
+
+int mr_init(const int *device_ids, int n_devices, mr_ctx **out) {
+    if (!out) return fail(nullptr, MR_ERR_INVALID, "mr_init: out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, MR_ERR_NO_DEVICE, "no CUDA device: %s (this engine has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (n_devices <= 0) n_devices = 1;
+    if (n_devices > count && !device_ids)
+        return fail(nullptr, MR_ERR_NO_DEVICE, "%d devices requested, %d present", n_devices, count);
+    mr_ctx *ctx = new mr_ctx();
+    ctx->dev.resize((size_t)n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        Device &dv = ctx->dev[(size_t)i];
+        dv.id = device_ids ? device_ids[i] : i;
+        cudaDeviceProp prop;
+        if (dv.id < 0 || dv.id >= count || cudaGetDeviceProperties(&prop, dv.id) != cudaSuccess) {
+            int rc = fail(nullptr, MR_ERR_NO_DEVICE, "device %d not usable", dv.id);
+            delete ctx;
+            return rc;
+        }
+        if (prop.major != 10) {
+            int rc = fail(nullptr, MR_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dv.id,
+                          prop.major, prop.minor);
+            delete ctx;
+            return rc;
+        }
+        dv.num_sms = prop.multiProcessorCount;
+        cudaSetDevice(dv.id);
+        if (cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&dv.d_counter_ext, sizeof(uint32_t)) != cudaSuccess) {
+            int rc = fail(nullptr, MR_ERR_CUDA, "stream/counter creation failed on device %d", dv.id);
+            mr_destroy(ctx);
+            return rc;
+        }
+        for (int s = 0; s < MR_NUM_SLOTS; ++s) {
+            SlotDev &sd = dv.slot[s];
+            if (cudaMalloc(&sd.d_counter, sizeof(uint32_t)) != cudaSuccess || cudaEventCreate(&sd.ev_begin) != cudaSuccess ||
+                cudaEventCreate(&sd.ev_end) != cudaSuccess) {
+                int rc = fail(nullptr, MR_ERR_CUDA, "slot setup failed on device %d", dv.id);
+                mr_destroy(ctx);
+                return rc;
+            }
+        }
+    }
+    *out = ctx;
+    return MR_OK;
+}
+
+void mr_destroy(mr_ctx *ctx) {
+    if (!ctx) return;
+    for (Device &dv : ctx->dev) {
+        cudaSetDevice(dv.id);
+        if (dv.stream) cudaStreamSynchronize(dv.stream);
+        for (int s = 0; s < MR_NUM_SLOTS; ++s) {
+            SlotDev &sd = dv.slot[s];
+            sd.leaves.release();
+            sd.results.release();
+            sd.amaf.release();
+            sd.mast_delta.release();
+            sd.trace.release();
+            sd.rec.release();
+            sd.final_state.release();
+            if (sd.d_counter) cudaFree(sd.d_counter);
+            if (sd.ev_begin) cudaEventDestroy(sd.ev_begin);
+            if (sd.ev_end) cudaEventDestroy(sd.ev_end);
+        }
+        dv.mast_rank.release();
+        dv.scratch.release();
+        if (dv.d_counter_ext) cudaFree(dv.d_counter_ext);
+        if (dv.stream) cudaStreamDestroy(dv.stream);
+    }
+    if (ctx->nccl_comm && ctx->nccl_lib) {
+        typedef int (*destroy_fn)(void *);
+        destroy_fn f = (destroy_fn)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+        if (f) f(ctx->nccl_comm);
+    }
+    delete ctx;
+}
+
+int mr_num_devices(const mr_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0; }
+
+int mr_set_mast(mr_ctx *ctx, int game, const mr_action_stat *mast_in) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (game < 0 || game >= MR_NUM_GAMES || !mast_in) return fail(ctx, MR_ERR_INVALID, "mr_set_mast: bad arguments");
+    for (Device &dv : ctx->dev) {
+        CUDA_TRY(ctx, cudaSetDevice(dv.id));
+        int rc = upload_mast(ctx, dv, game, mast_in);
+        if (rc != MR_OK) return rc;
+        CUDA_TRY(ctx, cudaStreamSynchronize(dv.stream));
+    }
+    return MR_OK;
+}
+
+int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *leaves, const mr_action_stat *mast_in) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (slot < 0 || slot >= MR_NUM_SLOTS) return fail(ctx, MR_ERR_INVALID, "slot %d out of range", slot);
+    SlotState &ss = ctx->slot[slot];
+    if (ss.busy) return fail(ctx, MR_ERR_BUSY, "slot %d already has a batch in flight", slot);
+    if (!leaves) return fail(ctx, MR_ERR_INVALID, "null leaves");
+    kernel_fn fn = nullptr;
+    uint32_t trace_cap = 0;
+    int rc = validate(ctx, desc, mast_in != nullptr, &fn, &trace_cap);
+    if (rc != MR_OK) return rc;
+    const int nd = (int)ctx->dev.size();
+    LaunchPlan lp;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->dev[0].id));
+    rc = plan_launch(ctx, ctx->dev[0], fn, desc, nd, &lp);
+    if (rc != MR_OK) return rc;
+    const int na = kGames[desc->game].num_actions;
+    const uint32_t n = desc->n_leaves, k = desc->playouts_per_leaf;
+    const uint64_t total = (uint64_t)n * k;
+
+    for (int di = 0; di < nd; ++di) {
+        Device &dv = ctx->dev[(size_t)di];
+        SlotDev &sd = dv.slot[slot];
+        CUDA_TRY(ctx, cudaSetDevice(dv.id));
+        sd.task_begin = (uint32_t)((uint64_t)lp.n_tasks * di / nd);
+        sd.task_end = (uint32_t)((uint64_t)lp.n_tasks * (di + 1) / nd);
+        auto g_of_task = [&](uint32_t t) {
+            const uint32_t li = t / lp.chunks_per_leaf, ci = t % lp.chunks_per_leaf;
+            return (uint64_t)li * k + (uint64_t)ci * lp.chunk;
+        };
+        sd.g_begin = sd.task_begin < lp.n_tasks ? g_of_task(sd.task_begin) : total;
+        sd.g_end = sd.task_end < lp.n_tasks ? g_of_task(sd.task_end) : total;
+
+        CUDA_TRY(ctx, sd.leaves.reserve(n, true));
+        CUDA_TRY(ctx, sd.results.reserve(n, true));
+        memcpy(sd.leaves.h, leaves, sizeof(mr_leaf) * n);
+        CUDA_TRY(ctx, cudaMemcpyAsync(sd.leaves.d, sd.leaves.h, sizeof(mr_leaf) * n, cudaMemcpyHostToDevice, dv.stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(sd.results.d, 0, sizeof(mr_leaf_result) * n, dv.stream));
+        if (desc->policy == MR_EPS_MAST) {
+            rc = upload_mast(ctx, dv, (int)desc->game, mast_in);
+            if (rc != MR_OK) return rc;
+        }
+        KernelParams kp;
+        fill_params(kp, desc, lp, trace_cap);
+        kp.leaves = sd.leaves.d;
+        kp.results = sd.results.d;
+        kp.task_begin = sd.task_begin;
+        kp.task_end = sd.task_end;
+        kp.mast_rank = dv.mast_rank.d;
+        if (desc->flags & MR_WANT_AMAF) {
+            CUDA_TRY(ctx, sd.amaf.reserve((size_t)n * 2 * na, true));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.amaf.d, 0, sizeof(mr_action_stat) * n * 2 * na, dv.stream));
+            kp.amaf = sd.amaf.d;
+        }
+        if (desc->flags & MR_WANT_MAST_DELTA) {
+            CUDA_TRY(ctx, sd.mast_delta.reserve((size_t)2 * na, true));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.mast_delta.d, 0, sizeof(mr_action_stat) * 2 * na, dv.stream));
+            kp.mast_delta = sd.mast_delta.d;
+        }
+        if (desc->flags & MR_WANT_TRACE) {
+            CUDA_TRY(ctx, sd.trace.reserve((size_t)total * desc->max_trace, true));
+            CUDA_TRY(ctx, sd.rec.reserve((size_t)total, true));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.trace.d, 0, sizeof(uint16_t) * total * desc->max_trace, dv.stream));
+            kp.trace = sd.trace.d;
+            kp.rec = sd.rec.d;
+        }
+        if (desc->flags & MR_WANT_FINAL_STATE) {
+            CUDA_TRY(ctx, sd.final_state.reserve((size_t)total, true));
+            kp.final_state = sd.final_state.d;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(sd.ev_begin, dv.stream));
+        rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter);
+        if (rc != MR_OK) return rc;
+        CUDA_TRY(ctx, cudaEventRecord(sd.ev_end, dv.stream));
+
+        // results come back on the same stream
+        CUDA_TRY(ctx, cudaMemcpyAsync(sd.results.h, sd.results.d, sizeof(mr_leaf_result) * n, cudaMemcpyDeviceToHost, dv.stream));
+        if (desc->flags & MR_WANT_AMAF)
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.amaf.h, sd.amaf.d, sizeof(mr_action_stat) * n * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
+        if (desc->flags & MR_WANT_MAST_DELTA)
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.mast_delta.h, sd.mast_delta.d, sizeof(mr_action_stat) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
+        const uint64_t gb = sd.g_begin, ge = sd.g_end;
+        if (ge > gb) {
+            if (desc->flags & MR_WANT_TRACE) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(sd.trace.h + gb * desc->max_trace, sd.trace.d + gb * desc->max_trace,
+                                              sizeof(uint16_t) * (ge - gb) * desc->max_trace, cudaMemcpyDeviceToHost, dv.stream));
+                CUDA_TRY(ctx, cudaMemcpyAsync(sd.rec.h + gb, sd.rec.d + gb, sizeof(mr_playout_record) * (ge - gb),
+                                              cudaMemcpyDeviceToHost, dv.stream));
+            }
+            if (desc->flags & MR_WANT_FINAL_STATE)
+                CUDA_TRY(ctx, cudaMemcpyAsync(sd.final_state.h + gb, sd.final_state.d + gb, sizeof(mr_leaf) * (ge - gb),
+                                              cudaMemcpyDeviceToHost, dv.stream));
+        }
+    }
+    ss.busy = true;
+    ss.desc = *desc;
+    ss.chunk = lp.chunk;
+    ss.chunks_per_leaf = lp.chunks_per_leaf;
+    ss.n_tasks = lp.n_tasks;
+    return MR_OK;
+}
+
+int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out, mr_action_stat *mast_delta_out,
+            uint16_t *trace_out, mr_playout_record *rec_out, mr_leaf *final_out) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (slot < 0 || slot >= MR_NUM_SLOTS) return fail(ctx, MR_ERR_INVALID, "slot %d out of range", slot);
+    SlotState &ss = ctx->slot[slot];
+    if (!ss.busy) return fail(ctx, MR_ERR_INVALID, "slot %d has no batch in flight", slot);
+    if (!out) return fail(ctx, MR_ERR_INVALID, "null result buffer");
+    const mr_batch_desc &d = ss.desc;
+    const int na = kGames[d.game].num_actions;
+    const uint32_t n = d.n_leaves;
+    ss.busy = false; // whatever happens below, the slot is released
+    float worst_ms = 0.f;
+    for (Device &dv : ctx->dev) {
+        CUDA_TRY(ctx, cudaSetDevice(dv.id));
+        CUDA_TRY(ctx, cudaStreamSynchronize(dv.stream));
+        SlotDev &sd = dv.slot[slot];
+        if (sd.task_end > sd.task_begin) {
+            float ms = 0.f;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&ms, sd.ev_begin, sd.ev_end));
+            worst_ms = std::max(worst_ms, ms);
+        }
+    }
+    ss.kernel_ms = worst_ms;
+    memset(out, 0, sizeof(mr_leaf_result) * n);
+    if (amaf_out && (d.flags & MR_WANT_AMAF)) memset(amaf_out, 0, sizeof(mr_action_stat) * (size_t)n * 2 * na);
+    if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) memset(mast_delta_out, 0, sizeof(mr_action_stat) * 2 * na);
+    for (Device &dv : ctx->dev) {
+        SlotDev &sd = dv.slot[slot];
+        if (sd.task_end == sd.task_begin) continue;
+        for (uint32_t i = 0; i < n; ++i) {
+            out[i].wins[0] += sd.results.h[i].wins[0];
+            out[i].wins[1] += sd.results.h[i].wins[1];
+            out[i].draws += sd.results.h[i].draws;
+            out[i].cutoffs += sd.results.h[i].cutoffs;
+            out[i].sum_depth += sd.results.h[i].sum_depth;
+        }
+        if (amaf_out && (d.flags & MR_WANT_AMAF)) {
+            const size_t cnt = (size_t)n * 2 * na;
+            for (size_t i = 0; i < cnt; ++i) {
+                amaf_out[i].visits += sd.amaf.h[i].visits;
+                amaf_out[i].score += sd.amaf.h[i].score;
+            }
+        }
+        if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) {
+            for (int i = 0; i < 2 * na; ++i) {
+                mast_delta_out[i].visits += sd.mast_delta.h[i].visits;
+                mast_delta_out[i].score += sd.mast_delta.h[i].score;
+            }
+        }
+        const uint64_t gb = sd.g_begin, ge = sd.g_end;
+        if (ge > gb) {
+            if (d.flags & MR_WANT_TRACE) {
+                if (trace_out)
+                    memcpy(trace_out + gb * d.max_trace, sd.trace.h + gb * d.max_trace, sizeof(uint16_t) * (ge - gb) * d.max_trace);
+                if (rec_out) memcpy(rec_out + gb, sd.rec.h + gb, sizeof(mr_playout_record) * (ge - gb));
+            }
+            if ((d.flags & MR_WANT_FINAL_STATE) && final_out) memcpy(final_out + gb, sd.final_state.h + gb, sizeof(mr_leaf) * (ge - gb));
+        }
+    }
+    return MR_OK;
+}
+
+int mr_playout_batch(mr_ctx *ctx, const mr_batch_desc *desc, const mr_leaf *leaves, const mr_action_stat *mast_in,
+                     mr_leaf_result *out, mr_action_stat *amaf_out, mr_action_stat *mast_delta_out, uint16_t *trace_out,
+                     mr_playout_record *rec_out, mr_leaf *final_out) {
+    int rc = mr_submit(ctx, 0, desc, leaves, mast_in);
+    if (rc != MR_OK) return rc;
+    return mr_wait(ctx, 0, out, amaf_out, mast_delta_out, trace_out, rec_out, final_out);
+}
+
+int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, const void *d_leaves, void *d_results,
+                     void *d_amaf, void *d_mast_delta, void *stream) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (device_index < 0 || device_index >= (int)ctx->dev.size()) return fail(ctx, MR_ERR_INVALID, "device index %d out of range", device_index);
+    if (!d_leaves || !d_results) return fail(ctx, MR_ERR_INVALID, "null device buffer");
+    Device &dv = ctx->dev[(size_t)device_index];
+    if (!desc) return fail(ctx, MR_ERR_INVALID, "null batch descriptor");
+    if (desc->flags & (MR_WANT_TRACE | MR_WANT_FINAL_STATE))
+        return fail(ctx, MR_ERR_INVALID, "trace / final-state outputs are not available on the device-resident path");
+    kernel_fn fn = nullptr;
+    uint32_t trace_cap = 0;
+    int rc = validate(ctx, desc, dv.mast_game == (int)desc->game, &fn, &trace_cap);
+    if (rc != MR_OK) return rc;
+    if ((desc->flags & MR_WANT_AMAF) && !d_amaf) return fail(ctx, MR_ERR_INVALID, "MR_WANT_AMAF without d_amaf");
+    if ((desc->flags & MR_WANT_MAST_DELTA) && !d_mast_delta) return fail(ctx, MR_ERR_INVALID, "MR_WANT_MAST_DELTA without d_mast_delta");
+    CUDA_TRY(ctx, cudaSetDevice(dv.id));
+    LaunchPlan lp;
+    rc = plan_launch(ctx, dv, fn, desc, 1, &lp);
+    if (rc != MR_OK) return rc;
+    KernelParams kp;
+    fill_params(kp, desc, lp, trace_cap);
+    kp.leaves = (const mr_leaf *)d_leaves;
+    kp.results = (mr_leaf_result *)d_results;
+    kp.amaf = (mr_action_stat *)d_amaf;
+    kp.mast_delta = (mr_action_stat *)d_mast_delta;
+    kp.task_begin = 0;
+    kp.task_end = lp.n_tasks;
+    kp.mast_rank = dv.mast_rank.d;
+    cudaStream_t st = stream ? (cudaStream_t)stream : dv.stream;
+    return launch_on(ctx, dv, fn, kp, lp, st, dv.d_counter_ext);
+}
+
+int mr_last_kernel_ms(mr_ctx *ctx, int slot, float *ms) {
+    if (!ctx || !ms || slot < 0 || slot >= MR_NUM_SLOTS) return fail(ctx, MR_ERR_INVALID, "mr_last_kernel_ms: bad arguments");
+    *ms = ctx->slot[slot].kernel_ms;
+    return MR_OK;
+}
+
+uint64_t mr_kernel_launches(const mr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int mr_allreduce_root(mr_ctx *ctx, int32_t *const *bufs, int n_bufs, size_t n) {
+    if (!ctx || !bufs || n_bufs <= 0) return fail(ctx, MR_ERR_INVALID, "mr_allreduce_root: bad arguments");
+    std::vector<int64_t> sum(n, 0);
+    for (int b = 0; b < n_bufs; ++b) {
+        if (!bufs[b]) return fail(ctx, MR_ERR_INVALID, "mr_allreduce_root: null buffer %d", b);
+        for (size_t i = 0; i < n; ++i) sum[i] += bufs[b][i];
+    }
+    for (int b = 0; b < n_bufs; ++b)
+        for (size_t i = 0; i < n; ++i) bufs[b][i] = (int32_t)sum[i];
+    return MR_OK;
+}
+
+// ---- NCCL, loaded at run time so the library carries no link-time dependency on it ----
+namespace {
+typedef struct {
+    char internal[MR_COMM_ID_BYTES];
+} nccl_uid;
+typedef int (*nccl_get_uid_fn)(nccl_uid *);
+typedef int (*nccl_init_rank_fn)(void **, int, nccl_uid, int);
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*nccl_errstr_fn)(int);
+
+void *open_nccl() {
+    // prefer the copy already mapped into the process (torch's), then the system one
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        void *h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD);
+        if (h) return h;
+    }
+    for (const char *nm : names) {
+        void *h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) return h;
+    }
+    return nullptr;
+}
+} // namespace
+
+int mr_comm_unique_id(uint8_t id[MR_COMM_ID_BYTES]) {
+    void *lib = open_nccl();
+    if (!lib) return fail(nullptr, MR_ERR_COMM, "libnccl.so.2 not found");
+    nccl_get_uid_fn f = (nccl_get_uid_fn)dlsym(lib, "ncclGetUniqueId");
+    if (!f) return fail(nullptr, MR_ERR_COMM, "ncclGetUniqueId missing");
+    nccl_uid u;
+    int rc = f(&u);
+    if (rc != 0) return fail(nullptr, MR_ERR_COMM, "ncclGetUniqueId failed: %d", rc);
+    memcpy(id, u.internal, MR_COMM_ID_BYTES);
+    return MR_OK;
+}
+
+int mr_comm_init(mr_ctx *ctx, const uint8_t id[MR_COMM_ID_BYTES], int rank, int world_size) {
+    if (!ctx || !id || rank < 0 || rank >= world_size) return fail(ctx, MR_ERR_INVALID, "mr_comm_init: bad arguments");
+    if (ctx->dev.size() != 1) return fail(ctx, MR_ERR_INVALID, "mr_comm_init: one device per rank");
+    ctx->nccl_lib = open_nccl();
+    if (!ctx->nccl_lib) return fail(ctx, MR_ERR_COMM, "libnccl.so.2 not found");
+    nccl_init_rank_fn f = (nccl_init_rank_fn)dlsym(ctx->nccl_lib, "ncclCommInitRank");
+    if (!f) return fail(ctx, MR_ERR_COMM, "ncclCommInitRank missing");
+    nccl_uid u;
+    memcpy(u.internal, id, MR_COMM_ID_BYTES);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->dev[0].id));
+    int rc = f(&ctx->nccl_comm, world_size, u, rank);
+    if (rc != 0) return fail(ctx, MR_ERR_COMM, "ncclCommInitRank failed: %d", rc);
+    ctx->comm_rank = rank;
+    ctx->comm_world = world_size;
+    return MR_OK;
+}
+
+int mr_comm_allreduce_i32(mr_ctx *ctx, void *d_buf, size_t n, void *stream) {
+    if (!ctx || !d_buf) return fail(ctx, MR_ERR_INVALID, "mr_comm_allreduce_i32: bad arguments");
+    if (!ctx->nccl_comm) return fail(ctx, MR_ERR_COMM, "communicator not initialised (mr_comm_init)");
+    nccl_allreduce_fn f = (nccl_allreduce_fn)dlsym(ctx->nccl_lib, "ncclAllReduce");
+    if (!f) return fail(ctx, MR_ERR_COMM, "ncclAllReduce missing");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->dev[0].id));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->dev[0].stream;
+    const int nccl_int32 = 2, nccl_sum = 0;
+    int rc = f(d_buf, d_buf, n, nccl_int32, nccl_sum, ctx->nccl_comm, st);
+    if (rc != 0) return fail(ctx, MR_ERR_COMM, "ncclAllReduce failed: %d", rc);
+    return MR_OK;
+}
+
+int mr_measure_int_peak(mr_ctx *ctx, int device_index, int kind, double *ops_per_second, double *sm_clock_mhz) {
+    if (!ctx || !ops_per_second) return fail(ctx, MR_ERR_INVALID, "mr_measure_int_peak: bad arguments");
+    if (device_index < 0 || device_index >= (int)ctx->dev.size()) return fail(ctx, MR_ERR_INVALID, "device index out of range");
+    if (kind < 0 || kind >= mr::INT_PEAK_KINDS) return fail(ctx, MR_ERR_INVALID, "unknown kind %d", kind);
+    Device &dv = ctx->dev[(size_t)device_index];
+    CUDA_TRY(ctx, cudaSetDevice(dv.id));
+    uint32_t *d_sink = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_sink, sizeof(uint32_t) * 1024));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0));
+    CUDA_TRY(ctx, cudaEventCreate(&e1));
+    const int blocks = dv.num_sms * 2, threads = 1024;
+    const int iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(ctx, cudaEventRecord(e0, dv.stream));
+        mr::launch_int_peak(kind, blocks, threads, iters, d_sink, dv.stream);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(e1, dv.stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(dv.stream));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)blocks * threads * iters * mr::INT_PEAK_OPS_PER_ITER;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    ctx->launches += 0; // micro-benchmark launches are not rollout launches
+    *ops_per_second = best;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dv.id);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_sink);
+    return MR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,93 @@
+// common.cuh -- shared device-side definitions of the rollout engine (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mcts_rollout.h"
+
+namespace mr {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int THREADS_PER_BLOCK = WARPS_PER_BLOCK * 32;
+
+// step() result codes.  Bit 3 says a ply was made; the low bits say how the playout ended.
+enum : int {
+    ST_CONTINUE = 0,
+    ST_WIN_P0 = 1,
+    ST_WIN_P1 = 2,
+    ST_DRAW = 3,       // terminal draw
+    ST_NO_ACTIONS = 4, // no actions but not terminal: NaturalEnd/NotTerminal, scored as a draw (simulate.rs:112-116)
+    ST_END_MASK = 7,
+    ST_MOVED = 8
+};
+
+// Everything one launch needs; passed by value (lives in the constant bank, so warp-uniform reads of
+// it are free operands of ALU instructions).
+struct KernelParams {
+    const mr_leaf *leaves;
+    mr_leaf_result *results;
+    uint32_t *task_counter; // persistent-warp work queue head
+    uint32_t n_leaves;
+    uint32_t k;               // playouts per leaf
+    uint32_t chunk;           // playouts per task (a task never straddles leaves)
+    uint32_t chunks_per_leaf; // ceil(k / chunk)
+    uint32_t task_begin;      // this device's share of the task range
+    uint32_t task_end;
+    uint32_t max_depth; // 0xffffffff = unlimited
+    uint32_t seed_lo, seed_hi;
+    uint32_t leaf_id_base;
+    uint32_t eps_thr_m1; // explore iff eps_enable && x1 <= eps_thr_m1
+    uint32_t eps_enable;
+    uint32_t max_trace;
+    // optional outputs
+    mr_action_stat *amaf;       // [n_leaves][2][NA]
+    mr_action_stat *mast_delta; // [2][NA]
+    uint16_t *trace;            // [n_leaves*k][max_trace]
+    mr_playout_record *rec;     // [n_leaves*k]
+    mr_leaf *final_state;       // [n_leaves*k]
+    // MAST snapshot as dense order-preserving ranks of score/visits (unvisited == value 1.0)
+    const uint16_t *mast_rank; // [2][NA]
+    uint16_t *trace_scratch;   // [resident warps][trace_cap][32] u16, MAST-delta staging
+    uint32_t trace_cap;
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ uint32_t lo32(uint64_t v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t hi32(uint64_t v) { return (uint32_t)(v >> 32); }
+__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ uint64_t bit64(uint32_t pos) { return 1ull << pos; }
+
+// ---- Philox4x32-10 (Salmon et al. SC'11), the draw discipline's generator ----
+// ctr = (leaf_id, playout_id, ply >> 2, stream), key = (seed_lo, seed_hi); word [ply & 3] serves ply.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(M0, c0), l0 = M0 * c0;
+        const uint32_t h1 = __umulhi(M1, c2), l1 = M1 * c2;
+        c0 = h1 ^ c1 ^ k0;
+        c1 = l1;
+        c2 = h0 ^ c3 ^ k1;
+        c3 = l0;
+        k0 += W0;
+        k1 += W1;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// util.rs:129-132 PRIMES, packed for random_best's stride
+__device__ __constant__ uint32_t MR_PRIMES[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991,
+                                                  53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693};
+
+} // namespace mr

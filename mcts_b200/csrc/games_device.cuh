@@ -1,0 +1,771 @@
+// games_device.cuh -- the five bitboard games as per-lane register state machines (sm_100a).
+//
+// Each game keeps the reference's RULES and ACTION ORDER (so that "the idx-th legal action" means the
+// same action as in the reference's generate_actions list) but not its data layout or algorithm:
+// moves are never materialised; legal-move sets live in bitboards, the idx-th action is found with
+// popcount rank/select, and terminal tests are incremental.  Reference lines each rule follows are
+// cited at the rule.
+//
+// Common contract (used by rollout_kernel.cuh):
+//   struct Shared            per-warp leaf-derived data in shared memory
+//   prepare(sh, leaf, lane)  all 32 lanes; fills sh; returns the leaf's own TerminalStatus (mr_outcome)
+//   reset(sh)                lane state := leaf
+//   step<POLICY, PARITY>(..) one ply for the lane; mover = sh.turn ^ PARITY; returns ST_* code
+//   store_final(sh, out, parity_after)  debug: lane state -> reference-layout mr_leaf
+#pragma once
+
+#include "common.cuh"
+
+namespace mr {
+
+__device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+
+// Position of the idx-th (0-based) set bit of a 32-bit word, by binary search on popcounts.
+__device__ __forceinline__ uint32_t select32(uint32_t w, uint32_t idx) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const uint32_t m = ((1u << step) - 1u) << pos;
+        const uint32_t c = __popc(w & m);
+        if (idx >= c) {
+            idx -= c;
+            pos += step;
+        }
+    }
+    return pos;
+}
+
+// ==========================================================================================
+// Connect4 6x7 -- games/connect4/src/lib.rs
+//   rules: legal = non-full columns ascending (:303-312); drop at height (:314-339); win = four in a
+//   row N/E/NE/NW (:195-207); terminal = winner or 42 stones (:372-374); winner keeps the turn.
+//   device layout: one BYTE per column (bit = col*8 + row), rows 6-7 of every byte stay zero, so
+//   `all + 0x01..01` yields the drop cell of every column at once and shifted-AND line tests need no
+//   wall masks.
+// ==========================================================================================
+struct Connect4 {
+    static constexpr int NA = 7;
+    static constexpr uint64_t BOTTOM = 0x0001010101010101ull;
+    static constexpr uint64_t BOARD = 0x003F3F3F3F3F3F3Full;
+    static constexpr uint64_t TOPROW = 0x0020202020202020ull;
+
+    struct Shared {
+        uint64_t cur; // stones of the player to move, column-byte layout
+        uint64_t all;
+        uint32_t turn;
+        uint32_t n_open; // columns that are not full
+    };
+
+    uint64_t cur, all;
+    uint32_t n_open;
+
+    __device__ static uint64_t to_colbyte(uint64_t rm) { // reference row-major (idx = row*7 + col) -> col*8 + row
+        uint64_t out = 0;
+        for (int row = 0; row < 6; ++row)
+            for (int col = 0; col < 7; ++col)
+                if ((rm >> (row * 7 + col)) & 1) out |= 1ull << (col * 8 + row);
+        return out;
+    }
+    __device__ static uint64_t to_rowmajor(uint64_t cb) {
+        uint64_t out = 0;
+        for (int row = 0; row < 6; ++row)
+            for (int col = 0; col < 7; ++col)
+                if ((cb >> (col * 8 + row)) & 1) out |= 1ull << (row * 7 + col);
+        return out;
+    }
+
+    __device__ static bool four(uint64_t me) {
+        uint64_t m, acc;
+        m = me & (me >> 1);
+        acc = m & (m >> 2);
+        m = me & (me >> 8);
+        acc |= m & (m >> 16);
+        m = me & (me >> 7);
+        acc |= m & (m >> 14);
+        m = me & (me >> 9);
+        acc |= m & (m >> 18);
+        return acc != 0;
+    }
+
+    __device__ static int prepare(Shared &sh, const mr_leaf &leaf, uint32_t lane) {
+        const uint64_t black = to_colbyte(leaf.board[0]), white = to_colbyte(leaf.board[1]);
+        const uint64_t all = black | white;
+        if (lane == 0) {
+            sh.cur = leaf.turn ? white : black;
+            sh.all = all;
+            sh.turn = leaf.turn;
+            sh.n_open = __popcll((all + BOTTOM) & BOARD);
+        }
+        if (leaf.flag) return leaf.turn ? MR_WINNER_P1 : MR_WINNER_P0; // :380-386 winner == turn
+        if (__popcll(all) == 42) return MR_DRAW;
+        return MR_NOT_TERMINAL;
+    }
+
+    __device__ void reset(const Shared &sh) {
+        cur = sh.cur;
+        all = sh.all;
+        n_open = sh.n_open;
+    }
+
+    template <int POLICY, int PARITY>
+    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action) {
+        const uint64_t moves = (all + BOTTOM) & BOARD; // one bit per open column, ascending column order
+        uint64_t bit;
+        if (POLICY == MR_DECISIVE_WIN) {
+            // first legal column (ascending) whose drop wins for the mover (simulate.rs:662-670); a Connect4
+            // move cannot lose immediately, a drawing move exists only as the 42nd stone (the single action)
+            uint64_t winning = 0;
+            for (uint64_t m = moves; m; m &= m - 1) {
+                const uint64_t b = m & (0 - m);
+                if (four(cur | b)) {
+                    winning = b;
+                    break;
+                }
+            }
+            bit = winning;
+        } else {
+            bit = 0;
+        }
+        if (bit == 0) {
+            uint32_t idx = mulhi(x0, n_open);
+            const uint32_t lo = lo32(moves), hi = hi32(moves);
+            const uint32_t nlo = __popc(lo);
+            const bool in_hi = idx >= nlo;
+            uint32_t w = in_hi ? hi : lo;
+            idx = in_hi ? idx - nlo : idx;
+            if (idx > 0) w &= w - 1;
+            if (idx > 1) w &= w - 1;
+            if (idx > 2) w &= w - 1;
+            const uint32_t b = w & (0u - w);
+            bit = in_hi ? mk64(0, b) : mk64(b, 0);
+        }
+        action = (uint32_t)(__ffsll((long long)bit) - 1) >> 3; // column
+        all |= bit;
+        const uint64_t me = cur | bit;
+        n_open -= (bit & TOPROW) ? 1u : 0u;
+        cur = all ^ me; // the opponent moves next
+        const uint32_t mover = sh.turn ^ PARITY;
+        if (four(me)) return ST_MOVED | (mover ? ST_WIN_P1 : ST_WIN_P0);
+        if (n_open == 0) return ST_MOVED | ST_DRAW;
+        return ST_MOVED;
+    }
+
+    // parity_next: (plies played) & 1
+    __device__ void store_final(const Shared &sh, mr_leaf *out, uint32_t plies, int end_code) const {
+        // `cur` is the stones of the player who would move next (or, after a win, of the loser)
+        const uint32_t next = (sh.turn + plies) & 1;
+        const uint64_t nxt = to_rowmajor(cur), oth = to_rowmajor(all ^ cur);
+        const bool won = end_code == ST_WIN_P0 || end_code == ST_WIN_P1;
+        out->board[0] = next == 0 ? nxt : oth;
+        out->board[1] = next == 0 ? oth : nxt;
+        out->board[2] = out->board[3] = 0;
+        // the winner keeps the turn (:332-336)
+        out->turn = (uint8_t)(won ? next ^ 1 : next);
+        out->flag = won ? 1 : 0;
+        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+    }
+};
+
+// ==========================================================================================
+// Breakthrough 8x8 -- games/breakthrough/src/lib.rs
+//   moves (:131-156): for src ascending, dst ascending = {west diagonal, straight, east diagonal};
+//   diagonals may capture (dst not own), straight needs an empty cell.  Black moves south (-8),
+//   White north (+8).  apply (:158-188): far wall reached => winner, turn kept.  No capture-all win;
+//   a side without moves ends the playout as a draw (simulate.rs:112-116).
+//   device: three SOURCE-space masks W,F,E; per-cell move count = W+F+E as a bit-sliced 2-bit number
+//   (S = xor, C = majority); the idx-th move in reference order is a popcount rank/select over (S,C).
+// ==========================================================================================
+struct ThroughBase {
+    static constexpr int NA = 4096;
+    static constexpr uint64_t NOT_COL0 = 0xFEFEFEFEFEFEFEFEull;
+    static constexpr uint64_t NOT_COL7 = 0x7F7F7F7F7F7F7F7Full;
+
+    struct Shared {
+        uint64_t black, white;
+        uint32_t turn;
+    };
+
+    uint64_t black, white;
+
+    __device__ static int prepare(Shared &sh, const mr_leaf &leaf, uint32_t lane) {
+        if (lane == 0) {
+            sh.black = leaf.board[0];
+            sh.white = leaf.board[1];
+            sh.turn = leaf.turn;
+        }
+        if (leaf.flag) return leaf.turn ? MR_WINNER_P1 : MR_WINNER_P0;
+        return MR_NOT_TERMINAL;
+    }
+    __device__ void reset(const Shared &sh) {
+        black = sh.black;
+        white = sh.white;
+    }
+    __device__ void store_final(const Shared &sh, mr_leaf *out, uint32_t plies, int end_code) const {
+        const uint32_t next = (sh.turn + plies) & 1;
+        const bool won = end_code == ST_WIN_P0 || end_code == ST_WIN_P1;
+        out->board[0] = black;
+        out->board[1] = white;
+        out->board[2] = out->board[3] = 0;
+        out->turn = (uint8_t)(won ? next ^ 1 : next);
+        out->flag = won ? 1 : 0;
+        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+    }
+    // own/opp update for a move src -> dst by `white`; returns true when the far wall is reached
+    __device__ bool apply_move(bool is_white, uint32_t src, uint32_t dst) {
+        const uint64_t s = bit64(src), d = bit64(dst);
+        if (is_white) {
+            white = (white | d) & ~s;
+            black &= ~d;
+            return dst >= 56;
+        } else {
+            black = (black | d) & ~s;
+            white &= ~d;
+            return dst < 8;
+        }
+    }
+};
+
+struct Breakthrough : ThroughBase {
+    // source-space masks of the three move kinds for the mover
+    __device__ static void masks(bool is_white, uint64_t own, uint64_t opp, uint64_t &W, uint64_t &F, uint64_t &E) {
+        const uint64_t occ = own | opp;
+        if (is_white) { // dst = src+7 (W), src+8 (F), src+9 (E)
+            F = own & (~occ >> 8);
+            W = own & NOT_COL0 & (~own >> 7);
+            E = own & NOT_COL7 & (~own >> 9);
+        } else { // dst = src-9 (W), src-8 (F), src-7 (E)
+            F = own & (~occ << 8);
+            W = own & NOT_COL0 & (~own << 9);
+            E = own & NOT_COL7 & (~own << 7);
+        }
+    }
+
+    // rank/select: the idx-th move in (src ascending; W,F,E) order.  Returns src, sets dir (0=W,1=F,2=E).
+    __device__ static uint32_t select_move(uint64_t W, uint64_t F, uint64_t E, uint64_t S, uint64_t C, uint32_t idx,
+                                           uint32_t &dir) {
+        const uint32_t cl = __popc(lo32(S)) + 2u * __popc(lo32(C));
+        const bool in_hi = idx >= cl;
+        idx = in_hi ? idx - cl : idx;
+        const uint32_t s = in_hi ? hi32(S) : lo32(S), c = in_hi ? hi32(C) : lo32(C);
+        uint32_t pos = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const uint32_t m = ((1u << step) - 1u) << pos;
+            const uint32_t cnt = __popc(s & m) + 2u * __popc(c & m);
+            if (idx >= cnt) {
+                idx -= cnt;
+                pos += step;
+            }
+        }
+        const uint32_t w = ((in_hi ? hi32(W) : lo32(W)) >> pos) & 1u;
+        const uint32_t f = ((in_hi ? hi32(F) : lo32(F)) >> pos) & 1u;
+        // idx is now the residual among this cell's set kinds in W,F,E order
+        if (w && idx == 0) {
+            dir = 0;
+        } else {
+            idx -= w;
+            dir = (f && idx == 0) ? 1u : 2u;
+        }
+        return pos + (in_hi ? 32u : 0u);
+    }
+
+    template <int POLICY, int PARITY>
+    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action);
+};
+
+// ==========================================================================================
+// Knightthrough 8x8 -- games/knightthrough/src/lib.rs:126-190
+//   same state/apply/goal as Breakthrough; moves = all eight knight jumps staying on the board minus own
+//   pieces, src ascending then dst ascending, i.e. jump deltas in the order -17,-15,-10,-6,+6,+10,+15,+17.
+// ==========================================================================================
+struct Knightthrough : ThroughBase {
+    __device__ static void masks(uint64_t own, uint64_t M[8]) {
+        const uint64_t n = ~own;
+        constexpr uint64_t GE1 = 0xFEFEFEFEFEFEFEFEull, LE6 = 0x7F7F7F7F7F7F7F7Full;
+        constexpr uint64_t GE2 = 0xFCFCFCFCFCFCFCFCull, LE5 = 0x3F3F3F3F3F3F3F3Full;
+        M[0] = own & GE1 & (n << 17); // (-2,-1)
+        M[1] = own & LE6 & (n << 15); // (-2,+1)
+        M[2] = own & GE2 & (n << 10); // (-1,-2)
+        M[3] = own & LE5 & (n << 6);  // (-1,+2)
+        M[4] = own & GE2 & (n >> 6);  // (+1,-2)
+        M[5] = own & LE5 & (n >> 10); // (+1,+2)
+        M[6] = own & GE1 & (n >> 15); // (+2,-1)
+        M[7] = own & LE6 & (n >> 17); // (+2,+1)
+    }
+    __device__ static int delta(uint32_t k) {
+        // -17,-15,-10,-6,+6,+10,+15,+17 packed as bytes biased by +17
+        const uint64_t tbl = 0x22201B170B070200ull;
+        return (int)((tbl >> (8 * k)) & 0xff) - 17;
+    }
+
+    template <int POLICY, int PARITY>
+    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action);
+};
+
+// ---- MAST greedy pick shared by Breakthrough / Knightthrough ----
+// random_best (util.rs:135-163) over scores given as order-preserving ranks: visit list positions
+// i_j = (i0 + j*stride) mod n, keep the first strict maximum.  `rank_of(i)` returns the rank of the i-th
+// legal action in list order.  Implemented as: one pass in list order for the maximum and its
+// multiplicity, then (only when tied) a walk in visiting order until a maximal action is met.
+template <class RankOf>
+__device__ __forceinline__ uint32_t mast_random_best(uint32_t n, uint32_t r, RankOf rank_of) {
+    const uint32_t i0 = r >> 4;
+    const uint32_t stride = MR_PRIMES[r & 15u] % n;
+    uint32_t best = rank_of(0), best_i = 0, count = 1;
+    for (uint32_t i = 1; i < n; ++i) {
+        const uint32_t v = rank_of(i);
+        if (v > best) {
+            best = v;
+            best_i = i;
+            count = 1;
+        } else if (v == best) {
+            ++count;
+        }
+    }
+    if (count == 1) return best_i;
+    uint32_t i = i0;
+    for (uint32_t j = 0; j < n; ++j) {
+        if (rank_of(i) == best) return i;
+        i += stride;
+        if (i >= n) i -= n;
+    }
+    return best_i; // unreachable
+}
+
+template <int POLICY, int PARITY>
+__device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p,
+                                  uint32_t &action) {
+    const bool is_white = ((sh.turn ^ PARITY) & 1u) != 0;
+    const uint64_t own = is_white ? white : black, opp = is_white ? black : white;
+    uint64_t W, F, E;
+    masks(is_white, own, opp, W, F, E);
+    const uint64_t S = W ^ F ^ E, C = (W & F) | (W & E) | (F & E);
+    const uint32_t n = __popcll(S) + 2u * __popcll(C);
+    if (n == 0) return ST_NO_ACTIONS;
+    uint32_t idx;
+    if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+        const uint16_t *tab = p.mast_rank + (is_white ? NA : 0);
+        const int base = is_white ? 7 : -9;
+        auto rank_of = [&](uint32_t i) -> uint32_t {
+            uint32_t d;
+            const uint32_t s = select_move(W, F, E, S, C, i, d);
+            return tab[s * 64u + (uint32_t)((int)s + base + (int)d)];
+        };
+        idx = mast_random_best(n, mulhi(x0, 16u * n), rank_of);
+    } else {
+        idx = mulhi(x0, n);
+    }
+    uint32_t dir;
+    const uint32_t src = select_move(W, F, E, S, C, idx, dir);
+    const uint32_t dst = (uint32_t)((int)src + (is_white ? 7 : -9) + (int)dir);
+    action = (src << 8) | dst;
+    const bool won = apply_move(is_white, src, dst);
+    if (won) return ST_MOVED | (is_white ? ST_WIN_P1 : ST_WIN_P0);
+    return ST_MOVED;
+}
+
+template <int POLICY, int PARITY>
+__device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p,
+                                   uint32_t &action) {
+    const bool is_white = ((sh.turn ^ PARITY) & 1u) != 0;
+    const uint64_t own = is_white ? white : black;
+    uint64_t M[8];
+    masks(own, M);
+    // per-cell move count as a bit-sliced 4-bit number (carry-save adder tree over the 8 masks)
+    uint64_t s01 = M[0] ^ M[1] ^ M[2], c01 = (M[0] & M[1]) | (M[0] & M[2]) | (M[1] & M[2]);
+    uint64_t s23 = M[3] ^ M[4] ^ M[5], c23 = (M[3] & M[4]) | (M[3] & M[5]) | (M[4] & M[5]);
+    uint64_t s45 = M[6] ^ M[7], c45 = M[6] & M[7];
+    const uint64_t B0 = s01 ^ s23 ^ s45;                                  // weight 1
+    const uint64_t k0 = (s01 & s23) | (s01 & s45) | (s23 & s45);          // weight 2 carry
+    const uint64_t t1 = c01 ^ c23 ^ c45, u1 = (c01 & c23) | (c01 & c45) | (c23 & c45); // weight 2 sum, weight 4 carry
+    const uint64_t B1 = t1 ^ k0, k1 = t1 & k0;                            // weight 2, carry to 4
+    const uint64_t B2 = u1 ^ k1, B3 = u1 & k1;                            // weight 4, weight 8
+    const uint32_t n = __popcll(B0) + 2u * __popcll(B1) + 4u * __popcll(B2) + 8u * __popcll(B3);
+    if (n == 0) return ST_NO_ACTIONS;
+
+    auto select_move = [&](uint32_t idx, uint32_t &kind) -> uint32_t {
+        const uint32_t cl = __popc(lo32(B0)) + 2u * __popc(lo32(B1)) + 4u * __popc(lo32(B2)) + 8u * __popc(lo32(B3));
+        const bool in_hi = idx >= cl;
+        idx = in_hi ? idx - cl : idx;
+        const uint32_t b0 = in_hi ? hi32(B0) : lo32(B0), b1 = in_hi ? hi32(B1) : lo32(B1);
+        const uint32_t b2 = in_hi ? hi32(B2) : lo32(B2), b3 = in_hi ? hi32(B3) : lo32(B3);
+        uint32_t pos = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const uint32_t m = ((1u << step) - 1u) << pos;
+            const uint32_t cnt = __popc(b0 & m) + 2u * __popc(b1 & m) + 4u * __popc(b2 & m) + 8u * __popc(b3 & m);
+            if (idx >= cnt) {
+                idx -= cnt;
+                pos += step;
+            }
+        }
+        // residual: idx-th set kind at this cell, kinds in ascending-dst order
+        uint32_t kk = 7;
+        bool found = false;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t b = ((in_hi ? hi32(M[q]) : lo32(M[q])) >> pos) & 1u;
+            if (!found && b && idx == 0) {
+                kk = q;
+                found = true;
+            }
+            idx -= (found ? 0u : b);
+        }
+        kind = kk;
+        return pos + (in_hi ? 32u : 0u);
+    };
+
+    uint32_t idx;
+    if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+        const uint16_t *tab = p.mast_rank + (is_white ? NA : 0);
+        auto rank_of = [&](uint32_t i) -> uint32_t {
+            uint32_t kq;
+            const uint32_t s = select_move(i, kq);
+            return tab[s * 64u + (uint32_t)((int)s + delta(kq))];
+        };
+        idx = mast_random_best(n, mulhi(x0, 16u * n), rank_of);
+    } else {
+        idx = mulhi(x0, n);
+    }
+    uint32_t kind;
+    const uint32_t src = select_move(idx, kind);
+    const uint32_t dst = (uint32_t)((int)src + delta(kind));
+    action = (src << 8) | dst;
+    const bool won = apply_move(is_white, src, dst);
+    if (won) return ST_MOVED | (is_white ? ST_WIN_P1 : ST_WIN_P0);
+    return ST_MOVED;
+}
+
+// ==========================================================================================
+// Othello 8x8 -- games/othello/src/lib.rs
+//   movegen (:132-180) and flips (:188-234) by directional fills; actions = legal squares ascending, or
+//   the single PASS (=64) when there are none (:484-499); apply (:502-541); terminal = 64 discs, or
+//   last_pass and the mover has no move (:565-579); winner by disc count (:585-596).
+// ==========================================================================================
+struct Othello {
+    static constexpr int NA = 65;
+    static constexpr uint64_t NOT_A = 0xFEFEFEFEFEFEFEFEull; // not column 0
+    static constexpr uint64_t NOT_H = 0x7F7F7F7F7F7F7F7Full; // not column 7
+
+    struct Shared {
+        uint64_t black, white;
+        uint32_t turn, last_pass;
+    };
+    uint64_t black, white;
+    uint32_t last_pass;
+
+    // discs of `o` reachable from `g` by repeated shifts (left when L, else right) by `s`, staying inside `o & mask`
+    template <int S, bool L>
+    __device__ static uint64_t fill(uint64_t g, uint64_t o, uint64_t mask) {
+        const uint64_t om = o & mask;
+        uint64_t f = (L ? (g << S) : (g >> S)) & om;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) f |= (L ? (f << S) : (f >> S)) & om;
+        return f;
+    }
+    template <int S, bool L>
+    __device__ static uint64_t sh(uint64_t v) { return L ? (v << S) : (v >> S); }
+
+    __device__ static uint64_t legal_moves(uint64_t P, uint64_t O) {
+        const uint64_t empty = ~(P | O);
+        uint64_t m = 0;
+        m |= sh<8, true>(fill<8, true>(P, O, ~0ull));
+        m |= sh<8, false>(fill<8, false>(P, O, ~0ull));
+        m |= sh<1, true>(fill<1, true>(P, O, NOT_A)) & NOT_A;   // east: results never land in column 0
+        m |= sh<1, false>(fill<1, false>(P, O, NOT_H)) & NOT_H; // west
+        m |= sh<9, true>(fill<9, true>(P, O, NOT_A)) & NOT_A;   // north-east
+        m |= sh<9, false>(fill<9, false>(P, O, NOT_H)) & NOT_H; // south-west
+        m |= sh<7, true>(fill<7, true>(P, O, NOT_H)) & NOT_H;   // north-west
+        m |= sh<7, false>(fill<7, false>(P, O, NOT_A)) & NOT_A; // south-east
+        return m & empty;
+    }
+    template <int S, bool L>
+    __device__ static uint64_t flips_dir(uint64_t mv, uint64_t P, uint64_t O, uint64_t mask) {
+        const uint64_t f = fill<S, L>(mv, O, mask);
+        const uint64_t end = sh<S, L>(f) & mask & P;
+        return end ? f : 0ull;
+    }
+    __device__ static uint64_t flips(uint64_t mv, uint64_t P, uint64_t O) {
+        uint64_t f = 0;
+        f |= flips_dir<8, true>(mv, P, O, ~0ull);
+        f |= flips_dir<8, false>(mv, P, O, ~0ull);
+        f |= flips_dir<1, true>(mv, P, O, NOT_A);
+        f |= flips_dir<1, false>(mv, P, O, NOT_H);
+        f |= flips_dir<9, true>(mv, P, O, NOT_A);
+        f |= flips_dir<9, false>(mv, P, O, NOT_H);
+        f |= flips_dir<7, true>(mv, P, O, NOT_H);
+        f |= flips_dir<7, false>(mv, P, O, NOT_A);
+        return f;
+    }
+    __device__ static int count_outcome(uint64_t b, uint64_t w) {
+        const int nb = __popcll(b), nw = __popcll(w);
+        return nb > nw ? MR_WINNER_P0 : (nb < nw ? MR_WINNER_P1 : MR_DRAW);
+    }
+
+    __device__ static int prepare(Shared &s, const mr_leaf &leaf, uint32_t lane) {
+        if (lane == 0) {
+            s.black = leaf.board[0];
+            s.white = leaf.board[1];
+            s.turn = leaf.turn;
+            s.last_pass = leaf.flag;
+        }
+        const uint64_t b = leaf.board[0], w = leaf.board[1];
+        bool term = __popcll(b | w) == 64;
+        if (!term && leaf.flag) term = legal_moves(leaf.turn ? w : b, leaf.turn ? b : w) == 0;
+        return term ? count_outcome(b, w) : MR_NOT_TERMINAL;
+    }
+    __device__ void reset(const Shared &s) {
+        black = s.black;
+        white = s.white;
+        last_pass = s.last_pass;
+    }
+
+    template <int POLICY, int PARITY>
+    __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action) {
+        const bool is_white = ((s.turn ^ PARITY) & 1u) != 0;
+        const uint64_t P = is_white ? white : black, O = is_white ? black : white;
+        const uint64_t moves = legal_moves(P, O);
+        if (moves == 0) {
+            // the only action is PASS.  (A double pass is terminal and was caught after the first pass.)
+            action = 64;
+            last_pass = 1;
+            // terminal next iff the opponent has no move either (:565-579)
+            if (legal_moves(O, P) == 0) return ST_MOVED | terminal_code(black, white);
+            return ST_MOVED;
+        }
+        // DecisiveMove<Win> (simulate.rs:662-687) can only find a terminal child when a single action
+        // exists (the 64th disc, or a PASS), so it never changes the pick: see DESIGN.md "Decisive move".
+        const uint32_t n = __popcll(moves);
+        uint32_t idx = mulhi(x0, n);
+        const uint32_t nlo = __popc(lo32(moves));
+        const bool in_hi = idx >= nlo;
+        const uint32_t sq = select32(in_hi ? hi32(moves) : lo32(moves), in_hi ? idx - nlo : idx) + (in_hi ? 32u : 0u);
+        const uint64_t mv = bit64(sq);
+        const uint64_t fl = flips(mv, P, O);
+        const uint64_t nP = P | mv | fl, nO = O & ~fl;
+        black = is_white ? nO : nP;
+        white = is_white ? nP : nO;
+        last_pass = 0;
+        action = sq;
+        if (__popcll(black | white) == 64) return ST_MOVED | terminal_code(black, white);
+        return ST_MOVED;
+    }
+    __device__ static int terminal_code(uint64_t b, uint64_t w) {
+        const int o = count_outcome(b, w);
+        return o == MR_WINNER_P0 ? ST_WIN_P0 : (o == MR_WINNER_P1 ? ST_WIN_P1 : ST_DRAW);
+    }
+    __device__ void store_final(const Shared &s, mr_leaf *out, uint32_t plies, int end_code) const {
+        out->board[0] = black;
+        out->board[1] = white;
+        out->board[2] = out->board[3] = 0;
+        out->turn = (uint8_t)((s.turn + plies) & 1);
+        out->flag = (uint8_t)last_pass;
+        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+    }
+};
+
+// ==========================================================================================
+// Hex 11x11 -- games/hex-gen/src/lib.rs (Position<11,2>)
+//   legal = empty cells ascending (:115-120); apply sets the cell, toggles the turn (:122-125); only the
+//   last mover is checked (:130-144): P0 connects north (row 10) <-> south (row 0), P1 west (col 0) <-> east
+//   (col 10) over the six hex neighbours N,S,E,W,NE(+12),SW(-12) (bitboard/src/board.rs:509-531).
+//   device: boards as 4 x u32; instead of a full flood6 fix-point every ply, each player keeps the set
+//   `conn` of own stones connected to its FIRST edge -- exactly flood6(first_edge) of the reference --
+//   grown incrementally only when the new stone touches it; the player has won iff conn meets the
+//   second edge.  Same answer at every ply, hence the same stop ply.
+// ==========================================================================================
+struct Hex11 {
+    static constexpr int NA = 121;
+    struct B128 {
+        uint32_t w[4];
+    };
+    struct Shared {
+        B128 stones[2];
+        B128 conn[2];
+        uint32_t turn;
+        uint32_t n_empty;
+    };
+    B128 stones[2];
+    B128 conn[2];
+    uint32_t n_empty;
+
+    __device__ static B128 zero() { return B128{{0, 0, 0, 0}}; }
+    __device__ static B128 band(B128 a, B128 b) { return B128{{a.w[0] & b.w[0], a.w[1] & b.w[1], a.w[2] & b.w[2], a.w[3] & b.w[3]}}; }
+    __device__ static B128 bor(B128 a, B128 b) { return B128{{a.w[0] | b.w[0], a.w[1] | b.w[1], a.w[2] | b.w[2], a.w[3] | b.w[3]}}; }
+    __device__ static B128 bandn(B128 a, B128 b) { return B128{{a.w[0] & ~b.w[0], a.w[1] & ~b.w[1], a.w[2] & ~b.w[2], a.w[3] & ~b.w[3]}}; }
+    __device__ static bool any(B128 a) { return (a.w[0] | a.w[1] | a.w[2] | a.w[3]) != 0; }
+    template <int S>
+    __device__ static B128 shl(B128 a) { // S < 32
+        return B128{{a.w[0] << S, __funnelshift_l(a.w[0], a.w[1], S), __funnelshift_l(a.w[1], a.w[2], S),
+                     __funnelshift_l(a.w[2], a.w[3], S)}};
+    }
+    template <int S>
+    __device__ static B128 shr(B128 a) {
+        return B128{{__funnelshift_r(a.w[0], a.w[1], S), __funnelshift_r(a.w[1], a.w[2], S),
+                     __funnelshift_r(a.w[2], a.w[3], S), a.w[3] >> S}};
+    }
+    // column / row masks of the 121-cell board (idx = row*11 + col), folded at compile time
+    __host__ __device__ static constexpr B128 col_mask(int col) {
+        B128 m{{0, 0, 0, 0}};
+        for (int r = 0; r < 11; ++r) {
+            const int i = r * 11 + col;
+            m.w[i >> 5] |= 1u << (i & 31);
+        }
+        return m;
+    }
+    __host__ __device__ static constexpr B128 row_mask(int row) {
+        B128 m{{0, 0, 0, 0}};
+        for (int c = 0; c < 11; ++c) {
+            const int i = row * 11 + c;
+            m.w[i >> 5] |= 1u << (i & 31);
+        }
+        return m;
+    }
+    __host__ __device__ static constexpr B128 inv(B128 c) { return B128{{~c.w[0], ~c.w[1], ~c.w[2], ~c.w[3]}}; }
+    // six-neighbourhood of a set, restricted to the board: N(+11) S(-11) E(+1) W(-1) NE(+12) SW(-12)
+    __device__ static B128 neighbours(B128 f, const B128 &NOT_COL0, const B128 &NOT_COL10, const B128 &BOARDM) {
+        const B128 fe = band(f, NOT_COL10); // may step east
+        const B128 fw = band(f, NOT_COL0);  // may step west
+        B128 n = shl<11>(f);
+        n = bor(n, shr<11>(f));
+        n = bor(n, shl<1>(fe));
+        n = bor(n, shr<1>(fw));
+        n = bor(n, shl<12>(fe));
+        n = bor(n, shr<12>(fw));
+        return band(n, BOARDM);
+    }
+    // flood from `seed` through `own` to a fix-point (bitboard/src/board.rs:509-531)
+    __device__ static B128 flood(B128 seed, B128 own, const B128 &NC0, const B128 &NC10, const B128 &BM) {
+        B128 f = band(seed, own);
+        for (;;) {
+            const B128 g = bandn(band(neighbours(f, NC0, NC10, BM), own), f);
+            if (!any(g)) break;
+            f = bor(f, g);
+        }
+        return f;
+    }
+    __host__ __device__ static constexpr B128 board_mask() { return B128{{0xffffffffu, 0xffffffffu, 0xffffffffu, 0x01ffffffu}}; }
+    // first / second edge of player p: P0 north(row 10) -> south(row 0); P1 west(col 0) -> east(col 10)
+    __device__ static B128 first_edge(int p) {
+        constexpr B128 n = row_mask(10), w = col_mask(0);
+        return p == 0 ? n : w;
+    }
+    __device__ static B128 second_edge(int p) {
+        constexpr B128 so = row_mask(0), e = col_mask(10);
+        return p == 0 ? so : e;
+    }
+
+    __device__ static int prepare(Shared &s, const mr_leaf &leaf, uint32_t lane) {
+        B128 st[2];
+        for (int pl = 0; pl < 2; ++pl) {
+            st[pl].w[0] = (uint32_t)leaf.board[2 * pl];
+            st[pl].w[1] = (uint32_t)(leaf.board[2 * pl] >> 32);
+            st[pl].w[2] = (uint32_t)leaf.board[2 * pl + 1];
+            st[pl].w[3] = (uint32_t)(leaf.board[2 * pl + 1] >> 32) & 0x01ffffffu;
+        }
+        constexpr B128 NC0 = inv(col_mask(0)), NC10 = inv(col_mask(10)), BM = board_mask();
+        B128 cn[2];
+        for (int pl = 0; pl < 2; ++pl) cn[pl] = flood(first_edge(pl), st[pl], NC0, NC10, BM);
+        const B128 occ = bor(st[0], st[1]);
+        const uint32_t n_occ = __popc(occ.w[0]) + __popc(occ.w[1]) + __popc(occ.w[2]) + __popc(occ.w[3]);
+        if (lane == 0) {
+            s.stones[0] = st[0];
+            s.stones[1] = st[1];
+            s.conn[0] = cn[0];
+            s.conn[1] = cn[1];
+            s.turn = leaf.turn;
+            s.n_empty = 121 - n_occ;
+        }
+        // :130-144 only the player who moved last is checked
+        const int last = (leaf.turn + 1) & 1;
+        if (any(band(cn[last], second_edge(last)))) return last ? MR_WINNER_P1 : MR_WINNER_P0;
+        if (n_occ == 121) return MR_DRAW; // :208-215 no winner and no actions
+        return MR_NOT_TERMINAL;
+    }
+    __device__ void reset(const Shared &s) {
+        stones[0] = s.stones[0];
+        stones[1] = s.stones[1];
+        conn[0] = s.conn[0];
+        conn[1] = s.conn[1];
+        n_empty = s.n_empty;
+    }
+
+    template <int POLICY, int PARITY>
+    __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action) {
+        const uint32_t mover = (s.turn ^ PARITY) & 1u;
+        if (n_empty == 0) return ST_DRAW; // cannot happen in Hex; kept for totality
+        // idx-th empty cell, ascending
+        uint32_t idx = mulhi(x0, n_empty);
+        const uint32_t e0 = ~(stones[0].w[0] | stones[1].w[0]);
+        const uint32_t e1 = ~(stones[0].w[1] | stones[1].w[1]);
+        const uint32_t e2 = ~(stones[0].w[2] | stones[1].w[2]);
+        const uint32_t e3 = ~(stones[0].w[3] | stones[1].w[3]) & 0x01ffffffu;
+        const uint32_t c0 = __popc(e0), c1 = __popc(e1), c2 = __popc(e2);
+        uint32_t wsel = 0, word = e0;
+        if (idx >= c0) {
+            idx -= c0;
+            wsel = 1;
+            word = e1;
+            if (idx >= c1) {
+                idx -= c1;
+                wsel = 2;
+                word = e2;
+                if (idx >= c2) {
+                    idx -= c2;
+                    wsel = 3;
+                    word = e3;
+                }
+            }
+        }
+        const uint32_t bitpos = select32(word, idx);
+        const uint32_t cell = wsel * 32u + bitpos;
+        action = cell;
+        const uint32_t b = 1u << bitpos;
+        B128 mv = zero();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mv.w[q] = (wsel == (uint32_t)q) ? b : 0u;
+        --n_empty;
+        constexpr B128 NC0 = inv(col_mask(0)), NC10 = inv(col_mask(10)), BM = board_mask();
+        // mover-specific update (both branches are the same code on different registers)
+        bool won;
+        if (mover == 0) {
+            stones[0] = bor(stones[0], mv);
+            won = grow(0, mv, NC0, NC10, BM);
+        } else {
+            stones[1] = bor(stones[1], mv);
+            won = grow(1, mv, NC0, NC10, BM);
+        }
+        if (won) return ST_MOVED | (mover ? ST_WIN_P1 : ST_WIN_P0);
+        if (n_empty == 0) return ST_MOVED | ST_DRAW;
+        return ST_MOVED;
+    }
+    // after the mover placed `mv`: extend conn[pl] if the stone touches it (or lies on the first edge)
+    __device__ bool grow(int pl, B128 mv, const B128 &NC0, const B128 &NC10, const B128 &BM) {
+        const B128 nb = neighbours(mv, NC0, NC10, BM);
+        const bool touches = any(band(nb, conn[pl])) || any(band(mv, first_edge(pl)));
+        if (touches) {
+            B128 f = bor(conn[pl], mv);
+            B128 frontier = mv;
+            for (;;) {
+                const B128 g = bandn(band(neighbours(frontier, NC0, NC10, BM), stones[pl]), f);
+                if (!any(g)) break;
+                f = bor(f, g);
+                frontier = g;
+            }
+            conn[pl] = f;
+            return any(band(f, second_edge(pl)));
+        }
+        return false;
+    }
+    __device__ void store_final(const Shared &s, mr_leaf *out, uint32_t plies, int end_code) const {
+        for (int pl = 0; pl < 2; ++pl) {
+            out->board[2 * pl] = mk64(stones[pl].w[0], stones[pl].w[1]);
+            out->board[2 * pl + 1] = mk64(stones[pl].w[2], stones[pl].w[3]);
+        }
+        out->turn = (uint8_t)((s.turn + plies) & 1);
+        out->flag = 0;
+        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+    }
+};
+
+} // namespace mr

@@ -1,0 +1,237 @@
+// rollout_kernel.cuh -- the persistent-warp playout kernel (sm_100a).
+//
+// Work decomposition
+//   task      = (leaf, chunk of `chunk` consecutive playout ids); a task never straddles leaves
+//   warp      = pulls tasks from a global atomic counter until the range is exhausted
+//   lane      = one playout at a time; lanes that finish pull the next playout id of the task at the
+//               next WINDOW boundary (a window = 4 plies = one Philox4x32 block), so all live lanes of a
+//               warp are always at the same ply phase: the Philox block is computed warp-synchronously and
+//               the mover's colour is a warp-uniform, compile-time-alternating quantity.
+//   reduction = per-lane counters -> warp REDUX -> one atomic set per task on results[leaf]
+//
+// Draw discipline (shared with the CPU oracle): word [ply & 3] of
+// Philox4x32-10(key = seed, ctr = (leaf_id, playout_id, ply >> 2, stream)); stream 0 = move choice,
+// stream 1 = epsilon test.
+#pragma once
+
+#include <type_traits>
+
+#include "games_device.cuh"
+
+namespace mr {
+
+__device__ __forceinline__ int end_code_to_outcome(int code) {
+    const int e = code & ST_END_MASK;
+    return e == ST_WIN_P0 ? MR_WINNER_P0 : (e == ST_WIN_P1 ? MR_WINNER_P1 : MR_DRAW);
+}
+
+// id of an action code in the dense per-game action space (MAST / AMAF tables)
+template <class G>
+__device__ __forceinline__ uint32_t action_index(uint32_t code) {
+    if (G::NA == 4096) return (code >> 8) * 64u + (code & 0xffu);
+    return code;
+}
+
+template <class G, int POLICY, int FLAGS>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const KernelParams p) {
+    constexpr bool WANT_AMAF = (FLAGS & MR_WANT_AMAF) != 0;
+    constexpr bool WANT_MAST = (FLAGS & MR_WANT_MAST_DELTA) != 0;
+    constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
+    constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
+    constexpr bool NEED_SCRATCH = WANT_AMAF || WANT_MAST;
+
+    __shared__ __align__(16) mr_leaf s_leaf[WARPS_PER_BLOCK];
+    __shared__ typename G::Shared s_game[WARPS_PER_BLOCK];
+
+    const uint32_t lane = lane_id();
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
+    typename G::Shared &sh = s_game[warp];
+    uint16_t *scratch = NEED_SCRATCH ? p.trace_scratch + (size_t)gwarp * p.trace_cap * 32u : nullptr;
+
+    for (;;) {
+        // ---- next task ----
+        uint32_t task = 0;
+        if (lane == 0) task = p.task_begin + atomicAdd(p.task_counter, 1u);
+        task = __shfl_sync(FULL_MASK, task, 0);
+        if (task >= p.task_end) break;
+        const uint32_t li = task / p.chunks_per_leaf;
+        const uint32_t ci = task - li * p.chunks_per_leaf;
+        const uint32_t pid_begin = ci * p.chunk;
+        const uint32_t pid_end = min(pid_begin + p.chunk, p.k);
+        const uint32_t leaf_id = p.leaf_id_base + li;
+
+        // ---- stage the leaf record in shared memory (one coalesced 40-byte read per warp) ----
+        __syncwarp();
+        if (lane < sizeof(mr_leaf) / 4)
+            reinterpret_cast<uint32_t *>(&s_leaf[warp])[lane] = reinterpret_cast<const uint32_t *>(p.leaves + li)[lane];
+        __syncwarp();
+        const int leaf_status = G::prepare(sh, s_leaf[warp], lane);
+        __syncwarp();
+        const uint32_t leaf_turn = s_leaf[warp].turn;
+
+        uint32_t acc_w0 = 0, acc_w1 = 0, acc_draw = 0, acc_cut = 0, acc_depth = 0;
+
+        if (leaf_status != MR_NOT_TERMINAL) {
+            // a terminal leaf: every playout is the zero-ply trial with the leaf's own status
+            // (simulate.rs:97-102); nothing is drawn
+            const uint32_t cnt = pid_end - pid_begin;
+            if (lane == 0) {
+                if (leaf_status == MR_WINNER_P0) acc_w0 = cnt;
+                else if (leaf_status == MR_WINNER_P1) acc_w1 = cnt;
+                else acc_draw = cnt;
+            }
+            if (WANT_TRACE || WANT_FINAL) {
+                for (uint32_t pid = pid_begin + lane; pid < pid_end; pid += 32) {
+                    const size_t g = (size_t)li * p.k + pid;
+                    if (WANT_TRACE && p.rec) {
+                        mr_playout_record r;
+                        r.depth = 0;
+                        r.outcome = (uint8_t)leaf_status;
+                        r.end_type = MR_END_TERMINAL;
+                        r.pad[0] = r.pad[1] = 0;
+                        p.rec[g] = r;
+                    }
+                    if (WANT_FINAL && p.final_state) p.final_state[g] = s_leaf[warp];
+                }
+            }
+        } else {
+            G st;
+            uint32_t pid = pid_begin + lane;
+            uint32_t next_pid = pid_begin + 32;
+            bool idle = pid >= pid_end;
+            bool alive = !idle;
+            uint32_t depth = 0, win = 0;
+            int end_code = 0;
+            bool cutoff = false;
+            st.reset(sh);
+
+            for (;;) {
+                uint32_t r0[4], r1[4] = {0, 0, 0, 0};
+                philox4x32_10(leaf_id, pid, win, 0u, p.seed_lo, p.seed_hi, r0);
+                if (POLICY == MR_EPS_MAST) philox4x32_10(leaf_id, pid, win, 1u, p.seed_lo, p.seed_hi, r1);
+                // one ply; J is the ply's phase inside the window, so the mover's colour (leaf turn ^ (J & 1))
+                // and the Philox word index are compile-time per call site
+                auto ply = [&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    if (alive) {
+                        if (depth >= p.max_depth) { // simulate.rs:104-108 TurnLimit
+                            alive = false;
+                            cutoff = true;
+                            end_code = ST_DRAW;
+                        } else {
+                            uint32_t action = 0;
+                            const int code = st.template step<POLICY, (j & 1)>(sh, r0[j], r1[j], p, action);
+                            if (code & ST_MOVED) {
+                                if (WANT_TRACE && p.trace) {
+                                    if (depth < p.max_trace)
+                                        p.trace[((size_t)li * p.k + pid) * p.max_trace + depth] = (uint16_t)action;
+                                }
+                                if (NEED_SCRATCH) {
+                                    if (depth < p.trace_cap) scratch[depth * 32u + lane] = (uint16_t)action;
+                                }
+                                ++depth;
+                            }
+                            if (code & ST_END_MASK) {
+                                alive = false;
+                                end_code = code & ST_END_MASK;
+                            }
+                        }
+                    }
+                };
+                ply(std::integral_constant<int, 0>{});
+                ply(std::integral_constant<int, 1>{});
+                ply(std::integral_constant<int, 2>{});
+                ply(std::integral_constant<int, 3>{});
+                ++win;
+
+                // ---- window boundary: retire finished playouts, hand out new playout ids ----
+                const bool fin = !alive && !idle;
+                const uint32_t fin_mask = __ballot_sync(FULL_MASK, fin);
+                if (fin_mask) {
+                    if (fin) {
+                        const int e = end_code;
+                        acc_w0 += (e == ST_WIN_P0);
+                        acc_w1 += (e == ST_WIN_P1);
+                        acc_draw += (e == ST_DRAW || e == ST_NO_ACTIONS);
+                        acc_cut += cutoff;
+                        acc_depth += depth;
+                        const size_t g = (size_t)li * p.k + pid;
+                        if (WANT_TRACE && p.rec) {
+                            mr_playout_record r;
+                            r.depth = depth;
+                            r.outcome = (uint8_t)end_code_to_outcome(e);
+                            r.end_type = (uint8_t)(cutoff ? MR_END_TURN_LIMIT
+                                                          : (e == ST_NO_ACTIONS ? MR_END_NO_ACTIONS : MR_END_TERMINAL));
+                            r.pad[0] = r.pad[1] = 0;
+                            p.rec[g] = r;
+                        }
+                        if (WANT_FINAL && p.final_state) st.store_final(sh, &p.final_state[g], depth, e);
+                    }
+                    if (NEED_SCRATCH) {
+                        // cooperative flush: for every finished lane f, all 32 lanes walk f's trace.
+                        // every (action, player) occurrence: visits += 1, score += utilities[player]
+                        // (backprop.rs:619-640 GRAVE, :857-870 GLOBAL/MAST)
+                        __syncwarp();
+                        for (uint32_t m = fin_mask; m; m &= m - 1) {
+                            const int f = __ffs(m) - 1;
+                            const uint32_t d_f = __shfl_sync(FULL_MASK, depth, f);
+                            const int e_f = __shfl_sync(FULL_MASK, end_code, f);
+                            const int u_p0 = e_f == ST_WIN_P0 ? 1 : (e_f == ST_WIN_P1 ? -1 : 0);
+                            for (uint32_t t = lane; t < d_f; t += 32) {
+                                const uint32_t a = action_index<G>(scratch[t * 32u + f]);
+                                const uint32_t pl = (leaf_turn + t) & 1u;
+                                const int u = pl == 0 ? u_p0 : -u_p0;
+                                if (WANT_AMAF && p.amaf) {
+                                    mr_action_stat *e = p.amaf + ((size_t)li * 2 + pl) * G::NA + a;
+                                    atomicAdd(&e->visits, 1u);
+                                    if (u) atomicAdd(&e->score, u);
+                                }
+                                if (WANT_MAST && p.mast_delta) {
+                                    mr_action_stat *e = p.mast_delta + (size_t)pl * G::NA + a;
+                                    atomicAdd(&e->visits, 1u);
+                                    if (u) atomicAdd(&e->score, u);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    const uint32_t rank = __popc(fin_mask & lanemask_lt());
+                    if (fin) {
+                        const uint32_t np = next_pid + rank;
+                        if (np < pid_end) {
+                            pid = np;
+                            st.reset(sh);
+                            alive = true;
+                            depth = 0;
+                            win = 0;
+                            end_code = 0;
+                            cutoff = false;
+                        } else {
+                            idle = true;
+                        }
+                    }
+                    next_pid += __popc(fin_mask);
+                    if (__all_sync(FULL_MASK, idle)) break;
+                }
+            }
+        }
+
+        // ---- one atomic set per task ----
+        acc_w0 = __reduce_add_sync(FULL_MASK, acc_w0);
+        acc_w1 = __reduce_add_sync(FULL_MASK, acc_w1);
+        acc_draw = __reduce_add_sync(FULL_MASK, acc_draw);
+        acc_cut = __reduce_add_sync(FULL_MASK, acc_cut);
+        acc_depth = __reduce_add_sync(FULL_MASK, acc_depth);
+        if (lane == 0) {
+            mr_leaf_result *r = p.results + li;
+            if (acc_w0) atomicAdd(&r->wins[0], acc_w0);
+            if (acc_w1) atomicAdd(&r->wins[1], acc_w1);
+            if (acc_draw) atomicAdd(&r->draws, acc_draw);
+            if (acc_cut) atomicAdd(&r->cutoffs, acc_cut);
+            if (acc_depth) atomicAdd(reinterpret_cast<unsigned long long *>(&r->sum_depth), (unsigned long long)acc_depth);
+        }
+    }
+}
+
+} // namespace mr

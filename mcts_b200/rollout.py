@@ -1,0 +1,379 @@
+"""Host-side mirror of the reference's simulation plug-in surface, over the C ABI.
+
+Reference interface mirrored (thomasmarsh/mcts, paths relative to the reference root):
+  * `SimulateStrategy<G>::playout(state, max_playout_depth, &TreeStats, prev_action, rng) -> Trial<G>`
+    and `backprop_flags()`                       mcts/src/strategies/mcts/simulate.rs:48-155
+  * the strategies in scope: `Uniform` (:157-216), `EpsilonGreedy<G, Mast>` (:485-570, :819-848),
+    `DecisiveMove<G, Uniform>` Win mode (:573-760)
+  * `Trial { actions, state, status.end_type, depth, terminal }`            simulate.rs:15-46
+  * `TreeSearch::simulate_many` (k playouts of one leaf)                    search/core.rs:218-258
+  * `TreeStats.player_actions` (the MAST table) and its writer             search/shared.rs:85-94, backprop.rs:857-870
+
+The reference is Rust and no Rust toolchain exists in this image, so the host side above the C ABI is
+written in Python (and C++ for the tree driver); INTEGRATION.md shows the Rust binding a maintainer
+would add.  Everything here runs on the GPU through libmcts_b200.so -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from enum import IntEnum
+
+import numpy as np
+
+from . import _lib
+from ._lib import LEAF_DTYPE, RECORD_DTYPE, RESULT_DTYPE, STAT_DTYPE, BatchDesc, RolloutError, ptr
+
+
+class Game(IntEnum):
+    CONNECT4 = 0
+    BREAKTHROUGH = 1
+    KNIGHTTHROUGH = 2
+    OTHELLO = 3
+    HEX11 = 4
+
+
+class Policy(IntEnum):
+    UNIFORM = 0
+    EPS_MAST = 1
+    DECISIVE_WIN = 2
+
+
+class Outcome(IntEnum):  # TerminalStatus (mcts/src/game.rs:117-122)
+    NOT_TERMINAL = 0
+    DRAW = 1
+    WINNER_P0 = 2
+    WINNER_P1 = 3
+
+
+class EndType(IntEnum):  # simulate.rs:15-20 (+ the no-actions ending, :112-116)
+    NATURAL_END = 0
+    TURN_LIMIT = 1
+    NO_ACTIONS = 2
+
+
+WANT_AMAF, WANT_MAST_DELTA, WANT_TRACE, WANT_FINAL_STATE = 1, 2, 4, 8
+
+# BackpropFlags bits (mcts/src/strategies/mcts/config.rs:11-30)
+BACKPROP_GRAVE, BACKPROP_GLOBAL, BACKPROP_AMAF = 1, 2, 4
+
+OTHELLO_PASS = 64
+_INITIAL = {
+    Game.CONNECT4: ((0, 0, 0, 0), 0, 0),
+    Game.BREAKTHROUGH: ((0xFFFF000000000000, 0xFFFF, 0, 0), 0, 0),  # breakthrough/lib.rs:64-82
+    Game.KNIGHTTHROUGH: ((0xFFFF000000000000, 0xFFFF, 0, 0), 0, 0),
+    Game.OTHELLO: (((1 << 28) | (1 << 35), (1 << 27) | (1 << 36), 0, 0), 0, 0),  # othello/lib.rs:10-11
+    Game.HEX11: ((0, 0, 0, 0), 0, 0),
+}
+
+
+def make_leaf(board, turn=0, flag=0) -> np.ndarray:
+    """One 40-byte leaf record (include/mcts_rollout.h mr_leaf)."""
+    s = np.zeros(1, dtype=LEAF_DTYPE)
+    b = list(board) + [0] * (4 - len(board))
+    s["board"][0] = np.array(b, dtype=np.uint64)
+    s["turn"] = turn
+    s["flag"] = flag
+    return s
+
+
+def initial_state(game: Game) -> np.ndarray:
+    board, turn, flag = _INITIAL[Game(game)]
+    return make_leaf(board, turn, flag)
+
+
+def num_actions(game: Game) -> int:
+    return _lib.load().mr_num_actions(int(game))
+
+
+# ---- the strategy objects: same names and knobs as the reference ----
+
+
+@dataclass(frozen=True)
+class Uniform:
+    """simulate.rs:157-216"""
+
+    policy = Policy.UNIFORM
+
+    def backprop_flags(self) -> int:
+        return 0
+
+
+@dataclass(frozen=True)
+class EpsilonGreedyMast:
+    """EpsilonGreedy<G, Mast> (simulate.rs:485-570 wrapping :819-848); epsilon default 0.1 (:525)."""
+
+    epsilon: float = 0.1
+    policy = Policy.EPS_MAST
+
+    def backprop_flags(self) -> int:
+        return BACKPROP_GLOBAL  # Mast::backprop_flags (simulate.rs:826-828)
+
+
+@dataclass(frozen=True)
+class DecisiveMoveWin:
+    """DecisiveMove<G, Uniform> with DecisiveMoveMode::Win (simulate.rs:573-760)."""
+
+    policy = Policy.DECISIVE_WIN
+
+    def backprop_flags(self) -> int:
+        return 0
+
+
+class MastTable:
+    """TreeStats.player_actions as a dense [2][num_actions] (visits, score) table
+    (search/shared.rs:88, node.rs:51-55).  `update` is the GLOBAL write of backprop.rs:857-870 applied
+    to a batch's aggregated delta."""
+
+    def __init__(self, game: Game):
+        self.game = Game(game)
+        self.table = np.zeros((2, num_actions(game)), dtype=STAT_DTYPE)
+
+    def update(self, delta: np.ndarray) -> None:
+        self.table["visits"] += delta["visits"]
+        self.table["score"] += delta["score"]
+
+
+@dataclass
+class Trial:
+    """simulate.rs:27-46"""
+
+    actions: list  # [(action code, player index)]
+    state: np.ndarray  # final leaf record
+    end_type: EndType
+    depth: int
+    terminal: Outcome  # NOT_TERMINAL for TurnLimit / no-actions endings (scored as a draw)
+
+
+@dataclass
+class BatchResult:
+    results: np.ndarray  # RESULT_DTYPE [n_leaves]
+    amaf: np.ndarray | None = None  # STAT_DTYPE [n_leaves][2][NA]
+    mast_delta: np.ndarray | None = None  # STAT_DTYPE [2][NA]
+    trace: np.ndarray | None = None  # u16 [n_leaves*k][max_trace]
+    records: np.ndarray | None = None  # RECORD_DTYPE [n_leaves*k]
+    final: np.ndarray | None = None  # LEAF_DTYPE [n_leaves*k]
+    kernel_ms: float = 0.0
+
+    def utilities_sum(self) -> np.ndarray:
+        """Per leaf, per player: sum of utilities = wins[p] - losses[p] (node.rs:673-681 aggregated)."""
+        r = self.results
+        k = r["wins"][:, 0].astype(np.int64) + r["wins"][:, 1] + r["draws"]
+        w = r["wins"].astype(np.int64)
+        return w - (k[:, None] - r["draws"].astype(np.int64)[:, None] - w)
+
+
+@dataclass
+class _Pending:
+    desc: BatchDesc
+    keep: list = field(default_factory=list)
+
+
+class GpuRollout:
+    """Drop-in for the CPU playout path: `SimulateStrategy` for one game, on one or more B200s.
+
+    `simulate_many` replaces TreeSearch::simulate_many for a whole batch of leaves;
+    `playout` is the single-trial form with the reference's argument meaning.
+    """
+
+    def __init__(self, game: Game, strategy=None, *, devices: list[int] | int = 1, seed: int = 0, max_playout_depth: int = 0):
+        self.lib = _lib.load()
+        self.game = Game(game)
+        self.strategy = strategy if strategy is not None else Uniform()
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.max_playout_depth = int(max_playout_depth)  # 0 = unlimited (config.rs:440 default usize::MAX)
+        if isinstance(devices, int):
+            ids, n = None, devices
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            ids, n = arr, len(devices)
+        h = C.c_void_p()
+        rc = self.lib.mr_init(ids, n, C.byref(h))
+        if rc != 0:
+            raise RolloutError(rc, self.lib.mr_last_error(None).decode())
+        self._h = h
+        self._pending: dict[int, _Pending] = {}
+        self.na = self.lib.mr_num_actions(int(self.game))
+
+    # -- lifecycle --
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.mr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise RolloutError(rc, self.lib.mr_last_error(self._h).decode())
+
+    # -- reference-shaped interface --
+    def backprop_flags(self) -> int:
+        return self.strategy.backprop_flags()
+
+    def _desc(self, n_leaves, k, flags, seed, leaf_id_base, max_trace, max_depth) -> BatchDesc:
+        return BatchDesc(
+            int(self.game),
+            int(self.strategy.policy),
+            n_leaves,
+            k,
+            self.max_playout_depth if max_depth is None else int(max_depth),
+            flags,
+            self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF,
+            leaf_id_base,
+            max_trace,
+            float(getattr(self.strategy, "epsilon", 0.0)),
+        )
+
+    def submit(
+        self,
+        leaves: np.ndarray,
+        k: int,
+        *,
+        slot: int = 0,
+        stats: MastTable | np.ndarray | None = None,
+        want_amaf=False,
+        want_mast_delta=False,
+        want_trace=False,
+        want_final=False,
+        max_trace: int = 0,
+        seed: int | None = None,
+        leaf_id_base: int = 0,
+        max_playout_depth: int | None = None,
+    ) -> None:
+        leaves = np.ascontiguousarray(leaves, dtype=LEAF_DTYPE).reshape(-1)
+        flags = (
+            (WANT_AMAF if want_amaf else 0)
+            | (WANT_MAST_DELTA if want_mast_delta else 0)
+            | (WANT_TRACE if want_trace else 0)
+            | (WANT_FINAL_STATE if want_final else 0)
+        )
+        d = self._desc(len(leaves), int(k), flags, seed, leaf_id_base, max_trace if want_trace else 0, max_playout_depth)
+        mast = None
+        if stats is not None:
+            mast = np.ascontiguousarray(stats.table if isinstance(stats, MastTable) else stats, dtype=STAT_DTYPE)
+            if mast.shape != (2, self.na):
+                raise ValueError(f"MAST table must have shape (2, {self.na})")
+        self._check(self.lib.mr_submit(self._h, slot, C.byref(d), ptr(leaves), ptr(mast)))
+        self._pending[slot] = _Pending(d, [leaves, mast])
+
+    def wait(self, slot: int = 0) -> BatchResult:
+        pend = self._pending.pop(slot, None)
+        if pend is None:
+            raise RuntimeError(f"slot {slot} has no batch in flight")
+        d = pend.desc
+        n, k = d.n_leaves, d.playouts_per_leaf
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        amaf = np.zeros((n, 2, self.na), dtype=STAT_DTYPE) if d.flags & WANT_AMAF else None
+        delta = np.zeros((2, self.na), dtype=STAT_DTYPE) if d.flags & WANT_MAST_DELTA else None
+        trace = np.zeros((n * k, d.max_trace), dtype=np.uint16) if d.flags & WANT_TRACE else None
+        rec = np.zeros(n * k, dtype=RECORD_DTYPE) if d.flags & WANT_TRACE else None
+        final = np.zeros(n * k, dtype=LEAF_DTYPE) if d.flags & WANT_FINAL_STATE else None
+        self._check(self.lib.mr_wait(self._h, slot, ptr(res), ptr(amaf), ptr(delta), ptr(trace), ptr(rec), ptr(final)))
+        ms = C.c_float()
+        self.lib.mr_last_kernel_ms(self._h, slot, C.byref(ms))
+        return BatchResult(res, amaf, delta, trace, rec, final, ms.value)
+
+    def simulate_many(self, leaves: np.ndarray, k: int, **kw) -> BatchResult:
+        """k playouts of every leaf (search/core.rs:218-258 for a batch of leaves)."""
+        self.submit(leaves, k, slot=0, **kw)
+        return self.wait(0)
+
+    def playout(
+        self,
+        state: np.ndarray,
+        max_playout_depth: int | None = None,
+        stats: MastTable | np.ndarray | None = None,
+        prev_action=None,
+        rng: tuple[int, int, int] | None = None,
+    ) -> Trial:
+        """One playout with the reference's argument meaning (simulate.rs:84-91).
+
+        `prev_action` is accepted and ignored, as every in-scope strategy ignores it.  `rng` names the
+        counter-based stream instead of carrying a SmallRng: (seed, leaf_id, playout_id).
+        """
+        seed, leaf_id, playout_id = rng if rng is not None else (self.seed, 0, 0)
+        depth_cap = self.max_playout_depth if max_playout_depth is None else int(max_playout_depth)
+        # playout ids are 0..k-1 inside a batch; run k = playout_id + 1 and keep the last
+        max_trace = depth_cap if depth_cap else 512
+        r = self.simulate_many(
+            state,
+            playout_id + 1,
+            stats=stats,
+            want_trace=True,
+            want_final=True,
+            max_trace=max_trace,
+            seed=seed,
+            leaf_id_base=leaf_id,
+            max_playout_depth=depth_cap,
+        )
+        rec = r.records[playout_id]
+        depth = int(rec["depth"])
+        turn0 = int(np.asarray(state).reshape(-1)[0]["turn"])
+        actions = [(int(a), (turn0 + t) & 1) for t, a in enumerate(r.trace[playout_id][:depth])]
+        end = EndType(int(rec["end_type"]))
+        terminal = Outcome(int(rec["outcome"])) if end == EndType.NATURAL_END else Outcome.NOT_TERMINAL
+        return Trial(actions, r.final[playout_id : playout_id + 1].copy(), end, depth, terminal)
+
+    # -- device-resident path and measurement helpers --
+    def set_mast(self, stats: MastTable | np.ndarray) -> None:
+        mast = np.ascontiguousarray(stats.table if isinstance(stats, MastTable) else stats, dtype=STAT_DTYPE)
+        self._check(self.lib.mr_set_mast(self._h, int(self.game), ptr(mast)))
+
+    def launch_device(
+        self, d_leaves: int, d_results: int, n_leaves: int, k: int, *, stream: int = 0, device_index: int = 0,
+        d_amaf: int = 0, d_mast_delta: int = 0, seed: int | None = None, leaf_id_base: int = 0,
+        max_playout_depth: int | None = None,
+    ) -> None:
+        """Launch on caller-owned DEVICE buffers (raw pointers) on `stream` (raw cudaStream_t); nothing is copied."""
+        flags = (WANT_AMAF if d_amaf else 0) | (WANT_MAST_DELTA if d_mast_delta else 0)
+        d = self._desc(n_leaves, k, flags, seed, leaf_id_base, 0, max_playout_depth)
+        self._check(
+            self.lib.mr_launch_device(
+                self._h, device_index, C.byref(d), C.c_void_p(d_leaves), C.c_void_p(d_results),
+                C.c_void_p(d_amaf) if d_amaf else None, C.c_void_p(d_mast_delta) if d_mast_delta else None,
+                C.c_void_p(stream) if stream else None,
+            )
+        )
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.mr_kernel_launches(self._h))
+
+    def measure_int_peak(self, kind: int = 0, device_index: int = 0) -> tuple[float, float]:
+        ops, mhz = C.c_double(), C.c_double()
+        self._check(self.lib.mr_measure_int_peak(self._h, device_index, kind, C.byref(ops), C.byref(mhz)))
+        return ops.value, mhz.value
+
+    def random_positions(self, plies: int, n: int, *, seed: int = 0) -> np.ndarray:
+        """`n` synthetic non-terminal positions after `plies` uniformly random plies from the initial
+        position, generated ON THE GPU (a depth-cut playout's final state).  Games that end before
+        `plies` are replaced by the next playout ids, so the set is deterministic."""
+        out = np.zeros(n, dtype=LEAF_DTYPE)
+        if plies == 0:
+            out[:] = initial_state(self.game)
+            return out
+        saved = self.strategy
+        self.strategy = Uniform()
+        try:
+            k = max(64, int(n * 1.5) + 16)
+            r = self.simulate_many(
+                initial_state(self.game), k, want_trace=True, want_final=True, max_trace=1, seed=seed, max_playout_depth=plies
+            )
+        finally:
+            self.strategy = saved
+        ok = (r.records["end_type"] == EndType.TURN_LIMIT) & (r.records["depth"] == plies)
+        sel = r.final[ok]
+        if len(sel) < n:
+            raise RuntimeError(f"only {len(sel)} of {n} random positions survived {plies} plies; lower plies")
+        out[:] = sel[:n]
+        return out

@@ -118,9 +118,9 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
                       orc_leaf_result *results, orc_action_stat *amaf_out, orc_action_stat *mast_delta_out,
                       uint16_t *trace_out, orc_playout_record *rec_out, orc_state *final_out, int n_threads);
 
-/* Random-play openings: `plies` uniformly random plies from the initial position (draws from
- * stream 0 of leaf_id = index, playout 0); terminal-before-`plies` games are re-drawn with the
- * next playout id.  Used to build synthetic positions for tests and the CPU baseline. */
+/* Random-play openings: position j = final state of the j-th surviving uniform playout (leaf_id 0,
+ * playout ids 0,1,2,...) from the initial position cut at `plies` plies; playouts that end earlier are
+ * skipped.  Same definition as the product's GpuRollout.random_positions. */
 void orc_random_positions(int game, uint64_t seed, uint32_t plies, uint32_t n, orc_state *out);
 
 /* ---- restated reference TEST oracles (naive_ref.c) ---- */

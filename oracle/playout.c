@@ -315,6 +315,10 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
 }
 
 void orc_random_positions(int game, uint64_t seed, uint32_t plies, uint32_t n, orc_state *out) {
+    /* position j = final state of the j-th SURVIVING playout (leaf_id 0, playout ids 0,1,2,...) of a
+     * uniform playout from the initial position cut at `plies`; a playout that ends earlier is skipped.
+     * The product's GpuRollout.random_positions uses the same definition, so both arms of the bench
+     * see the same positions. */
     orc_batch_desc d;
     memset(&d, 0, sizeof d);
     d.game = game;
@@ -324,15 +328,15 @@ void orc_random_positions(int game, uint64_t seed, uint32_t plies, uint32_t n, o
     d.playouts_per_leaf = 1;
     orc_state init;
     orc_initial_state(game, &init);
-    for (uint32_t i = 0; i < n; ++i) {
-        for (uint32_t attempt = 0;; ++attempt) {
-            orc_playout_record rec;
-            orc_state fin;
-            orc_playout(&d, &init, i, attempt, NULL, NULL, &rec, &fin);
-            if (plies == 0 || (rec.end_type == ORC_END_TURN_LIMIT && rec.depth == plies)) {
-                out[i] = fin;
-                break;
-            }
+    uint32_t got = 0;
+    for (uint32_t pid = 0; got < n; ++pid) {
+        if (plies == 0) {
+            out[got++] = init;
+            continue;
         }
+        orc_playout_record rec;
+        orc_state fin;
+        orc_playout(&d, &init, 0, pid, NULL, NULL, &rec, &fin);
+        if (rec.end_type == ORC_END_TURN_LIMIT && rec.depth == plies) out[got++] = fin;
     }
 }

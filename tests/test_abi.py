@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol the
+header declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from mcts_b200 import build
+
+    build.build()
+    import mcts_b200
+
+    lib = mcts_b200.load()
+    header = (ROOT / "include" / "mcts_rollout.h").read_text()
+    declared = set(re.findall(r"\b(mr_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mr_ctx"}
+    assert declared == set(mcts_b200.EXPORTS), declared ^ set(mcts_b200.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.mr_abi_version() == 1
+    assert [lib.mr_num_actions(g) for g in range(5)] == [7, 4096, 4096, 65, 121]
+    assert lib.mr_num_actions(9) == 0
+
+
+def test_struct_layouts_match_header():
+    import mcts_b200
+    from mcts_b200._lib import BatchDesc
+
+    assert mcts_b200.LEAF_DTYPE.itemsize == 40
+    assert mcts_b200.RESULT_DTYPE.itemsize == 24
+    assert mcts_b200.STAT_DTYPE.itemsize == 8
+    assert mcts_b200.RECORD_DTYPE.itemsize == 8
+    assert C.sizeof(BatchDesc) == 48
+    assert BatchDesc.seed.offset == 24 and BatchDesc.epsilon.offset == 40
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    import mcts_b200
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the no-device path cannot be exercised")
+    with pytest.raises(mcts_b200.RolloutError) as e:
+        mcts_b200.GpuRollout(mcts_b200.Game.CONNECT4)
+    assert "MR_ERR_NO_DEVICE" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The oracle is test infrastructure: nothing under mcts_b200/ or include/ may import, link or name it."""
+    bad = []
+    for p in list((ROOT / "mcts_b200").rglob("*.py")) + list((ROOT / "mcts_b200" / "csrc").glob("*")) + list((ROOT / "include").glob("*")):
+        if p.is_file() and p.suffix in {".py", ".cu", ".cuh", ".h", ".cpp"}:
+            txt = p.read_text()
+            if re.search(r"oracle_lib|liboracle|oracle/|orc_", txt):
+                bad.append(str(p))
+    assert not bad, bad
+
+
+def test_initial_states_match_oracle():
+    import mcts_b200 as mb
+    import oracle_lib as o
+
+    for g in range(5):
+        assert mb.initial_state(mb.Game(g)).tobytes() == o.initial_state(g).tobytes()

@@ -1,0 +1,220 @@
+"""GPU parity: the CUDA path (through the C ABI, libmcts_b200.so) against the CPU oracle, bit-exact.
+
+Every playout is a pure function of (leaf state, seed, leaf id, playout id), so parity is checked per
+playout: identical move trace, identical end record (depth, outcome, end type), identical final state,
+and identical aggregated statistics.  Integer work: the bar is bit-exact.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as o
+
+pytestmark = pytest.mark.gpu
+
+mb = pytest.importorskip("mcts_b200")
+
+GAMES = [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO, o.HEX11]
+MAX_TRACE = {o.CONNECT4: 42, o.BREAKTHROUGH: 256, o.KNIGHTTHROUGH: 300, o.OTHELLO: 128, o.HEX11: 121}
+MID_PLIES = {o.CONNECT4: [0, 8, 16], o.BREAKTHROUGH: [0, 10, 30], o.KNIGHTTHROUGH: [0, 10, 30], o.OTHELLO: [0, 10, 50], o.HEX11: [0, 10, 60]}
+
+
+def _leaves(game, n_per=6, seed=11):
+    parts = [o.random_positions(game, seed + p, p, n_per if p else 1) for p in MID_PLIES[game]]
+    return np.concatenate(parts)
+
+
+def _strategy(policy, eps=0.1):
+    return {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(eps), o.DECISIVE_WIN: mb.DecisiveMoveWin()}[policy]
+
+
+def _compare(game, policy, leaves, k, *, seed, max_depth=0, mast=None, eps=0.1, leaf_id_base=0, amaf=False, delta=False, devices=1):
+    mt = MAX_TRACE[game] if not max_depth else max_depth
+    ref = o.playout_batch(
+        game, leaves, k, policy=policy, eps=eps, max_depth=max_depth, seed=seed, leaf_id_base=leaf_id_base, mast=mast,
+        want_trace=True, max_trace=mt, want_final=True, want_amaf=amaf, want_mast_delta=delta, threads=o.host_threads(),
+    )
+    with mb.GpuRollout(mb.Game(game), _strategy(policy, eps), seed=seed, max_playout_depth=max_depth, devices=devices) as g:
+        got = g.simulate_many(
+            leaves.view(mb.LEAF_DTYPE), k, stats=mast, want_trace=True, want_final=True, max_trace=mt,
+            want_amaf=amaf, want_mast_delta=delta, leaf_id_base=leaf_id_base,
+        )
+    name = o.GAME_NAMES[game]
+    assert (got.records["depth"] == ref["records"]["depth"]).all(), name
+    assert (got.records["outcome"] == ref["records"]["outcome"]).all(), name
+    assert (got.records["end_type"] == ref["records"]["end_type"]).all(), name
+    assert (got.trace == ref["trace"]).all(), name
+    assert got.final.tobytes() == ref["final"].tobytes(), name
+    assert got.results.tobytes() == ref["results"].tobytes(), name
+    if amaf:
+        assert got.amaf.tobytes() == ref["amaf"].tobytes(), name
+    if delta:
+        assert got.mast_delta.tobytes() == ref["mast_delta"].tobytes(), name
+    return got, ref
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_uniform_playouts_bit_exact(game):
+    leaves = _leaves(game)
+    got, _ = _compare(game, o.UNIFORM, leaves, 96, seed=0xC0FFEE + game)
+    r = got.results
+    assert ((r["wins"][:, 0] + r["wins"][:, 1] + r["draws"]) == 96).all()
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_uniform_ragged_k_and_leaf_id_base(game):
+    # k not a multiple of 32, a single leaf, a non-zero leaf id base
+    leaves = _leaves(game, n_per=1)[-1:]
+    _compare(game, o.UNIFORM, leaves, 37, seed=5, leaf_id_base=1000)
+    _compare(game, o.UNIFORM, leaves, 1, seed=6)
+
+
+@pytest.mark.parametrize("game", [o.KNIGHTTHROUGH, o.BREAKTHROUGH, o.CONNECT4])
+def test_depth_cutoff(game):
+    leaves = _leaves(game, n_per=3)
+    got, _ = _compare(game, o.UNIFORM, leaves, 40, seed=77, max_depth=9)
+    assert got.results["cutoffs"].sum() > 0
+
+
+def test_terminal_and_stuck_leaves():
+    # a won Connect4 leaf, a full-board draw-less leaf is impossible to script cheaply; use won + stuck
+    won = o.initial_state(o.CONNECT4)
+    for c in [0, 1, 0, 1, 0, 1, 0]:
+        won = o.apply(o.CONNECT4, won, c)
+    mixed = np.concatenate([won, o.initial_state(o.CONNECT4)])
+    got, _ = _compare(o.CONNECT4, o.UNIFORM, mixed, 33, seed=1)
+    assert got.results[0]["wins"][0] == 33 and got.results[0]["sum_depth"] == 0
+    # Breakthrough: side to move has no action but the game is not terminal => draw with depth 0
+    stuck = o.make_state([(1 << 8) | (1 << 1), 1 << 0], turn=0, flag=0)
+    got, _ = _compare(o.BREAKTHROUGH, o.UNIFORM, stuck, 5, seed=2)
+    assert got.results[0]["draws"] == 5
+    # Othello: double-pass terminal leaf and a leaf whose mover must pass
+    dp = o.make_state([1 << 0, 1 << 63], turn=1, flag=1)
+    _compare(o.OTHELLO, o.UNIFORM, dp, 4, seed=3)
+    must_pass = o.make_state([1 << 0, 1 << 63], turn=0, flag=0)
+    _compare(o.OTHELLO, o.UNIFORM, must_pass, 4, seed=3)
+
+
+def _random_mast(game, seed, density=0.6):
+    rng = np.random.default_rng(seed)
+    na = o.num_actions(game)
+    mast = np.zeros((2, na), dtype=o.STAT_DTYPE)
+    visited = rng.random((2, na)) < density
+    visits = rng.integers(1, 40, size=(2, na))
+    score = (rng.integers(0, 41, size=(2, na)) * 2 - 40) * visits // 40
+    mast["visits"] = np.where(visited, visits, 0)
+    mast["score"] = np.where(visited, np.clip(score, -visits, visits), 0)
+    return mast
+
+
+@pytest.mark.parametrize("game", [o.BREAKTHROUGH, o.KNIGHTTHROUGH])
+@pytest.mark.parametrize("eps", [0.1, 0.0, 1.0])
+def test_eps_mast_bit_exact(game, eps):
+    leaves = _leaves(game, n_per=3)
+    for density in (0.0, 0.5, 1.0):  # empty table (all ties), mixed, fully visited
+        mast = _random_mast(game, 42 + int(density * 10), density)
+        _compare(game, o.EPS_MAST, leaves, 40, seed=9 + int(eps * 10), mast=mast, eps=eps, max_depth=200, delta=True)
+
+
+def test_mast_delta_feeds_next_batch():
+    """Two batches with the table updated in between (backprop.rs:857-870), GPU and oracle in lockstep."""
+    game = o.BREAKTHROUGH
+    leaves = _leaves(game, n_per=2)
+    mast = np.zeros((2, o.num_actions(game)), dtype=o.STAT_DTYPE)
+    for it in range(3):
+        got, ref = _compare(game, o.EPS_MAST, leaves, 64, seed=100 + it, mast=mast, max_depth=200, delta=True)
+        mast["visits"] += got.mast_delta["visits"]
+        mast["score"] += got.mast_delta["score"]
+    assert mast["visits"].sum() > 0
+
+
+@pytest.mark.parametrize("game", [o.HEX11, o.CONNECT4, o.OTHELLO])
+def test_amaf_tables_bit_exact(game):
+    leaves = _leaves(game, n_per=2)
+    got, _ = _compare(game, o.UNIFORM, leaves, 48, seed=31, amaf=True)
+    # occurrences == plies: every ply contributes one (action, player) visit
+    assert got.amaf["visits"].sum() == got.results["sum_depth"].sum()
+
+
+@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4])
+def test_decisive_win_bit_exact(game):
+    leaves = _leaves(game, n_per=4)
+    if game == o.OTHELLO:  # late positions, where the 64th-disc case can occur
+        leaves = np.concatenate([leaves, o.random_positions(game, 5, 56, 8)])
+    _compare(game, o.DECISIVE_WIN, leaves, 64, seed=17)
+
+
+def test_reference_shaped_playout_call():
+    """SimulateStrategy::playout(state, max_playout_depth, stats, prev_action, rng) -> Trial"""
+    game = o.CONNECT4
+    s = o.initial_state(game)
+    ref = o.playout_batch(game, s, 3, seed=99, leaf_id_base=7, want_trace=True, max_trace=42, want_final=True)
+    with mb.GpuRollout(mb.Game.CONNECT4, mb.Uniform()) as g:
+        t = g.playout(s.view(mb.LEAF_DTYPE), rng=(99, 7, 2))
+    rec = ref["records"][2]
+    assert t.depth == rec["depth"] and t.end_type == mb.EndType.NATURAL_END
+    assert [a for a, _ in t.actions] == [int(x) for x in ref["trace"][2][: t.depth]]
+    assert [p for _, p in t.actions] == [i & 1 for i in range(t.depth)]
+    assert t.state.tobytes() == ref["final"][2:3].tobytes()
+    assert int(t.terminal) == rec["outcome"]
+
+
+def test_double_buffered_slots_and_errors():
+    game = o.HEX11
+    a, b = _leaves(game, n_per=2), _leaves(game, n_per=3, seed=5)
+    with mb.GpuRollout(mb.Game.HEX11, seed=3) as g:
+        g.submit(a.view(mb.LEAF_DTYPE), 32, slot=0)
+        g.submit(b.view(mb.LEAF_DTYPE), 32, slot=1, leaf_id_base=500)
+        with pytest.raises(mb.RolloutError) as e:
+            g.submit(a.view(mb.LEAF_DTYPE), 32, slot=0)
+        assert "MR_ERR_BUSY" in str(e.value)
+        r1, r0 = g.wait(1), g.wait(0)
+        assert r0.results.tobytes() == o.playout_batch(game, a, 32, seed=3)["results"].tobytes()
+        assert r1.results.tobytes() == o.playout_batch(game, b, 32, seed=3, leaf_id_base=500)["results"].tobytes()
+        assert g.kernel_launches() == 2
+    with mb.GpuRollout(mb.Game.HEX11, mb.EpsilonGreedyMast()) as g:
+        with pytest.raises(mb.RolloutError) as e:
+            g.simulate_many(a.view(mb.LEAF_DTYPE), 4)
+        assert "MR_ERR_UNSUPPORTED" in str(e.value)
+    with mb.GpuRollout(mb.Game.KNIGHTTHROUGH, mb.Uniform()) as g:
+        with pytest.raises(mb.RolloutError) as e:  # unbounded playouts cannot carry a MAST delta
+            g.simulate_many(mb.initial_state(mb.Game.KNIGHTTHROUGH), 4, want_mast_delta=True)
+        assert "MR_ERR_INVALID" in str(e.value)
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_full_size_properties(game):
+    """At bench size the oracle is too slow to replay everything; check size-independent properties and
+    replay a random sample of leaves bit-exactly."""
+    n, k = 1024, 1024
+    with mb.GpuRollout(mb.Game(game), seed=2024) as g:
+        leaves = g.random_positions(MID_PLIES[game][1], n, seed=1)
+        assert leaves.tobytes() == o.random_positions(game, 1, MID_PLIES[game][1], n).tobytes()
+        r = g.simulate_many(leaves, k)
+        r2 = g.simulate_many(leaves, k)
+    res = r.results
+    assert res.tobytes() == r2.results.tobytes()  # idempotent: no hidden state between batches
+    assert ((res["wins"][:, 0].astype(np.int64) + res["wins"][:, 1] + res["draws"]) == k).all()
+    assert res["cutoffs"].sum() == 0
+    if game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.HEX11):
+        assert res["draws"].sum() <= (5 if game != o.HEX11 else 0)  # no draws in Hex; stuck positions are rare
+    sample = np.random.default_rng(0).choice(n, size=6, replace=False)
+    for i in sample:
+        ref = o.playout_batch(game, leaves[i : i + 1].view(o.STATE_DTYPE), k, seed=2024, leaf_id_base=int(i), threads=o.host_threads())
+        assert ref["results"][0].tobytes() == res[i].tobytes(), (o.GAME_NAMES[game], i)
+
+
+def test_win_rate_agrees_with_independent_cpu_rollouts():
+    """Root-child win rates from GPU playouts vs CPU oracle playouts drawn with a DIFFERENT seed agree
+    within a Wilson 99.9% interval (mcts-bench/src/tournament.rs:98-111)."""
+    game = o.CONNECT4
+    root = o.initial_state(game)
+    children = np.concatenate([o.apply(game, root, c) for c in range(7)])
+    k = 20000
+    with mb.GpuRollout(mb.Game.CONNECT4, seed=1) as g:
+        got = g.simulate_many(children.view(mb.LEAF_DTYPE), k).results
+    ref = o.playout_batch(game, children, k, seed=2, threads=o.host_threads())["results"]
+    z = 3.29
+    for c in range(7):
+        p1, p2 = got[c]["wins"][0] / k, ref[c]["wins"][0] / k
+        se = np.sqrt(p1 * (1 - p1) / k + p2 * (1 - p2) / k)
+        assert abs(p1 - p2) < z * se + 1e-9, (c, p1, p2)
