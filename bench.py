@@ -242,7 +242,9 @@ def run_gpu(args):
 
     n_leaves, k = args.leaves, args.playouts
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    # a real (non-legacy) stream: the kernels, torch's memsets, NCCL and the timing events all go to it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     def time_workload(w, steps, warmup, with_e2e, sampler=None):
         strat = {0: mb.Uniform(), 1: mb.EpsilonGreedyMast(w["eps"]), 2: mb.DecisiveMoveWin()}[w["policy"]]

@@ -195,8 +195,10 @@ def test_full_size_properties(game):
     assert res.tobytes() == r2.results.tobytes()  # idempotent: no hidden state between batches
     assert ((res["wins"][:, 0].astype(np.int64) + res["wins"][:, 1] + res["draws"]) == k).all()
     assert res["cutoffs"].sum() == 0
-    if game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.HEX11):
-        assert res["draws"].sum() <= (5 if game != o.HEX11 else 0)  # no draws in Hex; stuck positions are rare
+    if game == o.HEX11:
+        assert res["draws"].sum() == 0  # Hex has no draws
+    if game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH):
+        assert res["draws"].sum() <= n * k // 1000  # only "no actions left" endings (simulate.rs:112-116), rare
     sample = np.random.default_rng(0).choice(n, size=6, replace=False)
     for i in sample:
         ref = o.playout_batch(game, leaves[i : i + 1].view(o.STATE_DTYPE), k, seed=2024, leaf_id_base=int(i), threads=o.host_threads())
