@@ -156,6 +156,15 @@ def cpu_sample(w, n_leaves, k, threads, seed):
     return n_leaves * k / dt, plies / dt, dt
 
 
+def cpu_sample_size(w, threads, target_s):
+    """Bounded sample of the 4096 x 4096 workload that takes about `target_s` seconds on this host."""
+    pps, _, _ = cpu_sample(w, 64, 64, threads, 1)
+    want = max(4096.0, pps * target_s)
+    n = 4096 if want >= 4096 * 64 else 256
+    k = int(min(4096, max(32, want // n)))
+    return n, k
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -165,9 +174,10 @@ def run_reference(args):
     o.lib()
     threads = o.host_threads()
     w = HEADLINE
-    n_leaves, k = 64, 128  # bounded sample of the 4096 x 4096 workload
     for _ in range(args.warmup):
         cpu_sample(w, 16, 32, threads, 7)
+    # bounded sample of the 4096 x 4096 workload: the whole --steps run takes about a minute
+    n_leaves, k = cpu_sample_size(w, threads, max(2.0, 60.0 / max(1, args.steps)))
     times, rates = [], []
     for s in range(args.steps):
         pps, _, dt = cpu_sample(w, n_leaves, k, threads, 1000 + s)
@@ -400,10 +410,11 @@ def run_gpu(args):
 
         o.lib()
         threads = o.host_threads()
-        pps, plies_s, dt = cpu_sample(HEADLINE, 64, 128, threads, 4242)
+        cn, ck = cpu_sample_size(HEADLINE, threads, 12.0)
+        pps, plies_s, dt = cpu_sample(HEADLINE, cn, ck, threads, 4242)
         line["cpu_baseline"] = {
             "value": pps, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"64 leaves x 128 playouts of the {HEADLINE['name']} workload, {threads} pthreads, {dt:.1f} s",
+            "sample": f"{cn} leaves x {ck} playouts of the {HEADLINE['name']} workload, {threads} pthreads, {dt:.1f} s",
         }
     elif rank == 0:
         line["cpu_baseline"] = None

@@ -88,8 +88,7 @@ struct Device {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     SlotDev slot[MR_NUM_SLOTS];
-    DevBuf<uint16_t> mast_rank; // [2][NA]
-    int mast_game = -1;
+    int mast_game = -1; // game of the MAST snapshot held in ctx->mast_*
     DevBuf<uint16_t> scratch;
     uint32_t *d_counter_ext = nullptr; // task counter for mr_launch_device
 };
@@ -110,6 +109,10 @@ struct mr_ctx {
     SlotState slot[MR_NUM_SLOTS];
     std::string error;
     uint64_t launches = 0;
+    // MAST snapshot as rank bit-planes (copied into KernelParams at launch)
+    uint64_t mast_planes[2][MAST_KINDS][MAST_BITS] = {};
+    uint32_t mast_nbits[2] = {0, 0};
+    int mast_game = -1;
     // NCCL (loaded lazily with dlopen; see mr_comm_*)
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
@@ -193,29 +196,61 @@ struct Rational {
 inline bool rat_less(const Rational &a, const Rational &b) { return (__int128)a.num * b.den < (__int128)b.num * a.den; }
 inline bool rat_eq(const Rational &a, const Rational &b) { return (__int128)a.num * b.den == (__int128)b.num * a.den; }
 
-int compute_mast_ranks(mr_ctx *ctx, int na, const mr_action_stat *mast, uint16_t *out) {
+// (src, kind) -> dst for the two games that have a MAST kernel; -1 when the move leaves the board
+int through_dst(int game, int player, int src, int kind) {
+    const int row = src / 8, col = src % 8;
+    if (game == MR_BREAKTHROUGH) {
+        if (kind > 2) return -1;
+        const int dr = player == 0 ? -1 : 1, dc = kind - 1; // W, F, E
+        const int r = row + dr, c = col + dc;
+        return (r < 0 || r > 7 || c < 0 || c > 7) ? -1 : r * 8 + c;
+    }
+    static const int off[8][2] = {{-2, -1}, {-2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}, {2, -1}, {2, 1}}; // ascending dst
+    const int r = row + off[kind][0], c = col + off[kind][1];
+    return (r < 0 || r > 7 || c < 0 || c > 7) ? -1 : r * 8 + c;
+}
+
+int compute_mast_planes(mr_ctx *ctx, int game, const mr_action_stat *mast) {
+    if (game != MR_BREAKTHROUGH && game != MR_KNIGHTTHROUGH)
+        return fail(ctx, MR_ERR_UNSUPPORTED, "MAST snapshots are supported for Breakthrough / Knightthrough only");
+    const int na = kGames[game].num_actions;
+    const int kinds = game == MR_BREAKTHROUGH ? 3 : 8;
+    memset(ctx->mast_planes, 0, sizeof ctx->mast_planes);
     for (int pl = 0; pl < 2; ++pl) {
         const mr_action_stat *tab = mast + (size_t)pl * na;
+        // distinct values over the REAL actions of this player only (ids that no move can produce are ignored)
         std::vector<Rational> vals;
         vals.push_back({1, 1});
-        for (int a = 0; a < na; ++a) {
-            if (tab[a].visits >= (1u << 26))
-                return fail(ctx, MR_ERR_INVALID, "MAST visits %u >= 2^26: exact score comparison not guaranteed", tab[a].visits);
-            if (tab[a].visits > 0) vals.push_back({(int64_t)tab[a].score, (int64_t)tab[a].visits});
-        }
+        for (int src = 0; src < 64; ++src)
+            for (int q = 0; q < kinds; ++q) {
+                const int dst = through_dst(game, pl, src, q);
+                if (dst < 0) continue;
+                const mr_action_stat &e = tab[src * 64 + dst];
+                if (e.visits >= (1u << 26))
+                    return fail(ctx, MR_ERR_INVALID, "MAST visits %u >= 2^26: exact score comparison not guaranteed", e.visits);
+                if (e.visits > 0) vals.push_back({(int64_t)e.score, (int64_t)e.visits});
+            }
         std::sort(vals.begin(), vals.end(), rat_less);
         std::vector<Rational> uniq;
         for (const Rational &v : vals)
             if (uniq.empty() || !rat_eq(uniq.back(), v)) uniq.push_back(v);
-        if (uniq.size() > 65535) return fail(ctx, MR_ERR_INVALID, "too many distinct MAST values");
-        auto rank_of = [&](Rational v) {
-            return (uint16_t)(std::lower_bound(uniq.begin(), uniq.end(), v, rat_less) - uniq.begin());
-        };
-        const uint16_t unvisited = rank_of({1, 1});
-        for (int a = 0; a < na; ++a)
-            out[(size_t)pl * na + a] =
-                tab[a].visits > 0 ? rank_of({(int64_t)tab[a].score, (int64_t)tab[a].visits}) : unvisited;
+        uint32_t nbits = 0;
+        while ((1u << nbits) < uniq.size()) ++nbits;
+        if (nbits > (uint32_t)MAST_BITS) return fail(ctx, MR_ERR_INVALID, "too many distinct MAST values (%zu)", uniq.size());
+        ctx->mast_nbits[pl] = nbits;
+        auto rank_of = [&](Rational v) { return (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), v, rat_less) - uniq.begin()); };
+        const uint32_t unvisited = rank_of({1, 1});
+        for (int src = 0; src < 64; ++src)
+            for (int q = 0; q < kinds; ++q) {
+                const int dst = through_dst(game, pl, src, q);
+                if (dst < 0) continue;
+                const mr_action_stat &e = tab[src * 64 + dst];
+                const uint32_t rk = e.visits > 0 ? rank_of({(int64_t)e.score, (int64_t)e.visits}) : unvisited;
+                for (uint32_t b = 0; b < nbits; ++b)
+                    if ((rk >> b) & 1u) ctx->mast_planes[pl][q][b] |= 1ull << src;
+            }
     }
+    ctx->mast_game = game;
     return MR_OK;
 }
 
@@ -273,8 +308,13 @@ int plan_launch(mr_ctx *ctx, const Device &dv, kernel_fn fn, const mr_batch_desc
     return MR_OK;
 }
 
-void fill_params(KernelParams &kp, const mr_batch_desc *d, const LaunchPlan &lp, uint32_t trace_cap) {
+void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, const LaunchPlan &lp, uint32_t trace_cap) {
     memset(&kp, 0, sizeof kp);
+    if (d->policy == MR_EPS_MAST) {
+        memcpy(kp.mast_planes, ctx->mast_planes, sizeof kp.mast_planes);
+        kp.mast_nbits[0] = ctx->mast_nbits[0];
+        kp.mast_nbits[1] = ctx->mast_nbits[1];
+    }
     kp.n_leaves = d->n_leaves;
     kp.k = d->playouts_per_leaf;
     kp.chunk = lp.chunk;
@@ -309,16 +349,6 @@ int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const Lau
     fn<<<blocks, THREADS_PER_BLOCK, 0, stream>>>(kp);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
-    return MR_OK;
-}
-
-int upload_mast(mr_ctx *ctx, Device &dv, int game, const mr_action_stat *mast_in) {
-    const int na = kGames[game].num_actions;
-    CUDA_TRY(ctx, dv.mast_rank.reserve((size_t)2 * na, true));
-    int rc = compute_mast_ranks(ctx, na, mast_in, dv.mast_rank.h);
-    if (rc != MR_OK) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(dv.mast_rank.d, dv.mast_rank.h, sizeof(uint16_t) * 2 * na, cudaMemcpyHostToDevice, dv.stream));
-    dv.mast_game = game;
     return MR_OK;
 }
 
@@ -403,7 +433,6 @@ void mr_destroy(mr_ctx *ctx) {
             if (sd.ev_begin) cudaEventDestroy(sd.ev_begin);
             if (sd.ev_end) cudaEventDestroy(sd.ev_end);
         }
-        dv.mast_rank.release();
         dv.scratch.release();
         if (dv.d_counter_ext) cudaFree(dv.d_counter_ext);
         if (dv.stream) cudaStreamDestroy(dv.stream);
@@ -421,13 +450,7 @@ int mr_num_devices(const mr_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0; }
 int mr_set_mast(mr_ctx *ctx, int game, const mr_action_stat *mast_in) {
     if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
     if (game < 0 || game >= MR_NUM_GAMES || !mast_in) return fail(ctx, MR_ERR_INVALID, "mr_set_mast: bad arguments");
-    for (Device &dv : ctx->dev) {
-        CUDA_TRY(ctx, cudaSetDevice(dv.id));
-        int rc = upload_mast(ctx, dv, game, mast_in);
-        if (rc != MR_OK) return rc;
-        CUDA_TRY(ctx, cudaStreamSynchronize(dv.stream));
-    }
-    return MR_OK;
+    return compute_mast_planes(ctx, game, mast_in);
 }
 
 int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *leaves, const mr_action_stat *mast_in) {
@@ -440,6 +463,10 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
     uint32_t trace_cap = 0;
     int rc = validate(ctx, desc, mast_in != nullptr, &fn, &trace_cap);
     if (rc != MR_OK) return rc;
+    if (desc->policy == MR_EPS_MAST) {
+        rc = compute_mast_planes(ctx, (int)desc->game, mast_in);
+        if (rc != MR_OK) return rc;
+    }
     const int nd = (int)ctx->dev.size();
     LaunchPlan lp;
     CUDA_TRY(ctx, cudaSetDevice(ctx->dev[0].id));
@@ -467,17 +494,12 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
         memcpy(sd.leaves.h, leaves, sizeof(mr_leaf) * n);
         CUDA_TRY(ctx, cudaMemcpyAsync(sd.leaves.d, sd.leaves.h, sizeof(mr_leaf) * n, cudaMemcpyHostToDevice, dv.stream));
         CUDA_TRY(ctx, cudaMemsetAsync(sd.results.d, 0, sizeof(mr_leaf_result) * n, dv.stream));
-        if (desc->policy == MR_EPS_MAST) {
-            rc = upload_mast(ctx, dv, (int)desc->game, mast_in);
-            if (rc != MR_OK) return rc;
-        }
         KernelParams kp;
-        fill_params(kp, desc, lp, trace_cap);
+        fill_params(ctx, kp, desc, lp, trace_cap);
         kp.leaves = sd.leaves.d;
         kp.results = sd.results.d;
         kp.task_begin = sd.task_begin;
         kp.task_end = sd.task_end;
-        kp.mast_rank = dv.mast_rank.d;
         if (desc->flags & MR_WANT_AMAF) {
             CUDA_TRY(ctx, sd.amaf.reserve((size_t)n * 2 * na, true));
             CUDA_TRY(ctx, cudaMemsetAsync(sd.amaf.d, 0, sizeof(mr_action_stat) * n * 2 * na, dv.stream));
@@ -612,7 +634,7 @@ int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, c
         return fail(ctx, MR_ERR_INVALID, "trace / final-state outputs are not available on the device-resident path");
     kernel_fn fn = nullptr;
     uint32_t trace_cap = 0;
-    int rc = validate(ctx, desc, dv.mast_game == (int)desc->game, &fn, &trace_cap);
+    int rc = validate(ctx, desc, ctx->mast_game == (int)desc->game, &fn, &trace_cap);
     if (rc != MR_OK) return rc;
     if ((desc->flags & MR_WANT_AMAF) && !d_amaf) return fail(ctx, MR_ERR_INVALID, "MR_WANT_AMAF without d_amaf");
     if ((desc->flags & MR_WANT_MAST_DELTA) && !d_mast_delta) return fail(ctx, MR_ERR_INVALID, "MR_WANT_MAST_DELTA without d_mast_delta");
@@ -621,14 +643,13 @@ int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, c
     rc = plan_launch(ctx, dv, fn, desc, 1, &lp);
     if (rc != MR_OK) return rc;
     KernelParams kp;
-    fill_params(kp, desc, lp, trace_cap);
+    fill_params(ctx, kp, desc, lp, trace_cap);
     kp.leaves = (const mr_leaf *)d_leaves;
     kp.results = (mr_leaf_result *)d_results;
     kp.amaf = (mr_action_stat *)d_amaf;
     kp.mast_delta = (mr_action_stat *)d_mast_delta;
     kp.task_begin = 0;
     kp.task_end = lp.n_tasks;
-    kp.mast_rank = dv.mast_rank.d;
     cudaStream_t st = stream ? (cudaStream_t)stream : dv.stream;
     return launch_on(ctx, dv, fn, kp, lp, st, dv.d_counter_ext);
 }

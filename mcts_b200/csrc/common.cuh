@@ -11,6 +11,8 @@ namespace mr {
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int THREADS_PER_BLOCK = WARPS_PER_BLOCK * 32;
+constexpr int MAST_KINDS = 8;  // move kinds per source cell: 3 (Breakthrough) or 8 (Knightthrough)
+constexpr int MAST_BITS = 10;  // <= 513 distinct score values over the <= 512 real actions of a player
 
 // step() result codes.  Bit 3 says a ply was made; the low bits say how the playout ended.
 enum : int {
@@ -47,8 +49,11 @@ struct KernelParams {
     uint16_t *trace;            // [n_leaves*k][max_trace]
     mr_playout_record *rec;     // [n_leaves*k]
     mr_leaf *final_state;       // [n_leaves*k]
-    // MAST snapshot as dense order-preserving ranks of score/visits (unvisited == value 1.0)
-    const uint16_t *mast_rank; // [2][NA]
+    // MAST snapshot as BIT-PLANES of dense order-preserving ranks of score/visits (unvisited == 1.0):
+    // bit s of mast_planes[player][kind][b] = bit b of rank(player, action (src = s, kind)).  The greedy
+    // pick is then a bit-sliced arg-max over the legal-move masks, with no table lookups at all.
+    uint64_t mast_planes[2][MAST_KINDS][MAST_BITS];
+    uint32_t mast_nbits[2];
     uint16_t *trace_scratch;   // [resident warps][trace_cap][32] u16, MAST-delta staging
     uint32_t trace_cap;
 };

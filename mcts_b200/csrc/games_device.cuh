@@ -45,6 +45,9 @@ __device__ __forceinline__ uint32_t select32(uint32_t w, uint32_t idx) {
 // ==========================================================================================
 struct Connect4 {
     static constexpr int NA = 7;
+    static constexpr int NSLOTS = 7; // compact per-player statistic slots (== action ids here)
+    static constexpr bool MASK_AMAF = false;
+    __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
     static constexpr uint64_t BOTTOM = 0x0001010101010101ull;
     static constexpr uint64_t BOARD = 0x003F3F3F3F3F3F3Full;
     static constexpr uint64_t TOPROW = 0x0020202020202020ull;
@@ -108,7 +111,7 @@ struct Connect4 {
     }
 
     template <int POLICY, int PARITY>
-    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action) {
+    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         const uint64_t moves = (all + BOTTOM) & BOARD; // one bit per open column, ascending column order
         uint64_t bit;
         if (POLICY == MR_DECISIVE_WIN) {
@@ -140,6 +143,7 @@ struct Connect4 {
             bit = in_hi ? mk64(0, b) : mk64(b, 0);
         }
         action = (uint32_t)(__ffsll((long long)bit) - 1) >> 3; // column
+        slot = action;
         all |= bit;
         const uint64_t me = cur | bit;
         n_open -= (bit & TOPROW) ? 1u : 0u;
@@ -177,6 +181,7 @@ struct Connect4 {
 // ==========================================================================================
 struct ThroughBase {
     static constexpr int NA = 4096;
+    static constexpr bool MASK_AMAF = false;
     static constexpr uint64_t NOT_COL0 = 0xFEFEFEFEFEFEFEFEull;
     static constexpr uint64_t NOT_COL7 = 0x7F7F7F7F7F7F7F7Full;
 
@@ -226,6 +231,11 @@ struct ThroughBase {
 };
 
 struct Breakthrough : ThroughBase {
+    static constexpr int NSLOTS = 192; // src*3 + kind (W,F,E)
+    __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
+        const uint32_t src = slot / 3u, kind = slot - src * 3u;
+        return src * 64u + (uint32_t)((int)src + (pl ? 7 : -9) + (int)kind);
+    }
     // source-space masks of the three move kinds for the mover
     __device__ static void masks(bool is_white, uint64_t own, uint64_t opp, uint64_t &W, uint64_t &F, uint64_t &E) {
         const uint64_t occ = own | opp;
@@ -270,7 +280,7 @@ struct Breakthrough : ThroughBase {
     }
 
     template <int POLICY, int PARITY>
-    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action);
+    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot);
 };
 
 // ==========================================================================================
@@ -279,6 +289,11 @@ struct Breakthrough : ThroughBase {
 //   pieces, src ascending then dst ascending, i.e. jump deltas in the order -17,-15,-10,-6,+6,+10,+15,+17.
 // ==========================================================================================
 struct Knightthrough : ThroughBase {
+    static constexpr int NSLOTS = 512; // src*8 + kind (ascending-dst jump order)
+    __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
+        const uint32_t src = slot >> 3, kind = slot & 7u;
+        return src * 64u + (uint32_t)((int)src + delta(kind));
+    }
     __device__ static void masks(uint64_t own, uint64_t M[8]) {
         const uint64_t n = ~own;
         constexpr uint64_t GE1 = 0xFEFEFEFEFEFEFEFEull, LE6 = 0x7F7F7F7F7F7F7F7Full;
@@ -299,42 +314,54 @@ struct Knightthrough : ThroughBase {
     }
 
     template <int POLICY, int PARITY>
-    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action);
+    __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot);
 };
 
-// ---- MAST greedy pick shared by Breakthrough / Knightthrough ----
-// random_best (util.rs:135-163) over scores given as order-preserving ranks: visit list positions
-// i_j = (i0 + j*stride) mod n, keep the first strict maximum.  `rank_of(i)` returns the rank of the i-th
-// legal action in list order.  Implemented as: one pass in list order for the maximum and its
-// multiplicity, then (only when tied) a walk in visiting order until a maximal action is met.
-template <class RankOf>
-__device__ __forceinline__ uint32_t mast_random_best(uint32_t n, uint32_t r, RankOf rank_of) {
-    const uint32_t i0 = r >> 4;
-    const uint32_t stride = MR_PRIMES[r & 15u] % n;
-    uint32_t best = rank_of(0), best_i = 0, count = 1;
-    for (uint32_t i = 1; i < n; ++i) {
-        const uint32_t v = rank_of(i);
-        if (v > best) {
-            best = v;
-            best_i = i;
-            count = 1;
-        } else if (v == best) {
-            ++count;
+// ---- MAST greedy pick (Breakthrough / Knightthrough) ----
+// Mast::select_move = random_best over unigram scores (simulate.rs:794-848, util.rs:135-163): visit list
+// positions i_j = (i0 + j*stride) mod n and keep the FIRST strict maximum, i.e. the first position in
+// visiting order whose score equals the global maximum.
+//
+// Scores arrive as bit-planes of dense order-preserving ranks (KernelParams::mast_planes), so the set of
+// maximal legal actions is found by a bit-sliced arg-max: start from the legal-move masks and, from the
+// most significant rank bit down, keep only candidates with that bit set whenever any has it.
+// Three outcomes:  exactly one maximal action -> it is the pick, no list index needed;
+//                  every legal action maximal (e.g. an empty table) -> the pick is list position i0;
+//                  otherwise -> mark the maximal actions' list positions in a bitmask and walk the
+//                  visiting order until a marked position is met.
+template <int KINDS>
+__device__ __forceinline__ void mast_argmax(uint64_t cand[KINDS], const uint64_t (*planes)[MAST_BITS], uint32_t nbits) {
+    for (int b = (int)nbits - 1; b >= 0; --b) {
+        uint64_t t[KINDS];
+        uint64_t any = 0;
+#pragma unroll
+        for (int q = 0; q < KINDS; ++q) {
+            t[q] = cand[q] & planes[q][b];
+            any |= t[q];
+        }
+        if (any) {
+#pragma unroll
+            for (int q = 0; q < KINDS; ++q) cand[q] = t[q];
         }
     }
-    if (count == 1) return best_i;
+}
+
+// first position in visiting order (i0, i0+stride, ... mod n) whose bit is set in the n-bit mask (lo, hi)
+__device__ __forceinline__ uint32_t first_marked_in_visiting_order(uint64_t lo, uint64_t hi, uint32_t n, uint32_t i0,
+                                                                   uint32_t stride) {
     uint32_t i = i0;
     for (uint32_t j = 0; j < n; ++j) {
-        if (rank_of(i) == best) return i;
+        const uint64_t w = i < 64 ? lo : hi;
+        if ((w >> (i & 63u)) & 1ull) break;
         i += stride;
         if (i >= n) i -= n;
     }
-    return best_i; // unreachable
+    return i;
 }
 
 template <int POLICY, int PARITY>
 __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p,
-                                  uint32_t &action) {
+                                  uint32_t &action, uint32_t &slot) {
     const bool is_white = ((sh.turn ^ PARITY) & 1u) != 0;
     const uint64_t own = is_white ? white : black, opp = is_white ? black : white;
     uint64_t W, F, E;
@@ -342,23 +369,52 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
     const uint64_t S = W ^ F ^ E, C = (W & F) | (W & E) | (F & E);
     const uint32_t n = __popcll(S) + 2u * __popcll(C);
     if (n == 0) return ST_NO_ACTIONS;
-    uint32_t idx;
+    uint32_t idx = 0, src = 0, dir = 0;
+    bool have = false;
     if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
-        const uint16_t *tab = p.mast_rank + (is_white ? NA : 0);
-        const int base = is_white ? 7 : -9;
-        auto rank_of = [&](uint32_t i) -> uint32_t {
-            uint32_t d;
-            const uint32_t s = select_move(W, F, E, S, C, i, d);
-            return tab[s * 64u + (uint32_t)((int)s + base + (int)d)];
-        };
-        idx = mast_random_best(n, mulhi(x0, 16u * n), rank_of);
+        const uint32_t pl = is_white ? 1u : 0u;
+        uint64_t cand[3] = {W, F, E};
+        mast_argmax<3>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
+        const uint64_t cs = cand[0] ^ cand[1] ^ cand[2];
+        const uint64_t cc = (cand[0] & cand[1]) | (cand[0] & cand[2]) | (cand[1] & cand[2]);
+        const uint32_t m = __popcll(cs) + 2u * __popcll(cc);
+        if (m == 1) {
+            src = (uint32_t)__ffsll((long long)(cand[0] | cand[1] | cand[2])) - 1u;
+            dir = cand[0] ? 0u : (cand[1] ? 1u : 2u);
+            have = true;
+        } else {
+            const uint32_t r = mulhi(x0, 16u * n);
+            const uint32_t i0 = r >> 4;
+            if (m == n) {
+                idx = i0;
+            } else {
+                // mark list positions of the smaller of {maximal, non-maximal} actions
+                const bool comp = 2u * m > n;
+                uint64_t X[3] = {comp ? (W & ~cand[0]) : cand[0], comp ? (F & ~cand[1]) : cand[1],
+                                 comp ? (E & ~cand[2]) : cand[2]};
+                uint64_t T = 0;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    for (uint64_t x = X[q]; x; x &= x - 1) {
+                        const uint32_t s = (uint32_t)__ffsll((long long)x) - 1u;
+                        const uint64_t below = (1ull << s) - 1ull;
+                        uint32_t i = __popcll(S & below) + 2u * __popcll(C & below);
+                        if (q >= 1) i += (uint32_t)((W >> s) & 1ull);
+                        if (q >= 2) i += (uint32_t)((F >> s) & 1ull);
+                        T |= 1ull << i;
+                    }
+                }
+                if (comp) T = ~T & ((1ull << n) - 1ull); // n <= 48
+                idx = first_marked_in_visiting_order(T, 0, n, i0, MR_PRIMES[r & 15u] % n);
+            }
+        }
     } else {
         idx = mulhi(x0, n);
     }
-    uint32_t dir;
-    const uint32_t src = select_move(W, F, E, S, C, idx, dir);
+    if (!have) src = select_move(W, F, E, S, C, idx, dir);
     const uint32_t dst = (uint32_t)((int)src + (is_white ? 7 : -9) + (int)dir);
     action = (src << 8) | dst;
+    slot = src * 3u + dir;
     const bool won = apply_move(is_white, src, dst);
     if (won) return ST_MOVED | (is_white ? ST_WIN_P1 : ST_WIN_P0);
     return ST_MOVED;
@@ -366,23 +422,28 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
 
 template <int POLICY, int PARITY>
 __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p,
-                                   uint32_t &action) {
+                                   uint32_t &action, uint32_t &slot) {
     const bool is_white = ((sh.turn ^ PARITY) & 1u) != 0;
     const uint64_t own = is_white ? white : black;
     uint64_t M[8];
     masks(own, M);
     // per-cell move count as a bit-sliced 4-bit number (carry-save adder tree over the 8 masks)
-    uint64_t s01 = M[0] ^ M[1] ^ M[2], c01 = (M[0] & M[1]) | (M[0] & M[2]) | (M[1] & M[2]);
-    uint64_t s23 = M[3] ^ M[4] ^ M[5], c23 = (M[3] & M[4]) | (M[3] & M[5]) | (M[4] & M[5]);
-    uint64_t s45 = M[6] ^ M[7], c45 = M[6] & M[7];
-    const uint64_t B0 = s01 ^ s23 ^ s45;                                  // weight 1
-    const uint64_t k0 = (s01 & s23) | (s01 & s45) | (s23 & s45);          // weight 2 carry
+    const uint64_t s01 = M[0] ^ M[1] ^ M[2], c01 = (M[0] & M[1]) | (M[0] & M[2]) | (M[1] & M[2]);
+    const uint64_t s23 = M[3] ^ M[4] ^ M[5], c23 = (M[3] & M[4]) | (M[3] & M[5]) | (M[4] & M[5]);
+    const uint64_t s45 = M[6] ^ M[7], c45 = M[6] & M[7];
+    const uint64_t B0 = s01 ^ s23 ^ s45;                                               // weight 1
+    const uint64_t k0 = (s01 & s23) | (s01 & s45) | (s23 & s45);                       // carry into weight 2
     const uint64_t t1 = c01 ^ c23 ^ c45, u1 = (c01 & c23) | (c01 & c45) | (c23 & c45); // weight 2 sum, weight 4 carry
-    const uint64_t B1 = t1 ^ k0, k1 = t1 & k0;                            // weight 2, carry to 4
-    const uint64_t B2 = u1 ^ k1, B3 = u1 & k1;                            // weight 4, weight 8
+    const uint64_t B1 = t1 ^ k0, k1 = t1 & k0;                                         // weight 2, carry into 4
+    const uint64_t B2 = u1 ^ k1, B3 = u1 & k1;                                         // weight 4, weight 8
     const uint32_t n = __popcll(B0) + 2u * __popcll(B1) + 4u * __popcll(B2) + 8u * __popcll(B3);
     if (n == 0) return ST_NO_ACTIONS;
 
+    // number of legal moves of cells strictly below `s`
+    auto count_below = [&](uint32_t s) -> uint32_t {
+        const uint64_t below = (1ull << s) - 1ull;
+        return __popcll(B0 & below) + 2u * __popcll(B1 & below) + 4u * __popcll(B2 & below) + 8u * __popcll(B3 & below);
+    };
     auto select_move = [&](uint32_t idx, uint32_t &kind) -> uint32_t {
         const uint32_t cl = __popc(lo32(B0)) + 2u * __popc(lo32(B1)) + 4u * __popc(lo32(B2)) + 8u * __popc(lo32(B3));
         const bool in_hi = idx >= cl;
@@ -415,22 +476,57 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
         return pos + (in_hi ? 32u : 0u);
     };
 
-    uint32_t idx;
+    uint32_t idx = 0, src = 0, kind = 0;
+    bool have = false;
     if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
-        const uint16_t *tab = p.mast_rank + (is_white ? NA : 0);
-        auto rank_of = [&](uint32_t i) -> uint32_t {
-            uint32_t kq;
-            const uint32_t s = select_move(i, kq);
-            return tab[s * 64u + (uint32_t)((int)s + delta(kq))];
-        };
-        idx = mast_random_best(n, mulhi(x0, 16u * n), rank_of);
+        const uint32_t pl = is_white ? 1u : 0u;
+        uint64_t cand[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cand[q] = M[q];
+        mast_argmax<8>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
+        uint32_t m = 0;
+        uint64_t any = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            m += __popcll(cand[q]);
+            any |= cand[q];
+        }
+        if (m == 1) {
+            src = (uint32_t)__ffsll((long long)any) - 1u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (cand[q]) kind = q;
+            have = true;
+        } else {
+            const uint32_t r = mulhi(x0, 16u * n);
+            const uint32_t i0 = r >> 4;
+            if (m == n) {
+                idx = i0;
+            } else {
+                // mark the maximal actions' list positions (n <= 128), cell by cell
+                uint64_t Tlo = 0, Thi = 0;
+                for (uint64_t cells = any; cells; cells &= cells - 1) {
+                    const uint32_t s = (uint32_t)__ffsll((long long)cells) - 1u;
+                    uint32_t i = count_below(s);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if ((cand[q] >> s) & 1ull) {
+                            if (i < 64) Tlo |= 1ull << i;
+                            else Thi |= 1ull << (i - 64);
+                        }
+                        i += (uint32_t)((M[q] >> s) & 1ull);
+                    }
+                }
+                idx = first_marked_in_visiting_order(Tlo, Thi, n, i0, MR_PRIMES[r & 15u] % n);
+            }
+        }
     } else {
         idx = mulhi(x0, n);
     }
-    uint32_t kind;
-    const uint32_t src = select_move(idx, kind);
+    if (!have) src = select_move(idx, kind);
     const uint32_t dst = (uint32_t)((int)src + delta(kind));
     action = (src << 8) | dst;
+    slot = (src << 3) | kind;
     const bool won = apply_move(is_white, src, dst);
     if (won) return ST_MOVED | (is_white ? ST_WIN_P1 : ST_WIN_P0);
     return ST_MOVED;
@@ -444,6 +540,9 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
 // ==========================================================================================
 struct Othello {
     static constexpr int NA = 65;
+    static constexpr int NSLOTS = 65;
+    static constexpr bool MASK_AMAF = false;
+    __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
     static constexpr uint64_t NOT_A = 0xFEFEFEFEFEFEFEFEull; // not column 0
     static constexpr uint64_t NOT_H = 0x7F7F7F7F7F7F7F7Full; // not column 7
 
@@ -521,13 +620,14 @@ struct Othello {
     }
 
     template <int POLICY, int PARITY>
-    __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action) {
+    __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         const bool is_white = ((s.turn ^ PARITY) & 1u) != 0;
         const uint64_t P = is_white ? white : black, O = is_white ? black : white;
         const uint64_t moves = legal_moves(P, O);
         if (moves == 0) {
             // the only action is PASS.  (A double pass is terminal and was caught after the first pass.)
             action = 64;
+            slot = 64;
             last_pass = 1;
             // terminal next iff the opponent has no move either (:565-579)
             if (legal_moves(O, P) == 0) return ST_MOVED | terminal_code(black, white);
@@ -547,6 +647,7 @@ struct Othello {
         white = is_white ? nP : nO;
         last_pass = 0;
         action = sq;
+        slot = sq;
         if (__popcll(black | white) == 64) return ST_MOVED | terminal_code(black, white);
         return ST_MOVED;
     }
@@ -576,6 +677,11 @@ struct Othello {
 // ==========================================================================================
 struct Hex11 {
     static constexpr int NA = 121;
+    static constexpr int NSLOTS = 121;
+    // a Hex playout plays every cell at most once, so its (action, player) occurrences are exactly
+    // final stones minus leaf stones: AMAF is accumulated from board masks, no move trace needed
+    static constexpr bool MASK_AMAF = true;
+    __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
     struct B128 {
         uint32_t w[4];
     };
@@ -691,7 +797,7 @@ struct Hex11 {
     }
 
     template <int POLICY, int PARITY>
-    __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action) {
+    __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         const uint32_t mover = (s.turn ^ PARITY) & 1u;
         if (n_empty == 0) return ST_DRAW; // cannot happen in Hex; kept for totality
         // idx-th empty cell, ascending
@@ -720,6 +826,7 @@ struct Hex11 {
         const uint32_t bitpos = select32(word, idx);
         const uint32_t cell = wsel * 32u + bitpos;
         action = cell;
+        slot = cell;
         const uint32_t b = 1u << bitpos;
         B128 mv = zero();
 #pragma unroll
@@ -756,6 +863,19 @@ struct Hex11 {
             return any(band(f, second_edge(pl)));
         }
         return false;
+    }
+    // AMAF occurrences of finished lane f's playout = its final stones minus the leaf's stones; lane L owns
+    // cells L, L+32, L+64, L+96 of both players, so the per-warp table needs no atomics
+    __device__ void amaf_from_masks(const Shared &s, uint32_t *tab, int f, uint32_t lane, int u_p0) const {
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            const uint32_t inc = 1u + ((uint32_t)(pl == 0 ? u_p0 : -u_p0) << 16);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t played = __shfl_sync(FULL_MASK, stones[pl].w[w], f) & ~s.stones[pl].w[w];
+                if ((played >> lane) & 1u) tab[pl * NSLOTS + w * 32 + lane] += inc;
+            }
+        }
     }
     __device__ void store_final(const Shared &s, mr_leaf *out, uint32_t plies, int end_code) const {
         for (int pl = 0; pl < 2; ++pl) {

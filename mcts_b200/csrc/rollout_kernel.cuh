@@ -4,14 +4,17 @@
 //   task      = (leaf, chunk of `chunk` consecutive playout ids); a task never straddles leaves
 //   warp      = pulls tasks from a global atomic counter until the range is exhausted
 //   lane      = one playout at a time; lanes that finish pull the next playout id of the task at the
-//               next WINDOW boundary (a window = 4 plies = one Philox4x32 block), so all live lanes of a
-//               warp are always at the same ply phase: the Philox block is computed warp-synchronously and
-//               the mover's colour is a warp-uniform, compile-time-alternating quantity.
-//   reduction = per-lane counters -> warp REDUX -> one atomic set per task on results[leaf]
+//               next WINDOW boundary (a window = one Philox4x32 block: 4 plies, or 2 plies for the
+//               epsilon-MAST policy which needs two words per ply), so all live lanes of a warp are always
+//               at the same ply phase: the Philox block is computed warp-synchronously and the mover's
+//               colour is a warp-uniform, compile-time-alternating quantity.
+//   reduction = per-lane counters -> warp REDUX -> one atomic set per task on results[leaf];
+//               MAST / AMAF occurrence tables are accumulated in per-warp SHARED-MEMORY tables (packed
+//               visits:16 | score:16) and flushed to global memory with one atomic per touched entry.
 //
-// Draw discipline (shared with the CPU oracle): word [ply & 3] of
-// Philox4x32-10(key = seed, ctr = (leaf_id, playout_id, ply >> 2, stream)); stream 0 = move choice,
-// stream 1 = epsilon test.
+// Draw discipline (shared with the CPU oracle, DESIGN.md "Draw discipline"), Philox4x32-10 keyed by the seed:
+//   uniform / decisive : ctr = (leaf_id, playout_id, ply >> 2, 0);  x0 = out[ply & 3]
+//   epsilon-MAST       : ctr = (leaf_id, playout_id, ply >> 1, 1);  x0 = out[2*(ply & 1)], x1 = out[2*(ply & 1) + 1]
 #pragma once
 
 #include <type_traits>
@@ -25,11 +28,26 @@ __device__ __forceinline__ int end_code_to_outcome(int code) {
     return e == ST_WIN_P0 ? MR_WINNER_P0 : (e == ST_WIN_P1 ? MR_WINNER_P1 : MR_DRAW);
 }
 
-// id of an action code in the dense per-game action space (MAST / AMAF tables)
+constexpr uint32_t STAT_FLUSH_PLIES = 32000; // packed 16-bit fields: flush before any entry can overflow
+
+// per-warp packed table -> global (visits, score) table, one atomic per non-zero field
 template <class G>
-__device__ __forceinline__ uint32_t action_index(uint32_t code) {
-    if (G::NA == 4096) return (code >> 8) * 64u + (code & 0xffu);
-    return code;
+__device__ __forceinline__ void flush_stat_table(uint32_t *tab, mr_action_stat *out, uint32_t lane) {
+    __syncwarp();
+    for (uint32_t e = lane; e < 2u * G::NSLOTS; e += 32) {
+        const uint32_t v = tab[e];
+        if (v) {
+            tab[e] = 0;
+            const uint32_t pl = e >= (uint32_t)G::NSLOTS ? 1u : 0u;
+            const uint32_t slot = e - pl * G::NSLOTS;
+            mr_action_stat *o = out + (size_t)pl * G::NA + G::slot_action_id(pl, slot);
+            const uint32_t visits = v & 0xffffu;
+            const int score = (int)v >> 16; // v = visits + score * 65536 with visits < 65536: the arithmetic shift floors to score
+            atomicAdd(&o->visits, visits);
+            if (score) atomicAdd(&o->score, score);
+        }
+    }
+    __syncwarp();
 }
 
 template <class G, int POLICY, int FLAGS>
@@ -38,16 +56,29 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
     constexpr bool WANT_MAST = (FLAGS & MR_WANT_MAST_DELTA) != 0;
     constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
     constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
-    constexpr bool NEED_SCRATCH = WANT_AMAF || WANT_MAST;
+    constexpr bool MASK_AMAF = WANT_AMAF && G::MASK_AMAF;
+    constexpr bool NEED_SCRATCH = WANT_MAST || (WANT_AMAF && !G::MASK_AMAF); // per-lane slot trace
+    constexpr int WINDOW = POLICY == MR_EPS_MAST ? 2 : 4;
 
     __shared__ __align__(16) mr_leaf s_leaf[WARPS_PER_BLOCK];
     __shared__ typename G::Shared s_game[WARPS_PER_BLOCK];
+    __shared__ uint32_t s_mast[WARPS_PER_BLOCK][WANT_MAST ? 2 * G::NSLOTS : 1];
+    __shared__ uint32_t s_amaf[WARPS_PER_BLOCK][WANT_AMAF ? 2 * G::NSLOTS : 1];
 
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
     typename G::Shared &sh = s_game[warp];
     uint16_t *scratch = NEED_SCRATCH ? p.trace_scratch + (size_t)gwarp * p.trace_cap * 32u : nullptr;
+    uint32_t *mast_tab = s_mast[warp];
+    uint32_t *amaf_tab = s_amaf[warp];
+    uint32_t mast_plies = 0, amaf_plies = 0; // warp-uniform: plies accumulated since the last flush
+
+    if (WANT_MAST)
+        for (uint32_t e = lane; e < 2u * G::NSLOTS; e += 32) mast_tab[e] = 0;
+    if (WANT_AMAF)
+        for (uint32_t e = lane; e < 2u * G::NSLOTS; e += 32) amaf_tab[e] = 0;
+    __syncwarp();
 
     for (;;) {
         // ---- next task ----
@@ -107,9 +138,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
             st.reset(sh);
 
             for (;;) {
-                uint32_t r0[4], r1[4] = {0, 0, 0, 0};
-                philox4x32_10(leaf_id, pid, win, 0u, p.seed_lo, p.seed_hi, r0);
-                if (POLICY == MR_EPS_MAST) philox4x32_10(leaf_id, pid, win, 1u, p.seed_lo, p.seed_hi, r1);
+                uint32_t r[4];
+                philox4x32_10(leaf_id, pid, win, POLICY == MR_EPS_MAST ? 1u : 0u, p.seed_lo, p.seed_hi, r);
                 // one ply; J is the ply's phase inside the window, so the mover's colour (leaf turn ^ (J & 1))
                 // and the Philox word index are compile-time per call site
                 auto ply = [&](auto J) {
@@ -120,15 +150,17 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
                             cutoff = true;
                             end_code = ST_DRAW;
                         } else {
-                            uint32_t action = 0;
-                            const int code = st.template step<POLICY, (j & 1)>(sh, r0[j], r1[j], p, action);
+                            uint32_t action = 0, slot = 0;
+                            const uint32_t x0 = POLICY == MR_EPS_MAST ? r[(2 * j) & 3] : r[j];
+                            const uint32_t x1 = POLICY == MR_EPS_MAST ? r[(2 * j + 1) & 3] : 0u;
+                            const int code = st.template step<POLICY, (j & 1)>(sh, x0, x1, p, action, slot);
                             if (code & ST_MOVED) {
                                 if (WANT_TRACE && p.trace) {
                                     if (depth < p.max_trace)
                                         p.trace[((size_t)li * p.k + pid) * p.max_trace + depth] = (uint16_t)action;
                                 }
                                 if (NEED_SCRATCH) {
-                                    if (depth < p.trace_cap) scratch[depth * 32u + lane] = (uint16_t)action;
+                                    if (depth < p.trace_cap) scratch[depth * 32u + lane] = (uint16_t)slot;
                                 }
                                 ++depth;
                             }
@@ -141,8 +173,10 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
                 };
                 ply(std::integral_constant<int, 0>{});
                 ply(std::integral_constant<int, 1>{});
-                ply(std::integral_constant<int, 2>{});
-                ply(std::integral_constant<int, 3>{});
+                if constexpr (WINDOW == 4) {
+                    ply(std::integral_constant<int, 2>{});
+                    ply(std::integral_constant<int, 3>{});
+                }
                 ++win;
 
                 // ---- window boundary: retire finished playouts, hand out new playout ids ----
@@ -158,40 +192,52 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
                         acc_depth += depth;
                         const size_t g = (size_t)li * p.k + pid;
                         if (WANT_TRACE && p.rec) {
-                            mr_playout_record r;
-                            r.depth = depth;
-                            r.outcome = (uint8_t)end_code_to_outcome(e);
-                            r.end_type = (uint8_t)(cutoff ? MR_END_TURN_LIMIT
-                                                          : (e == ST_NO_ACTIONS ? MR_END_NO_ACTIONS : MR_END_TERMINAL));
-                            r.pad[0] = r.pad[1] = 0;
-                            p.rec[g] = r;
+                            mr_playout_record rr;
+                            rr.depth = depth;
+                            rr.outcome = (uint8_t)end_code_to_outcome(e);
+                            rr.end_type = (uint8_t)(cutoff ? MR_END_TURN_LIMIT
+                                                           : (e == ST_NO_ACTIONS ? MR_END_NO_ACTIONS : MR_END_TERMINAL));
+                            rr.pad[0] = rr.pad[1] = 0;
+                            p.rec[g] = rr;
                         }
                         if (WANT_FINAL && p.final_state) st.store_final(sh, &p.final_state[g], depth, e);
                     }
-                    if (NEED_SCRATCH) {
-                        // cooperative flush: for every finished lane f, all 32 lanes walk f's trace.
-                        // every (action, player) occurrence: visits += 1, score += utilities[player]
-                        // (backprop.rs:619-640 GRAVE, :857-870 GLOBAL/MAST)
+                    if (NEED_SCRATCH || MASK_AMAF) {
+                        // Cooperative statistics: for every finished lane f, all 32 lanes process f's playout.
+                        // Every (action, player) occurrence: visits += 1, score += utilities[player]
+                        // (backprop.rs:619-640 GRAVE/AMAF, :857-870 GLOBAL/MAST).
                         __syncwarp();
                         for (uint32_t m = fin_mask; m; m &= m - 1) {
                             const int f = __ffs(m) - 1;
                             const uint32_t d_f = __shfl_sync(FULL_MASK, depth, f);
                             const int e_f = __shfl_sync(FULL_MASK, end_code, f);
                             const int u_p0 = e_f == ST_WIN_P0 ? 1 : (e_f == ST_WIN_P1 ? -1 : 0);
-                            for (uint32_t t = lane; t < d_f; t += 32) {
-                                const uint32_t a = action_index<G>(scratch[t * 32u + f]);
-                                const uint32_t pl = (leaf_turn + t) & 1u;
-                                const int u = pl == 0 ? u_p0 : -u_p0;
-                                if (WANT_AMAF && p.amaf) {
-                                    mr_action_stat *e = p.amaf + ((size_t)li * 2 + pl) * G::NA + a;
-                                    atomicAdd(&e->visits, 1u);
-                                    if (u) atomicAdd(&e->score, u);
+                            if (WANT_MAST && p.mast_delta) {
+                                if (mast_plies + d_f > STAT_FLUSH_PLIES) {
+                                    flush_stat_table<G>(mast_tab, p.mast_delta, lane);
+                                    mast_plies = 0;
                                 }
-                                if (WANT_MAST && p.mast_delta) {
-                                    mr_action_stat *e = p.mast_delta + (size_t)pl * G::NA + a;
-                                    atomicAdd(&e->visits, 1u);
-                                    if (u) atomicAdd(&e->score, u);
+                                mast_plies += d_f;
+                            }
+                            if (WANT_AMAF && p.amaf) {
+                                if (amaf_plies + d_f > STAT_FLUSH_PLIES) {
+                                    flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * 2 * G::NA, lane);
+                                    amaf_plies = 0;
                                 }
+                                amaf_plies += d_f;
+                            }
+                            if (NEED_SCRATCH) {
+                                for (uint32_t t = lane; t < d_f; t += 32) {
+                                    const uint32_t slot = scratch[t * 32u + f];
+                                    const uint32_t pl = (leaf_turn + t) & 1u;
+                                    const int u = pl == 0 ? u_p0 : -u_p0;
+                                    const uint32_t inc = 1u + ((uint32_t)u << 16);
+                                    if (WANT_MAST && p.mast_delta) atomicAdd(&mast_tab[pl * G::NSLOTS + slot], inc);
+                                    if (WANT_AMAF && !G::MASK_AMAF && p.amaf) atomicAdd(&amaf_tab[pl * G::NSLOTS + slot], inc);
+                                }
+                            }
+                            if constexpr (MASK_AMAF) {
+                                if (p.amaf) st.amaf_from_masks(sh, amaf_tab, f, lane, u_p0);
                             }
                         }
                         __syncwarp();
@@ -215,6 +261,11 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
                     if (__all_sync(FULL_MASK, idle)) break;
                 }
             }
+            // the AMAF table is per leaf: it leaves shared memory with the task
+            if (WANT_AMAF && p.amaf) {
+                flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * 2 * G::NA, lane);
+                amaf_plies = 0;
+            }
         }
 
         // ---- one atomic set per task ----
@@ -224,14 +275,16 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
         acc_cut = __reduce_add_sync(FULL_MASK, acc_cut);
         acc_depth = __reduce_add_sync(FULL_MASK, acc_depth);
         if (lane == 0) {
-            mr_leaf_result *r = p.results + li;
-            if (acc_w0) atomicAdd(&r->wins[0], acc_w0);
-            if (acc_w1) atomicAdd(&r->wins[1], acc_w1);
-            if (acc_draw) atomicAdd(&r->draws, acc_draw);
-            if (acc_cut) atomicAdd(&r->cutoffs, acc_cut);
-            if (acc_depth) atomicAdd(reinterpret_cast<unsigned long long *>(&r->sum_depth), (unsigned long long)acc_depth);
+            mr_leaf_result *res = p.results + li;
+            if (acc_w0) atomicAdd(&res->wins[0], acc_w0);
+            if (acc_w1) atomicAdd(&res->wins[1], acc_w1);
+            if (acc_draw) atomicAdd(&res->draws, acc_draw);
+            if (acc_cut) atomicAdd(&res->cutoffs, acc_cut);
+            if (acc_depth) atomicAdd(reinterpret_cast<unsigned long long *>(&res->sum_depth), (unsigned long long)acc_depth);
         }
     }
+    // the MAST delta is batch-wide: it leaves shared memory when the warp runs out of tasks
+    if (WANT_MAST && p.mast_delta) flush_stat_table<G>(mast_tab, p.mast_delta, lane);
 }
 
 } // namespace mr

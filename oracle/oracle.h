@@ -91,6 +91,7 @@ uint64_t orc_othello_get_flips(uint64_t player, uint64_t opponent, uint64_t move
 /* ---- Philox4x32-10 and the draw discipline (playout.c) ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 uint32_t orc_draw(uint64_t seed, uint32_t leaf_id, uint32_t playout_id, uint32_t ply, uint32_t stream);
+void orc_draw_pair(uint64_t seed, uint32_t leaf_id, uint32_t playout_id, uint32_t ply, uint32_t *x0, uint32_t *x1);
 
 /* ---- playouts (playout.c) ---- */
 typedef struct {

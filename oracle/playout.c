@@ -21,8 +21,9 @@
  * The reference draws from rand 0.8's SmallRng (crates.io, absent from /root/reference,
  * unpinned by any reference test).  Here every random choice is a pure function of
  * (seed, leaf_id, playout_id, ply, stream):
- *     x = Philox4x32-10(key = (seed_lo, seed_hi), ctr = (leaf_id, playout_id, ply >> 2, stream))[ply & 3]
- *   stream 0 = move choice, stream 1 = epsilon test.
+ *   uniform / decisive : x0 = Philox4x32-10(key = (seed_lo, seed_hi), ctr = (leaf_id, playout_id, ply >> 2, 0))[ply & 3]
+ *   epsilon-MAST       : block = Philox4x32-10(key, ctr = (leaf_id, playout_id, ply >> 1, 1));
+ *                        x0 = block[2*(ply & 1)] (move choice), x1 = block[2*(ply & 1) + 1] (epsilon test)
  *   uniform pick over n      : index = mulhi32(x0, n)
  *   epsilon test             : explore iff x1 < eps_threshold (eps_threshold = floor(eps * 2^32))
  *   MAST greedy (random_best): r = mulhi32(x0, 16 n); i = r / 16; stride = PRIMES[r % 16]
@@ -69,6 +70,15 @@ uint32_t orc_draw(uint64_t seed, uint32_t leaf_id, uint32_t playout_id, uint32_t
     uint32_t out[4];
     orc_philox4x32_10(ctr, key, out);
     return out[ply & 3];
+}
+
+void orc_draw_pair(uint64_t seed, uint32_t leaf_id, uint32_t playout_id, uint32_t ply, uint32_t *x0, uint32_t *x1) {
+    uint32_t ctr[4] = {leaf_id, playout_id, ply >> 1, 1u};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t out[4];
+    orc_philox4x32_10(ctr, key, out);
+    *x0 = out[2 * (ply & 1)];
+    *x1 = out[2 * (ply & 1) + 1];
 }
 
 static inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -152,11 +162,14 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
         int pick = -1;
         if (d->policy == ORC_DECISIVE_WIN) pick = decisive_win_choose(game, &state, available, n, player);
         if (pick < 0) {
-            uint32_t x0 = orc_draw(d->seed, leaf_id, playout_id, depth, 0);
+            uint32_t x0;
             int greedy = 0;
             if (d->policy == ORC_EPS_MAST) {
-                uint32_t x1 = orc_draw(d->seed, leaf_id, playout_id, depth, 1);
+                uint32_t x1;
+                orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
                 greedy = !((uint64_t)x1 < d->eps_threshold);
+            } else {
+                x0 = orc_draw(d->seed, leaf_id, playout_id, depth, 0);
             }
             if (greedy) {
                 const orc_action_stat *tab = mast + (size_t)player * na;

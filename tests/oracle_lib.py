@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
         L.orc_philox4x32_10.argtypes = [vp, vp, vp]
         L.orc_draw.argtypes = [u64, u32, u32, u32, u32]
         L.orc_draw.restype = u32
+        L.orc_draw_pair.argtypes = [u64, u32, u32, u32, vp, vp]
         L.orc_playout_batch.argtypes = [C.POINTER(BatchDesc), vp, u32, vp, vp, vp, vp, vp, vp, vp, i32]
         L.orc_random_positions.argtypes = [i32, u64, u32, u32, vp]
         L.orc_stress_othello.argtypes = [u64, vp, vp]
@@ -161,6 +162,12 @@ def philox(ctr, key) -> list[int]:
 
 def draw(seed, leaf_id, playout_id, ply, stream=0) -> int:
     return lib().orc_draw(seed, leaf_id, playout_id, ply, stream)
+
+
+def draw_pair(seed, leaf_id, playout_id, ply) -> tuple[int, int]:
+    a, b = C.c_uint32(), C.c_uint32()
+    lib().orc_draw_pair(seed, leaf_id, playout_id, ply, C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def eps_threshold(eps: float) -> int:

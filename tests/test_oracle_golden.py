@@ -28,10 +28,13 @@ def test_philox_random123_kat():
 
 def test_draw_discipline_counter_layout():
     seed = 0x0123456789ABCDEF
+    key = [seed & 0xFFFFFFFF, seed >> 32]
     for ply in range(9):
-        for stream in (0, 1):
-            block = o.philox([7, 11, ply >> 2, stream], [seed & 0xFFFFFFFF, seed >> 32])
-            assert o.draw(seed, 7, 11, ply, stream) == block[ply & 3]
+        # uniform / decisive: one word per ply, four plies per Philox block, stream word 0
+        assert o.draw(seed, 7, 11, ply, 0) == o.philox([7, 11, ply >> 2, 0], key)[ply & 3]
+        # epsilon-MAST: two words per ply, two plies per block, stream word 1
+        block = o.philox([7, 11, ply >> 1, 1], key)
+        assert o.draw_pair(seed, 7, 11, ply) == (block[2 * (ply & 1)], block[2 * (ply & 1) + 1])
 
 
 # --------------------------------------------------------------------------------------------
@@ -430,7 +433,7 @@ def test_mast_empty_table_picks_random_best_start():  # util.rs:147-161 with all
     out = o.playout_batch(game, s, 32, policy=o.EPS_MAST, eps=0.0, mast=mast, seed=21, want_trace=True, max_trace=1, max_depth=1)
     acts = o.generate_actions(game, s)
     for pid in range(32):
-        x0 = o.draw(21, 0, pid, 0, 0)
+        x0, _ = o.draw_pair(21, 0, pid, 0)
         r = (x0 * 16 * len(acts)) >> 32
         assert out["trace"][pid, 0] == acts[r // 16]
 
