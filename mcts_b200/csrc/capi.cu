@@ -254,6 +254,38 @@ int compute_mast_planes(mr_ctx *ctx, int game, const mr_action_stat *mast) {
     return MR_OK;
 }
 
+// util.rs:129-132
+const uint32_t kPrimes[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991,
+                              53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693};
+
+// fills MR_STRIDE / MR_STRIDE_INV / MR_RCP32 on the current device
+cudaError_t upload_random_best_tables() {
+    static uint8_t stride[129][16], inv[129][16];
+    static uint32_t rcp[129];
+    memset(stride, 0, sizeof stride);
+    memset(inv, 0, sizeof inv);
+    memset(rcp, 0, sizeof rcp);
+    for (uint32_t n = 1; n <= 128; ++n) {
+        rcp[n] = n == 1 ? 0u : (uint32_t)((1ull << 32) / n) + 1u;
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t s = kPrimes[k] % n;
+            stride[n][k] = (uint8_t)s;
+            uint32_t iv = 0;
+            for (uint32_t c = 0; c < n; ++c)
+                if ((c * s) % n == 1 % n) {
+                    iv = c;
+                    break;
+                }
+            inv[n][k] = (uint8_t)iv;
+        }
+    }
+    cudaError_t e = cudaMemcpyToSymbol(MR_STRIDE, stride, sizeof stride);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(MR_STRIDE_INV, inv, sizeof inv);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(MR_RCP32, rcp, sizeof rcp);
+}
+
 int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_out, uint32_t *trace_cap_out) {
     if (!d) return fail(ctx, MR_ERR_INVALID, "null batch descriptor");
     if (d->game >= MR_NUM_GAMES) return fail(ctx, MR_ERR_INVALID, "unknown game %u", d->game);
@@ -396,7 +428,7 @@ int mr_init(const int *device_ids, int n_devices, mr_ctx **out) {
         dv.num_sms = prop.multiProcessorCount;
         cudaSetDevice(dv.id);
         if (cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc(&dv.d_counter_ext, sizeof(uint32_t)) != cudaSuccess) {
+            cudaMalloc(&dv.d_counter_ext, sizeof(uint32_t)) != cudaSuccess || upload_random_best_tables() != cudaSuccess) {
             int rc = fail(nullptr, MR_ERR_CUDA, "stream/counter creation failed on device %d", dv.id);
             mr_destroy(ctx);
             return rc;

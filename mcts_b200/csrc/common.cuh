@@ -91,6 +91,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[3] = c3;
 }
 
+// random_best helpers, filled by mr_init (capi.cu): for n legal actions and prime index k,
+//   MR_STRIDE[n][k]     = PRIMES[k] mod n                       (the visiting stride, util.rs:147-161)
+//   MR_STRIDE_INV[n][k] = its inverse mod n (PRIMES[k] is a prime > n, hence coprime with n)
+//   MR_RCP32[n]         = floor(2^32 / n) + 1, so that floor(t / n) == umulhi(t, MR_RCP32[n]) for t * n < 2^32
+__device__ uint8_t MR_STRIDE[129][16];
+__device__ uint8_t MR_STRIDE_INV[129][16];
+__device__ uint32_t MR_RCP32[129];
+
 // util.rs:129-132 PRIMES, packed for random_best's stride
 __device__ __constant__ uint32_t MR_PRIMES[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991,
                                                   53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693};

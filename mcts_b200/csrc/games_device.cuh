@@ -346,17 +346,11 @@ __device__ __forceinline__ void mast_argmax(uint64_t cand[KINDS], const uint64_t
     }
 }
 
-// first position in visiting order (i0, i0+stride, ... mod n) whose bit is set in the n-bit mask (lo, hi)
-__device__ __forceinline__ uint32_t first_marked_in_visiting_order(uint64_t lo, uint64_t hi, uint32_t n, uint32_t i0,
-                                                                   uint32_t stride) {
-    uint32_t i = i0;
-    for (uint32_t j = 0; j < n; ++j) {
-        const uint64_t w = i < 64 ? lo : hi;
-        if ((w >> (i & 63u)) & 1ull) break;
-        i += stride;
-        if (i >= n) i -= n;
-    }
-    return i;
+// visiting rank j of list position i: i = (i0 + j*stride) mod n  <=>  j = ((i - i0) mod n) * stride^-1 mod n
+__device__ __forceinline__ uint32_t visiting_rank(uint32_t i, uint32_t i0, uint32_t n, uint32_t inv, uint32_t rcp) {
+    const uint32_t d = i >= i0 ? i - i0 : i + n - i0;
+    const uint32_t t = d * inv;
+    return t - __umulhi(t, rcp) * n;
 }
 
 template <int POLICY, int PARITY>
@@ -387,25 +381,45 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
             const uint32_t i0 = r >> 4;
             if (m == n) {
                 idx = i0;
-            } else {
-                // mark list positions of the smaller of {maximal, non-maximal} actions
-                const bool comp = 2u * m > n;
-                uint64_t X[3] = {comp ? (W & ~cand[0]) : cand[0], comp ? (F & ~cand[1]) : cand[1],
-                                 comp ? (E & ~cand[2]) : cand[2]};
-                uint64_t T = 0;
+            } else if (m <= 6) {
+                // few maximal actions: the pick is the one with the smallest visiting rank
+                const uint32_t pk = r & 15u;
+                const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
+                uint32_t best_j = 0xffffffffu;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    for (uint64_t x = X[q]; x; x &= x - 1) {
+                    for (uint64_t x = cand[q]; x; x &= x - 1) {
                         const uint32_t s = (uint32_t)__ffsll((long long)x) - 1u;
                         const uint64_t below = (1ull << s) - 1ull;
                         uint32_t i = __popcll(S & below) + 2u * __popcll(C & below);
                         if (q >= 1) i += (uint32_t)((W >> s) & 1ull);
                         if (q >= 2) i += (uint32_t)((F >> s) & 1ull);
-                        T |= 1ull << i;
+                        const uint32_t j = visiting_rank(i, i0, n, inv, rcp);
+                        if (j < best_j) {
+                            best_j = j;
+                            src = s;
+                            dir = q;
+                        }
                     }
                 }
-                if (comp) T = ~T & ((1ull << n) - 1ull); // n <= 48
-                idx = first_marked_in_visiting_order(T, 0, n, i0, MR_PRIMES[r & 15u] % n);
+                have = true;
+            } else {
+                // many maximal actions: walk the visiting order, the first maximal action is close
+                const uint32_t stride = MR_STRIDE[n][r & 15u];
+                uint32_t i = i0;
+                for (uint32_t j = 0; j < n; ++j) {
+                    uint32_t d;
+                    const uint32_t s = select_move(W, F, E, S, C, i, d);
+                    const uint64_t cd = d == 0 ? cand[0] : (d == 1 ? cand[1] : cand[2]);
+                    if ((cd >> s) & 1ull) {
+                        src = s;
+                        dir = d;
+                        break;
+                    }
+                    i += stride;
+                    if (i >= n) i -= n;
+                }
+                have = true;
             }
         }
     } else {
@@ -502,22 +516,45 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
             const uint32_t i0 = r >> 4;
             if (m == n) {
                 idx = i0;
-            } else {
-                // mark the maximal actions' list positions (n <= 128), cell by cell
-                uint64_t Tlo = 0, Thi = 0;
+            } else if (m <= 6) {
+                const uint32_t pk = r & 15u;
+                const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
+                uint32_t best_j = 0xffffffffu;
                 for (uint64_t cells = any; cells; cells &= cells - 1) {
                     const uint32_t s = (uint32_t)__ffsll((long long)cells) - 1u;
                     uint32_t i = count_below(s);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         if ((cand[q] >> s) & 1ull) {
-                            if (i < 64) Tlo |= 1ull << i;
-                            else Thi |= 1ull << (i - 64);
+                            const uint32_t j = visiting_rank(i, i0, n, inv, rcp);
+                            if (j < best_j) {
+                                best_j = j;
+                                src = s;
+                                kind = q;
+                            }
                         }
                         i += (uint32_t)((M[q] >> s) & 1ull);
                     }
                 }
-                idx = first_marked_in_visiting_order(Tlo, Thi, n, i0, MR_PRIMES[r & 15u] % n);
+                have = true;
+            } else {
+                const uint32_t stride = MR_STRIDE[n][r & 15u];
+                uint32_t i = i0;
+                for (uint32_t j = 0; j < n; ++j) {
+                    uint32_t kq;
+                    const uint32_t s = select_move(i, kq);
+                    uint64_t ck = cand[0];
+#pragma unroll
+                    for (int q = 1; q < 8; ++q) ck = kq == (uint32_t)q ? cand[q] : ck;
+                    if ((ck >> s) & 1ull) {
+                        src = s;
+                        kind = kq;
+                        break;
+                    }
+                    i += stride;
+                    if (i >= n) i -= n;
+                }
+                have = true;
             }
         }
     } else {

@@ -202,45 +202,77 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
                         }
                         if (WANT_FINAL && p.final_state) st.store_final(sh, &p.final_state[g], depth, e);
                     }
-                    if (NEED_SCRATCH || MASK_AMAF) {
-                        // Cooperative statistics: for every finished lane f, all 32 lanes process f's playout.
+                    if (NEED_SCRATCH) {
+                        // Statistics from the finished playouts' traces, FLATTENED over the warp: entry q of the
+                        // concatenated traces belongs to the finished lane f with excl[f] <= q < incl[f].
                         // Every (action, player) occurrence: visits += 1, score += utilities[player]
                         // (backprop.rs:619-640 GRAVE/AMAF, :857-870 GLOBAL/MAST).
                         __syncwarp();
-                        for (uint32_t m = fin_mask; m; m &= m - 1) {
-                            const int f = __ffs(m) - 1;
-                            const uint32_t d_f = __shfl_sync(FULL_MASK, depth, f);
-                            const int e_f = __shfl_sync(FULL_MASK, end_code, f);
-                            const int u_p0 = e_f == ST_WIN_P0 ? 1 : (e_f == ST_WIN_P1 ? -1 : 0);
-                            if (WANT_MAST && p.mast_delta) {
-                                if (mast_plies + d_f > STAT_FLUSH_PLIES) {
-                                    flush_stat_table<G>(mast_tab, p.mast_delta, lane);
-                                    mast_plies = 0;
-                                }
-                                mast_plies += d_f;
+                        const uint32_t my_d = fin ? min(depth, p.trace_cap) : 0u;
+                        uint32_t incl = my_d;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
+                            if (lane >= (uint32_t)o) incl += v;
+                        }
+                        const uint32_t excl = incl - my_d;
+                        const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+                        if (WANT_MAST && p.mast_delta) {
+                            if (mast_plies + total > STAT_FLUSH_PLIES) {
+                                flush_stat_table<G>(mast_tab, p.mast_delta, lane);
+                                mast_plies = 0;
                             }
-                            if (WANT_AMAF && p.amaf) {
+                            mast_plies += total;
+                        }
+                        if (WANT_AMAF && !G::MASK_AMAF && p.amaf) {
+                            if (amaf_plies + total > STAT_FLUSH_PLIES) {
+                                flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * 2 * G::NA, lane);
+                                amaf_plies = 0;
+                            }
+                            amaf_plies += total;
+                        }
+                        for (uint32_t base = 0; base < total; base += 32) {
+                            const uint32_t q = base + lane;
+                            uint32_t f = 0; // number of lanes whose inclusive sum is <= q == owner lane of entry q
+#pragma unroll
+                            for (int step = 16; step >= 1; step >>= 1) {
+                                const uint32_t v = __shfl_sync(FULL_MASK, incl, (f + step - 1) & 31u);
+                                if (v <= q) f += step;
+                            }
+                            f &= 31u;
+                            const uint32_t ex_f = __shfl_sync(FULL_MASK, excl, f);
+                            const int e_f = __shfl_sync(FULL_MASK, end_code, f);
+                            if (q < total) {
+                                const uint32_t t = q - ex_f;
+                                const uint32_t slot = scratch[t * 32u + f];
+                                const uint32_t pl = (leaf_turn + t) & 1u;
+                                const int u_p0 = e_f == ST_WIN_P0 ? 1 : (e_f == ST_WIN_P1 ? -1 : 0);
+                                const int u = pl == 0 ? u_p0 : -u_p0;
+                                const uint32_t inc = 1u + ((uint32_t)u << 16);
+                                if (WANT_MAST && p.mast_delta) atomicAdd(&mast_tab[pl * G::NSLOTS + slot], inc);
+                                if (WANT_AMAF && !G::MASK_AMAF && p.amaf) atomicAdd(&amaf_tab[pl * G::NSLOTS + slot], inc);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if constexpr (MASK_AMAF) {
+                        // Hex: occurrences = final stones minus leaf stones, one finished lane at a time, no atomics
+                        if (p.amaf) {
+                            __syncwarp();
+                            for (uint32_t m = fin_mask; m; m &= m - 1) {
+                                const int f = __ffs(m) - 1;
+                                const uint32_t d_f = __shfl_sync(FULL_MASK, depth, f);
+                                const int e_f = __shfl_sync(FULL_MASK, end_code, f);
+                                const int u_p0 = e_f == ST_WIN_P0 ? 1 : (e_f == ST_WIN_P1 ? -1 : 0);
                                 if (amaf_plies + d_f > STAT_FLUSH_PLIES) {
                                     flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * 2 * G::NA, lane);
                                     amaf_plies = 0;
                                 }
                                 amaf_plies += d_f;
+                                st.amaf_from_masks(sh, amaf_tab, f, lane, u_p0);
                             }
-                            if (NEED_SCRATCH) {
-                                for (uint32_t t = lane; t < d_f; t += 32) {
-                                    const uint32_t slot = scratch[t * 32u + f];
-                                    const uint32_t pl = (leaf_turn + t) & 1u;
-                                    const int u = pl == 0 ? u_p0 : -u_p0;
-                                    const uint32_t inc = 1u + ((uint32_t)u << 16);
-                                    if (WANT_MAST && p.mast_delta) atomicAdd(&mast_tab[pl * G::NSLOTS + slot], inc);
-                                    if (WANT_AMAF && !G::MASK_AMAF && p.amaf) atomicAdd(&amaf_tab[pl * G::NSLOTS + slot], inc);
-                                }
-                            }
-                            if constexpr (MASK_AMAF) {
-                                if (p.amaf) st.amaf_from_masks(sh, amaf_tab, f, lane, u_p0);
-                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                     const uint32_t rank = __popc(fin_mask & lanemask_lt());
                     if (fin) {
