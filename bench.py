@@ -232,6 +232,7 @@ def run_gpu(args):
     import torch
 
     import mcts_b200 as mb
+    from mcts_b200 import root_merge
 
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -286,13 +287,13 @@ def run_gpu(args):
                 d_leaves.data_ptr(), d_results.data_ptr(), n_leaves, k, stream=stream.cuda_stream,
                 d_amaf=d_amaf.data_ptr() if d_amaf is not None else 0,
                 d_mast_delta=d_delta.data_ptr() if d_delta is not None else 0,
-                leaf_id_base=(rank * 1000 + i) * n_leaves,
+                leaf_id_base=root_merge.leaf_id_base(rank, world, i, n_leaves),
             )
             if dist is not None:
-                # the path's one exchange step: merge MAST delta + per-root-child stats over NVLink
+                # the path's one exchange step: merge MAST delta + per-root-child stats over NVLink (NCCL)
                 if d_delta is not None:
-                    dist.all_reduce(d_delta)
-                dist.all_reduce(d_root)
+                    root_merge.merge_sum_(d_delta)
+                root_merge.merge_sum_(d_root)
 
         for i in range(warmup):
             step(i)
@@ -337,11 +338,10 @@ def run_gpu(args):
             barrier()
             t0 = time.perf_counter()
             for i in range(steps):
-                r = g.simulate_many(leaves, k, stats=mast, want_mast_delta=want_delta, want_amaf=w["amaf"], leaf_id_base=(rank * 1000 + i) * n_leaves)
+                r = g.simulate_many(leaves, k, stats=mast, want_mast_delta=want_delta, want_amaf=w["amaf"],
+                                    leaf_id_base=root_merge.leaf_id_base(rank, world, i, n_leaves))
                 if dist is not None and want_delta:
-                    dd = torch.from_numpy(r.mast_delta.view(np.int32).reshape(-1).copy()).to(dev)
-                    dist.all_reduce(dd)
-                    dd.cpu()
+                    root_merge.merge_mast_delta(r.mast_delta, device=dev)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if dist is not None:
