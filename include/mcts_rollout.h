@@ -200,6 +200,66 @@ int mr_comm_unique_id(uint8_t id[MR_COMM_ID_BYTES]);
 int mr_comm_init(mr_ctx *ctx, const uint8_t id[MR_COMM_ID_BYTES], int rank, int world_size);
 int mr_comm_allreduce_i32(mr_ctx *ctx, void *d_buf, size_t n, void *stream);
 
+/*
+ * ---- Batched leaf-gather search driver ----
+ * A host tree (arena, UCB1 / UCB1-Tuned selection, expansion, aggregated backprop) whose simulation phase
+ * is the GPU engine: per batch it runs `batch_leaves` descents holding virtual loss (search/shared.rs:569-736,
+ * 665-671, 787-805), submits the leaves as one batch of `playouts_per_leaf` playouts each, and applies the
+ * aggregated results along every path (backprop.rs:704-731 with node.rs:673-681 summed over the k trials).
+ * With batch_leaves = 1 it is the reference's sequential loop (search/search_impl.rs:76-114); larger batches
+ * are the leaf-parallel generalisation of the tree-parallel worker loop (search/parallel.rs:188-251).
+ * In the reference this driver is Rust; here it is C++ inside the library because no Rust toolchain exists
+ * in the build image -- a Rust host would keep its own tree and call mr_submit / mr_wait directly.
+ */
+enum mr_select { MR_SELECT_UCB1 = 0, MR_SELECT_UCB1_TUNED = 1 }; /* select/ucb.rs:9-146 */
+enum mr_qinit { MR_QINIT_PARENT = 0, MR_QINIT_INFINITY = 1 };     /* node.rs:95-159 */
+
+typedef struct {
+    uint32_t game;              /* mr_game */
+    uint32_t policy;            /* mr_policy */
+    uint32_t select;            /* mr_select */
+    uint32_t q_init;            /* mr_qinit */
+    uint32_t max_iterations;    /* SearchConfig.max_iterations: number of leaf selections */
+    uint32_t batch_leaves;      /* leaves gathered per GPU batch (1 = the reference's sequential loop) */
+    uint32_t playouts_per_leaf; /* SearchConfig.num_rollouts_per_leaf */
+    uint32_t expand_threshold;  /* SearchConfig.expand_threshold (default 1) */
+    uint32_t max_playout_depth; /* 0 = unlimited */
+    uint32_t reserved;
+    double exploration_c;       /* sqrt(2) by default (select/ucb.rs:22-27) */
+    double epsilon;             /* MR_EPS_MAST */
+    uint64_t seed;
+} mr_search_desc;
+
+typedef struct {
+    uint16_t action; /* compact action code, as in traces */
+    uint16_t pad;
+    uint32_t visits;
+    int64_t score[2]; /* sum of utilities per player */
+} mr_root_child;
+
+typedef struct {
+    uint64_t playouts;
+    uint64_t playout_plies; /* sum of playout depths (accum_depth without the tree part) */
+    uint64_t nodes;
+    uint32_t batches;
+    uint32_t max_tree_depth;
+    double seconds_select;
+    double seconds_gpu;
+    double seconds_backprop;
+} mr_search_stats;
+
+/* The host-side `Game` surface the driver expands nodes with (generate_actions order == child order,
+ * game.rs:144-211).  Exposed so that hosts and tests can step leaf records without a second rules copy. */
+int mr_generate_actions(int game, const mr_leaf *state, uint16_t *out /* [MR_MAX_ROOT_CHILDREN] */);
+int mr_apply(int game, mr_leaf *state, uint16_t action);
+int mr_terminal_status(int game, const mr_leaf *state); /* mr_outcome */
+
+#define MR_MAX_ROOT_CHILDREN 256
+/* Runs one search from `root`; writes the chosen action (RobustChild: most visits, then expected score,
+ * select/basic.rs:13-45), the root children's statistics (children[MR_MAX_ROOT_CHILDREN]) and timing. */
+int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, uint16_t *best_action,
+              mr_root_child *children, uint32_t *n_children, mr_search_stats *stats);
+
 /* Integer-issue micro-benchmark used as the roofline denominator (DESIGN.md "Roofline"): runs a
  * dependent-chain kernel of `kind` (0 = LOP3, 1 = IADD3, 2 = SHF, 3 = IMAD, 4 = POPC, 5 = LOP3+IMAD mix)
  * on every SM and returns thread-level operations per second. */

@@ -4,6 +4,7 @@ The compute path is hand-written sm_100a CUDA behind the C ABI in include/mcts_r
 (libmcts_b200.so, built in-tree by mcts_b200.build).  There is no CPU fallback.
 """
 from ._lib import LEAF_DTYPE, RECORD_DTYPE, RESULT_DTYPE, STAT_DTYPE, EXPORTS, RolloutError, load
+from .search import GpuSearch, SearchResult
 from .rollout import (
     BatchResult,
     DecisiveMoveWin,
@@ -16,6 +17,9 @@ from .rollout import (
     Policy,
     Trial,
     Uniform,
+    apply,
+    generate_actions,
+    terminal_status,
     initial_state,
     make_leaf,
     num_actions,
@@ -24,5 +28,6 @@ from .rollout import (
 __all__ = [
     "BatchResult", "DecisiveMoveWin", "EndType", "EpsilonGreedyMast", "Game", "GpuRollout", "MastTable", "Outcome",
     "Policy", "Trial", "Uniform", "initial_state", "make_leaf", "num_actions", "LEAF_DTYPE", "RECORD_DTYPE",
-    "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load",
+    "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load", "GpuSearch", "SearchResult", "apply",
+    "generate_actions", "terminal_status",
 ]

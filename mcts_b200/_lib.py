@@ -39,6 +39,42 @@ class BatchDesc(C.Structure):
     ]
 
 
+class SearchDesc(C.Structure):
+    _fields_ = [
+        ("game", C.c_uint32),
+        ("policy", C.c_uint32),
+        ("select", C.c_uint32),
+        ("q_init", C.c_uint32),
+        ("max_iterations", C.c_uint32),
+        ("batch_leaves", C.c_uint32),
+        ("playouts_per_leaf", C.c_uint32),
+        ("expand_threshold", C.c_uint32),
+        ("max_playout_depth", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("exploration_c", C.c_double),
+        ("epsilon", C.c_double),
+        ("seed", C.c_uint64),
+    ]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [
+        ("playouts", C.c_uint64),
+        ("playout_plies", C.c_uint64),
+        ("nodes", C.c_uint64),
+        ("batches", C.c_uint32),
+        ("max_tree_depth", C.c_uint32),
+        ("seconds_select", C.c_double),
+        ("seconds_gpu", C.c_double),
+        ("seconds_backprop", C.c_double),
+    ]
+
+
+ROOT_CHILD_DTYPE = np.dtype([("action", "<u2"), ("pad", "<u2"), ("visits", "<u4"), ("score", "<i8", (2,))])
+assert ROOT_CHILD_DTYPE.itemsize == 24
+MAX_ROOT_CHILDREN = 256
+
+
 class RolloutError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"{ERR_NAMES.get(code, code)}: {message}")
@@ -65,6 +101,10 @@ EXPORTS = [
     "mr_comm_init",
     "mr_comm_allreduce_i32",
     "mr_measure_int_peak",
+    "mr_search",
+    "mr_generate_actions",
+    "mr_apply",
+    "mr_terminal_status",
 ]
 
 _lib = None
@@ -103,6 +143,10 @@ def load() -> C.CDLL:
     L.mr_comm_init.argtypes = [vp, vp, i32, i32]
     L.mr_comm_allreduce_i32.argtypes = [vp, vp, C.c_size_t, vp]
     L.mr_measure_int_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.mr_generate_actions.argtypes = [i32, vp, vp]
+    L.mr_apply.argtypes = [i32, vp, C.c_uint16]
+    L.mr_terminal_status.argtypes = [i32, vp]
+    L.mr_search.argtypes = [vp, C.POINTER(SearchDesc), vp, C.POINTER(C.c_uint16), vp, C.POINTER(u32), C.POINTER(SearchStats)]
     _lib = L
     return L
 

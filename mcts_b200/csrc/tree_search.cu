@@ -1,0 +1,368 @@
+// tree_search.cu -- batched leaf-gather MCTS driver over the GPU rollout engine (host code only).
+//
+// What it mirrors in the reference (thomasmarsh/mcts):
+//   descent ............ select_step, search/shared.rs:569-736 (expand :220-289, one virtual loss per edge :665-671)
+//   child choice ....... UCB1 / UCB1-Tuned, select/ucb.rs:9-146, unvisited value node.rs:139-159,
+//                        arg-max with random offset + prime stride, strict '>', select/mod.rs:343-386
+//   leaf fan-out ....... num_rollouts_per_leaf with k-1 extra virtual loss, search_impl.rs:101-113, shared.rs:787-805
+//   backprop ........... backprop.rs:704-731 with ChildArray::update / NodeStats::update (node.rs:295-302,673-681)
+//                        summed over the k trials of a leaf (exact: utilities are +1 / 0 / -1)
+//   MAST table ......... TreeStats.player_actions, written for playout trace AND tree path (backprop.rs:833-870)
+//   final move ......... RobustChild: (visits, expected score) lexicographic max, select/basic.rs:13-45
+// The tree (arena, edge statistics in the parent's child arrays, root_stats) stays on the host; only the
+// simulation phase crosses the C ABI (mr_submit / mr_wait).  Tie-break draws of the tree come from the same
+// Philox4x32-10 generator as the playouts, on their own stream: ctr = (descent id, depth, 0, 2).
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "host_games.h"
+#include "mcts_rollout.h"
+
+namespace {
+
+const uint32_t kPrimes[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991,
+                              53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693};
+
+uint32_t philox_word0(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+struct Stats { // NodeStats / one ChildArray row
+    uint32_t visits = 0, vloss = 0;
+    int64_t score[2] = {0, 0}, sumsq[2] = {0, 0};
+};
+// node.rs:126-133
+inline double expected_score(const Stats &s, int player) {
+    if (s.visits == 0) return 0.0;
+    const double lv = (double)s.vloss;
+    return ((double)s.score[player] - lv) / ((double)s.visits + lv);
+}
+
+enum : uint8_t { UNEXPANDED = 0, EXPANDED = 1, TERMINAL = 2 };
+
+struct Node {
+    mr_leaf state;
+    uint8_t status = UNEXPANDED;
+    uint8_t player = 0;
+    uint16_t n_children = 0;
+    uint32_t first = 0; // index of child 0 in the edge arrays
+};
+
+struct PathEntry {
+    uint32_t node;
+    uint32_t idx; // this node's slot in its parent's child array (unused for the root)
+};
+
+struct Tree {
+    int game;
+    std::vector<Node> nodes;
+    std::vector<uint16_t> action;
+    std::vector<int32_t> child; // -1 = not created yet
+    std::vector<Stats> edge;
+    Stats root_stats;
+    uint32_t max_depth = 0;
+
+    uint32_t add_node(const mr_leaf &s) {
+        Node n;
+        n.state = s;
+        n.player = s.turn;
+        nodes.push_back(n);
+        return (uint32_t)nodes.size() - 1;
+    }
+    // search/shared.rs:220-289: terminal_status first; otherwise children in generate_actions order
+    void expand(uint32_t id) {
+        Node &n = nodes[id];
+        if (mr_host::terminal_status(game, n.state) != MR_NOT_TERMINAL) {
+            n.status = TERMINAL;
+            return;
+        }
+        uint16_t acts[MR_MAX_ROOT_CHILDREN];
+        const int cnt = mr_host::generate_actions(game, n.state, acts);
+        if (cnt == 0) { // cannot be expanded further; the playout loop scores it as a draw (simulate.rs:112-116)
+            n.status = TERMINAL;
+            return;
+        }
+        n.first = (uint32_t)action.size();
+        n.n_children = (uint16_t)cnt;
+        for (int i = 0; i < cnt; ++i) {
+            action.push_back(acts[i]);
+            child.push_back(-1);
+            edge.push_back(Stats());
+        }
+        n.status = EXPANDED;
+    }
+};
+
+struct Search {
+    mr_ctx *ctx;
+    const mr_search_desc *d;
+    Tree t;
+    std::vector<mr_action_stat> mast; // [2][NA], TreeStats.player_actions
+    int na;
+
+    const Stats &current_stats(const std::vector<PathEntry> &path) const {
+        if (path.size() == 1) return t.root_stats;
+        const PathEntry &me = path.back();
+        const Node &parent = t.nodes[path[path.size() - 2].node];
+        return t.edge[parent.first + me.idx];
+    }
+
+    // select/mod.rs:343-386 with select/ucb.rs scores
+    uint32_t best_child(const std::vector<PathEntry> &path, uint32_t descent) {
+        const Node &node = t.nodes[path.back().node];
+        const int player = node.player;
+        const Stats &cur = current_stats(path);
+        const double parent_log = std::log(std::max(1.0, (double)cur.visits));
+        const double c = d->exploration_c;
+        // node.rs:139-159 value_estimate_unvisited
+        double q_unvisited;
+        if (d->q_init == MR_QINIT_INFINITY) q_unvisited = 10000.0;
+        else q_unvisited = cur.visits == 0 ? 10000.0 : expected_score(cur, player);
+        double unvisited_value;
+        if (d->select == MR_SELECT_UCB1_TUNED) unvisited_value = q_unvisited + (parent_log * std::min(1.0, 1.0) + c * std::sqrt(parent_log));
+        else unvisited_value = q_unvisited + c * std::sqrt(parent_log);
+
+        const uint32_t n = node.n_children;
+        const uint32_t r = mulhi32(philox_word0(d->seed, descent, (uint32_t)path.size() - 1, 0, 2), 16u * n);
+        uint32_t i = r / 16u;
+        const uint32_t stride = kPrimes[r % 16u];
+        bool have = false;
+        double best = 0.0;
+        uint32_t best_i = i;
+        for (uint32_t k = 0; k < n; ++k) {
+            const Stats &e = t.edge[node.first + i];
+            double score;
+            if (t.child[node.first + i] < 0) {
+                score = unvisited_value;
+            } else {
+                const double exploit = expected_score(e, player);
+                const double total = (double)(e.visits + e.vloss);
+                if (d->select == MR_SELECT_UCB1_TUNED) {
+                    const double var = std::max(0.0, (double)e.sumsq[player] / total - exploit * exploit);
+                    const double frac = parent_log / total;
+                    score = exploit + (frac * std::min(1.0, var) + c * std::sqrt(frac));
+                } else {
+                    score = exploit + c * std::sqrt(parent_log / total);
+                }
+            }
+            if (!have || score > best) {
+                have = true;
+                best = score;
+                best_i = i;
+            }
+            i = (i + stride) % n;
+        }
+        return best_i;
+    }
+
+    // search/shared.rs:569-736
+    void select(uint32_t descent, std::vector<PathEntry> &path) {
+        path.clear();
+        uint32_t cur = 0, incoming = 0;
+        for (;;) {
+            path.push_back({cur, incoming});
+            const uint32_t num_visits = current_stats(path).visits;
+            if (t.nodes[cur].status == TERMINAL) return;
+            if (num_visits < d->expand_threshold) return;
+            if (t.nodes[cur].status == UNEXPANDED) {
+                t.expand(cur);
+                if (t.nodes[cur].status == TERMINAL) return;
+            }
+            const uint32_t best = best_child(path, descent);
+            incoming = best;
+            const uint32_t slot = t.nodes[cur].first + best;
+            t.edge[slot].vloss += 1; // one virtual loss per traversed edge
+            if (t.child[slot] >= 0) {
+                cur = (uint32_t)t.child[slot];
+            } else {
+                mr_leaf s = t.nodes[cur].state;
+                mr_host::apply(t.game, s, t.action[slot]);
+                const uint32_t id = t.add_node(s);
+                t.child[slot] = (int32_t)id;
+                cur = id;
+                if (d->expand_threshold > 0) {
+                    path.push_back({cur, incoming});
+                    return;
+                }
+            }
+        }
+    }
+
+    // shared.rs:787-805: k-1 extra virtual losses on every edge of the path
+    void add_path_virtual_loss(const std::vector<PathEntry> &path, uint32_t extra) {
+        for (size_t i = 1; i < path.size(); ++i) t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += extra;
+    }
+
+    // k trials of one leaf, aggregated
+    void backprop(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k) {
+        const int64_t nonzero = (int64_t)k - r.draws;
+        const int64_t u[2] = {(int64_t)r.wins[0] - (nonzero - r.wins[0]), (int64_t)r.wins[1] - (nonzero - r.wins[1])};
+        for (size_t i = path.size(); i-- > 0;) {
+            Stats &s = i == 0 ? t.root_stats : t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
+            s.visits += k;
+            for (int p = 0; p < 2; ++p) {
+                s.score[p] += u[p];
+                s.sumsq[p] += nonzero;
+            }
+            if (i > 0) s.vloss -= k; // each trial's backprop removes one (backprop.rs:722-725)
+            if (i > 0 && !mast.empty()) {
+                // GLOBAL write for the tree-path part of amaf_actions (backprop.rs:833-870): the edge into this
+                // node was played by the parent's mover
+                const Node &parent = t.nodes[path[i - 1].node];
+                const int pl = parent.player;
+                mr_action_stat &m = mast[(size_t)pl * na + mr_host::action_id(t.game, t.action[parent.first + path[i].idx])];
+                m.visits += k;
+                m.score += (int32_t)u[pl];
+            }
+        }
+        if (path.size() > t.max_depth) t.max_depth = (uint32_t)path.size();
+    }
+};
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+extern "C" int mr_generate_actions(int game, const mr_leaf *state, uint16_t *out) {
+    if (game < 0 || game >= MR_NUM_GAMES || !state || !out) return -1;
+    return mr_host::generate_actions(game, *state, out);
+}
+extern "C" int mr_apply(int game, mr_leaf *state, uint16_t action) {
+    if (game < 0 || game >= MR_NUM_GAMES || !state) return MR_ERR_INVALID;
+    mr_host::apply(game, *state, action);
+    return MR_OK;
+}
+extern "C" int mr_terminal_status(int game, const mr_leaf *state) {
+    if (game < 0 || game >= MR_NUM_GAMES || !state) return -1;
+    return mr_host::terminal_status(game, *state);
+}
+
+extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, uint16_t *best_action,
+                         mr_root_child *children, uint32_t *n_children, mr_search_stats *stats) {
+    if (!ctx || !desc || !root || !best_action) return MR_ERR_INVALID;
+    if (desc->game >= MR_NUM_GAMES || desc->batch_leaves == 0 || desc->playouts_per_leaf == 0 || desc->max_iterations == 0)
+        return MR_ERR_INVALID;
+    Search s;
+    s.ctx = ctx;
+    s.d = desc;
+    s.t.game = (int)desc->game;
+    s.na = mr_num_actions((int)desc->game);
+    if (desc->policy == MR_EPS_MAST) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
+    s.t.nodes.reserve(desc->max_iterations + 16);
+    s.t.add_node(*root);
+
+    const uint32_t B = desc->batch_leaves, k = desc->playouts_per_leaf;
+    std::vector<std::vector<PathEntry>> paths(B);
+    std::vector<mr_leaf> leaves(B);
+    std::vector<mr_leaf_result> results(B);
+    std::vector<mr_action_stat> delta(desc->policy == MR_EPS_MAST ? (size_t)2 * s.na : 0);
+    mr_search_stats st;
+    memset(&st, 0, sizeof st);
+
+    uint32_t done = 0;
+    while (done < desc->max_iterations) {
+        const uint32_t nb = std::min(B, desc->max_iterations - done);
+        double t0 = now_s();
+        for (uint32_t b = 0; b < nb; ++b) {
+            s.select(done + b, paths[b]);
+            if (k > 1) s.add_path_virtual_loss(paths[b], k - 1);
+            leaves[b] = s.t.nodes[paths[b].back().node].state;
+        }
+        double t1 = now_s();
+        mr_batch_desc bd;
+        memset(&bd, 0, sizeof bd);
+        bd.game = desc->game;
+        bd.policy = desc->policy;
+        bd.n_leaves = nb;
+        bd.playouts_per_leaf = k;
+        bd.max_playout_depth = desc->max_playout_depth;
+        bd.flags = desc->policy == MR_EPS_MAST ? MR_WANT_MAST_DELTA : 0;
+        bd.seed = desc->seed;
+        bd.leaf_id_base = done;
+        bd.epsilon = desc->epsilon;
+        int rc = mr_playout_batch(ctx, &bd, leaves.data(), s.mast.empty() ? nullptr : s.mast.data(), results.data(), nullptr,
+                                  delta.empty() ? nullptr : delta.data(), nullptr, nullptr, nullptr);
+        if (rc != MR_OK) return rc;
+        double t2 = now_s();
+        for (uint32_t b = 0; b < nb; ++b) {
+            s.backprop(paths[b], results[b], k);
+            st.playout_plies += results[b].sum_depth;
+        }
+        for (size_t i = 0; i < delta.size(); ++i) { // playout-trace part of the GLOBAL write
+            s.mast[i].visits += delta[i].visits;
+            s.mast[i].score += delta[i].score;
+        }
+        double t3 = now_s();
+        st.seconds_select += t1 - t0;
+        st.seconds_gpu += t2 - t1;
+        st.seconds_backprop += t3 - t2;
+        st.batches += 1;
+        st.playouts += (uint64_t)nb * k;
+        done += nb;
+    }
+
+    // final move: RobustChild over the root children with the same random-offset arg-max (core.rs:138-198)
+    const Node &rootn = s.t.nodes[0];
+    if (rootn.status != EXPANDED || rootn.n_children == 0) {
+        *best_action = 0xffff;
+        if (n_children) *n_children = 0;
+        if (stats) *stats = st;
+        return MR_OK;
+    }
+    const uint32_t n = rootn.n_children;
+    const int player = rootn.player;
+    const double q_unvisited =
+        desc->q_init == MR_QINIT_INFINITY ? 10000.0 : (s.t.root_stats.visits == 0 ? 10000.0 : expected_score(s.t.root_stats, player));
+    const uint32_t r = mulhi32(philox_word0(desc->seed, 0xffffffffu, 0, 0, 2), 16u * n);
+    uint32_t i = r / 16u;
+    const uint32_t stride = kPrimes[r % 16u];
+    bool have = false;
+    int64_t best_v = 0;
+    double best_q = 0.0;
+    uint32_t best_i = i;
+    for (uint32_t c = 0; c < n; ++c) {
+        const Stats &e = s.t.edge[rootn.first + i];
+        const bool created = s.t.child[rootn.first + i] >= 0;
+        const int64_t v = created ? (int64_t)e.visits : 0;
+        const double q = created ? expected_score(e, player) : q_unvisited;
+        if (!have || v > best_v || (v == best_v && q > best_q)) {
+            have = true;
+            best_v = v;
+            best_q = q;
+            best_i = i;
+        }
+        i = (i + stride) % n;
+    }
+    *best_action = s.t.action[rootn.first + best_i];
+    if (children && n_children) {
+        *n_children = n;
+        for (uint32_t c = 0; c < n && c < MR_MAX_ROOT_CHILDREN; ++c) {
+            const Stats &e = s.t.edge[rootn.first + c];
+            children[c].action = s.t.action[rootn.first + c];
+            children[c].pad = 0;
+            children[c].visits = e.visits;
+            children[c].score[0] = e.score[0];
+            children[c].score[1] = e.score[1];
+        }
+    }
+    st.nodes = s.t.nodes.size();
+    st.max_tree_depth = s.t.max_depth;
+    if (stats) *stats = st;
+    return MR_OK;
+}

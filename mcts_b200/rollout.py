@@ -82,6 +82,26 @@ def initial_state(game: Game) -> np.ndarray:
     return make_leaf(board, turn, flag)
 
 
+def generate_actions(game: Game, state: np.ndarray) -> list[int]:
+    """Game::generate_actions on a leaf record (host rules of the tree driver)."""
+    out = np.zeros(256, dtype=np.uint16)
+    st = np.ascontiguousarray(state, dtype=LEAF_DTYPE)
+    n = _lib.load().mr_generate_actions(int(game), ptr(st), ptr(out))
+    return [int(a) for a in out[:n]]
+
+
+def apply(game: Game, state: np.ndarray, action: int) -> np.ndarray:
+    """Game::apply on a leaf record."""
+    st = np.ascontiguousarray(state, dtype=LEAF_DTYPE).copy()
+    _lib.load().mr_apply(int(game), ptr(st), int(action))
+    return st
+
+
+def terminal_status(game: Game, state: np.ndarray) -> Outcome:
+    st = np.ascontiguousarray(state, dtype=LEAF_DTYPE)
+    return Outcome(_lib.load().mr_terminal_status(int(game), ptr(st)))
+
+
 def num_actions(game: Game) -> int:
     return _lib.load().mr_num_actions(int(game))
 

@@ -135,16 +135,33 @@ int orc_naive_hex_winner(const uint8_t occ0[121], const uint8_t occ1[121], int l
 int orc_stress_othello(uint64_t num_games, uint64_t *games_done, uint64_t *plies_done);
 int orc_stress_through(int game, uint64_t num_games, uint64_t *goal_wins, uint64_t *stuck_games);
 
-/* ---- config-1 CPU search (search.c): UCB1 + uniform rollouts, single thread ---- */
+/* ---- the MCTS loop around the playout path (search.c): BASELINE.json config 1 on the CPU, and the checker of
+ * the product's GPU-driven tree driver ---- */
 typedef struct {
-    uint32_t iterations;
-    double exploration_c; /* sqrt(2) default (select/ucb.rs:22-27) */
+    int game;
+    int policy;
+    int select;                 /* 0 UCB1, 1 UCB1-Tuned (select/ucb.rs) */
+    int q_init;                 /* 0 Parent, 1 Infinity (node.rs:95-159) */
+    uint32_t max_iterations;    /* leaf selections */
+    uint32_t batch_leaves;      /* 1 = the reference's sequential loop */
+    uint32_t playouts_per_leaf; /* num_rollouts_per_leaf */
     uint32_t expand_threshold;
+    uint32_t max_playout_depth;
+    int threads;                /* for the playouts of one batch */
+    double exploration_c;
+    uint64_t eps_threshold;
     uint64_t seed;
-} orc_search_desc;
-int orc_uct_search(int game, const orc_state *root, const orc_search_desc *d, uint16_t *best_action,
-                   uint32_t *root_visits /* [n_root_children] */, uint16_t *root_actions, uint32_t *n_children,
-                   uint64_t *total_playout_plies);
+} orc_search_cfg;
+
+typedef struct {
+    uint16_t action;
+    uint16_t pad;
+    uint32_t visits;
+    int64_t score[2];
+} orc_root_child;
+
+int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_action, orc_root_child *children,
+               uint32_t *n_children, uint64_t *playout_plies);
 
 #ifdef __cplusplus
 }

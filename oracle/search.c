@@ -1,0 +1,332 @@
+/*
+ * oracle/search.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the reference's MCTS loop around the playout path, used (a) as BASELINE.json
+ * config 1 (Connect4 UCT, uniform rollouts, single thread, "rollouts/sec/core" as defined at
+ * mcts/src/strategies/mcts/search/core.rs:395-398) and (b) to check the product's GPU-driven tree driver
+ * root statistics bit for bit.
+ *
+ * Reference lines followed:
+ *   iteration loop ........ search/search_impl.rs:76-114 (select, k rollouts of the leaf, k backprops)
+ *   select_step ........... search/shared.rs:569-736; expand :220-289; virtual loss :665-671, :787-805
+ *   UCB1 / UCB1-Tuned ..... select/ucb.rs:9-146; unvisited value node.rs:139-159; expected score node.rs:126-133
+ *   random-offset arg-max . select/mod.rs:343-386 (strict '>', proven-loss skipping inert without the solver)
+ *   backprop .............. backprop.rs:686-731; NodeStats/ChildArray update node.rs:295-302, 673-681
+ *   GLOBAL (MAST) write ... backprop.rs:833-870 (playout trace + tree path)
+ *   final action .......... RobustChild select/basic.rs:13-45 through core.rs:138-198
+ *
+ * Batched mode (batch_leaves > 1) is the deterministic, sequential statement of what the tree-parallel
+ * workers do concurrently (search/parallel.rs:188-251): B descents that each leave their virtual losses in
+ * place, then all simulations, then all backprops.
+ * Tree tie-break draws: Philox4x32-10, ctr = (descent id, depth, 0, 2), word 0.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static const uint32_t PRIMES[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991,
+                                    53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693};
+
+typedef struct {
+    uint32_t visits, vloss;
+    int64_t score[2], sumsq[2];
+} stats_t;
+
+typedef struct {
+    orc_state state;
+    int status; /* 0 leaf (unexpanded), 1 expanded, 2 terminal */
+    int player;
+    int n_children;
+    uint32_t first;
+} node_t;
+
+typedef struct {
+    int game;
+    node_t *nodes;
+    size_t n_nodes, cap_nodes;
+    uint16_t *action;
+    int32_t *child;
+    stats_t *edge;
+    size_t n_edges, cap_edges;
+    stats_t root_stats;
+} tree_t;
+
+typedef struct {
+    uint32_t node, idx;
+} entry_t;
+
+static double expected_score(const stats_t *s, int player) { /* node.rs:126-133 */
+    if (s->visits == 0) return 0.0;
+    double lv = (double)s->vloss;
+    return ((double)s->score[player] - lv) / ((double)s->visits + lv);
+}
+
+static uint32_t tree_draw(uint64_t seed, uint32_t descent, uint32_t depth) {
+    uint32_t ctr[4] = {descent, depth, 0, 2}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, out[4];
+    orc_philox4x32_10(ctr, key, out);
+    return out[0];
+}
+
+static uint32_t add_node(tree_t *t, const orc_state *s) {
+    if (t->n_nodes == t->cap_nodes) {
+        t->cap_nodes = t->cap_nodes ? t->cap_nodes * 2 : 1024;
+        t->nodes = (node_t *)realloc(t->nodes, t->cap_nodes * sizeof(node_t));
+    }
+    node_t *n = &t->nodes[t->n_nodes];
+    memset(n, 0, sizeof *n);
+    n->state = *s;
+    n->player = orc_player_to_move(t->game, s);
+    return (uint32_t)t->n_nodes++;
+}
+
+static void expand(tree_t *t, uint32_t id) { /* shared.rs:220-289 */
+    node_t *n = &t->nodes[id];
+    if (orc_terminal_status(t->game, &n->state) != ORC_NOT_TERMINAL) {
+        n->status = 2;
+        return;
+    }
+    uint16_t acts[ORC_MAX_ACTIONS];
+    int cnt = orc_generate_actions(t->game, &n->state, acts);
+    if (cnt == 0) { /* the reference debug_asserts this away; a stuck position is played out as a draw */
+        n->status = 2;
+        return;
+    }
+    if (t->n_edges + (size_t)cnt > t->cap_edges) {
+        while (t->n_edges + (size_t)cnt > t->cap_edges) t->cap_edges = t->cap_edges ? t->cap_edges * 2 : 4096;
+        t->action = (uint16_t *)realloc(t->action, t->cap_edges * sizeof(uint16_t));
+        t->child = (int32_t *)realloc(t->child, t->cap_edges * sizeof(int32_t));
+        t->edge = (stats_t *)realloc(t->edge, t->cap_edges * sizeof(stats_t));
+    }
+    n->first = (uint32_t)t->n_edges;
+    n->n_children = cnt;
+    for (int i = 0; i < cnt; ++i) {
+        t->action[t->n_edges] = acts[i];
+        t->child[t->n_edges] = -1;
+        memset(&t->edge[t->n_edges], 0, sizeof(stats_t));
+        t->n_edges++;
+    }
+    n->status = 1;
+}
+
+static const stats_t *current_stats(const tree_t *t, const entry_t *path, int len) {
+    if (len == 1) return &t->root_stats;
+    return &t->edge[t->nodes[path[len - 2].node].first + path[len - 1].idx];
+}
+
+typedef struct {
+    int select; /* 0 UCB1, 1 UCB1-Tuned */
+    int q_init; /* 0 Parent, 1 Infinity */
+    double c;
+    uint32_t expand_threshold;
+    uint64_t seed;
+} sel_cfg;
+
+static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *path, int len, uint32_t descent) {
+    const node_t *node = &t->nodes[path[len - 1].node];
+    int player = node->player;
+    const stats_t *cur = current_stats(t, path, len);
+    double parent_log = log(fmax(1.0, (double)cur->visits)); /* ucb.rs:34-37 */
+    double q_unvisited = cfg->q_init == 1 ? 10000.0 : (cur->visits == 0 ? 10000.0 : expected_score(cur, player));
+    double unvisited_value = cfg->select == 1 ? q_unvisited + (parent_log * fmin(1.0, 1.0) + cfg->c * sqrt(parent_log))
+                                              : q_unvisited + cfg->c * sqrt(parent_log);
+    uint32_t n = (uint32_t)node->n_children;
+    uint32_t r = (uint32_t)(((uint64_t)tree_draw(cfg->seed, descent, (uint32_t)len - 1) * (16u * n)) >> 32);
+    uint32_t i = r / 16u, stride = PRIMES[r % 16u];
+    int have = 0;
+    double best = 0.0;
+    uint32_t best_i = i;
+    for (uint32_t k = 0; k < n; ++k) {
+        const stats_t *e = &t->edge[node->first + i];
+        double score;
+        if (t->child[node->first + i] < 0) {
+            score = unvisited_value;
+        } else {
+            double exploit = expected_score(e, player);
+            double total = (double)(e->visits + e->vloss);
+            if (cfg->select == 1) { /* ucb.rs:90-132 */
+                double var = fmax(0.0, (double)e->sumsq[player] / total - exploit * exploit);
+                double frac = parent_log / total;
+                score = exploit + (frac * fmin(1.0, var) + cfg->c * sqrt(frac));
+            } else { /* ucb.rs:40-52 */
+                score = exploit + cfg->c * sqrt(parent_log / total);
+            }
+        }
+        if (!have || score > best) {
+            have = 1;
+            best = score;
+            best_i = i;
+        }
+        i = (i + stride) % n;
+    }
+    return best_i;
+}
+
+/* shared.rs:569-736; returns the path length */
+static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t *path) {
+    int len = 0;
+    uint32_t cur = 0, incoming = 0;
+    for (;;) {
+        path[len].node = cur;
+        path[len].idx = incoming;
+        ++len;
+        uint32_t num_visits = current_stats(t, path, len)->visits;
+        if (t->nodes[cur].status == 2) return len;
+        if (num_visits < cfg->expand_threshold) return len;
+        if (t->nodes[cur].status == 0) {
+            expand(t, cur);
+            if (t->nodes[cur].status == 2) return len;
+        }
+        uint32_t best = best_child(t, cfg, path, len, descent);
+        incoming = best;
+        uint32_t slot = t->nodes[cur].first + best;
+        t->edge[slot].vloss += 1;
+        if (t->child[slot] >= 0) {
+            cur = (uint32_t)t->child[slot];
+        } else {
+            orc_state s = t->nodes[cur].state;
+            orc_apply(t->game, &s, t->action[slot]);
+            uint32_t id = add_node(t, &s);
+            t->child[slot] = (int32_t)id;
+            cur = id;
+            if (cfg->expand_threshold > 0) {
+                path[len].node = cur;
+                path[len].idx = incoming;
+                ++len;
+                return len;
+            }
+        }
+    }
+}
+
+static int action_id(int game, uint16_t a) {
+    if (game == ORC_BREAKTHROUGH || game == ORC_KNIGHTTHROUGH) return (int)(a >> 8) * 64 + (int)(a & 0xff);
+    return (int)a;
+}
+
+int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_action, orc_root_child *children,
+               uint32_t *n_children, uint64_t *playout_plies) {
+    tree_t t;
+    memset(&t, 0, sizeof t);
+    t.game = c->game;
+    add_node(&t, root);
+    sel_cfg cfg = {c->select, c->q_init, c->exploration_c, c->expand_threshold, c->seed};
+    const uint32_t B = c->batch_leaves, k = c->playouts_per_leaf;
+    const int na = orc_num_actions(c->game);
+    orc_action_stat *mast = c->policy == ORC_EPS_MAST ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    orc_action_stat *delta = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    const int max_path = 1024;
+    entry_t *paths = (entry_t *)malloc(sizeof(entry_t) * (size_t)B * max_path);
+    int *plen = (int *)malloc(sizeof(int) * B);
+    orc_state *leaves = (orc_state *)malloc(sizeof(orc_state) * B);
+    orc_leaf_result *results = (orc_leaf_result *)malloc(sizeof(orc_leaf_result) * B);
+    uint64_t plies = 0;
+
+    orc_batch_desc bd;
+    memset(&bd, 0, sizeof bd);
+    bd.game = c->game;
+    bd.policy = c->policy;
+    bd.eps_threshold = c->eps_threshold;
+    bd.max_playout_depth = c->max_playout_depth;
+    bd.seed = c->seed;
+    bd.playouts_per_leaf = k;
+
+    uint32_t done = 0;
+    while (done < c->max_iterations) {
+        uint32_t nb = B < c->max_iterations - done ? B : c->max_iterations - done;
+        for (uint32_t b = 0; b < nb; ++b) {
+            entry_t *path = paths + (size_t)b * max_path;
+            plen[b] = select_step(&t, &cfg, done + b, path);
+            for (int i = 1; i < plen[b]; ++i) /* add_path_virtual_loss(k - 1), shared.rs:787-805 */
+                t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
+            leaves[b] = t.nodes[path[plen[b] - 1].node].state;
+        }
+        bd.leaf_id_base = done;
+        if (delta) memset(delta, 0, sizeof(orc_action_stat) * 2 * (size_t)na);
+        orc_playout_batch(&bd, leaves, nb, mast, results, NULL, delta, NULL, NULL, NULL, c->threads > 0 ? c->threads : 1);
+        for (uint32_t b = 0; b < nb; ++b) {
+            const entry_t *path = paths + (size_t)b * max_path;
+            const orc_leaf_result *r = &results[b];
+            int64_t nonzero = (int64_t)k - r->draws;
+            int64_t u[2] = {(int64_t)r->wins[0] - (nonzero - r->wins[0]), (int64_t)r->wins[1] - (nonzero - r->wins[1])};
+            for (int i = plen[b] - 1; i >= 0; --i) {
+                stats_t *s = i == 0 ? &t.root_stats : &t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
+                s->visits += k;
+                for (int p = 0; p < 2; ++p) {
+                    s->score[p] += u[p];
+                    s->sumsq[p] += nonzero;
+                }
+                if (i > 0) {
+                    s->vloss -= k;
+                    if (mast) { /* tree-path part of the GLOBAL write */
+                        const node_t *parent = &t.nodes[path[i - 1].node];
+                        orc_action_stat *m = &mast[(size_t)parent->player * na + action_id(c->game, t.action[parent->first + path[i].idx])];
+                        m->visits += k;
+                        m->score += (int32_t)u[parent->player];
+                    }
+                }
+            }
+            plies += r->sum_depth;
+        }
+        if (mast)
+            for (int i = 0; i < 2 * na; ++i) {
+                mast[i].visits += delta[i].visits;
+                mast[i].score += delta[i].score;
+            }
+        done += nb;
+    }
+
+    const node_t *rootn = &t.nodes[0];
+    int rc = 0;
+    if (rootn->status != 1 || rootn->n_children == 0) {
+        *best_action = 0xffff;
+        if (n_children) *n_children = 0;
+    } else {
+        uint32_t n = (uint32_t)rootn->n_children;
+        int player = rootn->player;
+        double q_unvisited = c->q_init == 1 ? 10000.0 : (t.root_stats.visits == 0 ? 10000.0 : expected_score(&t.root_stats, player));
+        uint32_t r = (uint32_t)(((uint64_t)tree_draw(c->seed, 0xffffffffu, 0) * (16u * n)) >> 32);
+        uint32_t i = r / 16u, stride = PRIMES[r % 16u], best_i = i;
+        int have = 0;
+        int64_t best_v = 0;
+        double best_q = 0.0;
+        for (uint32_t q = 0; q < n; ++q) { /* RobustChild, basic.rs:13-45 */
+            const stats_t *e = &t.edge[rootn->first + i];
+            int created = t.child[rootn->first + i] >= 0;
+            int64_t v = created ? (int64_t)e->visits : 0;
+            double qq = created ? expected_score(e, player) : q_unvisited;
+            if (!have || v > best_v || (v == best_v && qq > best_q)) {
+                have = 1;
+                best_v = v;
+                best_q = qq;
+                best_i = i;
+            }
+            i = (i + stride) % n;
+        }
+        *best_action = t.action[rootn->first + best_i];
+        if (children && n_children) {
+            *n_children = n;
+            for (uint32_t q = 0; q < n; ++q) {
+                const stats_t *e = &t.edge[rootn->first + q];
+                children[q].action = t.action[rootn->first + q];
+                children[q].pad = 0;
+                children[q].visits = e->visits;
+                children[q].score[0] = e->score[0];
+                children[q].score[1] = e->score[1];
+            }
+        }
+    }
+    if (playout_plies) *playout_plies = plies;
+    free(t.nodes);
+    free(t.action);
+    free(t.child);
+    free(t.edge);
+    free(mast);
+    free(delta);
+    free(paths);
+    free(plen);
+    free(leaves);
+    free(results);
+    return rc;
+}

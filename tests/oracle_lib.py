@@ -46,13 +46,25 @@ class BatchDesc(C.Structure):
     ]
 
 
-class SearchDesc(C.Structure):
+class SearchCfg(C.Structure):
     _fields_ = [
-        ("iterations", C.c_uint32),
-        ("exploration_c", C.c_double),
+        ("game", C.c_int),
+        ("policy", C.c_int),
+        ("select", C.c_int),
+        ("q_init", C.c_int),
+        ("max_iterations", C.c_uint32),
+        ("batch_leaves", C.c_uint32),
+        ("playouts_per_leaf", C.c_uint32),
         ("expand_threshold", C.c_uint32),
+        ("max_playout_depth", C.c_uint32),
+        ("threads", C.c_int),
+        ("exploration_c", C.c_double),
+        ("eps_threshold", C.c_uint64),
         ("seed", C.c_uint64),
     ]
+
+
+ROOT_CHILD_DTYPE = np.dtype([("action", "<u2"), ("pad", "<u2"), ("visits", "<u4"), ("score", "<i8", (2,))])
 
 
 def build(force: bool = False) -> Path:
@@ -99,8 +111,7 @@ def lib() -> C.CDLL:
         L.orc_stress_othello.argtypes = [u64, vp, vp]
         L.orc_stress_through.argtypes = [i32, u64, vp, vp]
         L.orc_naive_hex_winner.argtypes = [vp, vp, i32]
-        if hasattr(L, "orc_uct_search"):
-            L.orc_uct_search.argtypes = [i32, vp, C.POINTER(SearchDesc), vp, vp, vp, vp, vp]
+        L.orc_search.argtypes = [C.POINTER(SearchCfg), vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -213,6 +224,20 @@ def playout_batch(
     if rc != 0:
         raise RuntimeError(f"orc_playout_batch failed: {rc}")
     return {"results": results, "amaf": amaf, "mast_delta": delta, "trace": trace, "records": rec, "final": final}
+
+
+def search(game, root, *, iterations, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,
+           max_depth=0, c=2.0 ** 0.5, eps=0.1, seed=0, threads=1):
+    """The restated reference MCTS loop with CPU playouts.  Returns (best_action, children, playout_plies)."""
+    cfg = SearchCfg(game, policy, select, q_init, iterations, batch_leaves, k, expand_threshold, max_depth, threads, c,
+                    eps_threshold(eps), seed)
+    root = np.ascontiguousarray(root, dtype=STATE_DTYPE)
+    children = np.zeros(256, dtype=ROOT_CHILD_DTYPE)
+    best, n, plies = C.c_uint16(), C.c_uint32(), C.c_uint64()
+    rc = lib().orc_search(C.byref(cfg), _p(root), C.byref(best), _p(children), C.byref(n), C.byref(plies))
+    if rc != 0:
+        raise RuntimeError(f"orc_search failed: {rc}")
+    return best.value, children[: n.value].copy(), plies.value
 
 
 def random_positions(game: int, seed: int, plies: int, n: int) -> np.ndarray:

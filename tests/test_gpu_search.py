@@ -1,0 +1,47 @@
+"""The GPU-driven tree driver (mr_search) against the restated reference loop with CPU playouts
+(oracle/search.c): same tree algorithm, same draws, bit-exact playouts => identical root statistics."""
+import numpy as np
+import pytest
+
+import oracle_lib as o
+
+pytestmark = pytest.mark.gpu
+mb = pytest.importorskip("mcts_b200")
+
+CASES = [
+    # game, policy, iterations, batch, k, select, q_init, max_depth
+    (o.CONNECT4, o.UNIFORM, 3000, 1, 1, 0, 0, 0),      # the reference's sequential loop
+    (o.CONNECT4, o.UNIFORM, 4096, 64, 8, 0, 0, 0),     # batched leaf-parallel with virtual loss
+    (o.CONNECT4, o.DECISIVE_WIN, 2048, 32, 4, 1, 1, 0),  # UCB1-Tuned + QInit::Infinity (Ucb1TunedDM)
+    (o.BREAKTHROUGH, o.EPS_MAST, 2048, 32, 16, 0, 0, 200),  # MAST table fed by kernel delta + tree path
+    (o.KNIGHTTHROUGH, o.EPS_MAST, 1024, 64, 8, 0, 0, 200),
+    (o.OTHELLO, o.DECISIVE_WIN, 1024, 32, 4, 1, 1, 0),
+    (o.HEX11, o.UNIFORM, 1024, 64, 4, 0, 0, 0),
+]
+
+
+@pytest.mark.parametrize("game,policy,iters,batch,k,select,q_init,max_depth", CASES)
+def test_search_root_statistics_bit_exact(game, policy, iters, batch, k, select, q_init, max_depth):
+    strat = {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(0.1), o.DECISIVE_WIN: mb.DecisiveMoveWin()}[policy]
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), strat, max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      max_playout_depth=max_depth, select=select, q_init=q_init, seed=77) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=policy, select=select,
+                                     q_init=q_init, max_depth=max_depth, seed=77, threads=o.host_threads())
+    assert got.playouts == iters * k
+    assert len(got.children) == len(children)
+    assert (got.children["action"] == children["action"]).all()
+    assert (got.children["visits"] == children["visits"]).all()
+    assert (got.children["score"] == children["score"]).all()
+    assert got.best_action == best
+    assert got.playout_plies == plies
+    # every iteration after the first passes through one root child: sum of child visits = (iters - 1) * k
+    assert int(got.children["visits"].sum()) == (iters - 1) * k
+
+
+def test_search_prefers_the_centre_in_connect4():
+    with mb.GpuSearch(mb.Game.CONNECT4, max_iterations=20000, batch_leaves=128, num_rollouts_per_leaf=8, seed=3) as s:
+        r = s.choose_action(mb.initial_state(mb.Game.CONNECT4))
+    assert r.best_action == 3
+    assert r.children["visits"].argmax() == 3
