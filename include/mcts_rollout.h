@@ -213,6 +213,11 @@ int mr_comm_allreduce_i32(mr_ctx *ctx, void *d_buf, size_t n, void *stream);
  */
 enum mr_select { MR_SELECT_UCB1 = 0, MR_SELECT_UCB1_TUNED = 1 }; /* select/ucb.rs:9-146 */
 enum mr_qinit { MR_QINIT_PARENT = 0, MR_QINIT_INFINITY = 1 };     /* node.rs:95-159 */
+/* MR_SEARCH_TRANSPOSITIONS: SearchConfig.use_transpositions -- a new child whose state is already in the
+ * table reuses that node (search/shared.rs:412-436, table.rs); statistics stay on the edges.  The table is
+ * keyed by the full 40-byte state record (exact, no Zobrist collisions); symmetry canonicalisation is not
+ * applied. */
+enum mr_search_flags { MR_SEARCH_TRANSPOSITIONS = 1 };
 
 typedef struct {
     uint32_t game;              /* mr_game */
@@ -224,7 +229,7 @@ typedef struct {
     uint32_t playouts_per_leaf; /* SearchConfig.num_rollouts_per_leaf */
     uint32_t expand_threshold;  /* SearchConfig.expand_threshold (default 1) */
     uint32_t max_playout_depth; /* 0 = unlimited */
-    uint32_t reserved;
+    uint32_t flags;             /* mr_search_flags */
     double exploration_c;       /* sqrt(2) by default (select/ucb.rs:22-27) */
     double epsilon;             /* MR_EPS_MAST */
     uint64_t seed;

@@ -50,7 +50,7 @@ class SearchDesc(C.Structure):
         ("playouts_per_leaf", C.c_uint32),
         ("expand_threshold", C.c_uint32),
         ("max_playout_depth", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("flags", C.c_uint32),
         ("exploration_c", C.c_double),
         ("epsilon", C.c_double),
         ("seed", C.c_uint64),

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "host_games.h"
@@ -67,8 +68,31 @@ struct PathEntry {
     uint32_t idx; // this node's slot in its parent's child array (unused for the root)
 };
 
+struct StateKey {
+    uint64_t w[5]; // the 40-byte record
+    bool operator==(const StateKey &o) const { return memcmp(w, o.w, sizeof w) == 0; }
+};
+struct StateKeyHash {
+    size_t operator()(const StateKey &k) const {
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (int i = 0; i < 5; ++i) {
+            h ^= k.w[i];
+            h *= 0x100000001b3ull;
+            h ^= h >> 29;
+        }
+        return (size_t)h;
+    }
+};
+inline StateKey key_of(const mr_leaf &s) {
+    StateKey k;
+    memcpy(k.w, &s, sizeof k.w);
+    return k;
+}
+
 struct Tree {
     int game;
+    bool use_table = false;
+    std::unordered_map<StateKey, uint32_t, StateKeyHash> table; // use_transpositions: state -> node
     std::vector<Node> nodes;
     std::vector<uint16_t> action;
     std::vector<int32_t> child; // -1 = not created yet
@@ -191,7 +215,18 @@ struct Search {
             } else {
                 mr_leaf s = t.nodes[cur].state;
                 mr_host::apply(t.game, s, t.action[slot]);
-                const uint32_t id = t.add_node(s);
+                uint32_t id;
+                if (t.use_table) { // resolve_child_id: reuse the node of an identical state (shared.rs:412-436)
+                    auto it = t.table.find(key_of(s));
+                    if (it != t.table.end()) {
+                        id = it->second;
+                    } else {
+                        id = t.add_node(s);
+                        t.table.emplace(key_of(s), id);
+                    }
+                } else {
+                    id = t.add_node(s);
+                }
                 t.child[slot] = (int32_t)id;
                 cur = id;
                 if (d->expand_threshold > 0) {
@@ -265,7 +300,9 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     s.na = mr_num_actions((int)desc->game);
     if (desc->policy == MR_EPS_MAST) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
     s.t.nodes.reserve(desc->max_iterations + 16);
+    s.t.use_table = (desc->flags & MR_SEARCH_TRANSPOSITIONS) != 0;
     s.t.add_node(*root);
+    if (s.t.use_table) s.t.table.emplace(key_of(*root), 0u);
 
     const uint32_t B = desc->batch_leaves, k = desc->playouts_per_leaf;
     std::vector<std::vector<PathEntry>> paths(B);

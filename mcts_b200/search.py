@@ -40,11 +40,11 @@ class GpuSearch:
 
     def __init__(self, game: Game, strategy=None, *, max_iterations=10_000, batch_leaves=256, num_rollouts_per_leaf=1,
                  expand_threshold=1, max_playout_depth=0, exploration_constant=math.sqrt(2.0), select=SELECT_UCB1,
-                 q_init=QINIT_PARENT, seed=0, devices=1):
+                 q_init=QINIT_PARENT, use_transpositions=False, seed=0, devices=1):
         self.rollout = GpuRollout(game, strategy or Uniform(), devices=devices, seed=seed, max_playout_depth=max_playout_depth)
         self.desc = SearchDesc(
             int(game), int(self.rollout.strategy.policy), select, q_init, max_iterations, batch_leaves,
-            num_rollouts_per_leaf, expand_threshold, max_playout_depth, 0, exploration_constant,
+            num_rollouts_per_leaf, expand_threshold, max_playout_depth, 1 if use_transpositions else 0, exploration_constant,
             float(getattr(self.rollout.strategy, "epsilon", 0.0)), int(seed) & 0xFFFFFFFFFFFFFFFF,
         )
 
@@ -65,3 +65,37 @@ class GpuSearch:
         self.rollout._check(L.mr_search(self.rollout._h, C.byref(self.desc), ptr(root), C.byref(best), ptr(children), C.byref(n), C.byref(st)))
         return SearchResult(best.value, children[: n.value].copy(), st.playouts, st.playout_plies, st.nodes, st.batches,
                             st.max_tree_depth, st.seconds_select, st.seconds_gpu, st.seconds_backprop)
+
+
+def flat_monte_carlo(rollout: GpuRollout, state: np.ndarray, samples_per_move: int = 100, max_rollout_depth: int = 100,
+                     ucb1: float | None = None, r: int = 0):
+    """FlatMonteCarloStrategy::choose_action (mcts/src/strategies/flat_mc.rs:58-151) as ONE GPU batch: every root
+    child is a leaf with `samples_per_move` uniform playouts.  The reference's rollout loop makes at most
+    `max_rollout_depth` moves and never checks the state reached by the last one, which is exactly a playout with
+    max_playout_depth = max_rollout_depth - 1 scored as 0 at the cutoff.  Returns (action, wins per root action).
+    `r` is the combined random_best draw in [0, 16 n)."""
+    from .rollout import apply, generate_actions
+    from .root_merge import PRIMES
+
+    game = rollout.game
+    st = np.ascontiguousarray(state, dtype=LEAF_DTYPE).reshape(-1)[:1]
+    player = int(st[0]["turn"])
+    actions = generate_actions(game, st)
+    if not actions:
+        raise ValueError("flat_monte_carlo on a state without actions (the reference panics here)")
+    leaves = np.concatenate([apply(game, st, a) for a in actions])
+    saved, rollout.strategy = rollout.strategy, Uniform()
+    try:
+        res = rollout.simulate_many(leaves, samples_per_move, max_playout_depth=max(0, max_rollout_depth - 1) or 1).results
+    finally:
+        rollout.strategy = saved
+    wins = res["wins"][:, player].astype(np.int64)
+    n = float(samples_per_move)
+    score = wins / n + ucb1 * (math.log(n) / n) if ucb1 is not None else wins.astype(np.float64)
+    cnt = len(actions)
+    i, stride, best, best_i = (r // 16) % cnt, PRIMES[r % 16], None, 0
+    for _ in range(cnt):  # random_best (util.rs:135-163)
+        if best is None or score[i] > best:
+            best, best_i = score[i], i
+        i = (i + stride) % cnt
+    return actions[best_i], wins

@@ -51,7 +51,22 @@ typedef struct {
     stats_t *edge;
     size_t n_edges, cap_edges;
     stats_t root_stats;
+    /* use_transpositions: open-addressing table state -> node id (table.rs keyed by zobrist hash in the
+     * reference; keyed by the whole state here, which cannot collide) */
+    int use_table;
+    uint32_t *tab;
+    size_t tab_cap, tab_used;
 } tree_t;
+
+static uint64_t state_hash(const orc_state *s) {
+    uint64_t w[5], h = 0x9e3779b97f4a7c15ull;
+    memcpy(w, s, sizeof w);
+    for (int i = 0; i < 5; ++i) {
+        h = (h ^ w[i]) * 0xff51afd7ed558ccdull;
+        h ^= h >> 32;
+    }
+    return h;
+}
 
 typedef struct {
     uint32_t node, idx;
@@ -79,6 +94,33 @@ static uint32_t add_node(tree_t *t, const orc_state *s) {
     n->state = *s;
     n->player = orc_player_to_move(t->game, s);
     return (uint32_t)t->n_nodes++;
+}
+
+/* returns the node holding `s`, creating (and registering) it when absent */
+static uint32_t table_resolve(tree_t *t, const orc_state *s) {
+    if ((t->tab_used + 1) * 2 > t->tab_cap) {
+        size_t ncap = t->tab_cap ? t->tab_cap * 2 : 4096;
+        uint32_t *nt = (uint32_t *)malloc(ncap * sizeof(uint32_t));
+        memset(nt, 0xff, ncap * sizeof(uint32_t));
+        for (size_t i = 0; i < t->tab_cap; ++i)
+            if (t->tab[i] != 0xffffffffu) {
+                size_t j = state_hash(&t->nodes[t->tab[i]].state) & (ncap - 1);
+                while (nt[j] != 0xffffffffu) j = (j + 1) & (ncap - 1);
+                nt[j] = t->tab[i];
+            }
+        free(t->tab);
+        t->tab = nt;
+        t->tab_cap = ncap;
+    }
+    size_t j = state_hash(s) & (t->tab_cap - 1);
+    while (t->tab[j] != 0xffffffffu) {
+        if (memcmp(&t->nodes[t->tab[j]].state, s, sizeof *s) == 0) return t->tab[j];
+        j = (j + 1) & (t->tab_cap - 1);
+    }
+    uint32_t id = add_node(t, s);
+    t->tab[j] = id;
+    t->tab_used++;
+    return id;
 }
 
 static void expand(tree_t *t, uint32_t id) { /* shared.rs:220-289 */
@@ -187,7 +229,7 @@ static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t 
         } else {
             orc_state s = t->nodes[cur].state;
             orc_apply(t->game, &s, t->action[slot]);
-            uint32_t id = add_node(t, &s);
+            uint32_t id = t->use_table ? table_resolve(t, &s) : add_node(t, &s);
             t->child[slot] = (int32_t)id;
             cur = id;
             if (cfg->expand_threshold > 0) {
@@ -210,7 +252,9 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     tree_t t;
     memset(&t, 0, sizeof t);
     t.game = c->game;
-    add_node(&t, root);
+    t.use_table = c->use_transpositions;
+    if (t.use_table) table_resolve(&t, root);
+    else add_node(&t, root);
     sel_cfg cfg = {c->select, c->q_init, c->exploration_c, c->expand_threshold, c->seed};
     const uint32_t B = c->batch_leaves, k = c->playouts_per_leaf;
     const int na = orc_num_actions(c->game);
@@ -322,6 +366,7 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     free(t.action);
     free(t.child);
     free(t.edge);
+    free(t.tab);
     free(mast);
     free(delta);
     free(paths);

@@ -40,6 +40,40 @@ def test_search_root_statistics_bit_exact(game, policy, iters, batch, k, select,
     assert int(got.children["visits"].sum()) == (iters - min(batch, iters)) * k
 
 
+def test_search_with_transposition_table_bit_exact():
+    """BASELINE.json config 4: Othello, decisive-move rollouts, transposition table on the host."""
+    game, iters, batch, k = o.OTHELLO, 4096, 64, 8
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game.OTHELLO, mb.DecisiveMoveWin(), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      select=1, q_init=1, use_transpositions=True, seed=9) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+        plain_nodes = None
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.DECISIVE_WIN, select=1,
+                                     q_init=1, seed=9, threads=o.host_threads(), use_transpositions=True)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    with mb.GpuSearch(mb.Game.OTHELLO, mb.DecisiveMoveWin(), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      select=1, q_init=1, use_transpositions=False, seed=9) as s:
+        plain_nodes = s.choose_action(root.view(mb.LEAF_DTYPE)).nodes
+    assert got.nodes < plain_nodes  # transpositions were actually shared
+
+
+def test_flat_monte_carlo_one_batch():
+    from mcts_b200.search import flat_monte_carlo
+
+    game = o.CONNECT4
+    s = o.initial_state(game)
+    for c in [3, 3, 2, 4]:
+        s = o.apply(game, s, c)
+    with mb.GpuRollout(mb.Game.CONNECT4, seed=4) as g:
+        action, wins = flat_monte_carlo(g, s.view(mb.LEAF_DTYPE), samples_per_move=500, max_rollout_depth=100, r=37)
+    acts = o.generate_actions(game, s)
+    leaves = np.concatenate([o.apply(game, s, a) for a in acts])
+    ref = o.playout_batch(game, leaves, 500, seed=4, max_depth=99)["results"]
+    assert (wins == ref["wins"][:, 0]).all()
+    assert action in acts and wins[acts.index(action)] == wins.max()
+
+
 def test_search_prefers_the_centre_in_connect4():
     with mb.GpuSearch(mb.Game.CONNECT4, max_iterations=20000, batch_leaves=128, num_rollouts_per_leaf=8, seed=3) as s:
         r = s.choose_action(mb.initial_state(mb.Game.CONNECT4))
