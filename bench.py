@@ -57,6 +57,7 @@ OPS_PER_PLY = {
     "othello_decisive_win": 750.0,
     "hex11_uniform_amaf": 65.0 + 116.0 * 2.9,
 }
+MAST_WARMUP_K = 16  # uniform playouts per leaf that populate the MAST table before the timed steps
 MEAN_LEGAL = {1: 25.7, 2: 47.8}  # BASELINE.md section 4 (oracle-measured mean branching)
 
 
@@ -143,8 +144,8 @@ def cpu_sample(w, n_leaves, k, threads, seed):
     leaves = o.random_positions(w["game"], w["pos_seed"], w["plies"], n_leaves)
     mast = None
     if w["policy"] == 1:
-        # a populated table: one uniform batch's delta (the same warm-up the GPU arm does)
-        warm = o.playout_batch(w["game"], leaves[: min(64, n_leaves)], 64, seed=seed + 1, max_depth=w["max_depth"], want_mast_delta=True, threads=threads)
+        # a steady-state table: the delta of one uniform batch over the leaves (the same warm-up the GPU arm does)
+        warm = o.playout_batch(w["game"], leaves, MAST_WARMUP_K, seed=999, max_depth=w["max_depth"], want_mast_delta=True, threads=threads)
         mast = warm["mast_delta"]
     t0 = time.perf_counter()
     out = o.playout_batch(
@@ -265,7 +266,7 @@ def run_gpu(args):
         mast = None
         if w["policy"] == 1:
             saved, g.strategy = g.strategy, mb.Uniform()
-            warm = g.simulate_many(leaves[:64], 64, want_mast_delta=True, seed=999)
+            warm = g.simulate_many(leaves, MAST_WARMUP_K, want_mast_delta=True, seed=999)
             g.strategy = saved
             mast = warm.mast_delta.copy()
             g.set_mast(mast)

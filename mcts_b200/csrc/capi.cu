@@ -2,7 +2,7 @@
 //
 // One mr_ctx drives one or more GPUs of this process.  Per GPU: one stream, one task-queue counter per
 // slot, grow-on-demand device buffers and pinned host staging.  A batch is cut into tasks
-// (leaf, chunk-of-playouts); the task range is split evenly over the ctx's GPUs (no data-path
+// (leaf, run-of-playouts); the global playout range is split evenly over the ctx's GPUs (no data-path
 // collective: every playout is independent given (leaf state, Philox key)); per-leaf results are summed
 // on the host.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
@@ -11,10 +11,12 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include "hex_kernel.cuh"
 #include "int_peak.cuh"
 #include "rollout_kernel.cuh"
 
@@ -76,10 +78,9 @@ struct SlotDev {
     DevBuf<uint16_t> trace;
     DevBuf<mr_playout_record> rec;
     DevBuf<mr_leaf> final_state;
-    uint32_t *d_counter = nullptr;
+    unsigned long long *d_counter = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // what this device covers for the batch in flight
-    uint32_t task_begin = 0, task_end = 0;
     uint64_t g_begin = 0, g_end = 0; // global playout index range
 };
 
@@ -90,13 +91,12 @@ struct Device {
     SlotDev slot[MR_NUM_SLOTS];
     int mast_game = -1; // game of the MAST snapshot held in ctx->mast_*
     DevBuf<uint16_t> scratch;
-    uint32_t *d_counter_ext = nullptr; // task counter for mr_launch_device
+    unsigned long long *d_counter_ext = nullptr; // work counter for mr_launch_device
 };
 
 struct SlotState {
     bool busy = false;
     mr_batch_desc desc{};
-    uint32_t chunk = 0, chunks_per_leaf = 0, n_tasks = 0;
     float kernel_ms = 0.f;
 };
 
@@ -160,6 +160,16 @@ kernel_fn pick_variant(int v) {
     }
 }
 
+kernel_fn pick_hex(int v) { // Hex has its own fill-then-search kernel; no MAST policy, AMAF from board masks
+    switch (v) {
+    case 0:
+    case 2: return hex_rollout_kernel<0>;
+    case 1:
+    case 3: return hex_rollout_kernel<MR_WANT_AMAF>;
+    default: return hex_rollout_kernel<MR_WANT_AMAF | MR_WANT_TRACE | MR_WANT_FINAL_STATE>;
+    }
+}
+
 kernel_fn pick_kernel(int game, int policy, int v) {
     switch (game) {
     case MR_CONNECT4:
@@ -179,7 +189,7 @@ kernel_fn pick_kernel(int game, int policy, int v) {
         if (policy == MR_UNIFORM || policy == MR_DECISIVE_WIN) return pick_variant<Othello, MR_UNIFORM>(v);
         return nullptr;
     case MR_HEX11:
-        if (policy == MR_UNIFORM) return pick_variant<Hex11, MR_UNIFORM>(v);
+        if (policy == MR_UNIFORM) return pick_hex(v);
         return nullptr;
     }
     return nullptr;
@@ -298,9 +308,12 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
         if (!has_mast) return fail(ctx, MR_ERR_INVALID, "MR_EPS_MAST needs a MAST snapshot (mast_in / mr_set_mast)");
         if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
     }
+    if (d->game == MR_HEX11 && (d->flags & MR_WANT_MAST_DELTA))
+        return fail(ctx, MR_ERR_UNSUPPORTED, "no MAST table is built for Hex (no MAST policy in scope for it)");
     if ((d->flags & MR_WANT_TRACE) && d->max_trace == 0) return fail(ctx, MR_ERR_INVALID, "MR_WANT_TRACE needs max_trace > 0");
     uint32_t cap = 0;
-    if (d->flags & (MR_WANT_AMAF | MR_WANT_MAST_DELTA)) {
+    const bool needs_scratch = (d->flags & MR_WANT_MAST_DELTA) || ((d->flags & MR_WANT_AMAF) && d->game != MR_HEX11);
+    if (needs_scratch) {
         const uint32_t bound = kGames[d->game].depth_bound;
         cap = d->max_playout_depth ? d->max_playout_depth : bound;
         if (bound && cap > bound) cap = bound;
@@ -315,27 +328,16 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
 }
 
 struct LaunchPlan {
-    uint32_t chunk, chunks_per_leaf, n_tasks;
     int blocks_per_sm;
 };
 
 int plan_launch(mr_ctx *ctx, const Device &dv, kernel_fn fn, const mr_batch_desc *d, int n_devices, LaunchPlan *lp) {
+    (void)d;
+    (void)n_devices;
     int bps = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, THREADS_PER_BLOCK, 0));
     if (bps < 1) return fail(ctx, MR_ERR_CUDA, "kernel does not fit on an SM");
-    const uint64_t resident_warps = (uint64_t)dv.num_sms * bps * WARPS_PER_BLOCK * n_devices;
-    const uint64_t total = (uint64_t)d->n_leaves * d->playouts_per_leaf;
-    // enough tasks for ~8 per resident warp, 32..1024 playouts each, never more than one leaf's worth
-    uint64_t want = total / (resident_warps * 8);
-    uint32_t chunk = 32;
-    while (chunk < 1024 && (uint64_t)chunk * 2 <= want) chunk *= 2;
-    if (chunk > d->playouts_per_leaf) chunk = d->playouts_per_leaf;
-    const uint64_t cpl = (d->playouts_per_leaf + chunk - 1) / chunk;
-    const uint64_t n_tasks = cpl * d->n_leaves;
-    if (n_tasks >= 0xffff0000ull) return fail(ctx, MR_ERR_INVALID, "too many tasks");
-    lp->chunk = chunk;
-    lp->chunks_per_leaf = (uint32_t)cpl;
-    lp->n_tasks = (uint32_t)n_tasks;
+    (void)dv;
     lp->blocks_per_sm = bps;
     return MR_OK;
 }
@@ -349,8 +351,7 @@ void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, co
     }
     kp.n_leaves = d->n_leaves;
     kp.k = d->playouts_per_leaf;
-    kp.chunk = lp.chunk;
-    kp.chunks_per_leaf = lp.chunks_per_leaf;
+    (void)lp;
     kp.max_depth = d->max_playout_depth ? d->max_playout_depth : 0xffffffffu;
     kp.seed_lo = (uint32_t)d->seed;
     kp.seed_hi = (uint32_t)(d->seed >> 32);
@@ -362,22 +363,36 @@ void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, co
     kp.eps_thr_m1 = thr > 0 ? (uint32_t)(thr - 1) : 0;
     kp.max_trace = d->max_trace;
     kp.trace_cap = trace_cap;
+    kp.grab_div = 2;
 }
 
 int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const LaunchPlan &lp, cudaStream_t stream,
-              uint32_t *d_counter) {
-    const uint32_t my_tasks = kp.task_end - kp.task_begin;
-    if (my_tasks == 0) return MR_OK;
+              unsigned long long *d_counter) {
+    const uint64_t work = kp.g_end - kp.g_begin;
+    if (work == 0) return MR_OK;
     uint32_t blocks = (uint32_t)dv.num_sms * lp.blocks_per_sm;
-    const uint32_t need_blocks = (my_tasks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    if (blocks > need_blocks) blocks = need_blocks;
+    const uint64_t need_blocks = (work + 32ull * WARPS_PER_BLOCK - 1) / (32ull * WARPS_PER_BLOCK);
+    if (blocks > need_blocks) blocks = (uint32_t)need_blocks;
+    kp.total_warps = blocks * WARPS_PER_BLOCK;
+    // Fixed-size grabs measured best on B200 (profiles/grab_sweep_r01.txt): 512 playouts (16 per lane) when
+    // the batch is large enough for >= 4 grabs per resident warp, smaller powers of two otherwise.
+    {
+        uint32_t chunk = 512;
+        while (chunk > 32 && (uint64_t)chunk * kp.total_warps * 4 > work) chunk >>= 1;
+        kp.grab_min = kp.grab_max = chunk;
+    }
+    if (const char *e = getenv("MR_GRAB_MIN")) kp.grab_min = (uint32_t)atoi(e) & ~31u; // tuning knobs
+    if (const char *e = getenv("MR_GRAB_MAX")) kp.grab_max = (uint32_t)atoi(e) & ~31u;
+    if (const char *e = getenv("MR_GRAB_DIV")) kp.grab_div = (uint32_t)atoi(e);
+    if (kp.grab_min < 32) kp.grab_min = 32;
+    if (kp.grab_max < kp.grab_min) kp.grab_max = kp.grab_min;
     if (kp.trace_cap) {
         const size_t need = (size_t)blocks * WARPS_PER_BLOCK * kp.trace_cap * 32u;
         CUDA_TRY(ctx, dv.scratch.reserve(need, false));
         kp.trace_scratch = dv.scratch.d;
     }
-    kp.task_counter = d_counter;
-    CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), stream));
+    kp.work_counter = d_counter;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
     fn<<<blocks, THREADS_PER_BLOCK, 0, stream>>>(kp);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
@@ -428,14 +443,14 @@ int mr_init(const int *device_ids, int n_devices, mr_ctx **out) {
         dv.num_sms = prop.multiProcessorCount;
         cudaSetDevice(dv.id);
         if (cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc(&dv.d_counter_ext, sizeof(uint32_t)) != cudaSuccess || upload_random_best_tables() != cudaSuccess) {
+            cudaMalloc(&dv.d_counter_ext, sizeof(unsigned long long)) != cudaSuccess || upload_random_best_tables() != cudaSuccess) {
             int rc = fail(nullptr, MR_ERR_CUDA, "stream/counter creation failed on device %d", dv.id);
             mr_destroy(ctx);
             return rc;
         }
         for (int s = 0; s < MR_NUM_SLOTS; ++s) {
             SlotDev &sd = dv.slot[s];
-            if (cudaMalloc(&sd.d_counter, sizeof(uint32_t)) != cudaSuccess || cudaEventCreate(&sd.ev_begin) != cudaSuccess ||
+            if (cudaMalloc(&sd.d_counter, sizeof(unsigned long long)) != cudaSuccess || cudaEventCreate(&sd.ev_begin) != cudaSuccess ||
                 cudaEventCreate(&sd.ev_end) != cudaSuccess) {
                 int rc = fail(nullptr, MR_ERR_CUDA, "slot setup failed on device %d", dv.id);
                 mr_destroy(ctx);
@@ -512,14 +527,8 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
         Device &dv = ctx->dev[(size_t)di];
         SlotDev &sd = dv.slot[slot];
         CUDA_TRY(ctx, cudaSetDevice(dv.id));
-        sd.task_begin = (uint32_t)((uint64_t)lp.n_tasks * di / nd);
-        sd.task_end = (uint32_t)((uint64_t)lp.n_tasks * (di + 1) / nd);
-        auto g_of_task = [&](uint32_t t) {
-            const uint32_t li = t / lp.chunks_per_leaf, ci = t % lp.chunks_per_leaf;
-            return (uint64_t)li * k + (uint64_t)ci * lp.chunk;
-        };
-        sd.g_begin = sd.task_begin < lp.n_tasks ? g_of_task(sd.task_begin) : total;
-        sd.g_end = sd.task_end < lp.n_tasks ? g_of_task(sd.task_end) : total;
+        sd.g_begin = total * (uint64_t)di / (uint64_t)nd;
+        sd.g_end = total * (uint64_t)(di + 1) / (uint64_t)nd;
 
         CUDA_TRY(ctx, sd.leaves.reserve(n, true));
         CUDA_TRY(ctx, sd.results.reserve(n, true));
@@ -530,8 +539,8 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
         fill_params(ctx, kp, desc, lp, trace_cap);
         kp.leaves = sd.leaves.d;
         kp.results = sd.results.d;
-        kp.task_begin = sd.task_begin;
-        kp.task_end = sd.task_end;
+        kp.g_begin = sd.g_begin;
+        kp.g_end = sd.g_end;
         if (desc->flags & MR_WANT_AMAF) {
             CUDA_TRY(ctx, sd.amaf.reserve((size_t)n * 2 * na, true));
             CUDA_TRY(ctx, cudaMemsetAsync(sd.amaf.d, 0, sizeof(mr_action_stat) * n * 2 * na, dv.stream));
@@ -579,9 +588,6 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
     }
     ss.busy = true;
     ss.desc = *desc;
-    ss.chunk = lp.chunk;
-    ss.chunks_per_leaf = lp.chunks_per_leaf;
-    ss.n_tasks = lp.n_tasks;
     return MR_OK;
 }
 
@@ -601,7 +607,7 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
         CUDA_TRY(ctx, cudaSetDevice(dv.id));
         CUDA_TRY(ctx, cudaStreamSynchronize(dv.stream));
         SlotDev &sd = dv.slot[slot];
-        if (sd.task_end > sd.task_begin) {
+        if (sd.g_end > sd.g_begin) {
             float ms = 0.f;
             CUDA_TRY(ctx, cudaEventElapsedTime(&ms, sd.ev_begin, sd.ev_end));
             worst_ms = std::max(worst_ms, ms);
@@ -613,7 +619,7 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
     if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) memset(mast_delta_out, 0, sizeof(mr_action_stat) * 2 * na);
     for (Device &dv : ctx->dev) {
         SlotDev &sd = dv.slot[slot];
-        if (sd.task_end == sd.task_begin) continue;
+        if (sd.g_end == sd.g_begin) continue;
         for (uint32_t i = 0; i < n; ++i) {
             out[i].wins[0] += sd.results.h[i].wins[0];
             out[i].wins[1] += sd.results.h[i].wins[1];
@@ -680,8 +686,8 @@ int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, c
     kp.results = (mr_leaf_result *)d_results;
     kp.amaf = (mr_action_stat *)d_amaf;
     kp.mast_delta = (mr_action_stat *)d_mast_delta;
-    kp.task_begin = 0;
-    kp.task_end = lp.n_tasks;
+    kp.g_begin = 0;
+    kp.g_end = (uint64_t)desc->n_leaves * desc->playouts_per_leaf;
     cudaStream_t st = stream ? (cudaStream_t)stream : dv.stream;
     return launch_on(ctx, dv, fn, kp, lp, st, dv.d_counter_ext);
 }

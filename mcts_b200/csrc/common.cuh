@@ -30,13 +30,17 @@ enum : int {
 struct KernelParams {
     const mr_leaf *leaves;
     mr_leaf_result *results;
-    uint32_t *task_counter; // persistent-warp work queue head
+    unsigned long long *work_counter; // persistent-warp work queue head: next global playout index (relative to g_begin)
     uint32_t n_leaves;
     uint32_t k;               // playouts per leaf
-    uint32_t chunk;           // playouts per task (a task never straddles leaves)
-    uint32_t chunks_per_leaf; // ceil(k / chunk)
-    uint32_t task_begin;      // this device's share of the task range
-    uint32_t task_end;
+    // Work = global playout indices g in [g_begin, g_end), g = leaf * k + playout.  Warps grab contiguous
+    // ranges with GUIDED self-scheduling (grab size ~ remaining / (2 * warps), between grab_min and grab_max):
+    // large grabs early keep the per-grab tail short, small grabs at the end balance the warps.
+    unsigned long long g_begin;
+    unsigned long long g_end;
+    uint32_t total_warps;
+    uint32_t grab_min, grab_max; // multiples of 32
+    uint32_t grab_div;           // grab = remaining / (grab_div * warps)
     uint32_t max_depth; // 0xffffffff = unlimited
     uint32_t seed_lo, seed_hi;
     uint32_t leaf_id_base;

@@ -91,7 +91,25 @@ struct Connect4 {
     }
 
     __device__ static int prepare(Shared &sh, const mr_leaf &leaf, uint32_t lane) {
-        const uint64_t black = to_colbyte(leaf.board[0]), white = to_colbyte(leaf.board[1]);
+        // row-major -> column-byte, cooperatively: lane L converts cells L and L + 32, then a warp OR
+        uint32_t blo = 0, bhi = 0, wlo = 0, whi = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t cell = lane + 32u * h; // reference index row*7 + col
+            if (cell < 42) {
+                const uint32_t row = cell / 7u, col = cell - row * 7u, pos = col * 8u + row;
+                const uint32_t b = (uint32_t)(leaf.board[0] >> cell) & 1u, w = (uint32_t)(leaf.board[1] >> cell) & 1u;
+                if (pos < 32) {
+                    blo |= b << pos;
+                    wlo |= w << pos;
+                } else {
+                    bhi |= b << (pos - 32);
+                    whi |= w << (pos - 32);
+                }
+            }
+        }
+        const uint64_t black = mk64(__reduce_or_sync(FULL_MASK, blo), __reduce_or_sync(FULL_MASK, bhi));
+        const uint64_t white = mk64(__reduce_or_sync(FULL_MASK, wlo), __reduce_or_sync(FULL_MASK, whi));
         const uint64_t all = black | white;
         if (lane == 0) {
             sh.cur = leaf.turn ? white : black;
@@ -707,10 +725,9 @@ struct Othello {
 //   legal = empty cells ascending (:115-120); apply sets the cell, toggles the turn (:122-125); only the
 //   last mover is checked (:130-144): P0 connects north (row 10) <-> south (row 0), P1 west (col 0) <-> east
 //   (col 10) over the six hex neighbours N,S,E,W,NE(+12),SW(-12) (bitboard/src/board.rs:509-531).
-//   device: boards as 4 x u32; instead of a full flood6 fix-point every ply, each player keeps the set
-//   `conn` of own stones connected to its FIRST edge -- exactly flood6(first_edge) of the reference --
-//   grown incrementally only when the new stone touches it; the player has won iff conn meets the
-//   second edge.  Same answer at every ply, hence the same stop ply.
+//   device: boards as 4 x u32; this struct only holds the board primitives (masks, six-neighbourhood, flood).
+//   The playout itself is hex_kernel.cuh's fill-then-search, which replaces the per-ply flood6 fix-point by
+//   one winner test at the end plus a binary search for the first connecting move -- same stop ply.
 // ==========================================================================================
 struct Hex11 {
     static constexpr int NA = 121;
@@ -722,16 +739,6 @@ struct Hex11 {
     struct B128 {
         uint32_t w[4];
     };
-    struct Shared {
-        B128 stones[2];
-        B128 conn[2];
-        uint32_t turn;
-        uint32_t n_empty;
-    };
-    B128 stones[2];
-    B128 conn[2];
-    uint32_t n_empty;
-
     __device__ static B128 zero() { return B128{{0, 0, 0, 0}}; }
     __device__ static B128 band(B128 a, B128 b) { return B128{{a.w[0] & b.w[0], a.w[1] & b.w[1], a.w[2] & b.w[2], a.w[3] & b.w[3]}}; }
     __device__ static B128 bor(B128 a, B128 b) { return B128{{a.w[0] | b.w[0], a.w[1] | b.w[1], a.w[2] | b.w[2], a.w[3] | b.w[3]}}; }
@@ -796,132 +803,6 @@ struct Hex11 {
     __device__ static B128 second_edge(int p) {
         constexpr B128 so = row_mask(0), e = col_mask(10);
         return p == 0 ? so : e;
-    }
-
-    __device__ static int prepare(Shared &s, const mr_leaf &leaf, uint32_t lane) {
-        B128 st[2];
-        for (int pl = 0; pl < 2; ++pl) {
-            st[pl].w[0] = (uint32_t)leaf.board[2 * pl];
-            st[pl].w[1] = (uint32_t)(leaf.board[2 * pl] >> 32);
-            st[pl].w[2] = (uint32_t)leaf.board[2 * pl + 1];
-            st[pl].w[3] = (uint32_t)(leaf.board[2 * pl + 1] >> 32) & 0x01ffffffu;
-        }
-        constexpr B128 NC0 = inv(col_mask(0)), NC10 = inv(col_mask(10)), BM = board_mask();
-        B128 cn[2];
-        for (int pl = 0; pl < 2; ++pl) cn[pl] = flood(first_edge(pl), st[pl], NC0, NC10, BM);
-        const B128 occ = bor(st[0], st[1]);
-        const uint32_t n_occ = __popc(occ.w[0]) + __popc(occ.w[1]) + __popc(occ.w[2]) + __popc(occ.w[3]);
-        if (lane == 0) {
-            s.stones[0] = st[0];
-            s.stones[1] = st[1];
-            s.conn[0] = cn[0];
-            s.conn[1] = cn[1];
-            s.turn = leaf.turn;
-            s.n_empty = 121 - n_occ;
-        }
-        // :130-144 only the player who moved last is checked
-        const int last = (leaf.turn + 1) & 1;
-        if (any(band(cn[last], second_edge(last)))) return last ? MR_WINNER_P1 : MR_WINNER_P0;
-        if (n_occ == 121) return MR_DRAW; // :208-215 no winner and no actions
-        return MR_NOT_TERMINAL;
-    }
-    __device__ void reset(const Shared &s) {
-        stones[0] = s.stones[0];
-        stones[1] = s.stones[1];
-        conn[0] = s.conn[0];
-        conn[1] = s.conn[1];
-        n_empty = s.n_empty;
-    }
-
-    template <int POLICY, int PARITY>
-    __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
-        const uint32_t mover = (s.turn ^ PARITY) & 1u;
-        if (n_empty == 0) return ST_DRAW; // cannot happen in Hex; kept for totality
-        // idx-th empty cell, ascending
-        uint32_t idx = mulhi(x0, n_empty);
-        const uint32_t e0 = ~(stones[0].w[0] | stones[1].w[0]);
-        const uint32_t e1 = ~(stones[0].w[1] | stones[1].w[1]);
-        const uint32_t e2 = ~(stones[0].w[2] | stones[1].w[2]);
-        const uint32_t e3 = ~(stones[0].w[3] | stones[1].w[3]) & 0x01ffffffu;
-        const uint32_t c0 = __popc(e0), c1 = __popc(e1), c2 = __popc(e2);
-        uint32_t wsel = 0, word = e0;
-        if (idx >= c0) {
-            idx -= c0;
-            wsel = 1;
-            word = e1;
-            if (idx >= c1) {
-                idx -= c1;
-                wsel = 2;
-                word = e2;
-                if (idx >= c2) {
-                    idx -= c2;
-                    wsel = 3;
-                    word = e3;
-                }
-            }
-        }
-        const uint32_t bitpos = select32(word, idx);
-        const uint32_t cell = wsel * 32u + bitpos;
-        action = cell;
-        slot = cell;
-        const uint32_t b = 1u << bitpos;
-        B128 mv = zero();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) mv.w[q] = (wsel == (uint32_t)q) ? b : 0u;
-        --n_empty;
-        constexpr B128 NC0 = inv(col_mask(0)), NC10 = inv(col_mask(10)), BM = board_mask();
-        // mover-specific update (both branches are the same code on different registers)
-        bool won;
-        if (mover == 0) {
-            stones[0] = bor(stones[0], mv);
-            won = grow(0, mv, NC0, NC10, BM);
-        } else {
-            stones[1] = bor(stones[1], mv);
-            won = grow(1, mv, NC0, NC10, BM);
-        }
-        if (won) return ST_MOVED | (mover ? ST_WIN_P1 : ST_WIN_P0);
-        if (n_empty == 0) return ST_MOVED | ST_DRAW;
-        return ST_MOVED;
-    }
-    // after the mover placed `mv`: extend conn[pl] if the stone touches it (or lies on the first edge)
-    __device__ bool grow(int pl, B128 mv, const B128 &NC0, const B128 &NC10, const B128 &BM) {
-        const B128 nb = neighbours(mv, NC0, NC10, BM);
-        const bool touches = any(band(nb, conn[pl])) || any(band(mv, first_edge(pl)));
-        if (touches) {
-            B128 f = bor(conn[pl], mv);
-            B128 frontier = mv;
-            for (;;) {
-                const B128 g = bandn(band(neighbours(frontier, NC0, NC10, BM), stones[pl]), f);
-                if (!any(g)) break;
-                f = bor(f, g);
-                frontier = g;
-            }
-            conn[pl] = f;
-            return any(band(f, second_edge(pl)));
-        }
-        return false;
-    }
-    // AMAF occurrences of finished lane f's playout = its final stones minus the leaf's stones; lane L owns
-    // cells L, L+32, L+64, L+96 of both players, so the per-warp table needs no atomics
-    __device__ void amaf_from_masks(const Shared &s, uint32_t *tab, int f, uint32_t lane, int u_p0) const {
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-            const uint32_t inc = 1u + ((uint32_t)(pl == 0 ? u_p0 : -u_p0) << 16);
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const uint32_t played = __shfl_sync(FULL_MASK, stones[pl].w[w], f) & ~s.stones[pl].w[w];
-                if ((played >> lane) & 1u) tab[pl * NSLOTS + w * 32 + lane] += inc;
-            }
-        }
-    }
-    __device__ void store_final(const Shared &s, mr_leaf *out, uint32_t plies, int end_code) const {
-        for (int pl = 0; pl < 2; ++pl) {
-            out->board[2 * pl] = mk64(stones[pl].w[0], stones[pl].w[1]);
-            out->board[2 * pl + 1] = mk64(stones[pl].w[2], stones[pl].w[3]);
-        }
-        out->turn = (uint8_t)((s.turn + plies) & 1);
-        out->flag = 0;
-        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
     }
 };
 

@@ -1,0 +1,359 @@
+// hex_kernel.cuh -- Hex 11x11 playouts as FILL-THEN-SEARCH (sm_100a).
+//
+// The reference checks the last mover's connection with a full flood6 fix-point after every ply
+// (games/hex-gen/src/lib.rs:130-144,208-215 through the default terminal_status, mcts/src/game.rs:202-211).
+// That answer is MONOTONE along a playout -- a connected chain stays connected, and in Hex at most one
+// player can ever connect -- and the moves themselves never depend on it (the idx-th empty cell, ascending,
+// lib.rs:115-120).  So a playout is computed as:
+//   1. fill  : play the uniform policy to the ply limit D = min(#empty cells, max_playout_depth) with NO
+//              connectivity work, recording the cell of every ply.  All playouts of a leaf have the same
+//              length, so the 32 lanes of a warp run in perfect lock-step (no refill, no dead lanes).
+//   2. who   : one flood per player on the position at ply D decides the winner (none => depth cutoff).
+//   3. when  : binary search over the winner's moves for the FIRST one that connects its two edges; each
+//              probe grows the stone mask and the edge-connected set incrementally from the last
+//              "not yet connected" probe.
+// The stop ply, winner, trace, final state and AMAF occurrences are exactly those of the per-ply loop.
+// Moves generated past the stop ply are discarded; they consume Philox words the reference would never
+// have drawn, which is unobservable because draws are keyed by (leaf, playout, ply).
+#pragma once
+
+#include "rollout_kernel.cuh"
+
+namespace mr {
+
+struct HexLeafShared {
+    Hex11::B128 stones[2];
+    Hex11::B128 conn[2]; // flood6(first edge) of each player at the leaf
+    uint32_t turn;
+    uint32_t n_empty;
+};
+
+template <int FLAGS>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK) hex_rollout_kernel(const KernelParams p) {
+    using H = Hex11;
+    using B128 = H::B128;
+    constexpr bool WANT_AMAF = (FLAGS & MR_WANT_AMAF) != 0;
+    constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
+    constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
+    constexpr bool NEED_BOARDS = WANT_AMAF || WANT_FINAL; // both players' stones at the stop ply
+    constexpr B128 NC0 = H::inv(H::col_mask(0)), NC10 = H::inv(H::col_mask(10)), BM = H::board_mask();
+
+    __shared__ __align__(16) mr_leaf s_leaf[WARPS_PER_BLOCK];
+    __shared__ HexLeafShared s_hex[WARPS_PER_BLOCK];
+    __shared__ uint8_t s_order[WARPS_PER_BLOCK][121][32]; // cell played at [ply][lane]
+    __shared__ uint32_t s_amaf[WARPS_PER_BLOCK][WANT_AMAF ? 2 * H::NSLOTS : 1];
+
+    const uint32_t lane = lane_id();
+    const uint32_t warp = threadIdx.x >> 5;
+    HexLeafShared &sh = s_hex[warp];
+    uint8_t(*order)[32] = s_order[warp];
+    uint32_t *amaf_tab = s_amaf[warp];
+    uint32_t amaf_plies = 0;
+    if (WANT_AMAF)
+        for (uint32_t e = lane; e < 2u * H::NSLOTS; e += 32) amaf_tab[e] = 0;
+    __syncwarp();
+
+    unsigned long long grab_lo = 0, grab_hi = 0;
+    const unsigned long long work_total = p.g_end - p.g_begin;
+    for (;;) {
+        if (grab_lo >= grab_hi) {
+            unsigned long long lo = 0;
+            uint32_t want = 0;
+            if (lane == 0) {
+                want = p.grab_max;
+                lo = atomicAdd(p.work_counter, (unsigned long long)want);
+            }
+            lo = __shfl_sync(FULL_MASK, lo, 0);
+            want = __shfl_sync(FULL_MASK, want, 0);
+            if (lo >= work_total) break;
+            grab_lo = lo;
+            grab_hi = lo + want < work_total ? lo + want : work_total;
+        }
+        const unsigned long long g0 = p.g_begin + grab_lo;
+        const uint32_t li = (uint32_t)(g0 / p.k);
+        const uint32_t pid_begin = (uint32_t)(g0 - (unsigned long long)li * p.k);
+        const unsigned long long room = (unsigned long long)p.k - pid_begin;
+        const unsigned long long take = grab_hi - grab_lo < room ? grab_hi - grab_lo : room;
+        const uint32_t pid_end = pid_begin + (uint32_t)take;
+        grab_lo += take;
+        const uint32_t leaf_id = p.leaf_id_base + li;
+
+        // ---- stage the leaf, flood both players' first edges once per task ----
+        __syncwarp();
+        if (lane < sizeof(mr_leaf) / 4)
+            reinterpret_cast<uint32_t *>(&s_leaf[warp])[lane] = reinterpret_cast<const uint32_t *>(p.leaves + li)[lane];
+        __syncwarp();
+        int leaf_status;
+        {
+            const mr_leaf &leaf = s_leaf[warp];
+            B128 st[2], cn[2];
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+                st[pl].w[0] = (uint32_t)leaf.board[2 * pl];
+                st[pl].w[1] = (uint32_t)(leaf.board[2 * pl] >> 32);
+                st[pl].w[2] = (uint32_t)leaf.board[2 * pl + 1];
+                st[pl].w[3] = (uint32_t)(leaf.board[2 * pl + 1] >> 32) & 0x01ffffffu;
+                cn[pl] = H::flood(H::first_edge(pl), st[pl], NC0, NC10, BM);
+            }
+            const B128 occ = H::bor(st[0], st[1]);
+            const uint32_t n_occ = __popc(occ.w[0]) + __popc(occ.w[1]) + __popc(occ.w[2]) + __popc(occ.w[3]);
+            if (lane == 0) {
+                sh.stones[0] = st[0];
+                sh.stones[1] = st[1];
+                sh.conn[0] = cn[0];
+                sh.conn[1] = cn[1];
+                sh.turn = leaf.turn;
+                sh.n_empty = 121 - n_occ;
+            }
+            const int last = (leaf.turn + 1) & 1; // only the player who moved last is checked (lib.rs:130-144)
+            if (H::any(H::band(cn[last], H::second_edge(last)))) leaf_status = last ? MR_WINNER_P1 : MR_WINNER_P0;
+            else if (n_occ == 121) leaf_status = MR_DRAW;
+            else leaf_status = MR_NOT_TERMINAL;
+        }
+        __syncwarp();
+        const uint32_t leaf_turn = sh.turn;
+        const uint32_t E = sh.n_empty;
+        const uint32_t D = min(E, p.max_depth); // plies every playout of this leaf is filled to
+
+        uint32_t acc_w0 = 0, acc_w1 = 0, acc_draw = 0, acc_cut = 0, acc_depth = 0;
+
+        if (leaf_status != MR_NOT_TERMINAL) {
+            const uint32_t cnt = pid_end - pid_begin;
+            if (lane == 0) {
+                if (leaf_status == MR_WINNER_P0) acc_w0 = cnt;
+                else if (leaf_status == MR_WINNER_P1) acc_w1 = cnt;
+                else acc_draw = cnt;
+            }
+            if (WANT_TRACE || WANT_FINAL) {
+                for (uint32_t pid = pid_begin + lane; pid < pid_end; pid += 32) {
+                    const size_t g = (size_t)li * p.k + pid;
+                    if (WANT_TRACE && p.rec) {
+                        mr_playout_record r;
+                        r.depth = 0;
+                        r.outcome = (uint8_t)leaf_status;
+                        r.end_type = MR_END_TERMINAL;
+                        r.pad[0] = r.pad[1] = 0;
+                        p.rec[g] = r;
+                    }
+                    if (WANT_FINAL && p.final_state) p.final_state[g] = s_leaf[warp];
+                }
+            }
+        } else {
+            for (uint32_t round = pid_begin; round < pid_end; round += 32) {
+                const uint32_t pid = round + lane;
+                const bool active = pid < pid_end;
+
+                // ---- 1. fill: D plies, lock-step, no connectivity work ----
+                B128 full[2] = {sh.stones[0], sh.stones[1]};
+                uint32_t n_empty = E; // warp-uniform
+                for (uint32_t base = 0; base < D; base += 4) {
+                    uint32_t r[4];
+                    philox4x32_10(leaf_id, pid, base >> 2, 0u, p.seed_lo, p.seed_hi, r);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t ply = base + j;
+                        if (ply < D) { // warp-uniform
+                            uint32_t idx = __umulhi(r[j], n_empty);
+                            const uint32_t e0 = ~(full[0].w[0] | full[1].w[0]);
+                            const uint32_t e1 = ~(full[0].w[1] | full[1].w[1]);
+                            const uint32_t e2 = ~(full[0].w[2] | full[1].w[2]);
+                            const uint32_t e3 = ~(full[0].w[3] | full[1].w[3]) & 0x01ffffffu;
+                            const uint32_t c0 = __popc(e0), c1 = __popc(e1), c2 = __popc(e2);
+                            uint32_t wsel = 0, word = e0;
+                            if (idx >= c0) {
+                                idx -= c0;
+                                wsel = 1;
+                                word = e1;
+                                if (idx >= c1) {
+                                    idx -= c1;
+                                    wsel = 2;
+                                    word = e2;
+                                    if (idx >= c2) {
+                                        idx -= c2;
+                                        wsel = 3;
+                                        word = e3;
+                                    }
+                                }
+                            }
+                            const uint32_t bitpos = select32(word, idx);
+                            const uint32_t b = 1u << bitpos;
+                            const uint32_t mover = (leaf_turn + ply) & 1u; // warp-uniform
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t add = (wsel == (uint32_t)q) ? b : 0u;
+                                if (mover == 0) full[0].w[q] |= add;
+                                else full[1].w[q] |= add;
+                            }
+                            order[ply][lane] = (uint8_t)(wsel * 32u + bitpos);
+                            --n_empty;
+                        }
+                    }
+                }
+                __syncwarp();
+
+                // ---- 2. who: the position at ply D decides the winner ----
+                int winner = -1;
+                B128 conn_d = H::zero();
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+                    if (winner < 0) {
+                        const B128 c = H::flood(H::bor(sh.conn[pl], H::first_edge(pl)), full[pl], NC0, NC10, BM);
+                        if (H::any(H::band(c, H::second_edge(pl)))) {
+                            winner = pl;
+                            conn_d = c;
+                        }
+                    }
+                }
+
+                // ---- 3. when: first of the winner's moves that connects ----
+                uint32_t depth = D;
+                B128 win_mask = H::zero(); // the winner's stones at the stop ply
+                if (winner >= 0) {
+                    // the winner's moves are plies first, first+2, ...; move i is ply first + 2i
+                    const uint32_t first = ((uint32_t)winner ^ leaf_turn) & 1u;
+                    const int n_w = (int)((D - first + 1) >> 1);
+                    int lo = -1, hi = n_w - 1; // not connected after move lo, connected after move hi
+                    B128 mask_lo = sh.stones[winner], conn_lo = sh.conn[winner];
+                    const B128 edge1 = H::first_edge(winner), edge2 = H::second_edge(winner);
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        B128 m = mask_lo;
+                        for (int i = lo + 1; i <= mid; ++i) {
+                            const uint32_t cell = order[first + 2u * (uint32_t)i][lane];
+                            const uint32_t b = 1u << (cell & 31u), ws = cell >> 5;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) m.w[q] |= (ws == (uint32_t)q) ? b : 0u;
+                        }
+                        // everything connected at `lo` stays connected; grow it through the added stones
+                        const B128 c = H::flood(H::bor(conn_lo, edge1), m, NC0, NC10, BM);
+                        if (H::any(H::band(c, edge2))) {
+                            hi = mid;
+                        } else {
+                            lo = mid;
+                            mask_lo = m;
+                            conn_lo = c;
+                        }
+                    }
+                    depth = first + 2u * (uint32_t)hi + 1u;
+                    if (NEED_BOARDS) {
+                        win_mask = mask_lo;
+                        for (int i = lo + 1; i <= hi; ++i) {
+                            const uint32_t cell = order[first + 2u * (uint32_t)i][lane];
+                            const uint32_t b = 1u << (cell & 31u), ws = cell >> 5;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) win_mask.w[q] |= (ws == (uint32_t)q) ? b : 0u;
+                        }
+                    }
+                }
+                (void)conn_d;
+
+                // ---- 4. results ----
+                const bool cut = winner < 0 && D < E; // no winner within max_playout_depth plies
+                if (active) {
+                    acc_w0 += (winner == 0);
+                    acc_w1 += (winner == 1);
+                    acc_draw += (winner < 0);
+                    acc_cut += cut;
+                    acc_depth += depth;
+                }
+                B128 fin[2];
+                if (NEED_BOARDS) {
+                    // both players' stones at the stop ply: the winner's from the search, the other's by replay
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+                        if (pl == winner) {
+                            fin[pl] = win_mask;
+                        } else if (winner < 0) {
+                            fin[pl] = full[pl];
+                        } else {
+                            B128 m = sh.stones[pl];
+                            const uint32_t first = ((uint32_t)pl ^ leaf_turn) & 1u;
+                            for (uint32_t ply = first; ply < depth; ply += 2) {
+                                const uint32_t cell = order[ply][lane];
+                                const uint32_t b = 1u << (cell & 31u), ws = cell >> 5;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) m.w[q] |= (ws == (uint32_t)q) ? b : 0u;
+                            }
+                            fin[pl] = m;
+                        }
+                    }
+                }
+                if (active) {
+                    const size_t g = (size_t)li * p.k + pid;
+                    if (WANT_TRACE && p.trace) {
+                        const uint32_t nt = min(depth, p.max_trace);
+                        for (uint32_t t = 0; t < nt; ++t) p.trace[g * p.max_trace + t] = order[t][lane];
+                    }
+                    if (WANT_TRACE && p.rec) {
+                        mr_playout_record rr;
+                        rr.depth = depth;
+                        rr.outcome = (uint8_t)(winner == 0 ? MR_WINNER_P0 : (winner == 1 ? MR_WINNER_P1 : MR_DRAW));
+                        rr.end_type = (uint8_t)(cut ? MR_END_TURN_LIMIT : MR_END_TERMINAL);
+                        rr.pad[0] = rr.pad[1] = 0;
+                        p.rec[g] = rr;
+                    }
+                    if (WANT_FINAL && p.final_state) {
+                        mr_leaf *out = &p.final_state[g];
+#pragma unroll
+                        for (int pl = 0; pl < 2; ++pl) {
+                            out->board[2 * pl] = mk64(fin[pl].w[0], fin[pl].w[1]);
+                            out->board[2 * pl + 1] = mk64(fin[pl].w[2], fin[pl].w[3]);
+                        }
+                        out->turn = (uint8_t)((leaf_turn + depth) & 1u);
+                        out->flag = 0;
+                        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+                    }
+                }
+                if (WANT_AMAF) {
+                    if (p.amaf) {
+                        // occurrences = stones at the stop ply minus leaf stones (every cell is played at most
+                        // once); lane L owns cells L, L+32, L+64, L+96 of both players: no atomics
+                        __syncwarp();
+                        const uint32_t n_act = min(32u, pid_end - round);
+                        for (uint32_t f = 0; f < n_act; ++f) {
+                            const uint32_t d_f = __shfl_sync(FULL_MASK, depth, f);
+                            const int w_f = __shfl_sync(FULL_MASK, winner, f);
+                            if (amaf_plies + d_f > STAT_FLUSH_PLIES) {
+                                flush_stat_table<H>(amaf_tab, p.amaf + (size_t)li * 2 * H::NA, lane);
+                                amaf_plies = 0;
+                            }
+                            amaf_plies += d_f;
+#pragma unroll
+                            for (int pl = 0; pl < 2; ++pl) {
+                                const int u = w_f < 0 ? 0 : (w_f == pl ? 1 : -1);
+                                const uint32_t inc = 1u + ((uint32_t)u << 16);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint32_t played = __shfl_sync(FULL_MASK, fin[pl].w[q], f) & ~sh.stones[pl].w[q];
+                                    if ((played >> lane) & 1u) amaf_tab[pl * H::NSLOTS + q * 32 + lane] += inc;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+            }
+            if (WANT_AMAF && p.amaf) {
+                flush_stat_table<H>(amaf_tab, p.amaf + (size_t)li * 2 * H::NA, lane);
+                amaf_plies = 0;
+            }
+        }
+
+        acc_w0 = __reduce_add_sync(FULL_MASK, acc_w0);
+        acc_w1 = __reduce_add_sync(FULL_MASK, acc_w1);
+        acc_draw = __reduce_add_sync(FULL_MASK, acc_draw);
+        acc_cut = __reduce_add_sync(FULL_MASK, acc_cut);
+        acc_depth = __reduce_add_sync(FULL_MASK, acc_depth);
+        if (lane == 0) {
+            mr_leaf_result *res = p.results + li;
+            if (acc_w0) atomicAdd(&res->wins[0], acc_w0);
+            if (acc_w1) atomicAdd(&res->wins[1], acc_w1);
+            if (acc_draw) atomicAdd(&res->draws, acc_draw);
+            if (acc_cut) atomicAdd(&res->cutoffs, acc_cut);
+            if (acc_depth) atomicAdd(reinterpret_cast<unsigned long long *>(&res->sum_depth), (unsigned long long)acc_depth);
+        }
+    }
+}
+
+} // namespace mr

@@ -1,8 +1,9 @@
 // rollout_kernel.cuh -- the persistent-warp playout kernel (sm_100a).
 //
 // Work decomposition
-//   task      = (leaf, chunk of `chunk` consecutive playout ids); a task never straddles leaves
-//   warp      = pulls tasks from a global atomic counter until the range is exhausted
+//   work      = global playout indices g = leaf * k + playout; a warp grabs contiguous ranges from a global
+//               atomic counter with guided self-scheduling and cuts them at leaf boundaries into
+//   task      = (leaf, run of consecutive playout ids); a task never straddles leaves
 //   lane      = one playout at a time; lanes that finish pull the next playout id of the task at the
 //               next WINDOW boundary (a window = one Philox4x32 block: 4 plies, or 2 plies for the
 //               epsilon-MAST policy which needs two words per ply), so all live lanes of a warp are always
@@ -80,16 +81,35 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
         for (uint32_t e = lane; e < 2u * G::NSLOTS; e += 32) amaf_tab[e] = 0;
     __syncwarp();
 
+    unsigned long long grab_lo = 0, grab_hi = 0; // the warp's current grab, relative to g_begin
+    const unsigned long long work_total = p.g_end - p.g_begin;
     for (;;) {
-        // ---- next task ----
-        uint32_t task = 0;
-        if (lane == 0) task = p.task_begin + atomicAdd(p.task_counter, 1u);
-        task = __shfl_sync(FULL_MASK, task, 0);
-        if (task >= p.task_end) break;
-        const uint32_t li = task / p.chunks_per_leaf;
-        const uint32_t ci = task - li * p.chunks_per_leaf;
-        const uint32_t pid_begin = ci * p.chunk;
-        const uint32_t pid_end = min(pid_begin + p.chunk, p.k);
+        // ---- next task: the part of the current grab that lies inside one leaf ----
+        if (grab_lo >= grab_hi) {
+            unsigned long long lo = 0;
+            uint32_t want = 0;
+            if (lane == 0) {
+                const unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(p.work_counter);
+                const unsigned long long remaining = seen < work_total ? work_total - seen : 0ull;
+                unsigned long long w = remaining / ((unsigned long long)p.grab_div * p.total_warps);
+                w = w > p.grab_max ? p.grab_max : w;
+                w = w < p.grab_min ? p.grab_min : w;
+                want = (uint32_t)w & ~31u;
+                lo = atomicAdd(p.work_counter, (unsigned long long)want);
+            }
+            lo = __shfl_sync(FULL_MASK, lo, 0);
+            want = __shfl_sync(FULL_MASK, want, 0);
+            if (lo >= work_total) break;
+            grab_lo = lo;
+            grab_hi = lo + want < work_total ? lo + want : work_total;
+        }
+        const unsigned long long g0 = p.g_begin + grab_lo;
+        const uint32_t li = (uint32_t)(g0 / p.k);
+        const uint32_t pid_begin = (uint32_t)(g0 - (unsigned long long)li * p.k);
+        const unsigned long long room = (unsigned long long)p.k - pid_begin; // playouts left in this leaf
+        const unsigned long long take = grab_hi - grab_lo < room ? grab_hi - grab_lo : room;
+        const uint32_t pid_end = pid_begin + (uint32_t)take;
+        grab_lo += take;
         const uint32_t leaf_id = p.leaf_id_base + li;
 
         // ---- stage the leaf record in shared memory (one coalesced 40-byte read per warp) ----

@@ -21,7 +21,7 @@ leaves = g.random_positions(w["plies"], n, seed=w["pos_seed"])
 mast = None
 if w["policy"] == 1:
     g.strategy = mb.Uniform()
-    mast = g.simulate_many(leaves[:64], 64, want_mast_delta=True, seed=999).mast_delta.copy()
+    mast = g.simulate_many(leaves, bench.MAST_WARMUP_K, want_mast_delta=True, seed=999).mast_delta.copy()
     g.strategy = strat
 for i in range(launches):
     r = g.simulate_many(leaves, k, stats=mast, want_mast_delta=(w["policy"] == 1), want_amaf=w["amaf"], leaf_id_base=i * n)
