@@ -83,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
         except OSError:
@@ -296,11 +296,11 @@ def run_gpu(args):
                     root_merge.merge_sum_(d_delta)
                 root_merge.merge_sum_(d_root)
 
+        if sampler:
+            sampler.start()  # before the warm-up: the timed region of this path is tens of milliseconds
         for i in range(warmup):
             step(i)
         barrier()
-        if sampler:
-            sampler.start()
         evs = []
         launches_before = g.kernel_launches()
         for i in range(steps):

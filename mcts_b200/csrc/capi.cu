@@ -179,10 +179,12 @@ kernel_fn pick_kernel(int game, int policy, int v) {
     case MR_BREAKTHROUGH:
         if (policy == MR_UNIFORM) return pick_variant<Breakthrough, MR_UNIFORM>(v);
         if (policy == MR_EPS_MAST) return pick_variant<Breakthrough, MR_EPS_MAST>(v);
+        if (policy == MR_DECISIVE_WIN) return pick_variant<Breakthrough, MR_DECISIVE_WIN>(v);
         return nullptr;
     case MR_KNIGHTTHROUGH:
         if (policy == MR_UNIFORM) return pick_variant<Knightthrough, MR_UNIFORM>(v);
         if (policy == MR_EPS_MAST) return pick_variant<Knightthrough, MR_EPS_MAST>(v);
+        if (policy == MR_DECISIVE_WIN) return pick_variant<Knightthrough, MR_DECISIVE_WIN>(v);
         return nullptr;
     case MR_OTHELLO:
         // DecisiveMove<Win> provably never changes an Othello pick, so it shares the kernel

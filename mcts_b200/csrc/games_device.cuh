@@ -45,6 +45,8 @@ __device__ __forceinline__ uint32_t select32(uint32_t w, uint32_t idx) {
 // ==========================================================================================
 struct Connect4 {
     static constexpr int NA = 7;
+    static constexpr bool ROLLED = false;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int NSLOTS = 7; // compact per-player statistic slots (== action ids here)
     static constexpr bool MASK_AMAF = false;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
@@ -199,6 +201,8 @@ struct Connect4 {
 // ==========================================================================================
 struct ThroughBase {
     static constexpr int NA = 4096;
+    static constexpr bool ROLLED = false;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr bool MASK_AMAF = false;
     static constexpr uint64_t NOT_COL0 = 0xFEFEFEFEFEFEFEFEull;
     static constexpr uint64_t NOT_COL7 = 0x7F7F7F7F7F7F7F7Full;
@@ -383,7 +387,20 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
     if (n == 0) return ST_NO_ACTIONS;
     uint32_t idx = 0, src = 0, dir = 0;
     bool have = false;
-    if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+    if (POLICY == MR_DECISIVE_WIN) {
+        // DecisiveMove<Win> (simulate.rs:662-687): the first action in list order whose child is a win for the
+        // mover.  A Breakthrough move wins iff it lands on the far wall, i.e. iff its source is on the row next
+        // to it; no move can lose or draw on the spot, so the loser/draw fallbacks never fire.
+        const uint64_t last_row = is_white ? 0x00FF000000000000ull : 0x000000000000FF00ull;
+        const uint64_t any_win = (W | F | E) & last_row;
+        if (any_win) {
+            src = (uint32_t)__ffsll((long long)any_win) - 1u;
+            dir = ((W >> src) & 1ull) ? 0u : (((F >> src) & 1ull) ? 1u : 2u);
+            have = true;
+        } else {
+            idx = mulhi(x0, n);
+        }
+    } else if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
         const uint32_t pl = is_white ? 1u : 0u;
         uint64_t cand[3] = {W, F, E};
         mast_argmax<3>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
@@ -510,7 +527,31 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
 
     uint32_t idx = 0, src = 0, kind = 0;
     bool have = false;
-    if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+    if (POLICY == MR_DECISIVE_WIN) {
+        // first action in list order that lands on the far wall (simulate.rs:662-687); a jump of two rows wins
+        // from the two rows next to it, a jump of one row from the row next to it
+        const uint64_t r1 = is_white ? 0x00FF000000000000ull : 0x000000000000FF00ull; // one row from the goal
+        const uint64_t r2 = is_white ? 0x0000FF0000000000ull : 0x0000000000FF0000ull; // two rows from the goal
+        uint64_t win[8];
+        uint64_t any_win = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            // kinds 0,1 jump -2 rows, 2,3 jump -1 row, 4,5 jump +1 row, 6,7 jump +2 rows
+            const bool toward = is_white ? q >= 4 : q < 4;
+            const bool two = q < 2 || q >= 6;
+            win[q] = toward ? (M[q] & (two ? (r1 | r2) : r1)) : 0ull;
+            any_win |= win[q];
+        }
+        if (any_win) {
+            src = (uint32_t)__ffsll((long long)any_win) - 1u;
+#pragma unroll
+            for (int q = 7; q >= 0; --q)
+                if ((win[q] >> src) & 1ull) kind = q;
+            have = true;
+        } else {
+            idx = mulhi(x0, n);
+        }
+    } else if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
         const uint32_t pl = is_white ? 1u : 0u;
         uint64_t cand[8];
 #pragma unroll
@@ -598,8 +639,10 @@ struct Othello {
     static constexpr int NSLOTS = 65;
     static constexpr bool MASK_AMAF = false;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
-    static constexpr uint64_t NOT_A = 0xFEFEFEFEFEFEFEFEull; // not column 0
-    static constexpr uint64_t NOT_H = 0x7F7F7F7F7F7F7F7Full; // not column 7
+    // The per-ply code (8 fills for moves + 8 for flips) is large: the four plies of a window run as a LOOP,
+    // with the ply's parity a run-time value, so the kernel fits the instruction cache.
+    static constexpr bool ROLLED = true;
+    static constexpr int MIN_BLOCKS = 1; // a register cap (6 blocks/SM, 80 regs) measured no faster on B200
 
     struct Shared {
         uint64_t black, white;
@@ -607,48 +650,46 @@ struct Othello {
     };
     uint64_t black, white;
     uint32_t last_pass;
+    uint32_t rt_parity; // parity of the current ply inside its window (PARITY == 2 call sites)
 
-    // discs of `o` reachable from `g` by repeated shifts (left when L, else right) by `s`, staying inside `o & mask`
-    template <int S, bool L>
-    __device__ static uint64_t fill(uint64_t g, uint64_t o, uint64_t mask) {
-        const uint64_t om = o & mask;
-        uint64_t f = (L ? (g << S) : (g >> S)) & om;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) f |= (L ? (f << S) : (f >> S)) & om;
-        return f;
-    }
     template <int S, bool L>
     __device__ static uint64_t sh(uint64_t v) { return L ? (v << S) : (v >> S); }
 
-    __device__ static uint64_t legal_moves(uint64_t P, uint64_t O) {
-        const uint64_t empty = ~(P | O);
-        uint64_t m = 0;
-        m |= sh<8, true>(fill<8, true>(P, O, ~0ull));
-        m |= sh<8, false>(fill<8, false>(P, O, ~0ull));
-        m |= sh<1, true>(fill<1, true>(P, O, NOT_A)) & NOT_A;   // east: results never land in column 0
-        m |= sh<1, false>(fill<1, false>(P, O, NOT_H)) & NOT_H; // west
-        m |= sh<9, true>(fill<9, true>(P, O, NOT_A)) & NOT_A;   // north-east
-        m |= sh<9, false>(fill<9, false>(P, O, NOT_H)) & NOT_H; // south-west
-        m |= sh<7, true>(fill<7, true>(P, O, NOT_H)) & NOT_H;   // north-west
-        m |= sh<7, false>(fill<7, false>(P, O, NOT_A)) & NOT_A; // south-east
-        return m & empty;
-    }
+    // discs of `om` reachable from `g` by repeated steps of S (left when L): parallel prefix, runs of <= 6 discs
+    // (the same Kogge-Stone scheme as othello/lib.rs:101-124, with the wall mask folded into `om`)
     template <int S, bool L>
-    __device__ static uint64_t flips_dir(uint64_t mv, uint64_t P, uint64_t O, uint64_t mask) {
-        const uint64_t f = fill<S, L>(mv, O, mask);
-        const uint64_t end = sh<S, L>(f) & mask & P;
-        return end ? f : 0ull;
+    __device__ static uint64_t ray(uint64_t g, uint64_t om) {
+        uint64_t f = om & sh<S, L>(g);
+        f |= om & sh<S, L>(f);
+        const uint64_t pre = om & sh<S, L>(om);
+        f |= pre & sh<2 * S, L>(f);
+        f |= pre & sh<2 * S, L>(f);
+        return f;
+    }
+
+    // othello/lib.rs:132-180.  An opponent disc on column 0 or 7 can never be outflanked along a row or a
+    // diagonal, so those axes flood through `O & INNER` and need no wrap masks on the final step.
+    static constexpr uint64_t INNER = 0x7E7E7E7E7E7E7E7Eull;
+    __device__ static uint64_t legal_moves(uint64_t P, uint64_t O) {
+        const uint64_t mO = O & INNER;
+        uint64_t m = sh<8, true>(ray<8, true>(P, O)) | sh<8, false>(ray<8, false>(P, O));
+        m |= sh<1, true>(ray<1, true>(P, mO)) | sh<1, false>(ray<1, false>(P, mO));
+        m |= sh<9, true>(ray<9, true>(P, mO)) | sh<9, false>(ray<9, false>(P, mO));
+        m |= sh<7, true>(ray<7, true>(P, mO)) | sh<7, false>(ray<7, false>(P, mO));
+        return m & ~(P | O);
+    }
+    // othello/lib.rs:188-234: a direction flips its run iff the cell after the run holds an own disc
+    template <int S, bool L>
+    __device__ static uint64_t flips_dir(uint64_t mv, uint64_t P, uint64_t om) {
+        const uint64_t f = ray<S, L>(mv, om);
+        return (sh<S, L>(f) & P) ? f : 0ull;
     }
     __device__ static uint64_t flips(uint64_t mv, uint64_t P, uint64_t O) {
-        uint64_t f = 0;
-        f |= flips_dir<8, true>(mv, P, O, ~0ull);
-        f |= flips_dir<8, false>(mv, P, O, ~0ull);
-        f |= flips_dir<1, true>(mv, P, O, NOT_A);
-        f |= flips_dir<1, false>(mv, P, O, NOT_H);
-        f |= flips_dir<9, true>(mv, P, O, NOT_A);
-        f |= flips_dir<9, false>(mv, P, O, NOT_H);
-        f |= flips_dir<7, true>(mv, P, O, NOT_H);
-        f |= flips_dir<7, false>(mv, P, O, NOT_A);
+        const uint64_t mO = O & INNER;
+        uint64_t f = flips_dir<8, true>(mv, P, O) | flips_dir<8, false>(mv, P, O);
+        f |= flips_dir<1, true>(mv, P, mO) | flips_dir<1, false>(mv, P, mO);
+        f |= flips_dir<9, true>(mv, P, mO) | flips_dir<9, false>(mv, P, mO);
+        f |= flips_dir<7, true>(mv, P, mO) | flips_dir<7, false>(mv, P, mO);
         return f;
     }
     __device__ static int count_outcome(uint64_t b, uint64_t w) {
@@ -676,7 +717,7 @@ struct Othello {
 
     template <int POLICY, int PARITY>
     __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
-        const bool is_white = ((s.turn ^ PARITY) & 1u) != 0;
+        const bool is_white = ((s.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u) != 0;
         const uint64_t P = is_white ? white : black, O = is_white ? black : white;
         const uint64_t moves = legal_moves(P, O);
         if (moves == 0) {

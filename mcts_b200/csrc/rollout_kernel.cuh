@@ -52,7 +52,7 @@ __device__ __forceinline__ void flush_stat_table(uint32_t *tab, mr_action_stat *
 }
 
 template <class G, int POLICY, int FLAGS>
-__global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const KernelParams p) {
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kernel(const KernelParams p) {
     constexpr bool WANT_AMAF = (FLAGS & MR_WANT_AMAF) != 0;
     constexpr bool WANT_MAST = (FLAGS & MR_WANT_MAST_DELTA) != 0;
     constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
@@ -160,10 +160,11 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
             for (;;) {
                 uint32_t r[4];
                 philox4x32_10(leaf_id, pid, win, POLICY == MR_EPS_MAST ? 1u : 0u, p.seed_lo, p.seed_hi, r);
-                // one ply; J is the ply's phase inside the window, so the mover's colour (leaf turn ^ (J & 1))
-                // and the Philox word index are compile-time per call site
-                auto ply = [&](auto J) {
-                    constexpr int j = decltype(J)::value;
+                // one ply.  PAR is the ply's parity inside the window: a compile-time 0/1 when the window is
+                // unrolled (the mover's colour = leaf turn ^ PAR is then fixed per call site), or 2 = "run-time,
+                // read st.rt_parity" for games whose window runs as a loop
+                auto ply = [&](auto PAR, const uint32_t x0, const uint32_t x1) {
+                    constexpr int par = decltype(PAR)::value;
                     if (alive) {
                         if (depth >= p.max_depth) { // simulate.rs:104-108 TurnLimit
                             alive = false;
@@ -171,9 +172,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
                             end_code = ST_DRAW;
                         } else {
                             uint32_t action = 0, slot = 0;
-                            const uint32_t x0 = POLICY == MR_EPS_MAST ? r[(2 * j) & 3] : r[j];
-                            const uint32_t x1 = POLICY == MR_EPS_MAST ? r[(2 * j + 1) & 3] : 0u;
-                            const int code = st.template step<POLICY, (j & 1)>(sh, x0, x1, p, action, slot);
+                            const int code = st.template step<POLICY, par>(sh, x0, x1, p, action, slot);
                             if (code & ST_MOVED) {
                                 if (WANT_TRACE && p.trace) {
                                     if (depth < p.max_trace)
@@ -191,11 +190,25 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK) rollout_kernel(const Kernel
                         }
                     }
                 };
-                ply(std::integral_constant<int, 0>{});
-                ply(std::integral_constant<int, 1>{});
-                if constexpr (WINDOW == 4) {
-                    ply(std::integral_constant<int, 2>{});
-                    ply(std::integral_constant<int, 3>{});
+                if constexpr (G::ROLLED) {
+                    static_assert(POLICY != MR_EPS_MAST, "rolled windows are built for one-word-per-ply policies");
+#pragma unroll 1
+                    for (uint32_t j = 0; j < (uint32_t)WINDOW; ++j) {
+                        st.rt_parity = j & 1u;
+                        const uint32_t x0 = r[0];
+                        r[0] = r[1];
+                        r[1] = r[2];
+                        r[2] = r[3];
+                        ply(std::integral_constant<int, 2>{}, x0, 0u);
+                    }
+                } else if constexpr (POLICY == MR_EPS_MAST) {
+                    ply(std::integral_constant<int, 0>{}, r[0], r[1]);
+                    ply(std::integral_constant<int, 1>{}, r[2], r[3]);
+                } else {
+                    ply(std::integral_constant<int, 0>{}, r[0], 0u);
+                    ply(std::integral_constant<int, 1>{}, r[1], 0u);
+                    ply(std::integral_constant<int, 0>{}, r[2], 0u);
+                    ply(std::integral_constant<int, 1>{}, r[3], 0u);
                 }
                 ++win;
 

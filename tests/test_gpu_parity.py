@@ -135,7 +135,7 @@ def test_amaf_tables_bit_exact(game):
     assert got.amaf["visits"].sum() == got.results["sum_depth"].sum()
 
 
-@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4])
+@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH])
 def test_decisive_win_bit_exact(game):
     leaves = _leaves(game, n_per=4)
     if game == o.OTHELLO:  # late positions, where the 64th-disc case can occur
