@@ -191,15 +191,19 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                     }
                 };
                 if constexpr (G::ROLLED) {
-                    static_assert(POLICY != MR_EPS_MAST, "rolled windows are built for one-word-per-ply policies");
 #pragma unroll 1
                     for (uint32_t j = 0; j < (uint32_t)WINDOW; ++j) {
                         st.rt_parity = j & 1u;
-                        const uint32_t x0 = r[0];
-                        r[0] = r[1];
-                        r[1] = r[2];
-                        r[2] = r[3];
-                        ply(std::integral_constant<int, 2>{}, x0, 0u);
+                        const uint32_t x0 = r[0], x1 = r[1];
+                        if constexpr (POLICY == MR_EPS_MAST) {
+                            r[0] = r[2];
+                            r[1] = r[3];
+                        } else {
+                            r[0] = r[1];
+                            r[1] = r[2];
+                            r[2] = r[3];
+                        }
+                        ply(std::integral_constant<int, 2>{}, x0, x1);
                     }
                 } else if constexpr (POLICY == MR_EPS_MAST) {
                     ply(std::integral_constant<int, 0>{}, r[0], r[1]);
