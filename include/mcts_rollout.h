@@ -211,7 +211,13 @@ int mr_comm_allreduce_i32(mr_ctx *ctx, void *d_buf, size_t n, void *stream);
  * In the reference this driver is Rust; here it is C++ inside the library because no Rust toolchain exists
  * in the build image -- a Rust host would keep its own tree and call mr_submit / mr_wait directly.
  */
-enum mr_select { MR_SELECT_UCB1 = 0, MR_SELECT_UCB1_TUNED = 1 }; /* select/ucb.rs:9-146 */
+enum mr_select {
+    MR_SELECT_UCB1 = 0,       /* select/ucb.rs:9-62 */
+    MR_SELECT_UCB1_TUNED = 1, /* select/ucb.rs:64-146 */
+    MR_SELECT_GRAVE = 2       /* select/rave.rs:118-238 Rave{threshold, schedule, RaveUcb::Ucb1}: reads the AMAF/GRAVE
+                                 tables the kernels accumulate (threshold 0 = RAVE, huge = HRAVE) */
+};
+enum mr_rave_schedule { MR_RAVE_HAND_SELECTED = 0, MR_RAVE_THRESHOLD = 1 }; /* select/rave.rs:42-76 */
 enum mr_qinit { MR_QINIT_PARENT = 0, MR_QINIT_INFINITY = 1 };     /* node.rs:95-159 */
 /* MR_SEARCH_TRANSPOSITIONS: SearchConfig.use_transpositions -- a new child whose state is already in the
  * table reuses that node (search/shared.rs:412-436, table.rs); statistics stay on the edges.  The table is
@@ -233,6 +239,10 @@ typedef struct {
     double exploration_c;       /* sqrt(2) by default (select/ucb.rs:22-27) */
     double epsilon;             /* MR_EPS_MAST */
     uint64_t seed;
+    uint32_t grave_threshold;   /* Rave.threshold (default 700) */
+    uint32_t rave_schedule;     /* mr_rave_schedule */
+    uint32_t rave_param;        /* HandSelected k (default 1000) / Threshold rave */
+    uint32_t pad;
 } mr_search_desc;
 
 typedef struct {

@@ -54,6 +54,10 @@ class SearchDesc(C.Structure):
         ("exploration_c", C.c_double),
         ("epsilon", C.c_double),
         ("seed", C.c_uint64),
+        ("grave_threshold", C.c_uint32),
+        ("rave_schedule", C.c_uint32),
+        ("rave_param", C.c_uint32),
+        ("pad", C.c_uint32),
     ]
 
 

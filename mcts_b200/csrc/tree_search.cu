@@ -131,12 +131,53 @@ struct Tree {
     }
 };
 
+struct GraveStat { // node.rs:51-55 ActionStats with an integer score
+    uint32_t visits = 0;
+    int64_t score = 0;
+};
+
 struct Search {
     mr_ctx *ctx;
     const mr_search_desc *d;
     Tree t;
     std::vector<mr_action_stat> mast; // [2][NA], TreeStats.player_actions
     int na;
+    // TreeStats.grave (search/shared.rs:52): per reference-node state, per player, per action.  The reference keys
+    // it by node.hash; here the key is the full state record (no collisions), so equal states share one table.
+    std::unordered_map<StateKey, uint32_t, StateKeyHash> grave_index;
+    std::vector<std::vector<GraveStat>> grave; // [table][2 * NA]
+
+    std::vector<GraveStat> *grave_of(const mr_leaf &s, bool create) {
+        auto it = grave_index.find(key_of(s));
+        if (it != grave_index.end()) return &grave[it->second];
+        if (!create) return nullptr;
+        grave_index.emplace(key_of(s), (uint32_t)grave.size());
+        grave.emplace_back((size_t)2 * na);
+        return &grave.back();
+    }
+
+    // select/rave.rs:60-75
+    double rave_beta(uint32_t n, uint32_t amaf_n) const {
+        (void)amaf_n;
+        if (d->rave_schedule == MR_RAVE_THRESHOLD) {
+            const double rave = (double)d->rave_param;
+            return std::max(0.0, rave - (double)n) / rave;
+        }
+        const double k = (double)d->rave_param;
+        return std::sqrt(k / (3.0 * (double)n + k));
+    }
+    // select/rave.rs:157-184 get_ref: the nearest node on the path (the child itself first) whose incoming edge
+    // has total_visits >= threshold, else the root
+    uint32_t grave_ref(const std::vector<PathEntry> &path, uint32_t child_node, uint32_t child_idx) const {
+        const Node &cur = t.nodes[path.back().node];
+        const Stats &ce = t.edge[cur.first + child_idx];
+        if (ce.visits + ce.vloss >= d->grave_threshold) return child_node;
+        for (size_t i = path.size(); i-- > 1;) {
+            const Stats &e = t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
+            if (e.visits + e.vloss >= d->grave_threshold) return path[i].node;
+        }
+        return 0;
+    }
 
     const Stats &current_stats(const std::vector<PathEntry> &path) const {
         if (path.size() == 1) return t.root_stats;
@@ -158,6 +199,7 @@ struct Search {
         else q_unvisited = cur.visits == 0 ? 10000.0 : expected_score(cur, player);
         double unvisited_value;
         if (d->select == MR_SELECT_UCB1_TUNED) unvisited_value = q_unvisited + (parent_log * std::min(1.0, 1.0) + c * std::sqrt(parent_log));
+        else if (d->select == MR_SELECT_GRAVE) unvisited_value = q_unvisited; // rave.rs:226-230: no exploration term
         else unvisited_value = q_unvisited + c * std::sqrt(parent_log);
 
         const uint32_t n = node.n_children;
@@ -179,6 +221,21 @@ struct Search {
                     const double var = std::max(0.0, (double)e.sumsq[player] / total - exploit * exploit);
                     const double frac = parent_log / total;
                     score = exploit + (frac * std::min(1.0, var) + c * std::sqrt(frac));
+                } else if (d->select == MR_SELECT_GRAVE) { // rave.rs:196-224
+                    const uint32_t ref = grave_ref(path, (uint32_t)t.child[node.first + i], i);
+                    uint32_t amaf_n = 0;
+                    double amaf_q = 0.0;
+                    auto git = grave_index.find(key_of(t.nodes[ref].state));
+                    if (git != grave_index.end()) {
+                        const GraveStat &g = grave[git->second][(size_t)player * na + mr_host::action_id(t.game, t.action[node.first + i])];
+                        amaf_n = g.visits;
+                        amaf_q = (double)g.score;
+                    }
+                    const uint32_t n_tot = e.visits + e.vloss;
+                    const double explore = c * std::sqrt(parent_log / (double)n_tot);
+                    const double b = rave_beta(n_tot, amaf_n);
+                    const double amaf = amaf_n == 0 ? 0.0 : amaf_q / (double)amaf_n;
+                    score = (1.0 - b) * exploit + b * amaf + explore;
                 } else {
                     score = exploit + c * std::sqrt(parent_log / total);
                 }
@@ -242,10 +299,32 @@ struct Search {
         for (size_t i = 1; i < path.size(); ++i) t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += extra;
     }
 
+    // update_grave (backprop.rs:619-640) for the k trials of one leaf: every non-root node X of the path gets, per
+    // (action, player) occurrence of [playout trace + the path's edges BELOW X], visits += 1 and score += u[player].
+    // `amaf` is the kernel's per-leaf occurrence table of the playout traces ([2][NA]).
+    void backprop_grave(const std::vector<PathEntry> &path, const mr_action_stat *amaf, const int64_t u[2], uint32_t k) {
+        std::vector<std::pair<uint32_t, int>> below; // (action id, player) of the edges below the node being updated
+        for (size_t i = path.size(); i-- > 1;) {
+            std::vector<GraveStat> &tab = *grave_of(t.nodes[path[i].node].state, true);
+            for (size_t e = 0; e < (size_t)2 * na; ++e) {
+                tab[e].visits += amaf[e].visits;
+                tab[e].score += amaf[e].score;
+            }
+            for (const auto &b : below) {
+                GraveStat &g = tab[(size_t)b.second * na + b.first];
+                g.visits += k;
+                g.score += u[b.second];
+            }
+            const Node &parent = t.nodes[path[i - 1].node];
+            below.emplace_back((uint32_t)mr_host::action_id(t.game, t.action[parent.first + path[i].idx]), (int)parent.player);
+        }
+    }
+
     // k trials of one leaf, aggregated
-    void backprop(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k) {
+    void backprop(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k, const mr_action_stat *amaf) {
         const int64_t nonzero = (int64_t)k - r.draws;
         const int64_t u[2] = {(int64_t)r.wins[0] - (nonzero - r.wins[0]), (int64_t)r.wins[1] - (nonzero - r.wins[1])};
+        if (amaf) backprop_grave(path, amaf, u, k);
         for (size_t i = path.size(); i-- > 0;) {
             Stats &s = i == 0 ? t.root_stats : t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
             s.visits += k;
@@ -309,6 +388,8 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     std::vector<mr_leaf> leaves(B);
     std::vector<mr_leaf_result> results(B);
     std::vector<mr_action_stat> delta(desc->policy == MR_EPS_MAST ? (size_t)2 * s.na : 0);
+    const bool want_amaf = desc->select == MR_SELECT_GRAVE;
+    std::vector<mr_action_stat> amaf(want_amaf ? (size_t)B * 2 * s.na : 0);
     mr_search_stats st;
     memset(&st, 0, sizeof st);
 
@@ -329,16 +410,17 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         bd.n_leaves = nb;
         bd.playouts_per_leaf = k;
         bd.max_playout_depth = desc->max_playout_depth;
-        bd.flags = desc->policy == MR_EPS_MAST ? MR_WANT_MAST_DELTA : 0;
+        bd.flags = (desc->policy == MR_EPS_MAST ? MR_WANT_MAST_DELTA : 0) | (want_amaf ? MR_WANT_AMAF : 0);
         bd.seed = desc->seed;
         bd.leaf_id_base = done;
         bd.epsilon = desc->epsilon;
-        int rc = mr_playout_batch(ctx, &bd, leaves.data(), s.mast.empty() ? nullptr : s.mast.data(), results.data(), nullptr,
-                                  delta.empty() ? nullptr : delta.data(), nullptr, nullptr, nullptr);
+        int rc = mr_playout_batch(ctx, &bd, leaves.data(), s.mast.empty() ? nullptr : s.mast.data(), results.data(),
+                                  want_amaf ? amaf.data() : nullptr, delta.empty() ? nullptr : delta.data(), nullptr, nullptr,
+                                  nullptr);
         if (rc != MR_OK) return rc;
         double t2 = now_s();
         for (uint32_t b = 0; b < nb; ++b) {
-            s.backprop(paths[b], results[b], k);
+            s.backprop(paths[b], results[b], k, want_amaf ? amaf.data() + (size_t)b * 2 * s.na : nullptr);
             st.playout_plies += results[b].sum_depth;
         }
         for (size_t i = 0; i < delta.size(); ++i) { // playout-trace part of the GLOBAL write

@@ -140,7 +140,7 @@ int orc_stress_through(int game, uint64_t num_games, uint64_t *goal_wins, uint64
 typedef struct {
     int game;
     int policy;
-    int select;                 /* 0 UCB1, 1 UCB1-Tuned (select/ucb.rs) */
+    int select;                 /* 0 UCB1, 1 UCB1-Tuned (select/ucb.rs), 2 GRAVE (select/rave.rs, RaveUcb::Ucb1) */
     int q_init;                 /* 0 Parent, 1 Infinity (node.rs:95-159) */
     uint32_t max_iterations;    /* leaf selections */
     uint32_t batch_leaves;      /* 1 = the reference's sequential loop */
@@ -152,6 +152,9 @@ typedef struct {
     double exploration_c;
     uint64_t eps_threshold;
     uint64_t seed;
+    uint32_t grave_threshold;   /* Rave.threshold */
+    int rave_schedule;          /* 0 HandSelected{k}, 1 Threshold{rave} (rave.rs:42-76) */
+    uint32_t rave_param;
 } orc_search_cfg;
 
 typedef struct {

@@ -14,6 +14,8 @@
  *   backprop .............. backprop.rs:686-731; NodeStats/ChildArray update node.rs:295-302, 673-681
  *   GLOBAL (MAST) write ... backprop.rs:833-870 (playout trace + tree path)
  *   final action .......... RobustChild select/basic.rs:13-45 through core.rs:138-198
+ *   GRAVE ................. select/rave.rs:60-75 (beta), :157-184 (get_ref), :196-230 (score); tables written by
+ *                           update_grave, backprop.rs:619-640, with amaf_actions grown per :833-854
  *
  * Batched mode (batch_leaves > 1) is the deterministic, sequential statement of what the tree-parallel
  * workers do concurrently (search/parallel.rs:188-251): B descents that each leave their virtual losses in
@@ -71,6 +73,55 @@ static uint64_t state_hash(const orc_state *s) {
 typedef struct {
     uint32_t node, idx;
 } entry_t;
+
+/* TreeStats.grave (search/shared.rs:52): state -> [2][na] (visits, score).  The reference keys by node.hash;
+ * the key here is the whole state. */
+typedef struct {
+    uint32_t visits;
+    int64_t score;
+} gstat_t;
+typedef struct {
+    orc_state *states;
+    gstat_t **tabs;
+    size_t n, cap;
+    uint32_t *slots;
+    size_t slot_cap;
+    int na;
+} grave_t;
+
+static gstat_t *grave_find(grave_t *g, const orc_state *s, int create) {
+    if (g->slot_cap == 0 || (g->n + 1) * 2 > g->slot_cap) {
+        if (!create && g->slot_cap == 0) return NULL;
+        if (create) {
+            size_t ncap = g->slot_cap ? g->slot_cap * 2 : 4096;
+            uint32_t *ns = (uint32_t *)malloc(ncap * sizeof(uint32_t));
+            memset(ns, 0xff, ncap * sizeof(uint32_t));
+            for (size_t i = 0; i < g->n; ++i) {
+                size_t j = state_hash(&g->states[i]) & (ncap - 1);
+                while (ns[j] != 0xffffffffu) j = (j + 1) & (ncap - 1);
+                ns[j] = (uint32_t)i;
+            }
+            free(g->slots);
+            g->slots = ns;
+            g->slot_cap = ncap;
+        }
+    }
+    size_t j = state_hash(s) & (g->slot_cap - 1);
+    while (g->slots[j] != 0xffffffffu) {
+        if (memcmp(&g->states[g->slots[j]], s, sizeof *s) == 0) return g->tabs[g->slots[j]];
+        j = (j + 1) & (g->slot_cap - 1);
+    }
+    if (!create) return NULL;
+    if (g->n == g->cap) {
+        g->cap = g->cap ? g->cap * 2 : 1024;
+        g->states = (orc_state *)realloc(g->states, g->cap * sizeof(orc_state));
+        g->tabs = (gstat_t **)realloc(g->tabs, g->cap * sizeof(gstat_t *));
+    }
+    g->states[g->n] = *s;
+    g->tabs[g->n] = (gstat_t *)calloc((size_t)2 * g->na, sizeof(gstat_t));
+    g->slots[j] = (uint32_t)g->n;
+    return g->tabs[g->n++];
+}
 
 static double expected_score(const stats_t *s, int player) { /* node.rs:126-133 */
     if (s->visits == 0) return 0.0;
@@ -158,12 +209,30 @@ static const stats_t *current_stats(const tree_t *t, const entry_t *path, int le
 }
 
 typedef struct {
-    int select; /* 0 UCB1, 1 UCB1-Tuned */
+    int select; /* 0 UCB1, 1 UCB1-Tuned, 2 GRAVE */
     int q_init; /* 0 Parent, 1 Infinity */
     double c;
     uint32_t expand_threshold;
     uint64_t seed;
+    uint32_t grave_threshold;
+    int rave_schedule;
+    uint32_t rave_param;
+    grave_t *grave;
 } sel_cfg;
+
+static int action_id(int game, uint16_t a);
+
+/* rave.rs:157-184 get_ref: nearest node on the path, the child first, whose edge has total_visits >= threshold */
+static uint32_t grave_ref(const tree_t *t, const sel_cfg *cfg, const entry_t *path, int len, uint32_t child_node, uint32_t child_idx) {
+    const node_t *cur = &t->nodes[path[len - 1].node];
+    const stats_t *ce = &t->edge[cur->first + child_idx];
+    if (ce->visits + ce->vloss >= cfg->grave_threshold) return child_node;
+    for (int i = len - 1; i >= 1; --i) {
+        const stats_t *e = &t->edge[t->nodes[path[i - 1].node].first + path[i].idx];
+        if (e->visits + e->vloss >= cfg->grave_threshold) return path[i].node;
+    }
+    return 0;
+}
 
 static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *path, int len, uint32_t descent) {
     const node_t *node = &t->nodes[path[len - 1].node];
@@ -171,8 +240,9 @@ static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *p
     const stats_t *cur = current_stats(t, path, len);
     double parent_log = log(fmax(1.0, (double)cur->visits)); /* ucb.rs:34-37 */
     double q_unvisited = cfg->q_init == 1 ? 10000.0 : (cur->visits == 0 ? 10000.0 : expected_score(cur, player));
-    double unvisited_value = cfg->select == 1 ? q_unvisited + (parent_log * fmin(1.0, 1.0) + cfg->c * sqrt(parent_log))
-                                              : q_unvisited + cfg->c * sqrt(parent_log);
+    double unvisited_value = cfg->select == 1   ? q_unvisited + (parent_log * fmin(1.0, 1.0) + cfg->c * sqrt(parent_log))
+                             : cfg->select == 2 ? q_unvisited /* rave.rs:226-230 */
+                                                : q_unvisited + cfg->c * sqrt(parent_log);
     uint32_t n = (uint32_t)node->n_children;
     uint32_t r = (uint32_t)(((uint64_t)tree_draw(cfg->seed, descent, (uint32_t)len - 1) * (16u * n)) >> 32);
     uint32_t i = r / 16u, stride = PRIMES[r % 16u];
@@ -191,6 +261,28 @@ static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *p
                 double var = fmax(0.0, (double)e->sumsq[player] / total - exploit * exploit);
                 double frac = parent_log / total;
                 score = exploit + (frac * fmin(1.0, var) + cfg->c * sqrt(frac));
+            } else if (cfg->select == 2) { /* rave.rs:196-224 */
+                uint32_t ref = grave_ref(t, cfg, path, len, (uint32_t)t->child[node->first + i], i);
+                uint32_t amaf_n = 0;
+                double amaf_q = 0.0;
+                gstat_t *tab = grave_find(cfg->grave, &t->nodes[ref].state, 0);
+                if (tab) {
+                    const gstat_t *g = &tab[(size_t)player * cfg->grave->na + action_id(t->game, t->action[node->first + i])];
+                    amaf_n = g->visits;
+                    amaf_q = (double)g->score;
+                }
+                uint32_t n_tot = e->visits + e->vloss;
+                double explore = cfg->c * sqrt(parent_log / (double)n_tot);
+                double b;
+                if (cfg->rave_schedule == 1) {
+                    double rave = (double)cfg->rave_param;
+                    b = fmax(0.0, rave - (double)n_tot) / rave;
+                } else {
+                    double kk = (double)cfg->rave_param;
+                    b = sqrt(kk / (3.0 * (double)n_tot + kk));
+                }
+                double amaf = amaf_n == 0 ? 0.0 : amaf_q / (double)amaf_n;
+                score = (1.0 - b) * exploit + b * amaf + explore;
             } else { /* ucb.rs:40-52 */
                 score = exploit + cfg->c * sqrt(parent_log / total);
             }
@@ -255,7 +347,12 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     t.use_table = c->use_transpositions;
     if (t.use_table) table_resolve(&t, root);
     else add_node(&t, root);
-    sel_cfg cfg = {c->select, c->q_init, c->exploration_c, c->expand_threshold, c->seed};
+    grave_t grave;
+    memset(&grave, 0, sizeof grave);
+    grave.na = orc_num_actions(c->game);
+    sel_cfg cfg = {c->select, c->q_init, c->exploration_c, c->expand_threshold, c->seed, c->grave_threshold, c->rave_schedule,
+                   c->rave_param, &grave};
+    const int want_amaf = c->select == 2;
     const uint32_t B = c->batch_leaves, k = c->playouts_per_leaf;
     const int na = orc_num_actions(c->game);
     orc_action_stat *mast = c->policy == ORC_EPS_MAST ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
@@ -265,6 +362,9 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     int *plen = (int *)malloc(sizeof(int) * B);
     orc_state *leaves = (orc_state *)malloc(sizeof(orc_state) * B);
     orc_leaf_result *results = (orc_leaf_result *)malloc(sizeof(orc_leaf_result) * B);
+    orc_action_stat *amaf = want_amaf ? (orc_action_stat *)malloc(sizeof(orc_action_stat) * (size_t)B * 2 * na) : NULL;
+    uint32_t *below_a = (uint32_t *)malloc(sizeof(uint32_t) * 1024);
+    int *below_p = (int *)malloc(sizeof(int) * 1024);
     uint64_t plies = 0;
 
     orc_batch_desc bd;
@@ -288,12 +388,33 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
         }
         bd.leaf_id_base = done;
         if (delta) memset(delta, 0, sizeof(orc_action_stat) * 2 * (size_t)na);
-        orc_playout_batch(&bd, leaves, nb, mast, results, NULL, delta, NULL, NULL, NULL, c->threads > 0 ? c->threads : 1);
+        if (amaf) memset(amaf, 0, sizeof(orc_action_stat) * (size_t)nb * 2 * na);
+        orc_playout_batch(&bd, leaves, nb, mast, results, amaf, delta, NULL, NULL, NULL, c->threads > 0 ? c->threads : 1);
         for (uint32_t b = 0; b < nb; ++b) {
             const entry_t *path = paths + (size_t)b * max_path;
             const orc_leaf_result *r = &results[b];
             int64_t nonzero = (int64_t)k - r->draws;
             int64_t u[2] = {(int64_t)r->wins[0] - (nonzero - r->wins[0]), (int64_t)r->wins[1] - (nonzero - r->wins[1])};
+            if (amaf) { /* update_grave for every non-root path node, leaf first (backprop.rs:619-640, 833-854) */
+                const orc_action_stat *la = amaf + (size_t)b * 2 * na;
+                int n_below = 0;
+                for (int i = plen[b] - 1; i >= 1; --i) {
+                    gstat_t *tab = grave_find(&grave, &t.nodes[path[i].node].state, 1);
+                    for (int e = 0; e < 2 * na; ++e) {
+                        tab[e].visits += la[e].visits;
+                        tab[e].score += la[e].score;
+                    }
+                    for (int q = 0; q < n_below; ++q) {
+                        gstat_t *g = &tab[(size_t)below_p[q] * na + below_a[q]];
+                        g->visits += k;
+                        g->score += u[below_p[q]];
+                    }
+                    const node_t *parent = &t.nodes[path[i - 1].node];
+                    below_a[n_below] = (uint32_t)action_id(c->game, t.action[parent->first + path[i].idx]);
+                    below_p[n_below] = parent->player;
+                    ++n_below;
+                }
+            }
             for (int i = plen[b] - 1; i >= 0; --i) {
                 stats_t *s = i == 0 ? &t.root_stats : &t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
                 s->visits += k;
@@ -367,6 +488,13 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     free(t.child);
     free(t.edge);
     free(t.tab);
+    for (size_t i = 0; i < grave.n; ++i) free(grave.tabs[i]);
+    free(grave.tabs);
+    free(grave.states);
+    free(grave.slots);
+    free(amaf);
+    free(below_a);
+    free(below_p);
     free(mast);
     free(delta);
     free(paths);

@@ -58,6 +58,26 @@ def test_search_with_transposition_table_bit_exact():
     assert got.nodes < plain_nodes  # transpositions were actually shared
 
 
+@pytest.mark.parametrize("game,iters,batch,k,thr,sched,param", [
+    (o.HEX11, 2048, 32, 8, 50, 0, 1000),   # BASELINE.json config 3: Hex 11x11, GRAVE reading in-kernel AMAF tables
+    (o.HEX11, 1024, 16, 4, 0, 1, 300),     # threshold 0 = plain RAVE, Threshold schedule
+    (o.CONNECT4, 2048, 32, 8, 100, 0, 1000),
+])
+def test_grave_search_bit_exact(game, iters, batch, k, thr, sched, param):
+    from mcts_b200.search import SELECT_GRAVE, QINIT_INFINITY
+
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), mb.Uniform(), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      select=SELECT_GRAVE, q_init=QINIT_INFINITY, grave_threshold=thr, rave_schedule=sched, rave_param=param,
+                      seed=13) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, select=2, q_init=1, seed=13,
+                                     threads=o.host_threads(), grave_threshold=thr, rave_schedule=sched, rave_param=param)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    assert (got.children["visits"] > 0).sum() > 3  # the AMAF term actually spreads the search
+
+
 def test_flat_monte_carlo_one_batch():
     from mcts_b200.search import flat_monte_carlo
 
