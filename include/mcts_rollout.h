@@ -277,7 +277,8 @@ int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, uint
 
 /* Integer-issue micro-benchmark used as the roofline denominator (DESIGN.md "Roofline"): runs a
  * dependent-chain kernel of `kind` (0 = LOP3, 1 = IADD3, 2 = SHF, 3 = IMAD, 4 = POPC, 5 = LOP3+IMAD mix)
- * on every SM and returns thread-level operations per second. */
+ * on every SM and returns thread-level operations per second (further kinds: 6 = IMAD.HI, 7 = IMAD.WIDE + LOP3,
+ * 8 = SHF by immediate, 9 = ISETP + SEL pair, each counted as one operation per chain step). */
 int mr_measure_int_peak(mr_ctx *ctx, int device_index, int kind, double *ops_per_second, double *sm_clock_mhz);
 
 #ifdef __cplusplus

@@ -20,6 +20,10 @@ namespace mr {
 
 __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 
+// a | b for disjoint a, b and a & ~b for b a subset of a, as carry-free 32-bit adds / subs (both integer pipes)
+__device__ __forceinline__ uint64_t add_disjoint(uint64_t a, uint64_t b) { return mk64(lo32(a) + lo32(b), hi32(a) + hi32(b)); }
+__device__ __forceinline__ uint64_t sub_subset(uint64_t a, uint64_t b) { return mk64(lo32(a) - lo32(b), hi32(a) - hi32(b)); }
+
 // Position of the idx-th (0-based) set bit of a 32-bit word, by binary search on popcounts.
 __device__ __forceinline__ uint32_t select32(uint32_t w, uint32_t idx) {
     uint32_t pos = 0;
@@ -81,16 +85,19 @@ struct Connect4 {
         return out;
     }
 
+    // four in a row through LEFT shifts: the low word of a 64-bit left shift is a multiply (IMAD.SHL, FMA pipe),
+    // only the high word needs a funnel shift (ALU pipe) -- half the ALU work of right shifts, and the ALU pipe
+    // is what bounds this kernel.  Spare rows 6-7 of every column byte (and byte 7) are zero, so nothing wraps.
     __device__ static bool four(uint64_t me) {
         uint64_t m, acc;
-        m = me & (me >> 1);
-        acc = m & (m >> 2);
-        m = me & (me >> 8);
-        acc |= m & (m >> 16);
-        m = me & (me >> 7);
-        acc |= m & (m >> 14);
-        m = me & (me >> 9);
-        acc |= m & (m >> 18);
+        m = me & (me << 1);
+        acc = m & (m << 2);
+        m = me & (me << 8);
+        acc |= m & (m << 16);
+        m = me & (me << 7);
+        acc |= m & (m << 14);
+        m = me & (me << 9);
+        acc |= m & (m << 18);
         return acc != 0;
     }
 
@@ -166,10 +173,12 @@ struct Connect4 {
         }
         action = (uint32_t)(__ffsll((long long)bit) - 1) >> 3; // column
         slot = action;
-        all |= bit;
-        const uint64_t me = cur | bit;
+        // `bit` is an empty cell: OR == ADD and, below, XOR with a subset == SUB, word by word without carries.
+        // Adds issue on both integer pipes, LOP3 only on the (saturated) ALU pipe.
+        all = add_disjoint(all, bit);
+        const uint64_t me = add_disjoint(cur, bit);
         n_open -= (bit & TOPROW) ? 1u : 0u;
-        cur = all ^ me; // the opponent moves next
+        cur = sub_subset(all, me); // the opponent moves next
         const uint32_t mover = (sh.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
         if (four(me)) return ST_MOVED | (mover ? ST_WIN_P1 : ST_WIN_P0);
         if (n_open == 0) return ST_MOVED | ST_DRAW;
@@ -242,12 +251,13 @@ struct ThroughBase {
     // own/opp update for a move src -> dst by `white`; returns true when the far wall is reached
     __device__ bool apply_move(bool is_white, uint32_t src, uint32_t dst) {
         const uint64_t s = bit64(src), d = bit64(dst);
+        // src holds an own piece, dst does not: (own | d) & ~s == own + d - s, carry-free per 32-bit word
         if (is_white) {
-            white = (white | d) & ~s;
+            white = sub_subset(add_disjoint(white, d), s);
             black &= ~d;
             return dst >= 56;
         } else {
-            black = (black | d) & ~s;
+            black = sub_subset(add_disjoint(black, d), s);
             white &= ~d;
             return dst < 8;
         }

@@ -11,7 +11,7 @@
 
 namespace mr {
 
-constexpr int INT_PEAK_KINDS = 6;
+constexpr int INT_PEAK_KINDS = 10;
 constexpr int INT_PEAK_CHAINS = 8;
 constexpr int INT_PEAK_UNROLL = 8;
 constexpr int INT_PEAK_OPS_PER_ITER = INT_PEAK_CHAINS * INT_PEAK_UNROLL;
@@ -23,6 +23,16 @@ __device__ __forceinline__ void int_op(uint32_t &x, uint32_t a, uint32_t b, int 
     if (KIND == 2) asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
     if (KIND == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
     if (KIND == 4) asm volatile("popc.b32 %0, %0;" : "+r"(x));
+    if (KIND == 6) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+    if (KIND == 7) { // 64-bit product of two 32-bit values (IMAD.WIDE), folded back to 32 bits with one xor
+        unsigned long long w;
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x), "r"(a));
+        x = (uint32_t)w ^ (uint32_t)(w >> 32);
+    }
+    if (KIND == 8) asm volatile("shf.r.wrap.b32 %0, %0, %1, 7;" : "+r"(x) : "r"(a)); // funnel shift by an immediate
+    if (KIND == 9) { // compare + select pair (ISETP + SEL)
+        asm volatile("{ .reg .pred q; setp.lt.u32 q, %0, %1; selp.u32 %0, %2, %0, q; }" : "+r"(x) : "r"(a), "r"(b));
+    }
     if (KIND == 5) { // alternate ALU-pipe and FMA-pipe instructions
         if (u & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
         else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(a), "r"(b));
@@ -55,7 +65,11 @@ inline void launch_int_peak(int kind, int blocks, int threads, int iters, uint32
     case 2: int_peak_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); break;
     case 3: int_peak_kernel<3><<<blocks, threads, 0, s>>>(iters, sink); break;
     case 4: int_peak_kernel<4><<<blocks, threads, 0, s>>>(iters, sink); break;
-    default: int_peak_kernel<5><<<blocks, threads, 0, s>>>(iters, sink); break;
+    case 5: int_peak_kernel<5><<<blocks, threads, 0, s>>>(iters, sink); break;
+    case 6: int_peak_kernel<6><<<blocks, threads, 0, s>>>(iters, sink); break;
+    case 7: int_peak_kernel<7><<<blocks, threads, 0, s>>>(iters, sink); break;
+    case 8: int_peak_kernel<8><<<blocks, threads, 0, s>>>(iters, sink); break;
+    default: int_peak_kernel<9><<<blocks, threads, 0, s>>>(iters, sink); break;
     }
 }
 

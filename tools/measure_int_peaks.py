@@ -8,7 +8,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import mcts_b200 as mb
 
-KINDS = ["lop3", "iadd3", "shf", "imad", "popc", "lop3+imad"]
+KINDS = ["lop3", "iadd3", "shf", "imad", "popc", "lop3+imad", "imad.hi", "imad.wide+lop3", "shf.imm", "isetp+sel"]
 out = {}
 with mb.GpuRollout(mb.Game.CONNECT4) as g:
     for i, name in enumerate(KINDS):
