@@ -435,20 +435,27 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
                 const uint32_t pk = r & 15u;
                 const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
                 uint32_t best_j = 0xffffffffu;
+                // cell by cell (the tied actions are mostly the winning moves of ONE piece): the prefix count of the
+                // cell is shared by its kinds
+                for (uint64_t cells = cand[0] | cand[1] | cand[2]; cells; cells &= cells - 1) {
+                    const uint32_t s = (uint32_t)__ffsll((long long)cells) - 1u;
+                    const uint64_t below = (1ull << s) - 1ull;
+                    uint32_t i = __popcll(S & below) + 2u * __popcll(C & below);
+                    const uint32_t legal = (uint32_t)((W >> s) & 1ull) | ((uint32_t)((F >> s) & 1ull) << 1) |
+                                           ((uint32_t)((E >> s) & 1ull) << 2);
+                    const uint32_t tied = (uint32_t)((cand[0] >> s) & 1ull) | ((uint32_t)((cand[1] >> s) & 1ull) << 1) |
+                                          ((uint32_t)((cand[2] >> s) & 1ull) << 2);
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    for (uint64_t x = cand[q]; x; x &= x - 1) {
-                        const uint32_t s = (uint32_t)__ffsll((long long)x) - 1u;
-                        const uint64_t below = (1ull << s) - 1ull;
-                        uint32_t i = __popcll(S & below) + 2u * __popcll(C & below);
-                        if (q >= 1) i += (uint32_t)((W >> s) & 1ull);
-                        if (q >= 2) i += (uint32_t)((F >> s) & 1ull);
-                        const uint32_t j = visiting_rank(i, i0, n, inv, rcp);
-                        if (j < best_j) {
-                            best_j = j;
-                            src = s;
-                            dir = q;
+                    for (int q = 0; q < 3; ++q) {
+                        if ((tied >> q) & 1u) {
+                            const uint32_t j = visiting_rank(i, i0, n, inv, rcp);
+                            if (j < best_j) {
+                                best_j = j;
+                                src = s;
+                                dir = q;
+                            }
                         }
+                        i += (legal >> q) & 1u;
                     }
                 }
                 have = true;
