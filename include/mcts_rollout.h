@@ -223,7 +223,9 @@ enum mr_qinit { MR_QINIT_PARENT = 0, MR_QINIT_INFINITY = 1 };     /* node.rs:95-
  * table reuses that node (search/shared.rs:412-436, table.rs); statistics stay on the edges.  The table is
  * keyed by the full 40-byte state record (exact, no Zobrist collisions); symmetry canonicalisation is not
  * applied. */
-enum mr_search_flags { MR_SEARCH_TRANSPOSITIONS = 1 };
+/* MR_SEARCH_PIPELINED: double-buffered driver over the two ABI slots -- batch N+1 is gathered (with batch N's
+ * virtual losses still in place) and submitted before batch N's results are applied. */
+enum mr_search_flags { MR_SEARCH_TRANSPOSITIONS = 1, MR_SEARCH_PIPELINED = 2 };
 
 typedef struct {
     uint32_t game;              /* mr_game */

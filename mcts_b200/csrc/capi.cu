@@ -90,7 +90,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     SlotDev slot[MR_NUM_SLOTS];
     int mast_game = -1; // game of the MAST snapshot held in ctx->mast_*
-    DevBuf<uint16_t> scratch;
+    DevBuf<uint16_t> scratch[MR_NUM_SLOTS + 1]; // per slot (+1 for mr_launch_device): launches may overlap across streams
     unsigned long long *d_counter_ext = nullptr; // work counter for mr_launch_device
 };
 
@@ -369,7 +369,7 @@ void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, co
 }
 
 int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const LaunchPlan &lp, cudaStream_t stream,
-              unsigned long long *d_counter) {
+              unsigned long long *d_counter, int scratch_slot) {
     const uint64_t work = kp.g_end - kp.g_begin;
     if (work == 0) return MR_OK;
     uint32_t blocks = (uint32_t)dv.num_sms * lp.blocks_per_sm;
@@ -390,8 +390,8 @@ int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const Lau
     if (kp.grab_max < kp.grab_min) kp.grab_max = kp.grab_min;
     if (kp.trace_cap) {
         const size_t need = (size_t)blocks * WARPS_PER_BLOCK * kp.trace_cap * 32u;
-        CUDA_TRY(ctx, dv.scratch.reserve(need, false));
-        kp.trace_scratch = dv.scratch.d;
+        CUDA_TRY(ctx, dv.scratch[scratch_slot].reserve(need, false));
+        kp.trace_scratch = dv.scratch[scratch_slot].d;
     }
     kp.work_counter = d_counter;
     CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
@@ -482,7 +482,7 @@ void mr_destroy(mr_ctx *ctx) {
             if (sd.ev_begin) cudaEventDestroy(sd.ev_begin);
             if (sd.ev_end) cudaEventDestroy(sd.ev_end);
         }
-        dv.scratch.release();
+        for (auto &sc : dv.scratch) sc.release();
         if (dv.d_counter_ext) cudaFree(dv.d_counter_ext);
         if (dv.stream) cudaStreamDestroy(dv.stream);
     }
@@ -565,7 +565,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             kp.final_state = sd.final_state.d;
         }
         CUDA_TRY(ctx, cudaEventRecord(sd.ev_begin, dv.stream));
-        rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter);
+        rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter, slot);
         if (rc != MR_OK) return rc;
         CUDA_TRY(ctx, cudaEventRecord(sd.ev_end, dv.stream));
 
@@ -691,7 +691,7 @@ int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, c
     kp.g_begin = 0;
     kp.g_end = (uint64_t)desc->n_leaves * desc->playouts_per_leaf;
     cudaStream_t st = stream ? (cudaStream_t)stream : dv.stream;
-    return launch_on(ctx, dv, fn, kp, lp, st, dv.d_counter_ext);
+    return launch_on(ctx, dv, fn, kp, lp, st, dv.d_counter_ext, MR_NUM_SLOTS);
 }
 
 int mr_last_kernel_ms(mr_ctx *ctx, int slot, float *ms) {

@@ -393,16 +393,41 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     mr_search_stats st;
     memset(&st, 0, sizeof st);
 
-    uint32_t done = 0;
-    while (done < desc->max_iterations) {
-        const uint32_t nb = std::min(B, desc->max_iterations - done);
-        double t0 = now_s();
+    // Two buffer sets, one per ABI slot.  Synchronous mode uses set 0 only.  Pipelined mode
+    // (MR_SEARCH_PIPELINED) gathers batch N+1 while batch N is on the GPU: its descents see batch N's virtual
+    // losses but not yet its results -- the same staleness the reference's tree-parallel workers live with
+    // (search/parallel.rs:188-251), made deterministic by the fixed order gather(N+1), submit(N+1), wait(N), backprop(N).
+    const bool pipelined = (desc->flags & MR_SEARCH_PIPELINED) != 0;
+    struct BatchBuf {
+        std::vector<std::vector<PathEntry>> paths;
+        std::vector<mr_leaf> leaves;
+        std::vector<mr_leaf_result> results;
+        std::vector<mr_action_stat> delta, amaf;
+        uint32_t nb = 0;
+    } buf[2];
+    for (auto &bb : buf) {
+        bb.paths.resize(B);
+        bb.leaves.resize(B);
+        bb.results.resize(B);
+        bb.delta.resize(desc->policy == MR_EPS_MAST ? (size_t)2 * s.na : 0);
+        bb.amaf.resize(want_amaf ? (size_t)B * 2 * s.na : 0);
+    }
+    (void)paths;
+    (void)leaves;
+    (void)results;
+    (void)delta;
+    (void)amaf;
+
+    auto gather_and_submit = [&](int slot, uint32_t first, uint32_t nb) -> int {
+        BatchBuf &bb = buf[slot];
+        bb.nb = nb;
+        const double t0 = now_s();
         for (uint32_t b = 0; b < nb; ++b) {
-            s.select(done + b, paths[b]);
-            if (k > 1) s.add_path_virtual_loss(paths[b], k - 1);
-            leaves[b] = s.t.nodes[paths[b].back().node].state;
+            s.select(first + b, bb.paths[b]);
+            if (k > 1) s.add_path_virtual_loss(bb.paths[b], k - 1);
+            bb.leaves[b] = s.t.nodes[bb.paths[b].back().node].state;
         }
-        double t1 = now_s();
+        st.seconds_select += now_s() - t0;
         mr_batch_desc bd;
         memset(&bd, 0, sizeof bd);
         bd.game = desc->game;
@@ -412,28 +437,54 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         bd.max_playout_depth = desc->max_playout_depth;
         bd.flags = (desc->policy == MR_EPS_MAST ? MR_WANT_MAST_DELTA : 0) | (want_amaf ? MR_WANT_AMAF : 0);
         bd.seed = desc->seed;
-        bd.leaf_id_base = done;
+        bd.leaf_id_base = first;
         bd.epsilon = desc->epsilon;
-        int rc = mr_playout_batch(ctx, &bd, leaves.data(), s.mast.empty() ? nullptr : s.mast.data(), results.data(),
-                                  want_amaf ? amaf.data() : nullptr, delta.empty() ? nullptr : delta.data(), nullptr, nullptr,
-                                  nullptr);
+        return mr_submit(ctx, slot, &bd, bb.leaves.data(), s.mast.empty() ? nullptr : s.mast.data());
+    };
+    auto wait_and_backprop = [&](int slot) -> int {
+        BatchBuf &bb = buf[slot];
+        const double t0 = now_s();
+        int rc = mr_wait(ctx, slot, bb.results.data(), want_amaf ? bb.amaf.data() : nullptr,
+                         bb.delta.empty() ? nullptr : bb.delta.data(), nullptr, nullptr, nullptr);
         if (rc != MR_OK) return rc;
-        double t2 = now_s();
-        for (uint32_t b = 0; b < nb; ++b) {
-            s.backprop(paths[b], results[b], k, want_amaf ? amaf.data() + (size_t)b * 2 * s.na : nullptr);
-            st.playout_plies += results[b].sum_depth;
+        const double t1 = now_s();
+        for (uint32_t b = 0; b < bb.nb; ++b) {
+            s.backprop(bb.paths[b], bb.results[b], k, want_amaf ? bb.amaf.data() + (size_t)b * 2 * s.na : nullptr);
+            st.playout_plies += bb.results[b].sum_depth;
         }
-        for (size_t i = 0; i < delta.size(); ++i) { // playout-trace part of the GLOBAL write
-            s.mast[i].visits += delta[i].visits;
-            s.mast[i].score += delta[i].score;
+        for (size_t i = 0; i < bb.delta.size(); ++i) { // playout-trace part of the GLOBAL write
+            s.mast[i].visits += bb.delta[i].visits;
+            s.mast[i].score += bb.delta[i].score;
         }
-        double t3 = now_s();
-        st.seconds_select += t1 - t0;
-        st.seconds_gpu += t2 - t1;
-        st.seconds_backprop += t3 - t2;
+        st.seconds_gpu += t1 - t0;
+        st.seconds_backprop += now_s() - t1;
         st.batches += 1;
-        st.playouts += (uint64_t)nb * k;
+        st.playouts += (uint64_t)bb.nb * k;
+        return MR_OK;
+    };
+
+    uint32_t done = 0;
+    int in_flight = -1; // slot of the batch on the GPU (pipelined mode)
+    while (done < desc->max_iterations) {
+        const uint32_t nb = std::min(B, desc->max_iterations - done);
+        const int slot = pipelined ? (in_flight == 0 ? 1 : 0) : 0;
+        int rc = gather_and_submit(slot, done, nb);
+        if (rc != MR_OK) return rc;
         done += nb;
+        if (pipelined) {
+            if (in_flight >= 0) {
+                rc = wait_and_backprop(in_flight);
+                if (rc != MR_OK) return rc;
+            }
+            in_flight = slot;
+        } else {
+            rc = wait_and_backprop(slot);
+            if (rc != MR_OK) return rc;
+        }
+    }
+    if (pipelined && in_flight >= 0) {
+        int rc = wait_and_backprop(in_flight);
+        if (rc != MR_OK) return rc;
     }
 
     // final move: RobustChild over the root children with the same random-offset arg-max (core.rs:138-198)

@@ -148,6 +148,7 @@ typedef struct {
     uint32_t expand_threshold;
     uint32_t max_playout_depth;
     int threads;                /* for the playouts of one batch */
+    int pipelined;              /* batch N+1 is gathered before batch N's results are applied (deterministic order) */
     int use_transpositions;     /* SearchConfig.use_transpositions: identical states share a node (shared.rs:412-436) */
     double exploration_c;
     uint64_t eps_threshold;

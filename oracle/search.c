@@ -376,29 +376,64 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     bd.seed = c->seed;
     bd.playouts_per_leaf = k;
 
+    /* Two buffer sets: in pipelined mode batch N+1 is gathered (seeing batch N's virtual losses, not its results)
+     * before batch N is applied -- the fixed order gather(N+1), simulate(N+1), backprop(N). */
+    entry_t *paths2 = (entry_t *)malloc(sizeof(entry_t) * (size_t)B * max_path);
+    int *plen2 = (int *)malloc(sizeof(int) * B);
+    orc_leaf_result *results2 = (orc_leaf_result *)malloc(sizeof(orc_leaf_result) * B);
+    orc_action_stat *amaf2 = want_amaf ? (orc_action_stat *)malloc(sizeof(orc_action_stat) * (size_t)B * 2 * na) : NULL;
+    orc_action_stat *delta2 = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    entry_t *set_paths[2] = {paths, paths2};
+    int *set_plen[2] = {plen, plen2};
+    orc_leaf_result *set_res[2] = {results, results2};
+    orc_action_stat *set_amaf[2] = {amaf, amaf2};
+    orc_action_stat *set_delta[2] = {delta, delta2};
+    uint32_t set_nb[2] = {0, 0};
+
     uint32_t done = 0;
-    while (done < c->max_iterations) {
-        uint32_t nb = B < c->max_iterations - done ? B : c->max_iterations - done;
-        for (uint32_t b = 0; b < nb; ++b) {
-            entry_t *path = paths + (size_t)b * max_path;
-            plen[b] = select_step(&t, &cfg, done + b, path);
-            for (int i = 1; i < plen[b]; ++i) /* add_path_virtual_loss(k - 1), shared.rs:787-805 */
-                t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
-            leaves[b] = t.nodes[path[plen[b] - 1].node].state;
+    int in_flight = -1;
+    for (;;) {
+        int slot = -1;
+        if (done < c->max_iterations) {
+            /* ---- gather + simulate one batch into `slot` ---- */
+            slot = c->pipelined ? (in_flight == 0 ? 1 : 0) : 0;
+            uint32_t nb = B < c->max_iterations - done ? B : c->max_iterations - done;
+            set_nb[slot] = nb;
+            for (uint32_t b = 0; b < nb; ++b) {
+                entry_t *path = set_paths[slot] + (size_t)b * max_path;
+                set_plen[slot][b] = select_step(&t, &cfg, done + b, path);
+                for (int i = 1; i < set_plen[slot][b]; ++i) /* add_path_virtual_loss(k - 1), shared.rs:787-805 */
+                    t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
+                leaves[b] = t.nodes[path[set_plen[slot][b] - 1].node].state;
+            }
+            bd.leaf_id_base = done;
+            if (set_delta[slot]) memset(set_delta[slot], 0, sizeof(orc_action_stat) * 2 * (size_t)na);
+            if (set_amaf[slot]) memset(set_amaf[slot], 0, sizeof(orc_action_stat) * (size_t)nb * 2 * na);
+            orc_playout_batch(&bd, leaves, nb, mast, set_res[slot], set_amaf[slot], set_delta[slot], NULL, NULL, NULL,
+                              c->threads > 0 ? c->threads : 1);
+            done += nb;
         }
-        bd.leaf_id_base = done;
-        if (delta) memset(delta, 0, sizeof(orc_action_stat) * 2 * (size_t)na);
-        if (amaf) memset(amaf, 0, sizeof(orc_action_stat) * (size_t)nb * 2 * na);
-        orc_playout_batch(&bd, leaves, nb, mast, results, amaf, delta, NULL, NULL, NULL, c->threads > 0 ? c->threads : 1);
-        for (uint32_t b = 0; b < nb; ++b) {
-            const entry_t *path = paths + (size_t)b * max_path;
-            const orc_leaf_result *r = &results[b];
+        /* ---- which batch gets applied now ---- */
+        int apply;
+        if (c->pipelined) {
+            apply = in_flight;
+            in_flight = slot;
+            if (apply < 0 && slot < 0) break;
+            if (apply < 0) continue;
+        } else {
+            if (slot < 0) break;
+            apply = slot;
+        }
+        for (uint32_t b = 0; b < set_nb[apply]; ++b) {
+            const entry_t *path = set_paths[apply] + (size_t)b * max_path;
+            const int *plen_a = set_plen[apply];
+            const orc_leaf_result *r = &set_res[apply][b];
             int64_t nonzero = (int64_t)k - r->draws;
             int64_t u[2] = {(int64_t)r->wins[0] - (nonzero - r->wins[0]), (int64_t)r->wins[1] - (nonzero - r->wins[1])};
-            if (amaf) { /* update_grave for every non-root path node, leaf first (backprop.rs:619-640, 833-854) */
-                const orc_action_stat *la = amaf + (size_t)b * 2 * na;
+            if (set_amaf[apply]) { /* update_grave for every non-root path node, leaf first (backprop.rs:619-640, 833-854) */
+                const orc_action_stat *la = set_amaf[apply] + (size_t)b * 2 * na;
                 int n_below = 0;
-                for (int i = plen[b] - 1; i >= 1; --i) {
+                for (int i = plen_a[b] - 1; i >= 1; --i) {
                     gstat_t *tab = grave_find(&grave, &t.nodes[path[i].node].state, 1);
                     for (int e = 0; e < 2 * na; ++e) {
                         tab[e].visits += la[e].visits;
@@ -415,7 +450,7 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                     ++n_below;
                 }
             }
-            for (int i = plen[b] - 1; i >= 0; --i) {
+            for (int i = plen_a[b] - 1; i >= 0; --i) {
                 stats_t *s = i == 0 ? &t.root_stats : &t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
                 s->visits += k;
                 for (int p = 0; p < 2; ++p) {
@@ -436,11 +471,16 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
         }
         if (mast)
             for (int i = 0; i < 2 * na; ++i) {
-                mast[i].visits += delta[i].visits;
-                mast[i].score += delta[i].score;
+                mast[i].visits += set_delta[apply][i].visits;
+                mast[i].score += set_delta[apply][i].score;
             }
-        done += nb;
+        if (!c->pipelined && done >= c->max_iterations) break;
     }
+    free(paths2);
+    free(plen2);
+    free(results2);
+    free(amaf2);
+    free(delta2);
 
     const node_t *rootn = &t.nodes[0];
     int rc = 0;

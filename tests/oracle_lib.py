@@ -58,6 +58,7 @@ class SearchCfg(C.Structure):
         ("expand_threshold", C.c_uint32),
         ("max_playout_depth", C.c_uint32),
         ("threads", C.c_int),
+        ("pipelined", C.c_int),
         ("use_transpositions", C.c_int),
         ("exploration_c", C.c_double),
         ("eps_threshold", C.c_uint64),
@@ -232,10 +233,11 @@ def playout_batch(
 
 def search(game, root, *, iterations, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,
            max_depth=0, c=2.0 ** 0.5, eps=0.1, seed=0, threads=1, use_transpositions=False, grave_threshold=700,
-           rave_schedule=0, rave_param=1000):
+           rave_schedule=0, rave_param=1000, pipelined=False):
     """The restated reference MCTS loop with CPU playouts.  Returns (best_action, children, playout_plies)."""
     cfg = SearchCfg(game, policy, select, q_init, iterations, batch_leaves, k, expand_threshold, max_depth, threads,
-                    int(use_transpositions), c, eps_threshold(eps), seed, grave_threshold, rave_schedule, rave_param)
+                    int(pipelined), int(use_transpositions), c, eps_threshold(eps), seed, grave_threshold, rave_schedule,
+                    rave_param)
     root = np.ascontiguousarray(root, dtype=STATE_DTYPE)
     children = np.zeros(256, dtype=ROOT_CHILD_DTYPE)
     best, n, plies = C.c_uint16(), C.c_uint32(), C.c_uint64()

@@ -40,6 +40,21 @@ def test_search_root_statistics_bit_exact(game, policy, iters, batch, k, select,
     assert int(got.children["visits"].sum()) == (iters - min(batch, iters)) * k
 
 
+@pytest.mark.parametrize("game,policy,depth", [(o.CONNECT4, o.UNIFORM, 0), (o.BREAKTHROUGH, o.EPS_MAST, 200)])
+def test_pipelined_search_bit_exact(game, policy, depth):
+    """Double-buffered driver: batch N+1 gathered and submitted (slot 1) while batch N (slot 0) is in flight."""
+    strat = {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(0.1)}[policy]
+    root = o.initial_state(game)
+    iters, batch, k = 4096 + 17, 64, 8  # a ragged last batch
+    with mb.GpuSearch(mb.Game(game), strat, max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      max_playout_depth=depth, pipelined=True, seed=21) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=policy, max_depth=depth,
+                                     seed=21, threads=o.host_threads(), pipelined=True)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies and got.playouts == iters * k
+
+
 def test_search_with_transposition_table_bit_exact():
     """BASELINE.json config 4: Othello, decisive-move rollouts, transposition table on the host."""
     game, iters, batch, k = o.OTHELLO, 4096, 64, 8
