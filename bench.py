@@ -372,6 +372,25 @@ def run_gpu(args):
             except Exception as e:  # a game that fails must not hide the headline
                 per_game[w["name"]] = {"error": str(e)}
 
+    # BASELINE.json config 1 through the whole search loop: Connect4 UCT (UCB1, c = sqrt 2, expand_threshold 1),
+    # uniform rollouts, ~100k playouts for one move from the empty board, GPU rollouts behind the tree driver
+    if not args.headline_only:
+        try:
+            with mb.GpuSearch(mb.Game.CONNECT4, mb.Uniform(), max_iterations=1600, batch_leaves=64, num_rollouts_per_leaf=64,
+                              pipelined=True, seed=7, devices=[local]) as srch:
+                srch.choose_action(mb.initial_state(mb.Game.CONNECT4))
+                t0 = time.perf_counter()
+                reps = 5
+                for _ in range(reps):
+                    sr = srch.choose_action(mb.initial_state(mb.Game.CONNECT4))
+                dt = (time.perf_counter() - t0) / reps
+            per_game["connect4_uct_100k_per_move"] = {
+                "playouts_per_move": sr.playouts, "seconds_per_move": dt, "playouts_per_s": sr.playouts / dt,
+                "best_action": sr.best_action, "batch_leaves": 64, "playouts_per_leaf": 64, "pipelined": True,
+            }
+        except Exception as e:
+            per_game["connect4_uct_100k_per_move"] = {"error": str(e)}
+
     peak_ops, clock_mhz = head["int_peak"]
     achieved = head["plies_per_s"] / world * ops_per_ply(HEADLINE)
     line = {
@@ -417,6 +436,14 @@ def run_gpu(args):
             "value": pps, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{cn} leaves x {ck} playouts of the {HEADLINE['name']} workload, {threads} pthreads, {dt:.1f} s",
         }
+        if not args.headline_only:
+            # config 1 on the CPU: 100 000 UCT iterations (k = 1) from the empty Connect4 board, one thread,
+            # the reference's own "rollouts/sec/core" definition (search/core.rs:395-398)
+            t0 = time.perf_counter()
+            best, _, _ = o.search(o.CONNECT4, o.initial_state(o.CONNECT4), iterations=100000, seed=7)
+            dts = time.perf_counter() - t0
+            line["cpu_baseline"]["connect4_uct_100k_per_move"] = {
+                "rollouts_per_s_per_core": 100000 / dts, "seconds_per_move": dts, "cores": 1, "best_action": best}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
