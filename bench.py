@@ -57,6 +57,9 @@ OPS_PER_PLY = {
     "othello_decisive_win": 750.0,
     "hex11_uniform_amaf": 65.0 + 116.0 * 2.9,
 }
+# DRAM bytes per launch of the headline kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
+# `ncu --set full` capture summarised in profiles/ncu_r01_breakthrough8x8_eps_mast.txt
+NCU_TRAFFIC_BYTES = {"breakthrough8x8_eps_mast": 7739904 + 186368}
 MAST_WARMUP_K = 16  # uniform playouts per leaf that populate the MAST table before the timed steps
 MEAN_LEGAL = {1: 25.7, 2: 47.8}  # BASELINE.md section 4 (oracle-measured mean branching)
 
@@ -418,7 +421,8 @@ def run_gpu(args):
             "peak": peak_ops / 1e12,
             "unit": "Tiop/s",
             "frac": achieved / peak_ops,
-            "traffic": None,
+            "traffic": NCU_TRAFFIC_BYTES.get(HEADLINE["name"]),
+            "traffic_unit": "bytes of DRAM per launch (ncu), for the record: the kernel is not HBM-bound",
             "note": "achieved = plies/s per GPU x ops/ply of the reference's arithmetic (SURVEY 8d model v1: %.0f ops/ply); "
             "peak = LOP3 issue rate measured live on this GPU (mr_measure_int_peak); the path moves <0.01 B/ply so HBM is not the bound"
             % ops_per_ply(HEADLINE),

@@ -212,7 +212,6 @@ struct Connect4 {
 // ==========================================================================================
 struct ThroughBase {
     static constexpr int NA = 4096;
-    static constexpr int MIN_BLOCKS = 1;
     static constexpr bool MASK_AMAF = false;
     static constexpr uint64_t NOT_COL0 = 0xFEFEFEFEFEFEFEFEull;
     static constexpr uint64_t NOT_COL7 = 0x7F7F7F7F7F7F7F7Full;
@@ -266,6 +265,7 @@ struct ThroughBase {
 
 struct Breakthrough : ThroughBase {
     static constexpr bool ROLLED = false;
+    static constexpr int MIN_BLOCKS = 6; // <= 80 registers: 24 warps/SM instead of 20, +4.7% on the MAST kernel (measured)
     static constexpr int NSLOTS = 192; // src*3 + kind (W,F,E)
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
         const uint32_t src = slot / 3u, kind = slot - src * 3u;
@@ -324,6 +324,7 @@ struct Breakthrough : ThroughBase {
 //   pieces, src ascending then dst ascending, i.e. jump deltas in the order -17,-15,-10,-6,+6,+10,+15,+17.
 // ==========================================================================================
 struct Knightthrough : ThroughBase {
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr bool ROLLED = true; // the step is large (8 masks, adder tree): a rolled window fits the I-cache (+14%)
     static constexpr int NSLOTS = 512; // src*8 + kind (ascending-dst jump order)
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
