@@ -51,7 +51,7 @@ struct Connect4 {
     static constexpr int NA = 7;
     // windows unrolled: measured 6-7% faster than a rolled window for this small step (profiles/roll_compare_r01.txt)
     static constexpr bool ROLLED = false;
-    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int MIN_BLOCKS = 1; // a 64-register cap (8 blocks/SM) measured 4% slower
     static constexpr int NSLOTS = 7; // compact per-player statistic slots (== action ids here)
     static constexpr bool MASK_AMAF = false;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
@@ -324,7 +324,7 @@ struct Breakthrough : ThroughBase {
 //   pieces, src ascending then dst ascending, i.e. jump deltas in the order -17,-15,-10,-6,+6,+10,+15,+17.
 // ==========================================================================================
 struct Knightthrough : ThroughBase {
-    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int MIN_BLOCKS = 5; // <= 96 registers: +13% on the MAST kernel (measured)
     static constexpr bool ROLLED = true; // the step is large (8 masks, adder tree): a rolled window fits the I-cache (+14%)
     static constexpr int NSLOTS = 512; // src*8 + kind (ascending-dst jump order)
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {

@@ -29,7 +29,7 @@ struct HexLeafShared {
 };
 
 template <int FLAGS>
-__global__ void __launch_bounds__(THREADS_PER_BLOCK) hex_rollout_kernel(const KernelParams p) {
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% measured */) hex_rollout_kernel(const KernelParams p) {
     using H = Hex11;
     using B128 = H::B128;
     constexpr bool WANT_AMAF = (FLAGS & MR_WANT_AMAF) != 0;
