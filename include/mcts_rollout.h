@@ -65,7 +65,12 @@ enum mr_game {
 enum mr_policy {
     MR_UNIFORM = 0,     /* simulate.rs:157-216  Uniform */
     MR_EPS_MAST = 1,    /* simulate.rs:485-570 + 819-848  EpsilonGreedy<G, Mast> */
-    MR_DECISIVE_WIN = 2 /* simulate.rs:573-760  DecisiveMove<G, Uniform>, mode Win */
+    MR_DECISIVE_WIN = 2, /* simulate.rs:573-760  DecisiveMove<G, Uniform>, mode Win */
+    /* modes WinLoss and WinLossDraw (simulate.rs:645-669).  For Connect4, Breakthrough, Knightthrough and Othello
+     * a move can only end the game in the mover's favour, or as the single remaining action, so all three modes
+     * pick the same action and share one kernel (DESIGN.md "Decisive move"); Hex is not built. */
+    MR_DECISIVE_WINLOSS = 3,
+    MR_DECISIVE_WINLOSSDRAW = 4
 };
 
 enum mr_flags {

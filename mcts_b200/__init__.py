@@ -7,6 +7,7 @@ from ._lib import LEAF_DTYPE, RECORD_DTYPE, RESULT_DTYPE, STAT_DTYPE, EXPORTS, R
 from .search import GpuSearch, SearchResult
 from .rollout import (
     BatchResult,
+    DecisiveMove,
     DecisiveMoveWin,
     EndType,
     EpsilonGreedyMast,
@@ -26,7 +27,7 @@ from .rollout import (
 )
 
 __all__ = [
-    "BatchResult", "DecisiveMoveWin", "EndType", "EpsilonGreedyMast", "Game", "GpuRollout", "MastTable", "Outcome",
+    "BatchResult", "DecisiveMove", "DecisiveMoveWin", "EndType", "EpsilonGreedyMast", "Game", "GpuRollout", "MastTable", "Outcome",
     "Policy", "Trial", "Uniform", "initial_state", "make_leaf", "num_actions", "LEAF_DTYPE", "RECORD_DTYPE",
     "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load", "GpuSearch", "SearchResult", "apply",
     "generate_actions", "terminal_status",

@@ -171,6 +171,8 @@ kernel_fn pick_hex(int v) { // Hex has its own fill-then-search kernel; no MAST 
 }
 
 kernel_fn pick_kernel(int game, int policy, int v) {
+    // WinLoss / WinLossDraw pick exactly what Win picks in the four games that have a decisive kernel
+    if (policy == MR_DECISIVE_WINLOSS || policy == MR_DECISIVE_WINLOSSDRAW) policy = MR_DECISIVE_WIN;
     switch (game) {
     case MR_CONNECT4:
         if (policy == MR_UNIFORM) return pick_variant<Connect4, MR_UNIFORM>(v);

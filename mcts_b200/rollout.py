@@ -37,6 +37,8 @@ class Policy(IntEnum):
     UNIFORM = 0
     EPS_MAST = 1
     DECISIVE_WIN = 2
+    DECISIVE_WINLOSS = 3
+    DECISIVE_WINLOSSDRAW = 4
 
 
 class Outcome(IntEnum):  # TerminalStatus (mcts/src/game.rs:117-122)
@@ -135,6 +137,21 @@ class DecisiveMoveWin:
     """DecisiveMove<G, Uniform> with DecisiveMoveMode::Win (simulate.rs:573-760)."""
 
     policy = Policy.DECISIVE_WIN
+
+    def backprop_flags(self) -> int:
+        return 0
+
+
+@dataclass(frozen=True)
+class DecisiveMove:
+    """DecisiveMove<G, Uniform> with an explicit mode: "win", "win_loss" or "win_loss_draw"
+    (DecisiveMoveMode, simulate.rs:586-604; AntiDecisive is not built)."""
+
+    mode: str = "win"
+
+    @property
+    def policy(self) -> Policy:
+        return {"win": Policy.DECISIVE_WIN, "win_loss": Policy.DECISIVE_WINLOSS, "win_loss_draw": Policy.DECISIVE_WINLOSSDRAW}[self.mode]
 
     def backprop_flags(self) -> int:
         return 0

@@ -114,21 +114,30 @@ static int random_best_index(const double *score, int n, uint32_t r) {
     return best;
 }
 
-/* simulate.rs:636-687 DecisiveMove::choose, Win mode */
-static int decisive_win_choose(int game, const orc_state *state, const uint16_t *available, int n, int player) {
+/* simulate.rs:636-687 DecisiveMove::choose, modes Win / WinLoss / WinLossDraw (AntiDecisive is not restated) */
+static int decisive_choose(int game, int mode, const orc_state *state, const uint16_t *available, int n, int player) {
     int draw = -1, loser = -1;
     for (int i = 0; i < n; ++i) {
         orc_state child = *state;
         orc_apply(game, &child, available[i]);
         int st = orc_terminal_status(game, &child);
-        if (st == ORC_WINNER_P0 || st == ORC_WINNER_P1) {
-            int winner = st == ORC_WINNER_P0 ? 0 : 1;
-            if (winner == player) return i;
-            loser = i;
-        } else if (st == ORC_DRAW) {
-            draw = i;
+        if (mode == ORC_DECISIVE_WINLOSSDRAW) { /* :645-656 any terminal child */
+            if (st != ORC_NOT_TERMINAL) return i;
+        } else if (mode == ORC_DECISIVE_WINLOSS) { /* :658-669 any winner at once, else the last draw */
+            if (st == ORC_WINNER_P0 || st == ORC_WINNER_P1) return i;
+            if (st == ORC_DRAW) draw = i;
+        } else { /* Win, :671-687 */
+            if (st == ORC_WINNER_P0 || st == ORC_WINNER_P1) {
+                int winner = st == ORC_WINNER_P0 ? 0 : 1;
+                if (winner == player) return i;
+                loser = i;
+            } else if (st == ORC_DRAW) {
+                draw = i;
+            }
         }
     }
+    if (mode == ORC_DECISIVE_WINLOSSDRAW) return -1;
+    if (mode == ORC_DECISIVE_WINLOSS) return draw;
     return loser >= 0 ? loser : draw; /* loser.or(draw) */
 }
 
@@ -160,7 +169,7 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
         }
         int player = orc_player_to_move(game, &state);
         int pick = -1;
-        if (d->policy == ORC_DECISIVE_WIN) pick = decisive_win_choose(game, &state, available, n, player);
+        if (d->policy >= ORC_DECISIVE_WIN) pick = decisive_choose(game, d->policy, &state, available, n, player);
         if (pick < 0) {
             uint32_t x0;
             int greedy = 0;

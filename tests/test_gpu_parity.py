@@ -23,8 +23,21 @@ def _leaves(game, n_per=6, seed=11):
     return np.concatenate(parts)
 
 
+def _random_mast(game, seed, density=0.6):
+    rng = np.random.default_rng(seed)
+    na = o.num_actions(game)
+    mast = np.zeros((2, na), dtype=o.STAT_DTYPE)
+    visited = rng.random((2, na)) < density
+    visits = rng.integers(1, 40, size=(2, na))
+    score = (rng.integers(0, 41, size=(2, na)) * 2 - 40) * visits // 40
+    mast["visits"] = np.where(visited, visits, 0)
+    mast["score"] = np.where(visited, np.clip(score, -visits, visits), 0)
+    return mast
+
+
 def _strategy(policy, eps=0.1):
-    return {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(eps), o.DECISIVE_WIN: mb.DecisiveMoveWin()}[policy]
+    return {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(eps), o.DECISIVE_WIN: mb.DecisiveMoveWin(),
+            o.DECISIVE_WINLOSS: mb.DecisiveMove("win_loss"), o.DECISIVE_WINLOSSDRAW: mb.DecisiveMove("win_loss_draw")}[policy]
 
 
 def _compare(game, policy, leaves, k, *, seed, max_depth=0, mast=None, eps=0.1, leaf_id_base=0, amaf=False, delta=False, devices=1):
@@ -61,6 +74,18 @@ def test_uniform_playouts_bit_exact(game):
 
 
 @pytest.mark.parametrize("game", GAMES)
+def test_white_to_move_leaves(game):
+    """Leaves after an odd number of plies: the second player (White / P1) moves first in every playout."""
+    odd = {o.CONNECT4: [1, 7, 15], o.BREAKTHROUGH: [1, 11, 31], o.KNIGHTTHROUGH: [1, 9, 21], o.OTHELLO: [1, 11, 49], o.HEX11: [1, 31, 75]}[game]
+    leaves = np.concatenate([o.random_positions(game, 40 + p, p, 4) for p in odd])
+    assert (leaves["turn"] == 1).all()
+    _compare(game, o.UNIFORM, leaves, 64, seed=0xBEEF + game, amaf=game in (o.HEX11, o.CONNECT4))
+    if game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH):
+        _compare(game, o.EPS_MAST, leaves, 64, seed=3, mast=_random_mast(game, 5, 0.7), max_depth=200, delta=True)
+        _compare(game, o.DECISIVE_WIN, leaves, 64, seed=4)
+
+
+@pytest.mark.parametrize("game", GAMES)
 def test_uniform_ragged_k_and_leaf_id_base(game):
     # k not a multiple of 32, a single leaf, a non-zero leaf id base
     leaves = _leaves(game, n_per=1)[-1:]
@@ -92,18 +117,6 @@ def test_terminal_and_stuck_leaves():
     _compare(o.OTHELLO, o.UNIFORM, dp, 4, seed=3)
     must_pass = o.make_state([1 << 0, 1 << 63], turn=0, flag=0)
     _compare(o.OTHELLO, o.UNIFORM, must_pass, 4, seed=3)
-
-
-def _random_mast(game, seed, density=0.6):
-    rng = np.random.default_rng(seed)
-    na = o.num_actions(game)
-    mast = np.zeros((2, na), dtype=o.STAT_DTYPE)
-    visited = rng.random((2, na)) < density
-    visits = rng.integers(1, 40, size=(2, na))
-    score = (rng.integers(0, 41, size=(2, na)) * 2 - 40) * visits // 40
-    mast["visits"] = np.where(visited, visits, 0)
-    mast["score"] = np.where(visited, np.clip(score, -visits, visits), 0)
-    return mast
 
 
 @pytest.mark.parametrize("game", [o.BREAKTHROUGH, o.KNIGHTTHROUGH])
@@ -141,6 +154,18 @@ def test_decisive_win_bit_exact(game):
     if game == o.OTHELLO:  # late positions, where the 64th-disc case can occur
         leaves = np.concatenate([leaves, o.random_positions(game, 5, 56, 8)])
     _compare(game, o.DECISIVE_WIN, leaves, 64, seed=17)
+
+
+@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH])
+@pytest.mark.parametrize("mode", [o.DECISIVE_WINLOSS, o.DECISIVE_WINLOSSDRAW])
+def test_decisive_other_modes_bit_exact(game, mode):
+    """WinLoss / WinLossDraw restated literally in the oracle; the product routes them to the Win kernel."""
+    leaves = _leaves(game, n_per=3)
+    if game == o.OTHELLO:
+        leaves = np.concatenate([leaves, o.random_positions(game, 6, 57, 8)])
+    if game == o.CONNECT4:  # nearly full boards: the drawing last stone
+        leaves = np.concatenate([leaves, o.random_positions(game, 7, 38, 8)])
+    _compare(game, mode, leaves, 48, seed=23)
 
 
 def test_reference_shaped_playout_call():
