@@ -192,16 +192,18 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                 __syncwarp();
 
                 // ---- 2. who: the position at ply D decides the winner ----
+                // On a full board exactly one player connects (Hex has no draws), so when P0 does not, P1 does and
+                // its flood can be skipped; a depth-cut position needs both tests.
                 int winner = -1;
-                B128 conn_d = H::zero();
-#pragma unroll
-                for (int pl = 0; pl < 2; ++pl) {
-                    if (winner < 0) {
-                        const B128 c = H::flood(H::bor(sh.conn[pl], H::first_edge(pl)), full[pl], NC0, NC10, BM);
-                        if (H::any(H::band(c, H::second_edge(pl)))) {
-                            winner = pl;
-                            conn_d = c;
-                        }
+                {
+                    const B128 c0 = H::flood(H::bor(sh.conn[0], H::first_edge(0)), full[0], NC0, NC10, BM);
+                    if (H::any(H::band(c0, H::second_edge(0)))) {
+                        winner = 0;
+                    } else if (D == E) {
+                        winner = 1;
+                    } else {
+                        const B128 c1 = H::flood(H::bor(sh.conn[1], H::first_edge(1)), full[1], NC0, NC10, BM);
+                        if (H::any(H::band(c1, H::second_edge(1)))) winner = 1;
                     }
                 }
 
@@ -245,7 +247,6 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                         }
                     }
                 }
-                (void)conn_d;
 
                 // ---- 4. results ----
                 const bool cut = winner < 0 && D < E; // no winner within max_playout_depth plies

@@ -160,13 +160,15 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
             for (;;) {
                 uint32_t r[4];
                 philox4x32_10(leaf_id, pid, win, POLICY == MR_EPS_MAST ? 1u : 0u, p.seed_lo, p.seed_hi, r);
+                // the depth cutoff can only fire in a window that reaches max_depth: one test per window, not per ply
+                const bool near_cutoff = depth + (uint32_t)WINDOW > p.max_depth || p.max_depth < (uint32_t)WINDOW;
                 // one ply.  PAR is the ply's parity inside the window: a compile-time 0/1 when the window is
                 // unrolled (the mover's colour = leaf turn ^ PAR is then fixed per call site), or 2 = "run-time,
                 // read st.rt_parity" for games whose window runs as a loop
                 auto ply = [&](auto PAR, const uint32_t x0, const uint32_t x1) {
                     constexpr int par = decltype(PAR)::value;
                     if (alive) {
-                        if (depth >= p.max_depth) { // simulate.rs:104-108 TurnLimit
+                        if (near_cutoff && depth >= p.max_depth) { // simulate.rs:104-108 TurnLimit
                             alive = false;
                             cutoff = true;
                             end_code = ST_DRAW;
