@@ -230,6 +230,26 @@ def test_full_size_properties(game):
         assert ref["results"][0].tobytes() == res[i].tobytes(), (o.GAME_NAMES[game], i)
 
 
+def test_headline_workload_at_full_size():
+    """BASELINE.json configs[1] at its bench size (4096 leaves x 4096 playouts, epsilon-MAST, depth 200): conservation
+    properties over the whole batch, the MAST delta's checksum, and bit-exact replay of sampled leaves by the oracle."""
+    game, n, k, depth = o.BREAKTHROUGH, 4096, 4096, 200
+    leaves = o.random_positions(game, 2, 20, n)
+    mast = o.playout_batch(game, leaves, 16, seed=999, max_depth=depth, want_mast_delta=True, threads=o.host_threads())["mast_delta"]
+    with mb.GpuRollout(mb.Game.BREAKTHROUGH, mb.EpsilonGreedyMast(0.1), seed=31337, max_playout_depth=depth) as g:
+        r = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, stats=mast, want_mast_delta=True)
+    res = r.results
+    assert ((res["wins"][:, 0].astype(np.int64) + res["wins"][:, 1] + res["draws"]) == k).all()
+    # every ply is one (action, player) occurrence; every decided playout scores +1 for the winner's plies, -1 for the loser's
+    assert int(r.mast_delta["visits"].sum()) == int(res["sum_depth"].sum())
+    assert abs(int(r.mast_delta["score"].sum())) <= int(res["sum_depth"].sum())
+    sample = np.random.default_rng(1).choice(n, size=4, replace=False)
+    for i in sample:
+        ref = o.playout_batch(game, leaves[i : i + 1], k, policy=o.EPS_MAST, eps=0.1, max_depth=depth, seed=31337, leaf_id_base=int(i),
+                              mast=mast, threads=o.host_threads())
+        assert ref["results"][0].tobytes() == res[i].tobytes(), i
+
+
 def test_win_rate_agrees_with_independent_cpu_rollouts():
     """Root-child win rates from GPU playouts vs CPU oracle playouts drawn with a DIFFERENT seed agree
     within a Wilson 99.9% interval (mcts-bench/src/tournament.rs:98-111)."""
