@@ -694,27 +694,31 @@ struct Othello {
     // othello/lib.rs:132-180.  An opponent disc on column 0 or 7 can never be outflanked along a row or a
     // diagonal, so those axes flood through `O & INNER` and need no wrap masks on the final step.
     static constexpr uint64_t INNER = 0x7E7E7E7E7E7E7E7Eull;
-    __device__ static uint64_t legal_moves(uint64_t P, uint64_t O) {
+    // The four "toward lower bits" directions are run as LEFT-shift rays on the bit-reversed boards (bit i <-> 63-i
+    // maps a right shift by s onto a left shift by s, and keeps the INNER column mask).  Left shifts put their low
+    // word on the FMA pipe (IMAD.SHL); right shifts are two ALU funnel shifts, and the ALU pipe is 95% busy here.
+    __device__ static uint64_t brev64(uint64_t v) { return mk64(__brev(hi32(v)), __brev(lo32(v))); }
+    __device__ static uint64_t moves_left(uint64_t P, uint64_t O) { // the four left-shift directions
         const uint64_t mO = O & INNER;
-        uint64_t m = sh<8, true>(ray<8, true>(P, O)) | sh<8, false>(ray<8, false>(P, O));
-        m |= sh<1, true>(ray<1, true>(P, mO)) | sh<1, false>(ray<1, false>(P, mO));
-        m |= sh<9, true>(ray<9, true>(P, mO)) | sh<9, false>(ray<9, false>(P, mO));
-        m |= sh<7, true>(ray<7, true>(P, mO)) | sh<7, false>(ray<7, false>(P, mO));
+        return sh<8, true>(ray<8, true>(P, O)) | sh<1, true>(ray<1, true>(P, mO)) | sh<9, true>(ray<9, true>(P, mO)) |
+               sh<7, true>(ray<7, true>(P, mO));
+    }
+    __device__ static uint64_t legal_moves(uint64_t P, uint64_t O) {
+        const uint64_t m = moves_left(P, O) | brev64(moves_left(brev64(P), brev64(O)));
         return m & ~(P | O);
     }
     // othello/lib.rs:188-234: a direction flips its run iff the cell after the run holds an own disc
-    template <int S, bool L>
+    template <int S>
     __device__ static uint64_t flips_dir(uint64_t mv, uint64_t P, uint64_t om) {
-        const uint64_t f = ray<S, L>(mv, om);
-        return (sh<S, L>(f) & P) ? f : 0ull;
+        const uint64_t f = ray<S, true>(mv, om);
+        return (sh<S, true>(f) & P) ? f : 0ull;
+    }
+    __device__ static uint64_t flips_left(uint64_t mv, uint64_t P, uint64_t O) {
+        const uint64_t mO = O & INNER;
+        return flips_dir<8>(mv, P, O) | flips_dir<1>(mv, P, mO) | flips_dir<9>(mv, P, mO) | flips_dir<7>(mv, P, mO);
     }
     __device__ static uint64_t flips(uint64_t mv, uint64_t P, uint64_t O) {
-        const uint64_t mO = O & INNER;
-        uint64_t f = flips_dir<8, true>(mv, P, O) | flips_dir<8, false>(mv, P, O);
-        f |= flips_dir<1, true>(mv, P, mO) | flips_dir<1, false>(mv, P, mO);
-        f |= flips_dir<9, true>(mv, P, mO) | flips_dir<9, false>(mv, P, mO);
-        f |= flips_dir<7, true>(mv, P, mO) | flips_dir<7, false>(mv, P, mO);
-        return f;
+        return flips_left(mv, P, O) | brev64(flips_left(brev64(mv), brev64(P), brev64(O)));
     }
     __device__ static int count_outcome(uint64_t b, uint64_t w) {
         const int nb = __popcll(b), nw = __popcll(w);
