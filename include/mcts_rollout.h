@@ -219,8 +219,11 @@ int mr_comm_allreduce_i32(mr_ctx *ctx, void *d_buf, size_t n, void *stream);
 enum mr_select {
     MR_SELECT_UCB1 = 0,       /* select/ucb.rs:9-62 */
     MR_SELECT_UCB1_TUNED = 1, /* select/ucb.rs:64-146 */
-    MR_SELECT_GRAVE = 2       /* select/rave.rs:118-238 Rave{threshold, schedule, RaveUcb::Ucb1}: reads the AMAF/GRAVE
+    MR_SELECT_GRAVE = 2,      /* select/rave.rs:118-238 Rave{threshold, schedule, RaveUcb::Ucb1}: reads the AMAF/GRAVE
                                  tables the kernels accumulate (threshold 0 = RAVE, huge = HRAVE) */
+    MR_SELECT_AMAF = 3        /* select/amaf.rs:48-86 alpha * amaf + (1 - alpha) * ucb1 over per-edge AMAF statistics
+                                 (node.rs:711-719), written by update_amaf (backprop.rs:565-617) from the same
+                                 per-leaf occurrence tables */
 };
 enum mr_rave_schedule { MR_RAVE_HAND_SELECTED = 0, MR_RAVE_THRESHOLD = 1 }; /* select/rave.rs:42-76 */
 enum mr_qinit { MR_QINIT_PARENT = 0, MR_QINIT_INFINITY = 1 };     /* node.rs:95-159 */
@@ -250,6 +253,7 @@ typedef struct {
     uint32_t rave_schedule;     /* mr_rave_schedule */
     uint32_t rave_param;        /* HandSelected k (default 1000) / Threshold rave */
     uint32_t pad;
+    double amaf_alpha;          /* MR_SELECT_AMAF: 1 = pure AMAF (the reference default), 0 = UCB1 */
 } mr_search_desc;
 
 typedef struct {

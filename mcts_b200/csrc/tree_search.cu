@@ -7,6 +7,7 @@
 //   leaf fan-out ....... num_rollouts_per_leaf with k-1 extra virtual loss, search_impl.rs:101-113, shared.rs:787-805
 //   backprop ........... backprop.rs:704-731 with ChildArray::update / NodeStats::update (node.rs:295-302,673-681)
 //                        summed over the k trials of a leaf (exact: utilities are +1 / 0 / -1)
+//   AMAF ............... select/amaf.rs:48-86 over per-edge AMAF rows written by update_amaf, backprop.rs:565-617
 //   MAST table ......... TreeStats.player_actions, written for playout trace AND tree path (backprop.rs:833-870)
 //   final move ......... RobustChild: (visits, expected score) lexicographic max, select/basic.rs:13-45
 // The tree (arena, edge statistics in the parent's child arrays, root_stats) stays on the host; only the
@@ -45,6 +46,8 @@ inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a
 struct Stats { // NodeStats / one ChildArray row
     uint32_t visits = 0, vloss = 0;
     int64_t score[2] = {0, 0}, sumsq[2] = {0, 0};
+    uint32_t amaf_visits = 0; // ChildArray amaf rows (node.rs:392-396,711-719): every player's count moves together
+    int64_t amaf_score[2] = {0, 0};
 };
 // node.rs:126-133
 inline double expected_score(const Stats &s, int player) {
@@ -199,7 +202,8 @@ struct Search {
         else q_unvisited = cur.visits == 0 ? 10000.0 : expected_score(cur, player);
         double unvisited_value;
         if (d->select == MR_SELECT_UCB1_TUNED) unvisited_value = q_unvisited + (parent_log * std::min(1.0, 1.0) + c * std::sqrt(parent_log));
-        else if (d->select == MR_SELECT_GRAVE) unvisited_value = q_unvisited; // rave.rs:226-230: no exploration term
+        else if (d->select == MR_SELECT_GRAVE || d->select == MR_SELECT_AMAF)
+            unvisited_value = q_unvisited; // rave.rs:226-230, amaf.rs:76-79: no exploration term
         else unvisited_value = q_unvisited + c * std::sqrt(parent_log);
 
         const uint32_t n = node.n_children;
@@ -236,6 +240,11 @@ struct Search {
                     const double b = rave_beta(n_tot, amaf_n);
                     const double amaf = amaf_n == 0 ? 0.0 : amaf_q / (double)amaf_n;
                     score = (1.0 - b) * exploit + b * amaf + explore;
+                } else if (d->select == MR_SELECT_AMAF) { // amaf.rs:58-74
+                    const double amaf_n = (double)std::max<uint32_t>(1u, e.amaf_visits);
+                    const double amaf = (double)e.amaf_score[player] / amaf_n;
+                    const double ucb1 = exploit + c * std::sqrt(parent_log / total);
+                    score = d->amaf_alpha * amaf + (1.0 - d->amaf_alpha) * ucb1;
                 } else {
                     score = exploit + c * std::sqrt(parent_log / total);
                 }
@@ -320,11 +329,41 @@ struct Search {
         }
     }
 
+    // update_amaf (backprop.rs:565-617) for the k trials of one leaf: at every non-root path node X with parent P,
+    // each occurrence of (action, P's mover) in [playout trace + the path's edges BELOW X] whose action is one of
+    // P's created children adds one AMAF visit and the trial's utilities to that child's row.  The playout part
+    // arrives pre-summed per (player, action) from the kernel; utilities are +1/-1/0, so the other player's sum
+    // is the negation of the mover's.
+    void backprop_amaf(const std::vector<PathEntry> &path, const mr_action_stat *amaf, const int64_t u[2], uint32_t k) {
+        std::vector<std::pair<uint32_t, int>> below;
+        for (size_t i = path.size(); i-- > 1;) {
+            const Node &parent = t.nodes[path[i - 1].node];
+            const int mover = parent.player;
+            for (uint32_t j = 0; j < parent.n_children; ++j) {
+                if (t.child[parent.first + j] < 0) continue;
+                const uint32_t a = (uint32_t)mr_host::action_id(t.game, t.action[parent.first + j]);
+                uint32_t cnt = amaf[(size_t)mover * na + a].visits;
+                int64_t sc = amaf[(size_t)mover * na + a].score;
+                for (const auto &b : below)
+                    if (b.second == mover && b.first == a) {
+                        cnt += k;
+                        sc += u[mover];
+                    }
+                Stats &e = t.edge[parent.first + j];
+                e.amaf_visits += cnt;
+                e.amaf_score[mover] += sc;
+                e.amaf_score[1 - mover] -= sc;
+            }
+            below.emplace_back((uint32_t)mr_host::action_id(t.game, t.action[parent.first + path[i].idx]), mover);
+        }
+    }
+
     // k trials of one leaf, aggregated
     void backprop(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k, const mr_action_stat *amaf) {
         const int64_t nonzero = (int64_t)k - r.draws;
         const int64_t u[2] = {(int64_t)r.wins[0] - (nonzero - r.wins[0]), (int64_t)r.wins[1] - (nonzero - r.wins[1])};
-        if (amaf) backprop_grave(path, amaf, u, k);
+        if (amaf && d->select == MR_SELECT_GRAVE) backprop_grave(path, amaf, u, k);
+        if (amaf && d->select == MR_SELECT_AMAF) backprop_amaf(path, amaf, u, k);
         for (size_t i = path.size(); i-- > 0;) {
             Stats &s = i == 0 ? t.root_stats : t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
             s.visits += k;
@@ -372,6 +411,7 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     if (!ctx || !desc || !root || !best_action) return MR_ERR_INVALID;
     if (desc->game >= MR_NUM_GAMES || desc->batch_leaves == 0 || desc->playouts_per_leaf == 0 || desc->max_iterations == 0)
         return MR_ERR_INVALID;
+    if (desc->select > MR_SELECT_AMAF) return MR_ERR_INVALID;
     Search s;
     s.ctx = ctx;
     s.d = desc;
@@ -388,7 +428,7 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     std::vector<mr_leaf> leaves(B);
     std::vector<mr_leaf_result> results(B);
     std::vector<mr_action_stat> delta(desc->policy == MR_EPS_MAST ? (size_t)2 * s.na : 0);
-    const bool want_amaf = desc->select == MR_SELECT_GRAVE;
+    const bool want_amaf = desc->select == MR_SELECT_GRAVE || desc->select == MR_SELECT_AMAF;
     std::vector<mr_action_stat> amaf(want_amaf ? (size_t)B * 2 * s.na : 0);
     mr_search_stats st;
     memset(&st, 0, sizeof st);

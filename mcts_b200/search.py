@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import LEAF_DTYPE, MAX_ROOT_CHILDREN, ROOT_CHILD_DTYPE, SearchDesc, SearchStats, ptr
 from .rollout import Game, GpuRollout, Uniform
 
-SELECT_UCB1, SELECT_UCB1_TUNED, SELECT_GRAVE = 0, 1, 2
+SELECT_UCB1, SELECT_UCB1_TUNED, SELECT_GRAVE, SELECT_AMAF = 0, 1, 2, 3
 RAVE_HAND_SELECTED, RAVE_THRESHOLD = 0, 1
 QINIT_PARENT, QINIT_INFINITY = 0, 1
 
@@ -42,13 +42,13 @@ class GpuSearch:
     def __init__(self, game: Game, strategy=None, *, max_iterations=10_000, batch_leaves=256, num_rollouts_per_leaf=1,
                  expand_threshold=1, max_playout_depth=0, exploration_constant=math.sqrt(2.0), select=SELECT_UCB1,
                  q_init=QINIT_PARENT, use_transpositions=False, pipelined=False, grave_threshold=700, rave_schedule=RAVE_HAND_SELECTED,
-                 rave_param=1000, seed=0, devices=1):
+                 rave_param=1000, amaf_alpha=1.0, seed=0, devices=1):
         self.rollout = GpuRollout(game, strategy or Uniform(), devices=devices, seed=seed, max_playout_depth=max_playout_depth)
         self.desc = SearchDesc(
             int(game), int(self.rollout.strategy.policy), select, q_init, max_iterations, batch_leaves,
             num_rollouts_per_leaf, expand_threshold, max_playout_depth, (1 if use_transpositions else 0) | (2 if pipelined else 0), exploration_constant,
             float(getattr(self.rollout.strategy, "epsilon", 0.0)), int(seed) & 0xFFFFFFFFFFFFFFFF,
-            grave_threshold, rave_schedule, rave_param, 0,
+            grave_threshold, rave_schedule, rave_param, 0, float(amaf_alpha),
         )
 
     def close(self):

@@ -140,7 +140,8 @@ int orc_stress_through(int game, uint64_t num_games, uint64_t *goal_wins, uint64
 typedef struct {
     int game;
     int policy;
-    int select;                 /* 0 UCB1, 1 UCB1-Tuned (select/ucb.rs), 2 GRAVE (select/rave.rs, RaveUcb::Ucb1) */
+    int select;                 /* 0 UCB1, 1 UCB1-Tuned (select/ucb.rs), 2 GRAVE (select/rave.rs, RaveUcb::Ucb1),
+                                   3 AMAF (select/amaf.rs) */
     int q_init;                 /* 0 Parent, 1 Infinity (node.rs:95-159) */
     uint32_t max_iterations;    /* leaf selections */
     uint32_t batch_leaves;      /* 1 = the reference's sequential loop */
@@ -156,6 +157,7 @@ typedef struct {
     uint32_t grave_threshold;   /* Rave.threshold */
     int rave_schedule;          /* 0 HandSelected{k}, 1 Threshold{rave} (rave.rs:42-76) */
     uint32_t rave_param;
+    double amaf_alpha;          /* select 3: alpha * amaf + (1 - alpha) * ucb1 (select/amaf.rs:58-74), reference default 1 */
 } orc_search_cfg;
 
 typedef struct {

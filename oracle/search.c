@@ -34,6 +34,8 @@ static const uint32_t PRIMES[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50
 typedef struct {
     uint32_t visits, vloss;
     int64_t score[2], sumsq[2];
+    uint32_t amaf_visits; /* ChildArray amaf rows, node.rs:392-396,711-719 (all players' counts move together) */
+    int64_t amaf_score[2];
 } stats_t;
 
 typedef struct {
@@ -209,7 +211,7 @@ static const stats_t *current_stats(const tree_t *t, const entry_t *path, int le
 }
 
 typedef struct {
-    int select; /* 0 UCB1, 1 UCB1-Tuned, 2 GRAVE */
+    int select; /* 0 UCB1, 1 UCB1-Tuned, 2 GRAVE, 3 AMAF */
     int q_init; /* 0 Parent, 1 Infinity */
     double c;
     uint32_t expand_threshold;
@@ -218,6 +220,7 @@ typedef struct {
     int rave_schedule;
     uint32_t rave_param;
     grave_t *grave;
+    double amaf_alpha;
 } sel_cfg;
 
 static int action_id(int game, uint16_t a);
@@ -241,7 +244,7 @@ static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *p
     double parent_log = log(fmax(1.0, (double)cur->visits)); /* ucb.rs:34-37 */
     double q_unvisited = cfg->q_init == 1 ? 10000.0 : (cur->visits == 0 ? 10000.0 : expected_score(cur, player));
     double unvisited_value = cfg->select == 1   ? q_unvisited + (parent_log * fmin(1.0, 1.0) + cfg->c * sqrt(parent_log))
-                             : cfg->select == 2 ? q_unvisited /* rave.rs:226-230 */
+                             : (cfg->select == 2 || cfg->select == 3) ? q_unvisited /* rave.rs:226-230, amaf.rs:76-79 */
                                                 : q_unvisited + cfg->c * sqrt(parent_log);
     uint32_t n = (uint32_t)node->n_children;
     uint32_t r = (uint32_t)(((uint64_t)tree_draw(cfg->seed, descent, (uint32_t)len - 1) * (16u * n)) >> 32);
@@ -283,6 +286,11 @@ static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *p
                 }
                 double amaf = amaf_n == 0 ? 0.0 : amaf_q / (double)amaf_n;
                 score = (1.0 - b) * exploit + b * amaf + explore;
+            } else if (cfg->select == 3) { /* amaf.rs:58-74 */
+                double amaf_n = (double)(e->amaf_visits > 1u ? e->amaf_visits : 1u);
+                double amaf = (double)e->amaf_score[player] / amaf_n;
+                double ucb1 = exploit + cfg->c * sqrt(parent_log / total);
+                score = cfg->amaf_alpha * amaf + (1.0 - cfg->amaf_alpha) * ucb1;
             } else { /* ucb.rs:40-52 */
                 score = exploit + cfg->c * sqrt(parent_log / total);
             }
@@ -351,8 +359,8 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     memset(&grave, 0, sizeof grave);
     grave.na = orc_num_actions(c->game);
     sel_cfg cfg = {c->select, c->q_init, c->exploration_c, c->expand_threshold, c->seed, c->grave_threshold, c->rave_schedule,
-                   c->rave_param, &grave};
-    const int want_amaf = c->select == 2;
+                   c->rave_param, &grave, c->amaf_alpha};
+    const int want_amaf = c->select == 2 || c->select == 3;
     const uint32_t B = c->batch_leaves, k = c->playouts_per_leaf;
     const int na = orc_num_actions(c->game);
     orc_action_stat *mast = c->policy == ORC_EPS_MAST ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
@@ -430,7 +438,36 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
             const orc_leaf_result *r = &set_res[apply][b];
             int64_t nonzero = (int64_t)k - r->draws;
             int64_t u[2] = {(int64_t)r->wins[0] - (nonzero - r->wins[0]), (int64_t)r->wins[1] - (nonzero - r->wins[1])};
-            if (set_amaf[apply]) { /* update_grave for every non-root path node, leaf first (backprop.rs:619-640, 833-854) */
+            if (set_amaf[apply] && c->select == 3) {
+                /* update_amaf (backprop.rs:565-617) for every non-root path node X, leaf first: occurrences of
+                 * (action, mover of X's parent) in [playout trace + path edges below X] that name a created child
+                 * of the parent add one AMAF visit and the trial's utilities to that child's row */
+                const orc_action_stat *la = set_amaf[apply] + (size_t)b * 2 * na;
+                int n_below = 0;
+                for (int i = plen_a[b] - 1; i >= 1; --i) {
+                    const node_t *parent = &t.nodes[path[i - 1].node];
+                    int mover = parent->player;
+                    for (int j = 0; j < parent->n_children; ++j) {
+                        if (t.child[parent->first + j] < 0) continue;
+                        uint32_t a = (uint32_t)action_id(c->game, t.action[parent->first + j]);
+                        uint32_t cnt = la[(size_t)mover * na + a].visits;
+                        int64_t sc = la[(size_t)mover * na + a].score;
+                        for (int q = 0; q < n_below; ++q)
+                            if (below_p[q] == mover && below_a[q] == a) {
+                                cnt += k;
+                                sc += u[mover];
+                            }
+                        stats_t *e = &t.edge[parent->first + j];
+                        e->amaf_visits += cnt;
+                        e->amaf_score[mover] += sc;
+                        e->amaf_score[1 - mover] -= sc;
+                    }
+                    below_a[n_below] = (uint32_t)action_id(c->game, t.action[parent->first + path[i].idx]);
+                    below_p[n_below] = mover;
+                    ++n_below;
+                }
+            }
+            if (set_amaf[apply] && c->select == 2) { /* update_grave for every non-root path node, leaf first (backprop.rs:619-640, 833-854) */
                 const orc_action_stat *la = set_amaf[apply] + (size_t)b * 2 * na;
                 int n_below = 0;
                 for (int i = plen_a[b] - 1; i >= 1; --i) {

@@ -93,6 +93,27 @@ def test_grave_search_bit_exact(game, iters, batch, k, thr, sched, param):
     assert (got.children["visits"] > 0).sum() > 3  # the AMAF term actually spreads the search
 
 
+@pytest.mark.parametrize("game,policy,iters,batch,k,alpha", [
+    (o.HEX11, o.UNIFORM, 2048, 32, 8, 1.0),          # strategy.rs:205-217 `Amaf`: pure AMAF (alpha 1, the default)
+    (o.CONNECT4, o.UNIFORM, 4096, 32, 4, 0.5),       # alpha blends AMAF with UCB1 (amaf.rs:70-74)
+    (o.BREAKTHROUGH, o.EPS_MAST, 2048, 64, 8, 0.7),  # strategy.rs:219-231 `AmafMast`
+    (o.OTHELLO, o.UNIFORM, 1024, 1, 1, 1.0),         # the reference's sequential loop (batch 1, k 1)
+])
+def test_amaf_search_bit_exact(game, policy, iters, batch, k, alpha):
+    from mcts_b200.search import SELECT_AMAF, QINIT_INFINITY
+
+    root = o.initial_state(game)
+    strat = mb.EpsilonGreedyMast(0.1) if policy == o.EPS_MAST else mb.Uniform()
+    with mb.GpuSearch(mb.Game(game), strat, max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      select=SELECT_AMAF, q_init=QINIT_INFINITY, amaf_alpha=alpha, max_playout_depth=200, seed=21) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=policy, select=3, q_init=1,
+                                     seed=21, threads=o.host_threads(), amaf_alpha=alpha, max_depth=200)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    assert (got.children["visits"] > 0).sum() > 3
+
+
 def test_flat_monte_carlo_one_batch():
     from mcts_b200.search import flat_monte_carlo
 
