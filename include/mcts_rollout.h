@@ -70,11 +70,15 @@ enum mr_policy {
      * a move can only end the game in the mover's favour, or as the single remaining action, so all three modes
      * pick the same action and share one kernel (DESIGN.md "Decisive move"); Hex is not built. */
     MR_DECISIVE_WINLOSS = 3,
-    MR_DECISIVE_WINLOSSDRAW = 4
+    MR_DECISIVE_WINLOSSDRAW = 4,
+    /* mode AntiDecisive (simulate.rs:689-735): an immediate win first; else the FIRST action in list order whose
+     * child is not terminal and leaves the opponent no immediately winning reply; else the inner (uniform) pick.
+     * Built for Connect4, Breakthrough, Knightthrough and Othello. */
+    MR_DECISIVE_ANTI = 5
 };
 
 enum mr_flags {
-    MR_WANT_AMAF = 1,        /* per-leaf AMAF/GRAVE occurrence table (Hex 11x11, Connect4, Othello) */
+    MR_WANT_AMAF = 1,        /* per-leaf AMAF/GRAVE occurrence table (every game) */
     MR_WANT_MAST_DELTA = 2,  /* batch-wide MAST (GLOBAL) table delta */
     MR_WANT_TRACE = 4,       /* parity/debug: per-playout move trace + record */
     MR_WANT_FINAL_STATE = 8  /* parity/debug: per-playout final state */

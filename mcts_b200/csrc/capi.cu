@@ -177,20 +177,24 @@ kernel_fn pick_kernel(int game, int policy, int v) {
     case MR_CONNECT4:
         if (policy == MR_UNIFORM) return pick_variant<Connect4, MR_UNIFORM>(v);
         if (policy == MR_DECISIVE_WIN) return pick_variant<Connect4, MR_DECISIVE_WIN>(v);
+        if (policy == MR_DECISIVE_ANTI) return pick_variant<Connect4, MR_DECISIVE_ANTI>(v);
         return nullptr;
     case MR_BREAKTHROUGH:
         if (policy == MR_UNIFORM) return pick_variant<Breakthrough, MR_UNIFORM>(v);
         if (policy == MR_EPS_MAST) return pick_variant<Breakthrough, MR_EPS_MAST>(v);
         if (policy == MR_DECISIVE_WIN) return pick_variant<Breakthrough, MR_DECISIVE_WIN>(v);
+        if (policy == MR_DECISIVE_ANTI) return pick_variant<Breakthrough, MR_DECISIVE_ANTI>(v);
         return nullptr;
     case MR_KNIGHTTHROUGH:
         if (policy == MR_UNIFORM) return pick_variant<Knightthrough, MR_UNIFORM>(v);
         if (policy == MR_EPS_MAST) return pick_variant<Knightthrough, MR_EPS_MAST>(v);
         if (policy == MR_DECISIVE_WIN) return pick_variant<Knightthrough, MR_DECISIVE_WIN>(v);
+        if (policy == MR_DECISIVE_ANTI) return pick_variant<Knightthrough, MR_DECISIVE_ANTI>(v);
         return nullptr;
     case MR_OTHELLO:
         // DecisiveMove<Win> provably never changes an Othello pick, so it shares the kernel
         if (policy == MR_UNIFORM || policy == MR_DECISIVE_WIN) return pick_variant<Othello, MR_UNIFORM>(v);
+        if (policy == MR_DECISIVE_ANTI) return pick_variant<Othello, MR_DECISIVE_ANTI>(v);
         return nullptr;
     case MR_HEX11:
         if (policy == MR_UNIFORM) return pick_hex(v);

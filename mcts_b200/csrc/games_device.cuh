@@ -101,6 +101,21 @@ struct Connect4 {
         return acc != 0;
     }
 
+    // cells where one more stone of `p` completes four in a row (occupied cells included; callers mask)
+    __device__ static uint64_t win_cells(uint64_t p) {
+        uint64_t r = (p << 1) & (p << 2) & (p << 3), pp;
+#define MR_C4_LINE(S)                        \
+    pp = (p << (S)) & (p << (2 * (S)));      \
+    r |= pp & ((p << (3 * (S))) | (p >> (S))); \
+    pp = (p >> (S)) & (p >> (2 * (S)));      \
+    r |= pp & ((p << (S)) | (p >> (3 * (S))));
+        MR_C4_LINE(8)
+        MR_C4_LINE(7)
+        MR_C4_LINE(9)
+#undef MR_C4_LINE
+        return r & BOARD;
+    }
+
     __device__ static int prepare(Shared &sh, const mr_leaf &leaf, uint32_t lane) {
         // row-major -> column-byte, cooperatively: lane L converts cells L and L + 32, then a warp OR
         uint32_t blo = 0, bhi = 0, wlo = 0, whi = 0;
@@ -155,6 +170,21 @@ struct Connect4 {
                 }
             }
             bit = winning;
+        } else if (POLICY == MR_DECISIVE_ANTI) {
+            // DecisiveMove<AntiDecisive> (simulate.rs:689-735).  Pass 1: the first column whose drop wins.
+            // Pass 2: the first column after which the opponent has no winning drop.  The opponent's winning
+            // cells W do not depend on our stone except that it fills one cell and opens the one above:
+            // with T = W & drop cells, no threat -> any drop x whose upper neighbour is not in W; one threat ->
+            // only x = T (same condition); two or more -> none.  (A board-filling drop is the single action.)
+            const uint64_t mine = win_cells(cur) & moves;
+            if (mine) {
+                bit = mine & (0 - mine);
+            } else {
+                const uint64_t W = win_cells(all ^ cur) & ~all;
+                const uint64_t T = W & moves;
+                const uint64_t cand = (T == 0 ? moves : ((T & (T - 1)) == 0 ? T : 0ull)) & ~(W >> 1);
+                bit = cand & (0 - cand);
+            }
         } else {
             bit = 0;
         }
@@ -402,7 +432,7 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
     if (n == 0) return ST_NO_ACTIONS;
     uint32_t idx = 0, src = 0, dir = 0;
     bool have = false;
-    if (POLICY == MR_DECISIVE_WIN) {
+    if (POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI) {
         // DecisiveMove<Win> (simulate.rs:662-687): the first action in list order whose child is a win for the
         // mover.  A Breakthrough move wins iff it lands on the far wall, i.e. iff its source is on the row next
         // to it; no move can lose or draw on the spot, so the loser/draw fallbacks never fire.
@@ -412,6 +442,30 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
             src = (uint32_t)__ffsll((long long)any_win) - 1u;
             dir = ((W >> src) & 1ull) ? 0u : (((F >> src) & 1ull) ? 1u : 2u);
             have = true;
+        } else if (POLICY == MR_DECISIVE_ANTI) {
+            // AntiDecisive pass 2 (simulate.rs:701-733): the first action after which the opponent cannot win at
+            // once.  An opposing piece one row from ITS goal always has a legal diagonal onto the goal row (no own
+            // piece can stand there), so the opponent can win iff such a piece survives our move: none -> the
+            // first legal action; exactly one -> the first action that captures it; more -> the inner pick.
+            const uint64_t threat = opp & (is_white ? 0x000000000000FF00ull : 0x00FF000000000000ull);
+            idx = mulhi(x0, n);
+            if (threat == 0) {
+                src = (uint32_t)__ffsll((long long)(W | F | E)) - 1u;
+                dir = ((W >> src) & 1ull) ? 0u : (((F >> src) & 1ull) ? 1u : 2u);
+                have = true;
+            } else if ((threat & (threat - 1)) == 0) {
+                // captures of cell t in list order (source ascending): Black E from t+7 then W from t+9,
+                // White E from t-9 then W from t-7
+                const int t = __ffsll((long long)threat) - 1;
+                const int s_e = is_white ? t - 9 : t + 7, s_w = is_white ? t - 7 : t + 9;
+                const bool e_ok = s_e >= 0 && s_e < 64 && ((E >> (s_e & 63)) & 1ull);
+                const bool w_ok = s_w >= 0 && s_w < 64 && ((W >> (s_w & 63)) & 1ull);
+                if (e_ok || w_ok) {
+                    src = (uint32_t)(e_ok ? s_e : s_w);
+                    dir = e_ok ? 2u : 0u;
+                    have = true;
+                }
+            }
         } else {
             idx = mulhi(x0, n);
         }
@@ -549,7 +603,7 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
 
     uint32_t idx = 0, src = 0, kind = 0;
     bool have = false;
-    if (POLICY == MR_DECISIVE_WIN) {
+    if (POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI) {
         // first action in list order that lands on the far wall (simulate.rs:662-687); a jump of two rows wins
         // from the two rows next to it, a jump of one row from the row next to it
         const uint64_t r1 = is_white ? 0x00FF000000000000ull : 0x000000000000FF00ull; // one row from the goal
@@ -570,6 +624,35 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
             for (int q = 7; q >= 0; --q)
                 if ((win[q] >> src) & 1ull) kind = q;
             have = true;
+        } else if (POLICY == MR_DECISIVE_ANTI) {
+            // AntiDecisive pass 2 (simulate.rs:701-733).  An opposing knight within two rows of ITS goal always has
+            // a legal jump onto the goal row, so the opponent can win at once iff such a knight survives our move:
+            // none -> the first legal action; exactly one -> the first action capturing it; more -> the inner pick.
+            const uint64_t opp = is_white ? black : white;
+            const uint64_t threat = opp & (is_white ? 0x0000000000FFFF00ull : 0x00FFFF0000000000ull);
+            idx = mulhi(x0, n);
+            if (threat == 0) {
+                uint64_t any = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) any |= M[q];
+                src = (uint32_t)__ffsll((long long)any) - 1u;
+#pragma unroll
+                for (int q = 7; q >= 0; --q)
+                    if ((M[q] >> src) & 1ull) kind = q;
+                have = true;
+            } else if ((threat & (threat - 1)) == 0) {
+                const int t = __ffsll((long long)threat) - 1;
+                // sources t - delta(kind); the largest delta gives the smallest source, i.e. the first in list order
+#pragma unroll
+                for (int q = 7; q >= 0; --q) {
+                    const int s0 = t - delta((uint32_t)q);
+                    if (!have && s0 >= 0 && s0 < 64 && ((M[q] >> (s0 & 63)) & 1ull)) {
+                        src = (uint32_t)s0;
+                        kind = q;
+                        have = true;
+                    }
+                }
+            }
         } else {
             idx = mulhi(x0, n);
         }
@@ -760,12 +843,47 @@ struct Othello {
         // DecisiveMove<Win> (simulate.rs:662-687) can only find a terminal child when a single action
         // exists (the 64th disc, or a PASS), so it never changes the pick: see DESIGN.md "Decisive move".
         const uint32_t n = __popcll(moves);
-        uint32_t idx = mulhi(x0, n);
-        const uint32_t nlo = __popc(lo32(moves));
-        const bool in_hi = idx >= nlo;
-        const uint32_t sq = select32(in_hi ? hi32(moves) : lo32(moves), in_hi ? idx - nlo : idx) + (in_hi ? 32u : 0u);
-        const uint64_t mv = bit64(sq);
-        const uint64_t fl = flips(mv, P, O);
+        uint32_t sq = 0;
+        uint64_t mv = 0, fl = 0;
+        bool have = false;
+        if (POLICY == MR_DECISIVE_ANTI) {
+            // DecisiveMove<AntiDecisive> (simulate.rs:689-735).  Pass 1 can only fire on the single 64th-disc action
+            // (the pick either way).  Pass 2: the first square whose child is not terminal and after which no
+            // opponent reply ends the game with a winner -- a reply ends the game only as the 64th disc, or as a
+            // PASS answered by a position where we cannot move either.
+            const uint32_t discs = __popcll(P | O);
+            for (uint64_t m = moves; m && !have; m &= m - 1) {
+                const uint64_t c_mv = m & (0 - m);
+                const uint64_t c_fl = flips(c_mv, P, O);
+                const uint64_t cP = P | c_mv | c_fl, cO = O & ~c_fl; // child: cO to move
+                if (discs == 63) break; // the child is terminal (full board): never preferred
+                const uint64_t replies = legal_moves(cO, cP);
+                bool opponent_can_win = false;
+                if (replies == 0) { // the only reply is PASS
+                    if (legal_moves(cP, cO) == 0) opponent_can_win = __popcll(cP) != __popcll(cO);
+                } else if (discs == 62) { // a reply places the 64th disc
+                    for (uint64_t r = replies; r; r &= r - 1) {
+                        const uint64_t r_mv = r & (0 - r);
+                        const uint64_t r_fl = flips(r_mv, cO, cP);
+                        if (__popcll(cO | r_mv | r_fl) != __popcll(cP & ~r_fl)) opponent_can_win = true;
+                    }
+                }
+                if (!opponent_can_win) {
+                    mv = c_mv;
+                    fl = c_fl;
+                    sq = (uint32_t)__ffsll((long long)c_mv) - 1u;
+                    have = true;
+                }
+            }
+        }
+        if (!have) {
+            uint32_t idx = mulhi(x0, n);
+            const uint32_t nlo = __popc(lo32(moves));
+            const bool in_hi = idx >= nlo;
+            sq = select32(in_hi ? hi32(moves) : lo32(moves), in_hi ? idx - nlo : idx) + (in_hi ? 32u : 0u);
+            mv = bit64(sq);
+            fl = flips(mv, P, O);
+        }
         const uint64_t nP = P | mv | fl, nO = O & ~fl;
         black = is_white ? nO : nP;
         white = is_white ? nP : nO;

@@ -39,6 +39,7 @@ class Policy(IntEnum):
     DECISIVE_WIN = 2
     DECISIVE_WINLOSS = 3
     DECISIVE_WINLOSSDRAW = 4
+    DECISIVE_ANTI = 5
 
 
 class Outcome(IntEnum):  # TerminalStatus (mcts/src/game.rs:117-122)
@@ -144,14 +145,15 @@ class DecisiveMoveWin:
 
 @dataclass(frozen=True)
 class DecisiveMove:
-    """DecisiveMove<G, Uniform> with an explicit mode: "win", "win_loss" or "win_loss_draw"
-    (DecisiveMoveMode, simulate.rs:586-604; AntiDecisive is not built)."""
+    """DecisiveMove<G, Uniform> with an explicit mode: "win", "win_loss", "win_loss_draw" or "anti_decisive"
+    (DecisiveMoveMode, simulate.rs:586-604)."""
 
     mode: str = "win"
 
     @property
     def policy(self) -> Policy:
-        return {"win": Policy.DECISIVE_WIN, "win_loss": Policy.DECISIVE_WINLOSS, "win_loss_draw": Policy.DECISIVE_WINLOSSDRAW}[self.mode]
+        return {"win": Policy.DECISIVE_WIN, "win_loss": Policy.DECISIVE_WINLOSS, "win_loss_draw": Policy.DECISIVE_WINLOSSDRAW,
+                "anti_decisive": Policy.DECISIVE_ANTI}[self.mode]
 
     def backprop_flags(self) -> int:
         return 0

@@ -114,9 +114,36 @@ static int random_best_index(const double *score, int n, uint32_t r) {
     return best;
 }
 
-/* simulate.rs:636-687 DecisiveMove::choose, modes Win / WinLoss / WinLossDraw (AntiDecisive is not restated) */
+/* simulate.rs:636-735 DecisiveMove::choose, modes Win / WinLoss / WinLossDraw / AntiDecisive */
 static int decisive_choose(int game, int mode, const orc_state *state, const uint16_t *available, int n, int player) {
     int draw = -1, loser = -1;
+    if (mode == ORC_DECISIVE_ANTI) { /* :689-735 */
+        /* pass 1: an immediate win of the mover, wherever it is in the list */
+        for (int i = 0; i < n; ++i) {
+            orc_state child = *state;
+            orc_apply(game, &child, available[i]);
+            int st = orc_terminal_status(game, &child);
+            if ((st == ORC_WINNER_P0 && player == 0) || (st == ORC_WINNER_P1 && player == 1)) return i;
+        }
+        /* pass 2: the first move with a non-terminal child that leaves the opponent no immediately winning reply
+         * (any Winner(_) among the replies counts) */
+        uint16_t replies[ORC_MAX_ACTIONS];
+        for (int i = 0; i < n; ++i) {
+            orc_state child = *state;
+            orc_apply(game, &child, available[i]);
+            if (orc_terminal_status(game, &child) != ORC_NOT_TERMINAL) continue;
+            int nr = orc_generate_actions(game, &child, replies);
+            int opponent_can_win = 0;
+            for (int j = 0; j < nr && !opponent_can_win; ++j) {
+                orc_state g = child;
+                orc_apply(game, &g, replies[j]);
+                int st = orc_terminal_status(game, &g);
+                opponent_can_win = st == ORC_WINNER_P0 || st == ORC_WINNER_P1;
+            }
+            if (!opponent_can_win) return i;
+        }
+        return -1;
+    }
     for (int i = 0; i < n; ++i) {
         orc_state child = *state;
         orc_apply(game, &child, available[i]);

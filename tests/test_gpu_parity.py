@@ -37,7 +37,8 @@ def _random_mast(game, seed, density=0.6):
 
 def _strategy(policy, eps=0.1):
     return {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(eps), o.DECISIVE_WIN: mb.DecisiveMoveWin(),
-            o.DECISIVE_WINLOSS: mb.DecisiveMove("win_loss"), o.DECISIVE_WINLOSSDRAW: mb.DecisiveMove("win_loss_draw")}[policy]
+            o.DECISIVE_WINLOSS: mb.DecisiveMove("win_loss"), o.DECISIVE_WINLOSSDRAW: mb.DecisiveMove("win_loss_draw"),
+            o.DECISIVE_ANTI: mb.DecisiveMove("anti_decisive")}[policy]
 
 
 def _compare(game, policy, leaves, k, *, seed, max_depth=0, mast=None, eps=0.1, leaf_id_base=0, amaf=False, delta=False, devices=1):
@@ -166,6 +167,29 @@ def test_decisive_other_modes_bit_exact(game, mode):
     if game == o.CONNECT4:  # nearly full boards: the drawing last stone
         leaves = np.concatenate([leaves, o.random_positions(game, 7, 38, 8)])
     _compare(game, mode, leaves, 48, seed=23)
+
+
+@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH])
+def test_anti_decisive_bit_exact(game):
+    """DecisiveMoveMode::AntiDecisive (simulate.rs:689-735): the oracle runs the reference's two literal passes
+    (apply + terminal_status per action, then per reply); the kernels use closed forms per game.  The mode takes
+    the FIRST safe action, so playouts of one leaf differ little: coverage comes from many leaves."""
+    plies = {o.CONNECT4: range(0, 40, 3), o.BREAKTHROUGH: range(0, 60, 4), o.KNIGHTTHROUGH: range(0, 40, 3),
+             o.OTHELLO: list(range(0, 56, 5)) + [56, 57, 58, 59, 60]}[game]
+    leaves = np.concatenate([o.random_positions(game, 300 + p, p, 24 if p else 1) for p in plies])
+    # (Knightthrough playouts have no depth bound of their own: statistics tables need max_playout_depth)
+    got, _ = _compare(game, o.DECISIVE_ANTI, leaves, 8, seed=31, amaf=game != o.OTHELLO, max_depth=300 if game == o.KNIGHTTHROUGH else 0)
+    r = got.results
+    assert ((r["wins"][:, 0] + r["wins"][:, 1] + r["draws"]) == 8).all()
+    # white-to-move leaves as well (odd ply counts are in the ranges above) and a depth cutoff
+    _compare(game, o.DECISIVE_ANTI, leaves[::5], 4, seed=32, max_depth=9)
+
+
+def test_anti_decisive_not_built_for_hex():
+    with mb.GpuRollout(mb.Game.HEX11, mb.DecisiveMove("anti_decisive")) as g:
+        with pytest.raises(mb.RolloutError) as e:
+            g.simulate_many(mb.initial_state(mb.Game.HEX11), 4)
+        assert "MR_ERR_UNSUPPORTED" in str(e.value)
 
 
 def test_reference_shaped_playout_call():
