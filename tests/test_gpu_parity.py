@@ -289,3 +289,34 @@ def test_win_rate_agrees_with_independent_cpu_rollouts():
         p1, p2 = got[c]["wins"][0] / k, ref[c]["wins"][0] / k
         se = np.sqrt(p1 * (1 - p1) / k + p2 * (1 - p2) / k)
         assert abs(p1 - p2) < z * se + 1e-9, (c, p1, p2)
+
+
+def test_randomized_differential_sweep():
+    """Seeded random batch shapes: game x policy x flags x (n, k) x leaf id base x depth cutoff, GPU vs oracle,
+    every playout's trace, record, final state and every aggregate compared bit for bit."""
+    rng = np.random.default_rng(20260101)
+    policies = {
+        o.CONNECT4: [o.UNIFORM, o.DECISIVE_WIN, o.DECISIVE_ANTI],
+        o.BREAKTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI],
+        o.KNIGHTTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WINLOSS, o.DECISIVE_ANTI],
+        o.OTHELLO: [o.UNIFORM, o.DECISIVE_WINLOSSDRAW, o.DECISIVE_ANTI],
+        o.HEX11: [o.UNIFORM],
+    }
+    max_plies = {o.CONNECT4: 30, o.BREAKTHROUGH: 50, o.KNIGHTTHROUGH: 30, o.OTHELLO: 56, o.HEX11: 100}
+    for case in range(40):
+        game = GAMES[case % 5]
+        policy = policies[game][int(rng.integers(len(policies[game])))]
+        n, k = int(rng.integers(1, 24)), int(rng.choice([1, 2, 7, 31, 32, 33, 64, 97]))
+        plies = int(rng.integers(0, max_plies[game]))
+        leaves = o.random_positions(game, 1000 + case, plies, n)
+        cutoff = int(rng.choice([0, 0, 5, 40]))
+        needs_bound = game == o.KNIGHTTHROUGH
+        amaf = bool(rng.integers(2))
+        delta = policy == o.EPS_MAST or (game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH) and bool(rng.integers(2)))
+        if (amaf or delta) and needs_bound and cutoff == 0:
+            cutoff = 250
+        if game == o.HEX11:
+            delta = False
+        mast = _random_mast(game, case, float(rng.random())) if policy == o.EPS_MAST else None
+        _compare(game, policy, leaves, k, seed=int(rng.integers(1 << 62)), max_depth=cutoff, mast=mast,
+                 eps=float(rng.choice([0.0, 0.1, 0.5])), leaf_id_base=int(rng.integers(1 << 20)), amaf=amaf, delta=delta)
