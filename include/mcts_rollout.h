@@ -74,7 +74,13 @@ enum mr_policy {
     /* mode AntiDecisive (simulate.rs:689-735): an immediate win first; else the FIRST action in list order whose
      * child is not terminal and leaves the opponent no immediately winning reply; else the inner (uniform) pick.
      * Built for Connect4, Breakthrough, Knightthrough and Othello. */
-    MR_DECISIVE_ANTI = 5
+    MR_DECISIVE_ANTI = 5,
+    /* simulate.rs:936-1033 + 538-570  EpsilonGreedy<G, Lgr<G, Uniform>> (strategy.rs:130-143 Ucb1Lgr): with
+     * probability epsilon a uniform pick; else the reply recorded for (mover, preceding action) if it is legal now;
+     * else a uniform pick.  Two draws per ply, as MR_EPS_MAST.  The reply table is frozen for the batch
+     * (mr_set_replies); the batch's last-write-wins updates come back through mr_reply_updates.  Connect4,
+     * Breakthrough, Knightthrough, Othello; needs a bounded playout (max_playout_depth) for Knightthrough. */
+    MR_EPS_LGR = 6
 };
 
 enum mr_flags {
@@ -97,13 +103,17 @@ enum mr_end_type { MR_END_TERMINAL = 0, MR_END_TURN_LIMIT = 1, MR_END_NO_ACTIONS
  *   Hex 11x11: board[0..1] = occupied[P0] words (low word first), board[2..3] = occupied[P1] words
  *   turn: player to move (0 = Black / P0, 1 = White / P1)
  *   flag: Connect4 / Breakthrough / Knightthrough `winner`; Othello `last_pass`; Hex unused
+ *   prev_action_plus1: 1 + compact code of the action played just before this state (the last edge of the tree
+ *       descent), 0 = none -- the `prev_action` argument of SimulateStrategy::playout (simulate.rs:67-90).  Call
+ *       context, not game state: read by MR_EPS_LGR only, reported as 0 in final states.
  * Zobrist hashes carried by the reference structs are tree-side state and are not part of the record.
  */
 typedef struct {
     uint64_t board[4];
     uint8_t turn;
     uint8_t flag;
-    uint8_t pad[6];
+    uint16_t prev_action_plus1;
+    uint8_t pad[4];
 } mr_leaf;
 
 /* Aggregate of one leaf's playouts; what k calls of ChildArray::update / NodeStats::update need:
@@ -189,6 +199,27 @@ int mr_playout_batch(mr_ctx *ctx, const mr_batch_desc *desc, const mr_leaf *leav
 int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, const void *d_leaves, void *d_results,
                      void *d_amaf, void *d_mast_delta, void *stream);
 int mr_set_mast(mr_ctx *ctx, int game, const mr_action_stat *mast_in);
+
+/* ---- Last Good Reply (MR_EPS_LGR) ----
+ * TreeStats.player_replies (search/shared.rs; read simulate.rs:1013-1032, written backprop.rs:908-923) crosses the
+ * ABI as replies[2][mr_num_actions]: 1 + compact code of player p's recorded reply to the preceding action with
+ * that dense id, 0 = none.  mr_set_replies copies the table; every later MR_EPS_LGR submit uses that copy, frozen
+ * for the batch.  NULL clears it.
+ *
+ * mr_reply_updates, called after mr_wait and before the slot's next submit, returns what the batch's trials would
+ * have written, in a form the host can merge with its tree-path pairs: per (p, preceding action id) the LAST
+ * occurrence -- in (global playout index g = leaf * k + playout, ply) order -- of a reply by p in a playout that p
+ * did not lose (utility == the trial's maximum: the winner, or both players of a zero-utility ending):
+ *   updates_out  [2][mr_num_actions]  order = ((g + 1) << 13) | (4096 + ply), 0 = no occurrence
+ *   last_win_out [n_leaves][2]        1 + the leaf's last playout index that p did not lose, 0 = none (the trials in
+ *                                     which the tree-path pairs above the leaf get written) */
+typedef struct {
+    uint64_t order;
+    uint16_t action_plus1; /* 1 + compact code of the reply */
+    uint16_t pad[3];
+} mr_reply_update;
+int mr_set_replies(mr_ctx *ctx, int game, const uint16_t *replies);
+int mr_reply_updates(mr_ctx *ctx, int slot, mr_reply_update *updates_out, uint32_t *last_win_out);
 
 /* Kernel time of the last completed batch on `slot` (max over the ctx's devices), measured with CUDA
  * events on the launching stream; and the number of rollout-kernel launches the ctx has issued. */

@@ -10,6 +10,7 @@ from .rollout import (
     DecisiveMove,
     DecisiveMoveWin,
     EndType,
+    EpsilonGreedyLgr,
     EpsilonGreedyMast,
     Game,
     GpuRollout,
@@ -27,7 +28,7 @@ from .rollout import (
 )
 
 __all__ = [
-    "BatchResult", "DecisiveMove", "DecisiveMoveWin", "EndType", "EpsilonGreedyMast", "Game", "GpuRollout", "MastTable", "Outcome",
+    "BatchResult", "DecisiveMove", "DecisiveMoveWin", "EndType", "EpsilonGreedyLgr", "EpsilonGreedyMast", "Game", "GpuRollout", "MastTable", "Outcome",
     "Policy", "Trial", "Uniform", "initial_state", "make_leaf", "num_actions", "LEAF_DTYPE", "RECORD_DTYPE",
     "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load", "GpuSearch", "SearchResult", "apply",
     "generate_actions", "terminal_status",

@@ -17,7 +17,8 @@ LIB_PATH = _build.LIB_PATH
 MR_OK = 0
 ERR_NAMES = {1: "MR_ERR_INVALID", 2: "MR_ERR_CUDA", 3: "MR_ERR_NO_DEVICE", 4: "MR_ERR_BUSY", 5: "MR_ERR_UNSUPPORTED", 6: "MR_ERR_COMM"}
 
-LEAF_DTYPE = np.dtype([("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("pad", "u1", (6,))])
+LEAF_DTYPE = np.dtype([("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("prev", "<u2"), ("pad", "u1", (4,))])
+REPLY_UPDATE_DTYPE = np.dtype([("order", "<u8"), ("action_plus1", "<u2"), ("pad", "<u2", (3,))])
 RESULT_DTYPE = np.dtype([("wins", "<u4", (2,)), ("draws", "<u4"), ("cutoffs", "<u4"), ("sum_depth", "<u8")])
 STAT_DTYPE = np.dtype([("visits", "<u4"), ("score", "<i4")])
 RECORD_DTYPE = np.dtype([("depth", "<u4"), ("outcome", "u1"), ("end_type", "u1"), ("pad", "u1", (2,))])
@@ -99,6 +100,8 @@ EXPORTS = [
     "mr_playout_batch",
     "mr_launch_device",
     "mr_set_mast",
+    "mr_set_replies",
+    "mr_reply_updates",
     "mr_last_kernel_ms",
     "mr_kernel_launches",
     "mr_allreduce_root",
@@ -140,6 +143,8 @@ def load() -> C.CDLL:
     L.mr_playout_batch.argtypes = [vp, C.POINTER(BatchDesc), vp, vp, vp, vp, vp, vp, vp, vp]
     L.mr_launch_device.argtypes = [vp, i32, C.POINTER(BatchDesc), vp, vp, vp, vp, vp]
     L.mr_set_mast.argtypes = [vp, i32, vp]
+    L.mr_set_replies.argtypes = [vp, i32, vp]
+    L.mr_reply_updates.argtypes = [vp, i32, vp, vp]
     L.mr_last_kernel_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.mr_kernel_launches.argtypes = [vp]
     L.mr_kernel_launches.restype = C.c_uint64

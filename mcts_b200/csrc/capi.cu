@@ -78,6 +78,9 @@ struct SlotDev {
     DevBuf<uint16_t> trace;
     DevBuf<mr_playout_record> rec;
     DevBuf<mr_leaf> final_state;
+    DevBuf<uint16_t> lgr_in;                // MR_EPS_LGR: frozen reply table
+    DevBuf<unsigned long long> lgr_stamps;  // MR_EPS_LGR: last winning occurrence per (player, preceding action)
+    DevBuf<uint32_t> lgr_last;              // MR_EPS_LGR: per leaf, last playout each player did not lose
     unsigned long long *d_counter = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // what this device covers for the batch in flight
@@ -98,6 +101,7 @@ struct SlotState {
     bool busy = false;
     mr_batch_desc desc{};
     float kernel_ms = 0.f;
+    bool lgr_ready = false; // a completed MR_EPS_LGR batch whose updates can still be read
 };
 
 typedef void (*kernel_fn)(const KernelParams);
@@ -113,6 +117,9 @@ struct mr_ctx {
     uint64_t mast_planes[2][MAST_KINDS][MAST_BITS] = {};
     uint32_t mast_nbits[2] = {0, 0};
     int mast_game = -1;
+    // Last Good Reply table (mr_set_replies), [2][num_actions] of its game
+    std::vector<uint16_t> replies;
+    int replies_game = -1;
     // NCCL (loaded lazily with dlopen; see mr_comm_*)
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
@@ -178,23 +185,27 @@ kernel_fn pick_kernel(int game, int policy, int v) {
         if (policy == MR_UNIFORM) return pick_variant<Connect4, MR_UNIFORM>(v);
         if (policy == MR_DECISIVE_WIN) return pick_variant<Connect4, MR_DECISIVE_WIN>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Connect4, MR_DECISIVE_ANTI>(v);
+        if (policy == MR_EPS_LGR) return pick_variant<Connect4, MR_EPS_LGR>(v);
         return nullptr;
     case MR_BREAKTHROUGH:
         if (policy == MR_UNIFORM) return pick_variant<Breakthrough, MR_UNIFORM>(v);
         if (policy == MR_EPS_MAST) return pick_variant<Breakthrough, MR_EPS_MAST>(v);
         if (policy == MR_DECISIVE_WIN) return pick_variant<Breakthrough, MR_DECISIVE_WIN>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Breakthrough, MR_DECISIVE_ANTI>(v);
+        if (policy == MR_EPS_LGR) return pick_variant<Breakthrough, MR_EPS_LGR>(v);
         return nullptr;
     case MR_KNIGHTTHROUGH:
         if (policy == MR_UNIFORM) return pick_variant<Knightthrough, MR_UNIFORM>(v);
         if (policy == MR_EPS_MAST) return pick_variant<Knightthrough, MR_EPS_MAST>(v);
         if (policy == MR_DECISIVE_WIN) return pick_variant<Knightthrough, MR_DECISIVE_WIN>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Knightthrough, MR_DECISIVE_ANTI>(v);
+        if (policy == MR_EPS_LGR) return pick_variant<Knightthrough, MR_EPS_LGR>(v);
         return nullptr;
     case MR_OTHELLO:
         // DecisiveMove<Win> provably never changes an Othello pick, so it shares the kernel
         if (policy == MR_UNIFORM || policy == MR_DECISIVE_WIN) return pick_variant<Othello, MR_UNIFORM>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Othello, MR_DECISIVE_ANTI>(v);
+        if (policy == MR_EPS_LGR) return pick_variant<Othello, MR_EPS_LGR>(v);
         return nullptr;
     case MR_HEX11:
         if (policy == MR_UNIFORM) return pick_hex(v);
@@ -316,18 +327,25 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
         if (!has_mast) return fail(ctx, MR_ERR_INVALID, "MR_EPS_MAST needs a MAST snapshot (mast_in / mr_set_mast)");
         if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
     }
+    if (d->policy == MR_EPS_LGR) {
+        if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
+        if (ctx->replies_game >= 0 && ctx->replies_game != (int)d->game)
+            return fail(ctx, MR_ERR_INVALID, "the reply table was set for game %d, the batch is game %u", ctx->replies_game, d->game);
+        if ((uint64_t)d->n_leaves * d->playouts_per_leaf >= (1ull << 37)) return fail(ctx, MR_ERR_INVALID, "batch too large for MR_EPS_LGR");
+    }
     if (d->game == MR_HEX11 && (d->flags & MR_WANT_MAST_DELTA))
         return fail(ctx, MR_ERR_UNSUPPORTED, "no MAST table is built for Hex (no MAST policy in scope for it)");
     if ((d->flags & MR_WANT_TRACE) && d->max_trace == 0) return fail(ctx, MR_ERR_INVALID, "MR_WANT_TRACE needs max_trace > 0");
     uint32_t cap = 0;
-    const bool needs_scratch = (d->flags & MR_WANT_MAST_DELTA) || ((d->flags & MR_WANT_AMAF) && d->game != MR_HEX11);
+    const bool needs_scratch = (d->flags & MR_WANT_MAST_DELTA) || ((d->flags & MR_WANT_AMAF) && d->game != MR_HEX11) ||
+                               d->policy == MR_EPS_LGR;
     if (needs_scratch) {
         const uint32_t bound = kGames[d->game].depth_bound;
         cap = d->max_playout_depth ? d->max_playout_depth : bound;
         if (bound && cap > bound) cap = bound;
         if (cap == 0)
-            return fail(ctx, MR_ERR_INVALID, "AMAF / MAST-delta need a bounded playout: set max_playout_depth for game %u", d->game);
-        if (cap > 4096) return fail(ctx, MR_ERR_INVALID, "max_playout_depth %u too large for AMAF / MAST-delta (limit 4096)", cap);
+            return fail(ctx, MR_ERR_INVALID, "AMAF / MAST-delta / LGR need a bounded playout: set max_playout_depth for game %u", d->game);
+        if (cap > 4096) return fail(ctx, MR_ERR_INVALID, "max_playout_depth %u too large for AMAF / MAST-delta / LGR (limit 4096)", cap);
     }
     if ((uint64_t)d->n_leaves * d->playouts_per_leaf > (1ull << 40)) return fail(ctx, MR_ERR_INVALID, "batch too large");
     *fn_out = fn;
@@ -484,6 +502,9 @@ void mr_destroy(mr_ctx *ctx) {
             sd.trace.release();
             sd.rec.release();
             sd.final_state.release();
+            sd.lgr_in.release();
+            sd.lgr_stamps.release();
+            sd.lgr_last.release();
             if (sd.d_counter) cudaFree(sd.d_counter);
             if (sd.ev_begin) cudaEventDestroy(sd.ev_begin);
             if (sd.ev_end) cudaEventDestroy(sd.ev_end);
@@ -506,6 +527,20 @@ int mr_set_mast(mr_ctx *ctx, int game, const mr_action_stat *mast_in) {
     if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
     if (game < 0 || game >= MR_NUM_GAMES || !mast_in) return fail(ctx, MR_ERR_INVALID, "mr_set_mast: bad arguments");
     return compute_mast_planes(ctx, game, mast_in);
+}
+
+int mr_set_replies(mr_ctx *ctx, int game, const uint16_t *replies) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (game < 0 || game >= MR_NUM_GAMES) return fail(ctx, MR_ERR_INVALID, "mr_set_replies: unknown game %d", game);
+    if (!replies) {
+        ctx->replies.clear();
+        ctx->replies_game = -1;
+        return MR_OK;
+    }
+    const size_t cnt = (size_t)2 * kGames[game].num_actions;
+    ctx->replies.assign(replies, replies + cnt);
+    ctx->replies_game = game;
+    return MR_OK;
 }
 
 int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *leaves, const mr_action_stat *mast_in) {
@@ -570,6 +605,21 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             CUDA_TRY(ctx, sd.final_state.reserve((size_t)total, true));
             kp.final_state = sd.final_state.d;
         }
+        if (desc->policy == MR_EPS_LGR) {
+            const size_t cnt = (size_t)2 * na;
+            CUDA_TRY(ctx, sd.lgr_stamps.reserve(cnt, true));
+            CUDA_TRY(ctx, sd.lgr_last.reserve((size_t)2 * n, true));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr_stamps.d, 0, sizeof(unsigned long long) * cnt, dv.stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr_last.d, 0, sizeof(uint32_t) * 2 * n, dv.stream));
+            kp.lgr_stamps = sd.lgr_stamps.d;
+            kp.lgr_last = sd.lgr_last.d;
+            if (!ctx->replies.empty()) {
+                CUDA_TRY(ctx, sd.lgr_in.reserve(cnt, true));
+                memcpy(sd.lgr_in.h, ctx->replies.data(), sizeof(uint16_t) * cnt);
+                CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_in.d, sd.lgr_in.h, sizeof(uint16_t) * cnt, cudaMemcpyHostToDevice, dv.stream));
+                kp.lgr_in = sd.lgr_in.d;
+            }
+        }
         CUDA_TRY(ctx, cudaEventRecord(sd.ev_begin, dv.stream));
         rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter, slot);
         if (rc != MR_OK) return rc;
@@ -581,6 +631,10 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.amaf.h, sd.amaf.d, sizeof(mr_action_stat) * n * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
         if (desc->flags & MR_WANT_MAST_DELTA)
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.mast_delta.h, sd.mast_delta.d, sizeof(mr_action_stat) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
+        if (desc->policy == MR_EPS_LGR) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_stamps.h, sd.lgr_stamps.d, sizeof(unsigned long long) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_last.h, sd.lgr_last.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, dv.stream));
+        }
         const uint64_t gb = sd.g_begin, ge = sd.g_end;
         if (ge > gb) {
             if (desc->flags & MR_WANT_TRACE) {
@@ -595,6 +649,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
         }
     }
     ss.busy = true;
+    ss.lgr_ready = false;
     ss.desc = *desc;
     return MR_OK;
 }
@@ -622,6 +677,7 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
         }
     }
     ss.kernel_ms = worst_ms;
+    ss.lgr_ready = d.policy == MR_EPS_LGR;
     memset(out, 0, sizeof(mr_leaf_result) * n);
     if (amaf_out && (d.flags & MR_WANT_AMAF)) memset(amaf_out, 0, sizeof(mr_action_stat) * (size_t)n * 2 * na);
     if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) memset(mast_delta_out, 0, sizeof(mr_action_stat) * 2 * na);
@@ -661,6 +717,44 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
     return MR_OK;
 }
 
+int mr_reply_updates(mr_ctx *ctx, int slot, mr_reply_update *updates_out, uint32_t *last_win_out) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (slot < 0 || slot >= MR_NUM_SLOTS) return fail(ctx, MR_ERR_INVALID, "slot %d out of range", slot);
+    SlotState &ss = ctx->slot[slot];
+    if (ss.busy || !ss.lgr_ready)
+        return fail(ctx, MR_ERR_INVALID, "slot %d holds no completed MR_EPS_LGR batch (call mr_wait first)", slot);
+    const mr_batch_desc &d = ss.desc;
+    const int game = (int)d.game, na = kGames[game].num_actions;
+    const bool through = game == MR_BREAKTHROUGH || game == MR_KNIGHTTHROUGH;
+    if (updates_out) {
+        for (int i = 0; i < 2 * na; ++i) {
+            unsigned long long best = 0;
+            for (Device &dv : ctx->dev) {
+                SlotDev &sd = dv.slot[slot];
+                if (sd.g_end > sd.g_begin) best = std::max(best, sd.lgr_stamps.h[i]);
+            }
+            mr_reply_update &u = updates_out[i];
+            memset(&u, 0, sizeof u);
+            if (best) {
+                const uint32_t id = (uint32_t)(best & 0x1fffull);
+                u.order = best >> 13;
+                u.action_plus1 = (uint16_t)((through ? ((id >> 6) << 8) | (id & 63u) : id) + 1u);
+            }
+        }
+    }
+    if (last_win_out) {
+        for (uint32_t i = 0; i < 2 * d.n_leaves; ++i) {
+            uint32_t best = 0;
+            for (Device &dv : ctx->dev) {
+                SlotDev &sd = dv.slot[slot];
+                if (sd.g_end > sd.g_begin) best = std::max(best, sd.lgr_last.h[i]);
+            }
+            last_win_out[i] = best;
+        }
+    }
+    return MR_OK;
+}
+
 int mr_playout_batch(mr_ctx *ctx, const mr_batch_desc *desc, const mr_leaf *leaves, const mr_action_stat *mast_in,
                      mr_leaf_result *out, mr_action_stat *amaf_out, mr_action_stat *mast_delta_out, uint16_t *trace_out,
                      mr_playout_record *rec_out, mr_leaf *final_out) {
@@ -678,6 +772,7 @@ int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, c
     if (!desc) return fail(ctx, MR_ERR_INVALID, "null batch descriptor");
     if (desc->flags & (MR_WANT_TRACE | MR_WANT_FINAL_STATE))
         return fail(ctx, MR_ERR_INVALID, "trace / final-state outputs are not available on the device-resident path");
+    if (desc->policy == MR_EPS_LGR) return fail(ctx, MR_ERR_UNSUPPORTED, "MR_EPS_LGR is not available on the device-resident path");
     kernel_fn fn = nullptr;
     uint32_t trace_cap = 0;
     int rc = validate(ctx, desc, ctx->mast_game == (int)desc->game, &fn, &trace_cap);

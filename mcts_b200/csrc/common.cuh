@@ -60,6 +60,10 @@ struct KernelParams {
     uint32_t mast_nbits[2];
     uint16_t *trace_scratch;   // [resident warps][trace_cap][32] u16, MAST-delta staging
     uint32_t trace_cap;
+    // Last Good Reply (MR_EPS_LGR): frozen reply table in, last-winning-occurrence stamps out
+    const uint16_t *lgr_in;          // [2][NA]: 1 + compact code of the reply to the preceding action id, 0 = none
+    unsigned long long *lgr_stamps;  // [2][NA]: ((g + 1) << 26) | ((4096 + ply) << 13) | reply action id, max-merged
+    uint32_t *lgr_last;              // [n_leaves][2]: 1 + last playout index the player did not lose, max-merged
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

@@ -55,6 +55,7 @@ struct Connect4 {
     static constexpr int NSLOTS = 7; // compact per-player statistic slots (== action ids here)
     static constexpr bool MASK_AMAF = false;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
+    __device__ static uint32_t code_to_slot(uint32_t pl, uint32_t code) { return code < 7u ? code : 0u; }
     static constexpr uint64_t BOTTOM = 0x0001010101010101ull;
     static constexpr uint64_t BOARD = 0x003F3F3F3F3F3F3Full;
     static constexpr uint64_t TOPROW = 0x0020202020202020ull;
@@ -69,6 +70,7 @@ struct Connect4 {
     uint64_t cur, all;
     uint32_t n_open;
     uint32_t rt_parity;
+    uint32_t lgr_reply; // MR_EPS_LGR: 1 + compact code of the recorded reply for this ply, 0 = none / exploring
 
     __device__ static uint64_t to_colbyte(uint64_t rm) { // reference row-major (idx = row*7 + col) -> col*8 + row
         uint64_t out = 0;
@@ -185,6 +187,9 @@ struct Connect4 {
                 const uint64_t cand = (T == 0 ? moves : ((T & (T - 1)) == 0 ? T : 0ull)) & ~(W >> 1);
                 bit = cand & (0 - cand);
             }
+        } else if (POLICY == MR_EPS_LGR) {
+            // the recorded reply column, if it is still open (simulate.rs:1022-1026)
+            bit = (lgr_reply && lgr_reply <= 7u) ? (moves & (0xFFull << (8u * (lgr_reply - 1u)))) : 0ull;
         } else {
             bit = 0;
         }
@@ -227,7 +232,8 @@ struct Connect4 {
         // the winner keeps the turn (:332-336)
         out->turn = (uint8_t)(won ? next ^ 1 : next);
         out->flag = won ? 1 : 0;
-        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+        out->prev_action_plus1 = 0;
+        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
     }
 };
 
@@ -253,6 +259,7 @@ struct ThroughBase {
 
     uint64_t black, white;
     uint32_t rt_parity;
+    uint32_t lgr_reply; // MR_EPS_LGR: 1 + compact code (src << 8 | dst) of the recorded reply, 0 = none / exploring
 
     __device__ static int prepare(Shared &sh, const mr_leaf &leaf, uint32_t lane) {
         if (lane == 0) {
@@ -275,7 +282,8 @@ struct ThroughBase {
         out->board[2] = out->board[3] = 0;
         out->turn = (uint8_t)(won ? next ^ 1 : next);
         out->flag = won ? 1 : 0;
-        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+        out->prev_action_plus1 = 0;
+        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
     }
     // own/opp update for a move src -> dst by `white`; returns true when the far wall is reached
     __device__ bool apply_move(bool is_white, uint32_t src, uint32_t dst) {
@@ -300,6 +308,12 @@ struct Breakthrough : ThroughBase {
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
         const uint32_t src = slot / 3u, kind = slot - src * 3u;
         return src * 64u + (uint32_t)((int)src + (pl ? 7 : -9) + (int)kind);
+    }
+    // compact code (src << 8 | dst) of a move by `pl` -> its slot; 0 for a code that is not such a move
+    __device__ static uint32_t code_to_slot(uint32_t pl, uint32_t code) {
+        const uint32_t src = code >> 8, dst = code & 0xffu;
+        const uint32_t kind = dst - src - (pl ? 7u : (uint32_t)-9);
+        return (src < 64u && kind < 3u) ? src * 3u + kind : 0u;
     }
     // source-space masks of the three move kinds for the mover
     __device__ static void masks(bool is_white, uint64_t own, uint64_t opp, uint64_t &W, uint64_t &F, uint64_t &E) {
@@ -360,6 +374,14 @@ struct Knightthrough : ThroughBase {
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
         const uint32_t src = slot >> 3, kind = slot & 7u;
         return src * 64u + (uint32_t)((int)src + delta(kind));
+    }
+    __device__ static uint32_t code_to_slot(uint32_t pl, uint32_t code) {
+        const uint32_t src = code >> 8, dst = code & 0xffu;
+        uint32_t kind = 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if ((int)dst - (int)src == delta((uint32_t)q)) kind = q;
+        return (src < 64u && kind < 8u) ? src * 8u + kind : 0u;
     }
     __device__ static void masks(uint64_t own, uint64_t M[8]) {
         const uint64_t n = ~own;
@@ -468,6 +490,21 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
             }
         } else {
             idx = mulhi(x0, n);
+        }
+    } else if (POLICY == MR_EPS_LGR) {
+        // the recorded reply, if it is legal now (simulate.rs:1022-1026); else the uniform pick
+        idx = mulhi(x0, n);
+        if (lgr_reply) {
+            const uint32_t s0 = (lgr_reply - 1u) >> 8, d0 = (lgr_reply - 1u) & 0xffu;
+            const uint32_t dr = d0 - s0 - (is_white ? 7u : (uint32_t)-9);
+            if (s0 < 64u && dr < 3u) {
+                const uint64_t mk = dr == 0 ? W : (dr == 1 ? F : E);
+                if ((mk >> s0) & 1ull) {
+                    src = s0;
+                    dir = dr;
+                    have = true;
+                }
+            }
         }
     } else if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
         const uint32_t pl = is_white ? 1u : 0u;
@@ -656,6 +693,20 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
         } else {
             idx = mulhi(x0, n);
         }
+    } else if (POLICY == MR_EPS_LGR) {
+        idx = mulhi(x0, n);
+        if (lgr_reply) {
+            const uint32_t s0 = (lgr_reply - 1u) >> 8, d0 = (lgr_reply - 1u) & 0xffu;
+            if (s0 < 64u) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if ((int)d0 - (int)s0 == delta((uint32_t)q) && ((M[q] >> s0) & 1ull)) {
+                        src = s0;
+                        kind = q;
+                        have = true;
+                    }
+            }
+        }
     } else if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
         const uint32_t pl = is_white ? 1u : 0u;
         uint64_t cand[8];
@@ -744,6 +795,7 @@ struct Othello {
     static constexpr int NSLOTS = 65;
     static constexpr bool MASK_AMAF = false;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
+    __device__ static uint32_t code_to_slot(uint32_t pl, uint32_t code) { return code < 65u ? code : 0u; }
     // The per-ply code (8 fills for moves + 8 for flips) is large: the four plies of a window run as a LOOP,
     // with the ply's parity a run-time value, so the kernel fits the instruction cache.
     static constexpr bool ROLLED = true;
@@ -756,6 +808,7 @@ struct Othello {
     uint64_t black, white;
     uint32_t last_pass;
     uint32_t rt_parity; // parity of the current ply inside its window (PARITY == 2 call sites)
+    uint32_t lgr_reply; // MR_EPS_LGR: 1 + square of the recorded reply (65 = PASS), 0 = none / exploring
 
     // (measured: writing the high word of right shifts as a multiply-high to move it to the FMA pipe is SLOWER,
     // 13.9 ms vs 13.2 ms per 2^24 playouts: IMAD.HI is half rate)
@@ -876,6 +929,14 @@ struct Othello {
                 }
             }
         }
+        if (POLICY == MR_EPS_LGR && lgr_reply && lgr_reply <= 64u && ((moves >> (lgr_reply - 1u)) & 1ull)) {
+            // the recorded reply square, if legal now (a recorded PASS is legal exactly when it is the only action,
+            // handled above)
+            sq = lgr_reply - 1u;
+            mv = bit64(sq);
+            fl = flips(mv, P, O);
+            have = true;
+        }
         if (!have) {
             uint32_t idx = mulhi(x0, n);
             const uint32_t nlo = __popc(lo32(moves));
@@ -903,7 +964,8 @@ struct Othello {
         out->board[2] = out->board[3] = 0;
         out->turn = (uint8_t)((s.turn + plies) & 1);
         out->flag = (uint8_t)last_pass;
-        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+        out->prev_action_plus1 = 0;
+        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
     }
 };
 

@@ -135,7 +135,11 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                         r.pad[0] = r.pad[1] = 0;
                         p.rec[g] = r;
                     }
-                    if (WANT_FINAL && p.final_state) p.final_state[g] = s_leaf[warp];
+                    if (WANT_FINAL && p.final_state) {
+                        mr_leaf fs = s_leaf[warp];
+                        fs.prev_action_plus1 = 0; // call context, not game state
+                        p.final_state[g] = fs;
+                    }
                 }
             }
         } else {
@@ -302,7 +306,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                         }
                         out->turn = (uint8_t)((leaf_turn + depth) & 1u);
                         out->flag = 0;
-                        for (int i = 0; i < 6; ++i) out->pad[i] = 0;
+                        out->prev_action_plus1 = 0;
+        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
                     }
                 }
                 if (WANT_AMAF) {

@@ -15,7 +15,7 @@
 //
 // Draw discipline (shared with the CPU oracle, DESIGN.md "Draw discipline"), Philox4x32-10 keyed by the seed:
 //   uniform / decisive : ctr = (leaf_id, playout_id, ply >> 2, 0);  x0 = out[ply & 3]
-//   epsilon-MAST       : ctr = (leaf_id, playout_id, ply >> 1, 1);  x0 = out[2*(ply & 1)], x1 = out[2*(ply & 1) + 1]
+//   epsilon-MAST / LGR : ctr = (leaf_id, playout_id, ply >> 1, 1);  x0 = out[2*(ply & 1)], x1 = out[2*(ply & 1) + 1]
 #pragma once
 
 #include <type_traits>
@@ -58,13 +58,18 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
     constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
     constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
     constexpr bool MASK_AMAF = WANT_AMAF && G::MASK_AMAF;
-    constexpr bool NEED_SCRATCH = WANT_MAST || (WANT_AMAF && !G::MASK_AMAF); // per-lane slot trace
-    constexpr int WINDOW = POLICY == MR_EPS_MAST ? 2 : 4;
+    constexpr bool IS_LGR = POLICY == MR_EPS_LGR;
+    constexpr bool PAIR_DRAWS = POLICY == MR_EPS_MAST || IS_LGR; // two Philox words per ply
+    constexpr bool NEED_SCRATCH = WANT_MAST || (WANT_AMAF && !G::MASK_AMAF) || IS_LGR; // per-lane slot trace
+    constexpr int WINDOW = PAIR_DRAWS ? 2 : 4;
 
     __shared__ __align__(16) mr_leaf s_leaf[WARPS_PER_BLOCK];
     __shared__ typename G::Shared s_game[WARPS_PER_BLOCK];
     __shared__ uint32_t s_mast[WARPS_PER_BLOCK][WANT_MAST ? 2 * G::NSLOTS : 1];
     __shared__ uint32_t s_amaf[WARPS_PER_BLOCK][WANT_AMAF ? 2 * G::NSLOTS : 1];
+    // LGR: per (player, slot of the preceding action) the largest stamp ((g + 1) << 26 | (4096 + ply) << 13 | reply slot);
+    // one table per BLOCK (64-bit entries: per-warp copies would not fit next to the MAST / AMAF tables)
+    __shared__ unsigned long long s_lgr[IS_LGR ? 2 * G::NSLOTS : 1];
 
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
@@ -73,12 +78,17 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
     uint16_t *scratch = NEED_SCRATCH ? p.trace_scratch + (size_t)gwarp * p.trace_cap * 32u : nullptr;
     uint32_t *mast_tab = s_mast[warp];
     uint32_t *amaf_tab = s_amaf[warp];
+    unsigned long long *lgr_tab = s_lgr;
     uint32_t mast_plies = 0, amaf_plies = 0; // warp-uniform: plies accumulated since the last flush
 
     if (WANT_MAST)
         for (uint32_t e = lane; e < 2u * G::NSLOTS; e += 32) mast_tab[e] = 0;
     if (WANT_AMAF)
         for (uint32_t e = lane; e < 2u * G::NSLOTS; e += 32) amaf_tab[e] = 0;
+    if (IS_LGR) {
+        for (uint32_t e = threadIdx.x; e < 2u * G::NSLOTS; e += THREADS_PER_BLOCK) lgr_tab[e] = 0;
+        __syncthreads();
+    }
     __syncwarp();
 
     unsigned long long grab_lo = 0, grab_hi = 0; // the warp's current grab, relative to g_begin
@@ -120,8 +130,16 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
         const int leaf_status = G::prepare(sh, s_leaf[warp], lane);
         __syncwarp();
         const uint32_t leaf_turn = s_leaf[warp].turn;
+        // LGR: the action that led to the leaf (playout()'s prev_action), as 1 + its slot in the numbering of the
+        // player who made it (the opponent of the leaf's mover); 0 = none
+        uint32_t leaf_prev_slot1 = 0;
+        if constexpr (IS_LGR) {
+            const uint32_t pa = s_leaf[warp].prev_action_plus1;
+            if (pa) leaf_prev_slot1 = G::code_to_slot(1u - (leaf_turn & 1u), pa - 1u) + 1u;
+        }
 
         uint32_t acc_w0 = 0, acc_w1 = 0, acc_draw = 0, acc_cut = 0, acc_depth = 0;
+        uint32_t acc_lw0 = 0, acc_lw1 = 0; // LGR: 1 + last playout id each player did not lose
 
         if (leaf_status != MR_NOT_TERMINAL) {
             // a terminal leaf: every playout is the zero-ply trial with the leaf's own status
@@ -131,6 +149,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                 if (leaf_status == MR_WINNER_P0) acc_w0 = cnt;
                 else if (leaf_status == MR_WINNER_P1) acc_w1 = cnt;
                 else acc_draw = cnt;
+                if (leaf_status != MR_WINNER_P1) acc_lw0 = pid_end;
+                if (leaf_status != MR_WINNER_P0) acc_lw1 = pid_end;
             }
             if (WANT_TRACE || WANT_FINAL) {
                 for (uint32_t pid = pid_begin + lane; pid < pid_end; pid += 32) {
@@ -143,7 +163,11 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                         r.pad[0] = r.pad[1] = 0;
                         p.rec[g] = r;
                     }
-                    if (WANT_FINAL && p.final_state) p.final_state[g] = s_leaf[warp];
+                    if (WANT_FINAL && p.final_state) {
+                        mr_leaf fs = s_leaf[warp];
+                        fs.prev_action_plus1 = 0; // call context, not game state
+                        p.final_state[g] = fs;
+                    }
                 }
             }
         } else {
@@ -155,11 +179,12 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
             uint32_t depth = 0, win = 0;
             int end_code = 0;
             bool cutoff = false;
+            uint32_t prev_slot1 = leaf_prev_slot1; // LGR: 1 + slot of the preceding action
             st.reset(sh);
 
             for (;;) {
                 uint32_t r[4];
-                philox4x32_10(leaf_id, pid, win, POLICY == MR_EPS_MAST ? 1u : 0u, p.seed_lo, p.seed_hi, r);
+                philox4x32_10(leaf_id, pid, win, PAIR_DRAWS ? 1u : 0u, p.seed_lo, p.seed_hi, r);
                 // the depth cutoff can only fire in a window that reaches max_depth: one test per window, not per ply
                 const bool near_cutoff = depth + (uint32_t)WINDOW > p.max_depth || p.max_depth < (uint32_t)WINDOW;
                 // one ply.  PAR is the ply's parity inside the window: a compile-time 0/1 when the window is
@@ -174,8 +199,19 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                             end_code = ST_DRAW;
                         } else {
                             uint32_t action = 0, slot = 0;
+                            if constexpr (IS_LGR) {
+                                // Lgr::select_move (simulate.rs:1013-1032) behind EpsilonGreedy (:538-570): unless this
+                                // ply explores, look up the mover's recorded reply to the preceding action
+                                uint32_t reply = 0;
+                                if (prev_slot1 && p.lgr_in && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+                                    const uint32_t pl = (leaf_turn ^ (par == 2 ? st.rt_parity : (uint32_t)par)) & 1u;
+                                    reply = p.lgr_in[pl * (uint32_t)G::NA + G::slot_action_id(1u - pl, prev_slot1 - 1u)];
+                                }
+                                st.lgr_reply = reply;
+                            }
                             const int code = st.template step<POLICY, par>(sh, x0, x1, p, action, slot);
                             if (code & ST_MOVED) {
+                                if (IS_LGR) prev_slot1 = slot + 1u;
                                 if (WANT_TRACE && p.trace) {
                                     if (depth < p.max_trace)
                                         p.trace[((size_t)li * p.k + pid) * p.max_trace + depth] = (uint16_t)action;
@@ -197,7 +233,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                     for (uint32_t j = 0; j < (uint32_t)WINDOW; ++j) {
                         st.rt_parity = j & 1u;
                         const uint32_t x0 = r[0], x1 = r[1];
-                        if constexpr (POLICY == MR_EPS_MAST) {
+                        if constexpr (PAIR_DRAWS) {
                             r[0] = r[2];
                             r[1] = r[3];
                         } else {
@@ -207,7 +243,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                         }
                         ply(std::integral_constant<int, 2>{}, x0, x1);
                     }
-                } else if constexpr (POLICY == MR_EPS_MAST) {
+                } else if constexpr (PAIR_DRAWS) {
                     ply(std::integral_constant<int, 0>{}, r[0], r[1]);
                     ply(std::integral_constant<int, 1>{}, r[2], r[3]);
                 } else {
@@ -229,6 +265,10 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                         acc_draw += (e == ST_DRAW || e == ST_NO_ACTIONS);
                         acc_cut += cutoff;
                         acc_depth += depth;
+                        if (IS_LGR) {
+                            if (e != ST_WIN_P1) acc_lw0 = max(acc_lw0, pid + 1u);
+                            if (e != ST_WIN_P0) acc_lw1 = max(acc_lw1, pid + 1u);
+                        }
                         const size_t g = (size_t)li * p.k + pid;
                         if (WANT_TRACE && p.rec) {
                             mr_playout_record rr;
@@ -281,6 +321,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                             f &= 31u;
                             const uint32_t ex_f = __shfl_sync(FULL_MASK, excl, f);
                             const int e_f = __shfl_sync(FULL_MASK, end_code, f);
+                            const uint32_t pid_f = IS_LGR ? __shfl_sync(FULL_MASK, pid, f) : 0u;
                             if (q < total) {
                                 const uint32_t t = q - ex_f;
                                 const uint32_t slot = scratch[t * 32u + f];
@@ -290,6 +331,16 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
                                 const uint32_t inc = 1u + ((uint32_t)u << 16);
                                 if (WANT_MAST && p.mast_delta) atomicAdd(&mast_tab[pl * G::NSLOTS + slot], inc);
                                 if (WANT_AMAF && !G::MASK_AMAF && p.amaf) atomicAdd(&amaf_tab[pl * G::NSLOTS + slot], inc);
+                                if constexpr (IS_LGR) {
+                                    // backprop.rs:908-923: a reply is recorded when its player's utility is the trial's
+                                    // maximum (u >= 0 here); last write wins == the largest (playout index, ply) stamp
+                                    const uint32_t prev1 = t > 0 ? (uint32_t)scratch[(t - 1u) * 32u + f] + 1u : leaf_prev_slot1;
+                                    if (p.lgr_stamps && u >= 0 && prev1) {
+                                        const unsigned long long g = (unsigned long long)li * p.k + pid_f;
+                                        const unsigned long long stamp = ((g + 1ull) << 26) | ((unsigned long long)(4096u + t) << 13) | slot;
+                                        atomicMax(&lgr_tab[pl * G::NSLOTS + prev1 - 1u], stamp);
+                                    }
+                                }
                             }
                         }
                         __syncwarp();
@@ -345,6 +396,14 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
         acc_draw = __reduce_add_sync(FULL_MASK, acc_draw);
         acc_cut = __reduce_add_sync(FULL_MASK, acc_cut);
         acc_depth = __reduce_add_sync(FULL_MASK, acc_depth);
+        if (IS_LGR && p.lgr_last) {
+            acc_lw0 = __reduce_max_sync(FULL_MASK, acc_lw0);
+            acc_lw1 = __reduce_max_sync(FULL_MASK, acc_lw1);
+            if (lane == 0) {
+                if (acc_lw0) atomicMax(&p.lgr_last[2u * li], acc_lw0);
+                if (acc_lw1) atomicMax(&p.lgr_last[2u * li + 1u], acc_lw1);
+            }
+        }
         if (lane == 0) {
             mr_leaf_result *res = p.results + li;
             if (acc_w0) atomicAdd(&res->wins[0], acc_w0);
@@ -356,6 +415,19 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kern
     }
     // the MAST delta is batch-wide: it leaves shared memory when the warp runs out of tasks
     if (WANT_MAST && p.mast_delta) flush_stat_table<G>(mast_tab, p.mast_delta, lane);
+    if (IS_LGR && p.lgr_stamps) {
+        // slot space -> dense action ids: key = (player, id of the preceding action, made by the other player)
+        __syncthreads(); // every warp of the block has run out of work
+        for (uint32_t e = threadIdx.x; e < 2u * G::NSLOTS; e += THREADS_PER_BLOCK) {
+            const unsigned long long v = lgr_tab[e];
+            if (v) {
+                const uint32_t pl = e >= (uint32_t)G::NSLOTS ? 1u : 0u;
+                const uint32_t prev_slot = e - pl * G::NSLOTS;
+                const unsigned long long out = (v & ~0x1fffull) | G::slot_action_id(pl, (uint32_t)(v & 0x1fffull));
+                atomicMax(&p.lgr_stamps[(size_t)pl * G::NA + G::slot_action_id(1u - pl, prev_slot)], out);
+            }
+        }
+    }
 }
 
 } // namespace mr

@@ -22,7 +22,7 @@ from enum import IntEnum
 import numpy as np
 
 from . import _lib
-from ._lib import LEAF_DTYPE, RECORD_DTYPE, RESULT_DTYPE, STAT_DTYPE, BatchDesc, RolloutError, ptr
+from ._lib import LEAF_DTYPE, RECORD_DTYPE, REPLY_UPDATE_DTYPE, RESULT_DTYPE, STAT_DTYPE, BatchDesc, RolloutError, ptr
 
 
 class Game(IntEnum):
@@ -40,6 +40,7 @@ class Policy(IntEnum):
     DECISIVE_WINLOSS = 3
     DECISIVE_WINLOSSDRAW = 4
     DECISIVE_ANTI = 5
+    EPS_LGR = 6
 
 
 class Outcome(IntEnum):  # TerminalStatus (mcts/src/game.rs:117-122)
@@ -58,7 +59,7 @@ class EndType(IntEnum):  # simulate.rs:15-20 (+ the no-actions ending, :112-116)
 WANT_AMAF, WANT_MAST_DELTA, WANT_TRACE, WANT_FINAL_STATE = 1, 2, 4, 8
 
 # BackpropFlags bits (mcts/src/strategies/mcts/config.rs:11-30)
-BACKPROP_GRAVE, BACKPROP_GLOBAL, BACKPROP_AMAF = 1, 2, 4
+BACKPROP_GRAVE, BACKPROP_GLOBAL, BACKPROP_AMAF, BACKPROP_LGR = 1, 2, 4, 16
 
 OTHELLO_PASS = 64
 _INITIAL = {
@@ -159,6 +160,17 @@ class DecisiveMove:
         return 0
 
 
+@dataclass(frozen=True)
+class EpsilonGreedyLgr:
+    """EpsilonGreedy<G, Lgr<G, Uniform>> (simulate.rs:485-570, 936-1033; strategy.rs:130-143 `Ucb1Lgr`)."""
+
+    epsilon: float = 0.1
+    policy = Policy.EPS_LGR
+
+    def backprop_flags(self) -> int:
+        return BACKPROP_LGR  # Lgr::backprop_flags (simulate.rs:984-986)
+
+
 class MastTable:
     """TreeStats.player_actions as a dense [2][num_actions] (visits, score) table
     (search/shared.rs:88, node.rs:51-55).  `update` is the GLOBAL write of backprop.rs:857-870 applied
@@ -193,6 +205,8 @@ class BatchResult:
     records: np.ndarray | None = None  # RECORD_DTYPE [n_leaves*k]
     final: np.ndarray | None = None  # LEAF_DTYPE [n_leaves*k]
     kernel_ms: float = 0.0
+    reply_updates: np.ndarray | None = None  # REPLY_UPDATE_DTYPE [2][NA]  (Policy.EPS_LGR)
+    last_win: np.ndarray | None = None  # u32 [n_leaves][2]                (Policy.EPS_LGR)
 
     def utilities_sum(self) -> np.ndarray:
         """Per leaf, per player: sum of utilities = wins[p] - losses[p] (node.rs:673-681 aggregated)."""
@@ -321,7 +335,12 @@ class GpuRollout:
         self._check(self.lib.mr_wait(self._h, slot, ptr(res), ptr(amaf), ptr(delta), ptr(trace), ptr(rec), ptr(final)))
         ms = C.c_float()
         self.lib.mr_last_kernel_ms(self._h, slot, C.byref(ms))
-        return BatchResult(res, amaf, delta, trace, rec, final, ms.value)
+        upd = last = None
+        if d.policy == int(Policy.EPS_LGR):
+            upd = np.zeros((2, self.na), dtype=REPLY_UPDATE_DTYPE)
+            last = np.zeros((n, 2), dtype=np.uint32)
+            self._check(self.lib.mr_reply_updates(self._h, slot, ptr(upd), ptr(last)))
+        return BatchResult(res, amaf, delta, trace, rec, final, ms.value, upd, last)
 
     def simulate_many(self, leaves: np.ndarray, k: int, **kw) -> BatchResult:
         """k playouts of every leaf (search/core.rs:218-258 for a batch of leaves)."""
@@ -368,6 +387,17 @@ class GpuRollout:
     def set_mast(self, stats: MastTable | np.ndarray) -> None:
         mast = np.ascontiguousarray(stats.table if isinstance(stats, MastTable) else stats, dtype=STAT_DTYPE)
         self._check(self.lib.mr_set_mast(self._h, int(self.game), ptr(mast)))
+
+    def set_replies(self, replies: np.ndarray | None) -> None:
+        """The Last-Good-Reply table for Policy.EPS_LGR batches: u16 [2][NA], 1 + compact code of player p's reply to
+        the preceding action with that dense id, 0 = none (TreeStats.player_replies).  None clears it."""
+        if replies is None:
+            self._check(self.lib.mr_set_replies(self._h, int(self.game), None))
+            return
+        tab = np.ascontiguousarray(replies, dtype=np.uint16)
+        if tab.shape != (2, self.na):
+            raise ValueError(f"reply table must have shape (2, {self.na})")
+        self._check(self.lib.mr_set_replies(self._h, int(self.game), ptr(tab)))
 
     def launch_device(
         self, d_leaves: int, d_results: int, n_leaves: int, k: int, *, stream: int = 0, device_index: int = 0,

@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 enum { ORC_CONNECT4 = 0, ORC_BREAKTHROUGH = 1, ORC_KNIGHTTHROUGH = 2, ORC_OTHELLO = 3, ORC_HEX11 = 4, ORC_NUM_GAMES = 5 };
-enum { ORC_UNIFORM = 0, ORC_EPS_MAST = 1, ORC_DECISIVE_WIN = 2, ORC_DECISIVE_WINLOSS = 3, ORC_DECISIVE_WINLOSSDRAW = 4, ORC_DECISIVE_ANTI = 5 };
+enum { ORC_UNIFORM = 0, ORC_EPS_MAST = 1, ORC_DECISIVE_WIN = 2, ORC_DECISIVE_WINLOSS = 3, ORC_DECISIVE_WINLOSSDRAW = 4, ORC_DECISIVE_ANTI = 5, ORC_EPS_LGR = 6 };
 enum { ORC_NOT_TERMINAL = 0, ORC_DRAW = 1, ORC_WINNER_P0 = 2, ORC_WINNER_P1 = 3 };
 enum { ORC_END_TERMINAL = 0, ORC_END_TURN_LIMIT = 1, ORC_END_NO_ACTIONS = 2 };
 
@@ -44,12 +44,16 @@ enum { ORC_END_TERMINAL = 0, ORC_END_TURN_LIMIT = 1, ORC_END_NO_ACTIONS = 2 };
  *     reference's row-major layout (idx = row*cols + col, row 0 = south/bottom).
  *   Hex 11x11: board[0..1] = P0 words (low word first), board[2..3] = P1 words.
  *   turn: player to move (0 = Black / P0).
- *   flag: Connect4/Breakthrough/Knightthrough `winner`; Othello `last_pass`. */
+ *   flag: Connect4/Breakthrough/Knightthrough `winner`; Othello `last_pass`.
+ *   prev_plus1: 1 + compact code of the action played just before this state (the last tree edge), 0 = none;
+ *     the `prev_action` argument of SimulateStrategy::playout (simulate.rs:67-90), read by ORC_EPS_LGR only and
+ *     not part of the game state (final states report 0). */
 typedef struct {
     uint64_t board[4];
     uint8_t turn;
     uint8_t flag;
-    uint8_t pad[6];
+    uint16_t prev_plus1;
+    uint8_t pad[4];
 } orc_state;
 
 typedef struct {
@@ -103,6 +107,19 @@ typedef struct {
     uint32_t leaf_id_base;
     uint32_t playouts_per_leaf;
     uint32_t max_trace; /* u16 slots per playout in trace_out */
+    /* ORC_EPS_LGR = EpsilonGreedy<Lgr<Uniform>> (simulate.rs:538-570, 936-1033; strategy.rs:130-143 Ucb1Lgr).
+     * replies: [2][num_actions] = 1 + compact code of player p's recorded reply to the preceding action with that
+     * dense id (0 = none); frozen for the batch.  Outputs (nullable), the batch's last-write-wins updates
+     * (backprop.rs:908-923) in a mergeable form: for every (p, id of the preceding action) the LAST occurrence, in
+     * (global playout index, ply) order, of a reply by p in a playout p did not lose:
+     *   reply_order_out  [2][num_actions] = ((g + 1) << 13) | (4096 + ply), g = leaf * k + playout; 0 = none
+     *   reply_action_out [2][num_actions] = 1 + compact code of that reply
+     *   last_win_out     [n_leaves][2]    = 1 + the leaf's last playout index that p did not lose (the trials in
+     *                                       which the tree-path pairs above the leaf are written); 0 = none */
+    const uint16_t *replies;
+    uint64_t *reply_order_out;
+    uint16_t *reply_action_out;
+    uint32_t *last_win_out;
 } orc_batch_desc;
 
 /* One playout.  trace (nullable) receives up to max_trace action ids.  final_state nullable. */

@@ -16,6 +16,8 @@
  *   random_best + PRIMES .... mcts/src/util.rs:129-163
  *   DecisiveMove (Win) ...... simulate.rs:636-687 (loser.or(draw) fallback :672-687)
  *   GLOBAL/MAST write ....... backprop.rs:857-870
+ *   Lgr (LGR-1) ............. simulate.rs:936-1033 (reply if recorded and legal, else inner); table write
+ *                             backprop.rs:908-923 (last write wins, only players whose utility is the maximum)
  *   GRAVE/AMAF occurrences .. backprop.rs:565-640
  *
  * The reference draws from rand 0.8's SmallRng (crates.io, absent from /root/reference,
@@ -173,6 +175,8 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
     const int game = d->game;
     const int na = orc_num_actions(game);
     orc_state state = *leaf;
+    state.prev_plus1 = 0; /* call context, not game state */
+    int prev = leaf->prev_plus1 ? (int)leaf->prev_plus1 - 1 : -1; /* playout()'s prev_action */
     uint32_t depth = 0;
     int status, end_type;
     uint16_t available[ORC_MAX_ACTIONS];
@@ -196,7 +200,7 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
         }
         int player = orc_player_to_move(game, &state);
         int pick = -1;
-        if (d->policy >= ORC_DECISIVE_WIN) pick = decisive_choose(game, d->policy, &state, available, n, player);
+        if (d->policy >= ORC_DECISIVE_WIN && d->policy <= ORC_DECISIVE_ANTI) pick = decisive_choose(game, d->policy, &state, available, n, player);
         if (pick < 0) {
             uint32_t x0;
             int greedy = 0;
@@ -204,6 +208,16 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
                 uint32_t x1;
                 orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
                 greedy = !((uint64_t)x1 < d->eps_threshold);
+            } else if (d->policy == ORC_EPS_LGR) {
+                uint32_t x1;
+                orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
+                int explore = (uint64_t)x1 < d->eps_threshold;
+                if (!explore && prev >= 0 && d->replies) { /* Lgr::select_move, simulate.rs:1013-1032 */
+                    uint16_t reply = d->replies[(size_t)player * na + action_id(game, (uint16_t)prev)];
+                    if (reply)
+                        for (int i = 0; i < n; ++i)
+                            if (available[i] == (uint16_t)(reply - 1)) pick = i;
+                }
             } else {
                 x0 = orc_draw(d->seed, leaf_id, playout_id, depth, 0);
             }
@@ -211,11 +225,12 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
                 const orc_action_stat *tab = mast + (size_t)player * na;
                 for (int i = 0; i < n; ++i) score[i] = unigram_score(tab, action_id(game, available[i]));
                 pick = random_best_index(score, n, mulhi32(x0, 16u * (uint32_t)n));
-            } else {
+            } else if (pick < 0) { /* (an LGR reply may already be chosen) */
                 pick = (int)mulhi32(x0, (uint32_t)n);
             }
         }
         uint16_t action = available[pick];
+        prev = action;
         if (trace && depth < d->max_trace) trace[depth] = action;
         orc_apply(game, &state, action);
         ++depth;
@@ -241,6 +256,8 @@ typedef struct {
     orc_playout_record *rec_out;
     orc_state *final_out;
     uint64_t begin, end; /* global playout index range [begin, end) */
+    uint64_t *reply_order;  /* thread-private */
+    uint16_t *reply_action; /* thread-private */
 } batch_job;
 
 static void add_trace_stats(int game, const orc_state *leaf, const uint16_t *trace, uint32_t depth, int outcome,
@@ -263,7 +280,7 @@ static void *batch_worker(void *arg) {
     const orc_batch_desc *d = j->d;
     const uint32_t k = d->playouts_per_leaf;
     const int na = orc_num_actions(d->game);
-    const int need_trace = j->amaf_out || j->mast_delta;
+    const int need_trace = j->amaf_out || j->mast_delta || j->reply_order || d->last_win_out;
     uint32_t cap = d->max_trace;
     uint16_t *scratch = NULL;
     orc_batch_desc local = *d;
@@ -308,6 +325,31 @@ static void *batch_worker(void *arg) {
             }
         }
         if (j->mast_delta) add_trace_stats(d->game, &j->leaves[li], scratch, rec.depth, rec.outcome, j->mast_delta);
+        if (j->reply_order || d->last_win_out) {
+            /* backprop.rs:908-923: a player "won" when its utility is the trial's maximum: the winner, or both
+             * players of a zero-utility ending */
+            for (int p = 0; p < 2; ++p) {
+                int lost = (rec.outcome == ORC_WINNER_P0 && p == 1) || (rec.outcome == ORC_WINNER_P1 && p == 0);
+                if (!lost && d->last_win_out) {
+                    uint32_t *lw = &d->last_win_out[(size_t)li * 2 + p], cur = __atomic_load_n(lw, __ATOMIC_RELAXED);
+                    while (cur < pi + 1 && !__atomic_compare_exchange_n(lw, &cur, pi + 1, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                    }
+                }
+            }
+            if (j->reply_order)
+                for (uint32_t t = 0; t < rec.depth; ++t) {
+                    int p = (j->leaves[li].turn + (int)t) & 1;
+                    int lost = (rec.outcome == ORC_WINNER_P0 && p == 1) || (rec.outcome == ORC_WINNER_P1 && p == 0);
+                    int pv = t > 0 ? (int)scratch[t - 1] : (j->leaves[li].prev_plus1 ? (int)j->leaves[li].prev_plus1 - 1 : -1);
+                    if (lost || pv < 0) continue;
+                    size_t key = (size_t)p * na + action_id(d->game, (uint16_t)pv);
+                    uint64_t order = ((g + 1) << 13) | (4096u + t);
+                    if (order > j->reply_order[key]) {
+                        j->reply_order[key] = order;
+                        j->reply_action[key] = (uint16_t)(scratch[t] + 1);
+                    }
+                }
+        }
     }
     free(scratch);
     return NULL;
@@ -319,7 +361,8 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
     if (d->game < 0 || d->game >= ORC_NUM_GAMES) return -1;
     if (d->policy == ORC_EPS_MAST && !mast) return -2;
     /* trace-derived statistics need a bounded trace: only Knightthrough can run unboundedly long */
-    if ((amaf_out || mast_delta_out) && d->max_playout_depth == 0 && d->game == ORC_KNIGHTTHROUGH) return -3;
+    if ((amaf_out || mast_delta_out || d->reply_order_out) && d->max_playout_depth == 0 && d->game == ORC_KNIGHTTHROUGH) return -3;
+    if (d->reply_order_out && !d->reply_action_out) return -4;
     const int na = orc_num_actions(d->game);
     const uint64_t total = (uint64_t)n_leaves * d->playouts_per_leaf;
     memset(results, 0, sizeof(orc_leaf_result) * n_leaves);
@@ -342,7 +385,12 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
         j->end = total * (uint64_t)(t + 1) / (uint64_t)n_threads;
         j->mast_delta = NULL;
         if (mast_delta_out) j->mast_delta = (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat));
+        if (d->reply_order_out) {
+            j->reply_order = (uint64_t *)calloc((size_t)2 * na, sizeof(uint64_t));
+            j->reply_action = (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t));
+        }
     }
+    if (d->last_win_out) memset(d->last_win_out, 0, sizeof(uint32_t) * 2 * n_leaves);
     if (n_threads == 1) {
         batch_worker(&jobs[0]);
     } else {
@@ -356,6 +404,19 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
                 mast_delta_out[i].score += jobs[t].mast_delta[i].score;
             }
             free(jobs[t].mast_delta);
+        }
+    }
+    if (d->reply_order_out) {
+        memset(d->reply_order_out, 0, sizeof(uint64_t) * 2 * na);
+        memset(d->reply_action_out, 0, sizeof(uint16_t) * 2 * na);
+        for (int t = 0; t < n_threads; ++t) {
+            for (int i = 0; i < 2 * na; ++i)
+                if (jobs[t].reply_order[i] > d->reply_order_out[i]) {
+                    d->reply_order_out[i] = jobs[t].reply_order[i];
+                    d->reply_action_out[i] = jobs[t].reply_action[i];
+                }
+            free(jobs[t].reply_order);
+            free(jobs[t].reply_action);
         }
     }
     free(jobs);

@@ -18,14 +18,14 @@ LIB_PATH = ORACLE_DIR / "_build" / "liboracle.so"
 
 CONNECT4, BREAKTHROUGH, KNIGHTTHROUGH, OTHELLO, HEX11 = range(5)
 GAME_NAMES = ["connect4", "breakthrough", "knightthrough", "othello", "hex11"]
-UNIFORM, EPS_MAST, DECISIVE_WIN, DECISIVE_WINLOSS, DECISIVE_WINLOSSDRAW, DECISIVE_ANTI = range(6)
+UNIFORM, EPS_MAST, DECISIVE_WIN, DECISIVE_WINLOSS, DECISIVE_WINLOSSDRAW, DECISIVE_ANTI, EPS_LGR = range(7)
 NOT_TERMINAL, DRAW, WINNER_P0, WINNER_P1 = range(4)
 END_TERMINAL, END_TURN_LIMIT, END_NO_ACTIONS = range(3)
 OTHELLO_PASS = 64
 MAX_ACTIONS = 256
 
 STATE_DTYPE = np.dtype(
-    [("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("pad", "u1", (6,))], align=False
+    [("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("prev", "<u2"), ("pad", "u1", (4,))], align=False
 )
 RESULT_DTYPE = np.dtype([("wins", "<u4", (2,)), ("draws", "<u4"), ("cutoffs", "<u4"), ("sum_depth", "<u8")])
 STAT_DTYPE = np.dtype([("visits", "<u4"), ("score", "<i4")])
@@ -43,6 +43,10 @@ class BatchDesc(C.Structure):
         ("leaf_id_base", C.c_uint32),
         ("playouts_per_leaf", C.c_uint32),
         ("max_trace", C.c_uint32),
+        ("replies", C.c_void_p),
+        ("reply_order_out", C.c_void_p),
+        ("reply_action_out", C.c_void_p),
+        ("last_win_out", C.c_void_p),
     ]
 
 
@@ -208,6 +212,8 @@ def playout_batch(
     max_trace=0,
     want_final=False,
     threads=1,
+    replies: np.ndarray | None = None,
+    want_reply_updates=False,
 ):
     """Runs n_leaves*k playouts.  Returns a dict with results (+ optional amaf / mast_delta / trace /
     records / final)."""
@@ -221,6 +227,16 @@ def playout_batch(
     trace = np.zeros((n * k, max_trace), dtype=np.uint16) if want_trace else None
     rec = np.zeros(n * k, dtype=RECORD_DTYPE) if (want_trace or want_final) else None
     final = np.zeros(n * k, dtype=STATE_DTYPE) if want_final else None
+    reply_order = reply_action = last_win = None
+    if replies is not None:
+        replies = np.ascontiguousarray(replies, dtype=np.uint16)
+        assert replies.shape == (2, na)
+        d.replies = replies.ctypes.data
+    if want_reply_updates:
+        reply_order = np.zeros((2, na), dtype=np.uint64)
+        reply_action = np.zeros((2, na), dtype=np.uint16)
+        last_win = np.zeros((n, 2), dtype=np.uint32)
+        d.reply_order_out, d.reply_action_out, d.last_win_out = reply_order.ctypes.data, reply_action.ctypes.data, last_win.ctypes.data
     if mast is not None:
         mast = np.ascontiguousarray(mast, dtype=STAT_DTYPE)
         assert mast.shape == (2, na)
@@ -229,7 +245,8 @@ def playout_batch(
     )
     if rc != 0:
         raise RuntimeError(f"orc_playout_batch failed: {rc}")
-    return {"results": results, "amaf": amaf, "mast_delta": delta, "trace": trace, "records": rec, "final": final}
+    return {"results": results, "amaf": amaf, "mast_delta": delta, "trace": trace, "records": rec, "final": final,
+            "reply_order": reply_order, "reply_action": reply_action, "last_win": last_win}
 
 
 def search(game, root, *, iterations, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,

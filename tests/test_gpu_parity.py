@@ -192,6 +192,59 @@ def test_anti_decisive_not_built_for_hex():
         assert "MR_ERR_UNSUPPORTED" in str(e.value)
 
 
+def _random_replies(game, leaves, seed, density):
+    """A reply table made of plausible replies: for a sample of (player, preceding action) keys, an action that was
+    legal for that player somewhere in uniform playouts of `leaves` (so that replies are often, not always, legal)."""
+    rng = np.random.default_rng(seed)
+    na = o.num_actions(game)
+    ref = o.playout_batch(game, leaves, 8, seed=seed, want_trace=True, max_trace=MAX_TRACE[game], max_depth=MAX_TRACE[game])
+    table = np.zeros((2, na), dtype=np.uint16)
+    aid = (lambda a: (a >> 8) * 64 + (a & 0xFF)) if game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH) else (lambda a: a)
+    for li in range(len(leaves)):
+        for j in range(8):
+            d = int(ref["records"][li * 8 + j]["depth"])
+            tr = ref["trace"][li * 8 + j]
+            for t in range(1, d):
+                if rng.random() < density:
+                    p = (int(leaves[li]["turn"]) + t) & 1
+                    table[p, aid(int(tr[t - 1]))] = int(tr[t]) + 1
+    return table
+
+
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO])
+@pytest.mark.parametrize("eps", [0.1, 0.0])
+def test_last_good_reply_bit_exact(game, eps):
+    """EpsilonGreedy<Lgr<Uniform>> (simulate.rs:936-1033): traces, records and final states per playout, and the
+    batch's reply-table updates (backprop.rs:908-923) as last-winning-occurrence stamps."""
+    leaves = _leaves(game, n_per=5)
+    # playout()'s prev_action: the move that led to the leaf -- some move of the player who is NOT to move
+    prevs = _random_replies(game, leaves, 3, 1.0)
+    by_player = [prevs[p][prevs[p] > 0] for p in range(2)]  # prevs[p] holds actions made by player p (+1)
+    for i in range(len(leaves)):
+        other = by_player[1 - int(leaves[i]["turn"])]
+        leaves["prev"][i] = 0 if i % 3 == 0 else other[i % len(other)]
+    depth = 200 if game == o.KNIGHTTHROUGH else 0
+    for density, k in ((0.0, 33), (0.3, 64), (1.0, 20)):
+        table = _random_replies(game, leaves, 5, density)
+        mt = MAX_TRACE[game]
+        ref = o.playout_batch(game, leaves, k, policy=o.EPS_LGR, eps=eps, seed=77, max_depth=depth, replies=table,
+                              want_reply_updates=True, want_trace=True, max_trace=mt, want_final=True, threads=o.host_threads())
+        with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyLgr(eps), seed=77, max_playout_depth=depth) as g:
+            g.set_replies(table)
+            got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, want_trace=True, want_final=True, max_trace=mt)
+        assert (got.records["depth"] == ref["records"]["depth"]).all()
+        assert (got.records["outcome"] == ref["records"]["outcome"]).all()
+        assert (got.trace == ref["trace"]).all()
+        assert got.final.tobytes() == ref["final"].tobytes()
+        assert got.results.tobytes() == ref["results"].tobytes()
+        assert (got.reply_updates["order"] == ref["reply_order"]).all()
+        assert (got.reply_updates["action_plus1"] == ref["reply_action"]).all()
+        assert (got.last_win == ref["last_win"]).all()
+        if density == 1.0 and eps == 0.0:
+            uni = o.playout_batch(game, leaves, k, policy=o.UNIFORM, seed=77, max_depth=depth)
+            assert got.results.tobytes() != uni["results"].tobytes()  # replies were actually played
+
+
 def test_reference_shaped_playout_call():
     """SimulateStrategy::playout(state, max_playout_depth, stats, prev_action, rng) -> Trial"""
     game = o.CONNECT4
