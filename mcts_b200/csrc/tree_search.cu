@@ -8,6 +8,8 @@
 //   backprop ........... backprop.rs:704-731 with ChildArray::update / NodeStats::update (node.rs:295-302,673-681)
 //                        summed over the k trials of a leaf (exact: utilities are +1 / 0 / -1)
 //   AMAF ............... select/amaf.rs:48-86 over per-edge AMAF rows written by update_amaf, backprop.rs:565-617
+//   LGR table .......... TreeStats.player_replies, last write wins over (trial, ply) order (backprop.rs:908-923): the
+//                        kernel's stamps for the playout part, the tree-path pairs added here
 //   MAST table ......... TreeStats.player_actions, written for playout trace AND tree path (backprop.rs:833-870)
 //   final move ......... RobustChild: (visits, expected score) lexicographic max, select/basic.rs:13-45
 // The tree (arena, edge statistics in the parent's child arrays, root_stats) stays on the host; only the
@@ -144,6 +146,7 @@ struct Search {
     const mr_search_desc *d;
     Tree t;
     std::vector<mr_action_stat> mast; // [2][NA], TreeStats.player_actions
+    std::vector<uint16_t> replies;    // [2][NA], TreeStats.player_replies: 1 + reply code by (player, preceding action id)
     int na;
     // TreeStats.grave (search/shared.rs:52): per reference-node state, per player, per action.  The reference keys
     // it by node.hash; here the key is the full state record (no collisions), so equal states share one table.
@@ -358,6 +361,34 @@ struct Search {
         }
     }
 
+    // backprop.rs:908-923 for one batch.  A trial writes replies[p][prev] = action for every consecutive pair of its
+    // chronological action list (tree path, then playout) whose second action was made by a player p that did not
+    // lose the trial; later writes win.  `upd` holds, per key, the last such write among the PLAYOUT pairs of the
+    // batch (order = ((g + 1) << 13) | (4096 + ply), g = leaf * k + playout).  The tree-path pairs of leaf b are
+    // written by every trial of b that p did not lose -- last of them playout last_win[b][p] - 1 -- before that
+    // trial's playout pairs: order ((g + 1) << 13) | depth index.
+    void merge_replies(const std::vector<std::vector<PathEntry>> &paths, uint32_t nb, uint32_t k,
+                       std::vector<mr_reply_update> &upd, const std::vector<uint32_t> &last_win) {
+        for (uint32_t b = 0; b < nb; ++b) {
+            const std::vector<PathEntry> &path = paths[b];
+            for (size_t i = 2; i < path.size(); ++i) {
+                const Node &grand = t.nodes[path[i - 2].node], &parent = t.nodes[path[i - 1].node];
+                const int p = parent.player;
+                const uint32_t lw = last_win[(size_t)b * 2 + p];
+                if (lw == 0) continue;
+                const uint16_t prev = t.action[grand.first + path[i - 1].idx], act = t.action[parent.first + path[i].idx];
+                const uint64_t order = ((((uint64_t)b * k + (lw - 1)) + 1) << 13) | (uint64_t)std::min<size_t>(i, 4095);
+                mr_reply_update &u = upd[(size_t)p * na + mr_host::action_id(t.game, prev)];
+                if (order > u.order) {
+                    u.order = order;
+                    u.action_plus1 = (uint16_t)(act + 1);
+                }
+            }
+        }
+        for (size_t i = 0; i < upd.size(); ++i)
+            if (upd[i].order) replies[i] = upd[i].action_plus1;
+    }
+
     // k trials of one leaf, aggregated
     void backprop(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k, const mr_action_stat *amaf) {
         const int64_t nonzero = (int64_t)k - r.draws;
@@ -418,6 +449,10 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     s.t.game = (int)desc->game;
     s.na = mr_num_actions((int)desc->game);
     if (desc->policy == MR_EPS_MAST) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
+    const bool lgr = desc->policy == MR_EPS_LGR;
+    if (lgr) s.replies.assign((size_t)2 * s.na, 0);
+    std::vector<mr_reply_update> reply_upd(lgr ? (size_t)2 * s.na : 0);
+    std::vector<uint32_t> last_win(lgr ? (size_t)2 * desc->batch_leaves : 0);
     s.t.nodes.reserve(desc->max_iterations + 16);
     s.t.use_table = (desc->flags & MR_SEARCH_TRANSPOSITIONS) != 0;
     s.t.add_node(*root);
@@ -466,6 +501,15 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
             s.select(first + b, bb.paths[b]);
             if (k > 1) s.add_path_virtual_loss(bb.paths[b], k - 1);
             bb.leaves[b] = s.t.nodes[bb.paths[b].back().node].state;
+            if (lgr && bb.paths[b].size() > 1) { // playout()'s prev_action: the last edge of the descent (shared.rs:763-778)
+                const std::vector<PathEntry> &path = bb.paths[b];
+                const Node &parent = s.t.nodes[path[path.size() - 2].node];
+                bb.leaves[b].prev_action_plus1 = (uint16_t)(s.t.action[parent.first + path.back().idx] + 1);
+            }
+        }
+        if (lgr) {
+            int rc = mr_set_replies(ctx, (int)desc->game, s.replies.data());
+            if (rc != MR_OK) return rc;
         }
         st.seconds_select += now_s() - t0;
         mr_batch_desc bd;
@@ -487,7 +531,12 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         int rc = mr_wait(ctx, slot, bb.results.data(), want_amaf ? bb.amaf.data() : nullptr,
                          bb.delta.empty() ? nullptr : bb.delta.data(), nullptr, nullptr, nullptr);
         if (rc != MR_OK) return rc;
+        if (lgr) {
+            rc = mr_reply_updates(ctx, slot, reply_upd.data(), last_win.data());
+            if (rc != MR_OK) return rc;
+        }
         const double t1 = now_s();
+        if (lgr) s.merge_replies(bb.paths, bb.nb, k, reply_upd, last_win);
         for (uint32_t b = 0; b < bb.nb; ++b) {
             s.backprop(bb.paths[b], bb.results[b], k, want_amaf ? bb.amaf.data() + (size_t)b * 2 * s.na : nullptr);
             st.playout_plies += bb.results[b].sum_depth;

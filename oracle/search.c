@@ -14,6 +14,8 @@
  *   backprop .............. backprop.rs:686-731; NodeStats/ChildArray update node.rs:295-302, 673-681
  *   GLOBAL (MAST) write ... backprop.rs:833-870 (playout trace + tree path)
  *   final action .......... RobustChild select/basic.rs:13-45 through core.rs:138-198
+ *   LGR table ............. TreeStats.player_replies, backprop.rs:908-923 (tree-path pairs and playout pairs of every
+ *                           trial a player did not lose, last write wins)
  *   GRAVE ................. select/rave.rs:60-75 (beta), :157-184 (get_ref), :196-230 (score); tables written by
  *                           update_grave, backprop.rs:619-640, with amaf_actions grown per :833-854
  *
@@ -365,6 +367,16 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     const int na = orc_num_actions(c->game);
     orc_action_stat *mast = c->policy == ORC_EPS_MAST ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
     orc_action_stat *delta = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    const int lgr = c->policy == ORC_EPS_LGR;
+    uint16_t *replies = lgr ? (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t)) : NULL;
+    uint64_t *upd_order[2] = {NULL, NULL};
+    uint16_t *upd_action[2] = {NULL, NULL};
+    uint32_t *last_win[2] = {NULL, NULL};
+    for (int q = 0; q < 2 && lgr; ++q) {
+        upd_order[q] = (uint64_t *)calloc((size_t)2 * na, sizeof(uint64_t));
+        upd_action[q] = (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t));
+        last_win[q] = (uint32_t *)calloc((size_t)2 * c->batch_leaves, sizeof(uint32_t));
+    }
     const int max_path = 1024;
     entry_t *paths = (entry_t *)malloc(sizeof(entry_t) * (size_t)B * max_path);
     int *plen = (int *)malloc(sizeof(int) * B);
@@ -413,7 +425,15 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                 for (int i = 1; i < set_plen[slot][b]; ++i) /* add_path_virtual_loss(k - 1), shared.rs:787-805 */
                     t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
                 leaves[b] = t.nodes[path[set_plen[slot][b] - 1].node].state;
+                if (lgr && set_plen[slot][b] > 1) { /* playout()'s prev_action: the last edge of the descent */
+                    int L = set_plen[slot][b];
+                    leaves[b].prev_plus1 = (uint16_t)(t.action[t.nodes[path[L - 2].node].first + path[L - 1].idx] + 1);
+                }
             }
+            bd.replies = replies; /* frozen for the batch: the playouts run before anything below is merged */
+            bd.reply_order_out = lgr ? upd_order[slot] : NULL;
+            bd.reply_action_out = lgr ? upd_action[slot] : NULL;
+            bd.last_win_out = lgr ? last_win[slot] : NULL;
             bd.leaf_id_base = done;
             if (set_delta[slot]) memset(set_delta[slot], 0, sizeof(orc_action_stat) * 2 * (size_t)na);
             if (set_amaf[slot]) memset(set_amaf[slot], 0, sizeof(orc_action_stat) * (size_t)nb * 2 * na);
@@ -431,6 +451,26 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
         } else {
             if (slot < 0) break;
             apply = slot;
+        }
+        if (lgr) { /* backprop.rs:908-923 over the whole batch: tree-path pairs join the playout stamps, then one write per key */
+            for (uint32_t b = 0; b < set_nb[apply]; ++b) {
+                const entry_t *path = set_paths[apply] + (size_t)b * max_path;
+                for (int i = 2; i < set_plen[apply][b]; ++i) {
+                    const node_t *grand = &t.nodes[path[i - 2].node], *parent = &t.nodes[path[i - 1].node];
+                    int p = parent->player;
+                    uint32_t lw = last_win[apply][(size_t)b * 2 + p];
+                    if (lw == 0) continue;
+                    uint16_t prev = t.action[grand->first + path[i - 1].idx], act = t.action[parent->first + path[i].idx];
+                    uint64_t order = ((((uint64_t)b * k + (lw - 1)) + 1) << 13) | (uint64_t)(i < 4095 ? i : 4095);
+                    size_t key = (size_t)p * na + action_id(c->game, prev);
+                    if (order > upd_order[apply][key]) {
+                        upd_order[apply][key] = order;
+                        upd_action[apply][key] = (uint16_t)(act + 1);
+                    }
+                }
+            }
+            for (int i = 0; i < 2 * na; ++i)
+                if (upd_order[apply][i]) replies[i] = upd_action[apply][i];
         }
         for (uint32_t b = 0; b < set_nb[apply]; ++b) {
             const entry_t *path = set_paths[apply] + (size_t)b * max_path;
@@ -569,6 +609,12 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     free(grave.tabs);
     free(grave.states);
     free(grave.slots);
+    free(replies);
+    for (int q = 0; q < 2; ++q) {
+        free(upd_order[q]);
+        free(upd_action[q]);
+        free(last_win[q]);
+    }
     free(amaf);
     free(below_a);
     free(below_p);

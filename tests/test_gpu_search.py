@@ -114,6 +114,27 @@ def test_amaf_search_bit_exact(game, policy, iters, batch, k, alpha):
     assert (got.children["visits"] > 0).sum() > 3
 
 
+@pytest.mark.parametrize("game,iters,batch,k,pipelined", [
+    (o.CONNECT4, 4096, 32, 4, False),       # strategy.rs:130-143 `Ucb1Lgr`: UCB1 + EpsilonGreedy<Lgr<Uniform>>
+    (o.BREAKTHROUGH, 2048, 64, 8, False),
+    (o.KNIGHTTHROUGH, 1024, 16, 16, True),  # pipelined: batch N+1 plays with the table as of batch N-1
+    (o.OTHELLO, 1024, 1, 1, False),         # the reference's sequential loop: every trial sees every earlier write
+])
+def test_lgr_search_bit_exact(game, iters, batch, k, pipelined):
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), mb.EpsilonGreedyLgr(0.1), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      max_playout_depth=200, pipelined=pipelined, seed=33) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_LGR, eps=0.1, seed=33,
+                                     threads=o.host_threads(), max_depth=200, pipelined=pipelined)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    # the table changes the playouts: same search with plain uniform rollouts over the same pair-draw stream differs
+    _, uni_children, uni_plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_LGR, eps=1.0,
+                                          seed=33, threads=o.host_threads(), max_depth=200, pipelined=pipelined)
+    assert uni_plies != plies
+
+
 def test_flat_monte_carlo_one_batch():
     from mcts_b200.search import flat_monte_carlo
 
