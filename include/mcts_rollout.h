@@ -64,7 +64,7 @@ enum mr_game {
 /* Simulation policies (the SimulateStrategy implementors in scope). */
 enum mr_policy {
     MR_UNIFORM = 0,     /* simulate.rs:157-216  Uniform */
-    MR_EPS_MAST = 1,    /* simulate.rs:485-570 + 819-848  EpsilonGreedy<G, Mast> */
+    MR_EPS_MAST = 1,    /* simulate.rs:485-570 + 819-848  EpsilonGreedy<G, Mast>; every game but Hex */
     MR_DECISIVE_WIN = 2, /* simulate.rs:573-760  DecisiveMove<G, Uniform>, mode Win */
     /* modes WinLoss and WinLossDraw (simulate.rs:645-669).  For Connect4, Breakthrough, Knightthrough and Othello
      * a move can only end the game in the mover's favour, or as the single remaining action, so all three modes

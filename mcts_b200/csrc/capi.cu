@@ -116,6 +116,7 @@ struct mr_ctx {
     // MAST snapshot as rank bit-planes (copied into KernelParams at launch)
     uint64_t mast_planes[2][MAST_KINDS][MAST_BITS] = {};
     uint32_t mast_nbits[2] = {0, 0};
+    uint16_t mast_rank_small[2][8] = {};
     int mast_game = -1;
     // Last Good Reply table (mr_set_replies), [2][num_actions] of its game
     std::vector<uint16_t> replies;
@@ -183,6 +184,7 @@ kernel_fn pick_kernel(int game, int policy, int v) {
     switch (game) {
     case MR_CONNECT4:
         if (policy == MR_UNIFORM) return pick_variant<Connect4, MR_UNIFORM>(v);
+        if (policy == MR_EPS_MAST) return pick_variant<Connect4, MR_EPS_MAST>(v);
         if (policy == MR_DECISIVE_WIN) return pick_variant<Connect4, MR_DECISIVE_WIN>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Connect4, MR_DECISIVE_ANTI>(v);
         if (policy == MR_EPS_LGR) return pick_variant<Connect4, MR_EPS_LGR>(v);
@@ -204,6 +206,7 @@ kernel_fn pick_kernel(int game, int policy, int v) {
     case MR_OTHELLO:
         // DecisiveMove<Win> provably never changes an Othello pick, so it shares the kernel
         if (policy == MR_UNIFORM || policy == MR_DECISIVE_WIN) return pick_variant<Othello, MR_UNIFORM>(v);
+        if (policy == MR_EPS_MAST) return pick_variant<Othello, MR_EPS_MAST>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Othello, MR_DECISIVE_ANTI>(v);
         if (policy == MR_EPS_LGR) return pick_variant<Othello, MR_EPS_LGR>(v);
         return nullptr;
@@ -239,12 +242,25 @@ int through_dst(int game, int player, int src, int kind) {
     return (r < 0 || r > 7 || c < 0 || c > 7) ? -1 : r * 8 + c;
 }
 
+// (player, cell, kind) -> dense action id of the MAST table, -1 when there is no such action.  Breakthrough /
+// Knightthrough: cell = source square, kind = move kind.  Othello: cell = square, one kind (PASS is always forced).
+// Connect4: cell = column.
+int mast_action_id(int game, int player, int cell, int kind) {
+    if (game == MR_BREAKTHROUGH || game == MR_KNIGHTTHROUGH) {
+        const int dst = through_dst(game, player, cell, kind);
+        return dst < 0 ? -1 : cell * 64 + dst;
+    }
+    if (game == MR_OTHELLO) return kind == 0 ? cell : -1;
+    if (game == MR_CONNECT4) return (kind == 0 && cell < 7) ? cell : -1;
+    return -1;
+}
+
 int compute_mast_planes(mr_ctx *ctx, int game, const mr_action_stat *mast) {
-    if (game != MR_BREAKTHROUGH && game != MR_KNIGHTTHROUGH)
-        return fail(ctx, MR_ERR_UNSUPPORTED, "MAST snapshots are supported for Breakthrough / Knightthrough only");
+    if (game == MR_HEX11) return fail(ctx, MR_ERR_UNSUPPORTED, "no MAST policy is built for Hex");
     const int na = kGames[game].num_actions;
-    const int kinds = game == MR_BREAKTHROUGH ? 3 : 8;
+    const int kinds = game == MR_BREAKTHROUGH ? 3 : (game == MR_KNIGHTTHROUGH ? 8 : 1);
     memset(ctx->mast_planes, 0, sizeof ctx->mast_planes);
+    memset(ctx->mast_rank_small, 0, sizeof ctx->mast_rank_small);
     for (int pl = 0; pl < 2; ++pl) {
         const mr_action_stat *tab = mast + (size_t)pl * na;
         // distinct values over the REAL actions of this player only (ids that no move can produce are ignored)
@@ -252,9 +268,9 @@ int compute_mast_planes(mr_ctx *ctx, int game, const mr_action_stat *mast) {
         vals.push_back({1, 1});
         for (int src = 0; src < 64; ++src)
             for (int q = 0; q < kinds; ++q) {
-                const int dst = through_dst(game, pl, src, q);
-                if (dst < 0) continue;
-                const mr_action_stat &e = tab[src * 64 + dst];
+                const int id = mast_action_id(game, pl, src, q);
+                if (id < 0) continue;
+                const mr_action_stat &e = tab[id];
                 if (e.visits >= (1u << 26))
                     return fail(ctx, MR_ERR_INVALID, "MAST visits %u >= 2^26: exact score comparison not guaranteed", e.visits);
                 if (e.visits > 0) vals.push_back({(int64_t)e.score, (int64_t)e.visits});
@@ -271,12 +287,13 @@ int compute_mast_planes(mr_ctx *ctx, int game, const mr_action_stat *mast) {
         const uint32_t unvisited = rank_of({1, 1});
         for (int src = 0; src < 64; ++src)
             for (int q = 0; q < kinds; ++q) {
-                const int dst = through_dst(game, pl, src, q);
-                if (dst < 0) continue;
-                const mr_action_stat &e = tab[src * 64 + dst];
+                const int id = mast_action_id(game, pl, src, q);
+                if (id < 0) continue;
+                const mr_action_stat &e = tab[id];
                 const uint32_t rk = e.visits > 0 ? rank_of({(int64_t)e.score, (int64_t)e.visits}) : unvisited;
                 for (uint32_t b = 0; b < nbits; ++b)
                     if ((rk >> b) & 1u) ctx->mast_planes[pl][q][b] |= 1ull << src;
+                if (game == MR_CONNECT4) ctx->mast_rank_small[pl][src] = (uint16_t)rk;
             }
     }
     ctx->mast_game = game;
@@ -374,6 +391,7 @@ void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, co
         memcpy(kp.mast_planes, ctx->mast_planes, sizeof kp.mast_planes);
         kp.mast_nbits[0] = ctx->mast_nbits[0];
         kp.mast_nbits[1] = ctx->mast_nbits[1];
+        memcpy(kp.mast_rank_small, ctx->mast_rank_small, sizeof kp.mast_rank_small);
     }
     kp.n_leaves = d->n_leaves;
     kp.k = d->playouts_per_leaf;

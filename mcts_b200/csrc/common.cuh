@@ -58,6 +58,7 @@ struct KernelParams {
     // pick is then a bit-sliced arg-max over the legal-move masks, with no table lookups at all.
     uint64_t mast_planes[2][MAST_KINDS][MAST_BITS];
     uint32_t mast_nbits[2];
+    uint16_t mast_rank_small[2][8]; // Connect4: the same dense ranks, one per column, read directly
     uint16_t *trace_scratch;   // [resident warps][trace_cap][32] u16, MAST-delta staging
     uint32_t trace_cap;
     // Last Good Reply (MR_EPS_LGR): frozen reply table in, last-winning-occurrence stamps out

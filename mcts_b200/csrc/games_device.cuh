@@ -24,6 +24,14 @@ __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) { return __umu
 __device__ __forceinline__ uint64_t add_disjoint(uint64_t a, uint64_t b) { return mk64(lo32(a) + lo32(b), hi32(a) + hi32(b)); }
 __device__ __forceinline__ uint64_t sub_subset(uint64_t a, uint64_t b) { return mk64(lo32(a) - lo32(b), hi32(a) - hi32(b)); }
 
+// visiting rank j of list position i in random_best's order i = (i0 + j*stride) mod n (util.rs:147-161):
+// j = ((i - i0) mod n) * stride^-1 mod n
+__device__ __forceinline__ uint32_t visiting_rank(uint32_t i, uint32_t i0, uint32_t n, uint32_t inv, uint32_t rcp) {
+    const uint32_t d = i >= i0 ? i - i0 : i + n - i0;
+    const uint32_t t = d * inv;
+    return t - __umulhi(t, rcp) * n;
+}
+
 // Position of the idx-th (0-based) set bit of a 32-bit word, by binary search on popcounts.
 __device__ __forceinline__ uint32_t select32(uint32_t w, uint32_t idx) {
     uint32_t pos = 0;
@@ -190,6 +198,26 @@ struct Connect4 {
         } else if (POLICY == MR_EPS_LGR) {
             // the recorded reply column, if it is still open (simulate.rs:1022-1026)
             bit = (lgr_reply && lgr_reply <= 7u) ? (moves & (0xFFull << (8u * (lgr_reply - 1u)))) : 0ull;
+        } else if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+            // Mast::select_move (simulate.rs:824-848) = random_best over the open columns: the first strict maximum in
+            // visiting order, i.e. the largest (rank, -visiting rank) key.  At most 7 actions: every column is scored.
+            const uint32_t pl = (sh.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
+            const uint32_t r = mulhi(x0, 16u * n_open);
+            const uint32_t i0 = r >> 4, inv = MR_STRIDE_INV[n_open][r & 15u], rcp = MR_RCP32[n_open];
+            uint32_t best_key = 0, i = 0;
+            bit = 0;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                const uint64_t b = moves & (0xFFull << (8 * c));
+                if (b) {
+                    const uint32_t key = ((uint32_t)p.mast_rank_small[pl][c] << 8) | (255u - visiting_rank(i, i0, n_open, inv, rcp));
+                    if (key >= best_key) { // keys of open columns are distinct; >= lets a zero key win the first time
+                        best_key = key;
+                        bit = b;
+                    }
+                    ++i;
+                }
+            }
         } else {
             bit = 0;
         }
@@ -433,13 +461,6 @@ __device__ __forceinline__ void mast_argmax(uint64_t cand[KINDS], const uint64_t
             for (int q = 0; q < KINDS; ++q) cand[q] = t[q];
         }
     }
-}
-
-// visiting rank j of list position i: i = (i0 + j*stride) mod n  <=>  j = ((i - i0) mod n) * stride^-1 mod n
-__device__ __forceinline__ uint32_t visiting_rank(uint32_t i, uint32_t i0, uint32_t n, uint32_t inv, uint32_t rcp) {
-    const uint32_t d = i >= i0 ? i - i0 : i + n - i0;
-    const uint32_t t = d * inv;
-    return t - __umulhi(t, rcp) * n;
 }
 
 template <int POLICY, int PARITY>
@@ -856,6 +877,12 @@ struct Othello {
     __device__ static uint64_t flips(uint64_t mv, uint64_t P, uint64_t O) {
         return flips_left(mv, P, O) | brev64(flips_left(brev64(mv), brev64(P), brev64(O)));
     }
+    // position of the idx-th set bit of a 64-bit mask
+    __device__ static uint32_t select64(uint64_t w, uint32_t idx) {
+        const uint32_t nlo = __popc(lo32(w));
+        const bool in_hi = idx >= nlo;
+        return select32(in_hi ? hi32(w) : lo32(w), in_hi ? idx - nlo : idx) + (in_hi ? 32u : 0u);
+    }
     __device__ static int count_outcome(uint64_t b, uint64_t w) {
         const int nb = __popcll(b), nw = __popcll(w);
         return nb > nw ? MR_WINNER_P0 : (nb < nw ? MR_WINNER_P1 : MR_DRAW);
@@ -929,6 +956,35 @@ struct Othello {
                 }
             }
         }
+        if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+            // Mast::select_move (simulate.rs:824-848): bit-sliced arg-max of the rank planes over the legal squares,
+            // then random_best's visiting order among the maximal ones (as for Breakthrough, with one move kind)
+            const uint32_t pl = is_white ? 1u : 0u;
+            uint64_t cand[1] = {moves};
+            mast_argmax<1>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
+            const uint32_t m = __popcll(cand[0]);
+            const uint32_t r = mulhi(x0, 16u * n);
+            const uint32_t i0 = r >> 4;
+            if (m == 1) {
+                sq = (uint32_t)__ffsll((long long)cand[0]) - 1u;
+            } else if (m == n) { // every legal square is maximal (e.g. an empty table): list position i0
+                sq = select64(moves, i0);
+            } else {
+                const uint32_t inv = MR_STRIDE_INV[n][r & 15u], rcp = MR_RCP32[n];
+                uint32_t best_j = 0xffffffffu;
+                for (uint64_t cells = cand[0]; cells; cells &= cells - 1) {
+                    const uint32_t s0 = (uint32_t)__ffsll((long long)cells) - 1u;
+                    const uint32_t j = visiting_rank((uint32_t)__popcll(moves & ((1ull << s0) - 1ull)), i0, n, inv, rcp);
+                    if (j < best_j) {
+                        best_j = j;
+                        sq = s0;
+                    }
+                }
+            }
+            mv = bit64(sq);
+            fl = flips(mv, P, O);
+            have = true;
+        }
         if (POLICY == MR_EPS_LGR && lgr_reply && lgr_reply <= 64u && ((moves >> (lgr_reply - 1u)) & 1ull)) {
             // the recorded reply square, if legal now (a recorded PASS is legal exactly when it is the only action,
             // handled above)
@@ -938,10 +994,7 @@ struct Othello {
             have = true;
         }
         if (!have) {
-            uint32_t idx = mulhi(x0, n);
-            const uint32_t nlo = __popc(lo32(moves));
-            const bool in_hi = idx >= nlo;
-            sq = select32(in_hi ? hi32(moves) : lo32(moves), in_hi ? idx - nlo : idx) + (in_hi ? 32u : 0u);
+            sq = select64(moves, mulhi(x0, n));
             mv = bit64(sq);
             fl = flips(mv, P, O);
         }

@@ -120,7 +120,7 @@ def test_terminal_and_stuck_leaves():
     _compare(o.OTHELLO, o.UNIFORM, must_pass, 4, seed=3)
 
 
-@pytest.mark.parametrize("game", [o.BREAKTHROUGH, o.KNIGHTTHROUGH])
+@pytest.mark.parametrize("game", [o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.CONNECT4, o.OTHELLO])
 @pytest.mark.parametrize("eps", [0.1, 0.0, 1.0])
 def test_eps_mast_bit_exact(game, eps):
     leaves = _leaves(game, n_per=3)
@@ -349,10 +349,10 @@ def test_randomized_differential_sweep():
     every playout's trace, record, final state and every aggregate compared bit for bit."""
     rng = np.random.default_rng(20260101)
     policies = {
-        o.CONNECT4: [o.UNIFORM, o.DECISIVE_WIN, o.DECISIVE_ANTI],
+        o.CONNECT4: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI],
         o.BREAKTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI],
         o.KNIGHTTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WINLOSS, o.DECISIVE_ANTI],
-        o.OTHELLO: [o.UNIFORM, o.DECISIVE_WINLOSSDRAW, o.DECISIVE_ANTI],
+        o.OTHELLO: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WINLOSSDRAW, o.DECISIVE_ANTI],
         o.HEX11: [o.UNIFORM],
     }
     max_plies = {o.CONNECT4: 30, o.BREAKTHROUGH: 50, o.KNIGHTTHROUGH: 30, o.OTHELLO: 56, o.HEX11: 100}

@@ -15,6 +15,8 @@ CASES = [
     (o.CONNECT4, o.DECISIVE_WIN, 2048, 32, 4, 1, 1, 0),  # UCB1-Tuned + QInit::Infinity (Ucb1TunedDM)
     (o.BREAKTHROUGH, o.EPS_MAST, 2048, 32, 16, 0, 0, 200),  # MAST table fed by kernel delta + tree path
     (o.KNIGHTTHROUGH, o.EPS_MAST, 1024, 64, 8, 0, 0, 200),
+    (o.CONNECT4, o.EPS_MAST, 2048, 32, 8, 0, 0, 0),    # Ucb1Mast (strategy.rs:98-111) on the games without move kinds
+    (o.OTHELLO, o.EPS_MAST, 1024, 16, 8, 0, 0, 0),
     (o.OTHELLO, o.DECISIVE_WIN, 1024, 32, 4, 1, 1, 0),
     (o.HEX11, o.UNIFORM, 1024, 64, 4, 0, 0, 0),
 ]
