@@ -60,6 +60,7 @@ struct Connect4 {
     // windows unrolled: measured 6-7% faster than a rolled window for this small step (profiles/roll_compare_r01.txt)
     static constexpr bool ROLLED = false;
     static constexpr int MIN_BLOCKS = 1; // a 64-register cap (8 blocks/SM) measured 4% slower
+    static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
     static constexpr int NSLOTS = 7; // compact per-player statistic slots (== action ids here)
     static constexpr bool MASK_AMAF = false;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
@@ -332,6 +333,8 @@ struct ThroughBase {
 struct Breakthrough : ThroughBase {
     static constexpr bool ROLLED = false;
     static constexpr int MIN_BLOCKS = 6; // <= 80 registers: 24 warps/SM instead of 20, +4.7% on the MAST kernel (measured)
+    // the MAST kernel gains another 5% at 7 blocks/SM (<= 72 registers); the uniform kernel does not (measured)
+    static constexpr int min_blocks(int policy) { return policy == MR_EPS_MAST ? 7 : MIN_BLOCKS; }
     static constexpr int NSLOTS = 192; // src*3 + kind (W,F,E)
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
         const uint32_t src = slot / 3u, kind = slot - src * 3u;
@@ -396,7 +399,8 @@ struct Breakthrough : ThroughBase {
 //   pieces, src ascending then dst ascending, i.e. jump deltas in the order -17,-15,-10,-6,+6,+10,+15,+17.
 // ==========================================================================================
 struct Knightthrough : ThroughBase {
-    static constexpr int MIN_BLOCKS = 5; // <= 96 registers: +13% on the MAST kernel (measured)
+    static constexpr int MIN_BLOCKS = 5; // <= 96 registers: +13% on the MAST kernel (measured); 4 and 6 are within noise of it
+    static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
     static constexpr bool ROLLED = true; // the step is large (8 masks, adder tree): a rolled window fits the I-cache (+14%)
     static constexpr int NSLOTS = 512; // src*8 + kind (ascending-dst jump order)
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
@@ -821,6 +825,7 @@ struct Othello {
     // with the ply's parity a run-time value, so the kernel fits the instruction cache.
     static constexpr bool ROLLED = true;
     static constexpr int MIN_BLOCKS = 1; // a register cap (6 blocks/SM, 80 regs) measured no faster on B200
+    static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
 
     struct Shared {
         uint64_t black, white;

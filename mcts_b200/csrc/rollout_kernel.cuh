@@ -52,7 +52,7 @@ __device__ __forceinline__ void flush_stat_table(uint32_t *tab, mr_action_stat *
 }
 
 template <class G, int POLICY, int FLAGS>
-__global__ void __launch_bounds__(THREADS_PER_BLOCK, G::MIN_BLOCKS) rollout_kernel(const KernelParams p) {
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) rollout_kernel(const KernelParams p) {
     constexpr bool WANT_AMAF = (FLAGS & MR_WANT_AMAF) != 0;
     constexpr bool WANT_MAST = (FLAGS & MR_WANT_MAST_DELTA) != 0;
     constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
