@@ -80,7 +80,13 @@ enum mr_policy {
      * else a uniform pick.  Two draws per ply, as MR_EPS_MAST.  The reply table is frozen for the batch
      * (mr_set_replies); the batch's last-write-wins updates come back through mr_reply_updates.  Connect4,
      * Breakthrough, Knightthrough, Othello; needs a bounded playout (max_playout_depth) for Knightthrough. */
-    MR_EPS_LGR = 6
+    MR_EPS_LGR = 6,
+    /* DecisiveMove<G, EpsilonGreedy<G, Mast>> (mcts-tune SimulateSpec::DecisiveMoveMast, config_ir.rs): the decisive
+     * scan first, the epsilon-greedy MAST pick when it finds nothing.  Mode Win is the `ucb1_tuned_dm_mast` family,
+     * mode WinLoss the `rave` family (family_catalog.rs:470-514); as for the plain decisive policies the modes pick
+     * the same action in these games and share a kernel.  Two draws per ply, as MR_EPS_MAST.  Not for Hex. */
+    MR_DECISIVE_MAST_WIN = 7,
+    MR_DECISIVE_MAST_WINLOSS = 8
 };
 
 enum mr_flags {

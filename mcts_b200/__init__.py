@@ -8,6 +8,7 @@ from .search import GpuSearch, SearchResult
 from .rollout import (
     BatchResult,
     DecisiveMove,
+    DecisiveMoveMast,
     DecisiveMoveWin,
     EndType,
     EpsilonGreedyLgr,
@@ -28,7 +29,7 @@ from .rollout import (
 )
 
 __all__ = [
-    "BatchResult", "DecisiveMove", "DecisiveMoveWin", "EndType", "EpsilonGreedyLgr", "EpsilonGreedyMast", "Game", "GpuRollout", "MastTable", "Outcome",
+    "BatchResult", "DecisiveMove", "DecisiveMoveMast", "DecisiveMoveWin", "EndType", "EpsilonGreedyLgr", "EpsilonGreedyMast", "Game", "GpuRollout", "MastTable", "Outcome",
     "Policy", "Trial", "Uniform", "initial_state", "make_leaf", "num_actions", "LEAF_DTYPE", "RECORD_DTYPE",
     "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load", "GpuSearch", "SearchResult", "apply",
     "generate_actions", "terminal_status",

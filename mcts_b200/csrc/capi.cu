@@ -181,6 +181,7 @@ kernel_fn pick_hex(int v) { // Hex has its own fill-then-search kernel; no MAST 
 kernel_fn pick_kernel(int game, int policy, int v) {
     // WinLoss / WinLossDraw pick exactly what Win picks in the four games that have a decisive kernel
     if (policy == MR_DECISIVE_WINLOSS || policy == MR_DECISIVE_WINLOSSDRAW) policy = MR_DECISIVE_WIN;
+    if (policy == MR_DECISIVE_MAST_WINLOSS) policy = MR_DECISIVE_MAST_WIN;
     switch (game) {
     case MR_CONNECT4:
         if (policy == MR_UNIFORM) return pick_variant<Connect4, MR_UNIFORM>(v);
@@ -188,6 +189,7 @@ kernel_fn pick_kernel(int game, int policy, int v) {
         if (policy == MR_DECISIVE_WIN) return pick_variant<Connect4, MR_DECISIVE_WIN>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Connect4, MR_DECISIVE_ANTI>(v);
         if (policy == MR_EPS_LGR) return pick_variant<Connect4, MR_EPS_LGR>(v);
+        if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<Connect4, MR_DECISIVE_MAST>(v);
         return nullptr;
     case MR_BREAKTHROUGH:
         if (policy == MR_UNIFORM) return pick_variant<Breakthrough, MR_UNIFORM>(v);
@@ -195,6 +197,7 @@ kernel_fn pick_kernel(int game, int policy, int v) {
         if (policy == MR_DECISIVE_WIN) return pick_variant<Breakthrough, MR_DECISIVE_WIN>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Breakthrough, MR_DECISIVE_ANTI>(v);
         if (policy == MR_EPS_LGR) return pick_variant<Breakthrough, MR_EPS_LGR>(v);
+        if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<Breakthrough, MR_DECISIVE_MAST>(v);
         return nullptr;
     case MR_KNIGHTTHROUGH:
         if (policy == MR_UNIFORM) return pick_variant<Knightthrough, MR_UNIFORM>(v);
@@ -202,11 +205,13 @@ kernel_fn pick_kernel(int game, int policy, int v) {
         if (policy == MR_DECISIVE_WIN) return pick_variant<Knightthrough, MR_DECISIVE_WIN>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Knightthrough, MR_DECISIVE_ANTI>(v);
         if (policy == MR_EPS_LGR) return pick_variant<Knightthrough, MR_EPS_LGR>(v);
+        if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<Knightthrough, MR_DECISIVE_MAST>(v);
         return nullptr;
     case MR_OTHELLO:
         // DecisiveMove<Win> provably never changes an Othello pick, so it shares the kernel
         if (policy == MR_UNIFORM || policy == MR_DECISIVE_WIN) return pick_variant<Othello, MR_UNIFORM>(v);
-        if (policy == MR_EPS_MAST) return pick_variant<Othello, MR_EPS_MAST>(v);
+        // (the decisive scan never changes an Othello pick, so DecisiveMove<EpsilonGreedy<Mast>> is the MAST kernel)
+        if (policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN) return pick_variant<Othello, MR_EPS_MAST>(v);
         if (policy == MR_DECISIVE_ANTI) return pick_variant<Othello, MR_DECISIVE_ANTI>(v);
         if (policy == MR_EPS_LGR) return pick_variant<Othello, MR_EPS_LGR>(v);
         return nullptr;
@@ -340,8 +345,8 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
     if (d->flags & ~15u) return fail(ctx, MR_ERR_INVALID, "unknown flags 0x%x", d->flags);
     kernel_fn fn = pick_kernel((int)d->game, (int)d->policy, flag_variant(d->flags));
     if (!fn) return fail(ctx, MR_ERR_UNSUPPORTED, "policy %u is not built for game %u", d->policy, d->game);
-    if (d->policy == MR_EPS_MAST) {
-        if (!has_mast) return fail(ctx, MR_ERR_INVALID, "MR_EPS_MAST needs a MAST snapshot (mast_in / mr_set_mast)");
+    if (policy_uses_mast((int)d->policy)) {
+        if (!has_mast) return fail(ctx, MR_ERR_INVALID, "a MAST policy needs a MAST snapshot (mast_in / mr_set_mast)");
         if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
     }
     if (d->policy == MR_EPS_LGR) {
@@ -387,7 +392,7 @@ int plan_launch(mr_ctx *ctx, const Device &dv, kernel_fn fn, const mr_batch_desc
 
 void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, const LaunchPlan &lp, uint32_t trace_cap) {
     memset(&kp, 0, sizeof kp);
-    if (d->policy == MR_EPS_MAST) {
+    if (policy_uses_mast((int)d->policy)) {
         memcpy(kp.mast_planes, ctx->mast_planes, sizeof kp.mast_planes);
         kp.mast_nbits[0] = ctx->mast_nbits[0];
         kp.mast_nbits[1] = ctx->mast_nbits[1];
@@ -571,7 +576,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
     uint32_t trace_cap = 0;
     int rc = validate(ctx, desc, mast_in != nullptr, &fn, &trace_cap);
     if (rc != MR_OK) return rc;
-    if (desc->policy == MR_EPS_MAST) {
+    if (policy_uses_mast((int)desc->policy)) {
         rc = compute_mast_planes(ctx, (int)desc->game, mast_in);
         if (rc != MR_OK) return rc;
     }

@@ -11,6 +11,12 @@ namespace mr {
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int THREADS_PER_BLOCK = WARPS_PER_BLOCK * 32;
+// kernel-side name of DecisiveMove<EpsilonGreedy<Mast>>: the ABI's Win and WinLoss modes share one instantiation
+constexpr int MR_DECISIVE_MAST = MR_DECISIVE_MAST_WIN;
+__host__ __device__ constexpr bool policy_uses_mast(int policy) {
+    return policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN || policy == MR_DECISIVE_MAST_WINLOSS;
+}
+
 constexpr int MAST_KINDS = 8;  // move kinds per source cell: 3 (Breakthrough) or 8 (Knightthrough)
 constexpr int MAST_BITS = 10;  // <= 513 distinct score values over the <= 512 real actions of a player
 

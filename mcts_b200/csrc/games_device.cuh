@@ -169,7 +169,8 @@ struct Connect4 {
     __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         const uint64_t moves = (all + BOTTOM) & BOARD; // one bit per open column, ascending column order
         uint64_t bit;
-        if (POLICY == MR_DECISIVE_WIN) {
+        constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST;
+        if (POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_MAST) {
             // first legal column (ascending) whose drop wins for the mover (simulate.rs:662-670); a Connect4
             // move cannot lose immediately, a drawing move exists only as the 42nd stone (the single action)
             uint64_t winning = 0;
@@ -199,7 +200,10 @@ struct Connect4 {
         } else if (POLICY == MR_EPS_LGR) {
             // the recorded reply column, if it is still open (simulate.rs:1022-1026)
             bit = (lgr_reply && lgr_reply <= 7u) ? (moves & (0xFFull << (8u * (lgr_reply - 1u)))) : 0ull;
-        } else if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+        } else {
+            bit = 0;
+        }
+        if (MAST_INNER && bit == 0 && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
             // Mast::select_move (simulate.rs:824-848) = random_best over the open columns: the first strict maximum in
             // visiting order, i.e. the largest (rank, -visiting rank) key.  At most 7 actions: every column is scored.
             const uint32_t pl = (sh.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
@@ -219,8 +223,6 @@ struct Connect4 {
                     ++i;
                 }
             }
-        } else {
-            bit = 0;
         }
         if (bit == 0) {
             uint32_t idx = mulhi(x0, n_open);
@@ -478,8 +480,11 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
     const uint32_t n = __popcll(S) + 2u * __popcll(C);
     if (n == 0) return ST_NO_ACTIONS;
     uint32_t idx = 0, src = 0, dir = 0;
-    bool have = false;
-    if (POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI) {
+    bool have = false, idx_set = false;
+    // DecisiveMove<.., inner> first tries the decisive scan and falls through to its inner strategy (simulate.rs:742-760)
+    constexpr bool DECISIVE = POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI || POLICY == MR_DECISIVE_MAST;
+    constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST;
+    if (DECISIVE) {
         // DecisiveMove<Win> (simulate.rs:662-687): the first action in list order whose child is a win for the
         // mover.  A Breakthrough move wins iff it lands on the far wall, i.e. iff its source is on the row next
         // to it; no move can lose or draw on the spot, so the loser/draw fallbacks never fire.
@@ -513,10 +518,9 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
                     have = true;
                 }
             }
-        } else {
-            idx = mulhi(x0, n);
         }
-    } else if (POLICY == MR_EPS_LGR) {
+    }
+    if (POLICY == MR_EPS_LGR) {
         // the recorded reply, if it is legal now (simulate.rs:1022-1026); else the uniform pick
         idx = mulhi(x0, n);
         if (lgr_reply) {
@@ -531,7 +535,8 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
                 }
             }
         }
-    } else if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+    }
+    if (MAST_INNER && !have && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
         const uint32_t pl = is_white ? 1u : 0u;
         uint64_t cand[3] = {W, F, E};
         mast_argmax<3>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
@@ -547,6 +552,7 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
             const uint32_t i0 = r >> 4;
             if (m == n) {
                 idx = i0;
+                idx_set = true;
             } else if (m <= 6) {
                 // few maximal actions: the pick is the one with the smallest visiting rank
                 const uint32_t pk = r & 15u;
@@ -595,9 +601,8 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
                 have = true;
             }
         }
-    } else {
-        idx = mulhi(x0, n);
     }
+    if (!have && !idx_set) idx = mulhi(x0, n);
     if (!have) src = select_move(W, F, E, S, C, idx, dir);
     const uint32_t dst = (uint32_t)((int)src + (is_white ? 7 : -9) + (int)dir);
     action = (src << 8) | dst;
@@ -664,8 +669,10 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
     };
 
     uint32_t idx = 0, src = 0, kind = 0;
-    bool have = false;
-    if (POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI) {
+    bool have = false, idx_set = false;
+    constexpr bool DECISIVE = POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI || POLICY == MR_DECISIVE_MAST;
+    constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST;
+    if (DECISIVE) {
         // first action in list order that lands on the far wall (simulate.rs:662-687); a jump of two rows wins
         // from the two rows next to it, a jump of one row from the row next to it
         const uint64_t r1 = is_white ? 0x00FF000000000000ull : 0x000000000000FF00ull; // one row from the goal
@@ -715,10 +722,9 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
                     }
                 }
             }
-        } else {
-            idx = mulhi(x0, n);
         }
-    } else if (POLICY == MR_EPS_LGR) {
+    }
+    if (POLICY == MR_EPS_LGR) {
         idx = mulhi(x0, n);
         if (lgr_reply) {
             const uint32_t s0 = (lgr_reply - 1u) >> 8, d0 = (lgr_reply - 1u) & 0xffu;
@@ -732,7 +738,8 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
                     }
             }
         }
-    } else if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+    }
+    if (MAST_INNER && !have && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
         const uint32_t pl = is_white ? 1u : 0u;
         uint64_t cand[8];
 #pragma unroll
@@ -756,6 +763,7 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
             const uint32_t i0 = r >> 4;
             if (m == n) {
                 idx = i0;
+                idx_set = true;
             } else if (m <= 6) {
                 const uint32_t pk = r & 15u;
                 const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
@@ -797,9 +805,8 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
                 have = true;
             }
         }
-    } else {
-        idx = mulhi(x0, n);
     }
+    if (!have && !idx_set) idx = mulhi(x0, n);
     if (!have) src = select_move(idx, kind);
     const uint32_t dst = (uint32_t)((int)src + delta(kind));
     action = (src << 8) | dst;
@@ -961,7 +968,7 @@ struct Othello {
                 }
             }
         }
-        if (POLICY == MR_EPS_MAST && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+        if ((POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST) && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
             // Mast::select_move (simulate.rs:824-848): bit-sliced arg-max of the rank planes over the legal squares,
             // then random_best's visiting order among the maximal ones (as for Breakthrough, with one move kind)
             const uint32_t pl = is_white ? 1u : 0u;

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
     constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
     constexpr bool MASK_AMAF = WANT_AMAF && G::MASK_AMAF;
     constexpr bool IS_LGR = POLICY == MR_EPS_LGR;
-    constexpr bool PAIR_DRAWS = POLICY == MR_EPS_MAST || IS_LGR; // two Philox words per ply
+    constexpr bool PAIR_DRAWS = policy_uses_mast(POLICY) || IS_LGR; // two Philox words per ply
     constexpr bool NEED_SCRATCH = WANT_MAST || (WANT_AMAF && !G::MASK_AMAF) || IS_LGR; // per-lane slot trace
     constexpr int WINDOW = PAIR_DRAWS ? 2 : 4;
 

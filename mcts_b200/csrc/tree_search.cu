@@ -448,7 +448,8 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     s.d = desc;
     s.t.game = (int)desc->game;
     s.na = mr_num_actions((int)desc->game);
-    if (desc->policy == MR_EPS_MAST) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
+    const bool uses_mast = desc->policy == MR_EPS_MAST || desc->policy == MR_DECISIVE_MAST_WIN || desc->policy == MR_DECISIVE_MAST_WINLOSS;
+    if (uses_mast) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
     const bool lgr = desc->policy == MR_EPS_LGR;
     if (lgr) s.replies.assign((size_t)2 * s.na, 0);
     std::vector<mr_reply_update> reply_upd(lgr ? (size_t)2 * s.na : 0);
@@ -462,7 +463,7 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     std::vector<std::vector<PathEntry>> paths(B);
     std::vector<mr_leaf> leaves(B);
     std::vector<mr_leaf_result> results(B);
-    std::vector<mr_action_stat> delta(desc->policy == MR_EPS_MAST ? (size_t)2 * s.na : 0);
+    std::vector<mr_action_stat> delta(uses_mast ? (size_t)2 * s.na : 0);
     const bool want_amaf = desc->select == MR_SELECT_GRAVE || desc->select == MR_SELECT_AMAF;
     std::vector<mr_action_stat> amaf(want_amaf ? (size_t)B * 2 * s.na : 0);
     mr_search_stats st;
@@ -484,7 +485,7 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         bb.paths.resize(B);
         bb.leaves.resize(B);
         bb.results.resize(B);
-        bb.delta.resize(desc->policy == MR_EPS_MAST ? (size_t)2 * s.na : 0);
+        bb.delta.resize(uses_mast ? (size_t)2 * s.na : 0);
         bb.amaf.resize(want_amaf ? (size_t)B * 2 * s.na : 0);
     }
     (void)paths;
@@ -519,7 +520,7 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         bd.n_leaves = nb;
         bd.playouts_per_leaf = k;
         bd.max_playout_depth = desc->max_playout_depth;
-        bd.flags = (desc->policy == MR_EPS_MAST ? MR_WANT_MAST_DELTA : 0) | (want_amaf ? MR_WANT_AMAF : 0);
+        bd.flags = (uses_mast ? MR_WANT_MAST_DELTA : 0) | (want_amaf ? MR_WANT_AMAF : 0);
         bd.seed = desc->seed;
         bd.leaf_id_base = first;
         bd.epsilon = desc->epsilon;

@@ -41,6 +41,8 @@ class Policy(IntEnum):
     DECISIVE_WINLOSSDRAW = 4
     DECISIVE_ANTI = 5
     EPS_LGR = 6
+    DECISIVE_MAST_WIN = 7
+    DECISIVE_MAST_WINLOSS = 8
 
 
 class Outcome(IntEnum):  # TerminalStatus (mcts/src/game.rs:117-122)
@@ -169,6 +171,22 @@ class EpsilonGreedyLgr:
 
     def backprop_flags(self) -> int:
         return BACKPROP_LGR  # Lgr::backprop_flags (simulate.rs:984-986)
+
+
+@dataclass(frozen=True)
+class DecisiveMoveMast:
+    """DecisiveMove<G, EpsilonGreedy<G, Mast>> (mcts-tune SimulateSpec::DecisiveMoveMast): mode "win" is the
+    `ucb1_tuned_dm_mast` family, "win_loss" the `rave` family (family_catalog.rs:470-514)."""
+
+    epsilon: float = 0.1
+    mode: str = "win"
+
+    @property
+    def policy(self) -> Policy:
+        return {"win": Policy.DECISIVE_MAST_WIN, "win_loss": Policy.DECISIVE_MAST_WINLOSS}[self.mode]
+
+    def backprop_flags(self) -> int:
+        return BACKPROP_GLOBAL
 
 
 class MastTable:

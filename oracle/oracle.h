@@ -31,7 +31,8 @@ extern "C" {
 #endif
 
 enum { ORC_CONNECT4 = 0, ORC_BREAKTHROUGH = 1, ORC_KNIGHTTHROUGH = 2, ORC_OTHELLO = 3, ORC_HEX11 = 4, ORC_NUM_GAMES = 5 };
-enum { ORC_UNIFORM = 0, ORC_EPS_MAST = 1, ORC_DECISIVE_WIN = 2, ORC_DECISIVE_WINLOSS = 3, ORC_DECISIVE_WINLOSSDRAW = 4, ORC_DECISIVE_ANTI = 5, ORC_EPS_LGR = 6 };
+enum { ORC_UNIFORM = 0, ORC_EPS_MAST = 1, ORC_DECISIVE_WIN = 2, ORC_DECISIVE_WINLOSS = 3, ORC_DECISIVE_WINLOSSDRAW = 4, ORC_DECISIVE_ANTI = 5, ORC_EPS_LGR = 6,
+       ORC_DECISIVE_MAST_WIN = 7, ORC_DECISIVE_MAST_WINLOSS = 8 /* DecisiveMove<EpsilonGreedy<Mast>>, modes Win / WinLoss */ };
 enum { ORC_NOT_TERMINAL = 0, ORC_DRAW = 1, ORC_WINNER_P0 = 2, ORC_WINNER_P1 = 3 };
 enum { ORC_END_TERMINAL = 0, ORC_END_TURN_LIMIT = 1, ORC_END_NO_ACTIONS = 2 };
 

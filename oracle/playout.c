@@ -200,11 +200,14 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
         }
         int player = orc_player_to_move(game, &state);
         int pick = -1;
+        /* DecisiveMove::select_move (simulate.rs:742-760): the decisive scan, else the inner strategy */
         if (d->policy >= ORC_DECISIVE_WIN && d->policy <= ORC_DECISIVE_ANTI) pick = decisive_choose(game, d->policy, &state, available, n, player);
+        if (d->policy == ORC_DECISIVE_MAST_WIN) pick = decisive_choose(game, ORC_DECISIVE_WIN, &state, available, n, player);
+        if (d->policy == ORC_DECISIVE_MAST_WINLOSS) pick = decisive_choose(game, ORC_DECISIVE_WINLOSS, &state, available, n, player);
         if (pick < 0) {
             uint32_t x0;
             int greedy = 0;
-            if (d->policy == ORC_EPS_MAST) {
+            if (d->policy == ORC_EPS_MAST || d->policy == ORC_DECISIVE_MAST_WIN || d->policy == ORC_DECISIVE_MAST_WINLOSS) {
                 uint32_t x1;
                 orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
                 greedy = !((uint64_t)x1 < d->eps_threshold);
@@ -359,7 +362,7 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
                       orc_leaf_result *results, orc_action_stat *amaf_out, orc_action_stat *mast_delta_out,
                       uint16_t *trace_out, orc_playout_record *rec_out, orc_state *final_out, int n_threads) {
     if (d->game < 0 || d->game >= ORC_NUM_GAMES) return -1;
-    if (d->policy == ORC_EPS_MAST && !mast) return -2;
+    if ((d->policy == ORC_EPS_MAST || d->policy == ORC_DECISIVE_MAST_WIN || d->policy == ORC_DECISIVE_MAST_WINLOSS) && !mast) return -2;
     /* trace-derived statistics need a bounded trace: only Knightthrough can run unboundedly long */
     if ((amaf_out || mast_delta_out || d->reply_order_out) && d->max_playout_depth == 0 && d->game == ORC_KNIGHTTHROUGH) return -3;
     if (d->reply_order_out && !d->reply_action_out) return -4;

@@ -365,7 +365,7 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     const int want_amaf = c->select == 2 || c->select == 3;
     const uint32_t B = c->batch_leaves, k = c->playouts_per_leaf;
     const int na = orc_num_actions(c->game);
-    orc_action_stat *mast = c->policy == ORC_EPS_MAST ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    orc_action_stat *mast = (c->policy == ORC_EPS_MAST || c->policy == ORC_DECISIVE_MAST_WIN || c->policy == ORC_DECISIVE_MAST_WINLOSS) ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
     orc_action_stat *delta = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
     const int lgr = c->policy == ORC_EPS_LGR;
     uint16_t *replies = lgr ? (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t)) : NULL;

@@ -38,7 +38,8 @@ def _random_mast(game, seed, density=0.6):
 def _strategy(policy, eps=0.1):
     return {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(eps), o.DECISIVE_WIN: mb.DecisiveMoveWin(),
             o.DECISIVE_WINLOSS: mb.DecisiveMove("win_loss"), o.DECISIVE_WINLOSSDRAW: mb.DecisiveMove("win_loss_draw"),
-            o.DECISIVE_ANTI: mb.DecisiveMove("anti_decisive")}[policy]
+            o.DECISIVE_ANTI: mb.DecisiveMove("anti_decisive"), o.DECISIVE_MAST_WIN: mb.DecisiveMoveMast(eps, "win"),
+            o.DECISIVE_MAST_WINLOSS: mb.DecisiveMoveMast(eps, "win_loss")}[policy]
 
 
 def _compare(game, policy, leaves, k, *, seed, max_depth=0, mast=None, eps=0.1, leaf_id_base=0, amaf=False, delta=False, devices=1):
@@ -190,6 +191,22 @@ def test_anti_decisive_not_built_for_hex():
         with pytest.raises(mb.RolloutError) as e:
             g.simulate_many(mb.initial_state(mb.Game.HEX11), 4)
         assert "MR_ERR_UNSUPPORTED" in str(e.value)
+
+
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO])
+@pytest.mark.parametrize("policy", [o.DECISIVE_MAST_WIN, o.DECISIVE_MAST_WINLOSS])
+def test_decisive_move_over_mast_bit_exact(game, policy):
+    """DecisiveMove<EpsilonGreedy<Mast>> (the `ucb1_tuned_dm_mast` and `rave` families): the decisive scan, then the
+    epsilon-greedy MAST pick; traces, records, final states, results and the MAST delta."""
+    leaves = _leaves(game, n_per=4)
+    if game == o.CONNECT4:
+        leaves = np.concatenate([leaves, o.random_positions(game, 9, 30, 8)])
+    for density, eps in ((0.0, 0.1), (0.6, 0.1), (1.0, 0.0)):
+        mast = _random_mast(game, 7 + int(density * 10), density)
+        got, ref = _compare(game, policy, leaves, 48, seed=41, mast=mast, eps=eps, max_depth=200, delta=True)
+    if game != o.OTHELLO:  # the decisive scan changes picks: not the plain MAST playouts
+        plain = o.playout_batch(game, leaves, 48, policy=o.EPS_MAST, eps=0.0, max_depth=200, seed=41, mast=mast)
+        assert plain["results"].tobytes() != ref["results"].tobytes()
 
 
 def _random_replies(game, leaves, seed, density):
@@ -350,7 +367,7 @@ def test_randomized_differential_sweep():
     rng = np.random.default_rng(20260101)
     policies = {
         o.CONNECT4: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI],
-        o.BREAKTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI],
+        o.BREAKTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI, o.DECISIVE_MAST_WINLOSS],
         o.KNIGHTTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WINLOSS, o.DECISIVE_ANTI],
         o.OTHELLO: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WINLOSSDRAW, o.DECISIVE_ANTI],
         o.HEX11: [o.UNIFORM],
@@ -365,11 +382,12 @@ def test_randomized_differential_sweep():
         cutoff = int(rng.choice([0, 0, 5, 40]))
         needs_bound = game == o.KNIGHTTHROUGH
         amaf = bool(rng.integers(2))
-        delta = policy == o.EPS_MAST or (game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH) and bool(rng.integers(2)))
+        delta = policy in (o.EPS_MAST, o.DECISIVE_MAST_WINLOSS) or (game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH) and bool(rng.integers(2)))
         if (amaf or delta) and needs_bound and cutoff == 0:
             cutoff = 250
         if game == o.HEX11:
             delta = False
-        mast = _random_mast(game, case, float(rng.random())) if policy == o.EPS_MAST else None
+        uses_mast = policy in (o.EPS_MAST, o.DECISIVE_MAST_WIN, o.DECISIVE_MAST_WINLOSS)
+        mast = _random_mast(game, case, float(rng.random())) if uses_mast else None
         _compare(game, policy, leaves, k, seed=int(rng.integers(1 << 62)), max_depth=cutoff, mast=mast,
                  eps=float(rng.choice([0.0, 0.1, 0.5])), leaf_id_base=int(rng.integers(1 << 20)), amaf=amaf, delta=delta)

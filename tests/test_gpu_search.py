@@ -137,6 +137,23 @@ def test_lgr_search_bit_exact(game, iters, batch, k, pipelined):
     assert uni_plies != plies
 
 
+def test_rave_family_search_bit_exact():
+    """mcts-tune's `rave` family (family_catalog.rs:483-514): Rave select over the in-kernel AMAF tables with
+    DecisiveMove<WinLoss, EpsilonGreedy<Mast>> rollouts -- AMAF tables, MAST delta and decisive scan in one kernel."""
+    from mcts_b200.search import SELECT_GRAVE, QINIT_INFINITY
+
+    game, iters, batch, k = o.BREAKTHROUGH, 2048, 32, 8
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), mb.DecisiveMoveMast(0.1, "win_loss"), max_iterations=iters, batch_leaves=batch,
+                      num_rollouts_per_leaf=k, select=SELECT_GRAVE, q_init=QINIT_INFINITY, grave_threshold=100,
+                      max_playout_depth=200, seed=17) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.DECISIVE_MAST_WINLOSS,
+                                     select=2, q_init=1, seed=17, threads=o.host_threads(), grave_threshold=100, max_depth=200)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+
+
 def test_flat_monte_carlo_one_batch():
     from mcts_b200.search import flat_monte_carlo
 
