@@ -69,3 +69,63 @@ def test_initial_states_match_oracle():
 
     for g in range(5):
         assert mb.initial_state(mb.Game(g)).tobytes() == o.initial_state(g).tobytes()
+
+
+def _compile_host_example(tmp_path):
+    import subprocess
+
+    from mcts_b200 import build
+
+    build.build()
+    exe = tmp_path / "host_loop"
+    subprocess.run(
+        ["gcc", "-O2", "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "host_loop.c"),
+         f"-L{build.OUT_DIR}", "-lmcts_b200", f"-Wl,-rpath,{build.OUT_DIR}", "-o", str(exe)],
+        check=True,
+    )
+    return exe
+
+
+def test_header_is_plain_c_and_struct_sizes(tmp_path):
+    """include/mcts_rollout.h compiles as C99 (no C++ / torch types at the boundary) and its PODs have the sizes the
+    bindings assume."""
+    import subprocess
+
+    src = tmp_path / "sizes.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "mcts_rollout.h"\n'
+        "int main(void) { printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(mr_leaf), sizeof(mr_leaf_result),\n"
+        "  sizeof(mr_action_stat), sizeof(mr_playout_record), sizeof(mr_batch_desc), sizeof(mr_search_desc),\n"
+        "  sizeof(mr_root_child), sizeof(mr_search_stats), sizeof(mr_reply_update)); return 0; }\n"
+    )
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    from mcts_b200._lib import BatchDesc, SearchDesc, SearchStats, REPLY_UPDATE_DTYPE, ROOT_CHILD_DTYPE
+
+    assert [int(x) for x in out] == [40, 24, 8, 8, C.sizeof(BatchDesc), C.sizeof(SearchDesc), ROOT_CHILD_DTYPE.itemsize,
+                                     C.sizeof(SearchStats), REPLY_UPDATE_DTYPE.itemsize]
+
+
+def test_c_host_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/host_loop.c: a plain-C caller of the ABI.  Without a device it must stop at mr_init with
+    MR_ERR_NO_DEVICE (exit code 3), never compute on the CPU."""
+    import subprocess
+
+    import torch
+
+    exe = _compile_host_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_example_runs_on_the_gpu(tmp_path):
+    import subprocess
+
+    exe = _compile_host_example(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "best column 3" in r.stdout
