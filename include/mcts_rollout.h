@@ -64,27 +64,27 @@ enum mr_game {
 /* Simulation policies (the SimulateStrategy implementors in scope). */
 enum mr_policy {
     MR_UNIFORM = 0,     /* simulate.rs:157-216  Uniform */
-    MR_EPS_MAST = 1,    /* simulate.rs:485-570 + 819-848  EpsilonGreedy<G, Mast>; every game but Hex */
+    MR_EPS_MAST = 1,    /* simulate.rs:485-570 + 819-848  EpsilonGreedy<G, Mast> */
     MR_DECISIVE_WIN = 2, /* simulate.rs:573-760  DecisiveMove<G, Uniform>, mode Win */
-    /* modes WinLoss and WinLossDraw (simulate.rs:645-669).  For Connect4, Breakthrough, Knightthrough and Othello
-     * a move can only end the game in the mover's favour, or as the single remaining action, so all three modes
-     * pick the same action and share one kernel (DESIGN.md "Decisive move"); Hex is not built. */
+    /* modes WinLoss and WinLossDraw (simulate.rs:645-669).  In all five games a move can only end the game in the
+     * mover's favour, or as the single remaining action, so the three modes pick the same action and share one
+     * kernel (DESIGN.md "Decisive move"). */
     MR_DECISIVE_WINLOSS = 3,
     MR_DECISIVE_WINLOSSDRAW = 4,
     /* mode AntiDecisive (simulate.rs:689-735): an immediate win first; else the FIRST action in list order whose
      * child is not terminal and leaves the opponent no immediately winning reply; else the inner (uniform) pick.
-     * Built for Connect4, Breakthrough, Knightthrough and Othello. */
+     */
     MR_DECISIVE_ANTI = 5,
     /* simulate.rs:936-1033 + 538-570  EpsilonGreedy<G, Lgr<G, Uniform>> (strategy.rs:130-143 Ucb1Lgr): with
      * probability epsilon a uniform pick; else the reply recorded for (mover, preceding action) if it is legal now;
      * else a uniform pick.  Two draws per ply, as MR_EPS_MAST.  The reply table is frozen for the batch
-     * (mr_set_replies); the batch's last-write-wins updates come back through mr_reply_updates.  Connect4,
-     * Breakthrough, Knightthrough, Othello; needs a bounded playout (max_playout_depth) for Knightthrough. */
+     * (mr_set_replies); the batch's last-write-wins updates come back through mr_reply_updates.  Needs a
+     * bounded playout (max_playout_depth) for Knightthrough. */
     MR_EPS_LGR = 6,
     /* DecisiveMove<G, EpsilonGreedy<G, Mast>> (mcts-tune SimulateSpec::DecisiveMoveMast, config_ir.rs): the decisive
      * scan first, the epsilon-greedy MAST pick when it finds nothing.  Mode Win is the `ucb1_tuned_dm_mast` family,
      * mode WinLoss the `rave` family (family_catalog.rs:470-514); as for the plain decisive policies the modes pick
-     * the same action in these games and share a kernel.  Two draws per ply, as MR_EPS_MAST.  Not for Hex. */
+     * the same action in these games and share a kernel.  Two draws per ply, as MR_EPS_MAST. */
     MR_DECISIVE_MAST_WIN = 7,
     MR_DECISIVE_MAST_WINLOSS = 8
 };

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "hex_kernel.cuh"
+#include "hex_step.cuh"
 #include "int_peak.cuh"
 #include "rollout_kernel.cuh"
 
@@ -168,17 +169,15 @@ kernel_fn pick_variant(int v) {
     }
 }
 
-kernel_fn pick_hex(int v) { // Hex has its own fill-then-search kernel; no MAST policy, AMAF from board masks
+kernel_fn pick_hex(int v) { // Hex, uniform policy: the fill-then-search kernel; AMAF from board masks
     switch (v) {
-    case 0:
-    case 2: return hex_rollout_kernel<0>;
-    case 1:
-    case 3: return hex_rollout_kernel<MR_WANT_AMAF>;
+    case 0: return hex_rollout_kernel<0>;
+    case 1: return hex_rollout_kernel<MR_WANT_AMAF>;
     default: return hex_rollout_kernel<MR_WANT_AMAF | MR_WANT_TRACE | MR_WANT_FINAL_STATE>;
     }
 }
 
-kernel_fn pick_kernel(int game, int policy, int v) {
+kernel_fn pick_kernel(int game, int policy, int v, uint32_t flags) {
     // WinLoss / WinLossDraw pick exactly what Win picks in the four games that have a decisive kernel
     if (policy == MR_DECISIVE_WINLOSS || policy == MR_DECISIVE_WINLOSSDRAW) policy = MR_DECISIVE_WIN;
     if (policy == MR_DECISIVE_MAST_WINLOSS) policy = MR_DECISIVE_MAST_WIN;
@@ -216,7 +215,15 @@ kernel_fn pick_kernel(int game, int policy, int v) {
         if (policy == MR_EPS_LGR) return pick_variant<Othello, MR_EPS_LGR>(v);
         return nullptr;
     case MR_HEX11:
-        if (policy == MR_UNIFORM) return pick_hex(v);
+        // uniform playouts never look at the position: fill-then-search (hex_kernel.cuh), unless the caller wants the
+        // MAST delta, which only the per-ply kernel (hex_step.cuh) produces; every other policy needs the position
+        if (policy == MR_UNIFORM && !(flags & MR_WANT_MAST_DELTA)) return pick_hex(v);
+        if (policy == MR_UNIFORM) return pick_variant<HexStep, MR_UNIFORM>(v);
+        if (policy == MR_EPS_MAST) return pick_variant<HexStep, MR_EPS_MAST>(v);
+        if (policy == MR_DECISIVE_WIN) return pick_variant<HexStep, MR_DECISIVE_WIN>(v);
+        if (policy == MR_DECISIVE_ANTI) return pick_variant<HexStep, MR_DECISIVE_ANTI>(v);
+        if (policy == MR_EPS_LGR) return pick_variant<HexStep, MR_EPS_LGR>(v);
+        if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<HexStep, MR_DECISIVE_MAST>(v);
         return nullptr;
     }
     return nullptr;
@@ -256,14 +263,14 @@ int mast_action_id(int game, int player, int cell, int kind) {
         return dst < 0 ? -1 : cell * 64 + dst;
     }
     if (game == MR_OTHELLO) return kind == 0 ? cell : -1;
+    if (game == MR_HEX11) return (kind < 2 && kind * 64 + cell < 121) ? kind * 64 + cell : -1; // kind = 64-bit half of the board
     if (game == MR_CONNECT4) return (kind == 0 && cell < 7) ? cell : -1;
     return -1;
 }
 
 int compute_mast_planes(mr_ctx *ctx, int game, const mr_action_stat *mast) {
-    if (game == MR_HEX11) return fail(ctx, MR_ERR_UNSUPPORTED, "no MAST policy is built for Hex");
     const int na = kGames[game].num_actions;
-    const int kinds = game == MR_BREAKTHROUGH ? 3 : (game == MR_KNIGHTTHROUGH ? 8 : 1);
+    const int kinds = game == MR_BREAKTHROUGH ? 3 : (game == MR_KNIGHTTHROUGH ? 8 : (game == MR_HEX11 ? 2 : 1));
     memset(ctx->mast_planes, 0, sizeof ctx->mast_planes);
     memset(ctx->mast_rank_small, 0, sizeof ctx->mast_rank_small);
     for (int pl = 0; pl < 2; ++pl) {
@@ -343,7 +350,7 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
     if (d->n_leaves == 0 || d->playouts_per_leaf == 0)
         return fail(ctx, MR_ERR_INVALID, "empty batch (n_leaves=%u, playouts_per_leaf=%u)", d->n_leaves, d->playouts_per_leaf);
     if (d->flags & ~15u) return fail(ctx, MR_ERR_INVALID, "unknown flags 0x%x", d->flags);
-    kernel_fn fn = pick_kernel((int)d->game, (int)d->policy, flag_variant(d->flags));
+    kernel_fn fn = pick_kernel((int)d->game, (int)d->policy, flag_variant(d->flags), d->flags);
     if (!fn) return fail(ctx, MR_ERR_UNSUPPORTED, "policy %u is not built for game %u", d->policy, d->game);
     if (policy_uses_mast((int)d->policy)) {
         if (!has_mast) return fail(ctx, MR_ERR_INVALID, "a MAST policy needs a MAST snapshot (mast_in / mr_set_mast)");
@@ -355,11 +362,11 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
             return fail(ctx, MR_ERR_INVALID, "the reply table was set for game %d, the batch is game %u", ctx->replies_game, d->game);
         if ((uint64_t)d->n_leaves * d->playouts_per_leaf >= (1ull << 37)) return fail(ctx, MR_ERR_INVALID, "batch too large for MR_EPS_LGR");
     }
-    if (d->game == MR_HEX11 && (d->flags & MR_WANT_MAST_DELTA))
-        return fail(ctx, MR_ERR_UNSUPPORTED, "no MAST table is built for Hex (no MAST policy in scope for it)");
     if ((d->flags & MR_WANT_TRACE) && d->max_trace == 0) return fail(ctx, MR_ERR_INVALID, "MR_WANT_TRACE needs max_trace > 0");
     uint32_t cap = 0;
-    const bool needs_scratch = (d->flags & MR_WANT_MAST_DELTA) || ((d->flags & MR_WANT_AMAF) && d->game != MR_HEX11) ||
+    // (the Hex fill-then-search kernel derives AMAF from board masks; every per-ply kernel uses the slot trace)
+    const bool hex_fast = d->game == MR_HEX11 && d->policy == MR_UNIFORM && !(d->flags & MR_WANT_MAST_DELTA);
+    const bool needs_scratch = (d->flags & MR_WANT_MAST_DELTA) || ((d->flags & MR_WANT_AMAF) && !hex_fast) ||
                                d->policy == MR_EPS_LGR;
     if (needs_scratch) {
         const uint32_t bound = kGames[d->game].depth_bound;

@@ -121,7 +121,7 @@ def test_terminal_and_stuck_leaves():
     _compare(o.OTHELLO, o.UNIFORM, must_pass, 4, seed=3)
 
 
-@pytest.mark.parametrize("game", [o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.CONNECT4, o.OTHELLO])
+@pytest.mark.parametrize("game", [o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.CONNECT4, o.OTHELLO, o.HEX11])
 @pytest.mark.parametrize("eps", [0.1, 0.0, 1.0])
 def test_eps_mast_bit_exact(game, eps):
     leaves = _leaves(game, n_per=3)
@@ -150,7 +150,7 @@ def test_amaf_tables_bit_exact(game):
     assert got.amaf["visits"].sum() == got.results["sum_depth"].sum()
 
 
-@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH])
+@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.HEX11])
 def test_decisive_win_bit_exact(game):
     leaves = _leaves(game, n_per=4)
     if game == o.OTHELLO:  # late positions, where the 64th-disc case can occur
@@ -158,7 +158,7 @@ def test_decisive_win_bit_exact(game):
     _compare(game, o.DECISIVE_WIN, leaves, 64, seed=17)
 
 
-@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH])
+@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.HEX11])
 @pytest.mark.parametrize("mode", [o.DECISIVE_WINLOSS, o.DECISIVE_WINLOSSDRAW])
 def test_decisive_other_modes_bit_exact(game, mode):
     """WinLoss / WinLossDraw restated literally in the oracle; the product routes them to the Win kernel."""
@@ -170,13 +170,13 @@ def test_decisive_other_modes_bit_exact(game, mode):
     _compare(game, mode, leaves, 48, seed=23)
 
 
-@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH])
+@pytest.mark.parametrize("game", [o.OTHELLO, o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.HEX11])
 def test_anti_decisive_bit_exact(game):
     """DecisiveMoveMode::AntiDecisive (simulate.rs:689-735): the oracle runs the reference's two literal passes
     (apply + terminal_status per action, then per reply); the kernels use closed forms per game.  The mode takes
     the FIRST safe action, so playouts of one leaf differ little: coverage comes from many leaves."""
     plies = {o.CONNECT4: range(0, 40, 3), o.BREAKTHROUGH: range(0, 60, 4), o.KNIGHTTHROUGH: range(0, 40, 3),
-             o.OTHELLO: list(range(0, 56, 5)) + [56, 57, 58, 59, 60]}[game]
+             o.OTHELLO: list(range(0, 56, 5)) + [56, 57, 58, 59, 60], o.HEX11: range(0, 110, 9)}[game]
     leaves = np.concatenate([o.random_positions(game, 300 + p, p, 24 if p else 1) for p in plies])
     # (Knightthrough playouts have no depth bound of their own: statistics tables need max_playout_depth)
     got, _ = _compare(game, o.DECISIVE_ANTI, leaves, 8, seed=31, amaf=game != o.OTHELLO, max_depth=300 if game == o.KNIGHTTHROUGH else 0)
@@ -186,14 +186,7 @@ def test_anti_decisive_bit_exact(game):
     _compare(game, o.DECISIVE_ANTI, leaves[::5], 4, seed=32, max_depth=9)
 
 
-def test_anti_decisive_not_built_for_hex():
-    with mb.GpuRollout(mb.Game.HEX11, mb.DecisiveMove("anti_decisive")) as g:
-        with pytest.raises(mb.RolloutError) as e:
-            g.simulate_many(mb.initial_state(mb.Game.HEX11), 4)
-        assert "MR_ERR_UNSUPPORTED" in str(e.value)
-
-
-@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO])
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO, o.HEX11])
 @pytest.mark.parametrize("policy", [o.DECISIVE_MAST_WIN, o.DECISIVE_MAST_WINLOSS])
 def test_decisive_move_over_mast_bit_exact(game, policy):
     """DecisiveMove<EpsilonGreedy<Mast>> (the `ucb1_tuned_dm_mast` and `rave` families): the decisive scan, then the
@@ -228,7 +221,7 @@ def _random_replies(game, leaves, seed, density):
     return table
 
 
-@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO])
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO, o.HEX11])
 @pytest.mark.parametrize("eps", [0.1, 0.0])
 def test_last_good_reply_bit_exact(game, eps):
     """EpsilonGreedy<Lgr<Uniform>> (simulate.rs:936-1033): traces, records and final states per playout, and the
@@ -291,9 +284,9 @@ def test_double_buffered_slots_and_errors():
         assert r1.results.tobytes() == o.playout_batch(game, b, 32, seed=3, leaf_id_base=500)["results"].tobytes()
         assert g.kernel_launches() == 2
     with mb.GpuRollout(mb.Game.HEX11, mb.EpsilonGreedyMast()) as g:
-        with pytest.raises(mb.RolloutError) as e:
+        with pytest.raises(mb.RolloutError) as e:  # a MAST policy without a MAST snapshot
             g.simulate_many(a.view(mb.LEAF_DTYPE), 4)
-        assert "MR_ERR_UNSUPPORTED" in str(e.value)
+        assert "MR_ERR_INVALID" in str(e.value)
     with mb.GpuRollout(mb.Game.KNIGHTTHROUGH, mb.Uniform()) as g:
         with pytest.raises(mb.RolloutError) as e:  # unbounded playouts cannot carry a MAST delta
             g.simulate_many(mb.initial_state(mb.Game.KNIGHTTHROUGH), 4, want_mast_delta=True)
@@ -370,7 +363,7 @@ def test_randomized_differential_sweep():
         o.BREAKTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI, o.DECISIVE_MAST_WINLOSS],
         o.KNIGHTTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WINLOSS, o.DECISIVE_ANTI],
         o.OTHELLO: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WINLOSSDRAW, o.DECISIVE_ANTI],
-        o.HEX11: [o.UNIFORM],
+        o.HEX11: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI, o.DECISIVE_MAST_WIN],
     }
     max_plies = {o.CONNECT4: 30, o.BREAKTHROUGH: 50, o.KNIGHTTHROUGH: 30, o.OTHELLO: 56, o.HEX11: 100}
     for case in range(40):
@@ -385,8 +378,8 @@ def test_randomized_differential_sweep():
         delta = policy in (o.EPS_MAST, o.DECISIVE_MAST_WINLOSS) or (game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH) and bool(rng.integers(2)))
         if (amaf or delta) and needs_bound and cutoff == 0:
             cutoff = 250
-        if game == o.HEX11:
-            delta = False
+        if game == o.HEX11 and policy == o.UNIFORM:
+            delta = bool(rng.integers(2))  # uniform + MAST delta routes Hex to the per-ply kernel
         uses_mast = policy in (o.EPS_MAST, o.DECISIVE_MAST_WIN, o.DECISIVE_MAST_WINLOSS)
         mast = _random_mast(game, case, float(rng.random())) if uses_mast else None
         _compare(game, policy, leaves, k, seed=int(rng.integers(1 << 62)), max_depth=cutoff, mast=mast,

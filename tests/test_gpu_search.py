@@ -17,6 +17,7 @@ CASES = [
     (o.KNIGHTTHROUGH, o.EPS_MAST, 1024, 64, 8, 0, 0, 200),
     (o.CONNECT4, o.EPS_MAST, 2048, 32, 8, 0, 0, 0),    # Ucb1Mast (strategy.rs:98-111) on the games without move kinds
     (o.OTHELLO, o.EPS_MAST, 1024, 16, 8, 0, 0, 0),
+    (o.HEX11, o.EPS_MAST, 1024, 32, 8, 0, 0, 0),       # the per-ply Hex kernel (hex_step.cuh) behind the driver
     (o.OTHELLO, o.DECISIVE_WIN, 1024, 32, 4, 1, 1, 0),
     (o.HEX11, o.UNIFORM, 1024, 64, 4, 0, 0, 0),
 ]
@@ -121,6 +122,7 @@ def test_amaf_search_bit_exact(game, policy, iters, batch, k, alpha):
     (o.BREAKTHROUGH, 2048, 64, 8, False),
     (o.KNIGHTTHROUGH, 1024, 16, 16, True),  # pipelined: batch N+1 plays with the table as of batch N-1
     (o.OTHELLO, 1024, 1, 1, False),         # the reference's sequential loop: every trial sees every earlier write
+    (o.HEX11, 1024, 32, 4, False),
 ])
 def test_lgr_search_bit_exact(game, iters, batch, k, pipelined):
     root = o.initial_state(game)
