@@ -16,10 +16,8 @@
 #include <string>
 #include <vector>
 
-#include "hex_kernel.cuh"
-#include "hex_step.cuh"
 #include "int_peak.cuh"
-#include "rollout_kernel.cuh"
+#include "kernels.h"
 
 using namespace mr;
 
@@ -105,7 +103,6 @@ struct SlotState {
     bool lgr_ready = false; // a completed MR_EPS_LGR batch whose updates can still be read
 };
 
-typedef void (*kernel_fn)(const KernelParams);
 
 } // namespace
 
@@ -148,83 +145,22 @@ int fail(mr_ctx *ctx, int code, const char *fmt, ...) {
             return fail(ctx, MR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-// ---- kernel table: (game, policy, flag variant) -> instantiation ----
-// flag variants: 0 = none, 1 = AMAF, 2 = MAST delta, 3 = AMAF|MAST, 4 = everything (debug / parity outputs)
-constexpr int kFlagVariant[5] = {0, MR_WANT_AMAF, MR_WANT_MAST_DELTA, MR_WANT_AMAF | MR_WANT_MAST_DELTA,
-                                 MR_WANT_AMAF | MR_WANT_MAST_DELTA | MR_WANT_TRACE | MR_WANT_FINAL_STATE};
-
+// ---- kernel table: (game, policy, flag variant) -> instantiation (the instantiations live in kernels_<game>.cu) ----
 int flag_variant(uint32_t flags) {
     if (flags & (MR_WANT_TRACE | MR_WANT_FINAL_STATE)) return 4;
     return (int)(flags & 3u);
 }
 
-template <class G, int POLICY>
-kernel_fn pick_variant(int v) {
-    switch (v) {
-    case 0: return rollout_kernel<G, POLICY, kFlagVariant[0]>;
-    case 1: return rollout_kernel<G, POLICY, kFlagVariant[1]>;
-    case 2: return rollout_kernel<G, POLICY, kFlagVariant[2]>;
-    case 3: return rollout_kernel<G, POLICY, kFlagVariant[3]>;
-    default: return rollout_kernel<G, POLICY, kFlagVariant[4]>;
-    }
-}
-
-kernel_fn pick_hex(int v) { // Hex, uniform policy: the fill-then-search kernel; AMAF from board masks
-    switch (v) {
-    case 0: return hex_rollout_kernel<0>;
-    case 1: return hex_rollout_kernel<MR_WANT_AMAF>;
-    default: return hex_rollout_kernel<MR_WANT_AMAF | MR_WANT_TRACE | MR_WANT_FINAL_STATE>;
-    }
-}
-
 kernel_fn pick_kernel(int game, int policy, int v, uint32_t flags) {
-    // WinLoss / WinLossDraw pick exactly what Win picks in the four games that have a decisive kernel
+    // WinLoss / WinLossDraw pick exactly what Win picks (DESIGN.md "Decisive move")
     if (policy == MR_DECISIVE_WINLOSS || policy == MR_DECISIVE_WINLOSSDRAW) policy = MR_DECISIVE_WIN;
     if (policy == MR_DECISIVE_MAST_WINLOSS) policy = MR_DECISIVE_MAST_WIN;
     switch (game) {
-    case MR_CONNECT4:
-        if (policy == MR_UNIFORM) return pick_variant<Connect4, MR_UNIFORM>(v);
-        if (policy == MR_EPS_MAST) return pick_variant<Connect4, MR_EPS_MAST>(v);
-        if (policy == MR_DECISIVE_WIN) return pick_variant<Connect4, MR_DECISIVE_WIN>(v);
-        if (policy == MR_DECISIVE_ANTI) return pick_variant<Connect4, MR_DECISIVE_ANTI>(v);
-        if (policy == MR_EPS_LGR) return pick_variant<Connect4, MR_EPS_LGR>(v);
-        if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<Connect4, MR_DECISIVE_MAST>(v);
-        return nullptr;
-    case MR_BREAKTHROUGH:
-        if (policy == MR_UNIFORM) return pick_variant<Breakthrough, MR_UNIFORM>(v);
-        if (policy == MR_EPS_MAST) return pick_variant<Breakthrough, MR_EPS_MAST>(v);
-        if (policy == MR_DECISIVE_WIN) return pick_variant<Breakthrough, MR_DECISIVE_WIN>(v);
-        if (policy == MR_DECISIVE_ANTI) return pick_variant<Breakthrough, MR_DECISIVE_ANTI>(v);
-        if (policy == MR_EPS_LGR) return pick_variant<Breakthrough, MR_EPS_LGR>(v);
-        if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<Breakthrough, MR_DECISIVE_MAST>(v);
-        return nullptr;
-    case MR_KNIGHTTHROUGH:
-        if (policy == MR_UNIFORM) return pick_variant<Knightthrough, MR_UNIFORM>(v);
-        if (policy == MR_EPS_MAST) return pick_variant<Knightthrough, MR_EPS_MAST>(v);
-        if (policy == MR_DECISIVE_WIN) return pick_variant<Knightthrough, MR_DECISIVE_WIN>(v);
-        if (policy == MR_DECISIVE_ANTI) return pick_variant<Knightthrough, MR_DECISIVE_ANTI>(v);
-        if (policy == MR_EPS_LGR) return pick_variant<Knightthrough, MR_EPS_LGR>(v);
-        if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<Knightthrough, MR_DECISIVE_MAST>(v);
-        return nullptr;
-    case MR_OTHELLO:
-        // DecisiveMove<Win> provably never changes an Othello pick, so it shares the kernel
-        if (policy == MR_UNIFORM || policy == MR_DECISIVE_WIN) return pick_variant<Othello, MR_UNIFORM>(v);
-        // (the decisive scan never changes an Othello pick, so DecisiveMove<EpsilonGreedy<Mast>> is the MAST kernel)
-        if (policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN) return pick_variant<Othello, MR_EPS_MAST>(v);
-        if (policy == MR_DECISIVE_ANTI) return pick_variant<Othello, MR_DECISIVE_ANTI>(v);
-        if (policy == MR_EPS_LGR) return pick_variant<Othello, MR_EPS_LGR>(v);
-        return nullptr;
-    case MR_HEX11:
-        // uniform playouts never look at the position: fill-then-search (hex_kernel.cuh), unless the caller wants the
-        // MAST delta, which only the per-ply kernel (hex_step.cuh) produces; every other policy needs the position
-        if (policy == MR_UNIFORM && !(flags & MR_WANT_MAST_DELTA)) return pick_hex(v);
-        if (policy == MR_UNIFORM) return pick_variant<HexStep, MR_UNIFORM>(v);
-        if (policy == MR_EPS_MAST) return pick_variant<HexStep, MR_EPS_MAST>(v);
-        if (policy == MR_DECISIVE_WIN) return pick_variant<HexStep, MR_DECISIVE_WIN>(v);
-        if (policy == MR_DECISIVE_ANTI) return pick_variant<HexStep, MR_DECISIVE_ANTI>(v);
-        if (policy == MR_EPS_LGR) return pick_variant<HexStep, MR_EPS_LGR>(v);
-        if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<HexStep, MR_DECISIVE_MAST>(v);
-        return nullptr;
+    case MR_CONNECT4: return pick_connect4(policy, v);
+    case MR_BREAKTHROUGH: return pick_breakthrough(policy, v);
+    case MR_KNIGHTTHROUGH: return pick_knightthrough(policy, v);
+    case MR_OTHELLO: return pick_othello(policy, v);
+    case MR_HEX11: return pick_hex11(policy, v, flags);
     }
     return nullptr;
 }
@@ -337,11 +273,14 @@ cudaError_t upload_random_best_tables() {
             inv[n][k] = (uint8_t)iv;
         }
     }
-    cudaError_t e = cudaMemcpyToSymbol(MR_STRIDE, stride, sizeof stride);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(MR_STRIDE_INV, inv, sizeof inv);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(MR_RCP32, rcp, sizeof rcp);
+    // every kernel translation unit holds its own copy of the tables
+    const table_upload_fn uploads[] = {upload_tables_connect4, upload_tables_breakthrough, upload_tables_knightthrough,
+                                       upload_tables_othello, upload_tables_hex11};
+    for (table_upload_fn f : uploads) {
+        cudaError_t e = f(stride, inv, rcp);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_out, uint32_t *trace_cap_out) {
