@@ -48,6 +48,13 @@ OTHERS = [
     dict(name="hex11_uniform_amaf", game=4, policy=0, plies=30, pos_seed=3, max_depth=0, eps=0.0, amaf=True),
     dict(name="breakthrough8x8_uniform", game=1, policy=0, plies=20, pos_seed=2, max_depth=0, eps=0.0, amaf=False),
 ]
+# not part of the bench line: extra workloads tools/profile_one.py can name (ncu captures, A/B timing)
+PROFILE_ONLY = [
+    dict(name="hex11_eps_mast", game=4, policy=1, plies=30, pos_seed=3, max_depth=0, eps=0.1, amaf=False),
+    dict(name="hex11_decisive_win", game=4, policy=2, plies=30, pos_seed=3, max_depth=0, eps=0.0, amaf=False),
+    dict(name="othello_eps_mast", game=3, policy=1, plies=30, pos_seed=4, max_depth=0, eps=0.1, amaf=False),
+    dict(name="connect4_eps_mast", game=0, policy=1, plies=12, pos_seed=1, max_depth=0, eps=0.1, amaf=False),
+]
 # ops per ply of a bit-parallel restatement of the reference's arithmetic (model v1)
 OPS_PER_PLY = {
     "connect4_uniform_midgame": 125.0,

@@ -224,8 +224,18 @@ struct HexStep : Hex11 {
         const B128 nx = nb(x);
         const bool t1 = any(band(x, first_edge(PL))) || any(band(nx, e1[PL]));
         const bool t2 = any(band(x, second_edge(PL))) || any(band(nx, e2[PL]));
-        if (t1) e1[PL] = bor(e1[PL], flood_from(x, bandn(s[PL], e1[PL])));
-        if (t2) e2[PL] = bor(e2[PL], flood_from(x, bandn(s[PL], e2[PL])));
+        // x joins a set it touches; own stones next to x that were not in the set yet come along, with whatever they
+        // reach -- usually there are none, and the flood (divergent, long) is skipped
+        if (t1) {
+            const B128 adj = bandn(band(nx, s[PL]), e1[PL]);
+            e1[PL] = bor(e1[PL], x);
+            if (any(adj)) e1[PL] = bor(e1[PL], flood_from(adj, bandn(s[PL], e1[PL])));
+        }
+        if (t2) {
+            const B128 adj = bandn(band(nx, s[PL]), e2[PL]);
+            e2[PL] = bor(e2[PL], x);
+            if (any(adj)) e2[PL] = bor(e2[PL], flood_from(adj, bandn(s[PL], e2[PL])));
+        }
         if (t1 && t2) return ST_MOVED | (PL ? ST_WIN_P1 : ST_WIN_P0);
         if (n_empty == 0) return ST_MOVED | ST_DRAW; // is_terminal on a full board, no connection of the mover (:208-215)
         return ST_MOVED;

@@ -14,7 +14,7 @@ name = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 launches = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-w = next(x for x in [bench.HEADLINE] + bench.OTHERS if x["name"] == name)
+w = next(x for x in [bench.HEADLINE] + bench.OTHERS + bench.PROFILE_ONLY if x["name"] == name)
 strat = {0: mb.Uniform(), 1: mb.EpsilonGreedyMast(w["eps"]), 2: mb.DecisiveMoveWin()}[w["policy"]]
 g = mb.GpuRollout(mb.Game(w["game"]), strat, seed=12345, max_playout_depth=w["max_depth"])
 leaves = g.random_positions(w["plies"], n, seed=w["pos_seed"])
