@@ -16,9 +16,12 @@ def ncu(name):
         return {}
     out = {}
     for line in f.read_text().splitlines():
-        m = re.match(r"\s+(\S+)\s+([0-9.]+)", line)
+        m = re.match(r"\s+(\S+)\s+([0-9.]+)\s*(\S*)", line)
         if m:
-            out[m.group(1)] = float(m.group(2))
+            v = float(m.group(2))
+            if m.group(1) == "gpu__time_duration.sum":  # normalise to milliseconds
+                v *= {"us": 1e-3, "usecond": 1e-3, "ns": 1e-6, "nsecond": 1e-6, "s": 1e3, "second": 1e3}.get(m.group(3), 1.0)
+            out[m.group(1)] = v
     return out
 
 
@@ -52,9 +55,10 @@ for k, v in pk.items():
     if isinstance(v, dict):
         L.append(f"| {k} | {v['per_sm_per_clk_at_max_clock']:.1f} | {v['thread_ops_per_s'] / 1e12:.2f} |")
 L.append("\n## ncu counters of the dominant kernels at bench size (`--set full`, one launch)\n")
-L.append("| kernel | duration | threads/inst (of 32) | issue active % | ALU pipe % | FMA pipe % | XU pipe % | warps active % | regs |")
+L.append("| kernel | duration (ms) | threads/inst (of 32) | issue active % | ALU pipe % | FMA pipe % | XU pipe % | warps active % | regs |")
 L.append("|---|---|---|---|---|---|---|---|---|")
-for name in ["breakthrough8x8_eps_mast", "connect4_uniform_midgame", "hex11_uniform_amaf", "othello_decisive_win"]:
+for name in ["breakthrough8x8_eps_mast", "breakthrough8x8_uniform", "knightthrough8x8_eps_mast", "connect4_uniform_midgame",
+             "hex11_uniform_amaf", "hex11_eps_mast_per_ply", "othello_decisive_win"]:
     n = ncu(name)
     if not n:
         continue
