@@ -86,7 +86,13 @@ enum mr_policy {
      * mode WinLoss the `rave` family (family_catalog.rs:470-514); as for the plain decisive policies the modes pick
      * the same action in these games and share a kernel.  Two draws per ply, as MR_EPS_MAST. */
     MR_DECISIVE_MAST_WIN = 7,
-    MR_DECISIVE_MAST_WINLOSS = 8
+    MR_DECISIVE_MAST_WINLOSS = 8,
+    /* simulate.rs:852-930 + 538-570  EpsilonGreedy<G, Nst> (strategy.rs:113-126 Ucb1Nst): MAST whose score of an action
+     * is the BIGRAM average of (preceding action, action) once that pair has at least `backoff_threshold` visits, the
+     * unigram (MAST) score otherwise.  The unigram table is mr_submit's mast_in, the bigram table comes from
+     * mr_set_bigrams; the batch's bigram statistics come back through mr_bigram_delta (the unigram ones as the usual
+     * MR_WANT_MAST_DELTA).  Two draws per ply, as MR_EPS_MAST. */
+    MR_EPS_NST = 9
 };
 
 enum mr_flags {
@@ -226,6 +232,26 @@ typedef struct {
 } mr_reply_update;
 int mr_set_replies(mr_ctx *ctx, int game, const uint16_t *replies);
 int mr_reply_updates(mr_ctx *ctx, int slot, mr_reply_update *updates_out, uint32_t *last_win_out);
+
+/* ---- N-gram Selection Technique (MR_EPS_NST) ----
+ * Bigram tables are keyed by COMPACT per-player action indices ("slots"), because the dense id space of Breakthrough /
+ * Knightthrough would be 4096 x 4096 per player:
+ *   Connect4 column (7); Othello square or PASS (65); Hex cell (121);
+ *   Breakthrough src*3 + kind, kind = 0,1,2 = the player's west-diagonal, straight, east-diagonal move
+ *   (dst - src = -9,-8,-7 for Black, +7,+8,+9 for White) (192);
+ *   Knightthrough src*8 + kind, kind = index of the jump in ascending-dst order -17,-15,-10,-6,+6,+10,+15,+17 (512).
+ * TreeStats.player_bigram_actions (search/shared.rs:60-66) crosses the ABI as bigram[2][S][S], S = mr_num_slots(game),
+ * indexed [mover][slot of the preceding action, in the OTHER player's numbering][slot of the action].
+ * mr_set_bigrams copies the table (NULL = empty) and the backoff threshold (Nst::backoff_threshold, default 5); every
+ * later MR_EPS_NST submit uses that copy.  mr_bigram_delta, called after mr_wait and before the slot's next submit,
+ * ADDS NOTHING and OVERWRITES bigram_delta_out[2][S][S] with the playouts' consecutive (preceding action, action)
+ * pairs -- including (leaf's prev_action_plus1, first playout action) -- visits += 1, score += utilities[mover]
+ * (backprop.rs:885-899); the tree-path pairs are the host's. */
+int mr_num_slots(int game);
+int mr_action_slot(int game, int player, uint16_t code); /* -1 when `code` is not an action of `player` */
+int mr_slot_action(int game, int player, int slot);      /* compact action code, -1 when no such action exists */
+int mr_set_bigrams(mr_ctx *ctx, int game, const mr_action_stat *bigram, uint32_t backoff_threshold);
+int mr_bigram_delta(mr_ctx *ctx, int slot, mr_action_stat *bigram_delta_out);
 
 /* Kernel time of the last completed batch on `slot` (max over the ctx's devices), measured with CUDA
  * events on the launching stream; and the number of rollout-kernel launches the ctx has issued. */

@@ -102,6 +102,11 @@ EXPORTS = [
     "mr_set_mast",
     "mr_set_replies",
     "mr_reply_updates",
+    "mr_num_slots",
+    "mr_action_slot",
+    "mr_slot_action",
+    "mr_set_bigrams",
+    "mr_bigram_delta",
     "mr_last_kernel_ms",
     "mr_kernel_launches",
     "mr_allreduce_root",
@@ -145,6 +150,11 @@ def load() -> C.CDLL:
     L.mr_set_mast.argtypes = [vp, i32, vp]
     L.mr_set_replies.argtypes = [vp, i32, vp]
     L.mr_reply_updates.argtypes = [vp, i32, vp, vp]
+    L.mr_num_slots.argtypes = [i32]
+    L.mr_action_slot.argtypes = [i32, i32, C.c_uint16]
+    L.mr_slot_action.argtypes = [i32, i32, i32]
+    L.mr_set_bigrams.argtypes = [vp, i32, vp, u32]
+    L.mr_bigram_delta.argtypes = [vp, i32, vp]
     L.mr_last_kernel_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.mr_kernel_launches.argtypes = [vp]
     L.mr_kernel_launches.restype = C.c_uint64

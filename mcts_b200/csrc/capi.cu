@@ -80,6 +80,10 @@ struct SlotDev {
     DevBuf<uint16_t> lgr_in;                // MR_EPS_LGR: frozen reply table
     DevBuf<unsigned long long> lgr_stamps;  // MR_EPS_LGR: last winning occurrence per (player, preceding action)
     DevBuf<uint32_t> lgr_last;              // MR_EPS_LGR: per leaf, last playout each player did not lose
+    DevBuf<uint64_t> nst_planes;            // MR_EPS_NST: rank planes per context [2][S + 1][KINDS][MAST_BITS]
+    DevBuf<uint32_t> nst_nbits;             // MR_EPS_NST: [2][S + 1]
+    DevBuf<uint16_t> nst_rank_small;        // MR_EPS_NST: [2][S + 1][8] (Connect4)
+    DevBuf<unsigned long long> nst_delta;   // MR_EPS_NST: [2][S][S] packed (visits | score << 32)
     unsigned long long *d_counter = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // what this device covers for the batch in flight
@@ -101,6 +105,7 @@ struct SlotState {
     mr_batch_desc desc{};
     float kernel_ms = 0.f;
     bool lgr_ready = false; // a completed MR_EPS_LGR batch whose updates can still be read
+    bool nst_ready = false; // a completed MR_EPS_NST batch whose bigram delta can still be read
 };
 
 
@@ -119,6 +124,14 @@ struct mr_ctx {
     // Last Good Reply table (mr_set_replies), [2][num_actions] of its game
     std::vector<uint16_t> replies;
     int replies_game = -1;
+    // N-gram Selection Technique (mr_set_bigrams): bigram[2][S][S] of its game and the backoff threshold; the per-context
+    // rank tables built from it and the submit's unigram table
+    std::vector<mr_action_stat> bigram;
+    int bigram_game = -1;
+    uint32_t nst_threshold = 5; // Nst::default (simulate.rs:875-881)
+    std::vector<uint64_t> nst_planes;
+    std::vector<uint32_t> nst_nbits;
+    std::vector<uint16_t> nst_rank_small;
     // NCCL (loaded lazily with dlopen; see mr_comm_*)
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
@@ -248,6 +261,115 @@ int compute_mast_planes(mr_ctx *ctx, int game, const mr_action_stat *mast) {
     return MR_OK;
 }
 
+// ---- compact per-player action slots (the key space of the bigram tables and of the kernels' shared-memory tables) ----
+const int kSlots[MR_NUM_GAMES] = {7, 192, 512, 65, 121};
+const int kKinds[MR_NUM_GAMES] = {1, 3, 8, 1, 2};
+const int kKnightDelta[8] = {-17, -15, -10, -6, 6, 10, 15, 17};
+
+int action_slot(int game, int player, uint32_t code) {
+    if (game == MR_BREAKTHROUGH) {
+        const int src = (int)(code >> 8), dst = (int)(code & 0xffu), kind = dst - src - (player ? 7 : -9);
+        if (src >= 64 || dst >= 64 || kind < 0 || kind > 2 || through_dst(game, player, src, kind) != dst) return -1;
+        return src * 3 + kind;
+    }
+    if (game == MR_KNIGHTTHROUGH) {
+        const int src = (int)(code >> 8), dst = (int)(code & 0xffu);
+        if (src >= 64 || dst >= 64) return -1;
+        for (int q = 0; q < 8; ++q)
+            if (dst - src == kKnightDelta[q] && through_dst(game, player, src, q) == dst) return src * 8 + q;
+        return -1;
+    }
+    return (int)code < kSlots[game] ? (int)code : -1;
+}
+
+int slot_action(int game, int player, int slot) {
+    if (slot < 0 || slot >= kSlots[game]) return -1;
+    if (game == MR_BREAKTHROUGH || game == MR_KNIGHTTHROUGH) {
+        const int kinds = kKinds[game], src = slot / kinds, dst = through_dst(game, player, src, slot % kinds);
+        return dst < 0 ? -1 : (src << 8) | dst;
+    }
+    return slot;
+}
+
+// (cell, kind) of the rank planes -> slot; the inverse of the kernels' plane indexing
+int plane_slot(int game, int cell, int kind) {
+    if (game == MR_BREAKTHROUGH) return cell * 3 + kind;
+    if (game == MR_KNIGHTTHROUGH) return cell * 8 + kind;
+    if (game == MR_HEX11) return kind * 64 + cell;
+    return cell;
+}
+
+// Nst::select_move (simulate.rs:898-930) scores an action by the bigram average of (preceding action, action) once that
+// pair has >= backoff_threshold visits, else by its unigram score.  The score of every action is therefore a function
+// of the CONTEXT (mover, preceding action) alone: the host ranks the mover's real actions once per context (exactly, as
+// for MAST) and ships rank bit-planes [2][S + 1][KINDS][MAST_BITS]; context 0 = no preceding action = the unigram ranks.
+int compute_nst_tables(mr_ctx *ctx, int game, const mr_action_stat *mast) {
+    const int na = kGames[game].num_actions, S = kSlots[game], kinds = kKinds[game];
+    const bool have_bigram = ctx->bigram_game == game && !ctx->bigram.empty();
+    const size_t n_ctx = (size_t)2 * (S + 1);
+    ctx->nst_planes.assign(n_ctx * kinds * MAST_BITS, 0);
+    ctx->nst_nbits.assign(n_ctx, 0);
+    ctx->nst_rank_small.assign(n_ctx * 8, 0);
+    struct Act {
+        int cell, kind, slot;
+        Rational uni;
+    };
+    for (int pl = 0; pl < 2; ++pl) {
+        const mr_action_stat *tab = mast + (size_t)pl * na;
+        std::vector<Act> acts;
+        for (int cell = 0; cell < 64; ++cell)
+            for (int q = 0; q < kinds; ++q) {
+                const int id = mast_action_id(game, pl, cell, q);
+                if (id < 0) continue;
+                const mr_action_stat &e = tab[id];
+                if (e.visits >= (1u << 26))
+                    return fail(ctx, MR_ERR_INVALID, "MAST visits %u >= 2^26: exact score comparison not guaranteed", e.visits);
+                acts.push_back({cell, q, plane_slot(game, cell, q), e.visits > 0 ? Rational{(int64_t)e.score, (int64_t)e.visits} : Rational{1, 1}});
+            }
+        std::vector<Rational> val(acts.size()), uniq;
+        size_t unigram_ctx = 0; // index of the context whose tables equal the unigram ones (context 0 of this player)
+        for (int c = 0; c <= S; ++c) {
+            const size_t ci = (size_t)pl * (S + 1) + c;
+            bool differs = false;
+            for (size_t a = 0; a < acts.size(); ++a) {
+                val[a] = acts[a].uni;
+                if (c > 0 && have_bigram) {
+                    const mr_action_stat &b = ctx->bigram[((size_t)pl * S + (c - 1)) * S + acts[a].slot];
+                    if (b.visits >= (1u << 26))
+                        return fail(ctx, MR_ERR_INVALID, "bigram visits %u >= 2^26: exact score comparison not guaranteed", b.visits);
+                    if (b.visits > 0 && b.visits >= ctx->nst_threshold) {
+                        val[a] = {(int64_t)b.score, (int64_t)b.visits};
+                        differs = true;
+                    }
+                }
+            }
+            if (c == 0) unigram_ctx = ci;
+            if (c > 0 && !differs) { // no pair of this context has reached the threshold: the unigram tables
+                std::copy_n(&ctx->nst_planes[unigram_ctx * kinds * MAST_BITS], (size_t)kinds * MAST_BITS, &ctx->nst_planes[ci * kinds * MAST_BITS]);
+                ctx->nst_nbits[ci] = ctx->nst_nbits[unigram_ctx];
+                std::copy_n(&ctx->nst_rank_small[unigram_ctx * 8], 8, &ctx->nst_rank_small[ci * 8]);
+                continue;
+            }
+            uniq.assign(val.begin(), val.end());
+            uniq.push_back({1, 1});
+            std::sort(uniq.begin(), uniq.end(), rat_less);
+            uniq.erase(std::unique(uniq.begin(), uniq.end(), rat_eq), uniq.end());
+            uint32_t nbits = 0;
+            while ((1u << nbits) < uniq.size()) ++nbits;
+            if (nbits > (uint32_t)MAST_BITS) return fail(ctx, MR_ERR_INVALID, "too many distinct NST values (%zu)", uniq.size());
+            ctx->nst_nbits[ci] = nbits;
+            uint64_t *planes = &ctx->nst_planes[ci * kinds * MAST_BITS];
+            for (size_t a = 0; a < acts.size(); ++a) {
+                const uint32_t rk = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), val[a], rat_less) - uniq.begin());
+                for (uint32_t b = 0; b < nbits; ++b)
+                    if ((rk >> b) & 1u) planes[(size_t)acts[a].kind * MAST_BITS + b] |= 1ull << acts[a].cell;
+                if (game == MR_CONNECT4) ctx->nst_rank_small[ci * 8 + acts[a].cell] = (uint16_t)rk;
+            }
+        }
+    }
+    return MR_OK;
+}
+
 // util.rs:129-132
 const uint32_t kPrimes[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991,
                               53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693};
@@ -301,18 +423,20 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
             return fail(ctx, MR_ERR_INVALID, "the reply table was set for game %d, the batch is game %u", ctx->replies_game, d->game);
         if ((uint64_t)d->n_leaves * d->playouts_per_leaf >= (1ull << 37)) return fail(ctx, MR_ERR_INVALID, "batch too large for MR_EPS_LGR");
     }
+    if (d->policy == MR_EPS_NST && ctx->bigram_game >= 0 && ctx->bigram_game != (int)d->game)
+        return fail(ctx, MR_ERR_INVALID, "the bigram table was set for game %d, the batch is game %u", ctx->bigram_game, d->game);
     if ((d->flags & MR_WANT_TRACE) && d->max_trace == 0) return fail(ctx, MR_ERR_INVALID, "MR_WANT_TRACE needs max_trace > 0");
     uint32_t cap = 0;
     // (the Hex fill-then-search kernel derives AMAF from board masks; every per-ply kernel uses the slot trace)
     const bool hex_fast = d->game == MR_HEX11 && d->policy == MR_UNIFORM && !(d->flags & MR_WANT_MAST_DELTA);
     const bool needs_scratch = (d->flags & MR_WANT_MAST_DELTA) || ((d->flags & MR_WANT_AMAF) && !hex_fast) ||
-                               d->policy == MR_EPS_LGR;
+                               d->policy == MR_EPS_LGR || d->policy == MR_EPS_NST;
     if (needs_scratch) {
         const uint32_t bound = kGames[d->game].depth_bound;
         cap = d->max_playout_depth ? d->max_playout_depth : bound;
         if (bound && cap > bound) cap = bound;
         if (cap == 0)
-            return fail(ctx, MR_ERR_INVALID, "AMAF / MAST-delta / LGR need a bounded playout: set max_playout_depth for game %u", d->game);
+            return fail(ctx, MR_ERR_INVALID, "AMAF / MAST-delta / LGR / NST need a bounded playout: set max_playout_depth for game %u", d->game);
         if (cap > 4096) return fail(ctx, MR_ERR_INVALID, "max_playout_depth %u too large for AMAF / MAST-delta / LGR (limit 4096)", cap);
     }
     if ((uint64_t)d->n_leaves * d->playouts_per_leaf > (1ull << 40)) return fail(ctx, MR_ERR_INVALID, "batch too large");
@@ -474,6 +598,10 @@ void mr_destroy(mr_ctx *ctx) {
             sd.lgr_in.release();
             sd.lgr_stamps.release();
             sd.lgr_last.release();
+            sd.nst_planes.release();
+            sd.nst_nbits.release();
+            sd.nst_rank_small.release();
+            sd.nst_delta.release();
             if (sd.d_counter) cudaFree(sd.d_counter);
             if (sd.ev_begin) cudaEventDestroy(sd.ev_begin);
             if (sd.ev_end) cudaEventDestroy(sd.ev_end);
@@ -524,6 +652,10 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
     if (rc != MR_OK) return rc;
     if (policy_uses_mast((int)desc->policy)) {
         rc = compute_mast_planes(ctx, (int)desc->game, mast_in);
+        if (rc != MR_OK) return rc;
+    }
+    if (desc->policy == MR_EPS_NST) {
+        rc = compute_nst_tables(ctx, (int)desc->game, mast_in);
         if (rc != MR_OK) return rc;
     }
     const int nd = (int)ctx->dev.size();
@@ -589,6 +721,24 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
                 kp.lgr_in = sd.lgr_in.d;
             }
         }
+        if (desc->policy == MR_EPS_NST) {
+            const size_t S = (size_t)kSlots[desc->game];
+            CUDA_TRY(ctx, sd.nst_planes.reserve(ctx->nst_planes.size(), true));
+            CUDA_TRY(ctx, sd.nst_nbits.reserve(ctx->nst_nbits.size(), true));
+            CUDA_TRY(ctx, sd.nst_rank_small.reserve(ctx->nst_rank_small.size(), true));
+            CUDA_TRY(ctx, sd.nst_delta.reserve(2 * S * S, true));
+            memcpy(sd.nst_planes.h, ctx->nst_planes.data(), sizeof(uint64_t) * ctx->nst_planes.size());
+            memcpy(sd.nst_nbits.h, ctx->nst_nbits.data(), sizeof(uint32_t) * ctx->nst_nbits.size());
+            memcpy(sd.nst_rank_small.h, ctx->nst_rank_small.data(), sizeof(uint16_t) * ctx->nst_rank_small.size());
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_planes.d, sd.nst_planes.h, sizeof(uint64_t) * ctx->nst_planes.size(), cudaMemcpyHostToDevice, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_nbits.d, sd.nst_nbits.h, sizeof(uint32_t) * ctx->nst_nbits.size(), cudaMemcpyHostToDevice, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_rank_small.d, sd.nst_rank_small.h, sizeof(uint16_t) * ctx->nst_rank_small.size(), cudaMemcpyHostToDevice, dv.stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.nst_delta.d, 0, sizeof(unsigned long long) * 2 * S * S, dv.stream));
+            kp.nst_planes = sd.nst_planes.d;
+            kp.nst_nbits = sd.nst_nbits.d;
+            kp.nst_rank_small = sd.nst_rank_small.d;
+            kp.nst_delta = sd.nst_delta.d;
+        }
         CUDA_TRY(ctx, cudaEventRecord(sd.ev_begin, dv.stream));
         rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter, slot);
         if (rc != MR_OK) return rc;
@@ -603,6 +753,10 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
         if (desc->policy == MR_EPS_LGR) {
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_stamps.h, sd.lgr_stamps.d, sizeof(unsigned long long) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_last.h, sd.lgr_last.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, dv.stream));
+        }
+        if (desc->policy == MR_EPS_NST) {
+            const size_t S = (size_t)kSlots[desc->game];
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_delta.h, sd.nst_delta.d, sizeof(unsigned long long) * 2 * S * S, cudaMemcpyDeviceToHost, dv.stream));
         }
         const uint64_t gb = sd.g_begin, ge = sd.g_end;
         if (ge > gb) {
@@ -619,6 +773,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
     }
     ss.busy = true;
     ss.lgr_ready = false;
+    ss.nst_ready = false;
     ss.desc = *desc;
     return MR_OK;
 }
@@ -647,6 +802,7 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
     }
     ss.kernel_ms = worst_ms;
     ss.lgr_ready = d.policy == MR_EPS_LGR;
+    ss.nst_ready = d.policy == MR_EPS_NST;
     memset(out, 0, sizeof(mr_leaf_result) * n);
     if (amaf_out && (d.flags & MR_WANT_AMAF)) memset(amaf_out, 0, sizeof(mr_action_stat) * (size_t)n * 2 * na);
     if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) memset(mast_delta_out, 0, sizeof(mr_action_stat) * 2 * na);
@@ -724,6 +880,54 @@ int mr_reply_updates(mr_ctx *ctx, int slot, mr_reply_update *updates_out, uint32
     return MR_OK;
 }
 
+int mr_num_slots(int game) { return (game < 0 || game >= MR_NUM_GAMES) ? 0 : kSlots[game]; }
+
+int mr_action_slot(int game, int player, uint16_t code) {
+    if (game < 0 || game >= MR_NUM_GAMES || player < 0 || player > 1) return -1;
+    return action_slot(game, player, code);
+}
+
+int mr_slot_action(int game, int player, int slot) {
+    if (game < 0 || game >= MR_NUM_GAMES || player < 0 || player > 1) return -1;
+    return slot_action(game, player, slot);
+}
+
+int mr_set_bigrams(mr_ctx *ctx, int game, const mr_action_stat *bigram, uint32_t backoff_threshold) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (game < 0 || game >= MR_NUM_GAMES) return fail(ctx, MR_ERR_INVALID, "mr_set_bigrams: unknown game %d", game);
+    ctx->nst_threshold = backoff_threshold;
+    if (!bigram) {
+        ctx->bigram.clear();
+        ctx->bigram_game = -1;
+        return MR_OK;
+    }
+    const size_t S = (size_t)kSlots[game];
+    ctx->bigram.assign(bigram, bigram + 2 * S * S);
+    ctx->bigram_game = game;
+    return MR_OK;
+}
+
+int mr_bigram_delta(mr_ctx *ctx, int slot, mr_action_stat *bigram_delta_out) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (slot < 0 || slot >= MR_NUM_SLOTS) return fail(ctx, MR_ERR_INVALID, "slot %d out of range", slot);
+    SlotState &ss = ctx->slot[slot];
+    if (ss.busy || !ss.nst_ready)
+        return fail(ctx, MR_ERR_INVALID, "slot %d holds no completed MR_EPS_NST batch (call mr_wait first)", slot);
+    if (!bigram_delta_out) return fail(ctx, MR_ERR_INVALID, "null bigram delta buffer");
+    const size_t S = (size_t)kSlots[ss.desc.game], cnt = 2 * S * S;
+    memset(bigram_delta_out, 0, sizeof(mr_action_stat) * cnt);
+    for (Device &dv : ctx->dev) {
+        SlotDev &sd = dv.slot[slot];
+        if (sd.g_end == sd.g_begin) continue;
+        for (size_t i = 0; i < cnt; ++i) {
+            const unsigned long long v = sd.nst_delta.h[i];
+            bigram_delta_out[i].visits += (uint32_t)v;
+            bigram_delta_out[i].score += (int32_t)(uint32_t)(v >> 32);
+        }
+    }
+    return MR_OK;
+}
+
 int mr_playout_batch(mr_ctx *ctx, const mr_batch_desc *desc, const mr_leaf *leaves, const mr_action_stat *mast_in,
                      mr_leaf_result *out, mr_action_stat *amaf_out, mr_action_stat *mast_delta_out, uint16_t *trace_out,
                      mr_playout_record *rec_out, mr_leaf *final_out) {
@@ -742,6 +946,7 @@ int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, c
     if (desc->flags & (MR_WANT_TRACE | MR_WANT_FINAL_STATE))
         return fail(ctx, MR_ERR_INVALID, "trace / final-state outputs are not available on the device-resident path");
     if (desc->policy == MR_EPS_LGR) return fail(ctx, MR_ERR_UNSUPPORTED, "MR_EPS_LGR is not available on the device-resident path");
+    if (desc->policy == MR_EPS_NST) return fail(ctx, MR_ERR_UNSUPPORTED, "MR_EPS_NST is not available on the device-resident path");
     kernel_fn fn = nullptr;
     uint32_t trace_cap = 0;
     int rc = validate(ctx, desc, ctx->mast_game == (int)desc->game, &fn, &trace_cap);

@@ -14,7 +14,7 @@ constexpr int THREADS_PER_BLOCK = WARPS_PER_BLOCK * 32;
 // kernel-side name of DecisiveMove<EpsilonGreedy<Mast>>: the ABI's Win and WinLoss modes share one instantiation
 constexpr int MR_DECISIVE_MAST = MR_DECISIVE_MAST_WIN;
 __host__ __device__ constexpr bool policy_uses_mast(int policy) {
-    return policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN || policy == MR_DECISIVE_MAST_WINLOSS;
+    return policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN || policy == MR_DECISIVE_MAST_WINLOSS || policy == MR_EPS_NST;
 }
 
 constexpr int MAST_KINDS = 8;  // move kinds per source cell: 3 (Breakthrough) or 8 (Knightthrough)
@@ -71,6 +71,12 @@ struct KernelParams {
     const uint16_t *lgr_in;          // [2][NA]: 1 + compact code of the reply to the preceding action id, 0 = none
     unsigned long long *lgr_stamps;  // [2][NA]: ((g + 1) << 26) | ((4096 + ply) << 13) | reply action id, max-merged
     uint32_t *lgr_last;              // [n_leaves][2]: 1 + last playout index the player did not lose, max-merged
+    // N-gram Selection Technique (MR_EPS_NST): rank planes per CONTEXT (mover, 1 + slot of the preceding action; 0 = no
+    // preceding action = the unigram ranks), resolved on the host from the bigram / unigram tables and the backoff
+    const uint64_t *nst_planes;      // [2][NSLOTS + 1][KINDS][MAST_BITS]
+    const uint32_t *nst_nbits;       // [2][NSLOTS + 1]
+    const uint16_t *nst_rank_small;  // Connect4: [2][NSLOTS + 1][8] ranks per column
+    unsigned long long *nst_delta;   // [2][NSLOTS][NSLOTS]: visits in the low word, score (two's complement) in the high word
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

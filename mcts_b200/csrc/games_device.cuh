@@ -62,6 +62,7 @@ struct Connect4 {
     static constexpr int MIN_BLOCKS = 1; // a 64-register cap (8 blocks/SM) measured 4% slower
     static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
     static constexpr int NSLOTS = 7; // compact per-player statistic slots (== action ids here)
+    static constexpr int KINDS = 1;
     static constexpr bool MASK_AMAF = false;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
     __device__ static uint32_t code_to_slot(uint32_t pl, uint32_t code) { return code < 7u ? code : 0u; }
@@ -80,6 +81,10 @@ struct Connect4 {
     uint32_t n_open;
     uint32_t rt_parity;
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + compact code of the recorded reply for this ply, 0 = none / exploring
+    // MR_EPS_NST: this ply's context (mover, preceding action) rank planes / per-column ranks, set by the kernel
+    const uint64_t (*nst_planes)[MAST_BITS];
+    uint32_t nst_nbits;
+    const uint16_t *nst_ranks;
 
     __device__ static uint64_t to_colbyte(uint64_t rm) { // reference row-major (idx = row*7 + col) -> col*8 + row
         uint64_t out = 0;
@@ -169,7 +174,7 @@ struct Connect4 {
     __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         const uint64_t moves = (all + BOTTOM) & BOARD; // one bit per open column, ascending column order
         uint64_t bit;
-        constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST;
+        constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST;
         if (POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_MAST) {
             // first legal column (ascending) whose drop wins for the mover (simulate.rs:662-670); a Connect4
             // move cannot lose immediately, a drawing move exists only as the 42nd stone (the single action)
@@ -215,7 +220,8 @@ struct Connect4 {
             for (int c = 0; c < 7; ++c) {
                 const uint64_t b = moves & (0xFFull << (8 * c));
                 if (b) {
-                    const uint32_t key = ((uint32_t)p.mast_rank_small[pl][c] << 8) | (255u - visiting_rank(i, i0, n_open, inv, rcp));
+                    const uint32_t rk = POLICY == MR_EPS_NST ? nst_ranks[c] : p.mast_rank_small[pl][c];
+                    const uint32_t key = (rk << 8) | (255u - visiting_rank(i, i0, n_open, inv, rcp));
                     if (key >= best_key) { // keys of open columns are distinct; >= lets a zero key win the first time
                         best_key = key;
                         bit = b;
@@ -291,6 +297,10 @@ struct ThroughBase {
     uint64_t black, white;
     uint32_t rt_parity;
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + compact code (src << 8 | dst) of the recorded reply, 0 = none / exploring
+    // MR_EPS_NST: this ply's context (mover, preceding action) rank planes / per-column ranks, set by the kernel
+    const uint64_t (*nst_planes)[MAST_BITS];
+    uint32_t nst_nbits;
+    const uint16_t *nst_ranks;
 
     __device__ static int prepare(Shared &sh, const mr_leaf &leaf, uint32_t lane) {
         if (lane == 0) {
@@ -337,7 +347,8 @@ struct Breakthrough : ThroughBase {
     static constexpr int MIN_BLOCKS = 6; // <= 80 registers: 24 warps/SM instead of 20, +4.7% on the MAST kernel (measured)
     // the MAST kernel gains another 5% at 7 blocks/SM (<= 72 registers); the uniform kernel does not (measured)
     static constexpr int min_blocks(int policy) { return policy == MR_EPS_MAST ? 7 : MIN_BLOCKS; }
-    static constexpr int NSLOTS = 192; // src*3 + kind (W,F,E)
+    static constexpr int NSLOTS = 192;
+    static constexpr int KINDS = 3; // src*3 + kind (W,F,E)
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
         const uint32_t src = slot / 3u, kind = slot - src * 3u;
         return src * 64u + (uint32_t)((int)src + (pl ? 7 : -9) + (int)kind);
@@ -405,6 +416,7 @@ struct Knightthrough : ThroughBase {
     static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
     static constexpr bool ROLLED = true; // the step is large (8 masks, adder tree): a rolled window fits the I-cache (+14%)
     static constexpr int NSLOTS = 512; // src*8 + kind (ascending-dst jump order)
+    static constexpr int KINDS = 8;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
         const uint32_t src = slot >> 3, kind = slot & 7u;
         return src * 64u + (uint32_t)((int)src + delta(kind));
@@ -483,7 +495,7 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
     bool have = false, idx_set = false;
     // DecisiveMove<.., inner> first tries the decisive scan and falls through to its inner strategy (simulate.rs:742-760)
     constexpr bool DECISIVE = POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI || POLICY == MR_DECISIVE_MAST;
-    constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST;
+    constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST;
     if (DECISIVE) {
         // DecisiveMove<Win> (simulate.rs:662-687): the first action in list order whose child is a win for the
         // mover.  A Breakthrough move wins iff it lands on the far wall, i.e. iff its source is on the row next
@@ -539,7 +551,8 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
     if (MAST_INNER && !have && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
         const uint32_t pl = is_white ? 1u : 0u;
         uint64_t cand[3] = {W, F, E};
-        mast_argmax<3>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
+        if (POLICY == MR_EPS_NST) mast_argmax<3>(cand, nst_planes, nst_nbits);
+        else mast_argmax<3>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
         const uint64_t cs = cand[0] ^ cand[1] ^ cand[2];
         const uint64_t cc = (cand[0] & cand[1]) | (cand[0] & cand[2]) | (cand[1] & cand[2]);
         const uint32_t m = __popcll(cs) + 2u * __popcll(cc);
@@ -671,7 +684,7 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
     uint32_t idx = 0, src = 0, kind = 0;
     bool have = false, idx_set = false;
     constexpr bool DECISIVE = POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI || POLICY == MR_DECISIVE_MAST;
-    constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST;
+    constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST;
     if (DECISIVE) {
         // first action in list order that lands on the far wall (simulate.rs:662-687); a jump of two rows wins
         // from the two rows next to it, a jump of one row from the row next to it
@@ -744,7 +757,8 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
         uint64_t cand[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) cand[q] = M[q];
-        mast_argmax<8>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
+        if (POLICY == MR_EPS_NST) mast_argmax<8>(cand, nst_planes, nst_nbits);
+        else mast_argmax<8>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
         uint32_t m = 0;
         uint64_t any = 0;
 #pragma unroll
@@ -825,6 +839,7 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
 struct Othello {
     static constexpr int NA = 65;
     static constexpr int NSLOTS = 65;
+    static constexpr int KINDS = 1;
     static constexpr bool MASK_AMAF = false;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
     __device__ static uint32_t code_to_slot(uint32_t pl, uint32_t code) { return code < 65u ? code : 0u; }
@@ -842,6 +857,9 @@ struct Othello {
     uint32_t last_pass;
     uint32_t rt_parity; // parity of the current ply inside its window (PARITY == 2 call sites)
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + square of the recorded reply (65 = PASS), 0 = none / exploring
+    const uint64_t (*nst_planes)[MAST_BITS]; // MR_EPS_NST: this ply's context rank planes, set by the kernel
+    uint32_t nst_nbits;
+    const uint16_t *nst_ranks;
 
     // (measured: writing the high word of right shifts as a multiply-high to move it to the FMA pipe is SLOWER,
     // 13.9 ms vs 13.2 ms per 2^24 playouts: IMAD.HI is half rate)
@@ -968,12 +986,13 @@ struct Othello {
                 }
             }
         }
-        if ((POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST) && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+        if ((POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST) && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
             // Mast::select_move (simulate.rs:824-848): bit-sliced arg-max of the rank planes over the legal squares,
             // then random_best's visiting order among the maximal ones (as for Breakthrough, with one move kind)
             const uint32_t pl = is_white ? 1u : 0u;
             uint64_t cand[1] = {moves};
-            mast_argmax<1>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
+            if (POLICY == MR_EPS_NST) mast_argmax<1>(cand, nst_planes, nst_nbits);
+            else mast_argmax<1>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
             const uint32_t m = __popcll(cand[0]);
             const uint32_t r = mulhi(x0, 16u * n);
             const uint32_t i0 = r >> 4;
@@ -1046,6 +1065,7 @@ struct Othello {
 struct Hex11 {
     static constexpr int NA = 121;
     static constexpr int NSLOTS = 121;
+    static constexpr int KINDS = 2; // the two 64-bit halves of the board
     // a Hex playout plays every cell at most once, so its (action, player) occurrences are exactly
     // final stones minus leaf stones: AMAF is accumulated from board masks, no move trace needed
     static constexpr bool MASK_AMAF = true;

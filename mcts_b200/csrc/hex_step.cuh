@@ -37,6 +37,9 @@ struct HexStep : Hex11 {
     uint32_t n_empty;
     uint32_t rt_parity;
     uint32_t lgr_reply;
+    const uint64_t (*nst_planes)[MAST_BITS]; // MR_EPS_NST: this ply's context rank planes, set by the kernel
+    uint32_t nst_nbits;
+    const uint16_t *nst_ranks;
 
     __device__ static constexpr B128 nc0() { return inv(col_mask(0)); }
     __device__ static constexpr B128 nc10() { return inv(col_mask(10)); }
@@ -142,7 +145,7 @@ struct HexStep : Hex11 {
     __device__ int step_pl(uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         constexpr int OP = 1 - PL;
         constexpr bool DECISIVE = POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI || POLICY == MR_DECISIVE_MAST;
-        constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST;
+        constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST;
         constexpr B128 BM = board_mask();
         const B128 empties = bandn(BM, bor(s[0], s[1]));
         const uint32_t n = n_empty;
@@ -176,7 +179,8 @@ struct HexStep : Hex11 {
             // Mast::select_move (simulate.rs:824-848): bit-sliced arg-max over the empty cells (the two 64-bit halves
             // of the board ride the "kind" dimension of the rank planes), then random_best's visiting order
             uint64_t cand[2] = {mk64(empties.w[0], empties.w[1]), mk64(empties.w[2], empties.w[3])};
-            mast_argmax<2>(cand, p.mast_planes[PL], p.mast_nbits[PL]);
+            if (POLICY == MR_EPS_NST) mast_argmax<2>(cand, nst_planes, nst_nbits);
+            else mast_argmax<2>(cand, p.mast_planes[PL], p.mast_nbits[PL]);
             const B128 c = B128{{lo32(cand[0]), hi32(cand[0]), lo32(cand[1]), hi32(cand[1])}};
             const uint32_t m = count(c);
             const uint32_t r = mulhi(x0, 16u * n);

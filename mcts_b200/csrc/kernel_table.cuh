@@ -35,6 +35,7 @@ kernel_fn pick_all_policies(int policy, int v) {
     if (policy == MR_DECISIVE_ANTI) return pick_variant<G, MR_DECISIVE_ANTI>(v);
     if (policy == MR_EPS_LGR) return pick_variant<G, MR_EPS_LGR>(v);
     if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<G, MR_DECISIVE_MAST>(v);
+    if (policy == MR_EPS_NST) return pick_variant<G, MR_EPS_NST>(v);
     return nullptr;
 }
 

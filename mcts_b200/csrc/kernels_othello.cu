@@ -10,6 +10,7 @@ kernel_fn pick_othello(int policy, int v) {
     if (policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN) return pick_variant<Othello, MR_EPS_MAST>(v);
     if (policy == MR_DECISIVE_ANTI) return pick_variant<Othello, MR_DECISIVE_ANTI>(v);
     if (policy == MR_EPS_LGR) return pick_variant<Othello, MR_EPS_LGR>(v);
+    if (policy == MR_EPS_NST) return pick_variant<Othello, MR_EPS_NST>(v);
     return nullptr;
 }
 cudaError_t upload_tables_othello(const uint8_t (*stride)[16], const uint8_t (*inv)[16], const uint32_t *rcp) {

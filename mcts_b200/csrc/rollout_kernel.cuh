@@ -59,8 +59,10 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
     constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
     constexpr bool MASK_AMAF = WANT_AMAF && G::MASK_AMAF;
     constexpr bool IS_LGR = POLICY == MR_EPS_LGR;
+    constexpr bool IS_NST = POLICY == MR_EPS_NST;
+    constexpr bool TRACK_PREV = IS_LGR || IS_NST; // the lane remembers the slot of the preceding action
     constexpr bool PAIR_DRAWS = policy_uses_mast(POLICY) || IS_LGR; // two Philox words per ply
-    constexpr bool NEED_SCRATCH = WANT_MAST || (WANT_AMAF && !G::MASK_AMAF) || IS_LGR; // per-lane slot trace
+    constexpr bool NEED_SCRATCH = WANT_MAST || (WANT_AMAF && !G::MASK_AMAF) || IS_LGR || IS_NST; // per-lane slot trace
     constexpr int WINDOW = PAIR_DRAWS ? 2 : 4;
 
     __shared__ __align__(16) mr_leaf s_leaf[WARPS_PER_BLOCK];
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
         // LGR: the action that led to the leaf (playout()'s prev_action), as 1 + its slot in the numbering of the
         // player who made it (the opponent of the leaf's mover); 0 = none
         uint32_t leaf_prev_slot1 = 0;
-        if constexpr (IS_LGR) {
+        if constexpr (TRACK_PREV) {
             const uint32_t pa = s_leaf[warp].prev_action_plus1;
             if (pa) leaf_prev_slot1 = G::code_to_slot(1u - (leaf_turn & 1u), pa - 1u) + 1u;
         }
@@ -209,9 +211,17 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                                 }
                                 st.lgr_reply = reply;
                             }
+                            if constexpr (IS_NST) {
+                                // Nst::select_move (simulate.rs:898-930): the ranks of this ply's context
+                                const uint32_t pl = (leaf_turn ^ (par == 2 ? st.rt_parity : (uint32_t)par)) & 1u;
+                                const uint32_t ctx = pl * ((uint32_t)G::NSLOTS + 1u) + prev_slot1;
+                                st.nst_planes = reinterpret_cast<const uint64_t(*)[MAST_BITS]>(p.nst_planes + (size_t)ctx * G::KINDS * MAST_BITS);
+                                st.nst_nbits = p.nst_nbits[ctx];
+                                st.nst_ranks = p.nst_rank_small + (size_t)ctx * 8u;
+                            }
                             const int code = st.template step<POLICY, par>(sh, x0, x1, p, action, slot);
                             if (code & ST_MOVED) {
-                                if (IS_LGR) prev_slot1 = slot + 1u;
+                                if (TRACK_PREV) prev_slot1 = slot + 1u;
                                 if (WANT_TRACE && p.trace) {
                                     if (depth < p.max_trace)
                                         p.trace[((size_t)li * p.k + pid) * p.max_trace + depth] = (uint16_t)action;
@@ -331,6 +341,13 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                                 const uint32_t inc = 1u + ((uint32_t)u << 16);
                                 if (WANT_MAST && p.mast_delta) atomicAdd(&mast_tab[pl * G::NSLOTS + slot], inc);
                                 if (WANT_AMAF && !G::MASK_AMAF && p.amaf) atomicAdd(&amaf_tab[pl * G::NSLOTS + slot], inc);
+                                if constexpr (IS_NST) {
+                                    // backprop.rs:885-899: every consecutive (preceding action, action) pair of the playout
+                                    const uint32_t prev1 = t > 0 ? (uint32_t)scratch[(t - 1u) * 32u + f] + 1u : leaf_prev_slot1;
+                                    if (p.nst_delta && prev1)
+                                        atomicAdd(&p.nst_delta[((size_t)pl * G::NSLOTS + prev1 - 1u) * G::NSLOTS + slot],
+                                                  1ull + ((unsigned long long)(uint32_t)u << 32));
+                                }
                                 if constexpr (IS_LGR) {
                                     // backprop.rs:908-923: a reply is recorded when its player's utility is the trial's
                                     // maximum (u >= 0 here); last write wins == the largest (playout index, ply) stamp

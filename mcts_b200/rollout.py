@@ -43,6 +43,7 @@ class Policy(IntEnum):
     EPS_LGR = 6
     DECISIVE_MAST_WIN = 7
     DECISIVE_MAST_WINLOSS = 8
+    EPS_NST = 9
 
 
 class Outcome(IntEnum):  # TerminalStatus (mcts/src/game.rs:117-122)
@@ -61,7 +62,7 @@ class EndType(IntEnum):  # simulate.rs:15-20 (+ the no-actions ending, :112-116)
 WANT_AMAF, WANT_MAST_DELTA, WANT_TRACE, WANT_FINAL_STATE = 1, 2, 4, 8
 
 # BackpropFlags bits (mcts/src/strategies/mcts/config.rs:11-30)
-BACKPROP_GRAVE, BACKPROP_GLOBAL, BACKPROP_AMAF, BACKPROP_LGR = 1, 2, 4, 16
+BACKPROP_GRAVE, BACKPROP_GLOBAL, BACKPROP_AMAF, BACKPROP_NST, BACKPROP_LGR = 1, 2, 4, 8, 16
 
 OTHELLO_PASS = 64
 _INITIAL = {
@@ -110,6 +111,19 @@ def terminal_status(game: Game, state: np.ndarray) -> Outcome:
 
 def num_actions(game: Game) -> int:
     return _lib.load().mr_num_actions(int(game))
+
+
+def num_slots(game: Game) -> int:
+    """Size of the compact per-player action index that keys the bigram (NST) tables."""
+    return _lib.load().mr_num_slots(int(game))
+
+
+def action_slot(game: Game, player: int, code: int) -> int:
+    return _lib.load().mr_action_slot(int(game), int(player), int(code))
+
+
+def slot_action(game: Game, player: int, slot: int) -> int:
+    return _lib.load().mr_slot_action(int(game), int(player), int(slot))
 
 
 # ---- the strategy objects: same names and knobs as the reference ----
@@ -174,6 +188,18 @@ class EpsilonGreedyLgr:
 
 
 @dataclass(frozen=True)
+class EpsilonGreedyNst:
+    """EpsilonGreedy<G, Nst> (simulate.rs:485-570, 852-930; strategy.rs:113-126 `Ucb1Nst`)."""
+
+    epsilon: float = 0.1
+    backoff_threshold: int = 5  # Nst::default (simulate.rs:875-881)
+    policy = Policy.EPS_NST
+
+    def backprop_flags(self) -> int:
+        return BACKPROP_GLOBAL | BACKPROP_NST  # Nst::backprop_flags (simulate.rs:894-896)
+
+
+@dataclass(frozen=True)
 class DecisiveMoveMast:
     """DecisiveMove<G, EpsilonGreedy<G, Mast>> (mcts-tune SimulateSpec::DecisiveMoveMast): mode "win" is the
     `ucb1_tuned_dm_mast` family, "win_loss" the `rave` family (family_catalog.rs:470-514)."""
@@ -225,6 +251,7 @@ class BatchResult:
     kernel_ms: float = 0.0
     reply_updates: np.ndarray | None = None  # REPLY_UPDATE_DTYPE [2][NA]  (Policy.EPS_LGR)
     last_win: np.ndarray | None = None  # u32 [n_leaves][2]                (Policy.EPS_LGR)
+    bigram_delta: np.ndarray | None = None  # STAT_DTYPE [2][S][S]           (Policy.EPS_NST)
 
     def utilities_sum(self) -> np.ndarray:
         """Per leaf, per player: sum of utilities = wins[p] - losses[p] (node.rs:673-681 aggregated)."""
@@ -358,7 +385,12 @@ class GpuRollout:
             upd = np.zeros((2, self.na), dtype=REPLY_UPDATE_DTYPE)
             last = np.zeros((n, 2), dtype=np.uint32)
             self._check(self.lib.mr_reply_updates(self._h, slot, ptr(upd), ptr(last)))
-        return BatchResult(res, amaf, delta, trace, rec, final, ms.value, upd, last)
+        bigram = None
+        if d.policy == int(Policy.EPS_NST):
+            ns = self.lib.mr_num_slots(int(self.game))
+            bigram = np.zeros((2, ns, ns), dtype=STAT_DTYPE)
+            self._check(self.lib.mr_bigram_delta(self._h, slot, ptr(bigram)))
+        return BatchResult(res, amaf, delta, trace, rec, final, ms.value, upd, last, bigram)
 
     def simulate_many(self, leaves: np.ndarray, k: int, **kw) -> BatchResult:
         """k playouts of every leaf (search/core.rs:218-258 for a batch of leaves)."""
@@ -416,6 +448,19 @@ class GpuRollout:
         if tab.shape != (2, self.na):
             raise ValueError(f"reply table must have shape (2, {self.na})")
         self._check(self.lib.mr_set_replies(self._h, int(self.game), ptr(tab)))
+
+    def set_bigrams(self, bigram: np.ndarray | None, backoff_threshold: int | None = None) -> None:
+        """TreeStats.player_bigram_actions for Policy.EPS_NST batches: STAT_DTYPE [2][S][S], S = num_slots(game), indexed
+        [mover][slot of the preceding action in the other player's numbering][slot of the action].  None = empty."""
+        thr = getattr(self.strategy, "backoff_threshold", 5) if backoff_threshold is None else backoff_threshold
+        if bigram is None:
+            self._check(self.lib.mr_set_bigrams(self._h, int(self.game), None, int(thr)))
+            return
+        ns = self.lib.mr_num_slots(int(self.game))
+        tab = np.ascontiguousarray(bigram, dtype=STAT_DTYPE)
+        if tab.shape != (2, ns, ns):
+            raise ValueError(f"bigram table must have shape (2, {ns}, {ns})")
+        self._check(self.lib.mr_set_bigrams(self._h, int(self.game), ptr(tab), int(thr)))
 
     def launch_device(
         self, d_leaves: int, d_results: int, n_leaves: int, k: int, *, stream: int = 0, device_index: int = 0,

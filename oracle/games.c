@@ -12,6 +12,7 @@
 #include "oracle.h"
 #include "bitboard.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 bb_t bb_wall_table[BB_WALL_MAX_DIM + 1][BB_WALL_MAX_DIM + 1][4];
@@ -455,6 +456,41 @@ void orc_initial_state(int game, orc_state *out) {
         break;
     case ORC_HEX11: break; /* hex-gen/lib.rs:107-113: empty, P0 to move */
     }
+}
+
+/* Compact per-player action index ("slot"): the key space of the bigram (NST) tables, where the dense id space of
+ * Breakthrough / Knightthrough (src*64 + dst) would be 4096 x 4096 per player.
+ *   Connect4 column (7), Othello square or PASS (65), Hex cell (121),
+ *   Breakthrough src*3 + kind with kind = 0,1,2 for the west-diagonal, straight, east-diagonal move of that player
+ *   (dst - src = -9,-8,-7 for Black, +7,+8,+9 for White; breakthrough/lib.rs:131-156 order),
+ *   Knightthrough src*8 + kind with kind indexing the jumps in ascending-dst order (-17,-15,-10,-6,+6,+10,+15,+17). */
+int orc_num_slots(int game) {
+    switch (game) {
+    case ORC_CONNECT4: return 7;
+    case ORC_BREAKTHROUGH: return 192;
+    case ORC_KNIGHTTHROUGH: return 512;
+    case ORC_OTHELLO: return 65;
+    case ORC_HEX11: return 121;
+    }
+    return 0;
+}
+
+int orc_action_slot(int game, int player, uint16_t code) {
+    static const int kt_delta[8] = {-17, -15, -10, -6, 6, 10, 15, 17};
+    if (game == ORC_BREAKTHROUGH || game == ORC_KNIGHTTHROUGH) {
+        int src = code >> 8, dst = code & 0xff;
+        if (src >= 64 || dst >= 64) return -1;
+        int dr = dst / 8 - src / 8, dc = dst % 8 - src % 8;
+        if (game == ORC_BREAKTHROUGH) { /* one row toward the far wall, at most one column sideways */
+            if (dr != (player ? 1 : -1) || dc < -1 || dc > 1) return -1;
+            return src * 3 + dc + 1;
+        }
+        if (!((abs(dr) == 2 && abs(dc) == 1) || (abs(dr) == 1 && abs(dc) == 2))) return -1;
+        for (int q = 0; q < 8; ++q)
+            if (dst - src == kt_delta[q]) return src * 8 + q;
+        return -1;
+    }
+    return (int)code < orc_num_slots(game) ? (int)code : -1;
 }
 
 int orc_num_actions(int game) {

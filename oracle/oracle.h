@@ -32,7 +32,8 @@ extern "C" {
 
 enum { ORC_CONNECT4 = 0, ORC_BREAKTHROUGH = 1, ORC_KNIGHTTHROUGH = 2, ORC_OTHELLO = 3, ORC_HEX11 = 4, ORC_NUM_GAMES = 5 };
 enum { ORC_UNIFORM = 0, ORC_EPS_MAST = 1, ORC_DECISIVE_WIN = 2, ORC_DECISIVE_WINLOSS = 3, ORC_DECISIVE_WINLOSSDRAW = 4, ORC_DECISIVE_ANTI = 5, ORC_EPS_LGR = 6,
-       ORC_DECISIVE_MAST_WIN = 7, ORC_DECISIVE_MAST_WINLOSS = 8 /* DecisiveMove<EpsilonGreedy<Mast>>, modes Win / WinLoss */ };
+       ORC_DECISIVE_MAST_WIN = 7, ORC_DECISIVE_MAST_WINLOSS = 8, /* DecisiveMove<EpsilonGreedy<Mast>>, modes Win / WinLoss */
+       ORC_EPS_NST = 9 /* EpsilonGreedy<Nst> */ };
 enum { ORC_NOT_TERMINAL = 0, ORC_DRAW = 1, ORC_WINNER_P0 = 2, ORC_WINNER_P1 = 3 };
 enum { ORC_END_TERMINAL = 0, ORC_END_TURN_LIMIT = 1, ORC_END_NO_ACTIONS = 2 };
 
@@ -79,6 +80,8 @@ typedef struct {
 /* ---- rules (games.c) ---- */
 void orc_initial_state(int game, orc_state *out);
 int orc_num_actions(int game); /* size of the dense action-id space (MAST/AMAF tables) */
+int orc_num_slots(int game);   /* size of the compact per-player action index (bigram tables) */
+int orc_action_slot(int game, int player, uint16_t code); /* compact index of `player`'s action, -1 if it is not one */
 int orc_generate_actions(int game, const orc_state *s, uint16_t *out);
 void orc_apply(int game, orc_state *s, uint16_t action);
 int orc_is_terminal(int game, const orc_state *s);
@@ -121,6 +124,15 @@ typedef struct {
     uint64_t *reply_order_out;
     uint16_t *reply_action_out;
     uint32_t *last_win_out;
+    /* ORC_EPS_NST = EpsilonGreedy<Nst> (simulate.rs:852-930; strategy.rs:113-126 Ucb1Nst): an action is scored by the
+     * bigram average of (preceding action, action) once that pair has >= nst_threshold visits, else by its unigram
+     * (MAST) score; random_best over the scores.  bigram: [2][S][S] indexed [mover][slot of the preceding action, in
+     * the other player's numbering][slot of the action], S = orc_num_slots; frozen for the batch; the unigram table
+     * is the `mast` argument.  bigram_delta_out (nullable, ADDED to): the playouts' consecutive pairs, including
+     * (leaf's preceding action, first playout action), visits += 1 and score += utilities[mover] (backprop.rs:885-899). */
+    const orc_action_stat *bigram;
+    uint32_t nst_threshold;
+    orc_action_stat *bigram_delta_out;
 } orc_batch_desc;
 
 /* One playout.  trace (nullable) receives up to max_trace action ids.  final_state nullable. */

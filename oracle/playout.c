@@ -16,6 +16,8 @@
  *   random_best + PRIMES .... mcts/src/util.rs:129-163
  *   DecisiveMove (Win) ...... simulate.rs:636-687 (loser.or(draw) fallback :672-687)
  *   GLOBAL/MAST write ....... backprop.rs:857-870
+ *   Nst ..................... simulate.rs:852-930 (bigram score with a visit-count backoff to the unigram score);
+ *                             bigram write backprop.rs:885-899
  *   Lgr (LGR-1) ............. simulate.rs:936-1033 (reply if recorded and legal, else inner); table write
  *                             backprop.rs:908-923 (last write wins, only players whose utility is the maximum)
  *   GRAVE/AMAF occurrences .. backprop.rs:565-640
@@ -207,7 +209,8 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
         if (pick < 0) {
             uint32_t x0;
             int greedy = 0;
-            if (d->policy == ORC_EPS_MAST || d->policy == ORC_DECISIVE_MAST_WIN || d->policy == ORC_DECISIVE_MAST_WINLOSS) {
+            if (d->policy == ORC_EPS_MAST || d->policy == ORC_DECISIVE_MAST_WIN || d->policy == ORC_DECISIVE_MAST_WINLOSS ||
+                d->policy == ORC_EPS_NST) {
                 uint32_t x1;
                 orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
                 greedy = !((uint64_t)x1 < d->eps_threshold);
@@ -227,6 +230,14 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
             if (greedy) {
                 const orc_action_stat *tab = mast + (size_t)player * na;
                 for (int i = 0; i < n; ++i) score[i] = unigram_score(tab, action_id(game, available[i]));
+                if (d->policy == ORC_EPS_NST && prev >= 0 && d->bigram) { /* Nst::select_move, simulate.rs:898-930 */
+                    const int S = orc_num_slots(game);
+                    const orc_action_stat *row = d->bigram + ((size_t)player * S + (size_t)orc_action_slot(game, 1 - player, (uint16_t)prev)) * S;
+                    for (int i = 0; i < n; ++i) {
+                        const orc_action_stat *b = &row[orc_action_slot(game, player, available[i])];
+                        if (b->visits >= d->nst_threshold && b->visits > 0) score[i] = (double)b->score / (double)b->visits;
+                    }
+                }
                 pick = random_best_index(score, n, mulhi32(x0, 16u * (uint32_t)n));
             } else if (pick < 0) { /* (an LGR reply may already be chosen) */
                 pick = (int)mulhi32(x0, (uint32_t)n);
@@ -261,6 +272,7 @@ typedef struct {
     uint64_t begin, end; /* global playout index range [begin, end) */
     uint64_t *reply_order;  /* thread-private */
     uint16_t *reply_action; /* thread-private */
+    orc_action_stat *bigram_delta; /* thread-private */
 } batch_job;
 
 static void add_trace_stats(int game, const orc_state *leaf, const uint16_t *trace, uint32_t depth, int outcome,
@@ -283,7 +295,7 @@ static void *batch_worker(void *arg) {
     const orc_batch_desc *d = j->d;
     const uint32_t k = d->playouts_per_leaf;
     const int na = orc_num_actions(d->game);
-    const int need_trace = j->amaf_out || j->mast_delta || j->reply_order || d->last_win_out;
+    const int need_trace = j->amaf_out || j->mast_delta || j->reply_order || d->last_win_out || j->bigram_delta;
     uint32_t cap = d->max_trace;
     uint16_t *scratch = NULL;
     orc_batch_desc local = *d;
@@ -328,6 +340,19 @@ static void *batch_worker(void *arg) {
             }
         }
         if (j->mast_delta) add_trace_stats(d->game, &j->leaves[li], scratch, rec.depth, rec.outcome, j->mast_delta);
+        if (j->bigram_delta) { /* backprop.rs:885-899 over the playout part of the chronological list */
+            const int S = orc_num_slots(d->game);
+            for (uint32_t t = 0; t < rec.depth; ++t) {
+                int p = (j->leaves[li].turn + (int)t) & 1;
+                int pv = t > 0 ? (int)scratch[t - 1] : (j->leaves[li].prev_plus1 ? (int)j->leaves[li].prev_plus1 - 1 : -1);
+                if (pv < 0) continue;
+                int u = rec.outcome == ORC_DRAW ? 0 : ((rec.outcome == ORC_WINNER_P0 ? 0 : 1) == p ? 1 : -1);
+                orc_action_stat *e = &j->bigram_delta[((size_t)p * S + (size_t)orc_action_slot(d->game, 1 - p, (uint16_t)pv)) * S +
+                                                      (size_t)orc_action_slot(d->game, p, scratch[t])];
+                e->visits += 1;
+                e->score += u;
+            }
+        }
         if (j->reply_order || d->last_win_out) {
             /* backprop.rs:908-923: a player "won" when its utility is the trial's maximum: the winner, or both
              * players of a zero-utility ending */
@@ -362,9 +387,10 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
                       orc_leaf_result *results, orc_action_stat *amaf_out, orc_action_stat *mast_delta_out,
                       uint16_t *trace_out, orc_playout_record *rec_out, orc_state *final_out, int n_threads) {
     if (d->game < 0 || d->game >= ORC_NUM_GAMES) return -1;
-    if ((d->policy == ORC_EPS_MAST || d->policy == ORC_DECISIVE_MAST_WIN || d->policy == ORC_DECISIVE_MAST_WINLOSS) && !mast) return -2;
+    if ((d->policy == ORC_EPS_MAST || d->policy == ORC_DECISIVE_MAST_WIN || d->policy == ORC_DECISIVE_MAST_WINLOSS ||
+         d->policy == ORC_EPS_NST) && !mast) return -2;
     /* trace-derived statistics need a bounded trace: only Knightthrough can run unboundedly long */
-    if ((amaf_out || mast_delta_out || d->reply_order_out) && d->max_playout_depth == 0 && d->game == ORC_KNIGHTTHROUGH) return -3;
+    if ((amaf_out || mast_delta_out || d->reply_order_out || d->bigram_delta_out) && d->max_playout_depth == 0 && d->game == ORC_KNIGHTTHROUGH) return -3;
     if (d->reply_order_out && !d->reply_action_out) return -4;
     const int na = orc_num_actions(d->game);
     const uint64_t total = (uint64_t)n_leaves * d->playouts_per_leaf;
@@ -388,6 +414,10 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
         j->end = total * (uint64_t)(t + 1) / (uint64_t)n_threads;
         j->mast_delta = NULL;
         if (mast_delta_out) j->mast_delta = (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat));
+        if (d->bigram_delta_out) {
+            const size_t S = (size_t)orc_num_slots(d->game);
+            j->bigram_delta = (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat));
+        }
         if (d->reply_order_out) {
             j->reply_order = (uint64_t *)calloc((size_t)2 * na, sizeof(uint64_t));
             j->reply_action = (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t));
@@ -407,6 +437,16 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
                 mast_delta_out[i].score += jobs[t].mast_delta[i].score;
             }
             free(jobs[t].mast_delta);
+        }
+    }
+    if (d->bigram_delta_out) {
+        const size_t S = (size_t)orc_num_slots(d->game), cnt = 2 * S * S;
+        for (int t = 0; t < n_threads; ++t) {
+            for (size_t i = 0; i < cnt; ++i) {
+                d->bigram_delta_out[i].visits += jobs[t].bigram_delta[i].visits;
+                d->bigram_delta_out[i].score += jobs[t].bigram_delta[i].score;
+            }
+            free(jobs[t].bigram_delta);
         }
     }
     if (d->reply_order_out) {

@@ -18,7 +18,7 @@ LIB_PATH = ORACLE_DIR / "_build" / "liboracle.so"
 
 CONNECT4, BREAKTHROUGH, KNIGHTTHROUGH, OTHELLO, HEX11 = range(5)
 GAME_NAMES = ["connect4", "breakthrough", "knightthrough", "othello", "hex11"]
-UNIFORM, EPS_MAST, DECISIVE_WIN, DECISIVE_WINLOSS, DECISIVE_WINLOSSDRAW, DECISIVE_ANTI, EPS_LGR, DECISIVE_MAST_WIN, DECISIVE_MAST_WINLOSS = range(9)
+UNIFORM, EPS_MAST, DECISIVE_WIN, DECISIVE_WINLOSS, DECISIVE_WINLOSSDRAW, DECISIVE_ANTI, EPS_LGR, DECISIVE_MAST_WIN, DECISIVE_MAST_WINLOSS, EPS_NST = range(10)
 NOT_TERMINAL, DRAW, WINNER_P0, WINNER_P1 = range(4)
 END_TERMINAL, END_TURN_LIMIT, END_NO_ACTIONS = range(3)
 OTHELLO_PASS = 64
@@ -47,6 +47,9 @@ class BatchDesc(C.Structure):
         ("reply_order_out", C.c_void_p),
         ("reply_action_out", C.c_void_p),
         ("last_win_out", C.c_void_p),
+        ("bigram", C.c_void_p),
+        ("nst_threshold", C.c_uint32),
+        ("bigram_delta_out", C.c_void_p),
     ]
 
 
@@ -149,6 +152,14 @@ def num_actions(game: int) -> int:
     return lib().orc_num_actions(game)
 
 
+def num_slots(game: int) -> int:
+    return lib().orc_num_slots(game)
+
+
+def action_slot(game: int, player: int, code: int) -> int:
+    return lib().orc_action_slot(game, player, code)
+
+
 def generate_actions(game: int, state: np.ndarray) -> list[int]:
     out = np.zeros(MAX_ACTIONS, dtype=np.uint16)
     n = lib().orc_generate_actions(game, _p(state), _p(out))
@@ -214,6 +225,9 @@ def playout_batch(
     threads=1,
     replies: np.ndarray | None = None,
     want_reply_updates=False,
+    bigram: np.ndarray | None = None,
+    nst_threshold=5,
+    want_bigram_delta=False,
 ):
     """Runs n_leaves*k playouts.  Returns a dict with results (+ optional amaf / mast_delta / trace /
     records / final)."""
@@ -237,6 +251,16 @@ def playout_batch(
         reply_action = np.zeros((2, na), dtype=np.uint16)
         last_win = np.zeros((n, 2), dtype=np.uint32)
         d.reply_order_out, d.reply_action_out, d.last_win_out = reply_order.ctypes.data, reply_action.ctypes.data, last_win.ctypes.data
+    bigram_delta = None
+    ns = num_slots(game)
+    if bigram is not None:
+        bigram = np.ascontiguousarray(bigram, dtype=STAT_DTYPE)
+        assert bigram.shape == (2, ns, ns)
+        d.bigram = bigram.ctypes.data
+    d.nst_threshold = nst_threshold
+    if want_bigram_delta:
+        bigram_delta = np.zeros((2, ns, ns), dtype=STAT_DTYPE)
+        d.bigram_delta_out = bigram_delta.ctypes.data
     if mast is not None:
         mast = np.ascontiguousarray(mast, dtype=STAT_DTYPE)
         assert mast.shape == (2, na)
@@ -246,7 +270,7 @@ def playout_batch(
     if rc != 0:
         raise RuntimeError(f"orc_playout_batch failed: {rc}")
     return {"results": results, "amaf": amaf, "mast_delta": delta, "trace": trace, "records": rec, "final": final,
-            "reply_order": reply_order, "reply_action": reply_action, "last_win": last_win}
+            "reply_order": reply_order, "reply_action": reply_action, "last_win": last_win, "bigram_delta": bigram_delta}
 
 
 def search(game, root, *, iterations, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,

@@ -71,6 +71,33 @@ def test_initial_states_match_oracle():
         assert mb.initial_state(mb.Game(g)).tobytes() == o.initial_state(g).tobytes()
 
 
+def test_action_slots_match_oracle():
+    """mr_num_slots / mr_action_slot / mr_slot_action (host functions, no GPU): the compact per-player action index of
+    the bigram tables, against the oracle's, and slot -> action -> slot round trips."""
+    import mcts_b200 as mb
+    import oracle_lib as o
+    from mcts_b200.rollout import action_slot, num_slots, slot_action
+
+    for g in range(5):
+        ns = num_slots(mb.Game(g))
+        assert ns == o.num_slots(g) == [7, 192, 512, 65, 121][g]
+        for p in range(2):
+            real = 0
+            for slot in range(ns):
+                code = slot_action(mb.Game(g), p, slot)
+                if code < 0:
+                    continue
+                real += 1
+                assert action_slot(mb.Game(g), p, code) == slot == o.action_slot(g, p, code)
+            assert real == [7, 154, 336, 65, 121][g]  # 7*8*3 - 2*7 diagonal-off-board; knight jumps on an 8x8 board
+            assert slot_action(mb.Game(g), p, ns) == -1 and action_slot(mb.Game(g), p, 0xFFFF) == -1
+        # every action the rules generate has a slot
+        for s in o.random_positions(g, 1, 9, 6):
+            st = np.array([s])
+            for a in o.generate_actions(g, st):
+                assert action_slot(mb.Game(g), int(s["turn"]), a) >= 0
+
+
 def _compile_host_example(tmp_path):
     import subprocess
 

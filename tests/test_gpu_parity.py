@@ -39,7 +39,7 @@ def _strategy(policy, eps=0.1):
     return {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(eps), o.DECISIVE_WIN: mb.DecisiveMoveWin(),
             o.DECISIVE_WINLOSS: mb.DecisiveMove("win_loss"), o.DECISIVE_WINLOSSDRAW: mb.DecisiveMove("win_loss_draw"),
             o.DECISIVE_ANTI: mb.DecisiveMove("anti_decisive"), o.DECISIVE_MAST_WIN: mb.DecisiveMoveMast(eps, "win"),
-            o.DECISIVE_MAST_WINLOSS: mb.DecisiveMoveMast(eps, "win_loss")}[policy]
+            o.DECISIVE_MAST_WINLOSS: mb.DecisiveMoveMast(eps, "win_loss"), o.EPS_NST: mb.EpsilonGreedyNst(eps)}[policy]
 
 
 def _compare(game, policy, leaves, k, *, seed, max_depth=0, mast=None, eps=0.1, leaf_id_base=0, amaf=False, delta=False, devices=1):
@@ -253,6 +253,43 @@ def test_last_good_reply_bit_exact(game, eps):
         if density == 1.0 and eps == 0.0:
             uni = o.playout_batch(game, leaves, k, policy=o.UNIFORM, seed=77, max_depth=depth)
             assert got.results.tobytes() != uni["results"].tobytes()  # replies were actually played
+
+
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO, o.HEX11])
+@pytest.mark.parametrize("eps", [0.1, 0.0])
+def test_nst_bit_exact(game, eps):
+    """EpsilonGreedy<Nst> (simulate.rs:852-930): per-playout traces, records and final states, the unigram (MAST) delta
+    and the bigram delta (backprop.rs:885-899), for bigram tables at several backoff thresholds."""
+    leaves = _leaves(game, n_per=5)
+    prevs = _random_replies(game, leaves, 3, 1.0)
+    by_player = [prevs[p][prevs[p] > 0] for p in range(2)]
+    for i in range(len(leaves)):
+        other = by_player[1 - int(leaves[i]["turn"])]
+        leaves["prev"][i] = 0 if i % 3 == 0 else other[i % len(other)]
+    depth = 200 if game == o.KNIGHTTHROUGH else 0
+    mt = MAX_TRACE[game]
+    # statistics of uniform playouts as the tables: realistic, with many pairs above and below the threshold
+    base = o.playout_batch(game, leaves, 96, seed=13, max_depth=depth, want_mast_delta=True, want_bigram_delta=True, threads=o.host_threads())
+    mast, bigram = base["mast_delta"], base["bigram_delta"]
+    for thr, table, k in ((5, bigram, 48), (1, bigram, 33), (0, bigram, 16), (5, None, 16)):
+        ref = o.playout_batch(game, leaves, k, policy=o.EPS_NST, eps=eps, seed=78, max_depth=depth, mast=mast, bigram=table,
+                              nst_threshold=thr, want_mast_delta=True, want_bigram_delta=True, want_trace=True, max_trace=mt,
+                              want_final=True, threads=o.host_threads())
+        with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyNst(eps, thr), seed=78, max_playout_depth=depth) as g:
+            g.set_bigrams(table)
+            got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, stats=mast, want_trace=True, want_final=True, max_trace=mt,
+                                  want_mast_delta=True)
+        name = (o.GAME_NAMES[game], thr)
+        assert (got.records["depth"] == ref["records"]["depth"]).all(), name
+        assert (got.records["outcome"] == ref["records"]["outcome"]).all(), name
+        assert (got.trace == ref["trace"]).all(), name
+        assert got.final.tobytes() == ref["final"].tobytes(), name
+        assert got.results.tobytes() == ref["results"].tobytes(), name
+        assert got.mast_delta.tobytes() == ref["mast_delta"].tobytes(), name
+        assert got.bigram_delta.tobytes() == ref["bigram_delta"].tobytes(), name
+        if table is not None and thr == 1 and eps == 0.0:
+            plain = o.playout_batch(game, leaves, k, policy=o.EPS_MAST, eps=eps, seed=78, max_depth=depth, mast=mast)
+            assert got.results.tobytes() != plain["results"].tobytes()  # the bigram scores changed picks
 
 
 def test_reference_shaped_playout_call():

@@ -456,3 +456,37 @@ def test_mast_prefers_best_scored_action_and_delta_counts():
     d = out["mast_delta"]
     assert d["visits"].sum() == 40 and d[0, (fav >> 8) * 64 + (fav & 0xFF)]["visits"] == 40
     assert d["score"].sum() == 0  # depth cutoff => draw => zero utility
+
+
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO, o.HEX11])
+def test_nst_backs_off_to_mast_and_bigram_delta_sums_to_mast_delta(game):  # simulate.rs:898-930, backprop.rs:885-899
+    """Nst with no bigram entry at the threshold IS Mast; and since every playout ply of a leaf that carries its
+    preceding action has a predecessor, the bigram delta summed over predecessors equals the MAST delta."""
+    depth = 200 if game == o.KNIGHTTHROUGH else 0
+    leaves = np.concatenate([o.random_positions(game, 3, 6, 4), o.random_positions(game, 4, 13, 4)])
+    uni = o.playout_batch(game, leaves, 8, seed=2, max_depth=depth, want_trace=True, max_trace=1)
+    ns, na = o.num_slots(game), o.num_actions(game)
+    for i in range(len(leaves)):  # some action of the player who is not to move (only its slot matters here)
+        p = 1 - int(leaves[i]["turn"])
+        codes = [c for c in range(1 << 14) if o.action_slot(game, p, c) >= 0] if i == 0 else codes_by_player[p]
+        if i == 0:
+            codes_by_player = {p: codes, 1 - p: [c for c in range(1 << 14) if o.action_slot(game, 1 - p, c) >= 0]}
+        leaves["prev"][i] = codes_by_player[p][(7 * i) % len(codes_by_player[p])] + 1
+    base = o.playout_batch(game, leaves, 32, seed=5, max_depth=depth, want_mast_delta=True, want_bigram_delta=True)
+    mast, bigram = base["mast_delta"], base["bigram_delta"]
+    aid = (lambda c: (c >> 8) * 64 + (c & 0xFF)) if game in (o.BREAKTHROUGH, o.KNIGHTTHROUGH) else (lambda c: c)
+    for p in range(2):
+        col_v, col_s = bigram["visits"][p].sum(axis=0), bigram["score"][p].sum(axis=0)
+        for slot in range(ns):
+            code = next((c for c in codes_by_player[p] if o.action_slot(game, p, c) == slot), None)
+            if code is None:
+                assert col_v[slot] == 0
+                continue
+            assert col_v[slot] == mast["visits"][p, aid(code)] and col_s[slot] == mast["score"][p, aid(code)]
+    kw = dict(policy=o.EPS_NST, eps=0.0, seed=9, max_depth=depth, mast=mast, want_trace=True, max_trace=64)
+    as_mast = o.playout_batch(game, leaves, 16, **{**kw, "policy": o.EPS_MAST})
+    never = o.playout_batch(game, leaves, 16, bigram=bigram, nst_threshold=1 << 30, **kw)
+    empty = o.playout_batch(game, leaves, 16, bigram=None, **kw)
+    assert (never["trace"] == as_mast["trace"]).all() and (empty["trace"] == as_mast["trace"]).all()
+    used = o.playout_batch(game, leaves, 16, bigram=bigram, nst_threshold=1, **kw)
+    assert not (used["trace"] == as_mast["trace"]).all()  # the bigram scores changed picks
