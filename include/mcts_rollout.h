@@ -319,7 +319,7 @@ typedef struct {
     uint32_t grave_threshold;   /* Rave.threshold (default 700) */
     uint32_t rave_schedule;     /* mr_rave_schedule */
     uint32_t rave_param;        /* HandSelected k (default 1000) / Threshold rave */
-    uint32_t pad;
+    uint32_t nst_backoff_threshold; /* MR_EPS_NST: Nst::backoff_threshold (simulate.rs:875-881; the reference's default is 5) */
     double amaf_alpha;          /* MR_SELECT_AMAF: 1 = pure AMAF (the reference default), 0 = UCB1 */
 } mr_search_desc;
 

@@ -58,7 +58,7 @@ class SearchDesc(C.Structure):
         ("grave_threshold", C.c_uint32),
         ("rave_schedule", C.c_uint32),
         ("rave_param", C.c_uint32),
-        ("pad", C.c_uint32),
+        ("nst_backoff_threshold", C.c_uint32),
         ("amaf_alpha", C.c_double),
     ]
 

@@ -10,6 +10,8 @@
 //   AMAF ............... select/amaf.rs:48-86 over per-edge AMAF rows written by update_amaf, backprop.rs:565-617
 //   LGR table .......... TreeStats.player_replies, last write wins over (trial, ply) order (backprop.rs:908-923): the
 //                        kernel's stamps for the playout part, the tree-path pairs added here
+//   NST table .......... TreeStats.player_bigram_actions over consecutive (preceding action, action) pairs of tree path
+//                        and playout (backprop.rs:885-899): the kernel's bigram delta plus the tree-path pairs added here
 //   MAST table ......... TreeStats.player_actions, written for playout trace AND tree path (backprop.rs:833-870)
 //   final move ......... RobustChild: (visits, expected score) lexicographic max, select/basic.rs:13-45
 // The tree (arena, edge statistics in the parent's child arrays, root_stats) stays on the host; only the
@@ -146,6 +148,7 @@ struct Search {
     const mr_search_desc *d;
     Tree t;
     std::vector<mr_action_stat> mast; // [2][NA], TreeStats.player_actions
+    std::vector<mr_action_stat> bigram; // [2][S][S], TreeStats.player_bigram_actions over compact action slots (MR_EPS_NST)
     std::vector<uint16_t> replies;    // [2][NA], TreeStats.player_replies: 1 + reply code by (player, preceding action id)
     int na;
     // TreeStats.grave (search/shared.rs:52): per reference-node state, per player, per action.  The reference keys
@@ -389,6 +392,22 @@ struct Search {
             if (upd[i].order) replies[i] = upd[i].action_plus1;
     }
 
+    // backprop.rs:885-899, tree-path part, for the k trials of one leaf: every pair of consecutive edges of the descent
+    // (the pair (last edge, first playout action) and the pairs inside the playouts arrive from the kernel)
+    void backprop_bigrams(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k) {
+        const int64_t nonzero = (int64_t)k - r.draws;
+        const int64_t u[2] = {(int64_t)r.wins[0] - (nonzero - r.wins[0]), (int64_t)r.wins[1] - (nonzero - r.wins[1])};
+        const size_t S = (size_t)mr_num_slots(t.game);
+        for (size_t i = 2; i < path.size(); ++i) {
+            const Node &grand = t.nodes[path[i - 2].node], &parent = t.nodes[path[i - 1].node];
+            const int p = parent.player;
+            const uint16_t prev = t.action[grand.first + path[i - 1].idx], act = t.action[parent.first + path[i].idx];
+            mr_action_stat &e = bigram[((size_t)p * S + (size_t)mr_action_slot(t.game, 1 - p, prev)) * S + (size_t)mr_action_slot(t.game, p, act)];
+            e.visits += k;
+            e.score += (int32_t)u[p];
+        }
+    }
+
     // k trials of one leaf, aggregated
     void backprop(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k, const mr_action_stat *amaf) {
         const int64_t nonzero = (int64_t)k - r.draws;
@@ -448,7 +467,11 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     s.d = desc;
     s.t.game = (int)desc->game;
     s.na = mr_num_actions((int)desc->game);
-    const bool uses_mast = desc->policy == MR_EPS_MAST || desc->policy == MR_DECISIVE_MAST_WIN || desc->policy == MR_DECISIVE_MAST_WINLOSS;
+    const bool nst = desc->policy == MR_EPS_NST;
+    const bool uses_mast = desc->policy == MR_EPS_MAST || desc->policy == MR_DECISIVE_MAST_WIN || desc->policy == MR_DECISIVE_MAST_WINLOSS || nst;
+    const size_t n_bigram = nst ? (size_t)2 * mr_num_slots((int)desc->game) * mr_num_slots((int)desc->game) : 0;
+    s.bigram.assign(n_bigram, mr_action_stat{0, 0});
+    std::vector<mr_action_stat> bigram_delta(n_bigram);
     if (uses_mast) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
     const bool lgr = desc->policy == MR_EPS_LGR;
     if (lgr) s.replies.assign((size_t)2 * s.na, 0);
@@ -502,7 +525,7 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
             s.select(first + b, bb.paths[b]);
             if (k > 1) s.add_path_virtual_loss(bb.paths[b], k - 1);
             bb.leaves[b] = s.t.nodes[bb.paths[b].back().node].state;
-            if (lgr && bb.paths[b].size() > 1) { // playout()'s prev_action: the last edge of the descent (shared.rs:763-778)
+            if ((lgr || nst) && bb.paths[b].size() > 1) { // playout()'s prev_action: the last edge of the descent (shared.rs:763-778)
                 const std::vector<PathEntry> &path = bb.paths[b];
                 const Node &parent = s.t.nodes[path[path.size() - 2].node];
                 bb.leaves[b].prev_action_plus1 = (uint16_t)(s.t.action[parent.first + path.back().idx] + 1);
@@ -510,6 +533,10 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         }
         if (lgr) {
             int rc = mr_set_replies(ctx, (int)desc->game, s.replies.data());
+            if (rc != MR_OK) return rc;
+        }
+        if (nst) { // frozen for the batch, like the MAST table
+            int rc = mr_set_bigrams(ctx, (int)desc->game, s.bigram.data(), desc->nst_backoff_threshold);
             if (rc != MR_OK) return rc;
         }
         st.seconds_select += now_s() - t0;
@@ -536,9 +563,18 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
             rc = mr_reply_updates(ctx, slot, reply_upd.data(), last_win.data());
             if (rc != MR_OK) return rc;
         }
+        if (nst) {
+            rc = mr_bigram_delta(ctx, slot, bigram_delta.data());
+            if (rc != MR_OK) return rc;
+        }
         const double t1 = now_s();
         if (lgr) s.merge_replies(bb.paths, bb.nb, k, reply_upd, last_win);
+        for (size_t i = 0; i < n_bigram; ++i) {
+            s.bigram[i].visits += bigram_delta[i].visits;
+            s.bigram[i].score += bigram_delta[i].score;
+        }
         for (uint32_t b = 0; b < bb.nb; ++b) {
+            if (nst) s.backprop_bigrams(bb.paths[b], bb.results[b], k);
             s.backprop(bb.paths[b], bb.results[b], k, want_amaf ? bb.amaf.data() + (size_t)b * 2 * s.na : nullptr);
             st.playout_plies += bb.results[b].sum_depth;
         }

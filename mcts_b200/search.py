@@ -48,7 +48,7 @@ class GpuSearch:
             int(game), int(self.rollout.strategy.policy), select, q_init, max_iterations, batch_leaves,
             num_rollouts_per_leaf, expand_threshold, max_playout_depth, (1 if use_transpositions else 0) | (2 if pipelined else 0), exploration_constant,
             float(getattr(self.rollout.strategy, "epsilon", 0.0)), int(seed) & 0xFFFFFFFFFFFFFFFF,
-            grave_threshold, rave_schedule, rave_param, 0, float(amaf_alpha),
+            grave_threshold, rave_schedule, rave_param, int(getattr(self.rollout.strategy, "backoff_threshold", 5)), float(amaf_alpha),
         )
 
     def close(self):

@@ -188,6 +188,7 @@ typedef struct {
     int rave_schedule;          /* 0 HandSelected{k}, 1 Threshold{rave} (rave.rs:42-76) */
     uint32_t rave_param;
     double amaf_alpha;          /* select 3: alpha * amaf + (1 - alpha) * ucb1 (select/amaf.rs:58-74), reference default 1 */
+    uint32_t nst_threshold;     /* ORC_EPS_NST: Nst::backoff_threshold (simulate.rs:875-881, reference default 5) */
 } orc_search_cfg;
 
 typedef struct {

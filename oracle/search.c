@@ -365,7 +365,13 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     const int want_amaf = c->select == 2 || c->select == 3;
     const uint32_t B = c->batch_leaves, k = c->playouts_per_leaf;
     const int na = orc_num_actions(c->game);
-    orc_action_stat *mast = (c->policy == ORC_EPS_MAST || c->policy == ORC_DECISIVE_MAST_WIN || c->policy == ORC_DECISIVE_MAST_WINLOSS) ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    const int nst = c->policy == ORC_EPS_NST;
+    orc_action_stat *mast = (c->policy == ORC_EPS_MAST || c->policy == ORC_DECISIVE_MAST_WIN || c->policy == ORC_DECISIVE_MAST_WINLOSS || nst) ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    /* TreeStats.player_bigram_actions (shared.rs:60-66) as [2][S][S] over compact action slots, and one delta per buffer set */
+    const size_t S = (size_t)orc_num_slots(c->game);
+    orc_action_stat *bigram = nst ? (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat)) : NULL;
+    orc_action_stat *bg_delta[2] = {NULL, NULL};
+    for (int q = 0; q < 2 && nst; ++q) bg_delta[q] = (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat));
     orc_action_stat *delta = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
     const int lgr = c->policy == ORC_EPS_LGR;
     uint16_t *replies = lgr ? (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t)) : NULL;
@@ -425,7 +431,7 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                 for (int i = 1; i < set_plen[slot][b]; ++i) /* add_path_virtual_loss(k - 1), shared.rs:787-805 */
                     t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
                 leaves[b] = t.nodes[path[set_plen[slot][b] - 1].node].state;
-                if (lgr && set_plen[slot][b] > 1) { /* playout()'s prev_action: the last edge of the descent */
+                if ((lgr || nst) && set_plen[slot][b] > 1) { /* playout()'s prev_action: the last edge of the descent */
                     int L = set_plen[slot][b];
                     leaves[b].prev_plus1 = (uint16_t)(t.action[t.nodes[path[L - 2].node].first + path[L - 1].idx] + 1);
                 }
@@ -434,6 +440,10 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
             bd.reply_order_out = lgr ? upd_order[slot] : NULL;
             bd.reply_action_out = lgr ? upd_action[slot] : NULL;
             bd.last_win_out = lgr ? last_win[slot] : NULL;
+            bd.bigram = bigram; /* frozen for the batch, like the MAST table */
+            bd.nst_threshold = c->nst_threshold;
+            bd.bigram_delta_out = nst ? bg_delta[slot] : NULL;
+            if (nst) memset(bg_delta[slot], 0, sizeof(orc_action_stat) * 2 * S * S);
             bd.leaf_id_base = done;
             if (set_delta[slot]) memset(set_delta[slot], 0, sizeof(orc_action_stat) * 2 * (size_t)na);
             if (set_amaf[slot]) memset(set_amaf[slot], 0, sizeof(orc_action_stat) * (size_t)nb * 2 * na);
@@ -544,8 +554,24 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                     }
                 }
             }
+            if (nst) { /* backprop.rs:885-899, tree-path part: consecutive edges of the descent, once per trial of the leaf */
+                for (int i = 2; i < plen_a[b]; ++i) {
+                    const node_t *grand = &t.nodes[path[i - 2].node], *parent = &t.nodes[path[i - 1].node];
+                    int p = parent->player;
+                    uint16_t prev = t.action[grand->first + path[i - 1].idx], act = t.action[parent->first + path[i].idx];
+                    orc_action_stat *e = &bigram[((size_t)p * S + (size_t)orc_action_slot(c->game, 1 - p, prev)) * S +
+                                                 (size_t)orc_action_slot(c->game, p, act)];
+                    e->visits += k;
+                    e->score += (int32_t)u[p];
+                }
+            }
             plies += r->sum_depth;
         }
+        if (nst) /* the playout part: (last edge, first playout action) and every later consecutive pair */
+            for (size_t i = 0; i < 2 * S * S; ++i) {
+                bigram[i].visits += bg_delta[apply][i].visits;
+                bigram[i].score += bg_delta[apply][i].score;
+            }
         if (mast)
             for (int i = 0; i < 2 * na; ++i) {
                 mast[i].visits += set_delta[apply][i].visits;
@@ -610,6 +636,9 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     free(grave.states);
     free(grave.slots);
     free(replies);
+    free(bigram);
+    free(bg_delta[0]);
+    free(bg_delta[1]);
     for (int q = 0; q < 2; ++q) {
         free(upd_order[q]);
         free(upd_action[q]);

@@ -74,6 +74,7 @@ class SearchCfg(C.Structure):
         ("rave_schedule", C.c_int),
         ("rave_param", C.c_uint32),
         ("amaf_alpha", C.c_double),
+        ("nst_threshold", C.c_uint32),
     ]
 
 
@@ -275,11 +276,11 @@ def playout_batch(
 
 def search(game, root, *, iterations, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,
            max_depth=0, c=2.0 ** 0.5, eps=0.1, seed=0, threads=1, use_transpositions=False, grave_threshold=700,
-           rave_schedule=0, rave_param=1000, pipelined=False, amaf_alpha=1.0):
+           rave_schedule=0, rave_param=1000, pipelined=False, amaf_alpha=1.0, nst_threshold=5):
     """The restated reference MCTS loop with CPU playouts.  Returns (best_action, children, playout_plies)."""
     cfg = SearchCfg(game, policy, select, q_init, iterations, batch_leaves, k, expand_threshold, max_depth, threads,
                     int(pipelined), int(use_transpositions), c, eps_threshold(eps), seed, grave_threshold, rave_schedule,
-                    rave_param, amaf_alpha)
+                    rave_param, amaf_alpha, nst_threshold)
     root = np.ascontiguousarray(root, dtype=STATE_DTYPE)
     children = np.zeros(256, dtype=ROOT_CHILD_DTYPE)
     best, n, plies = C.c_uint16(), C.c_uint32(), C.c_uint64()

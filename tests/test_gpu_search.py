@@ -139,6 +139,30 @@ def test_lgr_search_bit_exact(game, iters, batch, k, pipelined):
     assert uni_plies != plies
 
 
+@pytest.mark.parametrize("game,iters,batch,k,thr,pipelined", [
+    (o.CONNECT4, 2048, 32, 8, 5, False),
+    (o.BREAKTHROUGH, 1024, 16, 16, 2, True),
+    (o.KNIGHTTHROUGH, 256, 8, 16, 5, False),
+    (o.OTHELLO, 768, 1, 1, 1, False),  # the reference's sequential loop: every trial sees every earlier write
+    (o.HEX11, 1024, 32, 4, 5, False),
+])
+def test_nst_search_bit_exact(game, iters, batch, k, thr, pipelined):
+    """The `Ucb1Nst` strategy (strategy.rs:113-126) end to end: UCB1 over EpsilonGreedy<Nst> rollouts, the bigram table fed
+    by the kernel's delta and the tree-path pairs (backprop.rs:885-899), the unigram table as for MAST."""
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), mb.EpsilonGreedyNst(0.1, thr), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      max_playout_depth=200, pipelined=pipelined, seed=35) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_NST, eps=0.1, seed=35,
+                                     threads=o.host_threads(), max_depth=200, pipelined=pipelined, nst_threshold=thr)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    # the bigram table changes the playouts: the same search with plain MAST rollouts differs
+    _, _, mast_plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_MAST, eps=0.1, seed=35,
+                                threads=o.host_threads(), max_depth=200, pipelined=pipelined)
+    assert mast_plies != plies
+
+
 def test_rave_family_search_bit_exact():
     """mcts-tune's `rave` family (family_catalog.rs:483-514): Rave select over the in-kernel AMAF tables with
     DecisiveMove<WinLoss, EpsilonGreedy<Mast>> rollouts -- AMAF tables, MAST delta and decisive scan in one kernel."""
