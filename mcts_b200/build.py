@@ -60,7 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: Path) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{CSRC}", "-c", str(src), "-o", str(obj)]
+        extra = os.environ.get("MR_NVCC_EXTRA", "").split()  # experiment switches (-DNAME=1) for A/B library variants
+        cmd = [nvcc, *NVCC_FLAGS, *extra, f"-I{ROOT / 'include'}", f"-I{CSRC}", "-c", str(src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -124,4 +124,44 @@ __device__ uint32_t MR_RCP32[129];
 __device__ __constant__ uint32_t MR_PRIMES[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991,
                                                   53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693};
 
+// ---- ALU -> FMA pipe balancing ----
+// These kernels are bound by the ALU pipe (LOP3 / SHF / SEL / ISETP at 77-92 % busy, ncu) while the FMA pipe idles at
+// ~15 %.  A conditional move or a conditional add written as a PREDICATED IMAD runs on the FMA pipe instead of taking an
+// ALU slot as a SEL.  The multiplier 1 / -1 comes from constant memory, so the compiler cannot fold the IMAD back into a
+// MOV / SEL / IADD3; a constant-bank operand costs no register and no extra instruction.
+#ifndef MR_FMA_BALANCE
+#define MR_FMA_BALANCE 1
+#endif
+__device__ __constant__ uint32_t MR_ONE = 1u;
+__device__ __constant__ uint32_t MR_NEG_ONE = 0xffffffffu;
+
+// dst = src when `nonzero` != 0
+__device__ __forceinline__ void cmov_nz(uint32_t &dst, uint32_t src, uint32_t nonzero) {
+#if MR_FMA_BALANCE
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p mad.lo.u32 %0, %1, %3, 0;\n\t}" : "+r"(dst) : "r"(src), "r"(nonzero), "r"(MR_ONE));
+#else
+    dst = nonzero ? src : dst;
+#endif
+}
+// if (idx >= cnt) { idx -= cnt; pos += step; }   -- one step of a rank/select binary search
+__device__ __forceinline__ void select_step(uint32_t &idx, uint32_t &pos, uint32_t cnt, uint32_t step) {
+#if MR_FMA_BALANCE
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %0, %2;\n\t@p mad.lo.u32 %0, %2, %5, %0;\n\t@p mad.lo.u32 %1, %3, %4, %1;\n\t}"
+        : "+r"(idx), "+r"(pos)
+        : "r"(cnt), "r"(step), "r"(MR_ONE), "r"(MR_NEG_ONE));
+#else
+    if (idx >= cnt) {
+        idx -= cnt;
+        pos += step;
+    }
+#endif
+}
+// v << s with PTX semantics: a shift amount >= 32 (including "negative" amounts as unsigned) gives 0, so word q of a
+// multi-word board receives bit `cell` as shl_clamp(1, cell - 32 q) with no compare / select
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+}
+
 } // namespace mr

@@ -179,16 +179,15 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                                     }
                                 }
                             }
-                            const uint32_t bitpos = select32(word, idx);
-                            const uint32_t b = 1u << bitpos;
+                            const uint32_t cell = wsel * 32u + select32(word, idx);
                             const uint32_t mover = (leaf_turn + ply) & 1u; // warp-uniform
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t add = (wsel == (uint32_t)q) ? b : 0u;
+                            for (int q = 0; q < 4; ++q) { // word q receives the bit iff 0 <= cell - 32 q < 32: a clamped shift
+                                const uint32_t add = shl_clamp(1u, cell - 32u * (uint32_t)q);
                                 if (mover == 0) full[0].w[q] |= add;
                                 else full[1].w[q] |= add;
                             }
-                            order[ply][lane] = (uint8_t)(wsel * 32u + bitpos);
+                            order[ply][lane] = (uint8_t)cell;
                             --n_empty;
                         }
                     }
@@ -226,9 +225,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                         B128 m = mask_lo;
                         for (int i = lo + 1; i <= mid; ++i) {
                             const uint32_t cell = order[first + 2u * (uint32_t)i][lane];
-                            const uint32_t b = 1u << (cell & 31u), ws = cell >> 5;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) m.w[q] |= (ws == (uint32_t)q) ? b : 0u;
+                            #pragma unroll
+                            for (int q = 0; q < 4; ++q) m.w[q] |= shl_clamp(1u, cell - 32u * (uint32_t)q);
                         }
                         // everything connected at `lo` stays connected; grow it through the added stones
                         const B128 c = H::flood(H::bor(conn_lo, edge1), m, NC0, NC10, BM);
@@ -245,9 +243,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                         win_mask = mask_lo;
                         for (int i = lo + 1; i <= hi; ++i) {
                             const uint32_t cell = order[first + 2u * (uint32_t)i][lane];
-                            const uint32_t b = 1u << (cell & 31u), ws = cell >> 5;
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) win_mask.w[q] |= (ws == (uint32_t)q) ? b : 0u;
+                            for (int q = 0; q < 4; ++q) win_mask.w[q] |= shl_clamp(1u, cell - 32u * (uint32_t)q);
                         }
                     }
                 }
@@ -275,9 +272,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                             const uint32_t first = ((uint32_t)pl ^ leaf_turn) & 1u;
                             for (uint32_t ply = first; ply < depth; ply += 2) {
                                 const uint32_t cell = order[ply][lane];
-                                const uint32_t b = 1u << (cell & 31u), ws = cell >> 5;
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) m.w[q] |= (ws == (uint32_t)q) ? b : 0u;
+                                #pragma unroll
+                                for (int q = 0; q < 4; ++q) m.w[q] |= shl_clamp(1u, cell - 32u * (uint32_t)q);
                             }
                             fin[pl] = m;
                         }

@@ -53,8 +53,7 @@ struct HexStep : Hex11 {
     }
     __device__ static uint32_t count(B128 a) { return __popc(a.w[0]) + __popc(a.w[1]) + __popc(a.w[2]) + __popc(a.w[3]); }
     __device__ static B128 cell_bit(uint32_t cell) {
-        const uint32_t b = 1u << (cell & 31u), ws = cell >> 5;
-        return B128{{ws == 0 ? b : 0u, ws == 1 ? b : 0u, ws == 2 ? b : 0u, ws == 3 ? b : 0u}};
+        return B128{{shl_clamp(1u, cell), shl_clamp(1u, cell - 32u), shl_clamp(1u, cell - 64u), shl_clamp(1u, cell - 96u)}};
     }
     __device__ static bool has_cell(B128 a, uint32_t cell) {
         const uint32_t ws = cell >> 5;
