@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                             win = 0;
                             end_code = 0;
                             cutoff = false;
+                            prev_slot1 = leaf_prev_slot1; // the new playout starts from the leaf's context again
                         } else {
                             idle = true;
                         }

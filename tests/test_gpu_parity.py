@@ -292,6 +292,57 @@ def test_nst_bit_exact(game, eps):
             assert got.results.tobytes() != plain["results"].tobytes()  # the bigram scores changed picks
 
 
+@pytest.mark.parametrize("game", GAMES)
+@pytest.mark.parametrize("policy", [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI, o.DECISIVE_MAST_WIN])
+def test_lane_refill_paths_bit_exact(game, policy, monkeypatch):
+    """Bench-size batches run 512-playout grabs: a lane retires a playout and pulls the next one of its task at a window
+    boundary.  Small batches never do (32-playout grabs), so this forces the grab size and checks every per-playout and
+    aggregate output again, with tasks cut at leaf boundaries (k = 200 is not a multiple of 32)."""
+    monkeypatch.setenv("MR_GRAB_MIN", "512")
+    monkeypatch.setenv("MR_GRAB_MAX", "512")
+    leaves = _leaves(game, n_per=2)
+    depth = 200 if game == o.KNIGHTTHROUGH else 0
+    mast = _random_mast(game, 3) if policy in (o.EPS_MAST, o.DECISIVE_MAST_WIN) else None
+    _compare(game, policy, leaves, 200, seed=91, max_depth=depth, mast=mast, amaf=True, delta=True)
+
+
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.OTHELLO])
+@pytest.mark.parametrize("policy", [o.EPS_LGR, o.EPS_NST])
+def test_context_policies_on_long_tasks(game, policy, monkeypatch):
+    """Many playouts per leaf: lanes retire playouts and pull new ones inside one task, and every new playout must start
+    from the LEAF's preceding action again (not from the last move of the playout the lane just finished).  Small batches
+    are cut into 32-playout grabs (one playout per lane); the launch knob forces the 512-playout grabs of bench-size
+    batches."""
+    monkeypatch.setenv("MR_GRAB_MIN", "512")
+    monkeypatch.setenv("MR_GRAB_MAX", "512")
+    leaves = _leaves(game, n_per=1)
+    prevs = _random_replies(game, leaves, 3, 1.0)
+    by_player = [prevs[p][prevs[p] > 0] for p in range(2)]
+    for i in range(len(leaves)):
+        other = by_player[1 - int(leaves[i]["turn"])]
+        leaves["prev"][i] = other[i % len(other)]
+    k, mt = 1500, MAX_TRACE[game]
+    base = o.playout_batch(game, leaves, 64, seed=13, want_mast_delta=True, want_bigram_delta=True, threads=o.host_threads())
+    kw = dict(policy=policy, eps=0.1, seed=5, want_trace=True, max_trace=mt, threads=o.host_threads())
+    if policy == o.EPS_LGR:
+        table = _random_replies(game, leaves, 5, 1.0)
+        ref = o.playout_batch(game, leaves, k, replies=table, want_reply_updates=True, **kw)
+        with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyLgr(0.1), seed=5) as g:
+            g.set_replies(table)
+            got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, want_trace=True, max_trace=mt)
+        assert (got.reply_updates["order"] == ref["reply_order"]).all()
+        assert (got.reply_updates["action_plus1"] == ref["reply_action"]).all()
+    else:
+        ref = o.playout_batch(game, leaves, k, mast=base["mast_delta"], bigram=base["bigram_delta"], nst_threshold=1,
+                              want_bigram_delta=True, **kw)
+        with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyNst(0.1, 1), seed=5) as g:
+            g.set_bigrams(base["bigram_delta"])
+            got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, stats=base["mast_delta"], want_trace=True, max_trace=mt)
+        assert got.bigram_delta.tobytes() == ref["bigram_delta"].tobytes()
+    assert (got.trace == ref["trace"]).all()
+    assert got.results.tobytes() == ref["results"].tobytes()
+
+
 def test_reference_shaped_playout_call():
     """SimulateStrategy::playout(state, max_playout_depth, stats, prev_action, rng) -> Trial"""
     game = o.CONNECT4
