@@ -92,7 +92,13 @@ enum mr_policy {
      * unigram (MAST) score otherwise.  The unigram table is mr_submit's mast_in, the bigram table comes from
      * mr_set_bigrams; the batch's bigram statistics come back through mr_bigram_delta (the unigram ones as the usual
      * MR_WANT_MAST_DELTA).  Two draws per ply, as MR_EPS_MAST. */
-    MR_EPS_NST = 9
+    MR_EPS_NST = 9,
+    /* simulate.rs:1036-1142 + 538-570  EpsilonGreedy<G, Lgr2<G, Lgr<G, Uniform>>> (strategy.rs:143-156 Ucb1Lgr2, LGRF-2):
+     * unless the ply explores, the reply recorded for (mover, its own previous action IN THIS PLAYOUT, the opponent's
+     * answer) if legal; else the LGR-1 reply of MR_EPS_LGR; else a uniform pick.  Both tables are frozen for the batch
+     * (mr_set_replies, mr_set_replies2); the LGR-1 updates come back through mr_reply_updates, the 2-ply table's
+     * inserts and removals ("forgetting") through mr_reply2_inserts / mr_reply2_resolve.  Two draws per ply. */
+    MR_EPS_LGR2 = 10
 };
 
 enum mr_flags {
@@ -117,7 +123,10 @@ enum mr_end_type { MR_END_TERMINAL = 0, MR_END_TURN_LIMIT = 1, MR_END_NO_ACTIONS
  *   flag: Connect4 / Breakthrough / Knightthrough `winner`; Othello `last_pass`; Hex unused
  *   prev_action_plus1: 1 + compact code of the action played just before this state (the last edge of the tree
  *       descent), 0 = none -- the `prev_action` argument of SimulateStrategy::playout (simulate.rs:67-90).  Call
- *       context, not game state: read by MR_EPS_LGR only, reported as 0 in final states.
+ *       context, not game state: read by MR_EPS_LGR / MR_EPS_NST / MR_EPS_LGR2 only, reported as 0 in final states.
+ *   prev2_action_plus1: the same for the action before that one (the second-to-last edge of the descent, made by the
+ *       player now to move), 0 = none; ignored when prev_action_plus1 is 0.  Read by MR_EPS_LGR2 only, and only for
+ *       the table UPDATES of the first two plies (a playout's own-previous-move context starts empty, simulate.rs:98).
  * Zobrist hashes carried by the reference structs are tree-side state and are not part of the record.
  */
 typedef struct {
@@ -125,7 +134,8 @@ typedef struct {
     uint8_t turn;
     uint8_t flag;
     uint16_t prev_action_plus1;
-    uint8_t pad[4];
+    uint16_t prev2_action_plus1;
+    uint8_t pad[2];
 } mr_leaf;
 
 /* Aggregate of one leaf's playouts; what k calls of ChildArray::update / NodeStats::update need:
@@ -232,6 +242,31 @@ typedef struct {
 } mr_reply_update;
 int mr_set_replies(mr_ctx *ctx, int game, const uint16_t *replies);
 int mr_reply_updates(mr_ctx *ctx, int slot, mr_reply_update *updates_out, uint32_t *last_win_out);
+
+/* ---- Last Good Reply with Forgetting, 2-ply (MR_EPS_LGR2) ----
+ * TreeStats.player_replies2 (search/shared.rs:77-84; read simulate.rs:1113-1141, written backprop.rs:926-966) crosses the
+ * ABI as replies2[2][S][S], S = mr_num_slots(game): [mover][slot of the mover's own previous action][slot of the
+ * opponent's answer] = 1 + compact code of the recorded reply, 0 = none.  mr_set_replies2 copies it (NULL clears).
+ *
+ * The reference updates the table trial by trial: a player that did not lose INSERTS (context -> action) for each of
+ * its plies, a player that lost REMOVES the entry of the context if it still names the action it just played.  The
+ * outcome after a batch depends only on, per context, the LAST insert and whether a removal of that same action
+ * follows it (all of a player's events in one trial are of one kind, so "follows" is decided by the global playout
+ * index g alone).  The batch therefore reports in two steps, called after mr_wait and before the slot's next submit:
+ *   mr_reply2_inserts   inserts_out [2][S][S]: per context the last insert of the PLAYOUT part (windows of three
+ *                       consecutive actions of [leaf prev2, leaf prev, playout...] that end in a playout action), same
+ *                       order stamp as mr_reply_update; last_lose_out [n_leaves][2] (nullable) = 1 + the leaf's last
+ *                       playout index that p LOST (the trials in which tree-path windows remove), 0 = none
+ *   mr_reply2_resolve   merged [2][S][S]: the CANDIDATE entry per context -- the caller's last insert after adding its
+ *                       tree-path windows (order > 0), or the entry its table holds now (order = 0, action_plus1 =
+ *                       that entry), or nothing (action_plus1 = 0).  Replays the batch on the GPU and sets removed_out
+ *                       [2][S][S] to 1 where a losing playout with a LATER g played the candidate action in that
+ *                       context, else 0.
+ * New entry of a context = none if removed (or removed by one of the caller's own later tree-path windows), else the
+ * merged insert's action, else the old entry. */
+int mr_set_replies2(mr_ctx *ctx, int game, const uint16_t *replies2);
+int mr_reply2_inserts(mr_ctx *ctx, int slot, mr_reply_update *inserts_out, uint32_t *last_lose_out);
+int mr_reply2_resolve(mr_ctx *ctx, int slot, const mr_reply_update *merged, uint8_t *removed_out);
 
 /* ---- N-gram Selection Technique (MR_EPS_NST) ----
  * Bigram tables are keyed by COMPACT per-player action indices ("slots"), because the dense id space of Breakthrough /

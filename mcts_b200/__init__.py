@@ -12,6 +12,7 @@ from .rollout import (
     DecisiveMoveWin,
     EndType,
     EpsilonGreedyLgr,
+    EpsilonGreedyLgr2,
     EpsilonGreedyMast,
     EpsilonGreedyNst,
     Game,
@@ -30,7 +31,7 @@ from .rollout import (
 )
 
 __all__ = [
-    "BatchResult", "DecisiveMove", "DecisiveMoveMast", "DecisiveMoveWin", "EndType", "EpsilonGreedyLgr", "EpsilonGreedyMast", "EpsilonGreedyNst", "Game", "GpuRollout", "MastTable", "Outcome",
+    "BatchResult", "DecisiveMove", "DecisiveMoveMast", "DecisiveMoveWin", "EndType", "EpsilonGreedyLgr", "EpsilonGreedyLgr2", "EpsilonGreedyMast", "EpsilonGreedyNst", "Game", "GpuRollout", "MastTable", "Outcome",
     "Policy", "Trial", "Uniform", "initial_state", "make_leaf", "num_actions", "LEAF_DTYPE", "RECORD_DTYPE",
     "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load", "GpuSearch", "SearchResult", "apply",
     "generate_actions", "terminal_status",

@@ -17,7 +17,7 @@ LIB_PATH = _build.LIB_PATH
 MR_OK = 0
 ERR_NAMES = {1: "MR_ERR_INVALID", 2: "MR_ERR_CUDA", 3: "MR_ERR_NO_DEVICE", 4: "MR_ERR_BUSY", 5: "MR_ERR_UNSUPPORTED", 6: "MR_ERR_COMM"}
 
-LEAF_DTYPE = np.dtype([("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("prev", "<u2"), ("pad", "u1", (4,))])
+LEAF_DTYPE = np.dtype([("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("prev", "<u2"), ("prev2", "<u2"), ("pad", "u1", (2,))])
 REPLY_UPDATE_DTYPE = np.dtype([("order", "<u8"), ("action_plus1", "<u2"), ("pad", "<u2", (3,))])
 RESULT_DTYPE = np.dtype([("wins", "<u4", (2,)), ("draws", "<u4"), ("cutoffs", "<u4"), ("sum_depth", "<u8")])
 STAT_DTYPE = np.dtype([("visits", "<u4"), ("score", "<i4")])
@@ -102,6 +102,9 @@ EXPORTS = [
     "mr_set_mast",
     "mr_set_replies",
     "mr_reply_updates",
+    "mr_set_replies2",
+    "mr_reply2_inserts",
+    "mr_reply2_resolve",
     "mr_num_slots",
     "mr_action_slot",
     "mr_slot_action",
@@ -150,6 +153,9 @@ def load() -> C.CDLL:
     L.mr_set_mast.argtypes = [vp, i32, vp]
     L.mr_set_replies.argtypes = [vp, i32, vp]
     L.mr_reply_updates.argtypes = [vp, i32, vp, vp]
+    L.mr_set_replies2.argtypes = [vp, i32, vp]
+    L.mr_reply2_inserts.argtypes = [vp, i32, vp, vp]
+    L.mr_reply2_resolve.argtypes = [vp, i32, vp, vp]
     L.mr_num_slots.argtypes = [i32]
     L.mr_action_slot.argtypes = [i32, i32, C.c_uint16]
     L.mr_slot_action.argtypes = [i32, i32, i32]

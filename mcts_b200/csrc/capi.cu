@@ -80,6 +80,13 @@ struct SlotDev {
     DevBuf<uint16_t> lgr_in;                // MR_EPS_LGR: frozen reply table
     DevBuf<unsigned long long> lgr_stamps;  // MR_EPS_LGR: last winning occurrence per (player, preceding action)
     DevBuf<uint32_t> lgr_last;              // MR_EPS_LGR: per leaf, last playout each player did not lose
+    DevBuf<uint16_t> lgr2_in;               // MR_EPS_LGR2: frozen 2-ply reply table [2][S][S]
+    DevBuf<unsigned long long> lgr2_stamps; // MR_EPS_LGR2: last insert per context (pass 1)
+    DevBuf<uint32_t> lgr2_last_lose;        // MR_EPS_LGR2: per leaf, last playout each player lost
+    DevBuf<unsigned long long> lgr2_target; // MR_EPS_LGR2 pass 2: candidate entry per context
+    DevBuf<uint8_t> lgr2_removed;           // MR_EPS_LGR2 pass 2: contexts whose candidate a later losing playout removes
+    DevBuf<mr_leaf_result> results2;        // MR_EPS_LGR2 pass 2: scratch results of the replay
+    KernelParams kp_saved{};                // the batch's launch parameters, for the pass-2 replay
     DevBuf<uint64_t> nst_planes;            // MR_EPS_NST: rank planes per context [2][S + 1][KINDS][MAST_BITS]
     DevBuf<uint32_t> nst_nbits;             // MR_EPS_NST: [2][S + 1]
     DevBuf<uint16_t> nst_rank_small;        // MR_EPS_NST: [2][S + 1][8] (Connect4)
@@ -106,6 +113,8 @@ struct SlotState {
     float kernel_ms = 0.f;
     bool lgr_ready = false; // a completed MR_EPS_LGR batch whose updates can still be read
     bool nst_ready = false; // a completed MR_EPS_NST batch whose bigram delta can still be read
+    bool lgr2_ready = false; // a completed MR_EPS_LGR2 batch that can still be resolved
+    uint32_t trace_cap = 0;
 };
 
 
@@ -124,6 +133,9 @@ struct mr_ctx {
     // Last Good Reply table (mr_set_replies), [2][num_actions] of its game
     std::vector<uint16_t> replies;
     int replies_game = -1;
+    // LGRF-2 table (mr_set_replies2), [2][S][S] of its game
+    std::vector<uint16_t> replies2;
+    int replies2_game = -1;
     // N-gram Selection Technique (mr_set_bigrams): bigram[2][S][S] of its game and the backoff threshold; the per-context
     // rank tables built from it and the submit's unigram table
     std::vector<mr_action_stat> bigram;
@@ -417,7 +429,9 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
         if (!has_mast) return fail(ctx, MR_ERR_INVALID, "a MAST policy needs a MAST snapshot (mast_in / mr_set_mast)");
         if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
     }
-    if (d->policy == MR_EPS_LGR) {
+    if (policy_is_lgr((int)d->policy)) {
+        if (d->policy == MR_EPS_LGR2 && ctx->replies2_game >= 0 && ctx->replies2_game != (int)d->game)
+            return fail(ctx, MR_ERR_INVALID, "the 2-ply reply table was set for game %d, the batch is game %u", ctx->replies2_game, d->game);
         if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
         if (ctx->replies_game >= 0 && ctx->replies_game != (int)d->game)
             return fail(ctx, MR_ERR_INVALID, "the reply table was set for game %d, the batch is game %u", ctx->replies_game, d->game);
@@ -430,7 +444,7 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
     // (the Hex fill-then-search kernel derives AMAF from board masks; every per-ply kernel uses the slot trace)
     const bool hex_fast = d->game == MR_HEX11 && d->policy == MR_UNIFORM && !(d->flags & MR_WANT_MAST_DELTA);
     const bool needs_scratch = (d->flags & MR_WANT_MAST_DELTA) || ((d->flags & MR_WANT_AMAF) && !hex_fast) ||
-                               d->policy == MR_EPS_LGR || d->policy == MR_EPS_NST;
+                               policy_is_lgr((int)d->policy) || d->policy == MR_EPS_NST;
     if (needs_scratch) {
         const uint32_t bound = kGames[d->game].depth_bound;
         cap = d->max_playout_depth ? d->max_playout_depth : bound;
@@ -598,6 +612,12 @@ void mr_destroy(mr_ctx *ctx) {
             sd.lgr_in.release();
             sd.lgr_stamps.release();
             sd.lgr_last.release();
+            sd.lgr2_in.release();
+            sd.lgr2_stamps.release();
+            sd.lgr2_last_lose.release();
+            sd.lgr2_target.release();
+            sd.lgr2_removed.release();
+            sd.results2.release();
             sd.nst_planes.release();
             sd.nst_nbits.release();
             sd.nst_rank_small.release();
@@ -706,7 +726,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             CUDA_TRY(ctx, sd.final_state.reserve((size_t)total, true));
             kp.final_state = sd.final_state.d;
         }
-        if (desc->policy == MR_EPS_LGR) {
+        if (policy_is_lgr((int)desc->policy)) {
             const size_t cnt = (size_t)2 * na;
             CUDA_TRY(ctx, sd.lgr_stamps.reserve(cnt, true));
             CUDA_TRY(ctx, sd.lgr_last.reserve((size_t)2 * n, true));
@@ -719,6 +739,21 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
                 memcpy(sd.lgr_in.h, ctx->replies.data(), sizeof(uint16_t) * cnt);
                 CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_in.d, sd.lgr_in.h, sizeof(uint16_t) * cnt, cudaMemcpyHostToDevice, dv.stream));
                 kp.lgr_in = sd.lgr_in.d;
+            }
+        }
+        if (desc->policy == MR_EPS_LGR2) {
+            const size_t S = (size_t)kSlots[desc->game], cnt2 = 2 * S * S;
+            CUDA_TRY(ctx, sd.lgr2_stamps.reserve(cnt2, true));
+            CUDA_TRY(ctx, sd.lgr2_last_lose.reserve((size_t)2 * n, true));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_stamps.d, 0, sizeof(unsigned long long) * cnt2, dv.stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_last_lose.d, 0, sizeof(uint32_t) * 2 * n, dv.stream));
+            kp.lgr2_stamps = sd.lgr2_stamps.d;
+            kp.lgr2_last_lose = sd.lgr2_last_lose.d;
+            if (!ctx->replies2.empty()) {
+                CUDA_TRY(ctx, sd.lgr2_in.reserve(cnt2, true));
+                memcpy(sd.lgr2_in.h, ctx->replies2.data(), sizeof(uint16_t) * cnt2);
+                CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_in.d, sd.lgr2_in.h, sizeof(uint16_t) * cnt2, cudaMemcpyHostToDevice, dv.stream));
+                kp.lgr2_in = sd.lgr2_in.d;
             }
         }
         if (desc->policy == MR_EPS_NST) {
@@ -743,6 +778,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
         rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter, slot);
         if (rc != MR_OK) return rc;
         CUDA_TRY(ctx, cudaEventRecord(sd.ev_end, dv.stream));
+        sd.kp_saved = kp;
 
         // results come back on the same stream
         CUDA_TRY(ctx, cudaMemcpyAsync(sd.results.h, sd.results.d, sizeof(mr_leaf_result) * n, cudaMemcpyDeviceToHost, dv.stream));
@@ -750,7 +786,12 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.amaf.h, sd.amaf.d, sizeof(mr_action_stat) * n * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
         if (desc->flags & MR_WANT_MAST_DELTA)
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.mast_delta.h, sd.mast_delta.d, sizeof(mr_action_stat) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
-        if (desc->policy == MR_EPS_LGR) {
+        if (desc->policy == MR_EPS_LGR2) {
+            const size_t S = (size_t)kSlots[desc->game];
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_stamps.h, sd.lgr2_stamps.d, sizeof(unsigned long long) * 2 * S * S, cudaMemcpyDeviceToHost, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_last_lose.h, sd.lgr2_last_lose.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, dv.stream));
+        }
+        if (policy_is_lgr((int)desc->policy)) {
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_stamps.h, sd.lgr_stamps.d, sizeof(unsigned long long) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_last.h, sd.lgr_last.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, dv.stream));
         }
@@ -774,6 +815,8 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
     ss.busy = true;
     ss.lgr_ready = false;
     ss.nst_ready = false;
+    ss.lgr2_ready = false;
+    ss.trace_cap = trace_cap;
     ss.desc = *desc;
     return MR_OK;
 }
@@ -801,7 +844,8 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
         }
     }
     ss.kernel_ms = worst_ms;
-    ss.lgr_ready = d.policy == MR_EPS_LGR;
+    ss.lgr_ready = policy_is_lgr((int)d.policy);
+    ss.lgr2_ready = d.policy == MR_EPS_LGR2;
     ss.nst_ready = d.policy == MR_EPS_NST;
     memset(out, 0, sizeof(mr_leaf_result) * n);
     if (amaf_out && (d.flags & MR_WANT_AMAF)) memset(amaf_out, 0, sizeof(mr_action_stat) * (size_t)n * 2 * na);
@@ -847,7 +891,7 @@ int mr_reply_updates(mr_ctx *ctx, int slot, mr_reply_update *updates_out, uint32
     if (slot < 0 || slot >= MR_NUM_SLOTS) return fail(ctx, MR_ERR_INVALID, "slot %d out of range", slot);
     SlotState &ss = ctx->slot[slot];
     if (ss.busy || !ss.lgr_ready)
-        return fail(ctx, MR_ERR_INVALID, "slot %d holds no completed MR_EPS_LGR batch (call mr_wait first)", slot);
+        return fail(ctx, MR_ERR_INVALID, "slot %d holds no completed MR_EPS_LGR / MR_EPS_LGR2 batch (call mr_wait first)", slot);
     const mr_batch_desc &d = ss.desc;
     const int game = (int)d.game, na = kGames[game].num_actions;
     const bool through = game == MR_BREAKTHROUGH || game == MR_KNIGHTTHROUGH;
@@ -876,6 +920,123 @@ int mr_reply_updates(mr_ctx *ctx, int slot, mr_reply_update *updates_out, uint32
             }
             last_win_out[i] = best;
         }
+    }
+    return MR_OK;
+}
+
+int mr_set_replies2(mr_ctx *ctx, int game, const uint16_t *replies2) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (game < 0 || game >= MR_NUM_GAMES) return fail(ctx, MR_ERR_INVALID, "mr_set_replies2: unknown game %d", game);
+    if (!replies2) {
+        ctx->replies2.clear();
+        ctx->replies2_game = -1;
+        return MR_OK;
+    }
+    const size_t S = (size_t)kSlots[game];
+    ctx->replies2.assign(replies2, replies2 + 2 * S * S);
+    ctx->replies2_game = game;
+    return MR_OK;
+}
+
+int mr_reply2_inserts(mr_ctx *ctx, int slot, mr_reply_update *inserts_out, uint32_t *last_lose_out) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (slot < 0 || slot >= MR_NUM_SLOTS) return fail(ctx, MR_ERR_INVALID, "slot %d out of range", slot);
+    SlotState &ss = ctx->slot[slot];
+    if (ss.busy || !ss.lgr2_ready)
+        return fail(ctx, MR_ERR_INVALID, "slot %d holds no completed MR_EPS_LGR2 batch (call mr_wait first)", slot);
+    const mr_batch_desc &d = ss.desc;
+    const int game = (int)d.game;
+    const size_t S = (size_t)kSlots[game];
+    if (inserts_out) {
+        for (size_t i = 0; i < 2 * S * S; ++i) {
+            unsigned long long best = 0;
+            for (Device &dv : ctx->dev) {
+                SlotDev &sd = dv.slot[slot];
+                if (sd.g_end > sd.g_begin) best = std::max(best, sd.lgr2_stamps.h[i]);
+            }
+            mr_reply_update &u = inserts_out[i];
+            memset(&u, 0, sizeof u);
+            if (best) {
+                const int pl = i >= S * S ? 1 : 0;
+                u.order = best >> 13;
+                u.action_plus1 = (uint16_t)(slot_action(game, pl, (int)(best & 0x1fffull)) + 1);
+            }
+        }
+    }
+    if (last_lose_out) {
+        for (uint32_t i = 0; i < 2 * d.n_leaves; ++i) {
+            uint32_t best = 0;
+            for (Device &dv : ctx->dev) {
+                SlotDev &sd = dv.slot[slot];
+                if (sd.g_end > sd.g_begin) best = std::max(best, sd.lgr2_last_lose.h[i]);
+            }
+            last_lose_out[i] = best;
+        }
+    }
+    return MR_OK;
+}
+
+int mr_reply2_resolve(mr_ctx *ctx, int slot, const mr_reply_update *merged, uint8_t *removed_out) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    if (slot < 0 || slot >= MR_NUM_SLOTS) return fail(ctx, MR_ERR_INVALID, "slot %d out of range", slot);
+    SlotState &ss = ctx->slot[slot];
+    if (ss.busy || !ss.lgr2_ready)
+        return fail(ctx, MR_ERR_INVALID, "slot %d holds no completed MR_EPS_LGR2 batch (call mr_wait first)", slot);
+    if (!merged || !removed_out) return fail(ctx, MR_ERR_INVALID, "mr_reply2_resolve: null buffer");
+    const mr_batch_desc &d = ss.desc;
+    const int game = (int)d.game;
+    const size_t S = (size_t)kSlots[game], cnt = 2 * S * S;
+    // candidate entry per context: the caller's last insert (order > 0), or the entry its table holds now (order == 0,
+    // removable by any losing playout of the batch)
+    std::vector<unsigned long long> target(cnt, 0ull);
+    for (size_t i = 0; i < cnt; ++i) {
+        if (!merged[i].action_plus1) continue;
+        const int pl = i >= S * S ? 1 : 0;
+        const int a = action_slot(game, pl, (uint32_t)merged[i].action_plus1 - 1u);
+        if (a < 0) return fail(ctx, MR_ERR_INVALID, "mr_reply2_resolve: merged[%zu] names no action of player %d", i, pl);
+        target[i] = ((unsigned long long)(merged[i].order >> 13) << 16) | (unsigned long long)(a + 1);
+    }
+    kernel_fn fn = pick_kernel(game, MR_EPS_LGR2, 0, 0);
+    if (!fn) return fail(ctx, MR_ERR_UNSUPPORTED, "MR_EPS_LGR2 is not built for game %d", game);
+    memset(removed_out, 0, cnt);
+    for (Device &dv : ctx->dev) {
+        SlotDev &sd = dv.slot[slot];
+        if (sd.g_end == sd.g_begin) continue;
+        CUDA_TRY(ctx, cudaSetDevice(dv.id));
+        LaunchPlan lp;
+        int rc = plan_launch(ctx, dv, fn, &d, 1, &lp);
+        if (rc != MR_OK) return rc;
+        CUDA_TRY(ctx, sd.lgr2_target.reserve(cnt, true));
+        CUDA_TRY(ctx, sd.lgr2_removed.reserve(cnt, true));
+        CUDA_TRY(ctx, sd.results2.reserve(d.n_leaves, false));
+        memcpy(sd.lgr2_target.h, target.data(), sizeof(unsigned long long) * cnt);
+        CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_target.d, sd.lgr2_target.h, sizeof(unsigned long long) * cnt, cudaMemcpyHostToDevice, dv.stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_removed.d, 0, cnt, dv.stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(sd.results2.d, 0, sizeof(mr_leaf_result) * d.n_leaves, dv.stream));
+        // the same playouts again (same leaves, tables, seed and range), with every other output switched off
+        KernelParams kp = sd.kp_saved;
+        kp.results = sd.results2.d;
+        kp.amaf = nullptr;
+        kp.mast_delta = nullptr;
+        kp.trace = nullptr;
+        kp.rec = nullptr;
+        kp.final_state = nullptr;
+        kp.lgr_stamps = nullptr;
+        kp.lgr_last = nullptr;
+        kp.lgr2_stamps = nullptr;
+        kp.lgr2_last_lose = nullptr;
+        kp.lgr2_target = sd.lgr2_target.d;
+        kp.lgr2_removed = sd.lgr2_removed.d;
+        rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter, slot);
+        if (rc != MR_OK) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_removed.h, sd.lgr2_removed.d, cnt, cudaMemcpyDeviceToHost, dv.stream));
+    }
+    for (Device &dv : ctx->dev) {
+        SlotDev &sd = dv.slot[slot];
+        if (sd.g_end == sd.g_begin) continue;
+        CUDA_TRY(ctx, cudaSetDevice(dv.id));
+        CUDA_TRY(ctx, cudaStreamSynchronize(dv.stream));
+        for (size_t i = 0; i < cnt; ++i) removed_out[i] |= sd.lgr2_removed.h[i];
     }
     return MR_OK;
 }
@@ -945,7 +1106,7 @@ int mr_launch_device(mr_ctx *ctx, int device_index, const mr_batch_desc *desc, c
     if (!desc) return fail(ctx, MR_ERR_INVALID, "null batch descriptor");
     if (desc->flags & (MR_WANT_TRACE | MR_WANT_FINAL_STATE))
         return fail(ctx, MR_ERR_INVALID, "trace / final-state outputs are not available on the device-resident path");
-    if (desc->policy == MR_EPS_LGR) return fail(ctx, MR_ERR_UNSUPPORTED, "MR_EPS_LGR is not available on the device-resident path");
+    if (policy_is_lgr((int)desc->policy)) return fail(ctx, MR_ERR_UNSUPPORTED, "MR_EPS_LGR / MR_EPS_LGR2 are not available on the device-resident path");
     if (desc->policy == MR_EPS_NST) return fail(ctx, MR_ERR_UNSUPPORTED, "MR_EPS_NST is not available on the device-resident path");
     kernel_fn fn = nullptr;
     uint32_t trace_cap = 0;

@@ -17,6 +17,8 @@ __host__ __device__ constexpr bool policy_uses_mast(int policy) {
     return policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN || policy == MR_DECISIVE_MAST_WINLOSS || policy == MR_EPS_NST;
 }
 
+__host__ __device__ constexpr bool policy_is_lgr(int policy) { return policy == MR_EPS_LGR || policy == MR_EPS_LGR2; }
+
 constexpr int MAST_KINDS = 8;  // move kinds per source cell: 3 (Breakthrough) or 8 (Knightthrough)
 constexpr int MAST_BITS = 10;  // <= 513 distinct score values over the <= 512 real actions of a player
 
@@ -71,6 +73,14 @@ struct KernelParams {
     const uint16_t *lgr_in;          // [2][NA]: 1 + compact code of the reply to the preceding action id, 0 = none
     unsigned long long *lgr_stamps;  // [2][NA]: ((g + 1) << 26) | ((4096 + ply) << 13) | reply action id, max-merged
     uint32_t *lgr_last;              // [n_leaves][2]: 1 + last playout index the player did not lose, max-merged
+    // LGRF-2 (MR_EPS_LGR2), on top of the LGR-1 fields: the frozen 2-ply table in; pass 1 writes the last insert per
+    // context and each leaf's last lost playout; pass 2 (a replay with lgr2_target set) marks the contexts whose
+    // candidate entry a later losing playout removes
+    const uint16_t *lgr2_in;                // [2][S][S]: 1 + compact code of the reply to (own previous slot, opponent's slot)
+    unsigned long long *lgr2_stamps;        // [2][S][S]: ((g + 1) << 26) | ((4096 + ply) << 13) | reply slot, max-merged
+    uint32_t *lgr2_last_lose;               // [n_leaves][2]: 1 + last playout index the player lost, max-merged
+    const unsigned long long *lgr2_target;  // pass 2, [2][S][S]: ((g* + 1) << 16) | (1 + candidate slot), 0 = no candidate
+    uint8_t *lgr2_removed;                  // pass 2, [2][S][S]
     // N-gram Selection Technique (MR_EPS_NST): rank planes per CONTEXT (mover, 1 + slot of the preceding action; 0 = no
     // preceding action = the unigram ranks), resolved on the host from the bigram / unigram tables and the backoff
     const uint64_t *nst_planes;      // [2][NSLOTS + 1][KINDS][MAST_BITS]

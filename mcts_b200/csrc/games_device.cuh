@@ -77,6 +77,7 @@ struct Connect4 {
     uint32_t n_open;
     uint32_t rt_parity;
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + compact code of the recorded reply for this ply, 0 = none / exploring
+    uint32_t lgr_reply2; // MR_EPS_LGR2: the 2-ply table's reply, tried before lgr_reply
     // MR_EPS_NST: this ply's context (mover, preceding action) rank planes / per-column ranks, set by the kernel
     const uint64_t (*nst_planes)[MAST_BITS];
     uint32_t nst_nbits;
@@ -198,9 +199,13 @@ struct Connect4 {
                 const uint64_t cand = (T == 0 ? moves : ((T & (T - 1)) == 0 ? T : 0ull)) & ~(W >> 1);
                 bit = cand & (0 - cand);
             }
-        } else if (POLICY == MR_EPS_LGR) {
-            // the recorded reply column, if it is still open (simulate.rs:1022-1026)
+        } else if (policy_is_lgr(POLICY)) {
+            // the recorded reply column, if it is still open (simulate.rs:1022-1026); LGRF-2 tries its 2-ply reply first
             bit = (lgr_reply && lgr_reply <= 7u) ? (moves & (0xFFull << (8u * (lgr_reply - 1u)))) : 0ull;
+            if (POLICY == MR_EPS_LGR2) {
+                const uint64_t b2 = (lgr_reply2 && lgr_reply2 <= 7u) ? (moves & (0xFFull << (8u * (lgr_reply2 - 1u)))) : 0ull;
+                bit = b2 ? b2 : bit;
+            }
         } else {
             bit = 0;
         }
@@ -266,7 +271,8 @@ struct Connect4 {
         out->turn = (uint8_t)(won ? next ^ 1 : next);
         out->flag = won ? 1 : 0;
         out->prev_action_plus1 = 0;
-        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
+        out->prev2_action_plus1 = 0;
+        out->pad[0] = out->pad[1] = 0;
     }
 };
 
@@ -293,6 +299,7 @@ struct ThroughBase {
     uint64_t black, white;
     uint32_t rt_parity;
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + compact code (src << 8 | dst) of the recorded reply, 0 = none / exploring
+    uint32_t lgr_reply2; // MR_EPS_LGR2: the 2-ply table's reply, tried before lgr_reply
     // MR_EPS_NST: this ply's context (mover, preceding action) rank planes / per-column ranks, set by the kernel
     const uint64_t (*nst_planes)[MAST_BITS];
     uint32_t nst_nbits;
@@ -320,7 +327,8 @@ struct ThroughBase {
         out->turn = (uint8_t)(won ? next ^ 1 : next);
         out->flag = won ? 1 : 0;
         out->prev_action_plus1 = 0;
-        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
+        out->prev2_action_plus1 = 0;
+        out->pad[0] = out->pad[1] = 0;
     }
     // own/opp update for a move src -> dst by `white`; returns true when the far wall is reached
     __device__ bool apply_move(bool is_white, uint32_t src, uint32_t dst) {
@@ -538,18 +546,23 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
             }
         }
     }
-    if (POLICY == MR_EPS_LGR) {
-        // the recorded reply, if it is legal now (simulate.rs:1022-1026); else the uniform pick
+    if (policy_is_lgr(POLICY)) {
+        // the recorded reply, if it is legal now (simulate.rs:1022-1026); else the uniform pick.  LGRF-2 tries its 2-ply
+        // reply first (simulate.rs:1124-1131)
         idx = mulhi(x0, n);
-        if (lgr_reply) {
-            const uint32_t s0 = (lgr_reply - 1u) >> 8, d0 = (lgr_reply - 1u) & 0xffu;
-            const uint32_t dr = d0 - s0 - (is_white ? 7u : (uint32_t)-9);
-            if (s0 < 64u && dr < 3u) {
-                const uint64_t mk = dr == 0 ? W : (dr == 1 ? F : E);
-                if ((mk >> s0) & 1ull) {
-                    src = s0;
-                    dir = dr;
-                    have = true;
+#pragma unroll
+        for (int c = (POLICY == MR_EPS_LGR2 ? 0 : 1); c < 2; ++c) {
+            const uint32_t rep = c == 0 ? lgr_reply2 : lgr_reply;
+            if (!have && rep) {
+                const uint32_t s0 = (rep - 1u) >> 8, d0 = (rep - 1u) & 0xffu;
+                const uint32_t dr = d0 - s0 - (is_white ? 7u : (uint32_t)-9);
+                if (s0 < 64u && dr < 3u) {
+                    const uint64_t mk = dr == 0 ? W : (dr == 1 ? F : E);
+                    if ((mk >> s0) & 1ull) {
+                        src = s0;
+                        dir = dr;
+                        have = true;
+                    }
                 }
             }
         }
@@ -740,18 +753,22 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
             }
         }
     }
-    if (POLICY == MR_EPS_LGR) {
+    if (policy_is_lgr(POLICY)) {
         idx = mulhi(x0, n);
-        if (lgr_reply) {
-            const uint32_t s0 = (lgr_reply - 1u) >> 8, d0 = (lgr_reply - 1u) & 0xffu;
-            if (s0 < 64u) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if ((int)d0 - (int)s0 == delta((uint32_t)q) && ((M[q] >> s0) & 1ull)) {
-                        src = s0;
-                        kind = q;
-                        have = true;
-                    }
+        for (int c = (POLICY == MR_EPS_LGR2 ? 0 : 1); c < 2; ++c) {
+            const uint32_t rep = c == 0 ? lgr_reply2 : lgr_reply;
+            if (!have && rep) {
+                const uint32_t s0 = (rep - 1u) >> 8, d0 = (rep - 1u) & 0xffu;
+                if (s0 < 64u) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if ((int)d0 - (int)s0 == delta((uint32_t)q) && ((M[q] >> s0) & 1ull)) {
+                            src = s0;
+                            kind = q;
+                            have = true;
+                        }
+                }
             }
         }
     }
@@ -860,6 +877,7 @@ struct Othello {
     uint32_t last_pass;
     uint32_t rt_parity; // parity of the current ply inside its window (PARITY == 2 call sites)
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + square of the recorded reply (65 = PASS), 0 = none / exploring
+    uint32_t lgr_reply2; // MR_EPS_LGR2: the 2-ply table's reply, tried before lgr_reply
     const uint64_t (*nst_planes)[MAST_BITS]; // MR_EPS_NST: this ply's context rank planes, set by the kernel
     uint32_t nst_nbits;
     const uint16_t *nst_ranks;
@@ -1019,13 +1037,17 @@ struct Othello {
             fl = flips(mv, P, O);
             have = true;
         }
-        if (POLICY == MR_EPS_LGR && lgr_reply && lgr_reply <= 64u && ((moves >> (lgr_reply - 1u)) & 1ull)) {
+        if (policy_is_lgr(POLICY)) {
             // the recorded reply square, if legal now (a recorded PASS is legal exactly when it is the only action,
-            // handled above)
-            sq = lgr_reply - 1u;
-            mv = bit64(sq);
-            fl = flips(mv, P, O);
-            have = true;
+            // handled above); LGRF-2 tries its 2-ply reply first
+            uint32_t rep = (lgr_reply && lgr_reply <= 64u && ((moves >> (lgr_reply - 1u)) & 1ull)) ? lgr_reply : 0u;
+            if (POLICY == MR_EPS_LGR2 && lgr_reply2 && lgr_reply2 <= 64u && ((moves >> (lgr_reply2 - 1u)) & 1ull)) rep = lgr_reply2;
+            if (rep) {
+                sq = rep - 1u;
+                mv = bit64(sq);
+                fl = flips(mv, P, O);
+                have = true;
+            }
         }
         if (!have) {
             sq = select64(moves, mulhi(x0, n));
@@ -1052,7 +1074,8 @@ struct Othello {
         out->turn = (uint8_t)((s.turn + plies) & 1);
         out->flag = (uint8_t)last_pass;
         out->prev_action_plus1 = 0;
-        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
+        out->prev2_action_plus1 = 0;
+        out->pad[0] = out->pad[1] = 0;
     }
 };
 

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                     if (WANT_FINAL && p.final_state) {
                         mr_leaf fs = s_leaf[warp];
                         fs.prev_action_plus1 = 0; // call context, not game state
+                        fs.prev2_action_plus1 = 0;
                         p.final_state[g] = fs;
                     }
                 }
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                         out->turn = (uint8_t)((leaf_turn + depth) & 1u);
                         out->flag = 0;
                         out->prev_action_plus1 = 0;
-        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
+        out->prev2_action_plus1 = 0;
+        out->pad[0] = out->pad[1] = 0;
                     }
                 }
                 if (WANT_AMAF) {

@@ -37,6 +37,7 @@ struct HexStep : Hex11 {
     uint32_t n_empty;
     uint32_t rt_parity;
     uint32_t lgr_reply;
+    uint32_t lgr_reply2; // MR_EPS_LGR2: the 2-ply table's reply, tried before lgr_reply
     const uint64_t (*nst_planes)[MAST_BITS]; // MR_EPS_NST: this ply's context rank planes, set by the kernel
     uint32_t nst_nbits;
     const uint16_t *nst_ranks;
@@ -170,9 +171,14 @@ struct HexStep : Hex11 {
                 }
             }
         }
-        if (POLICY == MR_EPS_LGR && lgr_reply && lgr_reply <= 121u && has_cell(empties, lgr_reply - 1u)) {
-            cell = lgr_reply - 1u; // the recorded reply, still empty (simulate.rs:1022-1026)
-            have = true;
+        if (policy_is_lgr(POLICY)) { // the recorded reply, still empty (simulate.rs:1022-1026); LGRF-2's 2-ply reply first
+            if (POLICY == MR_EPS_LGR2 && lgr_reply2 && lgr_reply2 <= 121u && has_cell(empties, lgr_reply2 - 1u)) {
+                cell = lgr_reply2 - 1u;
+                have = true;
+            } else if (lgr_reply && lgr_reply <= 121u && has_cell(empties, lgr_reply - 1u)) {
+                cell = lgr_reply - 1u;
+                have = true;
+            }
         }
         if (MAST_INNER && !have && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
             // Mast::select_move (simulate.rs:824-848): bit-sliced arg-max over the empty cells (the two 64-bit halves
@@ -262,7 +268,8 @@ struct HexStep : Hex11 {
         out->turn = (uint8_t)((sh.turn + plies) & 1u);
         out->flag = 0;
         out->prev_action_plus1 = 0;
-        for (int i = 0; i < 4; ++i) out->pad[i] = 0;
+        out->prev2_action_plus1 = 0;
+        out->pad[0] = out->pad[1] = 0;
     }
 };
 

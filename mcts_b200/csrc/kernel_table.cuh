@@ -36,6 +36,7 @@ kernel_fn pick_all_policies(int policy, int v) {
     if (policy == MR_EPS_LGR) return pick_variant<G, MR_EPS_LGR>(v);
     if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<G, MR_DECISIVE_MAST>(v);
     if (policy == MR_EPS_NST) return pick_variant<G, MR_EPS_NST>(v);
+    if (policy == MR_EPS_LGR2) return pick_variant<G, MR_EPS_LGR2>(v);
     return nullptr;
 }
 

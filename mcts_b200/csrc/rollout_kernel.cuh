@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
     constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
     constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
     constexpr bool MASK_AMAF = WANT_AMAF && G::MASK_AMAF;
-    constexpr bool IS_LGR = POLICY == MR_EPS_LGR;
+    constexpr bool IS_LGR2 = POLICY == MR_EPS_LGR2; // LGRF-2 runs the LGR-1 machinery too (its inner strategy, both tables written)
+    constexpr bool IS_LGR = POLICY == MR_EPS_LGR || IS_LGR2;
     constexpr bool IS_NST = POLICY == MR_EPS_NST;
     constexpr bool TRACK_PREV = IS_LGR || IS_NST; // the lane remembers the slot of the preceding action
     constexpr bool PAIR_DRAWS = policy_uses_mast(POLICY) || IS_LGR; // two Philox words per ply
@@ -134,14 +135,19 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
         const uint32_t leaf_turn = s_leaf[warp].turn;
         // LGR: the action that led to the leaf (playout()'s prev_action), as 1 + its slot in the numbering of the
         // player who made it (the opponent of the leaf's mover); 0 = none
-        uint32_t leaf_prev_slot1 = 0;
+        uint32_t leaf_prev_slot1 = 0, leaf_prev2_slot1 = 0;
         if constexpr (TRACK_PREV) {
             const uint32_t pa = s_leaf[warp].prev_action_plus1;
             if (pa) leaf_prev_slot1 = G::code_to_slot(1u - (leaf_turn & 1u), pa - 1u) + 1u;
+            if constexpr (IS_LGR2) { // the action before that, made by the leaf's mover (table updates of plies 0 and 1 only)
+                const uint32_t pa2 = s_leaf[warp].prev2_action_plus1;
+                if (pa && pa2) leaf_prev2_slot1 = G::code_to_slot(leaf_turn & 1u, pa2 - 1u) + 1u;
+            }
         }
 
         uint32_t acc_w0 = 0, acc_w1 = 0, acc_draw = 0, acc_cut = 0, acc_depth = 0;
         uint32_t acc_lw0 = 0, acc_lw1 = 0; // LGR: 1 + last playout id each player did not lose
+        uint32_t acc_ll0 = 0, acc_ll1 = 0; // LGRF-2: 1 + last playout id each player lost
 
         if (leaf_status != MR_NOT_TERMINAL) {
             // a terminal leaf: every playout is the zero-ply trial with the leaf's own status
@@ -152,7 +158,9 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                 else if (leaf_status == MR_WINNER_P1) acc_w1 = cnt;
                 else acc_draw = cnt;
                 if (leaf_status != MR_WINNER_P1) acc_lw0 = pid_end;
+                else acc_ll0 = pid_end;
                 if (leaf_status != MR_WINNER_P0) acc_lw1 = pid_end;
+                else acc_ll1 = pid_end;
             }
             if (WANT_TRACE || WANT_FINAL) {
                 for (uint32_t pid = pid_begin + lane; pid < pid_end; pid += 32) {
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                     if (WANT_FINAL && p.final_state) {
                         mr_leaf fs = s_leaf[warp];
                         fs.prev_action_plus1 = 0; // call context, not game state
+                        fs.prev2_action_plus1 = 0;
                         p.final_state[g] = fs;
                     }
                 }
@@ -182,6 +191,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
             int end_code = 0;
             bool cutoff = false;
             uint32_t prev_slot1 = leaf_prev_slot1; // LGR: 1 + slot of the preceding action
+            uint32_t own_slot1 = 0;                // LGRF-2: 1 + slot of the mover's own previous action in THIS playout
             st.reset(sh);
 
             for (;;) {
@@ -210,6 +220,16 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                                     reply = p.lgr_in[pl * (uint32_t)G::NA + G::slot_action_id(1u - pl, prev_slot1 - 1u)];
                                 }
                                 st.lgr_reply = reply;
+                                if constexpr (IS_LGR2) {
+                                    // Lgr2::select_move (simulate.rs:1113-1141): the context exists from the playout's
+                                    // third ply on (own_prev_action starts empty, simulate.rs:98)
+                                    uint32_t reply2 = 0;
+                                    if (depth >= 2u && p.lgr2_in && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+                                        const uint32_t pl = (leaf_turn ^ (par == 2 ? st.rt_parity : (uint32_t)par)) & 1u;
+                                        reply2 = p.lgr2_in[((size_t)pl * G::NSLOTS + own_slot1 - 1u) * G::NSLOTS + prev_slot1 - 1u];
+                                    }
+                                    st.lgr_reply2 = reply2;
+                                }
                             }
                             if constexpr (IS_NST) {
                                 // Nst::select_move (simulate.rs:898-930): the ranks of this ply's context
@@ -221,6 +241,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                             }
                             const int code = st.template step<POLICY, par>(sh, x0, x1, p, action, slot);
                             if (code & ST_MOVED) {
+                                if (IS_LGR2) own_slot1 = prev_slot1; // the next mover's own previous action is the one before this
                                 if (TRACK_PREV) prev_slot1 = slot + 1u;
                                 if (WANT_TRACE && p.trace) {
                                     if (depth < p.max_trace)
@@ -277,7 +298,9 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                         acc_depth += depth;
                         if (IS_LGR) {
                             if (e != ST_WIN_P1) acc_lw0 = max(acc_lw0, pid + 1u);
+                            else acc_ll0 = max(acc_ll0, pid + 1u);
                             if (e != ST_WIN_P0) acc_lw1 = max(acc_lw1, pid + 1u);
+                            else acc_ll1 = max(acc_ll1, pid + 1u);
                         }
                         const size_t g = (size_t)li * p.k + pid;
                         if (WANT_TRACE && p.rec) {
@@ -357,6 +380,23 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                                         const unsigned long long stamp = ((g + 1ull) << 26) | ((unsigned long long)(4096u + t) << 13) | slot;
                                         atomicMax(&lgr_tab[pl * G::NSLOTS + prev1 - 1u], stamp);
                                     }
+                                    if constexpr (IS_LGR2) {
+                                        // backprop.rs:926-966 over the windows (own previous, opponent's answer, this
+                                        // action) that end in a playout action
+                                        const uint32_t own1 = t > 1 ? (uint32_t)scratch[(t - 2u) * 32u + f] + 1u
+                                                                    : (t == 1 ? leaf_prev_slot1 : leaf_prev2_slot1);
+                                        if (own1 && prev1) {
+                                            const size_t key = ((size_t)pl * G::NSLOTS + own1 - 1u) * G::NSLOTS + prev1 - 1u;
+                                            const unsigned long long g = (unsigned long long)li * p.k + pid_f;
+                                            if (p.lgr2_target) { // pass 2: does a LATER losing playout remove the candidate?
+                                                const unsigned long long tgt = p.lgr2_target[key];
+                                                if (u < 0 && tgt && (uint32_t)(tgt & 0xffffull) == slot + 1u && g + 1ull > (tgt >> 16))
+                                                    p.lgr2_removed[key] = 1;
+                                            } else if (p.lgr2_stamps && u >= 0) { // pass 1: the last insert per context
+                                                atomicMax(&p.lgr2_stamps[key], ((g + 1ull) << 26) | ((unsigned long long)(4096u + t) << 13) | slot);
+                                            }
+                                        }
+                                    }
                                 }
                             }
                         }
@@ -393,6 +433,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                             end_code = 0;
                             cutoff = false;
                             prev_slot1 = leaf_prev_slot1; // the new playout starts from the leaf's context again
+                            own_slot1 = 0;
                         } else {
                             idle = true;
                         }
@@ -420,6 +461,14 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
             if (lane == 0) {
                 if (acc_lw0) atomicMax(&p.lgr_last[2u * li], acc_lw0);
                 if (acc_lw1) atomicMax(&p.lgr_last[2u * li + 1u], acc_lw1);
+            }
+        }
+        if (IS_LGR2 && p.lgr2_last_lose) {
+            acc_ll0 = __reduce_max_sync(FULL_MASK, acc_ll0);
+            acc_ll1 = __reduce_max_sync(FULL_MASK, acc_ll1);
+            if (lane == 0) {
+                if (acc_ll0) atomicMax(&p.lgr2_last_lose[2u * li], acc_ll0);
+                if (acc_ll1) atomicMax(&p.lgr2_last_lose[2u * li + 1u], acc_ll1);
             }
         }
         if (lane == 0) {

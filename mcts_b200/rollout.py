@@ -44,6 +44,7 @@ class Policy(IntEnum):
     DECISIVE_MAST_WIN = 7
     DECISIVE_MAST_WINLOSS = 8
     EPS_NST = 9
+    EPS_LGR2 = 10
 
 
 class Outcome(IntEnum):  # TerminalStatus (mcts/src/game.rs:117-122)
@@ -62,7 +63,7 @@ class EndType(IntEnum):  # simulate.rs:15-20 (+ the no-actions ending, :112-116)
 WANT_AMAF, WANT_MAST_DELTA, WANT_TRACE, WANT_FINAL_STATE = 1, 2, 4, 8
 
 # BackpropFlags bits (mcts/src/strategies/mcts/config.rs:11-30)
-BACKPROP_GRAVE, BACKPROP_GLOBAL, BACKPROP_AMAF, BACKPROP_NST, BACKPROP_LGR = 1, 2, 4, 8, 16
+BACKPROP_GRAVE, BACKPROP_GLOBAL, BACKPROP_AMAF, BACKPROP_NST, BACKPROP_LGR, BACKPROP_LGR2 = 1, 2, 4, 8, 16, 32
 
 OTHELLO_PASS = 64
 _INITIAL = {
@@ -188,6 +189,17 @@ class EpsilonGreedyLgr:
 
 
 @dataclass(frozen=True)
+class EpsilonGreedyLgr2:
+    """EpsilonGreedy<G, Lgr2<G, Lgr<G, Uniform>>> (simulate.rs:485-570, 1036-1142; strategy.rs:143-156 `Ucb1Lgr2`, LGRF-2)."""
+
+    epsilon: float = 0.1
+    policy = Policy.EPS_LGR2
+
+    def backprop_flags(self) -> int:
+        return BACKPROP_LGR2 | BACKPROP_LGR  # Lgr2::backprop_flags (simulate.rs:1101-1103)
+
+
+@dataclass(frozen=True)
 class EpsilonGreedyNst:
     """EpsilonGreedy<G, Nst> (simulate.rs:485-570, 852-930; strategy.rs:113-126 `Ucb1Nst`)."""
 
@@ -252,6 +264,8 @@ class BatchResult:
     reply_updates: np.ndarray | None = None  # REPLY_UPDATE_DTYPE [2][NA]  (Policy.EPS_LGR)
     last_win: np.ndarray | None = None  # u32 [n_leaves][2]                (Policy.EPS_LGR)
     bigram_delta: np.ndarray | None = None  # STAT_DTYPE [2][S][S]           (Policy.EPS_NST)
+    reply2_inserts: np.ndarray | None = None  # REPLY_UPDATE_DTYPE [2][S][S]   (Policy.EPS_LGR2)
+    last_lose: np.ndarray | None = None  # u32 [n_leaves][2]                (Policy.EPS_LGR2)
 
     def utilities_sum(self) -> np.ndarray:
         """Per leaf, per player: sum of utilities = wins[p] - losses[p] (node.rs:673-681 aggregated)."""
@@ -381,7 +395,7 @@ class GpuRollout:
         ms = C.c_float()
         self.lib.mr_last_kernel_ms(self._h, slot, C.byref(ms))
         upd = last = None
-        if d.policy == int(Policy.EPS_LGR):
+        if d.policy in (int(Policy.EPS_LGR), int(Policy.EPS_LGR2)):
             upd = np.zeros((2, self.na), dtype=REPLY_UPDATE_DTYPE)
             last = np.zeros((n, 2), dtype=np.uint32)
             self._check(self.lib.mr_reply_updates(self._h, slot, ptr(upd), ptr(last)))
@@ -390,7 +404,13 @@ class GpuRollout:
             ns = self.lib.mr_num_slots(int(self.game))
             bigram = np.zeros((2, ns, ns), dtype=STAT_DTYPE)
             self._check(self.lib.mr_bigram_delta(self._h, slot, ptr(bigram)))
-        return BatchResult(res, amaf, delta, trace, rec, final, ms.value, upd, last, bigram)
+        ins2 = lose = None
+        if d.policy == int(Policy.EPS_LGR2):
+            ns = self.lib.mr_num_slots(int(self.game))
+            ins2 = np.zeros((2, ns, ns), dtype=REPLY_UPDATE_DTYPE)
+            lose = np.zeros((n, 2), dtype=np.uint32)
+            self._check(self.lib.mr_reply2_inserts(self._h, slot, ptr(ins2), ptr(lose)))
+        return BatchResult(res, amaf, delta, trace, rec, final, ms.value, upd, last, bigram, ins2, lose)
 
     def simulate_many(self, leaves: np.ndarray, k: int, **kw) -> BatchResult:
         """k playouts of every leaf (search/core.rs:218-258 for a batch of leaves)."""
@@ -448,6 +468,41 @@ class GpuRollout:
         if tab.shape != (2, self.na):
             raise ValueError(f"reply table must have shape (2, {self.na})")
         self._check(self.lib.mr_set_replies(self._h, int(self.game), ptr(tab)))
+
+    def set_replies2(self, replies2: np.ndarray | None) -> None:
+        """The LGRF-2 table for Policy.EPS_LGR2 batches: u16 [2][S][S], S = num_slots(game), indexed [mover][slot of the
+        mover's own previous action][slot of the opponent's answer] = 1 + compact code of the reply, 0 = none
+        (TreeStats.player_replies2).  None clears it."""
+        if replies2 is None:
+            self._check(self.lib.mr_set_replies2(self._h, int(self.game), None))
+            return
+        ns = self.lib.mr_num_slots(int(self.game))
+        tab = np.ascontiguousarray(replies2, dtype=np.uint16)
+        if tab.shape != (2, ns, ns):
+            raise ValueError(f"2-ply reply table must have shape (2, {ns}, {ns})")
+        self._check(self.lib.mr_set_replies2(self._h, int(self.game), ptr(tab)))
+
+    def resolve_replies2(self, merged: np.ndarray, table: np.ndarray | None = None, slot: int = 0) -> np.ndarray:
+        """Second step of the LGRF-2 update (mr_reply2_resolve): given the last insert per context (the batch's
+        `reply2_inserts`, merged with the caller's tree-path windows) and the table being updated, replays the batch and
+        returns u8 [2][S][S]: 1 where a later losing playout removes the candidate entry (backprop.rs:961-963)."""
+        ns = self.lib.mr_num_slots(int(self.game))
+        m = np.ascontiguousarray(merged, dtype=REPLY_UPDATE_DTYPE).copy()
+        if m.shape != (2, ns, ns):
+            raise ValueError(f"merged inserts must have shape (2, {ns}, {ns})")
+        if table is not None:  # contexts without an insert: the entry the table holds now is the candidate
+            keep = m["order"] == 0
+            m["action_plus1"][keep] = np.asarray(table, dtype=np.uint16)[keep]
+        removed = np.zeros((2, ns, ns), dtype=np.uint8)
+        self._check(self.lib.mr_reply2_resolve(self._h, slot, ptr(m), ptr(removed)))
+        return removed
+
+    @staticmethod
+    def apply_replies2(table: np.ndarray, merged: np.ndarray, removed: np.ndarray) -> np.ndarray:
+        """New table = none where removed, else the merged insert's action, else the old entry."""
+        out = np.where(merged["order"] > 0, merged["action_plus1"], table).astype(np.uint16)
+        out[removed != 0] = 0
+        return out
 
     def set_bigrams(self, bigram: np.ndarray | None, backoff_threshold: int | None = None) -> None:
         """TreeStats.player_bigram_actions for Policy.EPS_NST batches: STAT_DTYPE [2][S][S], S = num_slots(game), indexed

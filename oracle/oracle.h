@@ -33,7 +33,8 @@ extern "C" {
 enum { ORC_CONNECT4 = 0, ORC_BREAKTHROUGH = 1, ORC_KNIGHTTHROUGH = 2, ORC_OTHELLO = 3, ORC_HEX11 = 4, ORC_NUM_GAMES = 5 };
 enum { ORC_UNIFORM = 0, ORC_EPS_MAST = 1, ORC_DECISIVE_WIN = 2, ORC_DECISIVE_WINLOSS = 3, ORC_DECISIVE_WINLOSSDRAW = 4, ORC_DECISIVE_ANTI = 5, ORC_EPS_LGR = 6,
        ORC_DECISIVE_MAST_WIN = 7, ORC_DECISIVE_MAST_WINLOSS = 8, /* DecisiveMove<EpsilonGreedy<Mast>>, modes Win / WinLoss */
-       ORC_EPS_NST = 9 /* EpsilonGreedy<Nst> */ };
+       ORC_EPS_NST = 9, /* EpsilonGreedy<Nst> */
+       ORC_EPS_LGR2 = 10 /* EpsilonGreedy<Lgr2<Lgr<Uniform>>> */ };
 enum { ORC_NOT_TERMINAL = 0, ORC_DRAW = 1, ORC_WINNER_P0 = 2, ORC_WINNER_P1 = 3 };
 enum { ORC_END_TERMINAL = 0, ORC_END_TURN_LIMIT = 1, ORC_END_NO_ACTIONS = 2 };
 
@@ -54,8 +55,9 @@ typedef struct {
     uint64_t board[4];
     uint8_t turn;
     uint8_t flag;
-    uint16_t prev_plus1;
-    uint8_t pad[4];
+    uint16_t prev_plus1;  /* call context: 1 + the action that led to this state (playout()'s prev_action), 0 = none */
+    uint16_t prev2_plus1; /* call context: 1 + the action before that (made by the player now to move), 0 = none */
+    uint8_t pad[2];
 } orc_state;
 
 typedef struct {
@@ -133,6 +135,18 @@ typedef struct {
     const orc_action_stat *bigram;
     uint32_t nst_threshold;
     orc_action_stat *bigram_delta_out;
+    /* ORC_EPS_LGR2 = EpsilonGreedy<Lgr2<Lgr<Uniform>>> (simulate.rs:1036-1142; strategy.rs:143-156 Ucb1Lgr2): unless the
+     * ply explores, the mover plays replies2[mover][its own previous action IN THIS PLAYOUT][the opponent's reply to it]
+     * when recorded and legal, else the LGR-1 reply (`replies`), else the uniform pick.  replies2: [2][S][S] over action
+     * slots, values 1 + compact code, 0 = none; frozen for the batch.
+     * replies_final_out [2][num_actions] / replies2_final_out [2][S][S] (nullable): the two tables after the LITERAL
+     * trial-by-trial updates of backprop.rs:908-966 for every playout of the batch in global playout order, restricted
+     * to the windows that end in a playout action (the leaf's prev / prev2 supply the first contexts; windows lying
+     * wholly in the tree path are the caller's): LGR-1 last write wins; LGR-2 inserts when the player did not lose
+     * and REMOVES the entry when the player lost and the entry still names that action. */
+    const uint16_t *replies2;
+    uint16_t *replies_final_out;
+    uint16_t *replies2_final_out;
 } orc_batch_desc;
 
 /* One playout.  trace (nullable) receives up to max_trace action ids.  final_state nullable. */

@@ -18,6 +18,8 @@
  *   GLOBAL/MAST write ....... backprop.rs:857-870
  *   Nst ..................... simulate.rs:852-930 (bigram score with a visit-count backoff to the unigram score);
  *                             bigram write backprop.rs:885-899
+ *   Lgr2 (LGRF-2) ........... simulate.rs:1036-1142 (2-ply reply, else the inner Lgr); table write with forgetting
+ *                             backprop.rs:926-966
  *   Lgr (LGR-1) ............. simulate.rs:936-1033 (reply if recorded and legal, else inner); table write
  *                             backprop.rs:908-923 (last write wins, only players whose utility is the maximum)
  *   GRAVE/AMAF occurrences .. backprop.rs:565-640
@@ -178,7 +180,9 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
     const int na = orc_num_actions(game);
     orc_state state = *leaf;
     state.prev_plus1 = 0; /* call context, not game state */
+    state.prev2_plus1 = 0;
     int prev = leaf->prev_plus1 ? (int)leaf->prev_plus1 - 1 : -1; /* playout()'s prev_action */
+    int own_prev[2] = {-1, -1};                                   /* simulate.rs:98: filled only inside this playout */
     uint32_t depth = 0;
     int status, end_type;
     uint16_t available[ORC_MAX_ACTIONS];
@@ -214,11 +218,20 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
                 uint32_t x1;
                 orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
                 greedy = !((uint64_t)x1 < d->eps_threshold);
-            } else if (d->policy == ORC_EPS_LGR) {
+            } else if (d->policy == ORC_EPS_LGR || d->policy == ORC_EPS_LGR2) {
                 uint32_t x1;
                 orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
                 int explore = (uint64_t)x1 < d->eps_threshold;
-                if (!explore && prev >= 0 && d->replies) { /* Lgr::select_move, simulate.rs:1013-1032 */
+                if (!explore && d->policy == ORC_EPS_LGR2 && own_prev[player] >= 0 && prev >= 0 && d->replies2) {
+                    /* Lgr2::select_move, simulate.rs:1113-1141: the reply to (own previous move, opponent's answer) */
+                    const int S = orc_num_slots(game);
+                    uint16_t reply = d->replies2[((size_t)player * S + (size_t)orc_action_slot(game, player, (uint16_t)own_prev[player])) * S +
+                                                 (size_t)orc_action_slot(game, 1 - player, (uint16_t)prev)];
+                    if (reply)
+                        for (int i = 0; i < n; ++i)
+                            if (available[i] == (uint16_t)(reply - 1)) pick = i;
+                }
+                if (pick < 0 && !explore && prev >= 0 && d->replies) { /* Lgr::select_move, simulate.rs:1013-1032 */
                     uint16_t reply = d->replies[(size_t)player * na + action_id(game, (uint16_t)prev)];
                     if (reply)
                         for (int i = 0; i < n; ++i)
@@ -245,6 +258,7 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
         }
         uint16_t action = available[pick];
         prev = action;
+        own_prev[player] = action;
         if (trace && depth < d->max_trace) trace[depth] = action;
         orc_apply(game, &state, action);
         ++depth;
@@ -383,6 +397,51 @@ static void *batch_worker(void *arg) {
     return NULL;
 }
 
+/* backprop.rs:908-966 applied LITERALLY, one trial after the other in global playout order, to the windows of the
+ * chronological action list [leaf.prev2, leaf.prev, playout...] that end in a playout action. */
+static void reply_tables_literal(const orc_batch_desc *d, const orc_state *leaves, uint32_t n_leaves, const orc_action_stat *mast) {
+    const int game = d->game, na = orc_num_actions(game), S = orc_num_slots(game);
+    const uint32_t k = d->playouts_per_leaf;
+    uint16_t *t1 = d->replies_final_out, *t2 = d->replies2_final_out;
+    if (t1) {
+        if (d->replies) memcpy(t1, d->replies, sizeof(uint16_t) * 2 * (size_t)na);
+        else memset(t1, 0, sizeof(uint16_t) * 2 * (size_t)na);
+    }
+    if (t2) {
+        if (d->replies2) memcpy(t2, d->replies2, sizeof(uint16_t) * 2 * (size_t)S * S);
+        else memset(t2, 0, sizeof(uint16_t) * 2 * (size_t)S * S);
+    }
+    orc_batch_desc local = *d;
+    uint32_t cap = d->max_playout_depth ? d->max_playout_depth : 4096;
+    local.max_trace = cap;
+    uint16_t *chron = (uint16_t *)malloc(sizeof(uint16_t) * ((size_t)cap + 2));
+    for (uint64_t g = 0; g < (uint64_t)n_leaves * k; ++g) {
+        const orc_state *leaf = &leaves[g / k];
+        orc_playout_record rec;
+        orc_playout(&local, leaf, d->leaf_id_base + (uint32_t)(g / k), (uint32_t)(g % k), mast, chron + 2, &rec, NULL);
+        /* chron[0] = leaf.prev2 (made by the leaf's mover), chron[1] = leaf.prev (by the other player), then the playout */
+        const int have_prev = leaf->prev_plus1 != 0, have_prev2 = have_prev && leaf->prev2_plus1 != 0;
+        if (have_prev) chron[1] = (uint16_t)(leaf->prev_plus1 - 1);
+        if (have_prev2) chron[0] = (uint16_t)(leaf->prev2_plus1 - 1);
+        const int first = have_prev2 ? 0 : (have_prev ? 1 : 2);
+        const uint32_t depth = rec.depth < cap ? rec.depth : cap;
+        for (uint32_t t = 0; t < depth; ++t) {
+            const int i = (int)t + 2; /* position in chron */
+            const int p = (leaf->turn + (int)t) & 1;
+            const int lost = (rec.outcome == ORC_WINNER_P0 && p == 1) || (rec.outcome == ORC_WINNER_P1 && p == 0);
+            if (t1 && i - 1 >= first && !lost) /* :916-923 */
+                t1[(size_t)p * na + action_id(game, chron[i - 1])] = (uint16_t)(chron[i] + 1);
+            if (t2 && i - 2 >= first) { /* :947-964 */
+                uint16_t *e = &t2[((size_t)p * S + (size_t)orc_action_slot(game, p, chron[i - 2])) * S +
+                                  (size_t)orc_action_slot(game, 1 - p, chron[i - 1])];
+                if (!lost) *e = (uint16_t)(chron[i] + 1);
+                else if (*e == (uint16_t)(chron[i] + 1)) *e = 0;
+            }
+        }
+    }
+    free(chron);
+}
+
 int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t n_leaves, const orc_action_stat *mast,
                       orc_leaf_result *results, orc_action_stat *amaf_out, orc_action_stat *mast_delta_out,
                       uint16_t *trace_out, orc_playout_record *rec_out, orc_state *final_out, int n_threads) {
@@ -392,6 +451,8 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
     /* trace-derived statistics need a bounded trace: only Knightthrough can run unboundedly long */
     if ((amaf_out || mast_delta_out || d->reply_order_out || d->bigram_delta_out) && d->max_playout_depth == 0 && d->game == ORC_KNIGHTTHROUGH) return -3;
     if (d->reply_order_out && !d->reply_action_out) return -4;
+    if ((d->replies_final_out || d->replies2_final_out) && d->max_playout_depth == 0 && d->game == ORC_KNIGHTTHROUGH) return -3;
+    if (d->replies_final_out || d->replies2_final_out) reply_tables_literal(d, leaves, n_leaves, mast);
     const int na = orc_num_actions(d->game);
     const uint64_t total = (uint64_t)n_leaves * d->playouts_per_leaf;
     memset(results, 0, sizeof(orc_leaf_result) * n_leaves);

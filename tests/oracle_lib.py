@@ -18,14 +18,14 @@ LIB_PATH = ORACLE_DIR / "_build" / "liboracle.so"
 
 CONNECT4, BREAKTHROUGH, KNIGHTTHROUGH, OTHELLO, HEX11 = range(5)
 GAME_NAMES = ["connect4", "breakthrough", "knightthrough", "othello", "hex11"]
-UNIFORM, EPS_MAST, DECISIVE_WIN, DECISIVE_WINLOSS, DECISIVE_WINLOSSDRAW, DECISIVE_ANTI, EPS_LGR, DECISIVE_MAST_WIN, DECISIVE_MAST_WINLOSS, EPS_NST = range(10)
+UNIFORM, EPS_MAST, DECISIVE_WIN, DECISIVE_WINLOSS, DECISIVE_WINLOSSDRAW, DECISIVE_ANTI, EPS_LGR, DECISIVE_MAST_WIN, DECISIVE_MAST_WINLOSS, EPS_NST, EPS_LGR2 = range(11)
 NOT_TERMINAL, DRAW, WINNER_P0, WINNER_P1 = range(4)
 END_TERMINAL, END_TURN_LIMIT, END_NO_ACTIONS = range(3)
 OTHELLO_PASS = 64
 MAX_ACTIONS = 256
 
 STATE_DTYPE = np.dtype(
-    [("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("prev", "<u2"), ("pad", "u1", (4,))], align=False
+    [("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("prev", "<u2"), ("prev2", "<u2"), ("pad", "u1", (2,))], align=False
 )
 RESULT_DTYPE = np.dtype([("wins", "<u4", (2,)), ("draws", "<u4"), ("cutoffs", "<u4"), ("sum_depth", "<u8")])
 STAT_DTYPE = np.dtype([("visits", "<u4"), ("score", "<i4")])
@@ -50,6 +50,9 @@ class BatchDesc(C.Structure):
         ("bigram", C.c_void_p),
         ("nst_threshold", C.c_uint32),
         ("bigram_delta_out", C.c_void_p),
+        ("replies2", C.c_void_p),
+        ("replies_final_out", C.c_void_p),
+        ("replies2_final_out", C.c_void_p),
     ]
 
 
@@ -229,6 +232,8 @@ def playout_batch(
     bigram: np.ndarray | None = None,
     nst_threshold=5,
     want_bigram_delta=False,
+    replies2: np.ndarray | None = None,
+    want_final_tables=False,
 ):
     """Runs n_leaves*k playouts.  Returns a dict with results (+ optional amaf / mast_delta / trace /
     records / final)."""
@@ -262,6 +267,15 @@ def playout_batch(
     if want_bigram_delta:
         bigram_delta = np.zeros((2, ns, ns), dtype=STAT_DTYPE)
         d.bigram_delta_out = bigram_delta.ctypes.data
+    replies_final = replies2_final = None
+    if replies2 is not None:
+        replies2 = np.ascontiguousarray(replies2, dtype=np.uint16)
+        assert replies2.shape == (2, ns, ns)
+        d.replies2 = replies2.ctypes.data
+    if want_final_tables:
+        replies_final = np.zeros((2, na), dtype=np.uint16)
+        replies2_final = np.zeros((2, ns, ns), dtype=np.uint16)
+        d.replies_final_out, d.replies2_final_out = replies_final.ctypes.data, replies2_final.ctypes.data
     if mast is not None:
         mast = np.ascontiguousarray(mast, dtype=STAT_DTYPE)
         assert mast.shape == (2, na)
@@ -271,7 +285,8 @@ def playout_batch(
     if rc != 0:
         raise RuntimeError(f"orc_playout_batch failed: {rc}")
     return {"results": results, "amaf": amaf, "mast_delta": delta, "trace": trace, "records": rec, "final": final,
-            "reply_order": reply_order, "reply_action": reply_action, "last_win": last_win, "bigram_delta": bigram_delta}
+            "reply_order": reply_order, "reply_action": reply_action, "last_win": last_win, "bigram_delta": bigram_delta,
+            "replies_final": replies_final, "replies2_final": replies2_final}
 
 
 def search(game, root, *, iterations, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,

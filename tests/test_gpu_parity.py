@@ -343,6 +343,73 @@ def test_context_policies_on_long_tasks(game, policy, monkeypatch):
     assert got.results.tobytes() == ref["results"].tobytes()
 
 
+def _random_replies2(game, leaves, seed, density):
+    """A 2-ply reply table of plausible entries: (own previous action, opponent's answer) -> the action that followed in
+    uniform playouts of `leaves`."""
+    rng = np.random.default_rng(seed)
+    ns = o.num_slots(game)
+    ref = o.playout_batch(game, leaves, 8, seed=seed, want_trace=True, max_trace=MAX_TRACE[game], max_depth=MAX_TRACE[game])
+    table = np.zeros((2, ns, ns), dtype=np.uint16)
+    for li in range(len(leaves)):
+        for j in range(8):
+            d = int(ref["records"][li * 8 + j]["depth"])
+            tr = ref["trace"][li * 8 + j]
+            for t in range(2, d):
+                if rng.random() < density:
+                    p = (int(leaves[li]["turn"]) + t) & 1
+                    table[p, o.action_slot(game, p, int(tr[t - 2])), o.action_slot(game, 1 - p, int(tr[t - 1]))] = int(tr[t]) + 1
+    return table
+
+
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO, o.HEX11])
+@pytest.mark.parametrize("big_grabs", [False, True])
+def test_lgrf2_bit_exact(game, big_grabs, monkeypatch):
+    """EpsilonGreedy<Lgr2<Lgr<Uniform>>> (simulate.rs:1036-1142): per-playout traces, records and final states; and both
+    reply tables after the batch -- the LGR-1 table by last write, the 2-ply table with its forgetting rule
+    (backprop.rs:926-966) through the insert / resolve protocol -- against the oracle's LITERAL trial-by-trial updates."""
+    if big_grabs:
+        monkeypatch.setenv("MR_GRAB_MIN", "512")
+        monkeypatch.setenv("MR_GRAB_MAX", "512")
+    leaves = _leaves(game, n_per=3)
+    prevs = _random_replies(game, leaves, 3, 1.0)
+    by_player = [prevs[p][prevs[p] > 0] for p in range(2)]
+    for i in range(len(leaves)):
+        turn = int(leaves[i]["turn"])
+        other, own = by_player[1 - turn], by_player[turn]
+        leaves["prev"][i] = 0 if i % 4 == 0 else other[i % len(other)]
+        leaves["prev2"][i] = 0 if i % 3 == 0 else own[(5 * i) % len(own)]
+    depth = 200 if game == o.KNIGHTTHROUGH else 0
+    mt = MAX_TRACE[game]
+    for eps, density, k in ((0.1, 0.5, 150 if big_grabs else 40), (0.0, 1.0, 33), (0.1, 0.0, 20)):
+        t1 = _random_replies(game, leaves, 5, density)
+        t2 = _random_replies2(game, leaves, 6, density)
+        ref = o.playout_batch(game, leaves, k, policy=o.EPS_LGR2, eps=eps, seed=79, max_depth=depth, replies=t1, replies2=t2,
+                              want_final_tables=True, want_trace=True, max_trace=mt, want_final=True, threads=o.host_threads())
+        with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyLgr2(eps), seed=79, max_playout_depth=depth) as g:
+            g.set_replies(t1)
+            g.set_replies2(t2)
+            got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, want_trace=True, want_final=True, max_trace=mt)
+            removed = g.resolve_replies2(got.reply2_inserts, t2)
+        name = (o.GAME_NAMES[game], eps, density)
+        assert (got.records["depth"] == ref["records"]["depth"]).all(), name
+        assert (got.records["outcome"] == ref["records"]["outcome"]).all(), name
+        assert (got.trace == ref["trace"]).all(), name
+        assert got.final.tobytes() == ref["final"].tobytes(), name
+        assert got.results.tobytes() == ref["results"].tobytes(), name
+        new1 = np.where(got.reply_updates["order"] > 0, got.reply_updates["action_plus1"], t1)
+        assert (new1 == ref["replies_final"]).all(), name
+        new2 = mb.GpuRollout.apply_replies2(t2, got.reply2_inserts, removed)
+        assert (new2 == ref["replies2_final"]).all(), name
+        lost = [(ref["records"]["outcome"].reshape(len(leaves), k) == (o.WINNER_P1 if p == 0 else o.WINNER_P0)) for p in range(2)]
+        for p in range(2):
+            want = np.array([(np.nonzero(row)[0].max() + 1) if row.any() else 0 for row in lost[p]])
+            assert (got.last_lose[:, p] == want).all(), name
+        if density == 1.0:
+            assert removed.any() and (new2 != t2).any()  # the forgetting rule fired and inserts happened
+            plain = o.playout_batch(game, leaves, k, policy=o.EPS_LGR, eps=eps, seed=79, max_depth=depth, replies=t1)
+            assert plain["results"].tobytes() != ref["results"].tobytes()  # 2-ply replies were actually played
+
+
 def test_reference_shaped_playout_call():
     """SimulateStrategy::playout(state, max_playout_depth, stats, prev_action, rng) -> Trial"""
     game = o.CONNECT4
