@@ -10,6 +10,10 @@
 //   AMAF ............... select/amaf.rs:48-86 over per-edge AMAF rows written by update_amaf, backprop.rs:565-617
 //   LGR table .......... TreeStats.player_replies, last write wins over (trial, ply) order (backprop.rs:908-923): the
 //                        kernel's stamps for the playout part, the tree-path pairs added here
+//   LGRF-2 table ....... TreeStats.player_replies2 with forgetting (backprop.rs:926-966): the kernel's last insert per
+//                        context and its replay pass (mr_reply2_inserts / mr_reply2_resolve), merged here with the
+//                        tree-path windows of every leaf (inserted by its trials the player did not lose, removed by
+//                        the ones it lost)
 //   NST table .......... TreeStats.player_bigram_actions over consecutive (preceding action, action) pairs of tree path
 //                        and playout (backprop.rs:885-899): the kernel's bigram delta plus the tree-path pairs added here
 //   MAST table ......... TreeStats.player_actions, written for playout trace AND tree path (backprop.rs:833-870)
@@ -149,6 +153,7 @@ struct Search {
     Tree t;
     std::vector<mr_action_stat> mast; // [2][NA], TreeStats.player_actions
     std::vector<mr_action_stat> bigram; // [2][S][S], TreeStats.player_bigram_actions over compact action slots (MR_EPS_NST)
+    std::vector<uint16_t> replies2;   // [2][S][S], TreeStats.player_replies2 over action slots: 1 + reply code (MR_EPS_LGR2)
     std::vector<uint16_t> replies;    // [2][NA], TreeStats.player_replies: 1 + reply code by (player, preceding action id)
     int na;
     // TreeStats.grave (search/shared.rs:52): per reference-node state, per player, per action.  The reference keys
@@ -408,6 +413,51 @@ struct Search {
         }
     }
 
+    // backprop.rs:926-966 for one batch.  Per context (p, own previous action, opponent's answer) the table ends up as:
+    // the LAST insert (trials p did not lose), unless a later trial that p lost played the same action in that context;
+    // with no insert, the old entry unless some trial that p lost played it.  `ins` arrives with the playout part's last
+    // inserts; the tree-path windows of leaf b (three consecutive edges) are inserted by its trials up to
+    // last_win[b][p] - 1 and removed by its trials up to last_lose[b][p] - 1, always before that trial's playout windows.
+    int merge_replies2(mr_ctx *ctx, int slot, const std::vector<std::vector<PathEntry>> &paths, uint32_t nb, uint32_t k,
+                       std::vector<mr_reply_update> &ins, const std::vector<uint32_t> &last_win,
+                       const std::vector<uint32_t> &last_lose, std::vector<uint8_t> &removed) {
+        const size_t S = (size_t)mr_num_slots(t.game);
+        auto key_of_window = [&](const std::vector<PathEntry> &path, size_t i, int &p, uint16_t &act) -> size_t {
+            const Node &n2 = t.nodes[path[i - 3].node], &n1 = t.nodes[path[i - 2].node], &n0 = t.nodes[path[i - 1].node];
+            p = n0.player;
+            const uint16_t own = t.action[n2.first + path[i - 2].idx], opp = t.action[n1.first + path[i - 1].idx];
+            act = t.action[n0.first + path[i].idx];
+            return ((size_t)p * S + (size_t)mr_action_slot(t.game, p, own)) * S + (size_t)mr_action_slot(t.game, 1 - p, opp);
+        };
+        for (uint32_t b = 0; b < nb; ++b)
+            for (size_t i = 3; i < paths[b].size(); ++i) {
+                int p;
+                uint16_t act;
+                const size_t key = key_of_window(paths[b], i, p, act);
+                const uint32_t lw = last_win[(size_t)b * 2 + p];
+                if (lw == 0) continue;
+                const uint64_t order = ((((uint64_t)b * k + (lw - 1)) + 1) << 13) | (uint64_t)std::min<size_t>(i, 4095);
+                if (order > ins[key].order) {
+                    ins[key].order = order;
+                    ins[key].action_plus1 = (uint16_t)(act + 1);
+                }
+            }
+        for (size_t i = 0; i < ins.size(); ++i) // contexts without an insert: the current entry is the candidate
+            if (ins[i].order == 0) ins[i].action_plus1 = replies2[i];
+        int rc = mr_reply2_resolve(ctx, slot, ins.data(), removed.data());
+        if (rc != MR_OK) return rc;
+        for (uint32_t b = 0; b < nb; ++b)
+            for (size_t i = 3; i < paths[b].size(); ++i) {
+                int p;
+                uint16_t act;
+                const size_t key = key_of_window(paths[b], i, p, act);
+                const uint32_t ll = last_lose[(size_t)b * 2 + p];
+                if (ll && ins[key].action_plus1 == (uint16_t)(act + 1) && (uint64_t)b * k + ll > (ins[key].order >> 13)) removed[key] = 1;
+            }
+        for (size_t i = 0; i < ins.size(); ++i) replies2[i] = removed[i] ? (uint16_t)0 : ins[i].action_plus1;
+        return MR_OK;
+    }
+
     // k trials of one leaf, aggregated
     void backprop(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k, const mr_action_stat *amaf) {
         const int64_t nonzero = (int64_t)k - r.draws;
@@ -473,7 +523,13 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     s.bigram.assign(n_bigram, mr_action_stat{0, 0});
     std::vector<mr_action_stat> bigram_delta(n_bigram);
     if (uses_mast) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
-    const bool lgr = desc->policy == MR_EPS_LGR;
+    const bool lgr2 = desc->policy == MR_EPS_LGR2;
+    const bool lgr = desc->policy == MR_EPS_LGR || lgr2; // LGRF-2 keeps the LGR-1 table too (its inner strategy)
+    const size_t n_replies2 = lgr2 ? (size_t)2 * mr_num_slots((int)desc->game) * mr_num_slots((int)desc->game) : 0;
+    s.replies2.assign(n_replies2, 0);
+    std::vector<mr_reply_update> reply2_ins(n_replies2);
+    std::vector<uint8_t> reply2_removed(n_replies2);
+    std::vector<uint32_t> last_lose(lgr2 ? (size_t)2 * desc->batch_leaves : 0);
     if (lgr) s.replies.assign((size_t)2 * s.na, 0);
     std::vector<mr_reply_update> reply_upd(lgr ? (size_t)2 * s.na : 0);
     std::vector<uint32_t> last_win(lgr ? (size_t)2 * desc->batch_leaves : 0);
@@ -529,10 +585,18 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
                 const std::vector<PathEntry> &path = bb.paths[b];
                 const Node &parent = s.t.nodes[path[path.size() - 2].node];
                 bb.leaves[b].prev_action_plus1 = (uint16_t)(s.t.action[parent.first + path.back().idx] + 1);
+                if (lgr2 && path.size() > 2) { // and the edge before it (the first two plies' LGRF-2 contexts)
+                    const Node &grand = s.t.nodes[path[path.size() - 3].node];
+                    bb.leaves[b].prev2_action_plus1 = (uint16_t)(s.t.action[grand.first + path[path.size() - 2].idx] + 1);
+                }
             }
         }
         if (lgr) {
             int rc = mr_set_replies(ctx, (int)desc->game, s.replies.data());
+            if (rc != MR_OK) return rc;
+        }
+        if (lgr2) {
+            int rc = mr_set_replies2(ctx, (int)desc->game, s.replies2.data());
             if (rc != MR_OK) return rc;
         }
         if (nst) { // frozen for the batch, like the MAST table
@@ -565,6 +629,12 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         }
         if (nst) {
             rc = mr_bigram_delta(ctx, slot, bigram_delta.data());
+            if (rc != MR_OK) return rc;
+        }
+        if (lgr2) {
+            rc = mr_reply2_inserts(ctx, slot, reply2_ins.data(), last_lose.data());
+            if (rc != MR_OK) return rc;
+            rc = s.merge_replies2(ctx, slot, bb.paths, bb.nb, k, reply2_ins, last_win, last_lose, reply2_removed);
             if (rc != MR_OK) return rc;
         }
         const double t1 = now_s();

@@ -14,6 +14,9 @@
  *   backprop .............. backprop.rs:686-731; NodeStats/ChildArray update node.rs:295-302, 673-681
  *   GLOBAL (MAST) write ... backprop.rs:833-870 (playout trace + tree path)
  *   final action .......... RobustChild select/basic.rs:13-45 through core.rs:138-198
+ *   LGRF-2 table .......... TreeStats.player_replies2, backprop.rs:926-966, applied LITERALLY: trial after trial in global
+ *                           playout order over the whole chronological list (tree path, then playout), inserts for
+ *                           players that did not lose, removals of still-matching entries for players that lost
  *   LGR table ............. TreeStats.player_replies, backprop.rs:908-923 (tree-path pairs and playout pairs of every
  *                           trial a player did not lose, last write wins)
  *   GRAVE ................. select/rave.rs:60-75 (beta), :157-184 (get_ref), :196-230 (score); tables written by
@@ -373,7 +376,16 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     orc_action_stat *bg_delta[2] = {NULL, NULL};
     for (int q = 0; q < 2 && nst; ++q) bg_delta[q] = (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat));
     orc_action_stat *delta = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
-    const int lgr = c->policy == ORC_EPS_LGR;
+    const int lgr2 = c->policy == ORC_EPS_LGR2;
+    const int lgr = c->policy == ORC_EPS_LGR || lgr2; /* LGRF-2 keeps the LGR-1 table too (its inner strategy) */
+    uint16_t *replies2 = lgr2 ? (uint16_t *)calloc(2 * S * S, sizeof(uint16_t)) : NULL;
+    const uint32_t trace_cap = c->max_playout_depth ? c->max_playout_depth : 256;
+    uint16_t *trace2[2] = {NULL, NULL};
+    orc_playout_record *rec2[2] = {NULL, NULL};
+    for (int q = 0; q < 2 && lgr2; ++q) {
+        trace2[q] = (uint16_t *)calloc((size_t)c->batch_leaves * c->playouts_per_leaf * trace_cap, sizeof(uint16_t));
+        rec2[q] = (orc_playout_record *)calloc((size_t)c->batch_leaves * c->playouts_per_leaf, sizeof(orc_playout_record));
+    }
     uint16_t *replies = lgr ? (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t)) : NULL;
     uint64_t *upd_order[2] = {NULL, NULL};
     uint16_t *upd_action[2] = {NULL, NULL};
@@ -434,12 +446,16 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                 if ((lgr || nst) && set_plen[slot][b] > 1) { /* playout()'s prev_action: the last edge of the descent */
                     int L = set_plen[slot][b];
                     leaves[b].prev_plus1 = (uint16_t)(t.action[t.nodes[path[L - 2].node].first + path[L - 1].idx] + 1);
+                    if (lgr2 && L > 2) /* and the edge before it, for the kernel-side contract (unused by this literal mirror) */
+                        leaves[b].prev2_plus1 = (uint16_t)(t.action[t.nodes[path[L - 3].node].first + path[L - 2].idx] + 1);
                 }
             }
             bd.replies = replies; /* frozen for the batch: the playouts run before anything below is merged */
             bd.reply_order_out = lgr ? upd_order[slot] : NULL;
             bd.reply_action_out = lgr ? upd_action[slot] : NULL;
             bd.last_win_out = lgr ? last_win[slot] : NULL;
+            bd.replies2 = replies2; /* frozen for the batch */
+            bd.max_trace = lgr2 ? trace_cap : 0;
             bd.bigram = bigram; /* frozen for the batch, like the MAST table */
             bd.nst_threshold = c->nst_threshold;
             bd.bigram_delta_out = nst ? bg_delta[slot] : NULL;
@@ -447,8 +463,8 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
             bd.leaf_id_base = done;
             if (set_delta[slot]) memset(set_delta[slot], 0, sizeof(orc_action_stat) * 2 * (size_t)na);
             if (set_amaf[slot]) memset(set_amaf[slot], 0, sizeof(orc_action_stat) * (size_t)nb * 2 * na);
-            orc_playout_batch(&bd, leaves, nb, mast, set_res[slot], set_amaf[slot], set_delta[slot], NULL, NULL, NULL,
-                              c->threads > 0 ? c->threads : 1);
+            orc_playout_batch(&bd, leaves, nb, mast, set_res[slot], set_amaf[slot], set_delta[slot], lgr2 ? trace2[slot] : NULL,
+                              lgr2 ? rec2[slot] : NULL, NULL, c->threads > 0 ? c->threads : 1);
             done += nb;
         }
         /* ---- which batch gets applied now ---- */
@@ -481,6 +497,42 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
             }
             for (int i = 0; i < 2 * na; ++i)
                 if (upd_order[apply][i]) replies[i] = upd_action[apply][i];
+        }
+        if (lgr2) { /* backprop.rs:926-966, literally: every trial of the batch in order, tree path then playout */
+            uint16_t *chron = (uint16_t *)malloc(sizeof(uint16_t) * ((size_t)max_path + trace_cap));
+            int *who = (int *)malloc(sizeof(int) * ((size_t)max_path + trace_cap));
+            for (uint32_t b = 0; b < set_nb[apply]; ++b) {
+                const entry_t *path = set_paths[apply] + (size_t)b * max_path;
+                const int L = set_plen[apply][b];
+                int n_tree = 0;
+                for (int i = 1; i < L; ++i) {
+                    const node_t *parent = &t.nodes[path[i - 1].node];
+                    chron[n_tree] = t.action[parent->first + path[i].idx];
+                    who[n_tree++] = parent->player;
+                }
+                const int leaf_turn = t.nodes[path[L - 1].node].player;
+                for (uint32_t j = 0; j < k; ++j) {
+                    const orc_playout_record *rc = &rec2[apply][(size_t)b * k + j];
+                    const uint16_t *tr = trace2[apply] + ((size_t)b * k + j) * trace_cap;
+                    const uint32_t d = rc->depth < trace_cap ? rc->depth : trace_cap;
+                    int n = n_tree;
+                    for (uint32_t q = 0; q < d; ++q) {
+                        chron[n] = tr[q];
+                        who[n++] = (leaf_turn + (int)q) & 1;
+                    }
+                    for (int i = 2; i < n; ++i) {
+                        const int p = who[i];
+                        if (who[i - 2] != p) continue;
+                        const int lost = (rc->outcome == ORC_WINNER_P0 && p == 1) || (rc->outcome == ORC_WINNER_P1 && p == 0);
+                        uint16_t *e = &replies2[((size_t)p * S + (size_t)orc_action_slot(c->game, p, chron[i - 2])) * S +
+                                                (size_t)orc_action_slot(c->game, 1 - p, chron[i - 1])];
+                        if (!lost) *e = (uint16_t)(chron[i] + 1);
+                        else if (*e == (uint16_t)(chron[i] + 1)) *e = 0;
+                    }
+                }
+            }
+            free(chron);
+            free(who);
         }
         for (uint32_t b = 0; b < set_nb[apply]; ++b) {
             const entry_t *path = set_paths[apply] + (size_t)b * max_path;
@@ -636,6 +688,11 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     free(grave.states);
     free(grave.slots);
     free(replies);
+    free(replies2);
+    for (int q = 0; q < 2; ++q) {
+        free(trace2[q]);
+        free(rec2[q]);
+    }
     free(bigram);
     free(bg_delta[0]);
     free(bg_delta[1]);

@@ -163,6 +163,30 @@ def test_nst_search_bit_exact(game, iters, batch, k, thr, pipelined):
     assert mast_plies != plies
 
 
+@pytest.mark.parametrize("game,iters,batch,k,pipelined", [
+    (o.CONNECT4, 2048, 32, 8, False),
+    (o.BREAKTHROUGH, 1024, 16, 16, True),
+    (o.KNIGHTTHROUGH, 256, 8, 16, False),
+    (o.OTHELLO, 512, 1, 1, False),  # the reference's sequential loop: every trial sees every earlier insert and removal
+    (o.HEX11, 512, 16, 8, False),
+])
+def test_lgrf2_search_bit_exact(game, iters, batch, k, pipelined):
+    """The `Ucb1Lgr2` strategy (strategy.rs:143-156) end to end: the 2-ply table with forgetting, merged from the kernel's
+    insert / replay passes and the tree-path windows, against the oracle's literal trial-by-trial table updates."""
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), mb.EpsilonGreedyLgr2(0.1), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      max_playout_depth=200, pipelined=pipelined, seed=37) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_LGR2, eps=0.1, seed=37,
+                                     threads=o.host_threads(), max_depth=200, pipelined=pipelined)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    # the 2-ply table changes the playouts: the same search with LGR-1 rollouts differs
+    _, _, lgr_plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_LGR, eps=0.1, seed=37,
+                               threads=o.host_threads(), max_depth=200, pipelined=pipelined)
+    assert lgr_plies != plies
+
+
 def test_rave_family_search_bit_exact():
     """mcts-tune's `rave` family (family_catalog.rs:483-514): Rave select over the in-kernel AMAF tables with
     DecisiveMove<WinLoss, EpsilonGreedy<Mast>> rollouts -- AMAF tables, MAST delta and decisive scan in one kernel."""
