@@ -98,7 +98,10 @@ enum mr_policy {
      * answer) if legal; else the LGR-1 reply of MR_EPS_LGR; else a uniform pick.  Both tables are frozen for the batch
      * (mr_set_replies, mr_set_replies2); the LGR-1 updates come back through mr_reply_updates, the 2-ply table's
      * inserts and removals ("forgetting") through mr_reply2_inserts / mr_reply2_resolve.  Two draws per ply. */
-    MR_EPS_LGR2 = 10
+    MR_EPS_LGR2 = 10,
+    /* EpsilonGreedy<G, Lgr2<G, Lgr<G, Mast>>> (strategy.rs:158-171 Ucb1Lgr2Mast): as MR_EPS_LGR2 with the greedy MAST pick
+     * (random_best over the unigram scores of mast_in) instead of the uniform pick as the last fallback. */
+    MR_EPS_LGR2_MAST = 11
 };
 
 enum mr_flags {

@@ -13,6 +13,7 @@ from .rollout import (
     EndType,
     EpsilonGreedyLgr,
     EpsilonGreedyLgr2,
+    EpsilonGreedyLgr2Mast,
     EpsilonGreedyMast,
     EpsilonGreedyNst,
     Game,
@@ -31,7 +32,7 @@ from .rollout import (
 )
 
 __all__ = [
-    "BatchResult", "DecisiveMove", "DecisiveMoveMast", "DecisiveMoveWin", "EndType", "EpsilonGreedyLgr", "EpsilonGreedyLgr2", "EpsilonGreedyMast", "EpsilonGreedyNst", "Game", "GpuRollout", "MastTable", "Outcome",
+    "BatchResult", "DecisiveMove", "DecisiveMoveMast", "DecisiveMoveWin", "EndType", "EpsilonGreedyLgr", "EpsilonGreedyLgr2", "EpsilonGreedyLgr2Mast", "EpsilonGreedyMast", "EpsilonGreedyNst", "Game", "GpuRollout", "MastTable", "Outcome",
     "Policy", "Trial", "Uniform", "initial_state", "make_leaf", "num_actions", "LEAF_DTYPE", "RECORD_DTYPE",
     "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load", "GpuSearch", "SearchResult", "apply",
     "generate_actions", "terminal_status",

@@ -430,7 +430,7 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
         if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
     }
     if (policy_is_lgr((int)d->policy)) {
-        if (d->policy == MR_EPS_LGR2 && ctx->replies2_game >= 0 && ctx->replies2_game != (int)d->game)
+        if (policy_is_lgr2((int)d->policy) && ctx->replies2_game >= 0 && ctx->replies2_game != (int)d->game)
             return fail(ctx, MR_ERR_INVALID, "the 2-ply reply table was set for game %d, the batch is game %u", ctx->replies2_game, d->game);
         if (!(d->epsilon >= 0.0 && d->epsilon <= 1.0)) return fail(ctx, MR_ERR_INVALID, "epsilon %f outside [0,1]", d->epsilon);
         if (ctx->replies_game >= 0 && ctx->replies_game != (int)d->game)
@@ -741,7 +741,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
                 kp.lgr_in = sd.lgr_in.d;
             }
         }
-        if (desc->policy == MR_EPS_LGR2) {
+        if (policy_is_lgr2((int)desc->policy)) {
             const size_t S = (size_t)kSlots[desc->game], cnt2 = 2 * S * S;
             CUDA_TRY(ctx, sd.lgr2_stamps.reserve(cnt2, true));
             CUDA_TRY(ctx, sd.lgr2_last_lose.reserve((size_t)2 * n, true));
@@ -786,7 +786,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.amaf.h, sd.amaf.d, sizeof(mr_action_stat) * n * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
         if (desc->flags & MR_WANT_MAST_DELTA)
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.mast_delta.h, sd.mast_delta.d, sizeof(mr_action_stat) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
-        if (desc->policy == MR_EPS_LGR2) {
+        if (policy_is_lgr2((int)desc->policy)) {
             const size_t S = (size_t)kSlots[desc->game];
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_stamps.h, sd.lgr2_stamps.d, sizeof(unsigned long long) * 2 * S * S, cudaMemcpyDeviceToHost, dv.stream));
             CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_last_lose.h, sd.lgr2_last_lose.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, dv.stream));
@@ -845,7 +845,7 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
     }
     ss.kernel_ms = worst_ms;
     ss.lgr_ready = policy_is_lgr((int)d.policy);
-    ss.lgr2_ready = d.policy == MR_EPS_LGR2;
+    ss.lgr2_ready = policy_is_lgr2((int)d.policy);
     ss.nst_ready = d.policy == MR_EPS_NST;
     memset(out, 0, sizeof(mr_leaf_result) * n);
     if (amaf_out && (d.flags & MR_WANT_AMAF)) memset(amaf_out, 0, sizeof(mr_action_stat) * (size_t)n * 2 * na);
@@ -996,7 +996,7 @@ int mr_reply2_resolve(mr_ctx *ctx, int slot, const mr_reply_update *merged, uint
         if (a < 0) return fail(ctx, MR_ERR_INVALID, "mr_reply2_resolve: merged[%zu] names no action of player %d", i, pl);
         target[i] = ((unsigned long long)(merged[i].order >> 13) << 16) | (unsigned long long)(a + 1);
     }
-    kernel_fn fn = pick_kernel(game, MR_EPS_LGR2, 0, 0);
+    kernel_fn fn = pick_kernel(game, (int)d.policy, 0, 0);
     if (!fn) return fail(ctx, MR_ERR_UNSUPPORTED, "MR_EPS_LGR2 is not built for game %d", game);
     memset(removed_out, 0, cnt);
     for (Device &dv : ctx->dev) {

@@ -14,10 +14,16 @@ constexpr int THREADS_PER_BLOCK = WARPS_PER_BLOCK * 32;
 // kernel-side name of DecisiveMove<EpsilonGreedy<Mast>>: the ABI's Win and WinLoss modes share one instantiation
 constexpr int MR_DECISIVE_MAST = MR_DECISIVE_MAST_WIN;
 __host__ __device__ constexpr bool policy_uses_mast(int policy) {
-    return policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN || policy == MR_DECISIVE_MAST_WINLOSS || policy == MR_EPS_NST;
+    return policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN || policy == MR_DECISIVE_MAST_WINLOSS || policy == MR_EPS_NST ||
+           policy == MR_EPS_LGR2_MAST;
 }
 
-__host__ __device__ constexpr bool policy_is_lgr(int policy) { return policy == MR_EPS_LGR || policy == MR_EPS_LGR2; }
+__host__ __device__ constexpr bool policy_is_lgr2(int policy) { return policy == MR_EPS_LGR2 || policy == MR_EPS_LGR2_MAST; }
+__host__ __device__ constexpr bool policy_is_lgr(int policy) { return policy == MR_EPS_LGR || policy_is_lgr2(policy); }
+// the policies whose last resort is the (epsilon-)greedy MAST pick
+__host__ __device__ constexpr bool policy_mast_inner(int policy) {
+    return policy == MR_EPS_MAST || policy == MR_DECISIVE_MAST_WIN || policy == MR_EPS_NST || policy == MR_EPS_LGR2_MAST;
+}
 
 constexpr int MAST_KINDS = 8;  // move kinds per source cell: 3 (Breakthrough) or 8 (Knightthrough)
 constexpr int MAST_BITS = 10;  // <= 513 distinct score values over the <= 512 real actions of a player

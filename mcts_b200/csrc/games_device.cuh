@@ -171,7 +171,7 @@ struct Connect4 {
     __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         const uint64_t moves = (all + BOTTOM) & BOARD; // one bit per open column, ascending column order
         uint64_t bit;
-        constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST;
+        constexpr bool MAST_INNER = policy_mast_inner(POLICY);
         if (POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_MAST) {
             // first legal column (ascending) whose drop wins for the mover (simulate.rs:662-670); a Connect4
             // move cannot lose immediately, a drawing move exists only as the 42nd stone (the single action)
@@ -202,7 +202,7 @@ struct Connect4 {
         } else if (policy_is_lgr(POLICY)) {
             // the recorded reply column, if it is still open (simulate.rs:1022-1026); LGRF-2 tries its 2-ply reply first
             bit = (lgr_reply && lgr_reply <= 7u) ? (moves & (0xFFull << (8u * (lgr_reply - 1u)))) : 0ull;
-            if (POLICY == MR_EPS_LGR2) {
+            if (policy_is_lgr2(POLICY)) {
                 const uint64_t b2 = (lgr_reply2 && lgr_reply2 <= 7u) ? (moves & (0xFFull << (8u * (lgr_reply2 - 1u)))) : 0ull;
                 bit = b2 ? b2 : bit;
             }
@@ -509,7 +509,7 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
     bool have = false, idx_set = false;
     // DecisiveMove<.., inner> first tries the decisive scan and falls through to its inner strategy (simulate.rs:742-760)
     constexpr bool DECISIVE = POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI || POLICY == MR_DECISIVE_MAST;
-    constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST;
+    constexpr bool MAST_INNER = policy_mast_inner(POLICY);
     if (DECISIVE) {
         // DecisiveMove<Win> (simulate.rs:662-687): the first action in list order whose child is a win for the
         // mover.  A Breakthrough move wins iff it lands on the far wall, i.e. iff its source is on the row next
@@ -551,7 +551,7 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
         // reply first (simulate.rs:1124-1131)
         idx = mulhi(x0, n);
 #pragma unroll
-        for (int c = (POLICY == MR_EPS_LGR2 ? 0 : 1); c < 2; ++c) {
+        for (int c = (policy_is_lgr2(POLICY) ? 0 : 1); c < 2; ++c) {
             const uint32_t rep = c == 0 ? lgr_reply2 : lgr_reply;
             if (!have && rep) {
                 const uint32_t s0 = (rep - 1u) >> 8, d0 = (rep - 1u) & 0xffu;
@@ -700,7 +700,7 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
     uint32_t idx = 0, src = 0, kind = 0;
     bool have = false, idx_set = false;
     constexpr bool DECISIVE = POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI || POLICY == MR_DECISIVE_MAST;
-    constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST;
+    constexpr bool MAST_INNER = policy_mast_inner(POLICY);
     if (DECISIVE) {
         // first action in list order that lands on the far wall (simulate.rs:662-687); a jump of two rows wins
         // from the two rows next to it, a jump of one row from the row next to it
@@ -756,7 +756,7 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
     if (policy_is_lgr(POLICY)) {
         idx = mulhi(x0, n);
 #pragma unroll
-        for (int c = (POLICY == MR_EPS_LGR2 ? 0 : 1); c < 2; ++c) {
+        for (int c = (policy_is_lgr2(POLICY) ? 0 : 1); c < 2; ++c) {
             const uint32_t rep = c == 0 ? lgr_reply2 : lgr_reply;
             if (!have && rep) {
                 const uint32_t s0 = (rep - 1u) >> 8, d0 = (rep - 1u) & 0xffu;
@@ -1007,7 +1007,19 @@ struct Othello {
                 }
             }
         }
-        if ((POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST) && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
+        if (policy_is_lgr(POLICY)) {
+            // the recorded reply square, if legal now (a recorded PASS is legal exactly when it is the only action,
+            // handled above); LGRF-2 tries its 2-ply reply first
+            uint32_t rep = (lgr_reply && lgr_reply <= 64u && ((moves >> (lgr_reply - 1u)) & 1ull)) ? lgr_reply : 0u;
+            if (policy_is_lgr2(POLICY) && lgr_reply2 && lgr_reply2 <= 64u && ((moves >> (lgr_reply2 - 1u)) & 1ull)) rep = lgr_reply2;
+            if (rep) {
+                sq = rep - 1u;
+                mv = bit64(sq);
+                fl = flips(mv, P, O);
+                have = true;
+            }
+        }
+        if (policy_mast_inner(POLICY) && !have && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
             // Mast::select_move (simulate.rs:824-848): bit-sliced arg-max of the rank planes over the legal squares,
             // then random_best's visiting order among the maximal ones (as for Breakthrough, with one move kind)
             const uint32_t pl = is_white ? 1u : 0u;
@@ -1036,18 +1048,6 @@ struct Othello {
             mv = bit64(sq);
             fl = flips(mv, P, O);
             have = true;
-        }
-        if (policy_is_lgr(POLICY)) {
-            // the recorded reply square, if legal now (a recorded PASS is legal exactly when it is the only action,
-            // handled above); LGRF-2 tries its 2-ply reply first
-            uint32_t rep = (lgr_reply && lgr_reply <= 64u && ((moves >> (lgr_reply - 1u)) & 1ull)) ? lgr_reply : 0u;
-            if (POLICY == MR_EPS_LGR2 && lgr_reply2 && lgr_reply2 <= 64u && ((moves >> (lgr_reply2 - 1u)) & 1ull)) rep = lgr_reply2;
-            if (rep) {
-                sq = rep - 1u;
-                mv = bit64(sq);
-                fl = flips(mv, P, O);
-                have = true;
-            }
         }
         if (!have) {
             sq = select64(moves, mulhi(x0, n));

@@ -145,7 +145,7 @@ struct HexStep : Hex11 {
     __device__ int step_pl(uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         constexpr int OP = 1 - PL;
         constexpr bool DECISIVE = POLICY == MR_DECISIVE_WIN || POLICY == MR_DECISIVE_ANTI || POLICY == MR_DECISIVE_MAST;
-        constexpr bool MAST_INNER = POLICY == MR_EPS_MAST || POLICY == MR_DECISIVE_MAST || POLICY == MR_EPS_NST;
+        constexpr bool MAST_INNER = policy_mast_inner(POLICY);
         constexpr B128 BM = board_mask();
         const B128 empties = bandn(BM, bor(s[0], s[1]));
         const uint32_t n = n_empty;
@@ -172,7 +172,7 @@ struct HexStep : Hex11 {
             }
         }
         if (policy_is_lgr(POLICY)) { // the recorded reply, still empty (simulate.rs:1022-1026); LGRF-2's 2-ply reply first
-            if (POLICY == MR_EPS_LGR2 && lgr_reply2 && lgr_reply2 <= 121u && has_cell(empties, lgr_reply2 - 1u)) {
+            if (policy_is_lgr2(POLICY) && lgr_reply2 && lgr_reply2 <= 121u && has_cell(empties, lgr_reply2 - 1u)) {
                 cell = lgr_reply2 - 1u;
                 have = true;
             } else if (lgr_reply && lgr_reply <= 121u && has_cell(empties, lgr_reply - 1u)) {

@@ -37,6 +37,7 @@ kernel_fn pick_all_policies(int policy, int v) {
     if (policy == MR_DECISIVE_MAST_WIN) return pick_variant<G, MR_DECISIVE_MAST>(v);
     if (policy == MR_EPS_NST) return pick_variant<G, MR_EPS_NST>(v);
     if (policy == MR_EPS_LGR2) return pick_variant<G, MR_EPS_LGR2>(v);
+    if (policy == MR_EPS_LGR2_MAST) return pick_variant<G, MR_EPS_LGR2_MAST>(v);
     return nullptr;
 }
 

@@ -12,6 +12,7 @@ kernel_fn pick_othello(int policy, int v) {
     if (policy == MR_EPS_LGR) return pick_variant<Othello, MR_EPS_LGR>(v);
     if (policy == MR_EPS_NST) return pick_variant<Othello, MR_EPS_NST>(v);
     if (policy == MR_EPS_LGR2) return pick_variant<Othello, MR_EPS_LGR2>(v);
+    if (policy == MR_EPS_LGR2_MAST) return pick_variant<Othello, MR_EPS_LGR2_MAST>(v);
     return nullptr;
 }
 cudaError_t upload_tables_othello(const uint8_t (*stride)[16], const uint8_t (*inv)[16], const uint32_t *rcp) {

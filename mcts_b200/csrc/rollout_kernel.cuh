@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
     constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
     constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
     constexpr bool MASK_AMAF = WANT_AMAF && G::MASK_AMAF;
-    constexpr bool IS_LGR2 = POLICY == MR_EPS_LGR2; // LGRF-2 runs the LGR-1 machinery too (its inner strategy, both tables written)
-    constexpr bool IS_LGR = POLICY == MR_EPS_LGR || IS_LGR2;
+    constexpr bool IS_LGR2 = policy_is_lgr2(POLICY); // LGRF-2 runs the LGR-1 machinery too (its inner strategy, both tables written)
+    constexpr bool IS_LGR = policy_is_lgr(POLICY);
     constexpr bool IS_NST = POLICY == MR_EPS_NST;
     constexpr bool TRACK_PREV = IS_LGR || IS_NST; // the lane remembers the slot of the preceding action
     constexpr bool PAIR_DRAWS = policy_uses_mast(POLICY) || IS_LGR; // two Philox words per ply

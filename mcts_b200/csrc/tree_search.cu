@@ -518,12 +518,13 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     s.t.game = (int)desc->game;
     s.na = mr_num_actions((int)desc->game);
     const bool nst = desc->policy == MR_EPS_NST;
-    const bool uses_mast = desc->policy == MR_EPS_MAST || desc->policy == MR_DECISIVE_MAST_WIN || desc->policy == MR_DECISIVE_MAST_WINLOSS || nst;
+    const bool uses_mast = desc->policy == MR_EPS_MAST || desc->policy == MR_DECISIVE_MAST_WIN || desc->policy == MR_DECISIVE_MAST_WINLOSS || nst ||
+                           desc->policy == MR_EPS_LGR2_MAST;
     const size_t n_bigram = nst ? (size_t)2 * mr_num_slots((int)desc->game) * mr_num_slots((int)desc->game) : 0;
     s.bigram.assign(n_bigram, mr_action_stat{0, 0});
     std::vector<mr_action_stat> bigram_delta(n_bigram);
     if (uses_mast) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
-    const bool lgr2 = desc->policy == MR_EPS_LGR2;
+    const bool lgr2 = desc->policy == MR_EPS_LGR2 || desc->policy == MR_EPS_LGR2_MAST;
     const bool lgr = desc->policy == MR_EPS_LGR || lgr2; // LGRF-2 keeps the LGR-1 table too (its inner strategy)
     const size_t n_replies2 = lgr2 ? (size_t)2 * mr_num_slots((int)desc->game) * mr_num_slots((int)desc->game) : 0;
     s.replies2.assign(n_replies2, 0);

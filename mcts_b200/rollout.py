@@ -45,6 +45,7 @@ class Policy(IntEnum):
     DECISIVE_MAST_WINLOSS = 8
     EPS_NST = 9
     EPS_LGR2 = 10
+    EPS_LGR2_MAST = 11
 
 
 class Outcome(IntEnum):  # TerminalStatus (mcts/src/game.rs:117-122)
@@ -197,6 +198,17 @@ class EpsilonGreedyLgr2:
 
     def backprop_flags(self) -> int:
         return BACKPROP_LGR2 | BACKPROP_LGR  # Lgr2::backprop_flags (simulate.rs:1101-1103)
+
+
+@dataclass(frozen=True)
+class EpsilonGreedyLgr2Mast:
+    """EpsilonGreedy<G, Lgr2<G, Lgr<G, Mast>>> (strategy.rs:158-171 `Ucb1Lgr2Mast`): LGRF-2 -> LGR-1 -> greedy MAST."""
+
+    epsilon: float = 0.1
+    policy = Policy.EPS_LGR2_MAST
+
+    def backprop_flags(self) -> int:
+        return BACKPROP_LGR2 | BACKPROP_LGR | BACKPROP_GLOBAL
 
 
 @dataclass(frozen=True)
@@ -395,7 +407,7 @@ class GpuRollout:
         ms = C.c_float()
         self.lib.mr_last_kernel_ms(self._h, slot, C.byref(ms))
         upd = last = None
-        if d.policy in (int(Policy.EPS_LGR), int(Policy.EPS_LGR2)):
+        if d.policy in (int(Policy.EPS_LGR), int(Policy.EPS_LGR2), int(Policy.EPS_LGR2_MAST)):
             upd = np.zeros((2, self.na), dtype=REPLY_UPDATE_DTYPE)
             last = np.zeros((n, 2), dtype=np.uint32)
             self._check(self.lib.mr_reply_updates(self._h, slot, ptr(upd), ptr(last)))
@@ -405,7 +417,7 @@ class GpuRollout:
             bigram = np.zeros((2, ns, ns), dtype=STAT_DTYPE)
             self._check(self.lib.mr_bigram_delta(self._h, slot, ptr(bigram)))
         ins2 = lose = None
-        if d.policy == int(Policy.EPS_LGR2):
+        if d.policy in (int(Policy.EPS_LGR2), int(Policy.EPS_LGR2_MAST)):
             ns = self.lib.mr_num_slots(int(self.game))
             ins2 = np.zeros((2, ns, ns), dtype=REPLY_UPDATE_DTYPE)
             lose = np.zeros((n, 2), dtype=np.uint32)

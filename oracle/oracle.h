@@ -34,7 +34,8 @@ enum { ORC_CONNECT4 = 0, ORC_BREAKTHROUGH = 1, ORC_KNIGHTTHROUGH = 2, ORC_OTHELL
 enum { ORC_UNIFORM = 0, ORC_EPS_MAST = 1, ORC_DECISIVE_WIN = 2, ORC_DECISIVE_WINLOSS = 3, ORC_DECISIVE_WINLOSSDRAW = 4, ORC_DECISIVE_ANTI = 5, ORC_EPS_LGR = 6,
        ORC_DECISIVE_MAST_WIN = 7, ORC_DECISIVE_MAST_WINLOSS = 8, /* DecisiveMove<EpsilonGreedy<Mast>>, modes Win / WinLoss */
        ORC_EPS_NST = 9, /* EpsilonGreedy<Nst> */
-       ORC_EPS_LGR2 = 10 /* EpsilonGreedy<Lgr2<Lgr<Uniform>>> */ };
+       ORC_EPS_LGR2 = 10, /* EpsilonGreedy<Lgr2<Lgr<Uniform>>> */
+       ORC_EPS_LGR2_MAST = 11 /* EpsilonGreedy<Lgr2<Lgr<Mast>>> (strategy.rs:158-171 Ucb1Lgr2Mast) */ };
 enum { ORC_NOT_TERMINAL = 0, ORC_DRAW = 1, ORC_WINNER_P0 = 2, ORC_WINNER_P1 = 3 };
 enum { ORC_END_TERMINAL = 0, ORC_END_TURN_LIMIT = 1, ORC_END_NO_ACTIONS = 2 };
 

@@ -218,11 +218,11 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
                 uint32_t x1;
                 orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
                 greedy = !((uint64_t)x1 < d->eps_threshold);
-            } else if (d->policy == ORC_EPS_LGR || d->policy == ORC_EPS_LGR2) {
+            } else if (d->policy == ORC_EPS_LGR || d->policy == ORC_EPS_LGR2 || d->policy == ORC_EPS_LGR2_MAST) {
                 uint32_t x1;
                 orc_draw_pair(d->seed, leaf_id, playout_id, depth, &x0, &x1);
                 int explore = (uint64_t)x1 < d->eps_threshold;
-                if (!explore && d->policy == ORC_EPS_LGR2 && own_prev[player] >= 0 && prev >= 0 && d->replies2) {
+                if (!explore && d->policy != ORC_EPS_LGR && own_prev[player] >= 0 && prev >= 0 && d->replies2) {
                     /* Lgr2::select_move, simulate.rs:1113-1141: the reply to (own previous move, opponent's answer) */
                     const int S = orc_num_slots(game);
                     uint16_t reply = d->replies2[((size_t)player * S + (size_t)orc_action_slot(game, player, (uint16_t)own_prev[player])) * S +
@@ -237,6 +237,8 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
                         for (int i = 0; i < n; ++i)
                             if (available[i] == (uint16_t)(reply - 1)) pick = i;
                 }
+                /* Lgr<G, Mast>: the innermost strategy is the plain greedy Mast (no second epsilon test) */
+                if (d->policy == ORC_EPS_LGR2_MAST && pick < 0 && !explore) greedy = 1;
             } else {
                 x0 = orc_draw(d->seed, leaf_id, playout_id, depth, 0);
             }
@@ -447,7 +449,7 @@ int orc_playout_batch(const orc_batch_desc *d, const orc_state *leaves, uint32_t
                       uint16_t *trace_out, orc_playout_record *rec_out, orc_state *final_out, int n_threads) {
     if (d->game < 0 || d->game >= ORC_NUM_GAMES) return -1;
     if ((d->policy == ORC_EPS_MAST || d->policy == ORC_DECISIVE_MAST_WIN || d->policy == ORC_DECISIVE_MAST_WINLOSS ||
-         d->policy == ORC_EPS_NST) && !mast) return -2;
+         d->policy == ORC_EPS_NST || d->policy == ORC_EPS_LGR2_MAST) && !mast) return -2;
     /* trace-derived statistics need a bounded trace: only Knightthrough can run unboundedly long */
     if ((amaf_out || mast_delta_out || d->reply_order_out || d->bigram_delta_out) && d->max_playout_depth == 0 && d->game == ORC_KNIGHTTHROUGH) return -3;
     if (d->reply_order_out && !d->reply_action_out) return -4;

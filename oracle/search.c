@@ -369,14 +369,14 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     const uint32_t B = c->batch_leaves, k = c->playouts_per_leaf;
     const int na = orc_num_actions(c->game);
     const int nst = c->policy == ORC_EPS_NST;
-    orc_action_stat *mast = (c->policy == ORC_EPS_MAST || c->policy == ORC_DECISIVE_MAST_WIN || c->policy == ORC_DECISIVE_MAST_WINLOSS || nst) ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    orc_action_stat *mast = (c->policy == ORC_EPS_MAST || c->policy == ORC_DECISIVE_MAST_WIN || c->policy == ORC_DECISIVE_MAST_WINLOSS || nst || c->policy == ORC_EPS_LGR2_MAST) ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
     /* TreeStats.player_bigram_actions (shared.rs:60-66) as [2][S][S] over compact action slots, and one delta per buffer set */
     const size_t S = (size_t)orc_num_slots(c->game);
     orc_action_stat *bigram = nst ? (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat)) : NULL;
     orc_action_stat *bg_delta[2] = {NULL, NULL};
     for (int q = 0; q < 2 && nst; ++q) bg_delta[q] = (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat));
     orc_action_stat *delta = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
-    const int lgr2 = c->policy == ORC_EPS_LGR2;
+    const int lgr2 = c->policy == ORC_EPS_LGR2 || c->policy == ORC_EPS_LGR2_MAST;
     const int lgr = c->policy == ORC_EPS_LGR || lgr2; /* LGRF-2 keeps the LGR-1 table too (its inner strategy) */
     uint16_t *replies2 = lgr2 ? (uint16_t *)calloc(2 * S * S, sizeof(uint16_t)) : NULL;
     const uint32_t trace_cap = c->max_playout_depth ? c->max_playout_depth : 256;

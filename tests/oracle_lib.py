@@ -18,7 +18,7 @@ LIB_PATH = ORACLE_DIR / "_build" / "liboracle.so"
 
 CONNECT4, BREAKTHROUGH, KNIGHTTHROUGH, OTHELLO, HEX11 = range(5)
 GAME_NAMES = ["connect4", "breakthrough", "knightthrough", "othello", "hex11"]
-UNIFORM, EPS_MAST, DECISIVE_WIN, DECISIVE_WINLOSS, DECISIVE_WINLOSSDRAW, DECISIVE_ANTI, EPS_LGR, DECISIVE_MAST_WIN, DECISIVE_MAST_WINLOSS, EPS_NST, EPS_LGR2 = range(11)
+UNIFORM, EPS_MAST, DECISIVE_WIN, DECISIVE_WINLOSS, DECISIVE_WINLOSSDRAW, DECISIVE_ANTI, EPS_LGR, DECISIVE_MAST_WIN, DECISIVE_MAST_WINLOSS, EPS_NST, EPS_LGR2, EPS_LGR2_MAST = range(12)
 NOT_TERMINAL, DRAW, WINNER_P0, WINNER_P1 = range(4)
 END_TERMINAL, END_TURN_LIMIT, END_NO_ACTIONS = range(3)
 OTHELLO_PASS = 64

@@ -362,8 +362,8 @@ def _random_replies2(game, leaves, seed, density):
 
 
 @pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO, o.HEX11])
-@pytest.mark.parametrize("big_grabs", [False, True])
-def test_lgrf2_bit_exact(game, big_grabs, monkeypatch):
+@pytest.mark.parametrize("big_grabs,policy", [(False, o.EPS_LGR2), (True, o.EPS_LGR2), (False, o.EPS_LGR2_MAST), (True, o.EPS_LGR2_MAST)])
+def test_lgrf2_bit_exact(game, big_grabs, policy, monkeypatch):
     """EpsilonGreedy<Lgr2<Lgr<Uniform>>> (simulate.rs:1036-1142): per-playout traces, records and final states; and both
     reply tables after the batch -- the LGR-1 table by last write, the 2-ply table with its forgetting rule
     (backprop.rs:926-966) through the insert / resolve protocol -- against the oracle's LITERAL trial-by-trial updates."""
@@ -380,16 +380,23 @@ def test_lgrf2_bit_exact(game, big_grabs, monkeypatch):
         leaves["prev2"][i] = 0 if i % 3 == 0 else own[(5 * i) % len(own)]
     depth = 200 if game == o.KNIGHTTHROUGH else 0
     mt = MAX_TRACE[game]
+    with_mast = policy == o.EPS_LGR2_MAST  # Lgr2<Lgr<Mast>>: the greedy MAST pick as the last fallback (strategy.rs:158-171)
+    mast = _random_mast(game, 8) if with_mast else None
     for eps, density, k in ((0.1, 0.5, 150 if big_grabs else 40), (0.0, 1.0, 33), (0.1, 0.0, 20)):
         t1 = _random_replies(game, leaves, 5, density)
         t2 = _random_replies2(game, leaves, 6, density)
-        ref = o.playout_batch(game, leaves, k, policy=o.EPS_LGR2, eps=eps, seed=79, max_depth=depth, replies=t1, replies2=t2,
-                              want_final_tables=True, want_trace=True, max_trace=mt, want_final=True, threads=o.host_threads())
-        with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyLgr2(eps), seed=79, max_playout_depth=depth) as g:
+        ref = o.playout_batch(game, leaves, k, policy=policy, eps=eps, seed=79, max_depth=depth, replies=t1, replies2=t2, mast=mast,
+                              want_final_tables=True, want_trace=True, max_trace=mt, want_final=True, want_mast_delta=with_mast,
+                              threads=o.host_threads())
+        strat = mb.EpsilonGreedyLgr2Mast(eps) if with_mast else mb.EpsilonGreedyLgr2(eps)
+        with mb.GpuRollout(mb.Game(game), strat, seed=79, max_playout_depth=depth) as g:
             g.set_replies(t1)
             g.set_replies2(t2)
-            got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, want_trace=True, want_final=True, max_trace=mt)
+            got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, stats=mast, want_trace=True, want_final=True, max_trace=mt,
+                                  want_mast_delta=with_mast)
             removed = g.resolve_replies2(got.reply2_inserts, t2)
+        if with_mast:
+            assert got.mast_delta.tobytes() == ref["mast_delta"].tobytes()
         name = (o.GAME_NAMES[game], eps, density)
         assert (got.records["depth"] == ref["records"]["depth"]).all(), name
         assert (got.records["outcome"] == ref["records"]["outcome"]).all(), name
@@ -407,7 +414,7 @@ def test_lgrf2_bit_exact(game, big_grabs, monkeypatch):
         if density == 1.0:
             assert removed.any() and (new2 != t2).any()  # the forgetting rule fired and inserts happened
             plain = o.playout_batch(game, leaves, k, policy=o.EPS_LGR, eps=eps, seed=79, max_depth=depth, replies=t1)
-            assert plain["results"].tobytes() != ref["results"].tobytes()  # 2-ply replies were actually played
+            assert plain["results"].tobytes() != ref["results"].tobytes()  # 2-ply replies (and MAST picks) were actually played
 
 
 def test_reference_shaped_playout_call():

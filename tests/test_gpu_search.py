@@ -187,6 +187,22 @@ def test_lgrf2_search_bit_exact(game, iters, batch, k, pipelined):
     assert lgr_plies != plies
 
 
+def test_lgrf2_mast_search_bit_exact():
+    """`Ucb1Lgr2Mast` (strategy.rs:158-171): LGRF-2 -> LGR-1 -> greedy MAST, three tables maintained by the driver."""
+    game, iters, batch, k = o.BREAKTHROUGH, 1024, 16, 16
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), mb.EpsilonGreedyLgr2Mast(0.1), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      max_playout_depth=200, seed=39) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_LGR2_MAST, eps=0.1, seed=39,
+                                     threads=o.host_threads(), max_depth=200)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    _, _, plain = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_LGR2, eps=0.1, seed=39,
+                           threads=o.host_threads(), max_depth=200)
+    assert plain != plies
+
+
 def test_rave_family_search_bit_exact():
     """mcts-tune's `rave` family (family_catalog.rs:483-514): Rave select over the in-kernel AMAF tables with
     DecisiveMove<WinLoss, EpsilonGreedy<Mast>> rollouts -- AMAF tables, MAST delta and decisive scan in one kernel."""
