@@ -66,3 +66,48 @@ def test_two_gpu_context_is_bit_identical(game, policy):
         assert a.amaf.tobytes() == b.amaf.tobytes()
     ref = o.playout_batch(game, leaves, k, policy=policy, max_depth=depth, seed=77, mast=mast, threads=o.host_threads())
     assert ref["results"].tobytes() == b.results.tobytes()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+@pytest.mark.parametrize("game", [o.BREAKTHROUGH, o.CONNECT4])
+def test_two_gpu_context_table_policies(game):
+    """The table-updating policies merge differently across the ctx's devices: NST bigram deltas are summed, LGR / LGRF-2
+    insert stamps are max-merged, and the LGRF-2 removals come from a replay on every device.  One and two devices must
+    report identical tables."""
+    n, k = 6, 400
+    leaves = o.random_positions(game, 4, 10, n)
+    tr = o.playout_batch(game, leaves, 4, seed=2, want_trace=True, max_trace=4, max_depth=200)["trace"]
+    for i in range(n):  # plausible preceding actions: moves of uniform playouts from the same position colour
+        j = (i + 1) % n
+        if leaves[j]["turn"] != leaves[i]["turn"]:
+            leaves["prev"][i] = int(tr[j * 4][0]) + 1
+    base = o.playout_batch(game, leaves, 64, seed=3, max_depth=200, want_mast_delta=True, want_bigram_delta=True)
+    ns = o.num_slots(game)
+    t2 = np.zeros((2, ns, ns), dtype=np.uint16)
+    outs = []
+    for devices in (1, 2):
+        with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyNst(0.1, 1), seed=11, max_playout_depth=200, devices=devices) as g:
+            g.set_bigrams(base["bigram_delta"])
+            nst = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, stats=base["mast_delta"], want_mast_delta=True)
+        with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyLgr2(0.1), seed=11, max_playout_depth=200, devices=devices) as g:
+            first = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k)  # fills both tables from nothing
+            rem1 = g.resolve_replies2(first.reply2_inserts, t2)
+            tab1 = np.where(first.reply_updates["order"] > 0, first.reply_updates["action_plus1"], 0).astype(np.uint16)
+            tab2 = mb.GpuRollout.apply_replies2(t2, first.reply2_inserts, rem1)
+            g.set_replies(tab1)
+            g.set_replies2(tab2)
+            second = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, leaf_id_base=100)
+            rem2 = g.resolve_replies2(second.reply2_inserts, tab2)
+        outs.append((nst, first, rem1, second, rem2))
+    (a_nst, a1, a_r1, a2, a_r2), (b_nst, b1, b_r1, b2, b_r2) = outs
+    assert a_nst.results.tobytes() == b_nst.results.tobytes() and a_nst.bigram_delta.tobytes() == b_nst.bigram_delta.tobytes()
+    assert a_nst.mast_delta.tobytes() == b_nst.mast_delta.tobytes()
+    for x, y in ((a1, b1), (a2, b2)):
+        assert x.results.tobytes() == y.results.tobytes()
+        assert x.reply_updates.tobytes() == y.reply_updates.tobytes() and (x.last_win == y.last_win).all()
+        assert x.reply2_inserts.tobytes() == y.reply2_inserts.tobytes() and (x.last_lose == y.last_lose).all()
+    assert (a_r1 == b_r1).all() and (a_r2 == b_r2).all()
+    assert a_r2.any() and (a2.reply2_inserts["order"] > 0).any()
+    # and the single-device tables are the oracle's literal ones
+    ref = o.playout_batch(game, leaves, k, policy=o.EPS_LGR2, eps=0.1, seed=11, max_depth=200, want_final_tables=True, threads=o.host_threads())
+    assert (mb.GpuRollout.apply_replies2(t2, a1.reply2_inserts, a_r1) == ref["replies2_final"]).all()
