@@ -589,30 +589,27 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
                 // few maximal actions: the pick is the one with the smallest visiting rank
                 const uint32_t pk = r & 15u;
                 const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
-                uint32_t best_j = 0xffffffffu;
                 // cell by cell (the tied actions are mostly the winning moves of ONE piece): the prefix count of the
-                // cell is shared by its kinds
+                // cell gives the visiting rank of its first kind, every further legal kind is one list position on, i.e.
+                // + inv (mod n) in visiting rank.  The minimum is taken over packed keys (rank << 8 | cell << 2 | kind).
+                uint32_t best = 0xffffffffu;
+                const uint64_t legal_k[3] = {W, F, E};
                 for (uint64_t cells = cand[0] | cand[1] | cand[2]; cells; cells &= cells - 1) {
                     const uint32_t s = (uint32_t)__ffsll((long long)cells) - 1u;
-                    const uint64_t below = (1ull << s) - 1ull;
-                    uint32_t i = __popcll(S & below) + 2u * __popcll(C & below);
-                    const uint32_t legal = (uint32_t)((W >> s) & 1ull) | ((uint32_t)((F >> s) & 1ull) << 1) |
-                                           ((uint32_t)((E >> s) & 1ull) << 2);
-                    const uint32_t tied = (uint32_t)((cand[0] >> s) & 1ull) | ((uint32_t)((cand[1] >> s) & 1ull) << 1) |
-                                          ((uint32_t)((cand[2] >> s) & 1ull) << 2);
+                    const uint64_t bit = 1ull << s, below = bit - 1ull;
+                    const uint32_t i = __popcll(S & below) + 2u * __popcll(C & below);
+                    uint32_t j = visiting_rank(i, i0, n, inv, rcp);
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
-                        if ((tied >> q) & 1u) {
-                            const uint32_t j = visiting_rank(i, i0, n, inv, rcp);
-                            if (j < best_j) {
-                                best_j = j;
-                                src = s;
-                                dir = q;
-                            }
+                        if (cand[q] & bit) best = min(best, (j << 8) | (s << 2) | (uint32_t)q);
+                        if (legal_k[q] & bit) {
+                            j += inv;
+                            j = min(j, j - n); // j - n wraps to a huge value while j < n
                         }
-                        i += (legal >> q) & 1u;
                     }
                 }
+                src = (best >> 2) & 63u;
+                dir = best & 3u;
                 have = true;
             } else {
                 // many maximal actions: walk the visiting order, the first maximal action is close
@@ -801,23 +798,24 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
             } else if (m <= 6) {
                 const uint32_t pk = r & 15u;
                 const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
-                uint32_t best_j = 0xffffffffu;
+                // as for Breakthrough: rank of the cell's first kind, + inv (mod n) per further legal kind, minimum over
+                // packed keys (rank << 9 | cell << 3 | kind)
+                uint32_t best = 0xffffffffu;
                 for (uint64_t cells = any; cells; cells &= cells - 1) {
                     const uint32_t s = (uint32_t)__ffsll((long long)cells) - 1u;
-                    uint32_t i = count_below(s);
+                    const uint64_t bit = 1ull << s;
+                    uint32_t j = visiting_rank(count_below(s), i0, n, inv, rcp);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        if ((cand[q] >> s) & 1ull) {
-                            const uint32_t j = visiting_rank(i, i0, n, inv, rcp);
-                            if (j < best_j) {
-                                best_j = j;
-                                src = s;
-                                kind = q;
-                            }
+                        if (cand[q] & bit) best = min(best, (j << 9) | (s << 3) | (uint32_t)q);
+                        if (M[q] & bit) {
+                            j += inv;
+                            j = min(j, j - n);
                         }
-                        i += (uint32_t)((M[q] >> s) & 1ull);
                     }
                 }
+                src = (best >> 3) & 63u;
+                kind = best & 7u;
                 have = true;
             } else {
                 const uint32_t stride = MR_STRIDE[n][r & 15u];
