@@ -401,6 +401,37 @@ def run_gpu(args):
         except Exception as e:
             per_game["connect4_uct_100k_per_move"] = {"error": str(e)}
 
+    # BASELINE.json config 4: Breakthrough 8x8, 2^24 playouts for ONE move, the search root-sharded over the ranks (one
+    # searcher per GPU with its own seed and tree, search/parallel.rs:56-115), root-child totals merged with one NCCL
+    # all-reduce.  Strong scaling: every rank runs 2^24 / N playouts.
+    if not args.headline_only:
+        try:
+            total, bl, kk = 1 << 24, 1024, 1024
+            iters = max(1, total // (world * kk))
+            root = mb.initial_state(mb.Game.BREAKTHROUGH)
+            with mb.GpuSearch(mb.Game.BREAKTHROUGH, mb.EpsilonGreedyMast(0.1), max_iterations=iters, batch_leaves=bl,
+                              num_rollouts_per_leaf=kk, max_playout_depth=200, pipelined=True, seed=1000 + rank, devices=[local]) as srch:
+                mb.choose_action_root_parallel(srch, root, device=dev, draw=3)
+                barrier()
+                t0 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    action, mv, _ms, lres = mb.choose_action_root_parallel(srch, root, device=dev, draw=3)
+                barrier()
+                dt = (time.perf_counter() - t0) / reps
+            if dist is not None:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            per_game["breakthrough_root_parallel_2p24_per_move"] = {
+                "playouts_per_move": world * iters * kk, "seconds_per_move": dt, "playouts_per_s": world * iters * kk / dt,
+                "merged_root_child_visits": int(mv.sum()), "best_action": int(action),
+                "searchers": world, "iterations_per_searcher": iters, "batch_leaves": bl, "playouts_per_leaf": kk,
+                "scaling": "strong", "merge": "one all-reduce of the root-child (visits, score) totals per move",
+            }
+        except Exception as e:
+            per_game["breakthrough_root_parallel_2p24_per_move"] = {"error": str(e)}
+
     peak_ops, clock_mhz = head["int_peak"]
     achieved = head["plies_per_s"] / world * ops_per_ply(HEADLINE)
     line = {

@@ -70,6 +70,25 @@ class GpuSearch:
                             st.max_tree_depth, st.seconds_select, st.seconds_gpu, st.seconds_backprop)
 
 
+def choose_action_root_parallel(search: GpuSearch, state: np.ndarray, *, device=None, group=None, draw: int = 0):
+    """`choose_action_root_parallel` (search/parallel.rs:56-115) with one searcher per RANK instead of per thread: every
+    rank runs its own tree on its own GPU (the caller gives each rank its own `seed`, as the reference draws one per
+    worker), the per-root-child `(visits, score[2])` totals are summed over ranks with ONE all-reduce (NCCL over NVLink on
+    GPUs, gloo in the CPU tests), and every rank picks the child with the most merged visits by `random_best`
+    (`draw` in [0, 16 n) is the shared tie-break draw).  Returns (action, merged visits, merged scores, local result).
+
+    Children are reported in root action-list order on every rank (generate_actions is deterministic), so the merge is
+    an element-wise sum; unexplored children carry zero visits, like the reference's `is_explored` filter."""
+    from . import root_merge
+
+    local = search.choose_action(state)
+    visits, scores = root_merge.merge_root_stats(local.children["visits"], local.children["score"], device=device, group=group)
+    if len(visits) == 0:
+        return local.best_action, visits, scores, local
+    idx = root_merge.final_action_index(visits, int(draw) % (16 * len(visits)))
+    return int(local.children["action"][idx]), visits, scores, local
+
+
 def flat_monte_carlo(rollout: GpuRollout, state: np.ndarray, samples_per_move: int = 100, max_rollout_depth: int = 100,
                      ucb1: float | None = None, r: int = 0):
     """FlatMonteCarloStrategy::choose_action (mcts/src/strategies/flat_mc.rs:58-151) as ONE GPU batch: every root

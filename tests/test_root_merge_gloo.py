@@ -84,3 +84,56 @@ def test_final_action_matches_random_best_semantics():
     # no process group: merge is the identity
     mv, ms = root_merge.merge_root_stats(v, np.zeros((5, 2)))
     assert (mv == v).all()
+
+
+class _StubSearch:
+    """A searcher whose root totals are a fixed function of its rank (the merge logic needs no GPU)."""
+
+    def __init__(self, rank):
+        self.rank = rank
+
+    def choose_action(self, state):
+        from types import SimpleNamespace
+
+        from mcts_b200._lib import ROOT_CHILD_DTYPE
+
+        rng = np.random.default_rng(7 + self.rank)
+        ch = np.zeros(7, dtype=ROOT_CHILD_DTYPE)
+        ch["action"] = np.arange(7)
+        ch["visits"] = rng.integers(0, 500, size=7)
+        ch["score"] = rng.integers(-300, 300, size=(7, 2))
+        return SimpleNamespace(best_action=int(ch["action"][ch["visits"].argmax()]), children=ch)
+
+
+def _rp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mcts_b200.search import choose_action_root_parallel
+
+        action, visits, scores, local = choose_action_root_parallel(_StubSearch(rank), None, draw=37)
+        q.put((rank, action, visits, scores, local.children))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_root_parallel_choice():
+    """choose_action_root_parallel (search/parallel.rs:56-115 with one searcher per rank): every rank ends with the same
+    merged totals and the same action, the child with the most MERGED visits."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    v_sum = outs[0][4]["visits"].astype(np.int64) + outs[1][4]["visits"]
+    s_sum = outs[0][4]["score"] + outs[1][4]["score"]
+    for o in outs:
+        assert (o[2] == v_sum).all() and (o[3] == s_sum).all()
+        assert o[1] == int(v_sum.argmax())  # the maximum is unique here, so the tie-break draw does not matter
+    assert outs[0][1] == outs[1][1]
