@@ -76,6 +76,8 @@ struct Connect4 {
     uint64_t cur, all;
     uint32_t n_open;
     uint32_t rt_parity;
+    uint32_t turn_u; // the leaf's mover, as a WARP-UNIFORM value (kernel: a REDUX result), so that everything derived from
+                     // the mover's colour -- table indices, loop bounds, constant-bank addresses -- runs on the uniform datapath
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + compact code of the recorded reply for this ply, 0 = none / exploring
     uint32_t lgr_reply2; // MR_EPS_LGR2: the 2-ply table's reply, tried before lgr_reply
     // MR_EPS_NST: this ply's context (mover, preceding action) rank planes / per-column ranks, set by the kernel
@@ -212,7 +214,7 @@ struct Connect4 {
         if (MAST_INNER && bit == 0 && !(p.eps_enable && x1 <= p.eps_thr_m1)) {
             // Mast::select_move (simulate.rs:824-848) = random_best over the open columns: the first strict maximum in
             // visiting order, i.e. the largest (rank, -visiting rank) key.  At most 7 actions: every column is scored.
-            const uint32_t pl = (sh.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
+            const uint32_t pl = (turn_u ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
             const uint32_t r = mulhi(x0, 16u * n_open);
             const uint32_t i0 = r >> 4, inv = MR_STRIDE_INV[n_open][r & 15u], rcp = MR_RCP32[n_open];
             uint32_t best_key = 0, i = 0;
@@ -252,7 +254,7 @@ struct Connect4 {
         const uint64_t me = add_disjoint(cur, bit);
         n_open -= (bit & TOPROW) ? 1u : 0u;
         cur = sub_subset(all, me); // the opponent moves next
-        const uint32_t mover = (sh.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
+        const uint32_t mover = (turn_u ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
         if (four(me)) return ST_MOVED | (mover ? ST_WIN_P1 : ST_WIN_P0);
         if (n_open == 0) return ST_MOVED | ST_DRAW;
         return ST_MOVED;
@@ -298,6 +300,7 @@ struct ThroughBase {
 
     uint64_t black, white;
     uint32_t rt_parity;
+    uint32_t turn_u; // the leaf's mover as a warp-uniform value (see Connect4::turn_u)
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + compact code (src << 8 | dst) of the recorded reply, 0 = none / exploring
     uint32_t lgr_reply2; // MR_EPS_LGR2: the 2-ply table's reply, tried before lgr_reply
     // MR_EPS_NST: this ply's context (mover, preceding action) rank planes / per-column ranks, set by the kernel
@@ -498,7 +501,7 @@ __device__ __forceinline__ void mast_argmax(uint64_t cand[KINDS], const uint64_t
 template <int POLICY, int PARITY>
 __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p,
                                   uint32_t &action, uint32_t &slot) {
-    const bool is_white = ((sh.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u) != 0;
+    const bool is_white = ((turn_u ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u) != 0;
     const uint64_t own = is_white ? white : black, opp = is_white ? black : white;
     uint64_t W, F, E;
     masks(is_white, own, opp, W, F, E);
@@ -644,7 +647,7 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
 template <int POLICY, int PARITY>
 __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p,
                                    uint32_t &action, uint32_t &slot) {
-    const bool is_white = ((sh.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u) != 0;
+    const bool is_white = ((turn_u ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u) != 0;
     const uint64_t own = is_white ? white : black;
     uint64_t M[8];
     masks(own, M);
@@ -874,6 +877,7 @@ struct Othello {
     uint64_t black, white;
     uint32_t last_pass;
     uint32_t rt_parity; // parity of the current ply inside its window (PARITY == 2 call sites)
+    uint32_t turn_u; // the leaf's mover as a warp-uniform value (see Connect4::turn_u)
     uint32_t lgr_reply; // MR_EPS_LGR: 1 + square of the recorded reply (65 = PASS), 0 = none / exploring
     uint32_t lgr_reply2; // MR_EPS_LGR2: the 2-ply table's reply, tried before lgr_reply
     const uint64_t (*nst_planes)[MAST_BITS]; // MR_EPS_NST: this ply's context rank planes, set by the kernel
@@ -959,7 +963,7 @@ struct Othello {
 
     template <int POLICY, int PARITY>
     __device__ int step(const Shared &s, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
-        const bool is_white = ((s.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u) != 0;
+        const bool is_white = ((turn_u ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u) != 0;
         const uint64_t P = is_white ? white : black, O = is_white ? black : white;
         const uint64_t moves = legal_moves(P, O);
         if (moves == 0) {

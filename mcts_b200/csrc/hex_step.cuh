@@ -36,6 +36,7 @@ struct HexStep : Hex11 {
     B128 s[2], e1[2], e2[2]; // indexed by compile-time player only (registers)
     uint32_t n_empty;
     uint32_t rt_parity;
+    uint32_t turn_u; // the leaf's mover as a warp-uniform value (see Connect4::turn_u)
     uint32_t lgr_reply;
     uint32_t lgr_reply2; // MR_EPS_LGR2: the 2-ply table's reply, tried before lgr_reply
     const uint64_t (*nst_planes)[MAST_BITS]; // MR_EPS_NST: this ply's context rank planes, set by the kernel
@@ -254,7 +255,7 @@ struct HexStep : Hex11 {
     __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot) {
         // the mover is warp-uniform (one leaf per task, lanes in ply lock-step): the branch never diverges, and each
         // side's code indexes the per-player register sets with a compile-time constant
-        const uint32_t pl = (sh.turn ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
+        const uint32_t pl = (turn_u ^ (PARITY == 2 ? rt_parity : (uint32_t)PARITY)) & 1u;
         if (pl) return step_pl<POLICY, 1>(x0, x1, p, action, slot);
         return step_pl<POLICY, 0>(x0, x1, p, action, slot);
     }

@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
             uint32_t prev_slot1 = leaf_prev_slot1; // LGR: 1 + slot of the preceding action
             uint32_t own_slot1 = 0;                // LGRF-2: 1 + slot of the mover's own previous action in THIS playout
             st.reset(sh);
+            // the same value in every lane, but produced by a warp reduction: the compiler can then keep it (and the
+            // mover's colour, MAST table index, rank-bit loop and plane addresses derived from it) in uniform registers
+            st.turn_u = __reduce_or_sync(FULL_MASK, leaf_turn & 1u);
 
             for (;;) {
                 uint32_t r[4];
