@@ -2,8 +2,8 @@
  * oracle/oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * CPU restatement (plain C) of the simulation (playout) phase of thomasmarsh/mcts:
- * the five bitboard games, the playout loop and its three in-scope policies, and the
- * statistics a playout feeds into backprop.  It exists to CHECK the CUDA path
+ * the five bitboard games, the playout loop, every simulation policy of strategy.rs but
+ * MetaMcts, the statistics a playout feeds into backprop, and the MCTS loop around them.  It exists to CHECK the CUDA path
  * (tests/, __graft_entry__.smoke()) and to be TIMED as the CPU baseline
  * (bench.py cpu_baseline / --impl reference).  The product (mcts_b200/, include/)
  * never links, imports or calls anything in this directory.
