@@ -283,9 +283,13 @@ def run_gpu(args):
         want_delta = w["policy"] == 1
         d_leaves = torch.from_numpy(leaves.view(np.uint8).reshape(-1).copy()).to(dev)
         d_results = torch.zeros(n_leaves * 24, dtype=torch.uint8, device=dev)
-        d_delta = torch.zeros(2 * na * 2, dtype=torch.int32, device=dev) if want_delta else None
+        # what the ranks exchange once per step lives in ONE buffer: the MAST delta followed by the per-root-child
+        # (visits, score[2]) totals -- one all-reduce instead of two (latency-bound: <= 64 KB)
+        n_delta = 2 * na * 2 if want_delta else 0
+        d_merge = torch.zeros(n_delta + 48 * 3, dtype=torch.int32, device=dev)
+        d_delta = d_merge[:n_delta] if want_delta else None
+        d_root = d_merge[n_delta:]
         d_amaf = torch.zeros(n_leaves * 2 * na * 2, dtype=torch.int32, device=dev) if w["amaf"] else None
-        d_root = torch.zeros(48 * 3, dtype=torch.int32, device=dev)
         launches0 = g.kernel_launches()
 
         def step(i):
@@ -302,9 +306,7 @@ def run_gpu(args):
             )
             if dist is not None:
                 # the path's one exchange step: merge MAST delta + per-root-child stats over NVLink (NCCL)
-                if d_delta is not None:
-                    root_merge.merge_sum_(d_delta)
-                root_merge.merge_sum_(d_root)
+                root_merge.merge_sum_(d_merge)
 
         if sampler:
             sampler.start()  # before the warm-up: the timed region of this path is tens of milliseconds
@@ -406,7 +408,7 @@ def run_gpu(args):
     # all-reduce.  Strong scaling: every rank runs 2^24 / N playouts.
     if not args.headline_only:
         try:
-            total, bl, kk = 1 << 24, 1024, 1024
+            total, bl, kk = 1 << 24, 256, 1024  # 2^14 / N leaf selections per searcher, 64 / N batches
             iters = max(1, total // (world * kk))
             root = mb.initial_state(mb.Game.BREAKTHROUGH)
             with mb.GpuSearch(mb.Game.BREAKTHROUGH, mb.EpsilonGreedyMast(0.1), max_iterations=iters, batch_leaves=bl,

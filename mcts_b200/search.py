@@ -80,13 +80,24 @@ def choose_action_root_parallel(search: GpuSearch, state: np.ndarray, *, device=
     Children are reported in root action-list order on every rank (generate_actions is deterministic), so the merge is
     an element-wise sum; unexplored children carry zero visits, like the reference's `is_explored` filter."""
     from . import root_merge
+    from .rollout import generate_actions
 
     local = search.choose_action(state)
-    visits, scores = root_merge.merge_root_stats(local.children["visits"], local.children["score"], device=device, group=group)
-    if len(visits) == 0:
+    # always reduce one slot per legal root action, so that every rank enters the same collective even when its own root
+    # was never expanded (no children reported)
+    actions = local.children["action"] if len(local.children) else np.array(generate_actions(search.rollout.game, state), dtype=np.uint16)
+    visits = np.zeros(len(actions), dtype=np.int64)
+    scores = np.zeros((len(actions), 2), dtype=np.int64)
+    if len(local.children):
+        visits[:] = local.children["visits"]
+        scores[:] = local.children["score"]
+    if len(actions) == 0:
+        return local.best_action, visits, scores, local
+    visits, scores = root_merge.merge_root_stats(visits, scores, device=device, group=group)
+    if visits.sum() == 0:  # no rank expanded its root: nothing to choose from
         return local.best_action, visits, scores, local
     idx = root_merge.final_action_index(visits, int(draw) % (16 * len(visits)))
-    return int(local.children["action"][idx]), visits, scores, local
+    return int(actions[idx]), visits, scores, local
 
 
 def flat_monte_carlo(rollout: GpuRollout, state: np.ndarray, samples_per_move: int = 100, max_rollout_depth: int = 100,

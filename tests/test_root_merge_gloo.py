@@ -90,7 +90,10 @@ class _StubSearch:
     """A searcher whose root totals are a fixed function of its rank (the merge logic needs no GPU)."""
 
     def __init__(self, rank):
+        from types import SimpleNamespace
+
         self.rank = rank
+        self.rollout = SimpleNamespace(game=0)
 
     def choose_action(self, state):
         from types import SimpleNamespace
