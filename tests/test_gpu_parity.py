@@ -499,6 +499,53 @@ def test_headline_workload_at_full_size():
         assert ref["results"][0].tobytes() == res[i].tobytes(), i
 
 
+@pytest.mark.parametrize("policy", [o.EPS_LGR, o.EPS_NST, o.EPS_LGR2])
+def test_table_policies_at_large_size(policy):
+    """The context policies on a batch large enough for 512-playout grabs, lane refills and table flushes (1024 leaves x
+    1024 playouts): conservation properties over the whole batch and bit-exact replay of sampled leaves by the oracle
+    (a leaf's playouts depend only on the frozen tables, so the oracle can replay one leaf with its leaf id)."""
+    game, n, k, depth = o.BREAKTHROUGH, 1024, 1024, 200
+    leaves = o.random_positions(game, 2, 20, n)
+    tr = o.playout_batch(game, leaves[:64], 2, seed=4, want_trace=True, max_trace=2, max_depth=depth)
+    first = {}  # first move seen for each colour: a plausible preceding action for leaves of the other colour
+    for i in range(64):
+        first.setdefault(int(leaves[i]["turn"]), int(tr["trace"][2 * i][0]))
+    for i in range(n):
+        if i % 5 and (1 - int(leaves[i]["turn"])) in first:
+            leaves["prev"][i] = first[1 - int(leaves[i]["turn"])] + 1
+    base = o.playout_batch(game, leaves[:128], 64, seed=999, max_depth=depth, want_mast_delta=True, want_bigram_delta=True,
+                           threads=o.host_threads())
+    t1 = _random_replies(game, leaves[:32], 5, 1.0)
+    t2 = _random_replies2(game, leaves[:32], 6, 1.0)
+    strat = {o.EPS_LGR: mb.EpsilonGreedyLgr(0.1), o.EPS_NST: mb.EpsilonGreedyNst(0.1, 3), o.EPS_LGR2: mb.EpsilonGreedyLgr2(0.1)}[policy]
+    with mb.GpuRollout(mb.Game(game), strat, seed=4242, max_playout_depth=depth) as g:
+        g.set_replies(t1)
+        g.set_replies2(t2)
+        g.set_bigrams(base["bigram_delta"])
+        r = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, stats=base["mast_delta"] if policy == o.EPS_NST else None,
+                            want_mast_delta=policy == o.EPS_NST)
+        removed = g.resolve_replies2(r.reply2_inserts, t2) if policy == o.EPS_LGR2 else None
+    res = r.results
+    assert ((res["wins"][:, 0].astype(np.int64) + res["wins"][:, 1] + res["draws"]) == k).all()
+    plies = int(res["sum_depth"].sum())
+    if policy == o.EPS_NST:
+        assert int(r.mast_delta["visits"].sum()) == plies
+        # every ply with a predecessor is one bigram occurrence: all plies but the first ply of playouts whose leaf has none
+        # (Breakthrough leaves after 20 plies are not terminal: every playout has a first ply)
+        first_plies_without_context = int((leaves["prev"] == 0).sum()) * k
+        assert int(r.bigram_delta["visits"].sum()) == plies - first_plies_without_context
+    else:
+        assert (r.reply_updates["order"] > 0).any() and (r.last_win > 0).all()
+    if policy == o.EPS_LGR2:
+        assert (r.reply2_inserts["order"] > 0).any() and removed.any() and (r.last_lose > 0).any()
+    kw = {o.EPS_LGR: dict(replies=t1), o.EPS_NST: dict(mast=base["mast_delta"], bigram=base["bigram_delta"], nst_threshold=3),
+          o.EPS_LGR2: dict(replies=t1, replies2=t2)}[policy]
+    for i in np.random.default_rng(2).choice(n, size=3, replace=False):
+        ref = o.playout_batch(game, leaves[i : i + 1], k, policy=policy, eps=0.1, max_depth=depth, seed=4242, leaf_id_base=int(i),
+                              threads=o.host_threads(), **kw)
+        assert ref["results"][0].tobytes() == res[i].tobytes(), i
+
+
 def test_win_rate_agrees_with_independent_cpu_rollouts():
     """Root-child win rates from GPU playouts vs CPU oracle playouts drawn with a DIFFERENT seed agree
     within a Wilson 99.9% interval (mcts-bench/src/tournament.rs:98-111)."""
