@@ -42,6 +42,17 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
     __shared__ HexLeafShared s_hex[WARPS_PER_BLOCK];
     __shared__ uint8_t s_order[WARPS_PER_BLOCK][121][32]; // cell played at [ply][lane]
     __shared__ uint32_t s_amaf[WARPS_PER_BLOCK][WANT_AMAF ? 2 * H::NSLOTS : 1];
+    // s_nth[v][r] = position of the r-th set bit of the byte v: the last step of the fill phase's rank -> cell select
+    __shared__ uint8_t s_nth[256][8];
+    for (uint32_t v = threadIdx.x; v < 256u; v += THREADS_PER_BLOCK) {
+        uint32_t r = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < 8u; ++b) {
+            s_nth[v][b] = 0;
+            if ((v >> b) & 1u) s_nth[v][r++] = (uint8_t)b;
+        }
+    }
+    __syncthreads();
 
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
@@ -164,23 +175,24 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                             const uint32_t e2 = ~(full[0].w[2] | full[1].w[2]);
                             const uint32_t e3 = ~(full[0].w[3] | full[1].w[3]) & 0x01ffffffu;
                             const uint32_t c0 = __popc(e0), c1 = __popc(e1), c2 = __popc(e2);
-                            uint32_t wsel = 0, word = e0;
-                            if (idx >= c0) {
-                                idx -= c0;
-                                wsel = 1;
-                                word = e1;
-                                if (idx >= c1) {
-                                    idx -= c1;
-                                    wsel = 2;
-                                    word = e2;
-                                    if (idx >= c2) {
-                                        idx -= c2;
-                                        wsel = 3;
-                                        word = e3;
-                                    }
-                                }
-                            }
-                            const uint32_t cell = wsel * 32u + select32(word, idx);
+                            // the idx-th empty cell (ascending), branch-free: three compare steps (predicated IMADs) pick
+                            // the word, SWAR prefix popcounts the byte, a table the bit.  (Measured against the 5-step
+                            // binary search it replaces: 8 % fewer instructions, 14.05 -> 13.82 ms; prefix POPCs of the
+                            // word's low 1, 2, 3 bytes instead of the SWAR counts: 13.92 ms.)
+                            uint32_t wbase = 0, word = e0, sub = 0;
+                            pick_ge(idx, c0, sub, wbase, 32u, word, e1);
+                            pick_ge(idx, c0 + c1, sub, wbase, 64u, word, e2);
+                            pick_ge(idx, c0 + c1 + c2, sub, wbase, 96u, word, e3);
+                            idx -= sub;
+                            uint32_t bc = word - ((word >> 1) & 0x55555555u);
+                            bc = (bc & 0x33333333u) + ((bc >> 2) & 0x33333333u);
+                            bc = (bc + (bc >> 4)) & 0x0f0f0f0fu;            // set bits per byte
+                            const uint32_t incl = bc * 0x01010101u;          // byte j: set bits of bytes 0..j
+                            // bit 7 of byte j is set iff incl_j > idx (incl_j + 127 - idx >= 128; no carry between bytes)
+                            const uint32_t hit = (incl + (0x7fu - idx) * 0x01010101u) & 0x80808080u;
+                            const uint32_t sh8 = ((uint32_t)__ffs((int)hit) - 1u) & ~7u; // 8 * (index of the byte)
+                            const uint32_t below = ((incl << 8) >> sh8) & 0xffu;         // set bits in the bytes before it
+                            const uint32_t cell = wbase + sh8 + s_nth[(word >> sh8) & 0xffu][idx - below];
                             const uint32_t mover = (leaf_turn + ply) & 1u; // warp-uniform
 #pragma unroll
                             for (int q = 0; q < 4; ++q) { // word q receives the bit iff 0 <= cell - 32 q < 32: a clamped shift
