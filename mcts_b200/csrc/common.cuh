@@ -172,22 +172,6 @@ __device__ __forceinline__ void select_step(uint32_t &idx, uint32_t &pos, uint32
     }
 #endif
 }
-// if (idx >= thr) { sub = thr; base = nbase; word = nword; }   -- one level of a rank -> position descent whose three
-// updates are predicated IMADs on the FMA pipe (one ISETP on the ALU pipe)
-__device__ __forceinline__ void pick_ge(uint32_t idx, uint32_t thr, uint32_t &sub, uint32_t &base, uint32_t nbase, uint32_t &word,
-                                        uint32_t nword) {
-#if MR_FMA_BALANCE
-    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %3, %4;\n\t@p mad.lo.u32 %0, %4, %7, 0;\n\t@p mad.lo.u32 %1, %5, %7, 0;\n\t@p mad.lo.u32 %2, %6, %7, 0;\n\t}"
-        : "+r"(sub), "+r"(base), "+r"(word)
-        : "r"(idx), "r"(thr), "r"(nbase), "r"(nword), "r"(MR_ONE));
-#else
-    if (idx >= thr) {
-        sub = thr;
-        base = nbase;
-        word = nword;
-    }
-#endif
-}
 // v << s with PTX semantics: a shift amount >= 32 (including "negative" amounts as unsigned) gives 0, so word q of a
 // multi-word board receives bit `cell` as shl_clamp(1, cell - 32 q) with no compare / select
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s) {
