@@ -403,6 +403,32 @@ def run_gpu(args):
         except Exception as e:
             per_game["connect4_uct_100k_per_move"] = {"error": str(e)}
 
+    # BASELINE.json configs 2-3 through the search loop (one move each, this rank's GPU): Hex 11x11 GRAVE over the
+    # in-kernel AMAF tables; Othello with decisive-move rollouts and the transposition table on the host
+    if not args.headline_only:
+        from mcts_b200.search import QINIT_INFINITY, SELECT_GRAVE
+
+        searches = {
+            "hex11_grave_amaf_search": dict(game=mb.Game.HEX11, strat=mb.Uniform(), kw=dict(select=SELECT_GRAVE, q_init=QINIT_INFINITY, grave_threshold=700)),
+            "othello_decisive_tt_search": dict(game=mb.Game.OTHELLO, strat=mb.DecisiveMoveWin(), kw=dict(use_transpositions=True)),
+        }
+        for name, cfg in searches.items():
+            try:
+                with mb.GpuSearch(cfg["game"], cfg["strat"], max_iterations=4096, batch_leaves=128, num_rollouts_per_leaf=64,
+                                  pipelined=True, seed=7, devices=[local], **cfg["kw"]) as srch:
+                    srch.choose_action(mb.initial_state(cfg["game"]))
+                    t0 = time.perf_counter()
+                    reps = 3
+                    for _ in range(reps):
+                        sr = srch.choose_action(mb.initial_state(cfg["game"]))
+                    dt = (time.perf_counter() - t0) / reps
+                per_game[name] = {
+                    "playouts_per_move": sr.playouts, "seconds_per_move": dt, "playouts_per_s": sr.playouts / dt, "best_action": sr.best_action,
+                    "nodes": sr.nodes, "batch_leaves": 128, "playouts_per_leaf": 64, "pipelined": True,
+                }
+            except Exception as e:
+                per_game[name] = {"error": str(e)}
+
     # BASELINE.json config 4: Breakthrough 8x8, 2^24 playouts for ONE move, the search root-sharded over the ranks (one
     # searcher per GPU with its own seed and tree, search/parallel.rs:56-115), root-child totals merged with one NCCL
     # all-reduce.  Strong scaling: every rank runs 2^24 / N playouts.

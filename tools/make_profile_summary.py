@@ -48,6 +48,26 @@ if s and c and "seconds_per_move" in s:
     L.append(f"\nConfig 1 (Connect4 UCT, ~100k playouts for one move from the empty board): GPU-driven tree driver {s['seconds_per_move'] * 1e3:.2f} ms per move"
              f" ({s['playouts_per_s']:.3e} playouts/s, best move {s['best_action']}); restated reference loop on one CPU core {c['seconds_per_move'] * 1e3:.0f} ms"
              f" ({c['rollouts_per_s_per_core']:.3e} rollouts/s/core, best move {c['best_action']}).\n")
+moves = [("hex11_grave_amaf_search", "Config 3 (Hex 11x11, GRAVE over the in-kernel AMAF tables)"),
+         ("othello_decisive_tt_search", "Config 4a (Othello, decisive-move rollouts, transposition table on the host)"),
+         ("breakthrough_root_parallel_2p24_per_move", "Config 4b / 5 (Breakthrough, 2^24 playouts for one move, one searcher per GPU, root totals merged by one all-reduce)")]
+for key, title in moves:
+    v = b["per_game"].get(key)
+    if v and "seconds_per_move" in v:
+        L.append(f"{title}: {v['playouts_per_move']} playouts in {v['seconds_per_move'] * 1e3:.2f} ms per move ({v['playouts_per_s']:.3e} playouts/s through the tree driver).\n")
+import glob
+scal = []
+for f in sorted(glob.glob(str(P / "bench_r01_n*.json"))):
+    d = json.loads(Path(f).read_text().strip().splitlines()[-1])
+    scal.append((d["n_gpus"], d["value"], d["ms_per_step"], d["e2e"]["value"]))
+if scal:
+    L.append("## Scaling of the headline workload (weak: 4096 x 4096 playouts per GPU per step, one all-reduce per step)\n")
+    L.append("| GPUs | playouts/s | ms/step | e2e playouts/s | vs 1 GPU |")
+    L.append("|---|---|---|---|---|")
+    L.append(f"| 1 | {b['value']:.3e} | {b['ms_per_step']:.3f} | {b['e2e']['value']:.3e} | 1.00 |")
+    for n, v, ms, e in sorted(scal):
+        L.append(f"| {n} | {v:.3e} | {ms:.3f} | {e:.3e} | {v / b['value']:.2f} |")
+    L.append("")
 L.append("## Measured integer peaks (`tools/measure_int_peaks.py`, thread-ops per SM per clock at 1965 MHz)\n")
 L.append("| op | /SM/clk | T thread-ops/s |")
 L.append("|---|---|---|")
