@@ -351,9 +351,13 @@ struct ThroughBase {
 
 struct Breakthrough : ThroughBase {
     static constexpr bool ROLLED = false;
-    static constexpr int MIN_BLOCKS = 6; // <= 80 registers: 24 warps/SM instead of 20, +4.7% on the MAST kernel (measured)
-    // the MAST kernel gains another 5% at 7 blocks/SM (<= 72 registers); the uniform kernel does not (measured)
-    static constexpr int min_blocks(int policy) { return policy == MR_EPS_MAST ? 7 : MIN_BLOCKS; }
+#ifndef MR_BT_BLOCKS
+#define MR_BT_BLOCKS 6
+#endif
+    // <= 80 registers, 24 warps/SM.  Measured on the MAST kernel after the pipe-balancing / uniform-datapath changes:
+    // 4 blocks 4.12 ms, 5: 4.11, 6: 3.73, 7: 3.76, 8: 3.80 (the 7-block cap that was best before them is no longer)
+    static constexpr int MIN_BLOCKS = MR_BT_BLOCKS;
+    static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
     static constexpr int NSLOTS = 192;
     static constexpr int KINDS = 3; // src*3 + kind (W,F,E)
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
