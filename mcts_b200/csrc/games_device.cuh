@@ -913,10 +913,22 @@ struct Othello {
     // The four "toward lower bits" directions are run as LEFT-shift rays on the bit-reversed boards (bit i <-> 63-i
     // maps a right shift by s onto a left shift by s, and keeps the INNER column mask).  Left shifts put their low
     // word on the FMA pipe (IMAD.SHL); right shifts are two ALU funnel shifts, and the ALU pipe is 95% busy here.
+    // The +1 direction (next cell of the same row) needs no parallel prefix: adding the cells right after the own discs
+    // to the inner opponent discs ripples a carry through every contiguous run that starts there and drops it on the
+    // first cell after the run (`mO` holds columns 1..6 only, so a carry never leaves its row).  6 instructions instead
+    // of a 22-instruction ray; with the bit-reversed boards this covers both row directions.
+    __device__ static uint64_t moves_carry1(uint64_t P, uint64_t mO) {
+        const uint64_t x = P << 1;
+        return (mO + x) & ~mO & ~x; // cells where a carry landed (an own disc's neighbour without a run is `x` itself)
+    }
+    __device__ static uint64_t flips_carry1(uint64_t mv, uint64_t P, uint64_t mO) {
+        const uint64_t x = mv << 1, a = mO + x;
+        return ((a & ~mO & ~x) & P) ? (mO & ~a) : 0ull; // the run the carry cleared, if it landed on an own disc
+    }
     __device__ static uint64_t brev64(uint64_t v) { return mk64(__brev(hi32(v)), __brev(lo32(v))); }
     __device__ static uint64_t moves_left(uint64_t P, uint64_t O) { // the four left-shift directions
         const uint64_t mO = O & INNER;
-        return sh<8, true>(ray<8, true>(P, O)) | sh<1, true>(ray<1, true>(P, mO)) | sh<9, true>(ray<9, true>(P, mO)) |
+        return sh<8, true>(ray<8, true>(P, O)) | moves_carry1(P, mO) | sh<9, true>(ray<9, true>(P, mO)) |
                sh<7, true>(ray<7, true>(P, mO));
     }
     __device__ static uint64_t legal_moves(uint64_t P, uint64_t O) {
@@ -931,7 +943,7 @@ struct Othello {
     }
     __device__ static uint64_t flips_left(uint64_t mv, uint64_t P, uint64_t O) {
         const uint64_t mO = O & INNER;
-        return flips_dir<8>(mv, P, O) | flips_dir<1>(mv, P, mO) | flips_dir<9>(mv, P, mO) | flips_dir<7>(mv, P, mO);
+        return flips_dir<8>(mv, P, O) | flips_carry1(mv, P, mO) | flips_dir<9>(mv, P, mO) | flips_dir<7>(mv, P, mO);
     }
     __device__ static uint64_t flips(uint64_t mv, uint64_t P, uint64_t O) {
         return flips_left(mv, P, O) | brev64(flips_left(brev64(mv), brev64(P), brev64(O)));
