@@ -60,6 +60,8 @@ struct Connect4 {
     static constexpr int NSLOTS = 7; // compact per-player statistic slots (== action ids here)
     static constexpr int KINDS = 1;
     static constexpr bool MASK_AMAF = false;
+    template <class S>
+    __device__ static void init_shared(S &, uint32_t) {} // no per-warp tables
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) { return slot; }
     __device__ static uint32_t code_to_slot(uint32_t pl, uint32_t code) { return code < 7u ? code : 0u; }
     static constexpr uint64_t BOTTOM = 0x0001010101010101ull;
@@ -290,6 +292,8 @@ struct Connect4 {
 struct ThroughBase {
     static constexpr int NA = 4096;
     static constexpr bool MASK_AMAF = false;
+    template <class S>
+    __device__ static void init_shared(S &, uint32_t) {} // no per-warp tables
     static constexpr uint64_t NOT_COL0 = 0xFEFEFEFEFEFEFEFEull;
     static constexpr uint64_t NOT_COL7 = 0x7F7F7F7F7F7F7F7Full;
 
@@ -877,7 +881,19 @@ struct Othello {
     struct Shared {
         uint64_t black, white;
         uint32_t turn, last_pass;
+        uint64_t ray[3][64]; // squares beyond x towards +8 / +9 / +7 up to the board edge (flips_ray)
     };
+    __device__ static void init_shared(Shared &s, uint32_t lane) { // once per warp, before the first task
+        for (uint32_t e = lane; e < 192u; e += 32u) {
+            const int k = (int)(e >> 6), r0 = (int)((e & 63u) >> 3), c0 = (int)(e & 7u), dc = k == 0 ? 0 : (k == 1 ? 1 : -1);
+            uint64_t m = 0;
+            for (int i = 1; i < 8; ++i) {
+                const int r = r0 + i, c = c0 + dc * i;
+                if (r <= 7 && c >= 0 && c <= 7) m |= 1ull << (r * 8 + c);
+            }
+            s.ray[k][e & 63u] = m;
+        }
+    }
     uint64_t black, white;
     uint32_t last_pass;
     uint32_t rt_parity; // parity of the current ply inside its window (PARITY == 2 call sites)
@@ -947,6 +963,25 @@ struct Othello {
     }
     __device__ static uint64_t flips(uint64_t mv, uint64_t P, uint64_t O) {
         return flips_left(mv, P, O) | brev64(flips_left(brev64(mv), brev64(P), brev64(O)));
+    }
+    // The flips of ONE known square need no prefix network in the other directions either: with every bit off the ray set
+    // (`O | ~ray`), adding the first ray cell ripples a carry along the ray through the opponent's run -- across the gaps
+    // between ray cells, which are all ones -- and drops it on the first ray cell that is not an opponent disc.  The run
+    // flips iff that cell holds an own disc; a run that reaches the edge carries out of the word.  (The classic
+    // "outflank by carry" of Othello engines; the reference's Kogge-Stone fills are othello/lib.rs:188-234.)
+    template <int S, int K>
+    __device__ static uint64_t flips_ray(const Shared &s, uint32_t sq, uint64_t mv, uint64_t P, uint64_t O) {
+        const uint64_t m = s.ray[K][sq];
+        const uint64_t u = O | ~m, t = u + (mv << S);
+        return (t & ~u & m & P) ? (u & ~t & m) : 0ull;
+    }
+    __device__ static uint64_t flips_left_sq(const Shared &s, uint32_t sq, uint64_t mv, uint64_t P, uint64_t O) {
+        return flips_ray<8, 0>(s, sq, mv, P, O) | flips_carry1(mv, P, O & INNER) | flips_ray<9, 1>(s, sq, mv, P, O) |
+               flips_ray<7, 2>(s, sq, mv, P, O);
+    }
+    __device__ static uint64_t flips_sq(const Shared &s, uint32_t sq, uint64_t P, uint64_t O) {
+        const uint64_t mv = bit64(sq);
+        return flips_left_sq(s, sq, mv, P, O) | brev64(flips_left_sq(s, 63u - sq, brev64(mv), brev64(P), brev64(O)));
     }
     // position of the idx-th set bit of a 64-bit mask
     __device__ static uint32_t select64(uint64_t w, uint32_t idx) {
@@ -1035,7 +1070,7 @@ struct Othello {
             if (rep) {
                 sq = rep - 1u;
                 mv = bit64(sq);
-                fl = flips(mv, P, O);
+                fl = flips_sq(s, sq, P, O);
                 have = true;
             }
         }
@@ -1066,13 +1101,13 @@ struct Othello {
                 }
             }
             mv = bit64(sq);
-            fl = flips(mv, P, O);
+            fl = flips_sq(s, sq, P, O);
             have = true;
         }
         if (!have) {
             sq = select64(moves, mulhi(x0, n));
             mv = bit64(sq);
-            fl = flips(mv, P, O);
+            fl = flips_sq(s, sq, P, O);
         }
         const uint64_t nP = P | mv | fl, nO = O & ~fl;
         black = is_white ? nO : nP;

@@ -22,6 +22,8 @@ namespace mr {
 
 struct HexStep : Hex11 {
     static constexpr bool MASK_AMAF = false; // statistics come from the slot trace, like the other per-ply games
+    template <class S>
+    __device__ static void init_shared(S &, uint32_t) {} // no per-warp tables
     static constexpr bool ROLLED = true;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }

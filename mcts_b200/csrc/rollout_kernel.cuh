@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
         for (uint32_t e = threadIdx.x; e < 2u * G::NSLOTS; e += THREADS_PER_BLOCK) lgr_tab[e] = 0;
         __syncthreads();
     }
+    G::init_shared(sh, lane); // per-warp lookup tables of the game (Othello: ray masks)
     __syncwarp();
 
     unsigned long long grab_lo = 0, grab_hi = 0; // the warp's current grab, relative to g_begin
