@@ -292,7 +292,7 @@ def run_gpu(args):
         d_amaf = torch.zeros(n_leaves * 2 * na * 2, dtype=torch.int32, device=dev) if w["amaf"] else None
         launches0 = g.kernel_launches()
 
-        def step(i):
+        def launch(i):
             d_results.zero_()
             if d_delta is not None:
                 d_delta.zero_()
@@ -304,6 +304,9 @@ def run_gpu(args):
                 d_mast_delta=d_delta.data_ptr() if d_delta is not None else 0,
                 leaf_id_base=root_merge.leaf_id_base(rank, world, i, n_leaves),
             )
+
+        def step(i):
+            launch(i)
             if dist is not None:
                 # the path's one exchange step: merge MAST delta + per-root-child stats over NVLink (NCCL)
                 root_merge.merge_sum_(d_merge)
@@ -323,8 +326,20 @@ def run_gpu(args):
             e1.record(stream)
             evs.append((e0, e1))
         barrier()
-        clocks = sampler.stop() if sampler else None
         launches = g.kernel_launches() - launches_before
+        clocks = None
+        if sampler:
+            # the timed region lasts tens of milliseconds and nvidia-smi reports every ~20 ms: keep the identical load
+            # running (untimed) for another 0.4 s so that the clock / throttle-reason record has a dozen samples under load
+            t_end = time.perf_counter() + 0.4
+            i = 0
+            while time.perf_counter() < t_end:
+                launch(warmup + steps + i)  # this rank's kernels only: the other ranks do not take part
+                i += 1
+                if i % 8 == 0:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            clocks = sampler.stop()
         step_ms = [a.elapsed_time(b) for a, b in evs]
         total_ms = sum(step_ms)
         if dist is not None:
