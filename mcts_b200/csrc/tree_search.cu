@@ -72,6 +72,7 @@ struct Node {
     uint8_t player = 0;
     uint16_t n_children = 0;
     uint32_t first = 0; // index of child 0 in the edge arrays
+    int32_t grave_tab = -1; // cached index of this state's GRAVE table (-1 = not looked up successfully yet)
 };
 
 struct PathEntry {
@@ -142,9 +143,11 @@ struct Tree {
     }
 };
 
-struct GraveStat { // node.rs:51-55 ActionStats with an integer score
-    uint32_t visits = 0;
-    int64_t score = 0;
+struct GraveTable { // per state: [2 * NA] ActionStats (node.rs:51-55) with integer scores, as two arrays so that the
+                    // per-leaf table merge of backprop_grave is two straight vectorisable loops
+    std::vector<uint32_t> visits;
+    std::vector<int64_t> score;
+    explicit GraveTable(size_t n) : visits(n, 0u), score(n, 0) {}
 };
 
 struct Search {
@@ -159,13 +162,20 @@ struct Search {
     // TreeStats.grave (search/shared.rs:52): per reference-node state, per player, per action.  The reference keys
     // it by node.hash; here the key is the full state record (no collisions), so equal states share one table.
     std::unordered_map<StateKey, uint32_t, StateKeyHash> grave_index;
-    std::vector<std::vector<GraveStat>> grave; // [table][2 * NA]
+    std::vector<GraveTable> grave; // one per distinct state
 
-    std::vector<GraveStat> *grave_of(const mr_leaf &s, bool create) {
-        auto it = grave_index.find(key_of(s));
-        if (it != grave_index.end()) return &grave[it->second];
+    // (the table of a node is found once through the state-keyed index and then remembered in the node: the selection
+    // formula asks for it once per CHILD, 121 times per visited Hex node)
+    GraveTable *grave_of(Node &n, bool create) {
+        if (n.grave_tab >= 0) return &grave[(size_t)n.grave_tab];
+        auto it = grave_index.find(key_of(n.state));
+        if (it != grave_index.end()) {
+            n.grave_tab = (int32_t)it->second;
+            return &grave[it->second];
+        }
         if (!create) return nullptr;
-        grave_index.emplace(key_of(s), (uint32_t)grave.size());
+        n.grave_tab = (int32_t)grave.size();
+        grave_index.emplace(key_of(n.state), (uint32_t)grave.size());
         grave.emplace_back((size_t)2 * na);
         return &grave.back();
     }
@@ -240,11 +250,10 @@ struct Search {
                     const uint32_t ref = grave_ref(path, (uint32_t)t.child[node.first + i], i);
                     uint32_t amaf_n = 0;
                     double amaf_q = 0.0;
-                    auto git = grave_index.find(key_of(t.nodes[ref].state));
-                    if (git != grave_index.end()) {
-                        const GraveStat &g = grave[git->second][(size_t)player * na + mr_host::action_id(t.game, t.action[node.first + i])];
-                        amaf_n = g.visits;
-                        amaf_q = (double)g.score;
+                    if (const GraveTable *tab = grave_of(t.nodes[ref], false)) {
+                        const size_t e = (size_t)player * na + mr_host::action_id(t.game, t.action[node.first + i]);
+                        amaf_n = tab->visits[e];
+                        amaf_q = (double)tab->score[e];
                     }
                     const uint32_t n_tot = e.visits + e.vloss;
                     const double explore = c * std::sqrt(parent_log / (double)n_tot);
@@ -325,15 +334,16 @@ struct Search {
     void backprop_grave(const std::vector<PathEntry> &path, const mr_action_stat *amaf, const int64_t u[2], uint32_t k) {
         std::vector<std::pair<uint32_t, int>> below; // (action id, player) of the edges below the node being updated
         for (size_t i = path.size(); i-- > 1;) {
-            std::vector<GraveStat> &tab = *grave_of(t.nodes[path[i].node].state, true);
-            for (size_t e = 0; e < (size_t)2 * na; ++e) {
-                tab[e].visits += amaf[e].visits;
-                tab[e].score += amaf[e].score;
-            }
+            GraveTable &tab = *grave_of(t.nodes[path[i].node], true);
+            uint32_t *__restrict__ tv = tab.visits.data();
+            int64_t *__restrict__ ts = tab.score.data();
+            const size_t cnt = (size_t)2 * na;
+            for (size_t e = 0; e < cnt; ++e) tv[e] += amaf[e].visits;
+            for (size_t e = 0; e < cnt; ++e) ts[e] += amaf[e].score;
             for (const auto &b : below) {
-                GraveStat &g = tab[(size_t)b.second * na + b.first];
-                g.visits += k;
-                g.score += u[b.second];
+                const size_t e = (size_t)b.second * na + b.first;
+                tv[e] += k;
+                ts[e] += u[b.second];
             }
             const Node &parent = t.nodes[path[i - 1].node];
             below.emplace_back((uint32_t)mr_host::action_id(t.game, t.action[parent.first + path[i].idx]), (int)parent.player);
