@@ -507,12 +507,14 @@ int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const Lau
     const uint64_t need_blocks = (work + 32ull * WARPS_PER_BLOCK - 1) / (32ull * WARPS_PER_BLOCK);
     if (blocks > need_blocks) blocks = (uint32_t)need_blocks;
     kp.total_warps = blocks * WARPS_PER_BLOCK;
-    // Fixed-size grabs measured best on B200 (profiles/grab_sweep_r01.txt): 512 playouts (16 per lane) when
-    // the batch is large enough for >= 4 grabs per resident warp, smaller powers of two otherwise.
+    // Guided self-scheduling (profiles/grab_sweep_r01.txt): a warp grabs remaining / (2 * warps) playouts, between 128 and
+    // 512 (16 per lane) when the batch is large enough for >= 4 full grabs per resident warp, smaller powers of two
+    // otherwise -- large grabs while there is plenty of work, small ones at the end so that the warps finish together.
     {
         uint32_t chunk = 512;
         while (chunk > 32 && (uint64_t)chunk * kp.total_warps * 4 > work) chunk >>= 1;
-        kp.grab_min = kp.grab_max = chunk;
+        kp.grab_max = chunk;
+        kp.grab_min = chunk >= 128 ? chunk / 4 : 32;
     }
     if (const char *e = getenv("MR_GRAB_MIN")) kp.grab_min = (uint32_t)atoi(e) & ~31u; // tuning knobs
     if (const char *e = getenv("MR_GRAB_MAX")) kp.grab_max = (uint32_t)atoi(e) & ~31u;
