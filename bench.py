@@ -66,7 +66,7 @@ OPS_PER_PLY = {
 }
 # DRAM bytes per launch of the headline kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
 # `ncu --set full` capture summarised in profiles/ncu_r01_breakthrough8x8_eps_mast.txt
-NCU_TRAFFIC_BYTES = {"breakthrough8x8_eps_mast": 10348288 + 280832}  # profiles/ncu_r01_breakthrough8x8_eps_mast.txt
+NCU_TRAFFIC_BYTES = {"breakthrough8x8_eps_mast": 10414848 + 364544}  # profiles/ncu_r01_breakthrough8x8_eps_mast.txt
 MAST_WARMUP_K = 16  # uniform playouts per leaf that populate the MAST table before the timed steps
 MEAN_LEGAL = {1: 25.7, 2: 47.8}  # BASELINE.md section 4 (oracle-measured mean branching)
 
