@@ -55,6 +55,7 @@ struct Connect4 {
     static constexpr int NA = 7;
     // windows unrolled: measured 6-7% faster than a rolled window for this small step (profiles/roll_compare_r01.txt)
     static constexpr bool ROLLED = false;
+    __host__ __device__ static constexpr bool rolled(int) { return ROLLED; }
     static constexpr int MIN_BLOCKS = 1; // a 64-register cap (8 blocks/SM) measured 4% slower
     static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
     static constexpr int NSLOTS = 7; // compact per-player statistic slots (== action ids here)
@@ -355,6 +356,7 @@ struct ThroughBase {
 
 struct Breakthrough : ThroughBase {
     static constexpr bool ROLLED = false;
+    __host__ __device__ static constexpr bool rolled(int) { return ROLLED; }
 #ifndef MR_BT_BLOCKS
 #define MR_BT_BLOCKS 6
 #endif
@@ -426,7 +428,9 @@ struct Breakthrough : ThroughBase {
 struct Knightthrough : ThroughBase {
     static constexpr int MIN_BLOCKS = 5; // <= 96 registers: +13% on the MAST kernel (measured); 4 and 6 are within noise of it
     static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
-    static constexpr bool ROLLED = true; // the step is large (8 masks, adder tree): a rolled window fits the I-cache (+14%)
+    // the step is large (8 masks, adder tree): the MAST kernels run the window as a loop (fits the I-cache, +1.3 %
+    // measured); the kernels without the arg-max are 4 % faster unrolled (compile-time ply parity, uniform datapath)
+    __host__ __device__ static constexpr bool rolled(int policy) { return policy_mast_inner(policy); }
     static constexpr int NSLOTS = 512; // src*8 + kind (ascending-dst jump order)
     static constexpr int KINDS = 8;
     __device__ static uint32_t slot_action_id(uint32_t pl, uint32_t slot) {
@@ -875,6 +879,7 @@ struct Othello {
     // The per-ply code (8 fills for moves + 8 for flips) is large: the four plies of a window run as a LOOP,
     // with the ply's parity a run-time value, so the kernel fits the instruction cache.
     static constexpr bool ROLLED = true;
+    __host__ __device__ static constexpr bool rolled(int) { return ROLLED; }
     static constexpr int MIN_BLOCKS = 1; // a register cap (6 blocks/SM, 80 regs) measured no faster on B200
     static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
 

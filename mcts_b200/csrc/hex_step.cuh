@@ -25,6 +25,7 @@ struct HexStep : Hex11 {
     template <class S>
     __device__ static void init_shared(S &, uint32_t) {} // no per-warp tables
     static constexpr bool ROLLED = true;
+    __host__ __device__ static constexpr bool rolled(int) { return ROLLED; }
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int min_blocks(int policy) { return MIN_BLOCKS; }
     __device__ static uint32_t code_to_slot(uint32_t pl, uint32_t code) { return code < 121u ? code : 0u; }

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                         }
                     }
                 };
-                if constexpr (G::ROLLED) {
+                if constexpr (G::rolled(POLICY)) {
 #pragma unroll 1
                     for (uint32_t j = 0; j < (uint32_t)WINDOW; ++j) {
                         st.rt_parity = j & 1u;
