@@ -455,6 +455,47 @@ def test_double_buffered_slots_and_errors():
         assert "MR_ERR_INVALID" in str(e.value)
 
 
+def test_table_policy_error_paths():
+    """The table-policy entry points fail loudly on misuse: a table of another game, reading results before mr_wait or
+    from a batch of another policy, a merged LGRF-2 candidate that names no action of the player."""
+    import ctypes as C
+
+    from mcts_b200._lib import REPLY_UPDATE_DTYPE, ptr
+
+    leaves = _leaves(o.CONNECT4, n_per=2).view(mb.LEAF_DTYPE)
+    mast = _random_mast(o.CONNECT4, 1)
+    with mb.GpuRollout(mb.Game.CONNECT4, mb.EpsilonGreedyNst(0.1), seed=1) as g:
+        ns_bt = o.num_slots(o.BREAKTHROUGH)
+        other = np.zeros((2, ns_bt, ns_bt), dtype=mb.STAT_DTYPE)
+        assert g.lib.mr_set_bigrams(g._h, int(mb.Game.BREAKTHROUGH), ptr(other), 5) == 0
+        with pytest.raises(mb.RolloutError) as e:  # the bigram table belongs to another game
+            g.simulate_many(leaves, 8, stats=mast)
+        assert "MR_ERR_INVALID" in str(e.value)
+        g.set_bigrams(None)
+        with pytest.raises(mb.RolloutError):  # an NST batch needs the unigram (MAST) table
+            g.simulate_many(leaves, 8)
+        out = np.zeros((2, 7, 7), dtype=mb.STAT_DTYPE)
+        assert g.lib.mr_bigram_delta(g._h, 0, ptr(out)) != 0  # no completed NST batch on the slot
+        g.submit(leaves, 8, stats=mast)
+        assert g.lib.mr_bigram_delta(g._h, 0, ptr(out)) != 0  # still in flight
+        r = g.wait()
+        assert r.bigram_delta is not None and int(r.bigram_delta["visits"].sum()) > 0
+    with mb.GpuRollout(mb.Game.CONNECT4, mb.EpsilonGreedyLgr(0.1), seed=1) as g:
+        g.simulate_many(leaves, 8)
+        ins = np.zeros((2, 7, 7), dtype=REPLY_UPDATE_DTYPE)
+        assert g.lib.mr_reply2_inserts(g._h, 0, ptr(ins), None) != 0  # an LGR-1 batch holds no 2-ply inserts
+    with mb.GpuRollout(mb.Game.CONNECT4, mb.EpsilonGreedyLgr2(0.1), seed=1) as g:
+        r = g.simulate_many(leaves, 8)
+        bad = r.reply2_inserts.copy()
+        bad["order"][0, 0, 0] = 1 << 13
+        bad["action_plus1"][0, 0, 0] = 9  # column 8 does not exist
+        with pytest.raises(mb.RolloutError) as e:
+            g.resolve_replies2(bad)
+        assert "names no action" in str(e.value)
+        assert g.resolve_replies2(r.reply2_inserts).shape == (2, 7, 7)  # and the slot can still be resolved afterwards
+        assert mb.num_actions(mb.Game.CONNECT4) == 7 and C.sizeof(C.c_void_p) == 8
+
+
 @pytest.mark.parametrize("game", GAMES)
 def test_full_size_properties(game):
     """At bench size the oracle is too slow to replay everything; check size-independent properties and
