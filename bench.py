@@ -44,6 +44,8 @@ HEADLINE = dict(name="breakthrough8x8_eps_mast", game=1, policy=1, plies=20, pos
 OTHERS = [
     dict(name="connect4_uniform_midgame", game=0, policy=0, plies=12, pos_seed=1, max_depth=0, eps=0.0, amaf=False),
     dict(name="knightthrough8x8_eps_mast", game=2, policy=1, plies=20, pos_seed=2, max_depth=200, eps=0.1, amaf=False),
+    # (after 20 random plies a Knightthrough game is almost over: 2.4 plies per playout; 8-ply openings show the per-ply rate)
+    dict(name="knightthrough8x8_eps_mast_opening8", game=2, policy=1, plies=8, pos_seed=2, max_depth=200, eps=0.1, amaf=False),
     dict(name="othello_decisive_win", game=3, policy=2, plies=30, pos_seed=4, max_depth=0, eps=0.0, amaf=False),
     dict(name="hex11_uniform_amaf", game=4, policy=0, plies=30, pos_seed=3, max_depth=0, eps=0.0, amaf=True),
     dict(name="breakthrough8x8_uniform", game=1, policy=0, plies=20, pos_seed=2, max_depth=0, eps=0.0, amaf=False),
@@ -61,6 +63,7 @@ OPS_PER_PLY = {
     "breakthrough8x8_uniform": 160.0,
     "breakthrough8x8_eps_mast": None,  # 160 + 8 * n_legal on the greedy plies; n_legal measured below
     "knightthrough8x8_eps_mast": None,  # 220 + 8 * n_legal on the greedy plies
+    "knightthrough8x8_eps_mast_opening8": None,
     "othello_decisive_win": 750.0,
     "hex11_uniform_amaf": 65.0 + 116.0 * 2.9,
 }
