@@ -190,12 +190,9 @@ struct Search {
         const double k = (double)d->rave_param;
         return std::sqrt(k / (3.0 * (double)n + k));
     }
-    // select/rave.rs:157-184 get_ref: the nearest node on the path (the child itself first) whose incoming edge
-    // has total_visits >= threshold, else the root
-    uint32_t grave_ref(const std::vector<PathEntry> &path, uint32_t child_node, uint32_t child_idx) const {
-        const Node &cur = t.nodes[path.back().node];
-        const Stats &ce = t.edge[cur.first + child_idx];
-        if (ce.visits + ce.vloss >= d->grave_threshold) return child_node;
+    // select/rave.rs:157-184 get_ref: the child itself when its incoming edge has total_visits >= threshold (decided in
+    // best_child), else the nearest such node on the path, else the root
+    uint32_t grave_ref_ancestor(const std::vector<PathEntry> &path) const {
         for (size_t i = path.size(); i-- > 1;) {
             const Stats &e = t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
             if (e.visits + e.vloss >= d->grave_threshold) return path[i].node;
@@ -234,6 +231,9 @@ struct Search {
         bool have = false;
         double best = 0.0;
         uint32_t best_i = i;
+        bool anc_done = false;
+        uint32_t anc_ref = 0;
+        const GraveTable *anc_tab = nullptr;
         for (uint32_t k = 0; k < n; ++k) {
             const Stats &e = t.edge[node.first + i];
             double score;
@@ -247,10 +247,17 @@ struct Search {
                     const double frac = parent_log / total;
                     score = exploit + (frac * std::min(1.0, var) + c * std::sqrt(frac));
                 } else if (d->select == MR_SELECT_GRAVE) { // rave.rs:196-224
-                    const uint32_t ref = grave_ref(path, (uint32_t)t.child[node.first + i], i);
+                    // get_ref: the child itself once its edge has the threshold visits, else the nearest such ancestor --
+                    // which is the same node for every child of this node, so it is resolved once (anc_ref / anc_tab)
+                    const bool own_ref = e.visits + e.vloss >= d->grave_threshold;
+                    if (!own_ref && !anc_done) {
+                        anc_ref = grave_ref_ancestor(path);
+                        anc_tab = grave_of(t.nodes[anc_ref], false);
+                        anc_done = true;
+                    }
                     uint32_t amaf_n = 0;
                     double amaf_q = 0.0;
-                    if (const GraveTable *tab = grave_of(t.nodes[ref], false)) {
+                    if (const GraveTable *tab = own_ref ? grave_of(t.nodes[(uint32_t)t.child[node.first + i]], false) : anc_tab) {
                         const size_t e = (size_t)player * na + mr_host::action_id(t.game, t.action[node.first + i]);
                         amaf_n = tab->visits[e];
                         amaf_q = (double)tab->score[e];
