@@ -607,7 +607,9 @@ def test_win_rate_agrees_with_independent_cpu_rollouts():
 def test_randomized_differential_sweep():
     """Seeded random batch shapes: game x policy x flags x (n, k) x leaf id base x depth cutoff, GPU vs oracle,
     every playout's trace, record, final state and every aggregate compared bit for bit."""
-    rng = np.random.default_rng(20260101)
+    import os
+
+    rng = np.random.default_rng(int(os.environ.get("MR_FUZZ_SEED", "20260101")))  # a longer sweep: MR_FUZZ_CASES=400 MR_FUZZ_SEED=7
     policies = {
         o.CONNECT4: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI],
         o.BREAKTHROUGH: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI, o.DECISIVE_MAST_WINLOSS],
@@ -616,7 +618,7 @@ def test_randomized_differential_sweep():
         o.HEX11: [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_ANTI, o.DECISIVE_MAST_WIN],
     }
     max_plies = {o.CONNECT4: 30, o.BREAKTHROUGH: 50, o.KNIGHTTHROUGH: 30, o.OTHELLO: 56, o.HEX11: 100}
-    for case in range(40):
+    for case in range(int(os.environ.get("MR_FUZZ_CASES", "40"))):
         game = GAMES[case % 5]
         policy = policies[game][int(rng.integers(len(policies[game])))]
         n, k = int(rng.integers(1, 24)), int(rng.choice([1, 2, 7, 31, 32, 33, 64, 97]))
