@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                         out->turn = (uint8_t)((leaf_turn + depth) & 1u);
                         out->flag = 0;
                         out->prev_action_plus1 = 0;
-        out->prev2_action_plus1 = 0;
-        out->pad[0] = out->pad[1] = 0;
+                        out->prev2_action_plus1 = 0;
+                        out->pad[0] = out->pad[1] = 0;
                     }
                 }
                 if (WANT_AMAF) {
