@@ -490,3 +490,20 @@ def test_nst_backs_off_to_mast_and_bigram_delta_sums_to_mast_delta(game):  # sim
     assert (never["trace"] == as_mast["trace"]).all() and (empty["trace"] == as_mast["trace"]).all()
     used = o.playout_batch(game, leaves, 16, bigram=bigram, nst_threshold=1, **kw)
     assert not (used["trace"] == as_mast["trace"]).all()  # the bigram scores changed picks
+
+
+@pytest.mark.parametrize("game", [o.CONNECT4, o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.OTHELLO, o.HEX11])
+def test_random_play_terminates(game):
+    """The games' own smoke tests (`random_play::<G>()`, mcts/src/util.rs:227-233; connect4/lib.rs:461, breakthrough/lib.rs:270,
+    knightthrough/lib.rs:264, hex-gen/lib.rs:265, othello's equivalent): uniformly random self-play from the initial
+    position reaches a terminal state -- here 400 games per game, each ending NaturalEnd with a terminal status, within
+    the game's own length bound (Knightthrough, whose knights also jump backwards, within 2000 plies)."""
+    bound = {o.CONNECT4: 42, o.BREAKTHROUGH: 224, o.KNIGHTTHROUGH: 2000, o.OTHELLO: 128, o.HEX11: 121}[game]
+    r = o.playout_batch(game, o.initial_state(game), 400, seed=17, max_depth=bound + 1, want_final=True, want_trace=True, max_trace=1)
+    rec = r["records"]
+    assert (rec["end_type"] == o.END_TERMINAL).all()
+    assert (rec["depth"] <= bound).all() and (rec["depth"] > 0).all()
+    for s in r["final"][:50]:
+        assert o.terminal_status(game, np.array([s])) != o.NOT_TERMINAL
+    if game == o.HEX11:  # Hex has no draws
+        assert (rec["outcome"] != o.DRAW).all()
