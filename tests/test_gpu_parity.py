@@ -417,6 +417,50 @@ def test_lgrf2_bit_exact(game, big_grabs, policy, monkeypatch):
             assert plain["results"].tobytes() != ref["results"].tobytes()  # 2-ply replies (and MAST picks) were actually played
 
 
+def test_reference_policy_kats_on_the_gpu():
+    """The reference's own policy KATs (mcts-tests/tests/decisive_move.rs:10-61, ttt_strategies.rs:916-1075), set up on
+    Connect4 as in tests/test_oracle_golden.py, answered by the CUDA path directly."""
+    def play(cols):
+        st = mb.initial_state(mb.Game.CONNECT4)
+        for c in cols:
+            st = mb.apply(mb.Game.CONNECT4, st, c)
+        return st
+
+    def first_moves(strategy, state, n=64, setup=None, **kw):
+        with mb.GpuRollout(mb.Game.CONNECT4, strategy, seed=5, max_playout_depth=1) as g:
+            if setup:
+                setup(g)
+            r = g.simulate_many(state, n, want_trace=True, max_trace=1, **kw)
+        return set(int(a) for a in r.trace[:, 0]), r
+
+    block = play([6, 0, 6, 1, 5, 2])  # White threatens d1, Black has no win: the block is the only anti-decisive move
+    assert first_moves(mb.DecisiveMove("anti_decisive"), block)[0] == {3}
+    assert len(first_moves(mb.Uniform(), block, n=256)[0]) == 7
+    win = play([0, 6, 1, 6, 2, 6])  # Black wins at d1 while White threatens g4: the win comes first
+    assert first_moves(mb.DecisiveMove("anti_decisive"), win)[0] == {3}
+    assert first_moves(mb.DecisiveMoveWin(), win)[0] == {3}
+    # NST backoff: unigram favours column 1, the bigram after column 2 favours column 0
+    s = mb.initial_state(mb.Game.CONNECT4)
+    s["prev"] = 3
+    mast = np.zeros((2, 7), dtype=mb.STAT_DTYPE)
+    mast["visits"][0] = 10
+    mast["score"][0] = [0, 10, -10, -10, -10, -10, -10]
+    bigram = np.zeros((2, 7, 7), dtype=mb.STAT_DTYPE)
+    bigram["visits"][0, 2, 0], bigram["score"][0, 2, 0] = 2, 2
+    bigram["visits"][0, 2, 1], bigram["score"][0, 2, 1] = 2, 0
+    assert first_moves(mb.EpsilonGreedyNst(0.0, 5), s, setup=lambda g: g.set_bigrams(bigram), stats=mast)[0] == {1}
+    bigram["visits"][0, 2, 0], bigram["score"][0, 2, 0] = 5, 5
+    bigram["visits"][0, 2, 1] = 5
+    assert first_moves(mb.EpsilonGreedyNst(0.0, 5), s, setup=lambda g: g.set_bigrams(bigram), stats=mast)[0] == {0}
+    s["prev"] = 0
+    assert first_moves(mb.EpsilonGreedyNst(0.0, 1), s, setup=lambda g: g.set_bigrams(bigram), stats=mast)[0] == {1}
+    # NST table population: a two-ply playout puts its one pair into the second mover's table only
+    with mb.GpuRollout(mb.Game.CONNECT4, mb.EpsilonGreedyNst(0.1), seed=7, max_playout_depth=2) as g:
+        r = g.simulate_many(mb.initial_state(mb.Game.CONNECT4), 1, stats=np.zeros((2, 7), dtype=mb.STAT_DTYPE), want_trace=True, max_trace=2)
+    a0, a1 = int(r.trace[0][0]), int(r.trace[0][1])
+    assert r.bigram_delta["visits"][1, a0, a1] == 1 and r.bigram_delta["visits"][1].sum() == 1 and r.bigram_delta["visits"][0].sum() == 0
+
+
 def test_reference_shaped_playout_call():
     """SimulateStrategy::playout(state, max_playout_depth, stats, prev_action, rng) -> Trial"""
     game = o.CONNECT4

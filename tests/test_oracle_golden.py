@@ -507,3 +507,63 @@ def test_random_play_terminates(game):
         assert o.terminal_status(game, np.array([s])) != o.NOT_TERMINAL
     if game == o.HEX11:  # Hex has no draws
         assert (rec["outcome"] != o.DRAW).all()
+
+
+# ---- the reference's policy KATs (mcts-tests), which it states on TicTacToe -- a game the rollout path does not carry.
+# ---- The strategies are game-independent, so the same situations are set up on Connect4 and driven through the oracle's
+# ---- playout loop (one ply: max_depth = 1, the trace holds the pick).
+
+def _first_moves(state, policy, n=64, **kw):
+    r = o.playout_batch(o.CONNECT4, state, n, policy=policy, seed=5, max_depth=1, want_trace=True, max_trace=1, **kw)
+    return set(int(a) for a in r["trace"][:, 0])
+
+
+def test_anti_decisive_blocks_the_opponents_only_winning_reply():  # mcts-tests/tests/decisive_move.rs:10-37
+    """White threatens d1 (a1 b1 c1 on the bottom row); Black has no win of its own, and every move but the block hands
+    White that win on the next reply: the block is the unique anti-decisive choice although it wins nothing."""
+    s = _c4_play([6, 0, 6, 1, 5, 2])  # Black: g1 g2 f1, White: a1 b1 c1; Black to move
+    assert int(s[0]["turn"]) == 0
+    assert _first_moves(s, o.DECISIVE_ANTI) == {3}
+    assert len(_first_moves(s, o.UNIFORM, n=256)) == 7  # (the uniform policy plays everything here)
+
+
+def test_anti_decisive_still_prefers_an_immediate_win():  # decisive_move.rs:39-61
+    """Black wins at d1 and White separately threatens g4: Black must take its own win rather than block."""
+    s = _c4_play([0, 6, 1, 6, 2, 6])  # Black: a1 b1 c1, White: g1 g2 g3
+    assert _first_moves(s, o.DECISIVE_ANTI) == {3}
+    assert _first_moves(s, o.DECISIVE_WIN) == {3}
+
+
+def test_nst_bigram_table_populated_by_backprop():  # mcts-tests/tests/ttt_strategies.rs:916-991
+    """A two-ply playout has exactly one consecutive pair: it lands in the SECOND mover's table with one visit, keyed by
+    (first action, second action), and the first mover's table stays empty."""
+    s = o.initial_state(o.CONNECT4)
+    mast = np.zeros((2, 7), dtype=o.STAT_DTYPE)
+    r = o.playout_batch(o.CONNECT4, s, 1, policy=o.EPS_NST, eps=0.1, seed=7, max_depth=2, mast=mast, want_trace=True, max_trace=2,
+                        want_bigram_delta=True)
+    assert int(r["records"][0]["depth"]) == 2
+    first, second = int(r["trace"][0][0]), int(r["trace"][0][1])
+    bg = r["bigram_delta"]
+    assert bg["visits"][1, first, second] == 1 and bg["visits"][1].sum() == 1
+    assert bg["visits"][0].sum() == 0  # not (mis)attributed to the other player's table
+
+
+def test_nst_backoff_falls_back_to_unigram_below_threshold():  # ttt_strategies.rs:993-1075
+    """Unigram favours column 1 (average 1.0 against 0.0 for column 0); the bigram in the context of the preceding action
+    favours column 0 but with too few samples.  (The KAT restricts `available` to the two moves; here the other five
+    columns are given the worst possible average instead.)"""
+    s = o.initial_state(o.CONNECT4).copy()
+    s["prev"] = 2 + 1  # the preceding action: column 2
+    mast = np.zeros((2, 7), dtype=o.STAT_DTYPE)
+    mast["visits"][0] = 10
+    mast["score"][0] = [0, 10, -10, -10, -10, -10, -10]
+    bigram = np.zeros((2, 7, 7), dtype=o.STAT_DTYPE)
+    bigram["visits"][0, 2, 0], bigram["score"][0, 2, 0] = 2, 2
+    bigram["visits"][0, 2, 1], bigram["score"][0, 2, 1] = 2, 0
+    kw = dict(eps=0.0, mast=mast, bigram=bigram)
+    assert _first_moves(s, o.EPS_NST, nst_threshold=5, **kw) == {1}  # 2 samples < 5: the unigram score decides
+    bigram["visits"][0, 2, 0], bigram["score"][0, 2, 0] = 5, 5
+    bigram["visits"][0, 2, 1] = 5
+    assert _first_moves(s, o.EPS_NST, nst_threshold=5, **kw) == {0}  # at the threshold the bigram score wins
+    s["prev"] = 0  # no preceding action (a playout straight from the root): always the unigram score
+    assert _first_moves(s, o.EPS_NST, nst_threshold=1, **kw) == {1}
