@@ -241,3 +241,41 @@ def test_search_prefers_the_centre_in_connect4():
         r = s.choose_action(mb.initial_state(mb.Game.CONNECT4))
     assert r.best_action == 3
     assert r.children["visits"].argmax() == 3
+
+
+# ---- the reference's leaf-parallel tests (mcts-tests/tests/ttt_strategies.rs:86-159), stated there on TicTacToe ----
+
+def _legal_root_actions(game):
+    return set(mb.generate_actions(mb.Game(game), mb.initial_state(mb.Game(game))))
+
+
+def test_leaf_parallel_picks_a_legal_action():  # ttt_strategies.rs:86-106: 200 iterations, num_rollouts_per_leaf = 4
+    with mb.GpuSearch(mb.Game.CONNECT4, mb.Uniform(), max_iterations=200, batch_leaves=1, num_rollouts_per_leaf=4, seed=1) as s:
+        r = s.choose_action(mb.initial_state(mb.Game.CONNECT4))
+    assert r.best_action in _legal_root_actions(o.CONNECT4) and r.playouts == 800
+
+
+def test_num_rollouts_per_leaf_one_is_deterministic_given_a_seed():  # ttt_strategies.rs:108-130
+    picks = []
+    for _ in range(2):
+        with mb.GpuSearch(mb.Game.CONNECT4, mb.Uniform(), max_iterations=200, batch_leaves=1, num_rollouts_per_leaf=1, seed=42) as s:
+            r = s.choose_action(mb.initial_state(mb.Game.CONNECT4))
+            picks.append((r.best_action, r.children.tobytes()))
+    assert picks[0] == picks[1]
+
+
+@pytest.mark.parametrize("batch", [1, 16])
+def test_leaf_parallel_virtual_loss_balances_across_many_iterations(batch):  # ttt_strategies.rs:132-159
+    """expand_threshold = 0 makes every descent run several levels deep, K = 3 adds two extra virtual losses per edge and
+    removes them over the three aggregated backprops: the root statistics must still equal the oracle loop's, which
+    applies the reference's per-trial accounting, and every playout must be accounted for."""
+    iters, k = 500, 3
+    root = o.initial_state(o.CONNECT4)
+    with mb.GpuSearch(mb.Game.CONNECT4, mb.Uniform(), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      expand_threshold=0, seed=9) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(o.CONNECT4, root, iterations=iters, batch_leaves=batch, k=k, expand_threshold=0, seed=9)
+    assert got.best_action in _legal_root_actions(o.CONNECT4)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    assert int(got.children["visits"].sum()) == iters * k  # with threshold 0 every descent passes through a root child
