@@ -36,8 +36,8 @@
 extern "C" {
 #endif
 
-#define MR_ABI_VERSION 1
-#define MR_NUM_SLOTS 2 /* double buffering: submit batch N+1 while batch N runs */
+#define MR_ABI_VERSION 2
+#define MR_NUM_SLOTS 4 /* batches in flight per ctx: each slot has its own stream; submit batch N+1.. while batch N runs */
 
 typedef struct mr_ctx mr_ctx;
 
@@ -48,7 +48,8 @@ enum mr_status {
     MR_ERR_NO_DEVICE = 3,   /* no CUDA device, or not compute capability 10.x */
     MR_ERR_BUSY = 4,        /* slot already has a batch in flight */
     MR_ERR_UNSUPPORTED = 5, /* game/policy/flag combination not built */
-    MR_ERR_COMM = 6         /* multi-process communicator failure */
+    MR_ERR_COMM = 6,        /* multi-process communicator failure */
+    MR_ERR_NO_MEMORY = 7    /* the host tree of mr_search could not allocate (nothing unwinds across the boundary) */
 };
 
 /* Games on the path.  Leaf layout per game is documented at mr_leaf. */
@@ -108,7 +109,12 @@ enum mr_flags {
     MR_WANT_AMAF = 1,        /* per-leaf AMAF/GRAVE occurrence table (every game) */
     MR_WANT_MAST_DELTA = 2,  /* batch-wide MAST (GLOBAL) table delta */
     MR_WANT_TRACE = 4,       /* parity/debug: per-playout move trace + record */
-    MR_WANT_FINAL_STATE = 8  /* parity/debug: per-playout final state */
+    MR_WANT_FINAL_STATE = 8, /* parity/debug: per-playout final state */
+    /* amaf_out / mast_delta_out (and d_amaf / d_mast_delta of mr_launch_device) are indexed by COMPACT per-player action
+     * slot, [2][mr_num_slots(game)], instead of by dense action id, [2][mr_num_actions(game)]: 192 / 512 instead of 4096
+     * entries per player for Breakthrough / Knightthrough (mr_action_slot / mr_slot_action convert); identical for the
+     * other games.  What a host tree or an all-reduce wants; the dense form is what the parity tests compare. */
+    MR_TABLES_IN_SLOTS = 16
 };
 
 /* TerminalStatus as utilities see it (mcts/src/game.rs:117-141). */
@@ -194,8 +200,11 @@ const char *mr_last_error(const mr_ctx *ctx); /* valid until the next call on ct
 int mr_num_devices(const mr_ctx *ctx);
 
 /* Asynchronous batch: copies `leaves` (and the MAST snapshot, mast_in = [2][mr_num_actions], required
- * for MR_EPS_MAST) into pinned staging before returning, enqueues H2D + kernels + D2H on the slot's
- * streams.  Replaces one `simulate_many` fan-out (search/core.rs:218-258) per leaf of the batch. */
+ * for MR_EPS_MAST) into pinned staging before returning and enqueues the batch on the slot's own stream, so up to
+ * MR_NUM_SLOTS batches are in flight and mr_wait(slot) waits for that slot's batch only.  Batches without the parity /
+ * LGR / NST outputs take the low-latency path: ONE kernel launch whose last block writes the results into host-mapped
+ * memory and raises a flag the host spins on (no separate memset / copy / synchronize calls).  Replaces one
+ * `simulate_many` fan-out (search/core.rs:218-258) per leaf of the batch. */
 int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *leaves,
               const mr_action_stat *mast_in);
 
@@ -205,6 +214,7 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
  *   amaf_out       [n_leaves][2][mr_num_actions]   (MR_WANT_AMAF; playout-trace occurrences only, the
  *                                                   tree-path suffix is added by the host, backprop.rs:833-854)
  *   mast_delta_out [2][mr_num_actions]             (MR_WANT_MAST_DELTA)
+ *                  with MR_TABLES_IN_SLOTS both tables are [..][2][mr_num_slots] instead
  *   trace_out      [n_leaves*k][max_trace] u16, rec_out [n_leaves*k]   (MR_WANT_TRACE)
  *   final_out      [n_leaves*k]                    (MR_WANT_FINAL_STATE) */
 int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out, mr_action_stat *mast_delta_out,
@@ -295,6 +305,9 @@ int mr_bigram_delta(mr_ctx *ctx, int slot, mr_action_stat *bigram_delta_out);
  * events on the launching stream; and the number of rollout-kernel launches the ctx has issued. */
 int mr_last_kernel_ms(mr_ctx *ctx, int slot, float *ms);
 uint64_t mr_kernel_launches(const mr_ctx *ctx);
+/* Kernel timing costs two event records per batch and, in mr_wait, a wait for the end event; latency-critical hosts
+ * (the search driver) switch it off: mr_last_kernel_ms then reports 0.  Enabled by default. */
+int mr_set_kernel_timing(mr_ctx *ctx, int enabled);
 
 /* Sums `n` int32 values element-wise across the devices/ranks of the search (the per-root-child
  * visit/score arrays of root-parallel search, search/parallel.rs:94-105).  Within one process it is a
@@ -330,14 +343,16 @@ enum mr_select {
                                  (node.rs:711-719), written by update_amaf (backprop.rs:565-617) from the same
                                  per-leaf occurrence tables */
 };
-enum mr_rave_schedule { MR_RAVE_HAND_SELECTED = 0, MR_RAVE_THRESHOLD = 1 }; /* select/rave.rs:42-76 */
+/* select/rave.rs:42-76: HandSelected sqrt(k / (3n + k)); Threshold max(0, rave - n) / rave;
+ * MinMSE amaf_n / (n + amaf_n + 4 n amaf_n bias^2) (rave_bias) */
+enum mr_rave_schedule { MR_RAVE_HAND_SELECTED = 0, MR_RAVE_THRESHOLD = 1, MR_RAVE_MIN_MSE = 2 };
 enum mr_qinit { MR_QINIT_PARENT = 0, MR_QINIT_INFINITY = 1 };     /* node.rs:95-159 */
 /* MR_SEARCH_TRANSPOSITIONS: SearchConfig.use_transpositions -- a new child whose state is already in the
  * table reuses that node (search/shared.rs:412-436, table.rs); statistics stay on the edges.  The table is
  * keyed by the full 40-byte state record (exact, no Zobrist collisions); symmetry canonicalisation is not
  * applied. */
-/* MR_SEARCH_PIPELINED: double-buffered driver over the two ABI slots -- batch N+1 is gathered (with batch N's
- * virtual losses still in place) and submitted before batch N's results are applied. */
+/* MR_SEARCH_PIPELINED: two batches in flight (= pipeline_depth 2) -- batch N+1 is gathered (with batch N's virtual
+ * losses still in place) and submitted before batch N's results are applied. */
 enum mr_search_flags { MR_SEARCH_TRANSPOSITIONS = 1, MR_SEARCH_PIPELINED = 2 };
 
 typedef struct {
@@ -359,6 +374,13 @@ typedef struct {
     uint32_t rave_param;        /* HandSelected k (default 1000) / Threshold rave */
     uint32_t nst_backoff_threshold; /* MR_EPS_NST: Nst::backoff_threshold (simulate.rs:875-881; the reference's default is 5) */
     double amaf_alpha;          /* MR_SELECT_AMAF: 1 = pure AMAF (the reference default), 0 = UCB1 */
+    double rave_bias;           /* MR_RAVE_MIN_MSE: RaveSchedule::MinMSE { bias } */
+    /* Batches in flight, 1..MR_NUM_SLOTS (0 = 1, or 2 with MR_SEARCH_PIPELINED).  Batch n is gathered and submitted
+     * before the results of batches n - depth + 1 .. n - 1 are applied: the host's select / backprop work overlaps the
+     * GPU, at the price of descents that see in-flight batches only as virtual losses (what the reference's
+     * tree-parallel workers see of each other, search/parallel.rs:188-251).  Deterministic for a given depth. */
+    uint32_t pipeline_depth;
+    uint32_t reserved;
 } mr_search_desc;
 
 typedef struct {
@@ -374,9 +396,10 @@ typedef struct {
     uint64_t nodes;
     uint32_t batches;
     uint32_t max_tree_depth;
-    double seconds_select;
-    double seconds_gpu;
-    double seconds_backprop;
+    double seconds_select;   /* host: descents (select_step) of all batches */
+    double seconds_gpu;      /* host time spent WAITING for batches (small when the pipeline hides the GPU) */
+    double seconds_backprop; /* host: aggregated backprop + table merges */
+    double seconds_submit;   /* host: mr_submit calls (staging copy, MAST ranking, kernel launch) */
 } mr_search_stats;
 
 /* The host-side `Game` surface the driver expands nodes with (generate_actions order == child order,
@@ -390,6 +413,43 @@ int mr_terminal_status(int game, const mr_leaf *state); /* mr_outcome */
  * select/basic.rs:13-45), the root children's statistics (children[MR_MAX_ROOT_CHILDREN]) and timing. */
 int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, uint16_t *best_action,
               mr_root_child *children, uint32_t *n_children, mr_search_stats *stats);
+
+/* Root-parallel search, choose_action_root_parallel (search/parallel.rs:56-115): `n_searchers` independent searches of
+ * `desc->max_iterations` iterations each, one host thread and one ctx (its own streams; the ctxs may share a GPU) per
+ * searcher, searcher i seeded from (desc->seed, i).  The root children's (visits, score) totals are summed per action and
+ * the action with the most merged visits wins (random_best).  children / n_children receive the MERGED totals in root
+ * action-list order, stats[n_searchers] each searcher's own counters. */
+int mr_search_root_parallel(mr_ctx *const *ctxs, int n_searchers, const mr_search_desc *desc, const mr_leaf *root,
+                            uint16_t *best_action, mr_root_child *children, uint32_t *n_children, mr_search_stats *stats);
+
+/* ---- Known-answer hooks ----
+ * The driver's selection formulas and its AMAF update, callable on hand-built inputs, so that the reference's own unit
+ * tests of this logic (mcts-tests/tests/ttt_strategies.rs:658-736 for update_amaf; the formulas of select/ucb.rs:40-146,
+ * select/rave.rs:60-75,196-224, select/amaf.rs:58-79) can be restated against the product code and not only against a
+ * twin implementation.  One row of a ChildArray / NodeStats (node.rs:295-302, 392-396, 673-719): */
+typedef struct {
+    uint32_t visits, vloss;
+    int64_t score[2];      /* sum of utilities per player */
+    int64_t sumsq[2];      /* sum of squared utilities per player */
+    uint32_t amaf_visits;
+    uint16_t action;       /* (out) compact action code of the child */
+    uint16_t created;      /* (out) the child node exists */
+    int64_t amaf_score[2];
+} mr_edge_stats;
+/* The value `player` (the mover at the current node) assigns to one child: `current` = the statistics of the node being
+ * left (root_stats, or the edge into it), `child` = the child's edge row, NULL = a child that does not exist yet
+ * (unvisited_value).  grave_n / grave_q = the reference node's AMAF count and score sum for (player, action), used by
+ * MR_SELECT_GRAVE only.  Reads select, q_init, exploration_c, rave_*, amaf_alpha of `desc`. */
+double mr_select_score(const mr_search_desc *desc, int player, const mr_edge_stats *current, const mr_edge_stats *child,
+                       uint32_t grave_n, int64_t grave_q);
+/* update_amaf (backprop.rs:565-617) on a two-level tree: `root` expanded, the children named in created[] and
+ * `processed` created, the descent path = root -> processed.  `amaf` is a per-leaf occurrence table as mr_wait returns
+ * it ([2][mr_num_actions]: per (player, action) the number of occurrences in the k trials and the sum of that player's
+ * utilities over them), utilities[p] the k trials' utility sums.  children_out[MR_MAX_ROOT_CHILDREN] receives every
+ * root child's AMAF row. */
+int mr_kat_update_amaf(int game, const mr_leaf *root, const uint16_t *created, uint32_t n_created, uint16_t processed,
+                       const mr_action_stat *amaf, const int64_t utilities[2], uint32_t k, mr_edge_stats *children_out,
+                       uint32_t *n_children);
 
 /* Integer-issue micro-benchmark used as the roofline denominator (DESIGN.md "Roofline"): runs a
  * dependent-chain kernel of `kind` (0 = LOP3, 1 = IADD3, 2 = SHF, 3 = IMAD, 4 = POPC, 5 = LOP3+IMAD mix)

@@ -15,7 +15,9 @@ from . import build as _build
 LIB_PATH = _build.LIB_PATH
 
 MR_OK = 0
-ERR_NAMES = {1: "MR_ERR_INVALID", 2: "MR_ERR_CUDA", 3: "MR_ERR_NO_DEVICE", 4: "MR_ERR_BUSY", 5: "MR_ERR_UNSUPPORTED", 6: "MR_ERR_COMM"}
+ERR_NAMES = {1: "MR_ERR_INVALID", 2: "MR_ERR_CUDA", 3: "MR_ERR_NO_DEVICE", 4: "MR_ERR_BUSY", 5: "MR_ERR_UNSUPPORTED", 6: "MR_ERR_COMM", 7: "MR_ERR_NO_MEMORY"}
+ABI_VERSION = 2
+NUM_SLOTS = 4
 
 LEAF_DTYPE = np.dtype([("board", "<u8", (4,)), ("turn", "u1"), ("flag", "u1"), ("prev", "<u2"), ("prev2", "<u2"), ("pad", "u1", (2,))])
 REPLY_UPDATE_DTYPE = np.dtype([("order", "<u8"), ("action_plus1", "<u2"), ("pad", "<u2", (3,))])
@@ -60,6 +62,9 @@ class SearchDesc(C.Structure):
         ("rave_param", C.c_uint32),
         ("nst_backoff_threshold", C.c_uint32),
         ("amaf_alpha", C.c_double),
+        ("rave_bias", C.c_double),
+        ("pipeline_depth", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -73,11 +78,15 @@ class SearchStats(C.Structure):
         ("seconds_select", C.c_double),
         ("seconds_gpu", C.c_double),
         ("seconds_backprop", C.c_double),
+        ("seconds_submit", C.c_double),
     ]
 
 
 ROOT_CHILD_DTYPE = np.dtype([("action", "<u2"), ("pad", "<u2"), ("visits", "<u4"), ("score", "<i8", (2,))])
 assert ROOT_CHILD_DTYPE.itemsize == 24
+EDGE_STATS_DTYPE = np.dtype([("visits", "<u4"), ("vloss", "<u4"), ("score", "<i8", (2,)), ("sumsq", "<i8", (2,)), ("amaf_visits", "<u4"),
+                             ("action", "<u2"), ("created", "<u2"), ("amaf_score", "<i8", (2,))])
+assert EDGE_STATS_DTYPE.itemsize == 64
 MAX_ROOT_CHILDREN = 256
 
 
@@ -112,12 +121,16 @@ EXPORTS = [
     "mr_bigram_delta",
     "mr_last_kernel_ms",
     "mr_kernel_launches",
+    "mr_set_kernel_timing",
     "mr_allreduce_root",
     "mr_comm_unique_id",
     "mr_comm_init",
     "mr_comm_allreduce_i32",
     "mr_measure_int_peak",
     "mr_search",
+    "mr_search_root_parallel",
+    "mr_select_score",
+    "mr_kat_update_amaf",
     "mr_generate_actions",
     "mr_apply",
     "mr_terminal_status",
@@ -173,6 +186,11 @@ def load() -> C.CDLL:
     L.mr_apply.argtypes = [i32, vp, C.c_uint16]
     L.mr_terminal_status.argtypes = [i32, vp]
     L.mr_search.argtypes = [vp, C.POINTER(SearchDesc), vp, C.POINTER(C.c_uint16), vp, C.POINTER(u32), C.POINTER(SearchStats)]
+    L.mr_set_kernel_timing.argtypes = [vp, i32]
+    L.mr_search_root_parallel.argtypes = [C.POINTER(vp), i32, C.POINTER(SearchDesc), vp, C.POINTER(C.c_uint16), vp, C.POINTER(u32), C.POINTER(SearchStats)]
+    L.mr_select_score.argtypes = [C.POINTER(SearchDesc), i32, vp, vp, u32, C.c_int64]
+    L.mr_select_score.restype = C.c_double
+    L.mr_kat_update_amaf.argtypes = [i32, vp, vp, u32, C.c_uint16, vp, vp, u32, vp, C.POINTER(u32)]
     _lib = L
     return L
 

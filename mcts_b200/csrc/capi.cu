@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "int_peak.cuh"
@@ -40,8 +41,9 @@ const GameInfo kGames[MR_NUM_GAMES] = {
 template <class T>
 struct DevBuf {
     T *d = nullptr;
-    T *h = nullptr; // pinned
+    T *h = nullptr; // pinned (host-mapped under UVA: the device can read / write it directly)
     size_t cap = 0;
+    bool fresh = false; // set when reserve() (re)allocated: the contents are undefined
     cudaError_t reserve(size_t n, bool want_host) {
         if (n <= cap && (!want_host || h)) return cudaSuccess;
         size_t ncap = std::max(n, cap);
@@ -49,15 +51,22 @@ struct DevBuf {
             if (d) cudaFree(d);
             d = nullptr;
             cudaError_t e = cudaMalloc(&d, ncap * sizeof(T));
-            if (e != cudaSuccess) return e;
+            if (e != cudaSuccess) {
+                release(); // a failed allocation leaves an EMPTY buffer, never a capacity without memory behind it
+                return e;
+            }
         }
         if (want_host && (n > cap || !h)) {
             if (h) cudaFreeHost(h);
             h = nullptr;
             cudaError_t e = cudaMallocHost(&h, ncap * sizeof(T));
-            if (e != cudaSuccess) return e;
+            if (e != cudaSuccess) {
+                release();
+                return e;
+            }
         }
         cap = ncap;
+        fresh = true;
         return cudaSuccess;
     }
     void release() {
@@ -93,6 +102,16 @@ struct SlotDev {
     DevBuf<unsigned long long> nst_delta;   // MR_EPS_NST: [2][S][S] packed (visits | score << 32)
     unsigned long long *d_counter = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaStream_t stream = nullptr;  // the slot's own stream: batches of different slots are independent
+    cudaEvent_t ev_done = nullptr;  // after the slot's last enqueued operation
+    // low-latency path (fused epilogue, common.cuh batch_epilogue)
+    unsigned int *d_done = nullptr; // ticket counter of the blocks that have finished
+    uint32_t *flag_h = nullptr;     // host-mapped: the epilogue publishes the batch's sequence number here
+    uint32_t seq = 0;               // sequence number of the last batch submitted on the fast path
+    bool fast = false;              // the batch in flight uses the fused epilogue
+    bool wait_event = false;        // its completion is ev_done (else: the host flag)
+    // whole-buffer-is-zero invariants of the fast path (the epilogue re-zeroes what a batch touched)
+    bool results_clean = false, mast_clean = false, amaf_clean = false, counter_clean = false;
     // what this device covers for the batch in flight
     uint64_t g_begin = 0, g_end = 0; // global playout index range
 };
@@ -125,6 +144,8 @@ struct mr_ctx {
     SlotState slot[MR_NUM_SLOTS];
     std::string error;
     uint64_t launches = 0;
+    bool timing = true; // record kernel begin / end events per batch (mr_last_kernel_ms); the search driver turns it off
+    std::unordered_map<const void *, int> occupancy; // kernel -> resident blocks per SM (queried once)
     // MAST snapshot as rank bit-planes (copied into KernelParams at launch)
     uint64_t mast_planes[2][MAST_KINDS][MAST_BITS] = {};
     uint32_t mast_nbits[2] = {0, 0};
@@ -422,7 +443,7 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
     if (d->game >= MR_NUM_GAMES) return fail(ctx, MR_ERR_INVALID, "unknown game %u", d->game);
     if (d->n_leaves == 0 || d->playouts_per_leaf == 0)
         return fail(ctx, MR_ERR_INVALID, "empty batch (n_leaves=%u, playouts_per_leaf=%u)", d->n_leaves, d->playouts_per_leaf);
-    if (d->flags & ~15u) return fail(ctx, MR_ERR_INVALID, "unknown flags 0x%x", d->flags);
+    if (d->flags & ~31u) return fail(ctx, MR_ERR_INVALID, "unknown flags 0x%x", d->flags);
     kernel_fn fn = pick_kernel((int)d->game, (int)d->policy, flag_variant(d->flags), d->flags);
     if (!fn) return fail(ctx, MR_ERR_UNSUPPORTED, "policy %u is not built for game %u", d->policy, d->game);
     if (policy_uses_mast((int)d->policy)) {
@@ -459,6 +480,9 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
     return MR_OK;
 }
 
+// entries per player of the AMAF / MAST-delta tables of a batch: dense action ids, or compact slots
+inline int table_len(const mr_batch_desc *d) { return (d->flags & MR_TABLES_IN_SLOTS) ? kSlots[d->game] : kGames[d->game].num_actions; }
+
 struct LaunchPlan {
     int blocks_per_sm;
 };
@@ -466,11 +490,15 @@ struct LaunchPlan {
 int plan_launch(mr_ctx *ctx, const Device &dv, kernel_fn fn, const mr_batch_desc *d, int n_devices, LaunchPlan *lp) {
     (void)d;
     (void)n_devices;
-    int bps = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, THREADS_PER_BLOCK, 0));
-    if (bps < 1) return fail(ctx, MR_ERR_CUDA, "kernel does not fit on an SM");
     (void)dv;
-    lp->blocks_per_sm = bps;
+    auto it = ctx->occupancy.find((const void *)fn);
+    if (it == ctx->occupancy.end()) {
+        int bps = 0;
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, THREADS_PER_BLOCK, 0));
+        if (bps < 1) return fail(ctx, MR_ERR_CUDA, "kernel does not fit on an SM");
+        it = ctx->occupancy.emplace((const void *)fn, bps).first;
+    }
+    lp->blocks_per_sm = it->second;
     return MR_OK;
 }
 
@@ -497,10 +525,12 @@ void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, co
     kp.max_trace = d->max_trace;
     kp.trace_cap = trace_cap;
     kp.grab_div = 2;
+    kp.tables_in_slots = (d->flags & MR_TABLES_IN_SLOTS) ? 1u : 0u;
+    kp.amaf_stride = 2u * (uint32_t)table_len(d);
 }
 
 int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const LaunchPlan &lp, cudaStream_t stream,
-              unsigned long long *d_counter, int scratch_slot) {
+              unsigned long long *d_counter, int scratch_slot, bool reset_counter = true) {
     const uint64_t work = kp.g_end - kp.g_begin;
     if (work == 0) return MR_OK;
     uint32_t blocks = (uint32_t)dv.num_sms * lp.blocks_per_sm;
@@ -516,9 +546,10 @@ int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const Lau
         kp.grab_max = chunk;
         kp.grab_min = chunk >= 128 ? chunk / 4 : 32;
     }
-    if (const char *e = getenv("MR_GRAB_MIN")) kp.grab_min = (uint32_t)atoi(e) & ~31u; // tuning knobs
-    if (const char *e = getenv("MR_GRAB_MAX")) kp.grab_max = (uint32_t)atoi(e) & ~31u;
-    if (const char *e = getenv("MR_GRAB_DIV")) kp.grab_div = (uint32_t)atoi(e);
+    static const char *env_min = getenv("MR_GRAB_MIN"), *env_max = getenv("MR_GRAB_MAX"), *env_div = getenv("MR_GRAB_DIV"); // tuning knobs
+    if (env_min) kp.grab_min = (uint32_t)atoi(env_min) & ~31u;
+    if (env_max) kp.grab_max = (uint32_t)atoi(env_max) & ~31u;
+    if (env_div) kp.grab_div = (uint32_t)atoi(env_div);
     if (kp.grab_min < 32) kp.grab_min = 32;
     if (kp.grab_max < kp.grab_min) kp.grab_max = kp.grab_min;
     if (kp.trace_cap) {
@@ -527,7 +558,7 @@ int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const Lau
         kp.trace_scratch = dv.scratch[scratch_slot].d;
     }
     kp.work_counter = d_counter;
-    CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
+    if (reset_counter) CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
     fn<<<blocks, THREADS_PER_BLOCK, 0, stream>>>(kp);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
@@ -586,11 +617,16 @@ int mr_init(const int *device_ids, int n_devices, mr_ctx **out) {
         for (int s = 0; s < MR_NUM_SLOTS; ++s) {
             SlotDev &sd = dv.slot[s];
             if (cudaMalloc(&sd.d_counter, sizeof(unsigned long long)) != cudaSuccess || cudaEventCreate(&sd.ev_begin) != cudaSuccess ||
-                cudaEventCreate(&sd.ev_end) != cudaSuccess) {
+                cudaEventCreate(&sd.ev_end) != cudaSuccess || cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&sd.ev_done, cudaEventDisableTiming) != cudaSuccess ||
+                cudaMalloc(&sd.d_done, sizeof(unsigned int)) != cudaSuccess || cudaMallocHost(&sd.flag_h, 64) != cudaSuccess ||
+                cudaMemset(sd.d_done, 0, sizeof(unsigned int)) != cudaSuccess || cudaMemset(sd.d_counter, 0, sizeof(unsigned long long)) != cudaSuccess) {
                 int rc = fail(nullptr, MR_ERR_CUDA, "slot setup failed on device %d", dv.id);
                 mr_destroy(ctx);
                 return rc;
             }
+            *sd.flag_h = 0;
+            sd.counter_clean = true;
         }
     }
     *out = ctx;
@@ -604,6 +640,13 @@ void mr_destroy(mr_ctx *ctx) {
         if (dv.stream) cudaStreamSynchronize(dv.stream);
         for (int s = 0; s < MR_NUM_SLOTS; ++s) {
             SlotDev &sd = dv.slot[s];
+            if (sd.stream) {
+                cudaStreamSynchronize(sd.stream);
+                cudaStreamDestroy(sd.stream);
+            }
+            if (sd.ev_done) cudaEventDestroy(sd.ev_done);
+            if (sd.d_done) cudaFree(sd.d_done);
+            if (sd.flag_h) cudaFreeHost(sd.flag_h);
             sd.leaves.release();
             sd.results.release();
             sd.amaf.release();
@@ -685,42 +728,77 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
     CUDA_TRY(ctx, cudaSetDevice(ctx->dev[0].id));
     rc = plan_launch(ctx, ctx->dev[0], fn, desc, nd, &lp);
     if (rc != MR_OK) return rc;
+    const int tl = table_len(desc); // entries per player of the AMAF / MAST-delta tables
     const int na = kGames[desc->game].num_actions;
     const uint32_t n = desc->n_leaves, k = desc->playouts_per_leaf;
     const uint64_t total = (uint64_t)n * k;
+    // Low-latency path: no parity outputs, no LGR / NST side tables -> one kernel launch whose fused epilogue delivers
+    // the results (and the MAST delta) into host-mapped memory.  Small batches also READ their leaves from the
+    // host-mapped staging buffer, so nothing but the launch is enqueued.
+    const bool fast = !(desc->flags & (MR_WANT_TRACE | MR_WANT_FINAL_STATE)) && !policy_is_lgr((int)desc->policy) && desc->policy != MR_EPS_NST;
+    static const uint64_t zero_copy_max = getenv("MR_ZERO_COPY_MAX") ? strtoull(getenv("MR_ZERO_COPY_MAX"), nullptr, 10) : (1ull << 20);
+    const bool zero_copy = fast && total <= zero_copy_max;
 
     for (int di = 0; di < nd; ++di) {
         Device &dv = ctx->dev[(size_t)di];
         SlotDev &sd = dv.slot[slot];
+        cudaStream_t stream = sd.stream;
         CUDA_TRY(ctx, cudaSetDevice(dv.id));
         sd.g_begin = total * (uint64_t)di / (uint64_t)nd;
         sd.g_end = total * (uint64_t)(di + 1) / (uint64_t)nd;
+        sd.fast = fast;
+        sd.wait_event = !fast;
+        if (sd.g_end == sd.g_begin) continue; // nothing for this device: mr_wait skips it
 
         CUDA_TRY(ctx, sd.leaves.reserve(n, true));
         CUDA_TRY(ctx, sd.results.reserve(n, true));
+        if (sd.results.fresh) sd.results_clean = false;
+        sd.results.fresh = false;
         memcpy(sd.leaves.h, leaves, sizeof(mr_leaf) * n);
-        CUDA_TRY(ctx, cudaMemcpyAsync(sd.leaves.d, sd.leaves.h, sizeof(mr_leaf) * n, cudaMemcpyHostToDevice, dv.stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(sd.results.d, 0, sizeof(mr_leaf_result) * n, dv.stream));
+        if (!zero_copy) CUDA_TRY(ctx, cudaMemcpyAsync(sd.leaves.d, sd.leaves.h, sizeof(mr_leaf) * n, cudaMemcpyHostToDevice, stream));
+        if (fast) {
+            if (!sd.results_clean) CUDA_TRY(ctx, cudaMemsetAsync(sd.results.d, 0, sizeof(mr_leaf_result) * sd.results.cap, stream));
+            sd.results_clean = true; // the epilogue re-zeroes the entries the batch touched
+        } else {
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.results.d, 0, sizeof(mr_leaf_result) * n, stream));
+            sd.results_clean = false;
+        }
         KernelParams kp;
         fill_params(ctx, kp, desc, lp, trace_cap);
-        kp.leaves = sd.leaves.d;
+        kp.leaves = zero_copy ? sd.leaves.h : sd.leaves.d;
         kp.results = sd.results.d;
         kp.g_begin = sd.g_begin;
         kp.g_end = sd.g_end;
         if (desc->flags & MR_WANT_AMAF) {
-            CUDA_TRY(ctx, sd.amaf.reserve((size_t)n * 2 * na, true));
-            CUDA_TRY(ctx, cudaMemsetAsync(sd.amaf.d, 0, sizeof(mr_action_stat) * n * 2 * na, dv.stream));
+            CUDA_TRY(ctx, sd.amaf.reserve((size_t)n * 2 * tl, true));
+            if (sd.amaf.fresh) sd.amaf_clean = false;
+            sd.amaf.fresh = false;
+            if (fast) { // zeroed again behind the copy-out below, off the next batch's critical path
+                if (!sd.amaf_clean) CUDA_TRY(ctx, cudaMemsetAsync(sd.amaf.d, 0, sizeof(mr_action_stat) * sd.amaf.cap, stream));
+                sd.amaf_clean = true;
+            } else {
+                CUDA_TRY(ctx, cudaMemsetAsync(sd.amaf.d, 0, sizeof(mr_action_stat) * n * 2 * tl, stream));
+                sd.amaf_clean = false;
+            }
             kp.amaf = sd.amaf.d;
         }
         if (desc->flags & MR_WANT_MAST_DELTA) {
-            CUDA_TRY(ctx, sd.mast_delta.reserve((size_t)2 * na, true));
-            CUDA_TRY(ctx, cudaMemsetAsync(sd.mast_delta.d, 0, sizeof(mr_action_stat) * 2 * na, dv.stream));
+            CUDA_TRY(ctx, sd.mast_delta.reserve((size_t)2 * na, true)); // (always the dense size: the buffer serves both forms)
+            if (sd.mast_delta.fresh) sd.mast_clean = false;
+            sd.mast_delta.fresh = false;
+            if (fast) {
+                if (!sd.mast_clean) CUDA_TRY(ctx, cudaMemsetAsync(sd.mast_delta.d, 0, sizeof(mr_action_stat) * sd.mast_delta.cap, stream));
+                sd.mast_clean = true;
+            } else {
+                CUDA_TRY(ctx, cudaMemsetAsync(sd.mast_delta.d, 0, sizeof(mr_action_stat) * 2 * tl, stream));
+                sd.mast_clean = false;
+            }
             kp.mast_delta = sd.mast_delta.d;
         }
         if (desc->flags & MR_WANT_TRACE) {
             CUDA_TRY(ctx, sd.trace.reserve((size_t)total * desc->max_trace, true));
             CUDA_TRY(ctx, sd.rec.reserve((size_t)total, true));
-            CUDA_TRY(ctx, cudaMemsetAsync(sd.trace.d, 0, sizeof(uint16_t) * total * desc->max_trace, dv.stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.trace.d, 0, sizeof(uint16_t) * total * desc->max_trace, stream));
             kp.trace = sd.trace.d;
             kp.rec = sd.rec.d;
         }
@@ -732,14 +810,14 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             const size_t cnt = (size_t)2 * na;
             CUDA_TRY(ctx, sd.lgr_stamps.reserve(cnt, true));
             CUDA_TRY(ctx, sd.lgr_last.reserve((size_t)2 * n, true));
-            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr_stamps.d, 0, sizeof(unsigned long long) * cnt, dv.stream));
-            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr_last.d, 0, sizeof(uint32_t) * 2 * n, dv.stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr_stamps.d, 0, sizeof(unsigned long long) * cnt, stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr_last.d, 0, sizeof(uint32_t) * 2 * n, stream));
             kp.lgr_stamps = sd.lgr_stamps.d;
             kp.lgr_last = sd.lgr_last.d;
             if (!ctx->replies.empty()) {
                 CUDA_TRY(ctx, sd.lgr_in.reserve(cnt, true));
                 memcpy(sd.lgr_in.h, ctx->replies.data(), sizeof(uint16_t) * cnt);
-                CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_in.d, sd.lgr_in.h, sizeof(uint16_t) * cnt, cudaMemcpyHostToDevice, dv.stream));
+                CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_in.d, sd.lgr_in.h, sizeof(uint16_t) * cnt, cudaMemcpyHostToDevice, stream));
                 kp.lgr_in = sd.lgr_in.d;
             }
         }
@@ -747,14 +825,14 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             const size_t S = (size_t)kSlots[desc->game], cnt2 = 2 * S * S;
             CUDA_TRY(ctx, sd.lgr2_stamps.reserve(cnt2, true));
             CUDA_TRY(ctx, sd.lgr2_last_lose.reserve((size_t)2 * n, true));
-            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_stamps.d, 0, sizeof(unsigned long long) * cnt2, dv.stream));
-            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_last_lose.d, 0, sizeof(uint32_t) * 2 * n, dv.stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_stamps.d, 0, sizeof(unsigned long long) * cnt2, stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_last_lose.d, 0, sizeof(uint32_t) * 2 * n, stream));
             kp.lgr2_stamps = sd.lgr2_stamps.d;
             kp.lgr2_last_lose = sd.lgr2_last_lose.d;
             if (!ctx->replies2.empty()) {
                 CUDA_TRY(ctx, sd.lgr2_in.reserve(cnt2, true));
                 memcpy(sd.lgr2_in.h, ctx->replies2.data(), sizeof(uint16_t) * cnt2);
-                CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_in.d, sd.lgr2_in.h, sizeof(uint16_t) * cnt2, cudaMemcpyHostToDevice, dv.stream));
+                CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_in.d, sd.lgr2_in.h, sizeof(uint16_t) * cnt2, cudaMemcpyHostToDevice, stream));
                 kp.lgr2_in = sd.lgr2_in.d;
             }
         }
@@ -767,52 +845,67 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
             memcpy(sd.nst_planes.h, ctx->nst_planes.data(), sizeof(uint64_t) * ctx->nst_planes.size());
             memcpy(sd.nst_nbits.h, ctx->nst_nbits.data(), sizeof(uint32_t) * ctx->nst_nbits.size());
             memcpy(sd.nst_rank_small.h, ctx->nst_rank_small.data(), sizeof(uint16_t) * ctx->nst_rank_small.size());
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_planes.d, sd.nst_planes.h, sizeof(uint64_t) * ctx->nst_planes.size(), cudaMemcpyHostToDevice, dv.stream));
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_nbits.d, sd.nst_nbits.h, sizeof(uint32_t) * ctx->nst_nbits.size(), cudaMemcpyHostToDevice, dv.stream));
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_rank_small.d, sd.nst_rank_small.h, sizeof(uint16_t) * ctx->nst_rank_small.size(), cudaMemcpyHostToDevice, dv.stream));
-            CUDA_TRY(ctx, cudaMemsetAsync(sd.nst_delta.d, 0, sizeof(unsigned long long) * 2 * S * S, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_planes.d, sd.nst_planes.h, sizeof(uint64_t) * ctx->nst_planes.size(), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_nbits.d, sd.nst_nbits.h, sizeof(uint32_t) * ctx->nst_nbits.size(), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_rank_small.d, sd.nst_rank_small.h, sizeof(uint16_t) * ctx->nst_rank_small.size(), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(sd.nst_delta.d, 0, sizeof(unsigned long long) * 2 * S * S, stream));
             kp.nst_planes = sd.nst_planes.d;
             kp.nst_nbits = sd.nst_nbits.d;
             kp.nst_rank_small = sd.nst_rank_small.d;
             kp.nst_delta = sd.nst_delta.d;
         }
-        CUDA_TRY(ctx, cudaEventRecord(sd.ev_begin, dv.stream));
-        rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter, slot);
+        if (fast) {
+            kp.done_counter = sd.d_done;
+            kp.host_results = sd.results.h;
+            kp.host_mast_delta = (desc->flags & MR_WANT_MAST_DELTA) ? sd.mast_delta.h : nullptr;
+            kp.mast_delta_len = (desc->flags & MR_WANT_MAST_DELTA) ? 2u * (uint32_t)tl : 0u;
+            kp.done_seq = ++sd.seq;
+            kp.host_flag = sd.flag_h;
+        }
+        if (ctx->timing) CUDA_TRY(ctx, cudaEventRecord(sd.ev_begin, stream));
+        rc = launch_on(ctx, dv, fn, kp, lp, stream, sd.d_counter, slot, !(fast && sd.counter_clean));
         if (rc != MR_OK) return rc;
-        CUDA_TRY(ctx, cudaEventRecord(sd.ev_end, dv.stream));
+        sd.counter_clean = fast; // the epilogue resets the work counter; the other kernels leave it at the batch size
+        if (ctx->timing) CUDA_TRY(ctx, cudaEventRecord(sd.ev_end, stream));
         sd.kp_saved = kp;
 
+        if (fast) {
+            if (desc->flags & MR_WANT_AMAF) { // the one large output: copied out (and zeroed again) behind the kernel
+                CUDA_TRY(ctx, cudaMemcpyAsync(sd.amaf.h, sd.amaf.d, sizeof(mr_action_stat) * n * 2 * tl, cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(ctx, cudaMemsetAsync(sd.amaf.d, 0, sizeof(mr_action_stat) * n * 2 * tl, stream));
+                CUDA_TRY(ctx, cudaEventRecord(sd.ev_done, stream));
+                sd.wait_event = true;
+            }
+            continue;
+        }
         // results come back on the same stream
-        CUDA_TRY(ctx, cudaMemcpyAsync(sd.results.h, sd.results.d, sizeof(mr_leaf_result) * n, cudaMemcpyDeviceToHost, dv.stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(sd.results.h, sd.results.d, sizeof(mr_leaf_result) * n, cudaMemcpyDeviceToHost, stream));
         if (desc->flags & MR_WANT_AMAF)
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.amaf.h, sd.amaf.d, sizeof(mr_action_stat) * n * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.amaf.h, sd.amaf.d, sizeof(mr_action_stat) * n * 2 * tl, cudaMemcpyDeviceToHost, stream));
         if (desc->flags & MR_WANT_MAST_DELTA)
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.mast_delta.h, sd.mast_delta.d, sizeof(mr_action_stat) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.mast_delta.h, sd.mast_delta.d, sizeof(mr_action_stat) * 2 * tl, cudaMemcpyDeviceToHost, stream));
         if (policy_is_lgr2((int)desc->policy)) {
             const size_t S = (size_t)kSlots[desc->game];
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_stamps.h, sd.lgr2_stamps.d, sizeof(unsigned long long) * 2 * S * S, cudaMemcpyDeviceToHost, dv.stream));
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_last_lose.h, sd.lgr2_last_lose.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_stamps.h, sd.lgr2_stamps.d, sizeof(unsigned long long) * 2 * S * S, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_last_lose.h, sd.lgr2_last_lose.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, stream));
         }
         if (policy_is_lgr((int)desc->policy)) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_stamps.h, sd.lgr_stamps.d, sizeof(unsigned long long) * 2 * na, cudaMemcpyDeviceToHost, dv.stream));
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_last.h, sd.lgr_last.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_stamps.h, sd.lgr_stamps.d, sizeof(unsigned long long) * 2 * na, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr_last.h, sd.lgr_last.d, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, stream));
         }
         if (desc->policy == MR_EPS_NST) {
             const size_t S = (size_t)kSlots[desc->game];
-            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_delta.h, sd.nst_delta.d, sizeof(unsigned long long) * 2 * S * S, cudaMemcpyDeviceToHost, dv.stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.nst_delta.h, sd.nst_delta.d, sizeof(unsigned long long) * 2 * S * S, cudaMemcpyDeviceToHost, stream));
         }
         const uint64_t gb = sd.g_begin, ge = sd.g_end;
-        if (ge > gb) {
-            if (desc->flags & MR_WANT_TRACE) {
-                CUDA_TRY(ctx, cudaMemcpyAsync(sd.trace.h + gb * desc->max_trace, sd.trace.d + gb * desc->max_trace,
-                                              sizeof(uint16_t) * (ge - gb) * desc->max_trace, cudaMemcpyDeviceToHost, dv.stream));
-                CUDA_TRY(ctx, cudaMemcpyAsync(sd.rec.h + gb, sd.rec.d + gb, sizeof(mr_playout_record) * (ge - gb),
-                                              cudaMemcpyDeviceToHost, dv.stream));
-            }
-            if (desc->flags & MR_WANT_FINAL_STATE)
-                CUDA_TRY(ctx, cudaMemcpyAsync(sd.final_state.h + gb, sd.final_state.d + gb, sizeof(mr_leaf) * (ge - gb),
-                                              cudaMemcpyDeviceToHost, dv.stream));
+        if (desc->flags & MR_WANT_TRACE) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.trace.h + gb * desc->max_trace, sd.trace.d + gb * desc->max_trace,
+                                          sizeof(uint16_t) * (ge - gb) * desc->max_trace, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.rec.h + gb, sd.rec.d + gb, sizeof(mr_playout_record) * (ge - gb), cudaMemcpyDeviceToHost, stream));
         }
+        if (desc->flags & MR_WANT_FINAL_STATE)
+            CUDA_TRY(ctx, cudaMemcpyAsync(sd.final_state.h + gb, sd.final_state.d + gb, sizeof(mr_leaf) * (ge - gb), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(ctx, cudaEventRecord(sd.ev_done, stream));
     }
     ss.busy = true;
     ss.lgr_ready = false;
@@ -823,6 +916,33 @@ int mr_submit(mr_ctx *ctx, int slot, const mr_batch_desc *desc, const mr_leaf *l
     return MR_OK;
 }
 
+// Waits for one device's share of the slot's batch.  Fast path: spin on the host-mapped flag the fused epilogue raises
+// (a PCIe write away from the kernel's last instruction); otherwise poll the slot's completion event.  Either way no
+// other slot's work is waited for.
+static int wait_slot_device(mr_ctx *ctx, Device &dv, SlotDev &sd) {
+    CUDA_TRY(ctx, cudaSetDevice(dv.id));
+    if (sd.wait_event) {
+        for (;;) {
+            cudaError_t e = cudaEventQuery(sd.ev_done);
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorNotReady) return fail(ctx, MR_ERR_CUDA, "batch failed: %s", cudaGetErrorString(e));
+            __builtin_ia32_pause();
+        }
+        return MR_OK;
+    }
+    const uint32_t want = sd.seq;
+    for (uint64_t spins = 0;; ++spins) {
+        if (__atomic_load_n(sd.flag_h, __ATOMIC_ACQUIRE) == want) return MR_OK;
+        __builtin_ia32_pause();
+        if ((spins & 0xfffffu) == 0xfffffu) { // every ~1M spins: a faulted kernel never raises the flag
+            cudaError_t e = cudaStreamQuery(sd.stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return fail(ctx, MR_ERR_CUDA, "batch failed: %s", cudaGetErrorString(e));
+            if (e == cudaSuccess && __atomic_load_n(sd.flag_h, __ATOMIC_ACQUIRE) != want)
+                return fail(ctx, MR_ERR_CUDA, "batch finished without publishing its results (flag %u, expected %u)", *sd.flag_h, want);
+        }
+    }
+}
+
 int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out, mr_action_stat *mast_delta_out,
             uint16_t *trace_out, mr_playout_record *rec_out, mr_leaf *final_out) {
     if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
@@ -831,16 +951,18 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
     if (!ss.busy) return fail(ctx, MR_ERR_INVALID, "slot %d has no batch in flight", slot);
     if (!out) return fail(ctx, MR_ERR_INVALID, "null result buffer");
     const mr_batch_desc &d = ss.desc;
-    const int na = kGames[d.game].num_actions;
+    const int na = table_len(&d); // entries per player of the two tables (dense ids or slots)
     const uint32_t n = d.n_leaves;
     ss.busy = false; // whatever happens below, the slot is released
     float worst_ms = 0.f;
     for (Device &dv : ctx->dev) {
-        CUDA_TRY(ctx, cudaSetDevice(dv.id));
-        CUDA_TRY(ctx, cudaStreamSynchronize(dv.stream));
         SlotDev &sd = dv.slot[slot];
-        if (sd.g_end > sd.g_begin) {
+        if (sd.g_end == sd.g_begin) continue;
+        int rc = wait_slot_device(ctx, dv, sd);
+        if (rc != MR_OK) return rc;
+        if (ctx->timing) {
             float ms = 0.f;
+            CUDA_TRY(ctx, cudaEventSynchronize(sd.ev_end)); // (the fused epilogue raises its flag before the event completes)
             CUDA_TRY(ctx, cudaEventElapsedTime(&ms, sd.ev_begin, sd.ev_end));
             worst_ms = std::max(worst_ms, ms);
         }
@@ -1012,9 +1134,9 @@ int mr_reply2_resolve(mr_ctx *ctx, int slot, const mr_reply_update *merged, uint
         CUDA_TRY(ctx, sd.lgr2_removed.reserve(cnt, true));
         CUDA_TRY(ctx, sd.results2.reserve(d.n_leaves, false));
         memcpy(sd.lgr2_target.h, target.data(), sizeof(unsigned long long) * cnt);
-        CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_target.d, sd.lgr2_target.h, sizeof(unsigned long long) * cnt, cudaMemcpyHostToDevice, dv.stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_removed.d, 0, cnt, dv.stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(sd.results2.d, 0, sizeof(mr_leaf_result) * d.n_leaves, dv.stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_target.d, sd.lgr2_target.h, sizeof(unsigned long long) * cnt, cudaMemcpyHostToDevice, sd.stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(sd.lgr2_removed.d, 0, cnt, sd.stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(sd.results2.d, 0, sizeof(mr_leaf_result) * d.n_leaves, sd.stream));
         // the same playouts again (same leaves, tables, seed and range), with every other output switched off
         KernelParams kp = sd.kp_saved;
         kp.results = sd.results2.d;
@@ -1029,15 +1151,16 @@ int mr_reply2_resolve(mr_ctx *ctx, int slot, const mr_reply_update *merged, uint
         kp.lgr2_last_lose = nullptr;
         kp.lgr2_target = sd.lgr2_target.d;
         kp.lgr2_removed = sd.lgr2_removed.d;
-        rc = launch_on(ctx, dv, fn, kp, lp, dv.stream, sd.d_counter, slot);
+        rc = launch_on(ctx, dv, fn, kp, lp, sd.stream, sd.d_counter, slot);
+        sd.counter_clean = false;
         if (rc != MR_OK) return rc;
-        CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_removed.h, sd.lgr2_removed.d, cnt, cudaMemcpyDeviceToHost, dv.stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(sd.lgr2_removed.h, sd.lgr2_removed.d, cnt, cudaMemcpyDeviceToHost, sd.stream));
     }
     for (Device &dv : ctx->dev) {
         SlotDev &sd = dv.slot[slot];
         if (sd.g_end == sd.g_begin) continue;
         CUDA_TRY(ctx, cudaSetDevice(dv.id));
-        CUDA_TRY(ctx, cudaStreamSynchronize(dv.stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(sd.stream));
         for (size_t i = 0; i < cnt; ++i) removed_out[i] |= sd.lgr2_removed.h[i];
     }
     return MR_OK;
@@ -1139,6 +1262,12 @@ int mr_last_kernel_ms(mr_ctx *ctx, int slot, float *ms) {
 }
 
 uint64_t mr_kernel_launches(const mr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int mr_set_kernel_timing(mr_ctx *ctx, int enabled) {
+    if (!ctx) return fail(nullptr, MR_ERR_INVALID, "null ctx");
+    ctx->timing = enabled != 0;
+    return MR_OK;
+}
 
 int mr_allreduce_root(mr_ctx *ctx, int32_t *const *bufs, int n_bufs, size_t n) {
     if (!ctx || !bufs || n_bufs <= 0) return fail(ctx, MR_ERR_INVALID, "mr_allreduce_root: bad arguments");

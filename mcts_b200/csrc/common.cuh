@@ -93,6 +93,20 @@ struct KernelParams {
     const uint32_t *nst_nbits;       // [2][NSLOTS + 1]
     const uint16_t *nst_rank_small;  // Connect4: [2][NSLOTS + 1][8] ranks per column
     unsigned long long *nst_delta;   // [2][NSLOTS][NSLOTS]: visits in the low word, score (two's complement) in the high word
+    // MR_TABLES_IN_SLOTS: amaf / mast_delta are indexed [2][NSLOTS] by compact per-player action slot instead of
+    // [2][NA] by dense action id (192 / 512 instead of 4096 entries per player for Breakthrough / Knightthrough)
+    uint32_t tables_in_slots;
+    uint32_t amaf_stride;      // entries per leaf in `amaf`: 2 * NA, or 2 * NSLOTS with tables_in_slots
+    // Fused epilogue of the low-latency submit path (batch_epilogue below), active when done_counter != nullptr: the
+    // last block to finish copies the per-leaf results and the MAST delta into HOST-mapped memory, re-zeroes the device
+    // copies and the two counters for the next batch, and publishes done_seq in *host_flag -- one kernel launch per
+    // batch, no memset / copy / synchronize calls around it; the host spins on the flag.
+    unsigned int *done_counter;
+    mr_leaf_result *host_results;     // [n_leaves], host-mapped
+    mr_action_stat *host_mast_delta;  // [mast_delta_len], host-mapped (nullptr without a MAST delta)
+    uint32_t mast_delta_len;
+    uint32_t done_seq;
+    volatile uint32_t *host_flag;
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
@@ -126,6 +140,50 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[1] = c1;
     out[2] = c2;
     out[3] = c3;
+}
+
+// ---- fused batch epilogue (low-latency submit path) ----
+// Every block calls this after its warps have run out of work.  The block that takes the last ticket sees every other
+// block's result atomics (each block fences before taking its ticket), copies them out and leaves the device buffers
+// zeroed for the slot's next batch.
+__device__ __forceinline__ void batch_epilogue(const KernelParams &p) {
+    if (!p.done_counter) return;
+    __shared__ uint32_t s_is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_is_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    {
+        uint2 *src = reinterpret_cast<uint2 *>(p.results);
+        uint2 *dst = reinterpret_cast<uint2 *>(p.host_results);
+        const uint32_t cnt = p.n_leaves * (uint32_t)(sizeof(mr_leaf_result) / sizeof(uint2));
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            dst[i] = __ldcg(src + i);
+            src[i] = make_uint2(0u, 0u);
+        }
+    }
+    if (p.host_mast_delta && p.mast_delta) {
+        uint2 *src = reinterpret_cast<uint2 *>(p.mast_delta);
+        uint2 *dst = reinterpret_cast<uint2 *>(p.host_mast_delta);
+        for (uint32_t i = threadIdx.x; i < p.mast_delta_len; i += blockDim.x) {
+            dst[i] = __ldcg(src + i);
+            src[i] = make_uint2(0u, 0u);
+        }
+    }
+    if (threadIdx.x == 0) {
+        *p.work_counter = 0ull;
+        *p.done_counter = 0u;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *p.host_flag = p.done_seq;
+        __threadfence_system();
+    }
 }
 
 // random_best helpers, filled by mr_init (capi.cu): for n legal actions and prime index k,

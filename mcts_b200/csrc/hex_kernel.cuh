@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                             const uint32_t d_f = __shfl_sync(FULL_MASK, depth, f);
                             const int w_f = __shfl_sync(FULL_MASK, winner, f);
                             if (amaf_plies + d_f > STAT_FLUSH_PLIES) {
-                                flush_stat_table<H>(amaf_tab, p.amaf + (size_t)li * 2 * H::NA, lane);
+                                flush_stat_table<H>(amaf_tab, p.amaf + (size_t)li * p.amaf_stride, lane, p.tables_in_slots);
                                 amaf_plies = 0;
                             }
                             amaf_plies += d_f;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                 __syncwarp();
             }
             if (WANT_AMAF && p.amaf) {
-                flush_stat_table<H>(amaf_tab, p.amaf + (size_t)li * 2 * H::NA, lane);
+                flush_stat_table<H>(amaf_tab, p.amaf + (size_t)li * p.amaf_stride, lane, p.tables_in_slots);
                 amaf_plies = 0;
             }
         }
@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
             if (acc_depth) atomicAdd(reinterpret_cast<unsigned long long *>(&res->sum_depth), (unsigned long long)acc_depth);
         }
     }
+    batch_epilogue(p);
 }
 
 } // namespace mr

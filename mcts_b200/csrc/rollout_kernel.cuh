@@ -33,7 +33,7 @@ constexpr uint32_t STAT_FLUSH_PLIES = 32000; // packed 16-bit fields: flush befo
 
 // per-warp packed table -> global (visits, score) table, one atomic per non-zero field
 template <class G>
-__device__ __forceinline__ void flush_stat_table(uint32_t *tab, mr_action_stat *out, uint32_t lane) {
+__device__ __forceinline__ void flush_stat_table(uint32_t *tab, mr_action_stat *out, uint32_t lane, uint32_t in_slots) {
     __syncwarp();
     for (uint32_t e = lane; e < 2u * G::NSLOTS; e += 32) {
         const uint32_t v = tab[e];
@@ -41,7 +41,7 @@ __device__ __forceinline__ void flush_stat_table(uint32_t *tab, mr_action_stat *
             tab[e] = 0;
             const uint32_t pl = e >= (uint32_t)G::NSLOTS ? 1u : 0u;
             const uint32_t slot = e - pl * G::NSLOTS;
-            mr_action_stat *o = out + (size_t)pl * G::NA + G::slot_action_id(pl, slot);
+            mr_action_stat *o = in_slots ? out + e : out + (size_t)pl * G::NA + G::slot_action_id(pl, slot);
             const uint32_t visits = v & 0xffffu;
             const int score = (int)v >> 16; // v = visits + score * 65536 with visits < 65536: the arithmetic shift floors to score
             atomicAdd(&o->visits, visits);
@@ -333,21 +333,24 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                         }
                         const uint32_t excl = incl - my_d;
                         const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
-                        if (WANT_MAST && p.mast_delta) {
-                            if (mast_plies + total > STAT_FLUSH_PLIES) {
-                                flush_stat_table<G>(mast_tab, p.mast_delta, lane);
-                                mast_plies = 0;
-                            }
-                            mast_plies += total;
-                        }
-                        if (WANT_AMAF && !G::MASK_AMAF && p.amaf) {
-                            if (amaf_plies + total > STAT_FLUSH_PLIES) {
-                                flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * 2 * G::NA, lane);
-                                amaf_plies = 0;
-                            }
-                            amaf_plies += total;
-                        }
                         for (uint32_t base = 0; base < total; base += 32) {
+                            // (the packed 16-bit fields must not overflow: flush before the running count of additions
+                            // since the last flush could pass the limit -- checked per 32 entries, so a single retire
+                            // round of up to 32 * trace_cap entries is safe for any trace_cap)
+                            if (WANT_MAST && p.mast_delta) {
+                                if (mast_plies + 32u > STAT_FLUSH_PLIES) {
+                                    flush_stat_table<G>(mast_tab, p.mast_delta, lane, p.tables_in_slots);
+                                    mast_plies = 0;
+                                }
+                                mast_plies += 32u;
+                            }
+                            if (WANT_AMAF && !G::MASK_AMAF && p.amaf) {
+                                if (amaf_plies + 32u > STAT_FLUSH_PLIES) {
+                                    flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * p.amaf_stride, lane, p.tables_in_slots);
+                                    amaf_plies = 0;
+                                }
+                                amaf_plies += 32u;
+                            }
                             const uint32_t q = base + lane;
                             uint32_t f = 0; // number of lanes whose inclusive sum is <= q == owner lane of entry q
 #pragma unroll
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                                 const int e_f = __shfl_sync(FULL_MASK, end_code, f);
                                 const int u_p0 = e_f == ST_WIN_P0 ? 1 : (e_f == ST_WIN_P1 ? -1 : 0);
                                 if (amaf_plies + d_f > STAT_FLUSH_PLIES) {
-                                    flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * 2 * G::NA, lane);
+                                    flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * p.amaf_stride, lane, p.tables_in_slots);
                                     amaf_plies = 0;
                                 }
                                 amaf_plies += d_f;
@@ -448,7 +451,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
             }
             // the AMAF table is per leaf: it leaves shared memory with the task
             if (WANT_AMAF && p.amaf) {
-                flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * 2 * G::NA, lane);
+                flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * p.amaf_stride, lane, p.tables_in_slots);
                 amaf_plies = 0;
             }
         }
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
         }
     }
     // the MAST delta is batch-wide: it leaves shared memory when the warp runs out of tasks
-    if (WANT_MAST && p.mast_delta) flush_stat_table<G>(mast_tab, p.mast_delta, lane);
+    if (WANT_MAST && p.mast_delta) flush_stat_table<G>(mast_tab, p.mast_delta, lane, p.tables_in_slots);
     if (IS_LGR && p.lgr_stamps) {
         // slot space -> dense action ids: key = (player, id of the preceding action, made by the other player)
         __syncthreads(); // every warp of the block has run out of work
@@ -499,6 +502,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
             }
         }
     }
+    batch_epilogue(p);
 }
 
 } // namespace mr

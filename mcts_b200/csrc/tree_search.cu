@@ -7,6 +7,8 @@
 //   leaf fan-out ....... num_rollouts_per_leaf with k-1 extra virtual loss, search_impl.rs:101-113, shared.rs:787-805
 //   backprop ........... backprop.rs:704-731 with ChildArray::update / NodeStats::update (node.rs:295-302,673-681)
 //                        summed over the k trials of a leaf (exact: utilities are +1 / 0 / -1)
+//   GRAVE / RAVE ....... select/rave.rs:60-75 (beta schedules HandSelected, MinMSE, Threshold), :157-184 (get_ref),
+//                        :196-230 (score); tables written by update_grave, backprop.rs:619-640
 //   AMAF ............... select/amaf.rs:48-86 over per-edge AMAF rows written by update_amaf, backprop.rs:565-617
 //   LGR table .......... TreeStats.player_replies, last write wins over (trial, ply) order (backprop.rs:908-923): the
 //                        kernel's stamps for the playout part, the tree-path pairs added here
@@ -18,12 +20,27 @@
 //                        and playout (backprop.rs:885-899): the kernel's bigram delta plus the tree-path pairs added here
 //   MAST table ......... TreeStats.player_actions, written for playout trace AND tree path (backprop.rs:833-870)
 //   final move ......... RobustChild: (visits, expected score) lexicographic max, select/basic.rs:13-45
+//   root parallel ...... choose_action_root_parallel, search/parallel.rs:56-115: one searcher per host thread, each with
+//                        its own seed, tree and ctx (streams); root-child totals summed, most merged visits wins
 // The tree (arena, edge statistics in the parent's child arrays, root_stats) stays on the host; only the
 // simulation phase crosses the C ABI (mr_submit / mr_wait).  Tie-break draws of the tree come from the same
 // Philox4x32-10 generator as the playouts, on their own stream: ctr = (descent id, depth, 0, 2).
+//
+// Two things are new relative to the reference's loop, both only visible with batch_leaves > 1 (with one leaf per batch
+// and one batch in flight the driver IS the sequential loop of search_impl.rs:76-114):
+//   * a batch of B descents is gathered before any of their results exist, and up to `pipeline_depth` batches are in
+//     flight (the staleness the reference's tree-parallel workers live with, parallel.rs:188-251, made deterministic
+//     by the fixed order gather(n), submit(n), apply(n - depth + 1));
+//   * the expansion test counts IN-FLIGHT trials: a node is simulated from when `num_visits + trials in flight through
+//     it < expand_threshold`, so the second descent that reaches a node whose first simulation is still on the GPU
+//     expands it and goes on instead of queueing the same leaf again.  Without this every descent of the first batch
+//     stops at the unvisited root, and a fresh node swallows as many descents as arrive before its first result.
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <new>
+#include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -35,7 +52,7 @@ namespace {
 const uint32_t kPrimes[16] = {14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991,
                               53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693};
 
-uint32_t philox_word0(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+void philox4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
@@ -47,21 +64,90 @@ uint32_t philox_word0(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    return c0;
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+uint32_t philox_word0(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t o[4];
+    philox4(seed, c0, c1, c2, c3, o);
+    return o[0];
 }
 inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 
-struct Stats { // NodeStats / one ChildArray row
+// NodeStats / one ChildArray row.  Utilities are +1 / -1 / 0 in a two-player zero-sum game, so score[1] == -score[0]
+// and sum_squared_score is the number of decisive trials for both players: one number each.
+struct Stats {
     uint32_t visits = 0, vloss = 0;
-    int64_t score[2] = {0, 0}, sumsq[2] = {0, 0};
-    uint32_t amaf_visits = 0; // ChildArray amaf rows (node.rs:392-396,711-719): every player's count moves together
-    int64_t amaf_score[2] = {0, 0};
+    int64_t score0 = 0, sumsq = 0;
+    int64_t score(int player) const { return player == 0 ? score0 : -score0; }
+};
+struct AmafRow { // ChildArray amaf rows (node.rs:392-396,711-719): every player's count moves together
+    uint32_t visits = 0;
+    int64_t score0 = 0;
 };
 // node.rs:126-133
 inline double expected_score(const Stats &s, int player) {
     if (s.visits == 0) return 0.0;
     const double lv = (double)s.vloss;
-    return ((double)s.score[player] - lv) / ((double)s.visits + lv);
+    return ((double)s.score(player) - lv) / ((double)s.visits + lv);
+}
+
+// select/rave.rs:60-75
+inline double rave_beta(const mr_search_desc *d, uint32_t n, uint32_t amaf_n) {
+    if (d->rave_schedule == MR_RAVE_THRESHOLD) {
+        const double rave = (double)d->rave_param;
+        return std::max(0.0, rave - (double)n) / rave;
+    }
+    if (d->rave_schedule == MR_RAVE_MIN_MSE) {
+        const double nn = (double)n, an = (double)amaf_n, bias = d->rave_bias;
+        return an / (nn + an + 4.0 * nn * an * bias * bias);
+    }
+    const double k = (double)d->rave_param;
+    return std::sqrt(k / (3.0 * (double)n + k));
+}
+
+// The value an unvisited (not yet created) child competes with: node.rs:139-159 value_estimate_unvisited, then the
+// strategy's own exploration term (ucb.rs:55-61, :134-146; none for Rave / Amaf, rave.rs:226-230, amaf.rs:76-79).
+inline double unvisited_child_score(const mr_search_desc *d, const Stats &cur, int player, double parent_log) {
+    double q;
+    if (d->q_init == MR_QINIT_INFINITY) q = 10000.0;
+    else q = cur.visits == 0 ? 10000.0 : expected_score(cur, player);
+    const double c = d->exploration_c;
+    if (d->select == MR_SELECT_UCB1_TUNED) return q + (parent_log * std::min(1.0, 1.0) + c * std::sqrt(parent_log));
+    if (d->select == MR_SELECT_GRAVE || d->select == MR_SELECT_AMAF) return q;
+    return q + c * std::sqrt(parent_log);
+}
+
+// The score of a created child: ucb.rs:40-52 (UCB1), :90-132 (UCB1-Tuned), rave.rs:196-224 (GRAVE; grave_n / grave_q are
+// the reference node's AMAF count and score sum of this action for the mover), amaf.rs:58-74 (AMAF).
+inline double created_child_score(const mr_search_desc *d, const Stats &e, const AmafRow *amaf_row, int player, double parent_log,
+                                  uint32_t grave_n, double grave_q) {
+    const double c = d->exploration_c;
+    const double exploit = expected_score(e, player);
+    const double total = (double)(e.visits + e.vloss);
+    switch (d->select) {
+    case MR_SELECT_UCB1_TUNED: {
+        const double var = std::max(0.0, (double)e.sumsq / total - exploit * exploit);
+        const double frac = parent_log / total;
+        return exploit + (frac * std::min(1.0, var) + c * std::sqrt(frac));
+    }
+    case MR_SELECT_GRAVE: {
+        const uint32_t n_tot = e.visits + e.vloss;
+        const double explore = c * std::sqrt(parent_log / (double)n_tot);
+        const double b = rave_beta(d, n_tot, grave_n);
+        const double amaf = grave_n == 0 ? 0.0 : grave_q / (double)grave_n;
+        return (1.0 - b) * exploit + b * amaf + explore;
+    }
+    case MR_SELECT_AMAF: {
+        const double amaf_n = (double)std::max<uint32_t>(1u, amaf_row->visits);
+        const double amaf = (double)(player == 0 ? amaf_row->score0 : -amaf_row->score0) / amaf_n;
+        const double ucb1 = exploit + c * std::sqrt(parent_log / total);
+        return d->amaf_alpha * amaf + (1.0 - d->amaf_alpha) * ucb1;
+    }
+    default: return exploit + c * std::sqrt(parent_log / total);
+    }
 }
 
 enum : uint8_t { UNEXPANDED = 0, EXPANDED = 1, TERMINAL = 2 };
@@ -71,7 +157,7 @@ struct Node {
     uint8_t status = UNEXPANDED;
     uint8_t player = 0;
     uint16_t n_children = 0;
-    uint32_t first = 0; // index of child 0 in the edge arrays
+    uint32_t first = 0;     // index of child 0 in the edge arrays
     int32_t grave_tab = -1; // cached index of this state's GRAVE table (-1 = not looked up successfully yet)
 };
 
@@ -104,12 +190,18 @@ inline StateKey key_of(const mr_leaf &s) {
 struct Tree {
     int game;
     bool use_table = false;
+    bool want_amaf_rows = false;
     std::unordered_map<StateKey, uint32_t, StateKeyHash> table; // use_transpositions: state -> node
     std::vector<Node> nodes;
+    // the edges, as parallel arrays (the selection loop reads child + edge, the rest is touched on expansion / backprop)
     std::vector<uint16_t> action;
+    std::vector<uint16_t> slot; // compact per-player slot of the action, in the numbering of the node's mover
     std::vector<int32_t> child; // -1 = not created yet
     std::vector<Stats> edge;
+    std::vector<AmafRow> amaf_row; // MR_SELECT_AMAF only
     Stats root_stats;
+    uint64_t root_inflight = 0;    // trials gathered through the root and not applied yet (the root has no edge to carry
+                                   // virtual losses; root_stats stays as the reference keeps it)
     uint32_t max_depth = 0;
 
     uint32_t add_node(const mr_leaf &s) {
@@ -136,15 +228,16 @@ struct Tree {
         n.n_children = (uint16_t)cnt;
         for (int i = 0; i < cnt; ++i) {
             action.push_back(acts[i]);
+            slot.push_back((uint16_t)mr_action_slot(game, n.player, acts[i]));
             child.push_back(-1);
             edge.push_back(Stats());
+            if (want_amaf_rows) amaf_row.push_back(AmafRow());
         }
         n.status = EXPANDED;
     }
 };
 
-struct GraveTable { // per state: [2 * NA] ActionStats (node.rs:51-55) with integer scores, as two arrays so that the
-                    // per-leaf table merge of backprop_grave is two straight vectorisable loops
+struct GraveTable { // per state: [2][S] ActionStats (node.rs:51-55) over compact action slots, integer scores
     std::vector<uint32_t> visits;
     std::vector<int64_t> score;
     explicit GraveTable(size_t n) : visits(n, 0u), score(n, 0) {}
@@ -154,11 +247,12 @@ struct Search {
     mr_ctx *ctx;
     const mr_search_desc *d;
     Tree t;
-    std::vector<mr_action_stat> mast; // [2][NA], TreeStats.player_actions
+    std::vector<mr_action_stat> mast;   // [2][NA], TreeStats.player_actions
     std::vector<mr_action_stat> bigram; // [2][S][S], TreeStats.player_bigram_actions over compact action slots (MR_EPS_NST)
-    std::vector<uint16_t> replies2;   // [2][S][S], TreeStats.player_replies2 over action slots: 1 + reply code (MR_EPS_LGR2)
-    std::vector<uint16_t> replies;    // [2][NA], TreeStats.player_replies: 1 + reply code by (player, preceding action id)
+    std::vector<uint16_t> replies2;     // [2][S][S], TreeStats.player_replies2 over action slots: 1 + reply code (MR_EPS_LGR2)
+    std::vector<uint16_t> replies;      // [2][NA], TreeStats.player_replies: 1 + reply code by (player, preceding action id)
     int na;
+    int S; // compact action slots per player
     // TreeStats.grave (search/shared.rs:52): per reference-node state, per player, per action.  The reference keys
     // it by node.hash; here the key is the full state record (no collisions), so equal states share one table.
     std::unordered_map<StateKey, uint32_t, StateKeyHash> grave_index;
@@ -176,20 +270,10 @@ struct Search {
         if (!create) return nullptr;
         n.grave_tab = (int32_t)grave.size();
         grave_index.emplace(key_of(n.state), (uint32_t)grave.size());
-        grave.emplace_back((size_t)2 * na);
+        grave.emplace_back((size_t)2 * S);
         return &grave.back();
     }
 
-    // select/rave.rs:60-75
-    double rave_beta(uint32_t n, uint32_t amaf_n) const {
-        (void)amaf_n;
-        if (d->rave_schedule == MR_RAVE_THRESHOLD) {
-            const double rave = (double)d->rave_param;
-            return std::max(0.0, rave - (double)n) / rave;
-        }
-        const double k = (double)d->rave_param;
-        return std::sqrt(k / (3.0 * (double)n + k));
-    }
     // select/rave.rs:157-184 get_ref: the child itself when its incoming edge has total_visits >= threshold (decided in
     // best_child), else the nearest such node on the path, else the root
     uint32_t grave_ref_ancestor(const std::vector<PathEntry> &path) const {
@@ -207,107 +291,84 @@ struct Search {
         return t.edge[parent.first + me.idx];
     }
 
-    // select/mod.rs:343-386 with select/ucb.rs scores
+    // select/mod.rs:343-386 with the strategies' scores
     uint32_t best_child(const std::vector<PathEntry> &path, uint32_t descent) {
         const Node &node = t.nodes[path.back().node];
         const int player = node.player;
         const Stats &cur = current_stats(path);
-        const double parent_log = std::log(std::max(1.0, (double)cur.visits));
-        const double c = d->exploration_c;
-        // node.rs:139-159 value_estimate_unvisited
-        double q_unvisited;
-        if (d->q_init == MR_QINIT_INFINITY) q_unvisited = 10000.0;
-        else q_unvisited = cur.visits == 0 ? 10000.0 : expected_score(cur, player);
-        double unvisited_value;
-        if (d->select == MR_SELECT_UCB1_TUNED) unvisited_value = q_unvisited + (parent_log * std::min(1.0, 1.0) + c * std::sqrt(parent_log));
-        else if (d->select == MR_SELECT_GRAVE || d->select == MR_SELECT_AMAF)
-            unvisited_value = q_unvisited; // rave.rs:226-230, amaf.rs:76-79: no exploration term
-        else unvisited_value = q_unvisited + c * std::sqrt(parent_log);
-
+        const double parent_log = std::log(std::max(1.0, (double)cur.visits)); // ucb.rs:34-37: without virtual loss
+        const double unvisited_value = unvisited_child_score(d, cur, player, parent_log);
         const uint32_t n = node.n_children;
         const uint32_t r = mulhi32(philox_word0(d->seed, descent, (uint32_t)path.size() - 1, 0, 2), 16u * n);
         uint32_t i = r / 16u;
-        const uint32_t stride = kPrimes[r % 16u];
+        const uint32_t stride = kPrimes[r % 16u] % n;
         bool have = false;
         double best = 0.0;
         uint32_t best_i = i;
         bool anc_done = false;
-        uint32_t anc_ref = 0;
         const GraveTable *anc_tab = nullptr;
+        const bool grave_sel = d->select == MR_SELECT_GRAVE;
         for (uint32_t k = 0; k < n; ++k) {
-            const Stats &e = t.edge[node.first + i];
+            const uint32_t ei = node.first + i;
             double score;
-            if (t.child[node.first + i] < 0) {
+            if (t.child[ei] < 0) {
                 score = unvisited_value;
             } else {
-                const double exploit = expected_score(e, player);
-                const double total = (double)(e.visits + e.vloss);
-                if (d->select == MR_SELECT_UCB1_TUNED) {
-                    const double var = std::max(0.0, (double)e.sumsq[player] / total - exploit * exploit);
-                    const double frac = parent_log / total;
-                    score = exploit + (frac * std::min(1.0, var) + c * std::sqrt(frac));
-                } else if (d->select == MR_SELECT_GRAVE) { // rave.rs:196-224
+                const Stats &e = t.edge[ei];
+                uint32_t grave_n = 0;
+                double grave_q = 0.0;
+                if (grave_sel) {
                     // get_ref: the child itself once its edge has the threshold visits, else the nearest such ancestor --
-                    // which is the same node for every child of this node, so it is resolved once (anc_ref / anc_tab)
+                    // which is the same node for every child of this node, so it is resolved once (anc_tab)
                     const bool own_ref = e.visits + e.vloss >= d->grave_threshold;
                     if (!own_ref && !anc_done) {
-                        anc_ref = grave_ref_ancestor(path);
-                        anc_tab = grave_of(t.nodes[anc_ref], false);
+                        anc_tab = grave_of(t.nodes[grave_ref_ancestor(path)], false);
                         anc_done = true;
                     }
-                    uint32_t amaf_n = 0;
-                    double amaf_q = 0.0;
-                    if (const GraveTable *tab = own_ref ? grave_of(t.nodes[(uint32_t)t.child[node.first + i]], false) : anc_tab) {
-                        const size_t e = (size_t)player * na + mr_host::action_id(t.game, t.action[node.first + i]);
-                        amaf_n = tab->visits[e];
-                        amaf_q = (double)tab->score[e];
+                    if (const GraveTable *tab = own_ref ? grave_of(t.nodes[(uint32_t)t.child[ei]], false) : anc_tab) {
+                        const size_t g = (size_t)player * S + t.slot[ei];
+                        grave_n = tab->visits[g];
+                        grave_q = (double)tab->score[g];
                     }
-                    const uint32_t n_tot = e.visits + e.vloss;
-                    const double explore = c * std::sqrt(parent_log / (double)n_tot);
-                    const double b = rave_beta(n_tot, amaf_n);
-                    const double amaf = amaf_n == 0 ? 0.0 : amaf_q / (double)amaf_n;
-                    score = (1.0 - b) * exploit + b * amaf + explore;
-                } else if (d->select == MR_SELECT_AMAF) { // amaf.rs:58-74
-                    const double amaf_n = (double)std::max<uint32_t>(1u, e.amaf_visits);
-                    const double amaf = (double)e.amaf_score[player] / amaf_n;
-                    const double ucb1 = exploit + c * std::sqrt(parent_log / total);
-                    score = d->amaf_alpha * amaf + (1.0 - d->amaf_alpha) * ucb1;
-                } else {
-                    score = exploit + c * std::sqrt(parent_log / total);
                 }
+                score = created_child_score(d, e, t.want_amaf_rows ? &t.amaf_row[ei] : nullptr, player, parent_log, grave_n, grave_q);
             }
             if (!have || score > best) {
                 have = true;
                 best = score;
                 best_i = i;
             }
-            i = (i + stride) % n;
+            i += stride;
+            if (i >= n) i -= n;
         }
         return best_i;
     }
 
-    // search/shared.rs:569-736
+    // search/shared.rs:569-736, with the in-flight trials counted by the expansion test (file header)
     void select(uint32_t descent, std::vector<PathEntry> &path) {
         path.clear();
         uint32_t cur = 0, incoming = 0;
         for (;;) {
             path.push_back({cur, incoming});
-            const uint32_t num_visits = current_stats(path).visits;
+            const Stats &cs = current_stats(path);
+            // trials in flight through this node from OTHER descents: every gathered descent holds k virtual losses on
+            // each of its edges (root_inflight for the root); this one has added 1 to the edge it just came down
+            const uint64_t others = path.size() == 1 ? t.root_inflight : (uint64_t)cs.vloss - 1u;
             if (t.nodes[cur].status == TERMINAL) return;
-            if (num_visits < d->expand_threshold) return;
+            if ((uint64_t)cs.visits + others < d->expand_threshold) return;
             if (t.nodes[cur].status == UNEXPANDED) {
                 t.expand(cur);
                 if (t.nodes[cur].status == TERMINAL) return;
             }
             const uint32_t best = best_child(path, descent);
             incoming = best;
-            const uint32_t slot = t.nodes[cur].first + best;
-            t.edge[slot].vloss += 1; // one virtual loss per traversed edge
-            if (t.child[slot] >= 0) {
-                cur = (uint32_t)t.child[slot];
+            const uint32_t ei = t.nodes[cur].first + best;
+            t.edge[ei].vloss += 1; // one virtual loss per traversed edge
+            if (t.child[ei] >= 0) {
+                cur = (uint32_t)t.child[ei];
             } else {
                 mr_leaf s = t.nodes[cur].state;
-                mr_host::apply(t.game, s, t.action[slot]);
+                mr_host::apply(t.game, s, t.action[ei]);
                 uint32_t id;
                 if (t.use_table) { // resolve_child_id: reuse the node of an identical state (shared.rs:412-436)
                     auto it = t.table.find(key_of(s));
@@ -320,7 +381,7 @@ struct Search {
                 } else {
                     id = t.add_node(s);
                 }
-                t.child[slot] = (int32_t)id;
+                t.child[ei] = (int32_t)id;
                 cur = id;
                 if (d->expand_threshold > 0) {
                     path.push_back({cur, incoming});
@@ -330,61 +391,62 @@ struct Search {
         }
     }
 
-    // shared.rs:787-805: k-1 extra virtual losses on every edge of the path
-    void add_path_virtual_loss(const std::vector<PathEntry> &path, uint32_t extra) {
-        for (size_t i = 1; i < path.size(); ++i) t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += extra;
+    // shared.rs:787-805: k-1 extra virtual losses on every edge of the path; the root counts the k trials in flight
+    void add_path_virtual_loss(const std::vector<PathEntry> &path, uint32_t k) {
+        for (size_t i = 1; i < path.size(); ++i) t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
+        t.root_inflight += k;
     }
 
     // update_grave (backprop.rs:619-640) for the k trials of one leaf: every non-root node X of the path gets, per
     // (action, player) occurrence of [playout trace + the path's edges BELOW X], visits += 1 and score += u[player].
-    // `amaf` is the kernel's per-leaf occurrence table of the playout traces ([2][NA]).
+    // `amaf` is the kernel's per-leaf occurrence table of the playout traces, [2][S] over action slots.
     void backprop_grave(const std::vector<PathEntry> &path, const mr_action_stat *amaf, const int64_t u[2], uint32_t k) {
-        std::vector<std::pair<uint32_t, int>> below; // (action id, player) of the edges below the node being updated
+        below.clear(); // (slot, player) of the edges below the node being updated
         for (size_t i = path.size(); i-- > 1;) {
             GraveTable &tab = *grave_of(t.nodes[path[i].node], true);
             uint32_t *__restrict__ tv = tab.visits.data();
             int64_t *__restrict__ ts = tab.score.data();
-            const size_t cnt = (size_t)2 * na;
+            const size_t cnt = (size_t)2 * S;
             for (size_t e = 0; e < cnt; ++e) tv[e] += amaf[e].visits;
             for (size_t e = 0; e < cnt; ++e) ts[e] += amaf[e].score;
             for (const auto &b : below) {
-                const size_t e = (size_t)b.second * na + b.first;
+                const size_t e = (size_t)b.second * S + b.first;
                 tv[e] += k;
                 ts[e] += u[b.second];
             }
             const Node &parent = t.nodes[path[i - 1].node];
-            below.emplace_back((uint32_t)mr_host::action_id(t.game, t.action[parent.first + path[i].idx]), (int)parent.player);
+            below.emplace_back((uint32_t)t.slot[parent.first + path[i].idx], (int)parent.player);
         }
     }
 
     // update_amaf (backprop.rs:565-617) for the k trials of one leaf: at every non-root path node X with parent P,
     // each occurrence of (action, P's mover) in [playout trace + the path's edges BELOW X] whose action is one of
     // P's created children adds one AMAF visit and the trial's utilities to that child's row.  The playout part
-    // arrives pre-summed per (player, action) from the kernel; utilities are +1/-1/0, so the other player's sum
+    // arrives pre-summed per (player, slot) from the kernel; utilities are +1/-1/0, so the other player's sum
     // is the negation of the mover's.
     void backprop_amaf(const std::vector<PathEntry> &path, const mr_action_stat *amaf, const int64_t u[2], uint32_t k) {
-        std::vector<std::pair<uint32_t, int>> below;
+        below.clear();
         for (size_t i = path.size(); i-- > 1;) {
             const Node &parent = t.nodes[path[i - 1].node];
             const int mover = parent.player;
             for (uint32_t j = 0; j < parent.n_children; ++j) {
                 if (t.child[parent.first + j] < 0) continue;
-                const uint32_t a = (uint32_t)mr_host::action_id(t.game, t.action[parent.first + j]);
-                uint32_t cnt = amaf[(size_t)mover * na + a].visits;
-                int64_t sc = amaf[(size_t)mover * na + a].score;
+                const uint32_t a = t.slot[parent.first + j];
+                uint32_t cnt = amaf[(size_t)mover * S + a].visits;
+                int64_t sc = amaf[(size_t)mover * S + a].score;
                 for (const auto &b : below)
                     if (b.second == mover && b.first == a) {
                         cnt += k;
                         sc += u[mover];
                     }
-                Stats &e = t.edge[parent.first + j];
-                e.amaf_visits += cnt;
-                e.amaf_score[mover] += sc;
-                e.amaf_score[1 - mover] -= sc;
+                AmafRow &e = t.amaf_row[parent.first + j];
+                e.visits += cnt;
+                e.score0 += mover == 0 ? sc : -sc;
             }
-            below.emplace_back((uint32_t)mr_host::action_id(t.game, t.action[parent.first + path[i].idx]), mover);
+            below.emplace_back((uint32_t)t.slot[parent.first + path[i].idx], mover);
         }
     }
+    std::vector<std::pair<uint32_t, int>> below;
 
     // backprop.rs:908-923 for one batch.  A trial writes replies[p][prev] = action for every consecutive pair of its
     // chronological action list (tree path, then playout) whose second action was made by a player p that did not
@@ -419,12 +481,11 @@ struct Search {
     void backprop_bigrams(const std::vector<PathEntry> &path, const mr_leaf_result &r, uint32_t k) {
         const int64_t nonzero = (int64_t)k - r.draws;
         const int64_t u[2] = {(int64_t)r.wins[0] - (nonzero - r.wins[0]), (int64_t)r.wins[1] - (nonzero - r.wins[1])};
-        const size_t S = (size_t)mr_num_slots(t.game);
+        const size_t SS = (size_t)S;
         for (size_t i = 2; i < path.size(); ++i) {
             const Node &grand = t.nodes[path[i - 2].node], &parent = t.nodes[path[i - 1].node];
             const int p = parent.player;
-            const uint16_t prev = t.action[grand.first + path[i - 1].idx], act = t.action[parent.first + path[i].idx];
-            mr_action_stat &e = bigram[((size_t)p * S + (size_t)mr_action_slot(t.game, 1 - p, prev)) * S + (size_t)mr_action_slot(t.game, p, act)];
+            mr_action_stat &e = bigram[((size_t)p * SS + t.slot[grand.first + path[i - 1].idx]) * SS + t.slot[parent.first + path[i].idx]];
             e.visits += k;
             e.score += (int32_t)u[p];
         }
@@ -435,16 +496,15 @@ struct Search {
     // with no insert, the old entry unless some trial that p lost played it.  `ins` arrives with the playout part's last
     // inserts; the tree-path windows of leaf b (three consecutive edges) are inserted by its trials up to
     // last_win[b][p] - 1 and removed by its trials up to last_lose[b][p] - 1, always before that trial's playout windows.
-    int merge_replies2(mr_ctx *ctx, int slot, const std::vector<std::vector<PathEntry>> &paths, uint32_t nb, uint32_t k,
+    int merge_replies2(int slot, const std::vector<std::vector<PathEntry>> &paths, uint32_t nb, uint32_t k,
                        std::vector<mr_reply_update> &ins, const std::vector<uint32_t> &last_win,
                        const std::vector<uint32_t> &last_lose, std::vector<uint8_t> &removed) {
-        const size_t S = (size_t)mr_num_slots(t.game);
+        const size_t SS = (size_t)S;
         auto key_of_window = [&](const std::vector<PathEntry> &path, size_t i, int &p, uint16_t &act) -> size_t {
             const Node &n2 = t.nodes[path[i - 3].node], &n1 = t.nodes[path[i - 2].node], &n0 = t.nodes[path[i - 1].node];
             p = n0.player;
-            const uint16_t own = t.action[n2.first + path[i - 2].idx], opp = t.action[n1.first + path[i - 1].idx];
             act = t.action[n0.first + path[i].idx];
-            return ((size_t)p * S + (size_t)mr_action_slot(t.game, p, own)) * S + (size_t)mr_action_slot(t.game, 1 - p, opp);
+            return ((size_t)p * SS + t.slot[n2.first + path[i - 2].idx]) * SS + t.slot[n1.first + path[i - 1].idx];
         };
         for (uint32_t b = 0; b < nb; ++b)
             for (size_t i = 3; i < paths[b].size(); ++i) {
@@ -484,11 +544,10 @@ struct Search {
         for (size_t i = path.size(); i-- > 0;) {
             Stats &s = i == 0 ? t.root_stats : t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
             s.visits += k;
-            for (int p = 0; p < 2; ++p) {
-                s.score[p] += u[p];
-                s.sumsq[p] += nonzero;
-            }
+            s.score0 += u[0];
+            s.sumsq += nonzero;
             if (i > 0) s.vloss -= k; // each trial's backprop removes one (backprop.rs:722-725)
+            else t.root_inflight -= k;
             if (i > 0 && !mast.empty()) {
                 // GLOBAL write for the tree-path part of amaf_actions (backprop.rs:833-870): the edge into this
                 // node was played by the parent's mover
@@ -507,43 +566,30 @@ double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-} // namespace
+struct RootTotals {
+    std::vector<mr_root_child> children;
+    uint16_t best_action = 0xffff;
+    mr_search_stats stats;
+};
 
-extern "C" int mr_generate_actions(int game, const mr_leaf *state, uint16_t *out) {
-    if (game < 0 || game >= MR_NUM_GAMES || !state || !out) return -1;
-    return mr_host::generate_actions(game, *state, out);
-}
-extern "C" int mr_apply(int game, mr_leaf *state, uint16_t action) {
-    if (game < 0 || game >= MR_NUM_GAMES || !state) return MR_ERR_INVALID;
-    mr_host::apply(game, *state, action);
-    return MR_OK;
-}
-extern "C" int mr_terminal_status(int game, const mr_leaf *state) {
-    if (game < 0 || game >= MR_NUM_GAMES || !state) return -1;
-    return mr_host::terminal_status(game, *state);
-}
-
-extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, uint16_t *best_action,
-                         mr_root_child *children, uint32_t *n_children, mr_search_stats *stats) {
-    if (!ctx || !desc || !root || !best_action) return MR_ERR_INVALID;
-    if (desc->game >= MR_NUM_GAMES || desc->batch_leaves == 0 || desc->playouts_per_leaf == 0 || desc->max_iterations == 0)
-        return MR_ERR_INVALID;
-    if (desc->select > MR_SELECT_AMAF) return MR_ERR_INVALID;
+// One search on one ctx.  `children_out` gets the root children in root action-list order.
+int run_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, RootTotals &out) {
     Search s;
     s.ctx = ctx;
     s.d = desc;
     s.t.game = (int)desc->game;
     s.na = mr_num_actions((int)desc->game);
+    s.S = mr_num_slots((int)desc->game);
     const bool nst = desc->policy == MR_EPS_NST;
     const bool uses_mast = desc->policy == MR_EPS_MAST || desc->policy == MR_DECISIVE_MAST_WIN || desc->policy == MR_DECISIVE_MAST_WINLOSS || nst ||
                            desc->policy == MR_EPS_LGR2_MAST;
-    const size_t n_bigram = nst ? (size_t)2 * mr_num_slots((int)desc->game) * mr_num_slots((int)desc->game) : 0;
+    const size_t n_bigram = nst ? (size_t)2 * s.S * s.S : 0;
     s.bigram.assign(n_bigram, mr_action_stat{0, 0});
     std::vector<mr_action_stat> bigram_delta(n_bigram);
     if (uses_mast) s.mast.assign((size_t)2 * s.na, mr_action_stat{0, 0});
     const bool lgr2 = desc->policy == MR_EPS_LGR2 || desc->policy == MR_EPS_LGR2_MAST;
     const bool lgr = desc->policy == MR_EPS_LGR || lgr2; // LGRF-2 keeps the LGR-1 table too (its inner strategy)
-    const size_t n_replies2 = lgr2 ? (size_t)2 * mr_num_slots((int)desc->game) * mr_num_slots((int)desc->game) : 0;
+    const size_t n_replies2 = lgr2 ? (size_t)2 * s.S * s.S : 0;
     s.replies2.assign(n_replies2, 0);
     std::vector<mr_reply_update> reply2_ins(n_replies2);
     std::vector<uint8_t> reply2_removed(n_replies2);
@@ -551,45 +597,46 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
     if (lgr) s.replies.assign((size_t)2 * s.na, 0);
     std::vector<mr_reply_update> reply_upd(lgr ? (size_t)2 * s.na : 0);
     std::vector<uint32_t> last_win(lgr ? (size_t)2 * desc->batch_leaves : 0);
-    s.t.nodes.reserve(desc->max_iterations + 16);
+    s.t.nodes.reserve(std::min<size_t>((size_t)desc->max_iterations + 16, (size_t)1 << 22)); // at most one new node per descent
     s.t.use_table = (desc->flags & MR_SEARCH_TRANSPOSITIONS) != 0;
+    s.t.want_amaf_rows = desc->select == MR_SELECT_AMAF;
     s.t.add_node(*root);
     if (s.t.use_table) s.t.table.emplace(key_of(*root), 0u);
 
     const uint32_t B = desc->batch_leaves, k = desc->playouts_per_leaf;
-    std::vector<std::vector<PathEntry>> paths(B);
-    std::vector<mr_leaf> leaves(B);
-    std::vector<mr_leaf_result> results(B);
-    std::vector<mr_action_stat> delta(uses_mast ? (size_t)2 * s.na : 0);
     const bool want_amaf = desc->select == MR_SELECT_GRAVE || desc->select == MR_SELECT_AMAF;
-    std::vector<mr_action_stat> amaf(want_amaf ? (size_t)B * 2 * s.na : 0);
     mr_search_stats st;
     memset(&st, 0, sizeof st);
 
-    // Two buffer sets, one per ABI slot.  Synchronous mode uses set 0 only.  Pipelined mode
-    // (MR_SEARCH_PIPELINED) gathers batch N+1 while batch N is on the GPU: its descents see batch N's virtual
-    // losses but not yet its results -- the same staleness the reference's tree-parallel workers live with
-    // (search/parallel.rs:188-251), made deterministic by the fixed order gather(N+1), submit(N+1), wait(N), backprop(N).
-    const bool pipelined = (desc->flags & MR_SEARCH_PIPELINED) != 0;
+    // One buffer set per ABI slot in use.  Batch n goes to slot n % depth; the fixed order is gather(n), submit(n),
+    // then -- once `depth` batches are in flight -- wait(n - depth + 1), backprop(n - depth + 1).  The descents of a
+    // batch see the virtual losses of every batch still in flight but not yet its results: the staleness the
+    // reference's tree-parallel workers live with (search/parallel.rs:188-251), made deterministic.
+    uint32_t depth = desc->pipeline_depth ? desc->pipeline_depth : ((desc->flags & MR_SEARCH_PIPELINED) ? 2u : 1u);
+    if (depth > MR_NUM_SLOTS) depth = MR_NUM_SLOTS;
     struct BatchBuf {
         std::vector<std::vector<PathEntry>> paths;
         std::vector<mr_leaf> leaves;
         std::vector<mr_leaf_result> results;
         std::vector<mr_action_stat> delta, amaf;
         uint32_t nb = 0;
-    } buf[2];
+    };
+    std::vector<BatchBuf> buf(depth);
+    const size_t delta_len = uses_mast ? (size_t)2 * s.S : 0; // the batch's MAST delta arrives in slot space
     for (auto &bb : buf) {
         bb.paths.resize(B);
         bb.leaves.resize(B);
         bb.results.resize(B);
-        bb.delta.resize(uses_mast ? (size_t)2 * s.na : 0);
-        bb.amaf.resize(want_amaf ? (size_t)B * 2 * s.na : 0);
+        bb.delta.resize(delta_len);
+        bb.amaf.resize(want_amaf ? (size_t)B * 2 * s.S : 0);
     }
-    (void)paths;
-    (void)leaves;
-    (void)results;
-    (void)delta;
-    (void)amaf;
+    // slot -> dense action id of the MAST table, per player
+    std::vector<uint32_t> slot_id(uses_mast ? (size_t)2 * s.S : 0, 0xffffffffu);
+    for (size_t e = 0; e < slot_id.size(); ++e) {
+        const int pl = e >= (size_t)s.S ? 1 : 0;
+        const int code = mr_slot_action((int)desc->game, pl, (int)(e - (size_t)pl * s.S));
+        if (code >= 0) slot_id[e] = (uint32_t)mr_host::action_id((int)desc->game, (uint16_t)code);
+    }
 
     auto gather_and_submit = [&](int slot, uint32_t first, uint32_t nb) -> int {
         BatchBuf &bb = buf[slot];
@@ -597,7 +644,7 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         const double t0 = now_s();
         for (uint32_t b = 0; b < nb; ++b) {
             s.select(first + b, bb.paths[b]);
-            if (k > 1) s.add_path_virtual_loss(bb.paths[b], k - 1);
+            s.add_path_virtual_loss(bb.paths[b], k);
             bb.leaves[b] = s.t.nodes[bb.paths[b].back().node].state;
             if ((lgr || nst) && bb.paths[b].size() > 1) { // playout()'s prev_action: the last edge of the descent (shared.rs:763-778)
                 const std::vector<PathEntry> &path = bb.paths[b];
@@ -621,7 +668,8 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
             int rc = mr_set_bigrams(ctx, (int)desc->game, s.bigram.data(), desc->nst_backoff_threshold);
             if (rc != MR_OK) return rc;
         }
-        st.seconds_select += now_s() - t0;
+        const double t1 = now_s();
+        st.seconds_select += t1 - t0;
         mr_batch_desc bd;
         memset(&bd, 0, sizeof bd);
         bd.game = desc->game;
@@ -629,11 +677,13 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         bd.n_leaves = nb;
         bd.playouts_per_leaf = k;
         bd.max_playout_depth = desc->max_playout_depth;
-        bd.flags = (uses_mast ? MR_WANT_MAST_DELTA : 0) | (want_amaf ? MR_WANT_AMAF : 0);
+        bd.flags = (uses_mast ? MR_WANT_MAST_DELTA : 0) | (want_amaf ? MR_WANT_AMAF : 0) | MR_TABLES_IN_SLOTS;
         bd.seed = desc->seed;
         bd.leaf_id_base = first;
         bd.epsilon = desc->epsilon;
-        return mr_submit(ctx, slot, &bd, bb.leaves.data(), s.mast.empty() ? nullptr : s.mast.data());
+        const int rc = mr_submit(ctx, slot, &bd, bb.leaves.data(), s.mast.empty() ? nullptr : s.mast.data());
+        st.seconds_submit += now_s() - t1;
+        return rc;
     };
     auto wait_and_backprop = [&](int slot) -> int {
         BatchBuf &bb = buf[slot];
@@ -652,7 +702,7 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         if (lgr2) {
             rc = mr_reply2_inserts(ctx, slot, reply2_ins.data(), last_lose.data());
             if (rc != MR_OK) return rc;
-            rc = s.merge_replies2(ctx, slot, bb.paths, bb.nb, k, reply2_ins, last_win, last_lose, reply2_removed);
+            rc = s.merge_replies2(slot, bb.paths, bb.nb, k, reply2_ins, last_win, last_lose, reply2_removed);
             if (rc != MR_OK) return rc;
         }
         const double t1 = now_s();
@@ -663,12 +713,15 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         }
         for (uint32_t b = 0; b < bb.nb; ++b) {
             if (nst) s.backprop_bigrams(bb.paths[b], bb.results[b], k);
-            s.backprop(bb.paths[b], bb.results[b], k, want_amaf ? bb.amaf.data() + (size_t)b * 2 * s.na : nullptr);
+            s.backprop(bb.paths[b], bb.results[b], k, want_amaf ? bb.amaf.data() + (size_t)b * 2 * s.S : nullptr);
             st.playout_plies += bb.results[b].sum_depth;
         }
-        for (size_t i = 0; i < bb.delta.size(); ++i) { // playout-trace part of the GLOBAL write
-            s.mast[i].visits += bb.delta[i].visits;
-            s.mast[i].score += bb.delta[i].score;
+        for (size_t e = 0; e < bb.delta.size(); ++e) { // playout-trace part of the GLOBAL write
+            if (!bb.delta[e].visits) continue;
+            const int pl = e >= (size_t)s.S ? 1 : 0;
+            mr_action_stat &m = s.mast[(size_t)pl * s.na + slot_id[e]];
+            m.visits += bb.delta[e].visits;
+            m.score += bb.delta[e].score;
         }
         st.seconds_gpu += t1 - t0;
         st.seconds_backprop += now_s() - t1;
@@ -677,38 +730,47 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         return MR_OK;
     };
 
-    uint32_t done = 0;
-    int in_flight = -1; // slot of the batch on the GPU (pipelined mode)
+    mr_set_kernel_timing(ctx, 0); // two event records and an event wait per batch are not free at 20 us per batch
+    struct TimingGuard {
+        mr_ctx *c;
+        ~TimingGuard() { mr_set_kernel_timing(c, 1); }
+    } timing_guard{ctx};
+
+    uint32_t done = 0, submitted = 0, applied = 0; // batch counters
     while (done < desc->max_iterations) {
         const uint32_t nb = std::min(B, desc->max_iterations - done);
-        const int slot = pipelined ? (in_flight == 0 ? 1 : 0) : 0;
-        int rc = gather_and_submit(slot, done, nb);
-        if (rc != MR_OK) return rc;
+        int rc = gather_and_submit((int)(submitted % depth), done, nb);
+        if (rc != MR_OK) { // leave no batch in flight behind an error
+            for (; applied < submitted; ++applied) mr_wait(ctx, (int)(applied % depth), buf[applied % depth].results.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+            return rc;
+        }
         done += nb;
-        if (pipelined) {
-            if (in_flight >= 0) {
-                rc = wait_and_backprop(in_flight);
-                if (rc != MR_OK) return rc;
+        ++submitted;
+        if (submitted - applied >= depth) {
+            rc = wait_and_backprop((int)(applied % depth));
+            ++applied;
+            if (rc != MR_OK) {
+                for (; applied < submitted; ++applied) mr_wait(ctx, (int)(applied % depth), buf[applied % depth].results.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+                return rc;
             }
-            in_flight = slot;
-        } else {
-            rc = wait_and_backprop(slot);
-            if (rc != MR_OK) return rc;
         }
     }
-    if (pipelined && in_flight >= 0) {
-        int rc = wait_and_backprop(in_flight);
-        if (rc != MR_OK) return rc;
+    for (; applied < submitted; ++applied) {
+        int rc = wait_and_backprop((int)(applied % depth));
+        if (rc != MR_OK) {
+            for (++applied; applied < submitted; ++applied) mr_wait(ctx, (int)(applied % depth), buf[applied % depth].results.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+            return rc;
+        }
     }
 
     // final move: RobustChild over the root children with the same random-offset arg-max (core.rs:138-198)
+    st.nodes = s.t.nodes.size();
+    st.max_tree_depth = s.t.max_depth;
+    out.stats = st;
+    out.children.clear();
+    out.best_action = 0xffff;
     const Node &rootn = s.t.nodes[0];
-    if (rootn.status != EXPANDED || rootn.n_children == 0) {
-        *best_action = 0xffff;
-        if (n_children) *n_children = 0;
-        if (stats) *stats = st;
-        return MR_OK;
-    }
+    if (rootn.status != EXPANDED || rootn.n_children == 0) return MR_OK;
     const uint32_t n = rootn.n_children;
     const int player = rootn.player;
     const double q_unvisited =
@@ -733,20 +795,222 @@ extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf 
         }
         i = (i + stride) % n;
     }
-    *best_action = s.t.action[rootn.first + best_i];
-    if (children && n_children) {
-        *n_children = n;
-        for (uint32_t c = 0; c < n && c < MR_MAX_ROOT_CHILDREN; ++c) {
-            const Stats &e = s.t.edge[rootn.first + c];
-            children[c].action = s.t.action[rootn.first + c];
-            children[c].pad = 0;
-            children[c].visits = e.visits;
-            children[c].score[0] = e.score[0];
-            children[c].score[1] = e.score[1];
-        }
+    out.best_action = s.t.action[rootn.first + best_i];
+    out.children.resize(n);
+    for (uint32_t c = 0; c < n; ++c) {
+        const Stats &e = s.t.edge[rootn.first + c];
+        out.children[c].action = s.t.action[rootn.first + c];
+        out.children[c].pad = 0;
+        out.children[c].visits = e.visits;
+        out.children[c].score[0] = e.score0;
+        out.children[c].score[1] = -e.score0;
     }
-    st.nodes = s.t.nodes.size();
-    st.max_tree_depth = s.t.max_depth;
-    if (stats) *stats = st;
     return MR_OK;
+}
+
+int check_desc(const mr_search_desc *desc) {
+    if (desc->game >= MR_NUM_GAMES || desc->batch_leaves == 0 || desc->playouts_per_leaf == 0 || desc->max_iterations == 0) return MR_ERR_INVALID;
+    if (desc->select > MR_SELECT_AMAF) return MR_ERR_INVALID;
+    if (desc->rave_schedule > MR_RAVE_MIN_MSE) return MR_ERR_INVALID;
+    if (desc->pipeline_depth > MR_NUM_SLOTS) return MR_ERR_INVALID;
+    return MR_OK;
+}
+
+// nothing may unwind across the C boundary: allocation failures of the host tree become an error code
+template <class F>
+int guarded(F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return MR_ERR_NO_MEMORY;
+    } catch (...) {
+        return MR_ERR_INVALID;
+    }
+}
+
+} // namespace
+
+extern "C" int mr_generate_actions(int game, const mr_leaf *state, uint16_t *out) {
+    if (game < 0 || game >= MR_NUM_GAMES || !state || !out) return -1;
+    return mr_host::generate_actions(game, *state, out);
+}
+extern "C" int mr_apply(int game, mr_leaf *state, uint16_t action) {
+    if (game < 0 || game >= MR_NUM_GAMES || !state) return MR_ERR_INVALID;
+    mr_host::apply(game, *state, action);
+    return MR_OK;
+}
+extern "C" int mr_terminal_status(int game, const mr_leaf *state) {
+    if (game < 0 || game >= MR_NUM_GAMES || !state) return -1;
+    return mr_host::terminal_status(game, *state);
+}
+
+extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, uint16_t *best_action,
+                         mr_root_child *children, uint32_t *n_children, mr_search_stats *stats) {
+    if (!ctx || !desc || !root || !best_action) return MR_ERR_INVALID;
+    if (int rc = check_desc(desc)) return rc;
+    return guarded([&]() -> int {
+        RootTotals rt;
+        const int rc = run_search(ctx, desc, root, rt);
+        if (rc != MR_OK) return rc;
+        *best_action = rt.best_action;
+        if (n_children) *n_children = (uint32_t)rt.children.size();
+        if (children && n_children)
+            for (size_t c = 0; c < rt.children.size() && c < MR_MAX_ROOT_CHILDREN; ++c) children[c] = rt.children[c];
+        if (stats) *stats = rt.stats;
+        return MR_OK;
+    });
+}
+
+// search/parallel.rs:56-115.  The reference draws one seed per worker from the search's own rng; here searcher i's seed
+// is words 0..1 of Philox(desc->seed; ctr = (i, 0, 0, 3)), and the final random_best draw is word 0 of ctr = (0, 0, 1, 3).
+extern "C" int mr_search_root_parallel(mr_ctx *const *ctxs, int n_searchers, const mr_search_desc *desc, const mr_leaf *root,
+                                       uint16_t *best_action, mr_root_child *children, uint32_t *n_children, mr_search_stats *stats) {
+    if (!ctxs || n_searchers <= 0 || !desc || !root || !best_action) return MR_ERR_INVALID;
+    for (int i = 0; i < n_searchers; ++i)
+        if (!ctxs[i]) return MR_ERR_INVALID;
+    if (int rc = check_desc(desc)) return rc;
+    return guarded([&]() -> int {
+        std::vector<RootTotals> totals((size_t)n_searchers);
+        std::vector<mr_search_desc> descs((size_t)n_searchers, *desc);
+        std::vector<int> rcs((size_t)n_searchers, MR_OK);
+        for (int i = 0; i < n_searchers; ++i) {
+            uint32_t w[4];
+            philox4(desc->seed, (uint32_t)i, 0, 0, 3, w);
+            descs[(size_t)i].seed = ((uint64_t)w[1] << 32) | w[0];
+        }
+        auto work = [&](int i) {
+            rcs[(size_t)i] = guarded([&]() -> int { return run_search(ctxs[i], &descs[(size_t)i], root, totals[(size_t)i]); });
+        };
+        std::vector<std::thread> threads;
+        for (int i = 1; i < n_searchers; ++i) threads.emplace_back(work, i);
+        work(0);
+        for (auto &th : threads) th.join();
+        for (int i = 0; i < n_searchers; ++i)
+            if (rcs[(size_t)i] != MR_OK) return rcs[(size_t)i];
+        // merged totals per root action (children are in root action-list order in every searcher; a searcher that
+        // never expanded its root reports none)
+        std::vector<mr_root_child> merged;
+        for (const RootTotals &rt : totals) {
+            if (rt.children.empty()) continue;
+            if (merged.empty()) {
+                merged = rt.children;
+                continue;
+            }
+            for (size_t c = 0; c < merged.size(); ++c) {
+                merged[c].visits += rt.children[c].visits;
+                merged[c].score[0] += rt.children[c].score[0];
+                merged[c].score[1] += rt.children[c].score[1];
+            }
+        }
+        *best_action = 0xffff;
+        if (n_children) *n_children = (uint32_t)merged.size();
+        if (!merged.empty()) {
+            // random_best over merged visits (parallel.rs:111-115, util.rs:135-163)
+            const uint32_t n = (uint32_t)merged.size();
+            const uint32_t r = mulhi32(philox_word0(desc->seed, 0, 0, 1, 3), 16u * n);
+            uint32_t i = r / 16u;
+            const uint32_t stride = kPrimes[r % 16u];
+            uint32_t best_i = i, best_v = 0;
+            bool have = false;
+            for (uint32_t c = 0; c < n; ++c) {
+                if (!have || merged[i].visits > best_v) {
+                    have = true;
+                    best_v = merged[i].visits;
+                    best_i = i;
+                }
+                i = (i + stride) % n;
+            }
+            *best_action = merged[best_i].action;
+            if (children)
+                for (size_t c = 0; c < merged.size() && c < MR_MAX_ROOT_CHILDREN; ++c) children[c] = merged[c];
+        }
+        if (stats)
+            for (int i = 0; i < n_searchers; ++i) stats[i] = totals[(size_t)i].stats;
+        return MR_OK;
+    });
+}
+
+// ---- known-answer hooks (include/mcts_rollout.h "Known-answer hooks") ----
+extern "C" double mr_select_score(const mr_search_desc *desc, int player, const mr_edge_stats *current, const mr_edge_stats *child,
+                                  uint32_t grave_n, int64_t grave_q) {
+    if (!desc || !current || player < 0 || player > 1) return NAN;
+    Stats cur;
+    cur.visits = current->visits;
+    cur.vloss = current->vloss;
+    cur.score0 = current->score[0];
+    cur.sumsq = current->sumsq[0];
+    const double parent_log = std::log(std::max(1.0, (double)cur.visits));
+    if (!child) return unvisited_child_score(desc, cur, player, parent_log);
+    Stats e;
+    e.visits = child->visits;
+    e.vloss = child->vloss;
+    e.score0 = child->score[0];
+    e.sumsq = child->sumsq[0];
+    AmafRow row;
+    row.visits = child->amaf_visits;
+    row.score0 = child->amaf_score[0];
+    return created_child_score(desc, e, &row, player, parent_log, grave_n, (double)grave_q);
+}
+
+extern "C" int mr_kat_update_amaf(int game, const mr_leaf *root, const uint16_t *created, uint32_t n_created, uint16_t processed,
+                                  const mr_action_stat *amaf, const int64_t utilities[2], uint32_t k, mr_edge_stats *children_out,
+                                  uint32_t *n_children) {
+    if (game < 0 || game >= MR_NUM_GAMES || !root || !created || !amaf || !utilities || !children_out || !n_children) return MR_ERR_INVALID;
+    return guarded([&]() -> int {
+        mr_search_desc d;
+        memset(&d, 0, sizeof d);
+        d.game = (uint32_t)game;
+        d.select = MR_SELECT_AMAF;
+        Search s;
+        s.ctx = nullptr;
+        s.d = &d;
+        s.t.game = game;
+        s.t.want_amaf_rows = true;
+        s.na = mr_num_actions(game);
+        s.S = mr_num_slots(game);
+        s.t.add_node(*root);
+        s.t.expand(0);
+        const Node &rootn = s.t.nodes[0];
+        if (rootn.status != EXPANDED) return MR_ERR_INVALID;
+        std::vector<PathEntry> path;
+        path.push_back({0, 0});
+        auto create = [&](uint16_t a) -> int {
+            for (uint32_t j = 0; j < rootn.n_children; ++j)
+                if (s.t.action[rootn.first + j] == a) {
+                    if (s.t.child[rootn.first + j] < 0) {
+                        mr_leaf st = rootn.state;
+                        mr_host::apply(game, st, a);
+                        const int32_t id = (int32_t)s.t.add_node(st);
+                        s.t.child[s.t.nodes[0].first + j] = id;
+                    }
+                    return (int)j;
+                }
+            return -1;
+        };
+        for (uint32_t c = 0; c < n_created; ++c)
+            if (create(created[c]) < 0) return MR_ERR_INVALID;
+        const int pj = create(processed);
+        if (pj < 0) return MR_ERR_INVALID;
+        const Node &r2 = s.t.nodes[0];
+        path.push_back({(uint32_t)s.t.child[r2.first + (uint32_t)pj], (uint32_t)pj});
+        // the occurrence table arrives dense ([2][NA], as the ABI's default form); the driver works in slot space
+        std::vector<mr_action_stat> in_slots((size_t)2 * s.S, mr_action_stat{0, 0});
+        for (int pl = 0; pl < 2; ++pl)
+            for (int sl = 0; sl < s.S; ++sl) {
+                const int code = mr_slot_action(game, pl, sl);
+                if (code >= 0) in_slots[(size_t)pl * s.S + sl] = amaf[(size_t)pl * s.na + mr_host::action_id(game, (uint16_t)code)];
+            }
+        s.backprop_amaf(path, in_slots.data(), utilities, k);
+        *n_children = r2.n_children;
+        for (uint32_t j = 0; j < r2.n_children; ++j) {
+            mr_edge_stats &o = children_out[j];
+            memset(&o, 0, sizeof o);
+            o.action = s.t.action[r2.first + j];
+            o.created = s.t.child[r2.first + j] >= 0;
+            o.amaf_visits = s.t.amaf_row[r2.first + j].visits;
+            o.amaf_score[0] = s.t.amaf_row[r2.first + j].score0;
+            o.amaf_score[1] = -s.t.amaf_row[r2.first + j].score0;
+        }
+        return MR_OK;
+    });
 }

@@ -61,7 +61,7 @@ class EndType(IntEnum):  # simulate.rs:15-20 (+ the no-actions ending, :112-116)
     NO_ACTIONS = 2
 
 
-WANT_AMAF, WANT_MAST_DELTA, WANT_TRACE, WANT_FINAL_STATE = 1, 2, 4, 8
+WANT_AMAF, WANT_MAST_DELTA, WANT_TRACE, WANT_FINAL_STATE, TABLES_IN_SLOTS = 1, 2, 4, 8, 16
 
 # BackpropFlags bits (mcts/src/strategies/mcts/config.rs:11-30)
 BACKPROP_GRAVE, BACKPROP_GLOBAL, BACKPROP_AMAF, BACKPROP_NST, BACKPROP_LGR, BACKPROP_LGR2 = 1, 2, 4, 8, 16, 32
@@ -126,6 +126,31 @@ def action_slot(game: Game, player: int, code: int) -> int:
 
 def slot_action(game: Game, player: int, slot: int) -> int:
     return _lib.load().mr_slot_action(int(game), int(player), int(slot))
+
+
+def slot_action_ids(game: Game) -> np.ndarray:
+    """[2][num_slots] dense action id (index into [2][num_actions] tables) of every compact slot, -1 for a slot that
+    names no action of that player (a move off the board)."""
+    g, ns = Game(game), num_slots(game)
+    out = np.full((2, ns), -1, dtype=np.int64)
+    through = g in (Game.BREAKTHROUGH, Game.KNIGHTTHROUGH)
+    for pl in range(2):
+        for sl in range(ns):
+            code = slot_action(g, pl, sl)
+            if code >= 0:
+                out[pl, sl] = (code >> 8) * 64 + (code & 0xFF) if through else code
+    return out
+
+
+def slots_to_dense(game: Game, table: np.ndarray) -> np.ndarray:
+    """Expands a [.., 2, num_slots] STAT_DTYPE table (MR_TABLES_IN_SLOTS) to the dense [.., 2, num_actions] form."""
+    ids = slot_action_ids(game)
+    na = _lib.load().mr_num_actions(int(game))
+    out = np.zeros(table.shape[:-1] + (na,), dtype=table.dtype)
+    for pl in range(2):
+        ok = ids[pl] >= 0
+        out[..., pl, ids[pl][ok]] = table[..., pl, ok]
+    return out
 
 
 # ---- the strategy objects: same names and knobs as the reference ----
@@ -374,13 +399,17 @@ class GpuRollout:
         seed: int | None = None,
         leaf_id_base: int = 0,
         max_playout_depth: int | None = None,
+        tables_in_slots: bool = False,
     ) -> None:
+        """`tables_in_slots`: the AMAF / MAST-delta tables come back indexed by compact per-player action slot,
+        [.., 2, num_slots(game)], instead of by dense action id (MR_TABLES_IN_SLOTS); `slot_action_ids` converts."""
         leaves = np.ascontiguousarray(leaves, dtype=LEAF_DTYPE).reshape(-1)
         flags = (
             (WANT_AMAF if want_amaf else 0)
             | (WANT_MAST_DELTA if want_mast_delta else 0)
             | (WANT_TRACE if want_trace else 0)
             | (WANT_FINAL_STATE if want_final else 0)
+            | (TABLES_IN_SLOTS if tables_in_slots else 0)
         )
         d = self._desc(len(leaves), int(k), flags, seed, leaf_id_base, max_trace if want_trace else 0, max_playout_depth)
         mast = None
@@ -398,8 +427,9 @@ class GpuRollout:
         d = pend.desc
         n, k = d.n_leaves, d.playouts_per_leaf
         res = np.zeros(n, dtype=RESULT_DTYPE)
-        amaf = np.zeros((n, 2, self.na), dtype=STAT_DTYPE) if d.flags & WANT_AMAF else None
-        delta = np.zeros((2, self.na), dtype=STAT_DTYPE) if d.flags & WANT_MAST_DELTA else None
+        tl = self.lib.mr_num_slots(int(self.game)) if d.flags & TABLES_IN_SLOTS else self.na
+        amaf = np.zeros((n, 2, tl), dtype=STAT_DTYPE) if d.flags & WANT_AMAF else None
+        delta = np.zeros((2, tl), dtype=STAT_DTYPE) if d.flags & WANT_MAST_DELTA else None
         trace = np.zeros((n * k, d.max_trace), dtype=np.uint16) if d.flags & WANT_TRACE else None
         rec = np.zeros(n * k, dtype=RECORD_DTYPE) if d.flags & WANT_TRACE else None
         final = np.zeros(n * k, dtype=LEAF_DTYPE) if d.flags & WANT_FINAL_STATE else None
@@ -439,10 +469,16 @@ class GpuRollout:
     ) -> Trial:
         """One playout with the reference's argument meaning (simulate.rs:84-91).
 
-        `prev_action` is accepted and ignored, as every in-scope strategy ignores it.  `rng` names the
+        `prev_action` (compact action code of the move that led to `state`, or None) is the first ply's reply
+        context of the LGR / LGRF-2 / NST strategies (simulate.rs select_move); it travels in the leaf record's
+        `prev` field (`prev_action_plus1`).  The other strategies ignore it, as in the reference.  `rng` names the
         counter-based stream instead of carrying a SmallRng: (seed, leaf_id, playout_id).
         """
         seed, leaf_id, playout_id = rng if rng is not None else (self.seed, 0, 0)
+        if prev_action is not None:
+            state = np.array(np.asarray(state).reshape(-1)[:1], dtype=LEAF_DTYPE)  # a copy: the caller's record is untouched
+            state["prev"] = int(prev_action) + 1
+            state["prev2"] = 0  # a playout's own-previous-move context starts empty (simulate.rs:98)
         depth_cap = self.max_playout_depth if max_playout_depth is None else int(max_playout_depth)
         # playout ids are 0..k-1 inside a batch; run k = playout_id + 1 and keep the last
         max_trace = depth_cap if depth_cap else 512
@@ -532,10 +568,11 @@ class GpuRollout:
     def launch_device(
         self, d_leaves: int, d_results: int, n_leaves: int, k: int, *, stream: int = 0, device_index: int = 0,
         d_amaf: int = 0, d_mast_delta: int = 0, seed: int | None = None, leaf_id_base: int = 0,
-        max_playout_depth: int | None = None,
+        max_playout_depth: int | None = None, tables_in_slots: bool = False,
     ) -> None:
-        """Launch on caller-owned DEVICE buffers (raw pointers) on `stream` (raw cudaStream_t); nothing is copied."""
-        flags = (WANT_AMAF if d_amaf else 0) | (WANT_MAST_DELTA if d_mast_delta else 0)
+        """Launch on caller-owned DEVICE buffers (raw pointers) on `stream` (raw cudaStream_t); nothing is copied.
+        With `tables_in_slots` d_amaf / d_mast_delta are [.., 2, num_slots(game)] instead of [.., 2, num_actions]."""
+        flags = (WANT_AMAF if d_amaf else 0) | (WANT_MAST_DELTA if d_mast_delta else 0) | (TABLES_IN_SLOTS if tables_in_slots else 0)
         d = self._desc(n_leaves, k, flags, seed, leaf_id_base, 0, max_playout_depth)
         self._check(
             self.lib.mr_launch_device(

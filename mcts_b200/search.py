@@ -14,11 +14,11 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import LEAF_DTYPE, MAX_ROOT_CHILDREN, ROOT_CHILD_DTYPE, SearchDesc, SearchStats, ptr
+from ._lib import EDGE_STATS_DTYPE, LEAF_DTYPE, MAX_ROOT_CHILDREN, ROOT_CHILD_DTYPE, SearchDesc, SearchStats, ptr
 from .rollout import Game, GpuRollout, Uniform
 
 SELECT_UCB1, SELECT_UCB1_TUNED, SELECT_GRAVE, SELECT_AMAF = 0, 1, 2, 3
-RAVE_HAND_SELECTED, RAVE_THRESHOLD = 0, 1
+RAVE_HAND_SELECTED, RAVE_THRESHOLD, RAVE_MIN_MSE = 0, 1, 2
 QINIT_PARENT, QINIT_INFINITY = 0, 1
 
 
@@ -34,6 +34,7 @@ class SearchResult:
     seconds_select: float
     seconds_gpu: float
     seconds_backprop: float
+    seconds_submit: float = 0.0
 
 
 class GpuSearch:
@@ -41,18 +42,27 @@ class GpuSearch:
 
     def __init__(self, game: Game, strategy=None, *, max_iterations=10_000, batch_leaves=256, num_rollouts_per_leaf=1,
                  expand_threshold=1, max_playout_depth=0, exploration_constant=math.sqrt(2.0), select=SELECT_UCB1,
-                 q_init=QINIT_PARENT, use_transpositions=False, pipelined=False, grave_threshold=700, rave_schedule=RAVE_HAND_SELECTED,
-                 rave_param=1000, amaf_alpha=1.0, seed=0, devices=1):
+                 q_init=QINIT_PARENT, use_transpositions=False, pipelined=False, pipeline_depth=0, grave_threshold=700,
+                 rave_schedule=RAVE_HAND_SELECTED, rave_param=1000, rave_bias=0.0, amaf_alpha=1.0, seed=0, devices=1, num_threads=1):
+        """`pipeline_depth` batches in flight (`pipelined=True` = 2).  `num_threads` > 1 = the reference's root-parallel
+        search (SearchConfig.num_threads, search/parallel.rs:56-115): that many independent searchers of
+        `max_iterations` iterations each, one host thread and one rollout context per searcher on the same device(s),
+        root-child totals merged."""
         self.rollout = GpuRollout(game, strategy or Uniform(), devices=devices, seed=seed, max_playout_depth=max_playout_depth)
+        self.extra_rollouts = [GpuRollout(game, strategy or Uniform(), devices=devices, seed=seed, max_playout_depth=max_playout_depth)
+                               for _ in range(max(1, int(num_threads)) - 1)]
         self.desc = SearchDesc(
             int(game), int(self.rollout.strategy.policy), select, q_init, max_iterations, batch_leaves,
             num_rollouts_per_leaf, expand_threshold, max_playout_depth, (1 if use_transpositions else 0) | (2 if pipelined else 0), exploration_constant,
             float(getattr(self.rollout.strategy, "epsilon", 0.0)), int(seed) & 0xFFFFFFFFFFFFFFFF,
             grave_threshold, rave_schedule, rave_param, int(getattr(self.rollout.strategy, "backoff_threshold", 5)), float(amaf_alpha),
+            float(rave_bias), int(pipeline_depth), 0,
         )
 
     def close(self):
         self.rollout.close()
+        for r in self.extra_rollouts:
+            r.close()
 
     def __enter__(self):
         return self
@@ -63,11 +73,57 @@ class GpuSearch:
     def choose_action(self, state: np.ndarray) -> SearchResult:
         root = np.ascontiguousarray(state, dtype=LEAF_DTYPE).reshape(-1)[:1]
         children = np.zeros(MAX_ROOT_CHILDREN, dtype=ROOT_CHILD_DTYPE)
-        best, n, st = C.c_uint16(), C.c_uint32(), SearchStats()
+        best, n = C.c_uint16(), C.c_uint32()
         L = _lib.load()
+        if self.extra_rollouts:
+            ctxs = [self.rollout] + self.extra_rollouts
+            handles = (C.c_void_p * len(ctxs))(*[r._h for r in ctxs])
+            sts = (SearchStats * len(ctxs))()
+            rc = L.mr_search_root_parallel(handles, len(ctxs), C.byref(self.desc), ptr(root), C.byref(best), ptr(children), C.byref(n), sts)
+            self.rollout._check(rc)
+            return SearchResult(
+                best.value, children[: n.value].copy(), sum(s.playouts for s in sts), sum(s.playout_plies for s in sts),
+                sum(s.nodes for s in sts), sum(s.batches for s in sts), max(s.max_tree_depth for s in sts),
+                max(s.seconds_select for s in sts), max(s.seconds_gpu for s in sts), max(s.seconds_backprop for s in sts),
+                max(s.seconds_submit for s in sts))
+        st = SearchStats()
         self.rollout._check(L.mr_search(self.rollout._h, C.byref(self.desc), ptr(root), C.byref(best), ptr(children), C.byref(n), C.byref(st)))
         return SearchResult(best.value, children[: n.value].copy(), st.playouts, st.playout_plies, st.nodes, st.batches,
-                            st.max_tree_depth, st.seconds_select, st.seconds_gpu, st.seconds_backprop)
+                            st.max_tree_depth, st.seconds_select, st.seconds_gpu, st.seconds_backprop, st.seconds_submit)
+
+
+def edge_stats(visits=0, vloss=0, score=(0, 0), sumsq=(0, 0), amaf_visits=0, amaf_score=(0, 0)) -> np.ndarray:
+    """One NodeStats / ChildArray row for the known-answer hooks."""
+    e = np.zeros(1, dtype=EDGE_STATS_DTYPE)
+    e["visits"], e["vloss"], e["score"], e["sumsq"], e["amaf_visits"], e["amaf_score"] = visits, vloss, score, sumsq, amaf_visits, amaf_score
+    return e
+
+
+def select_score(desc: SearchDesc, player: int, current: np.ndarray, child, grave_n: int = 0, grave_q: int = 0) -> float:
+    """mr_select_score: the tree driver's selection formula on hand-built statistics (host code, no GPU needed)."""
+    return _lib.load().mr_select_score(C.byref(desc), int(player), ptr(current), ptr(child) if child is not None else None, int(grave_n), int(grave_q))
+
+
+def make_search_desc(game=0, *, select=SELECT_UCB1, q_init=QINIT_PARENT, exploration_constant=math.sqrt(2.0), grave_threshold=700,
+                     rave_schedule=RAVE_HAND_SELECTED, rave_param=1000, rave_bias=0.0, amaf_alpha=1.0) -> SearchDesc:
+    return SearchDesc(int(game), 0, select, q_init, 1, 1, 1, 1, 0, 0, exploration_constant, 0.0, 0, grave_threshold, rave_schedule,
+                      rave_param, 5, float(amaf_alpha), float(rave_bias), 0, 0)
+
+
+def kat_update_amaf(game: Game, root: np.ndarray, created, processed: int, amaf: np.ndarray, utilities, k: int = 1) -> np.ndarray:
+    """mr_kat_update_amaf: update_amaf (backprop.rs:565-617) on a hand-built two-level tree (host code, no GPU needed)."""
+    from ._lib import STAT_DTYPE
+
+    root = np.ascontiguousarray(root, dtype=LEAF_DTYPE).reshape(-1)[:1]
+    created = np.ascontiguousarray(created, dtype=np.uint16)
+    amaf = np.ascontiguousarray(amaf, dtype=STAT_DTYPE)
+    util = np.ascontiguousarray(utilities, dtype=np.int64)
+    out = np.zeros(MAX_ROOT_CHILDREN, dtype=EDGE_STATS_DTYPE)
+    n = C.c_uint32()
+    rc = _lib.load().mr_kat_update_amaf(int(game), ptr(root), ptr(created), len(created), int(processed), ptr(amaf), ptr(util), int(k), ptr(out), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"mr_kat_update_amaf failed: {rc}")
+    return out[: n.value].copy()
 
 
 def choose_action_root_parallel(search: GpuSearch, state: np.ndarray, *, device=None, group=None, draw: int = 0):

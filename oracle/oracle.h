@@ -194,17 +194,20 @@ typedef struct {
     uint32_t expand_threshold;
     uint32_t max_playout_depth;
     int threads;                /* for the playouts of one batch */
-    int pipelined;              /* batch N+1 is gathered before batch N's results are applied (deterministic order) */
+    int pipeline_depth;         /* batches in flight (<= 1: none): batch n is gathered before the results of batches
+                                   n - depth + 1 .. n - 1 are applied (deterministic order) */
     int use_transpositions;     /* SearchConfig.use_transpositions: identical states share a node (shared.rs:412-436) */
     double exploration_c;
     uint64_t eps_threshold;
     uint64_t seed;
     uint32_t grave_threshold;   /* Rave.threshold */
-    int rave_schedule;          /* 0 HandSelected{k}, 1 Threshold{rave} (rave.rs:42-76) */
+    int rave_schedule;          /* 0 HandSelected{k}, 1 Threshold{rave}, 2 MinMSE{bias} (rave.rs:42-76) */
     uint32_t rave_param;
     double amaf_alpha;          /* select 3: alpha * amaf + (1 - alpha) * ucb1 (select/amaf.rs:58-74), reference default 1 */
     uint32_t nst_threshold;     /* ORC_EPS_NST: Nst::backoff_threshold (simulate.rs:875-881, reference default 5) */
+    double rave_bias;           /* rave_schedule 2 = MinMSE{bias} (rave.rs:68) */
 } orc_search_cfg;
+#define ORC_MAX_PIPELINE 4
 
 typedef struct {
     uint16_t action;
@@ -215,6 +218,21 @@ typedef struct {
 
 int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_action, orc_root_child *children,
                uint32_t *n_children, uint64_t *playout_plies);
+
+/* known-answer hooks (search.c): one NodeStats / ChildArray row, the selection formulas and update_amaf on hand-built
+ * inputs -- the restated forms of mcts-tests/tests/ttt_strategies.rs:658-736 and of select/ucb.rs, rave.rs, amaf.rs */
+typedef struct {
+    uint32_t visits, vloss;
+    int64_t score[2], sumsq[2];
+    uint32_t amaf_visits;
+    uint16_t action, created;
+    int64_t amaf_score[2];
+} orc_edge_stats;
+double orc_select_score(const orc_search_cfg *c, int player, const orc_edge_stats *current, const orc_edge_stats *child,
+                        uint32_t grave_n, int64_t grave_q);
+int orc_kat_update_amaf(int game, const orc_state *root, const uint16_t *created, uint32_t n_created, uint16_t processed,
+                        const orc_action_stat *amaf, const int64_t utilities[2], uint32_t k, orc_edge_stats *children_out,
+                        uint32_t *n_children);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,11 @@
  *
  * Batched mode (batch_leaves > 1) is the deterministic, sequential statement of what the tree-parallel
  * workers do concurrently (search/parallel.rs:188-251): B descents that each leave their virtual losses in
- * place, then all simulations, then all backprops.
+ * place, then all simulations, then all backprops -- with up to pipeline_depth batches gathered before the oldest
+ * one is applied.  As in the product's driver the expansion test counts the trials still in flight through a node
+ * (num_visits + in-flight < expand_threshold => simulate from here), so a node whose first simulation has not come
+ * back is expanded by the next descent that reaches it instead of being queued again; with one leaf per batch
+ * nothing is ever in flight and the loop is the reference's (search_impl.rs:76-114).
  * Tree tie-break draws: Philox4x32-10, ctr = (descent id, depth, 0, 2), word 0.
  */
 #include "oracle.h"
@@ -60,6 +64,8 @@ typedef struct {
     stats_t *edge;
     size_t n_edges, cap_edges;
     stats_t root_stats;
+    uint64_t root_inflight; /* trials gathered through the root whose results have not been applied yet (the root has no
+                               edge to carry virtual losses, and root_stats itself stays as the reference keeps it) */
     /* use_transpositions: open-addressing table state -> node id (table.rs keyed by zobrist hash in the
      * reference; keyed by the whole state here, which cannot collide) */
     int use_table;
@@ -226,6 +232,7 @@ typedef struct {
     uint32_t rave_param;
     grave_t *grave;
     double amaf_alpha;
+    double rave_bias;
 } sel_cfg;
 
 static int action_id(int game, uint16_t a);
@@ -242,15 +249,56 @@ static uint32_t grave_ref(const tree_t *t, const sel_cfg *cfg, const entry_t *pa
     return 0;
 }
 
+/* value of a child that does not exist yet: node.rs:139-159 value_estimate_unvisited plus the strategy's exploration
+ * term (ucb.rs:55-61, :134-146; none for Rave / Amaf, rave.rs:226-230, amaf.rs:76-79) */
+static double unvisited_score(const sel_cfg *cfg, const stats_t *cur, int player, double parent_log) {
+    double q_unvisited = cfg->q_init == 1 ? 10000.0 : (cur->visits == 0 ? 10000.0 : expected_score(cur, player));
+    return cfg->select == 1   ? q_unvisited + (parent_log * fmin(1.0, 1.0) + cfg->c * sqrt(parent_log))
+           : (cfg->select == 2 || cfg->select == 3) ? q_unvisited
+                              : q_unvisited + cfg->c * sqrt(parent_log);
+}
+
+/* score of a created child; amaf_n / amaf_q = the GRAVE reference node's entry for (mover, action) */
+static double created_score(const sel_cfg *cfg, const stats_t *e, int player, double parent_log, uint32_t amaf_n, double amaf_q) {
+    double exploit = expected_score(e, player);
+    double total = (double)(e->visits + e->vloss);
+    if (cfg->select == 1) { /* ucb.rs:90-132 */
+        double var = fmax(0.0, (double)e->sumsq[player] / total - exploit * exploit);
+        double frac = parent_log / total;
+        return exploit + (frac * fmin(1.0, var) + cfg->c * sqrt(frac));
+    }
+    if (cfg->select == 2) { /* rave.rs:196-224 */
+        uint32_t n_tot = e->visits + e->vloss;
+        double explore = cfg->c * sqrt(parent_log / (double)n_tot);
+        double b;
+        if (cfg->rave_schedule == 1) {
+            double rave = (double)cfg->rave_param;
+            b = fmax(0.0, rave - (double)n_tot) / rave;
+        } else if (cfg->rave_schedule == 2) { /* MinMSE { bias }, rave.rs:68 */
+            double nn = (double)n_tot, an = (double)amaf_n;
+            b = an / (nn + an + 4. * nn * an * cfg->rave_bias * cfg->rave_bias);
+        } else {
+            double kk = (double)cfg->rave_param;
+            b = sqrt(kk / (3.0 * (double)n_tot + kk));
+        }
+        double amaf = amaf_n == 0 ? 0.0 : amaf_q / (double)amaf_n;
+        return (1.0 - b) * exploit + b * amaf + explore;
+    }
+    if (cfg->select == 3) { /* amaf.rs:58-74 */
+        double an = (double)(e->amaf_visits > 1u ? e->amaf_visits : 1u);
+        double amaf = (double)e->amaf_score[player] / an;
+        double ucb1 = exploit + cfg->c * sqrt(parent_log / total);
+        return cfg->amaf_alpha * amaf + (1.0 - cfg->amaf_alpha) * ucb1;
+    }
+    return exploit + cfg->c * sqrt(parent_log / total); /* ucb.rs:40-52 */
+}
+
 static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *path, int len, uint32_t descent) {
     const node_t *node = &t->nodes[path[len - 1].node];
     int player = node->player;
     const stats_t *cur = current_stats(t, path, len);
     double parent_log = log(fmax(1.0, (double)cur->visits)); /* ucb.rs:34-37 */
-    double q_unvisited = cfg->q_init == 1 ? 10000.0 : (cur->visits == 0 ? 10000.0 : expected_score(cur, player));
-    double unvisited_value = cfg->select == 1   ? q_unvisited + (parent_log * fmin(1.0, 1.0) + cfg->c * sqrt(parent_log))
-                             : (cfg->select == 2 || cfg->select == 3) ? q_unvisited /* rave.rs:226-230, amaf.rs:76-79 */
-                                                : q_unvisited + cfg->c * sqrt(parent_log);
+    double unvisited_value = unvisited_score(cfg, cur, player, parent_log);
     uint32_t n = (uint32_t)node->n_children;
     uint32_t r = (uint32_t)(((uint64_t)tree_draw(cfg->seed, descent, (uint32_t)len - 1) * (16u * n)) >> 32);
     uint32_t i = r / 16u, stride = PRIMES[r % 16u];
@@ -263,42 +311,18 @@ static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *p
         if (t->child[node->first + i] < 0) {
             score = unvisited_value;
         } else {
-            double exploit = expected_score(e, player);
-            double total = (double)(e->visits + e->vloss);
-            if (cfg->select == 1) { /* ucb.rs:90-132 */
-                double var = fmax(0.0, (double)e->sumsq[player] / total - exploit * exploit);
-                double frac = parent_log / total;
-                score = exploit + (frac * fmin(1.0, var) + cfg->c * sqrt(frac));
-            } else if (cfg->select == 2) { /* rave.rs:196-224 */
+            uint32_t amaf_n = 0;
+            double amaf_q = 0.0;
+            if (cfg->select == 2) {
                 uint32_t ref = grave_ref(t, cfg, path, len, (uint32_t)t->child[node->first + i], i);
-                uint32_t amaf_n = 0;
-                double amaf_q = 0.0;
                 gstat_t *tab = grave_find(cfg->grave, &t->nodes[ref].state, 0);
                 if (tab) {
                     const gstat_t *g = &tab[(size_t)player * cfg->grave->na + action_id(t->game, t->action[node->first + i])];
                     amaf_n = g->visits;
                     amaf_q = (double)g->score;
                 }
-                uint32_t n_tot = e->visits + e->vloss;
-                double explore = cfg->c * sqrt(parent_log / (double)n_tot);
-                double b;
-                if (cfg->rave_schedule == 1) {
-                    double rave = (double)cfg->rave_param;
-                    b = fmax(0.0, rave - (double)n_tot) / rave;
-                } else {
-                    double kk = (double)cfg->rave_param;
-                    b = sqrt(kk / (3.0 * (double)n_tot + kk));
-                }
-                double amaf = amaf_n == 0 ? 0.0 : amaf_q / (double)amaf_n;
-                score = (1.0 - b) * exploit + b * amaf + explore;
-            } else if (cfg->select == 3) { /* amaf.rs:58-74 */
-                double amaf_n = (double)(e->amaf_visits > 1u ? e->amaf_visits : 1u);
-                double amaf = (double)e->amaf_score[player] / amaf_n;
-                double ucb1 = exploit + cfg->c * sqrt(parent_log / total);
-                score = cfg->amaf_alpha * amaf + (1.0 - cfg->amaf_alpha) * ucb1;
-            } else { /* ucb.rs:40-52 */
-                score = exploit + cfg->c * sqrt(parent_log / total);
             }
+            score = created_score(cfg, e, player, parent_log, amaf_n, amaf_q);
         }
         if (!have || score > best) {
             have = 1;
@@ -318,9 +342,12 @@ static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t 
         path[len].node = cur;
         path[len].idx = incoming;
         ++len;
-        uint32_t num_visits = current_stats(t, path, len)->visits;
+        const stats_t *cs = current_stats(t, path, len);
+        /* trials in flight through this node from other descents: k virtual losses per gathered descent on each of its
+         * edges (root_inflight for the root); this descent has put 1 on the edge it just came down */
+        uint64_t in_flight = len == 1 ? t->root_inflight : cs->vloss - 1u;
         if (t->nodes[cur].status == 2) return len;
-        if (num_visits < cfg->expand_threshold) return len;
+        if ((uint64_t)cs->visits + in_flight < cfg->expand_threshold) return len;
         if (t->nodes[cur].status == 0) {
             expand(t, cur);
             if (t->nodes[cur].status == 2) return len;
@@ -352,6 +379,36 @@ static int action_id(int game, uint16_t a) {
     return (int)a;
 }
 
+/* update_amaf (backprop.rs:565-617) for the k trials of one leaf, for every non-root path node X, leaf first:
+ * occurrences of (action, mover of X's parent) in [playout trace + path edges below X] that name a created child of the
+ * parent add one AMAF visit and the trial's utilities to that child's row.  `la` = the leaf's occurrence table [2][na]. */
+static void update_amaf_path(tree_t *t, const entry_t *path, int len, const orc_action_stat *la, int na, const int64_t u[2],
+                             uint32_t k, uint32_t *below_a, int *below_p) {
+    int n_below = 0;
+    for (int i = len - 1; i >= 1; --i) {
+        const node_t *parent = &t->nodes[path[i - 1].node];
+        int mover = parent->player;
+        for (int j = 0; j < parent->n_children; ++j) {
+            if (t->child[parent->first + j] < 0) continue;
+            uint32_t a = (uint32_t)action_id(t->game, t->action[parent->first + j]);
+            uint32_t cnt = la[(size_t)mover * na + a].visits;
+            int64_t sc = la[(size_t)mover * na + a].score;
+            for (int q = 0; q < n_below; ++q)
+                if (below_p[q] == mover && below_a[q] == a) {
+                    cnt += k;
+                    sc += u[mover];
+                }
+            stats_t *e = &t->edge[parent->first + j];
+            e->amaf_visits += cnt;
+            e->amaf_score[mover] += sc;
+            e->amaf_score[1 - mover] -= sc;
+        }
+        below_a[n_below] = (uint32_t)action_id(t->game, t->action[parent->first + path[i].idx]);
+        below_p[n_below] = mover;
+        ++n_below;
+    }
+}
+
 int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_action, orc_root_child *children,
                uint32_t *n_children, uint64_t *playout_plies) {
     tree_t t;
@@ -364,7 +421,8 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     memset(&grave, 0, sizeof grave);
     grave.na = orc_num_actions(c->game);
     sel_cfg cfg = {c->select, c->q_init, c->exploration_c, c->expand_threshold, c->seed, c->grave_threshold, c->rave_schedule,
-                   c->rave_param, &grave, c->amaf_alpha};
+                   c->rave_param, &grave, c->amaf_alpha, c->rave_bias};
+    int depth = c->pipeline_depth < 1 ? 1 : (c->pipeline_depth > ORC_MAX_PIPELINE ? ORC_MAX_PIPELINE : c->pipeline_depth);
     const int want_amaf = c->select == 2 || c->select == 3;
     const uint32_t B = c->batch_leaves, k = c->playouts_per_leaf;
     const int na = orc_num_actions(c->game);
@@ -373,34 +431,29 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     /* TreeStats.player_bigram_actions (shared.rs:60-66) as [2][S][S] over compact action slots, and one delta per buffer set */
     const size_t S = (size_t)orc_num_slots(c->game);
     orc_action_stat *bigram = nst ? (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat)) : NULL;
-    orc_action_stat *bg_delta[2] = {NULL, NULL};
-    for (int q = 0; q < 2 && nst; ++q) bg_delta[q] = (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat));
-    orc_action_stat *delta = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    orc_action_stat *bg_delta[ORC_MAX_PIPELINE] = {NULL};
+    for (int q = 0; q < depth && nst; ++q) bg_delta[q] = (orc_action_stat *)calloc(2 * S * S, sizeof(orc_action_stat));
     const int lgr2 = c->policy == ORC_EPS_LGR2 || c->policy == ORC_EPS_LGR2_MAST;
     const int lgr = c->policy == ORC_EPS_LGR || lgr2; /* LGRF-2 keeps the LGR-1 table too (its inner strategy) */
     uint16_t *replies2 = lgr2 ? (uint16_t *)calloc(2 * S * S, sizeof(uint16_t)) : NULL;
     const uint32_t trace_cap = c->max_playout_depth ? c->max_playout_depth : 256;
-    uint16_t *trace2[2] = {NULL, NULL};
-    orc_playout_record *rec2[2] = {NULL, NULL};
-    for (int q = 0; q < 2 && lgr2; ++q) {
+    uint16_t *trace2[ORC_MAX_PIPELINE] = {NULL};
+    orc_playout_record *rec2[ORC_MAX_PIPELINE] = {NULL};
+    for (int q = 0; q < depth && lgr2; ++q) {
         trace2[q] = (uint16_t *)calloc((size_t)c->batch_leaves * c->playouts_per_leaf * trace_cap, sizeof(uint16_t));
         rec2[q] = (orc_playout_record *)calloc((size_t)c->batch_leaves * c->playouts_per_leaf, sizeof(orc_playout_record));
     }
     uint16_t *replies = lgr ? (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t)) : NULL;
-    uint64_t *upd_order[2] = {NULL, NULL};
-    uint16_t *upd_action[2] = {NULL, NULL};
-    uint32_t *last_win[2] = {NULL, NULL};
-    for (int q = 0; q < 2 && lgr; ++q) {
+    uint64_t *upd_order[ORC_MAX_PIPELINE] = {NULL};
+    uint16_t *upd_action[ORC_MAX_PIPELINE] = {NULL};
+    uint32_t *last_win[ORC_MAX_PIPELINE] = {NULL};
+    for (int q = 0; q < depth && lgr; ++q) {
         upd_order[q] = (uint64_t *)calloc((size_t)2 * na, sizeof(uint64_t));
         upd_action[q] = (uint16_t *)calloc((size_t)2 * na, sizeof(uint16_t));
         last_win[q] = (uint32_t *)calloc((size_t)2 * c->batch_leaves, sizeof(uint32_t));
     }
     const int max_path = 1024;
-    entry_t *paths = (entry_t *)malloc(sizeof(entry_t) * (size_t)B * max_path);
-    int *plen = (int *)malloc(sizeof(int) * B);
     orc_state *leaves = (orc_state *)malloc(sizeof(orc_state) * B);
-    orc_leaf_result *results = (orc_leaf_result *)malloc(sizeof(orc_leaf_result) * B);
-    orc_action_stat *amaf = want_amaf ? (orc_action_stat *)malloc(sizeof(orc_action_stat) * (size_t)B * 2 * na) : NULL;
     uint32_t *below_a = (uint32_t *)malloc(sizeof(uint32_t) * 1024);
     int *below_p = (int *)malloc(sizeof(int) * 1024);
     uint64_t plies = 0;
@@ -414,27 +467,29 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     bd.seed = c->seed;
     bd.playouts_per_leaf = k;
 
-    /* Two buffer sets: in pipelined mode batch N+1 is gathered (seeing batch N's virtual losses, not its results)
-     * before batch N is applied -- the fixed order gather(N+1), simulate(N+1), backprop(N). */
-    entry_t *paths2 = (entry_t *)malloc(sizeof(entry_t) * (size_t)B * max_path);
-    int *plen2 = (int *)malloc(sizeof(int) * B);
-    orc_leaf_result *results2 = (orc_leaf_result *)malloc(sizeof(orc_leaf_result) * B);
-    orc_action_stat *amaf2 = want_amaf ? (orc_action_stat *)malloc(sizeof(orc_action_stat) * (size_t)B * 2 * na) : NULL;
-    orc_action_stat *delta2 = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
-    entry_t *set_paths[2] = {paths, paths2};
-    int *set_plen[2] = {plen, plen2};
-    orc_leaf_result *set_res[2] = {results, results2};
-    orc_action_stat *set_amaf[2] = {amaf, amaf2};
-    orc_action_stat *set_delta[2] = {delta, delta2};
-    uint32_t set_nb[2] = {0, 0};
+    /* One buffer set per batch in flight: batch n is gathered and simulated into set n % depth before the results of
+     * batches n - depth + 1 .. n - 1 are applied -- the fixed order gather(n), simulate(n), backprop(n - depth + 1). */
+    entry_t *set_paths[ORC_MAX_PIPELINE] = {NULL};
+    int *set_plen[ORC_MAX_PIPELINE] = {NULL};
+    orc_leaf_result *set_res[ORC_MAX_PIPELINE] = {NULL};
+    orc_action_stat *set_amaf[ORC_MAX_PIPELINE] = {NULL};
+    orc_action_stat *set_delta[ORC_MAX_PIPELINE] = {NULL};
+    uint32_t set_nb[ORC_MAX_PIPELINE] = {0};
+    for (int q = 0; q < depth; ++q) {
+        set_paths[q] = (entry_t *)malloc(sizeof(entry_t) * (size_t)B * max_path);
+        set_plen[q] = (int *)malloc(sizeof(int) * B);
+        set_res[q] = (orc_leaf_result *)malloc(sizeof(orc_leaf_result) * B);
+        set_amaf[q] = want_amaf ? (orc_action_stat *)malloc(sizeof(orc_action_stat) * (size_t)B * 2 * na) : NULL;
+        set_delta[q] = mast ? (orc_action_stat *)calloc((size_t)2 * na, sizeof(orc_action_stat)) : NULL;
+    }
 
-    uint32_t done = 0;
-    int in_flight = -1;
+    uint32_t done = 0, submitted = 0, applied = 0;
     for (;;) {
         int slot = -1;
         if (done < c->max_iterations) {
             /* ---- gather + simulate one batch into `slot` ---- */
-            slot = c->pipelined ? (in_flight == 0 ? 1 : 0) : 0;
+            slot = (int)(submitted % (uint32_t)depth);
+            ++submitted;
             uint32_t nb = B < c->max_iterations - done ? B : c->max_iterations - done;
             set_nb[slot] = nb;
             for (uint32_t b = 0; b < nb; ++b) {
@@ -442,6 +497,7 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                 set_plen[slot][b] = select_step(&t, &cfg, done + b, path);
                 for (int i = 1; i < set_plen[slot][b]; ++i) /* add_path_virtual_loss(k - 1), shared.rs:787-805 */
                     t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
+                t.root_inflight += k; /* the k trials now in flight through the root */
                 leaves[b] = t.nodes[path[set_plen[slot][b] - 1].node].state;
                 if ((lgr || nst) && set_plen[slot][b] > 1) { /* playout()'s prev_action: the last edge of the descent */
                     int L = set_plen[slot][b];
@@ -467,17 +523,11 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                               lgr2 ? rec2[slot] : NULL, NULL, c->threads > 0 ? c->threads : 1);
             done += nb;
         }
-        /* ---- which batch gets applied now ---- */
-        int apply;
-        if (c->pipelined) {
-            apply = in_flight;
-            in_flight = slot;
-            if (apply < 0 && slot < 0) break;
-            if (apply < 0) continue;
-        } else {
-            if (slot < 0) break;
-            apply = slot;
-        }
+        /* ---- which batch gets applied now: the oldest one, once `depth` batches are in flight (or nothing is left to gather) ---- */
+        if (slot >= 0 && submitted - applied < (uint32_t)depth) continue;
+        if (applied == submitted) break;
+        const int apply = (int)(applied % (uint32_t)depth);
+        ++applied;
         if (lgr) { /* backprop.rs:908-923 over the whole batch: tree-path pairs join the playout stamps, then one write per key */
             for (uint32_t b = 0; b < set_nb[apply]; ++b) {
                 const entry_t *path = set_paths[apply] + (size_t)b * max_path;
@@ -540,35 +590,8 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
             const orc_leaf_result *r = &set_res[apply][b];
             int64_t nonzero = (int64_t)k - r->draws;
             int64_t u[2] = {(int64_t)r->wins[0] - (nonzero - r->wins[0]), (int64_t)r->wins[1] - (nonzero - r->wins[1])};
-            if (set_amaf[apply] && c->select == 3) {
-                /* update_amaf (backprop.rs:565-617) for every non-root path node X, leaf first: occurrences of
-                 * (action, mover of X's parent) in [playout trace + path edges below X] that name a created child
-                 * of the parent add one AMAF visit and the trial's utilities to that child's row */
-                const orc_action_stat *la = set_amaf[apply] + (size_t)b * 2 * na;
-                int n_below = 0;
-                for (int i = plen_a[b] - 1; i >= 1; --i) {
-                    const node_t *parent = &t.nodes[path[i - 1].node];
-                    int mover = parent->player;
-                    for (int j = 0; j < parent->n_children; ++j) {
-                        if (t.child[parent->first + j] < 0) continue;
-                        uint32_t a = (uint32_t)action_id(c->game, t.action[parent->first + j]);
-                        uint32_t cnt = la[(size_t)mover * na + a].visits;
-                        int64_t sc = la[(size_t)mover * na + a].score;
-                        for (int q = 0; q < n_below; ++q)
-                            if (below_p[q] == mover && below_a[q] == a) {
-                                cnt += k;
-                                sc += u[mover];
-                            }
-                        stats_t *e = &t.edge[parent->first + j];
-                        e->amaf_visits += cnt;
-                        e->amaf_score[mover] += sc;
-                        e->amaf_score[1 - mover] -= sc;
-                    }
-                    below_a[n_below] = (uint32_t)action_id(c->game, t.action[parent->first + path[i].idx]);
-                    below_p[n_below] = mover;
-                    ++n_below;
-                }
-            }
+            if (set_amaf[apply] && c->select == 3)
+                update_amaf_path(&t, path, plen_a[b], set_amaf[apply] + (size_t)b * 2 * na, na, u, k, below_a, below_p);
             if (set_amaf[apply] && c->select == 2) { /* update_grave for every non-root path node, leaf first (backprop.rs:619-640, 833-854) */
                 const orc_action_stat *la = set_amaf[apply] + (size_t)b * 2 * na;
                 int n_below = 0;
@@ -596,6 +619,7 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                     s->score[p] += u[p];
                     s->sumsq[p] += nonzero;
                 }
+                if (i == 0) t.root_inflight -= k;
                 if (i > 0) {
                     s->vloss -= k;
                     if (mast) { /* tree-path part of the GLOBAL write */
@@ -629,13 +653,7 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
                 mast[i].visits += set_delta[apply][i].visits;
                 mast[i].score += set_delta[apply][i].score;
             }
-        if (!c->pipelined && done >= c->max_iterations) break;
     }
-    free(paths2);
-    free(plen2);
-    free(results2);
-    free(amaf2);
-    free(delta2);
 
     const node_t *rootn = &t.nodes[0];
     int rc = 0;
@@ -689,26 +707,94 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     free(grave.slots);
     free(replies);
     free(replies2);
-    for (int q = 0; q < 2; ++q) {
+    free(bigram);
+    for (int q = 0; q < ORC_MAX_PIPELINE; ++q) {
         free(trace2[q]);
         free(rec2[q]);
-    }
-    free(bigram);
-    free(bg_delta[0]);
-    free(bg_delta[1]);
-    for (int q = 0; q < 2; ++q) {
+        free(bg_delta[q]);
         free(upd_order[q]);
         free(upd_action[q]);
         free(last_win[q]);
+        free(set_paths[q]);
+        free(set_plen[q]);
+        free(set_res[q]);
+        free(set_amaf[q]);
+        free(set_delta[q]);
     }
-    free(amaf);
     free(below_a);
     free(below_p);
     free(mast);
-    free(delta);
-    free(paths);
-    free(plen);
     free(leaves);
-    free(results);
     return rc;
+}
+
+/* ---- known-answer hooks: the formulas and the AMAF update above on hand-built inputs (the checker's side of the
+ * product's mr_select_score / mr_kat_update_amaf) ---- */
+static void stats_from_edge(stats_t *s, const orc_edge_stats *e) {
+    memset(s, 0, sizeof *s);
+    s->visits = e->visits;
+    s->vloss = e->vloss;
+    for (int p = 0; p < 2; ++p) {
+        s->score[p] = e->score[p];
+        s->sumsq[p] = e->sumsq[p];
+        s->amaf_score[p] = e->amaf_score[p];
+    }
+    s->amaf_visits = e->amaf_visits;
+}
+
+double orc_select_score(const orc_search_cfg *c, int player, const orc_edge_stats *current, const orc_edge_stats *child,
+                        uint32_t grave_n, int64_t grave_q) {
+    sel_cfg cfg = {c->select, c->q_init, c->exploration_c, c->expand_threshold, c->seed, c->grave_threshold, c->rave_schedule,
+                   c->rave_param, NULL, c->amaf_alpha, c->rave_bias};
+    stats_t cur, e;
+    stats_from_edge(&cur, current);
+    double parent_log = log(fmax(1.0, (double)cur.visits));
+    if (!child) return unvisited_score(&cfg, &cur, player, parent_log);
+    stats_from_edge(&e, child);
+    return created_score(&cfg, &e, player, parent_log, grave_n, (double)grave_q);
+}
+
+int orc_kat_update_amaf(int game, const orc_state *root, const uint16_t *created, uint32_t n_created, uint16_t processed,
+                        const orc_action_stat *amaf, const int64_t utilities[2], uint32_t k, orc_edge_stats *children_out,
+                        uint32_t *n_children) {
+    tree_t t;
+    memset(&t, 0, sizeof t);
+    t.game = game;
+    add_node(&t, root);
+    expand(&t, 0);
+    if (t.nodes[0].status != 1) return 1;
+    int pj = -1;
+    for (uint32_t c = 0; c <= n_created; ++c) {
+        uint16_t a = c < n_created ? created[c] : processed;
+        int found = -1;
+        for (int j = 0; j < t.nodes[0].n_children; ++j)
+            if (t.action[t.nodes[0].first + j] == a) found = j;
+        if (found < 0) return 2;
+        if (t.child[t.nodes[0].first + found] < 0) {
+            orc_state s = t.nodes[0].state;
+            orc_apply(game, &s, a);
+            t.child[t.nodes[0].first + found] = (int32_t)add_node(&t, &s);
+        }
+        if (c == n_created) pj = found;
+    }
+    entry_t path[2] = {{0, 0}, {(uint32_t)t.child[t.nodes[0].first + pj], (uint32_t)pj}};
+    uint32_t below_a[4];
+    int below_p[4];
+    update_amaf_path(&t, path, 2, amaf, orc_num_actions(game), utilities, k, below_a, below_p);
+    *n_children = (uint32_t)t.nodes[0].n_children;
+    for (int j = 0; j < t.nodes[0].n_children; ++j) {
+        orc_edge_stats *o = &children_out[j];
+        const stats_t *e = &t.edge[t.nodes[0].first + j];
+        memset(o, 0, sizeof *o);
+        o->action = t.action[t.nodes[0].first + j];
+        o->created = t.child[t.nodes[0].first + j] >= 0;
+        o->amaf_visits = e->amaf_visits;
+        o->amaf_score[0] = e->amaf_score[0];
+        o->amaf_score[1] = e->amaf_score[1];
+    }
+    free(t.nodes);
+    free(t.action);
+    free(t.child);
+    free(t.edge);
+    return 0;
 }

@@ -13,6 +13,32 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_device_count() -> int:
+    """Device count from the CUDA runtime itself (no torch import): 0 when the driver or a device is missing."""
+    import ctypes
+
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+        except OSError:
+            continue
+        n = ctypes.c_int(0)
+        return n.value if rt.cudaGetDeviceCount(ctypes.byref(n)) == 0 else 0
+    return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests are skipped, not failed, on a host without a CUDA device."""
+    if not any("gpu" in it.keywords for it in items):
+        return
+    if _cuda_device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (cudaGetDeviceCount): gpu tests run on the B200 box")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import oracle_lib

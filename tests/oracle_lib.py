@@ -68,7 +68,7 @@ class SearchCfg(C.Structure):
         ("expand_threshold", C.c_uint32),
         ("max_playout_depth", C.c_uint32),
         ("threads", C.c_int),
-        ("pipelined", C.c_int),
+        ("pipeline_depth", C.c_int),
         ("use_transpositions", C.c_int),
         ("exploration_c", C.c_double),
         ("eps_threshold", C.c_uint64),
@@ -78,9 +78,13 @@ class SearchCfg(C.Structure):
         ("rave_param", C.c_uint32),
         ("amaf_alpha", C.c_double),
         ("nst_threshold", C.c_uint32),
+        ("rave_bias", C.c_double),
     ]
 
 
+EDGE_STATS_DTYPE = np.dtype([("visits", "<u4"), ("vloss", "<u4"), ("score", "<i8", (2,)), ("sumsq", "<i8", (2,)), ("amaf_visits", "<u4"),
+                             ("action", "<u2"), ("created", "<u2"), ("amaf_score", "<i8", (2,))])
+assert EDGE_STATS_DTYPE.itemsize == 64
 ROOT_CHILD_DTYPE = np.dtype([("action", "<u2"), ("pad", "<u2"), ("visits", "<u4"), ("score", "<i8", (2,))])
 
 
@@ -129,6 +133,9 @@ def lib() -> C.CDLL:
         L.orc_stress_through.argtypes = [i32, u64, vp, vp]
         L.orc_naive_hex_winner.argtypes = [vp, vp, i32]
         L.orc_search.argtypes = [C.POINTER(SearchCfg), vp, vp, vp, vp, vp]
+        L.orc_select_score.argtypes = [C.POINTER(SearchCfg), i32, vp, vp, u32, C.c_int64]
+        L.orc_select_score.restype = C.c_double
+        L.orc_kat_update_amaf.argtypes = [i32, vp, vp, u32, C.c_uint16, vp, vp, u32, vp, vp]
         _lib = L
     return _lib
 
@@ -289,13 +296,18 @@ def playout_batch(
             "replies_final": replies_final, "replies2_final": replies2_final}
 
 
-def search(game, root, *, iterations, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,
-           max_depth=0, c=2.0 ** 0.5, eps=0.1, seed=0, threads=1, use_transpositions=False, grave_threshold=700,
-           rave_schedule=0, rave_param=1000, pipelined=False, amaf_alpha=1.0, nst_threshold=5):
+def search_cfg(game=0, *, iterations=1, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,
+               max_depth=0, c=2.0 ** 0.5, eps=0.1, seed=0, threads=1, use_transpositions=False, grave_threshold=700,
+               rave_schedule=0, rave_param=1000, pipelined=False, pipeline_depth=0, amaf_alpha=1.0, nst_threshold=5, rave_bias=0.0):
+    depth = int(pipeline_depth) if pipeline_depth else (2 if pipelined else 1)
+    return SearchCfg(game, policy, select, q_init, iterations, batch_leaves, k, expand_threshold, max_depth, threads,
+                     depth, int(use_transpositions), c, eps_threshold(eps), seed, grave_threshold, rave_schedule,
+                     rave_param, amaf_alpha, nst_threshold, rave_bias)
+
+
+def search(game, root, **kw):
     """The restated reference MCTS loop with CPU playouts.  Returns (best_action, children, playout_plies)."""
-    cfg = SearchCfg(game, policy, select, q_init, iterations, batch_leaves, k, expand_threshold, max_depth, threads,
-                    int(pipelined), int(use_transpositions), c, eps_threshold(eps), seed, grave_threshold, rave_schedule,
-                    rave_param, amaf_alpha, nst_threshold)
+    cfg = search_cfg(game, **kw)
     root = np.ascontiguousarray(root, dtype=STATE_DTYPE)
     children = np.zeros(256, dtype=ROOT_CHILD_DTYPE)
     best, n, plies = C.c_uint16(), C.c_uint32(), C.c_uint64()
@@ -303,6 +315,30 @@ def search(game, root, *, iterations, batch_leaves=1, k=1, policy=UNIFORM, selec
     if rc != 0:
         raise RuntimeError(f"orc_search failed: {rc}")
     return best.value, children[: n.value].copy(), plies.value
+
+
+def edge_stats(visits=0, vloss=0, score=(0, 0), sumsq=(0, 0), amaf_visits=0, amaf_score=(0, 0)) -> np.ndarray:
+    e = np.zeros(1, dtype=EDGE_STATS_DTYPE)
+    e["visits"], e["vloss"], e["score"], e["sumsq"], e["amaf_visits"], e["amaf_score"] = visits, vloss, score, sumsq, amaf_visits, amaf_score
+    return e
+
+
+def select_score(cfg: SearchCfg, player: int, current: np.ndarray, child, grave_n=0, grave_q=0) -> float:
+    """The oracle's selection formula on hand-built statistics (child None = a child that does not exist yet)."""
+    return lib().orc_select_score(C.byref(cfg), player, _p(current), _p(child) if child is not None else None, grave_n, grave_q)
+
+
+def kat_update_amaf(game, root, created, processed, amaf, utilities, k=1) -> np.ndarray:
+    root = np.ascontiguousarray(root, dtype=STATE_DTYPE)
+    created = np.ascontiguousarray(created, dtype=np.uint16)
+    amaf = np.ascontiguousarray(amaf, dtype=STAT_DTYPE)
+    util = np.ascontiguousarray(utilities, dtype=np.int64)
+    out = np.zeros(256, dtype=EDGE_STATS_DTYPE)
+    n = C.c_uint32()
+    rc = lib().orc_kat_update_amaf(game, _p(root), _p(created), len(created), processed, _p(amaf), _p(util), k, _p(out), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"orc_kat_update_amaf failed: {rc}")
+    return out[: n.value].copy()
 
 
 def random_positions(game: int, seed: int, plies: int, n: int) -> np.ndarray:

@@ -23,7 +23,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(mcts_b200.EXPORTS), declared ^ set(mcts_b200.EXPORTS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.mr_abi_version() == 1
+    assert lib.mr_abi_version() == 2
     assert [lib.mr_num_actions(g) for g in range(5)] == [7, 4096, 4096, 65, 121]
     assert lib.mr_num_actions(9) == 0
 

@@ -39,8 +39,9 @@ def test_search_root_statistics_bit_exact(game, policy, iters, batch, k, select,
     assert (got.children["score"] == children["score"]).all()
     assert got.best_action == best
     assert got.playout_plies == plies
-    # the descents of the first batch all stop at the unvisited root; every later one passes through a root child
-    assert int(got.children["visits"].sum()) == (iters - min(batch, iters)) * k
+    # only the very first descent stops at the unvisited root: the expansion test counts the trials in flight, so the
+    # second descent of the first batch already expands the root (csrc/tree_search.cu header)
+    assert int(got.children["visits"].sum()) == (iters - 1) * k
 
 
 @pytest.mark.parametrize("game,policy,depth", [(o.CONNECT4, o.UNIFORM, 0), (o.BREAKTHROUGH, o.EPS_MAST, 200)])
@@ -279,3 +280,93 @@ def test_leaf_parallel_virtual_loss_balances_across_many_iterations(batch):  # t
     assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
     assert got.best_action == best and got.playout_plies == plies
     assert int(got.children["visits"].sum()) == iters * k  # with threshold 0 every descent passes through a root child
+
+
+@pytest.mark.parametrize("game,policy,depth,batch,k,max_depth", [
+    (o.CONNECT4, o.UNIFORM, 3, 64, 8, 0),
+    (o.CONNECT4, o.UNIFORM, 4, 16, 64, 0),
+    (o.BREAKTHROUGH, o.EPS_MAST, 4, 32, 16, 200),  # MAST table as of batch n - 3
+    (o.HEX11, o.UNIFORM, 3, 32, 8, 0),
+])
+def test_deep_pipeline_search_bit_exact(game, policy, depth, batch, k, max_depth):
+    """pipeline_depth batches in flight over the ABI's four slots (each with its own stream): batch n is gathered and
+    submitted before the results of batches n - depth + 1 .. n - 1 are applied; deterministic, mirrored by the oracle."""
+    strat = {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(0.1)}[policy]
+    root = o.initial_state(game)
+    iters = 2048 + 13  # a ragged last batch
+    with mb.GpuSearch(mb.Game(game), strat, max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      max_playout_depth=max_depth, pipeline_depth=depth, seed=23) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=policy, max_depth=max_depth,
+                                     seed=23, threads=o.host_threads(), pipeline_depth=depth)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies and got.playouts == iters * k
+    assert int(got.children["visits"].sum()) == (iters - 1) * k
+
+
+def test_grave_min_mse_schedule_bit_exact():
+    """RaveSchedule::MinMSE { bias } (select/rave.rs:68): beta depends on the reference node's AMAF count."""
+    from mcts_b200.search import QINIT_INFINITY, RAVE_MIN_MSE, SELECT_GRAVE
+
+    game, iters, batch, k = o.HEX11, 1024, 32, 8
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), mb.Uniform(), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      select=SELECT_GRAVE, q_init=QINIT_INFINITY, grave_threshold=50, rave_schedule=RAVE_MIN_MSE, rave_bias=0.1,
+                      seed=29) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, select=2, q_init=1, seed=29,
+                                     threads=o.host_threads(), grave_threshold=50, rave_schedule=2, rave_bias=0.1)
+    assert (got.children["visits"] == children["visits"]).all() and (got.children["score"] == children["score"]).all()
+    assert got.best_action == best and got.playout_plies == plies
+    # and the schedule matters: HandSelected from the same seed walks another tree
+    _, other, _ = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, select=2, q_init=1, seed=29,
+                           threads=o.host_threads(), grave_threshold=50, rave_schedule=0, rave_param=1000)
+    assert (other["visits"] != children["visits"]).any()
+
+
+def test_grave_with_decisive_mast_rollouts_picks_a_legal_action():
+    """ttt_strategies.rs:367-392 (RaveMastDm, 300 iterations, expand_threshold 0, use_transpositions, 4 tree workers)
+    on Connect4 through the GPU driver; tests/test_search_kats.py holds the oracle's run of the same case."""
+    from mcts_b200.search import SELECT_GRAVE
+
+    root = o.initial_state(o.CONNECT4)
+    with mb.GpuSearch(mb.Game.CONNECT4, mb.DecisiveMoveMast(0.1, "win"), max_iterations=300, batch_leaves=4, num_rollouts_per_leaf=1,
+                      select=SELECT_GRAVE, expand_threshold=0, use_transpositions=True, seed=5) as s:
+        got = s.choose_action(root.view(mb.LEAF_DTYPE))
+    best, children, plies = o.search(o.CONNECT4, root, iterations=300, batch_leaves=4, k=1, policy=o.DECISIVE_MAST_WIN, select=2,
+                                     q_init=0, expand_threshold=0, use_transpositions=True, grave_threshold=700, seed=5)
+    assert got.best_action in _legal_root_actions(o.CONNECT4)
+    assert got.best_action == best and (got.children["visits"] == children["visits"]).all() and got.playout_plies == plies
+    assert int(got.children["visits"].sum()) == 300
+
+
+def _searcher_seed(seed, i):
+    """mr_search_root_parallel's seed of searcher i: words 0..1 of Philox(seed; ctr = (i, 0, 0, 3))."""
+    import ctypes as C
+
+    ctr = (C.c_uint32 * 4)(i, 0, 0, 3)
+    key = (C.c_uint32 * 2)(seed & 0xFFFFFFFF, seed >> 32)
+    out = (C.c_uint32 * 4)()
+    o.lib().orc_philox4x32_10(ctr, key, out)
+    return (out[1] << 32) | out[0]
+
+
+def test_root_parallel_threads_equal_the_sum_of_independent_searches():
+    """choose_action_root_parallel (search/parallel.rs:56-115) with one host thread and one rollout context per
+    searcher, all on the same GPU: the merged root-child totals are exactly the sum of the searchers' own totals, each
+    searcher being the single-tree search with its derived seed, and the pick has the most merged visits."""
+    game, iters, batch, k, n_thr, seed = o.BREAKTHROUGH, 512, 32, 16, 3, 77
+    root = o.initial_state(game)
+    with mb.GpuSearch(mb.Game(game), mb.EpsilonGreedyMast(0.1), max_iterations=iters, batch_leaves=batch, num_rollouts_per_leaf=k,
+                      max_playout_depth=200, pipeline_depth=2, seed=seed, num_threads=n_thr) as s:
+        merged = s.choose_action(root.view(mb.LEAF_DTYPE))
+    visits = np.zeros(len(merged.children), dtype=np.int64)
+    score = np.zeros((len(merged.children), 2), dtype=np.int64)
+    for i in range(n_thr):
+        _, ch, _ = o.search(game, root, iterations=iters, batch_leaves=batch, k=k, policy=o.EPS_MAST, eps=0.1, max_depth=200,
+                            seed=_searcher_seed(seed, i), threads=o.host_threads(), pipeline_depth=2)
+        visits += ch["visits"]
+        score += ch["score"]
+    assert (merged.children["visits"] == visits).all() and (merged.children["score"] == score).all()
+    assert merged.playouts == n_thr * iters * k
+    assert visits[list(merged.children["action"]).index(merged.best_action)] == visits.max()
