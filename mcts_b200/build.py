@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     "-std=c++17",
     "-Xcompiler",
     "-fPIC",
+    "-Xcompiler",
+    "-ffp-contract=off",  # the tree driver's f64 selection formulas are compared bit for bit with the oracle's
     "--compress-mode=size",  # the fatbins shrink ~6x; the library travels to the GPU box with every snapshot
 ]
 

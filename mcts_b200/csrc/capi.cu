@@ -250,45 +250,64 @@ int mast_action_id(int game, int player, int cell, int kind) {
     return -1;
 }
 
+// the real actions of (game, player) as (cell, kind, dense id), built once
+struct MastAction {
+    uint8_t cell, kind;
+    uint16_t id;
+};
+const std::vector<MastAction> &mast_actions(int game, int player) {
+    static std::vector<MastAction> cache[MR_NUM_GAMES][2];
+    static bool built = false;
+    if (!built) {
+        for (int g = 0; g < MR_NUM_GAMES; ++g) {
+            const int kinds = g == MR_BREAKTHROUGH ? 3 : (g == MR_KNIGHTTHROUGH ? 8 : (g == MR_HEX11 ? 2 : 1));
+            for (int pl = 0; pl < 2; ++pl)
+                for (int src = 0; src < 64; ++src)
+                    for (int q = 0; q < kinds; ++q) {
+                        const int id = mast_action_id(g, pl, src, q);
+                        if (id >= 0) cache[g][pl].push_back({(uint8_t)src, (uint8_t)q, (uint16_t)id});
+                    }
+        }
+        built = true;
+    }
+    return cache[game][player];
+}
+
+// The unigram score as a sort key.  score / visits in f64 is order- AND equality-preserving for visits < 2^26: two
+// different fractions with denominators below 2^26 differ by more than 2^-52 while both lie in [-1, 1] (half an ulp is
+// at most 2^-54), and equal fractions round to the same double.  (This is also why the reference's own f64 comparison,
+// simulate.rs:806-817, equals the exact rational one.)
 int compute_mast_planes(mr_ctx *ctx, int game, const mr_action_stat *mast) {
     const int na = kGames[game].num_actions;
-    const int kinds = game == MR_BREAKTHROUGH ? 3 : (game == MR_KNIGHTTHROUGH ? 8 : (game == MR_HEX11 ? 2 : 1));
     memset(ctx->mast_planes, 0, sizeof ctx->mast_planes);
     memset(ctx->mast_rank_small, 0, sizeof ctx->mast_rank_small);
     for (int pl = 0; pl < 2; ++pl) {
         const mr_action_stat *tab = mast + (size_t)pl * na;
+        const std::vector<MastAction> &acts = mast_actions(game, pl);
         // distinct values over the REAL actions of this player only (ids that no move can produce are ignored)
-        std::vector<Rational> vals;
-        vals.push_back({1, 1});
-        for (int src = 0; src < 64; ++src)
-            for (int q = 0; q < kinds; ++q) {
-                const int id = mast_action_id(game, pl, src, q);
-                if (id < 0) continue;
-                const mr_action_stat &e = tab[id];
-                if (e.visits >= (1u << 26))
-                    return fail(ctx, MR_ERR_INVALID, "MAST visits %u >= 2^26: exact score comparison not guaranteed", e.visits);
-                if (e.visits > 0) vals.push_back({(int64_t)e.score, (int64_t)e.visits});
-            }
-        std::sort(vals.begin(), vals.end(), rat_less);
-        std::vector<Rational> uniq;
-        for (const Rational &v : vals)
-            if (uniq.empty() || !rat_eq(uniq.back(), v)) uniq.push_back(v);
+        double key[513], uniq[514];
+        size_t nu = 0;
+        uniq[nu++] = 1.0; // unvisited => 1.0
+        for (size_t a = 0; a < acts.size(); ++a) {
+            const mr_action_stat &e = tab[acts[a].id];
+            if (e.visits >= (1u << 26))
+                return fail(ctx, MR_ERR_INVALID, "MAST visits %u >= 2^26: exact score comparison not guaranteed", e.visits);
+            key[a] = e.visits > 0 ? (double)e.score / (double)e.visits : 1.0;
+            if (e.visits > 0) uniq[nu++] = key[a];
+        }
+        std::sort(uniq, uniq + nu);
+        nu = (size_t)(std::unique(uniq, uniq + nu) - uniq);
         uint32_t nbits = 0;
-        while ((1u << nbits) < uniq.size()) ++nbits;
-        if (nbits > (uint32_t)MAST_BITS) return fail(ctx, MR_ERR_INVALID, "too many distinct MAST values (%zu)", uniq.size());
+        while ((1u << nbits) < nu) ++nbits;
+        if (nbits > (uint32_t)MAST_BITS) return fail(ctx, MR_ERR_INVALID, "too many distinct MAST values (%zu)", nu);
         ctx->mast_nbits[pl] = nbits;
-        auto rank_of = [&](Rational v) { return (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), v, rat_less) - uniq.begin()); };
-        const uint32_t unvisited = rank_of({1, 1});
-        for (int src = 0; src < 64; ++src)
-            for (int q = 0; q < kinds; ++q) {
-                const int id = mast_action_id(game, pl, src, q);
-                if (id < 0) continue;
-                const mr_action_stat &e = tab[id];
-                const uint32_t rk = e.visits > 0 ? rank_of({(int64_t)e.score, (int64_t)e.visits}) : unvisited;
-                for (uint32_t b = 0; b < nbits; ++b)
-                    if ((rk >> b) & 1u) ctx->mast_planes[pl][q][b] |= 1ull << src;
-                if (game == MR_CONNECT4) ctx->mast_rank_small[pl][src] = (uint16_t)rk;
-            }
+        for (size_t a = 0; a < acts.size(); ++a) {
+            const uint32_t rk = (uint32_t)(std::lower_bound(uniq, uniq + nu, key[a]) - uniq);
+            const uint64_t bit = 1ull << acts[a].cell;
+            for (uint32_t b = 0; b < nbits; ++b)
+                if ((rk >> b) & 1u) ctx->mast_planes[pl][acts[a].kind][b] |= bit;
+            if (game == MR_CONNECT4) ctx->mast_rank_small[pl][acts[a].cell] = (uint16_t)rk;
+        }
     }
     ctx->mast_game = game;
     return MR_OK;
@@ -971,30 +990,39 @@ int mr_wait(mr_ctx *ctx, int slot, mr_leaf_result *out, mr_action_stat *amaf_out
     ss.lgr_ready = policy_is_lgr((int)d.policy);
     ss.lgr2_ready = policy_is_lgr2((int)d.policy);
     ss.nst_ready = d.policy == MR_EPS_NST;
-    memset(out, 0, sizeof(mr_leaf_result) * n);
-    if (amaf_out && (d.flags & MR_WANT_AMAF)) memset(amaf_out, 0, sizeof(mr_action_stat) * (size_t)n * 2 * na);
-    if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) memset(mast_delta_out, 0, sizeof(mr_action_stat) * 2 * na);
+    const bool single = ctx->dev.size() == 1; // one device: its tables ARE the totals, a copy instead of zero-and-add
+    if (!single) {
+        memset(out, 0, sizeof(mr_leaf_result) * n);
+        if (amaf_out && (d.flags & MR_WANT_AMAF)) memset(amaf_out, 0, sizeof(mr_action_stat) * (size_t)n * 2 * na);
+        if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) memset(mast_delta_out, 0, sizeof(mr_action_stat) * 2 * na);
+    }
     for (Device &dv : ctx->dev) {
         SlotDev &sd = dv.slot[slot];
         if (sd.g_end == sd.g_begin) continue;
-        for (uint32_t i = 0; i < n; ++i) {
-            out[i].wins[0] += sd.results.h[i].wins[0];
-            out[i].wins[1] += sd.results.h[i].wins[1];
-            out[i].draws += sd.results.h[i].draws;
-            out[i].cutoffs += sd.results.h[i].cutoffs;
-            out[i].sum_depth += sd.results.h[i].sum_depth;
-        }
-        if (amaf_out && (d.flags & MR_WANT_AMAF)) {
-            const size_t cnt = (size_t)n * 2 * na;
-            for (size_t i = 0; i < cnt; ++i) {
-                amaf_out[i].visits += sd.amaf.h[i].visits;
-                amaf_out[i].score += sd.amaf.h[i].score;
+        if (single) {
+            memcpy(out, sd.results.h, sizeof(mr_leaf_result) * n);
+            if (amaf_out && (d.flags & MR_WANT_AMAF)) memcpy(amaf_out, sd.amaf.h, sizeof(mr_action_stat) * (size_t)n * 2 * na);
+            if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) memcpy(mast_delta_out, sd.mast_delta.h, sizeof(mr_action_stat) * 2 * na);
+        } else {
+            for (uint32_t i = 0; i < n; ++i) {
+                out[i].wins[0] += sd.results.h[i].wins[0];
+                out[i].wins[1] += sd.results.h[i].wins[1];
+                out[i].draws += sd.results.h[i].draws;
+                out[i].cutoffs += sd.results.h[i].cutoffs;
+                out[i].sum_depth += sd.results.h[i].sum_depth;
             }
-        }
-        if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) {
-            for (int i = 0; i < 2 * na; ++i) {
-                mast_delta_out[i].visits += sd.mast_delta.h[i].visits;
-                mast_delta_out[i].score += sd.mast_delta.h[i].score;
+            if (amaf_out && (d.flags & MR_WANT_AMAF)) {
+                const size_t cnt = (size_t)n * 2 * na;
+                for (size_t i = 0; i < cnt; ++i) {
+                    amaf_out[i].visits += sd.amaf.h[i].visits;
+                    amaf_out[i].score += sd.amaf.h[i].score;
+                }
+            }
+            if (mast_delta_out && (d.flags & MR_WANT_MAST_DELTA)) {
+                for (int i = 0; i < 2 * na; ++i) {
+                    mast_delta_out[i].visits += sd.mast_delta.h[i].visits;
+                    mast_delta_out[i].score += sd.mast_delta.h[i].score;
+                }
             }
         }
         const uint64_t gb = sd.g_begin, ge = sd.g_end;

@@ -302,6 +302,20 @@ struct Search {
         const uint32_t r = mulhi32(philox_word0(d->seed, descent, (uint32_t)path.size() - 1, 0, 2), 16u * n);
         uint32_t i = r / 16u;
         const uint32_t stride = kPrimes[r % 16u] % n;
+        // No created child can score above 1 + ln N + c sqrt(ln N): exploit, AMAF mean and variance bound are <= 1, every
+        // exploration term is at most its value at n_total = 1 (for Amaf with alpha in [0, 1] the blend of two such
+        // numbers).  When the unvisited value is beyond that (QInit::Infinity, or a parent without visits), the arg-max
+        // is the first child in visiting order that does not exist yet -- found without evaluating a single formula.
+        // Exactly the result of the full loop below (strict '>' keeps the first maximum), only cheaper.
+        if (unvisited_value > 2.0 + parent_log + std::fabs(d->exploration_c) * std::sqrt(parent_log) &&
+            (d->select != MR_SELECT_AMAF || (d->amaf_alpha >= 0.0 && d->amaf_alpha <= 1.0))) {
+            uint32_t j = i;
+            for (uint32_t k = 0; k < n; ++k) {
+                if (t.child[node.first + j] < 0) return j;
+                j += stride;
+                if (j >= n) j -= n;
+            }
+        }
         bool have = false;
         double best = 0.0;
         uint32_t best_i = i;

@@ -602,13 +602,17 @@ class GpuRollout:
         self.strategy = Uniform()
         try:
             k = max(64, int(n * 1.5) + 16)
-            r = self.simulate_many(
-                initial_state(self.game), k, want_trace=True, want_final=True, max_trace=1, seed=seed, max_playout_depth=plies
-            )
+            while True:  # the survivors of playout ids 0..k-1 are a prefix of those of a larger k: growing k keeps the set
+                r = self.simulate_many(
+                    initial_state(self.game), k, want_trace=True, want_final=True, max_trace=1, seed=seed, max_playout_depth=plies
+                )
+                ok = (r.records["end_type"] == EndType.TURN_LIMIT) & (r.records["depth"] == plies)
+                sel = r.final[ok]
+                if len(sel) >= n or k >= 256 * n:
+                    break
+                k *= 4
         finally:
             self.strategy = saved
-        ok = (r.records["end_type"] == EndType.TURN_LIMIT) & (r.records["depth"] == plies)
-        sel = r.final[ok]
         if len(sel) < n:
             raise RuntimeError(f"only {len(sel)} of {n} random positions survived {plies} plies; lower plies")
         out[:] = sel[:n]

@@ -61,6 +61,19 @@ def merge_mast_delta(delta: np.ndarray, device=None, group=None) -> np.ndarray:
     return out
 
 
+def merge_table_i32(table: np.ndarray, device=None, group=None) -> np.ndarray:
+    """Sums a (visits, score) table -- any shape, e.g. the [2][num_slots] MAST delta of MR_TABLES_IN_SLOTS (3 KB for
+    Breakthrough) -- over ranks as int32, the element type it has on the device: host -> device -> one all-reduce
+    (NCCL over NVLink on GPUs, gloo in the CPU tests) -> host.  Returns a new array of the input's dtype and shape."""
+    buf = torch.from_numpy(np.ascontiguousarray(table).view(np.int32).reshape(-1).copy())
+    if device is not None:
+        buf = buf.to(device)
+    merge_sum_(buf, group)
+    out = np.empty_like(np.ascontiguousarray(table))
+    out.view(np.int32).reshape(-1)[:] = buf.cpu().numpy()
+    return out
+
+
 PRIMES = (14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991, 53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693)
 
 

@@ -29,6 +29,29 @@ typedef struct {
     uint8_t rows, cols, nw;
 } bb_t;
 
+/* ---- operation counters ("re-derive ops/ply by instrumenting the oracle with op counters") ----
+ * Built only into the counting variant of the library (-DORC_COUNT_OPS, _build/liboracle_ops.so).  Every primitive
+ * below reports what it executes per 64-bit WORD the board really has; games.c / playout.c report move-list stores,
+ * draws and MAST score evaluations.  Plain globals: counting runs are single-threaded. */
+enum {
+    ORC_OP_LOGIC64 = 0, /* and / or / xor / not / compare on one 64-bit word */
+    ORC_OP_SHIFT64,     /* one 64-bit shift (the carry shift of a two-word board counts separately) */
+    ORC_OP_POPC64,      /* 64-bit population count */
+    ORC_OP_CTZ64,       /* lowest-set-bit search of the ascending iteration (its clear-lowest is 2 LOGIC64) */
+    ORC_OP_LIST_STORE,  /* one action written to a materialised action list */
+    ORC_OP_DRAW,        /* one random word consumed */
+    ORC_OP_SCORE_EVAL,  /* one unigram / bigram score evaluated and compared (MAST-style policies) */
+    ORC_OP_PLY,         /* plies played */
+    ORC_OP_FLOOD_ITER,  /* flood6 fix-point iterations (Hex) */
+    ORC_OP_KINDS
+};
+#ifdef ORC_COUNT_OPS
+extern uint64_t orc_ops[ORC_OP_KINDS];
+#define BB_OP(kind, n) (orc_ops[kind] += (uint64_t)(n))
+#else
+#define BB_OP(kind, n) ((void)0)
+#endif
+
 enum { BB_NORTH = 0, BB_EAST = 1, BB_SOUTH = 2, BB_WEST = 3 };
 
 static inline bb_t bb_empty(int rows, int cols) {
@@ -44,33 +67,54 @@ static inline bb_t bb_empty(int rows, int cols) {
 static inline int bb_len(bb_t b) { return (int)b.rows * (int)b.cols; }
 
 /* board.rs:89-92 */
-static inline int bb_get_index(bb_t b, int idx) { return (int)((b.w[idx / 64] >> (idx % 64)) & 1u); }
+static inline int bb_get_index(bb_t b, int idx) {
+    BB_OP(ORC_OP_SHIFT64, 1);
+    BB_OP(ORC_OP_LOGIC64, 1);
+    return (int)((b.w[idx / 64] >> (idx % 64)) & 1u);
+}
 /* board.rs:95-98 */
 static inline bb_t bb_set_index(bb_t b, int idx) {
+    BB_OP(ORC_OP_SHIFT64, 1);
+    BB_OP(ORC_OP_LOGIC64, 1);
     b.w[idx / 64] |= (uint64_t)1 << (idx % 64);
     return b;
 }
 static inline bb_t bb_from_index(int rows, int cols, int idx) { return bb_set_index(bb_empty(rows, cols), idx); }
 
 static inline bb_t bb_and(bb_t a, bb_t b) {
+    BB_OP(ORC_OP_LOGIC64, a.nw);
     a.w[0] &= b.w[0];
     a.w[1] &= b.w[1];
     return a;
 }
 static inline bb_t bb_or(bb_t a, bb_t b) {
+    BB_OP(ORC_OP_LOGIC64, a.nw);
     a.w[0] |= b.w[0];
     a.w[1] |= b.w[1];
     return a;
 }
 static inline bb_t bb_xor(bb_t a, bb_t b) {
+    BB_OP(ORC_OP_LOGIC64, a.nw);
     a.w[0] ^= b.w[0];
     a.w[1] ^= b.w[1];
     return a;
 }
-static inline int bb_eq(bb_t a, bb_t b) { return a.w[0] == b.w[0] && a.w[1] == b.w[1]; }
-static inline int bb_none_set(bb_t a) { return (a.w[0] | a.w[1]) == 0; }
-static inline int bb_intersects(bb_t a, bb_t b) { return ((a.w[0] & b.w[0]) | (a.w[1] & b.w[1])) != 0; }
-static inline int bb_count_ones(bb_t a) { return __builtin_popcountll(a.w[0]) + __builtin_popcountll(a.w[1]); }
+static inline int bb_eq(bb_t a, bb_t b) {
+    BB_OP(ORC_OP_LOGIC64, a.nw);
+    return a.w[0] == b.w[0] && a.w[1] == b.w[1];
+}
+static inline int bb_none_set(bb_t a) {
+    BB_OP(ORC_OP_LOGIC64, a.nw);
+    return (a.w[0] | a.w[1]) == 0;
+}
+static inline int bb_intersects(bb_t a, bb_t b) {
+    BB_OP(ORC_OP_LOGIC64, 2 * a.nw);
+    return ((a.w[0] & b.w[0]) | (a.w[1] & b.w[1])) != 0;
+}
+static inline int bb_count_ones(bb_t a) {
+    BB_OP(ORC_OP_POPC64, a.nw);
+    return __builtin_popcountll(a.w[0]) + __builtin_popcountll(a.w[1]);
+}
 
 /* board.rs:205-215: mask of word w covering only bits inside 0..len */
 static inline uint64_t bb_word_mask(bb_t b, int w) {
@@ -83,6 +127,7 @@ static inline uint64_t bb_word_mask(bb_t b, int w) {
 
 /* board.rs:824-836: `!board` never sets padding bits */
 static inline bb_t bb_not(bb_t a) {
+    BB_OP(ORC_OP_LOGIC64, a.nw); /* the length mask is a constant: ~a & mask is one operation */
     a.w[0] = ~a.w[0] & bb_word_mask(a, 0);
     a.w[1] = ~a.w[1] & bb_word_mask(a, 1);
     return a;
@@ -91,6 +136,8 @@ static inline bb_t bb_not(bb_t a) {
 /* board.rs:225-240 raw_shl (rhs < 64), carrying across words */
 static inline bb_t bb_shl(bb_t a, int rhs) {
     if (rhs == 0) return a;
+    BB_OP(ORC_OP_SHIFT64, 2 * a.nw - 1); /* one shift per word, one carry shift per word boundary */
+    BB_OP(ORC_OP_LOGIC64, a.nw - 1);     /* the carry OR */
     bb_t out = a;
     for (int w = a.nw - 1; w >= 0; --w) {
         uint64_t v = a.w[w] << rhs;
@@ -103,6 +150,8 @@ static inline bb_t bb_shl(bb_t a, int rhs) {
 /* board.rs:242-258 raw_shr (rhs < 64) */
 static inline bb_t bb_shr(bb_t a, int rhs) {
     if (rhs == 0) return a;
+    BB_OP(ORC_OP_SHIFT64, 2 * a.nw - 1);
+    BB_OP(ORC_OP_LOGIC64, a.nw - 1);
     bb_t out = a;
     for (int w = 0; w < a.nw; ++w) {
         uint64_t v = a.w[w] >> rhs;
@@ -168,6 +217,7 @@ static inline bb_t bb_flood6(bb_t self, bb_t seed, int *iterations) {
         return flood;
     }
     for (;;) {
+        BB_OP(ORC_OP_FLOOD_ITER, 1);
         bb_t temp = flood;
         bb_t f = flood;
         f = bb_or(f, bb_shift_north(flood));
@@ -190,6 +240,8 @@ static inline int bb_pop_lowest(bb_t *b) {
     for (int w = 0; w < b->nw; ++w) {
         uint64_t word = b->w[w];
         if (word != 0) {
+            BB_OP(ORC_OP_CTZ64, 1);
+            BB_OP(ORC_OP_LOGIC64, 2);
             int bit = __builtin_ctzll(word);
             b->w[w] = word & (word - 1);
             return w * 64 + bit;

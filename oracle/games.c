@@ -74,7 +74,7 @@ static int c4_moves(const c4_state *t, uint16_t *out) {
     if (t->winner) return 0;
     bb_t occ = bb_or(t->black, t->white);
     for (int col = 0; col < occ.cols; ++col)
-        if (c4_height(occ, col) < occ.rows) out[n++] = (uint16_t)col;
+        if (c4_height(occ, col) < occ.rows) BB_OP(ORC_OP_LIST_STORE, 1), out[n++] = (uint16_t)col;
     return n;
 }
 
@@ -157,7 +157,7 @@ static int bt_moves(const bt_state *t, uint16_t *out) {
         bb_t available =
             bb_or(bb_or(bb_and(w, bb_not(player)), bb_and(e, bb_not(player))), bb_and(forward, bb_not(occupied)));
         int dst;
-        while ((dst = bb_pop_lowest(&available)) >= 0) out[n++] = (uint16_t)((src << 8) | dst);
+        while ((dst = bb_pop_lowest(&available)) >= 0) BB_OP(ORC_OP_LIST_STORE, 1), out[n++] = (uint16_t)((src << 8) | dst);
     }
     return n;
 }
@@ -180,7 +180,7 @@ static int kt_moves(const bt_state *t, uint16_t *out) {
         }
         bb_t available = bb_and(knight, bb_not(player));
         int dst;
-        while ((dst = bb_pop_lowest(&available)) >= 0) out[n++] = (uint16_t)((src << 8) | dst);
+        while ((dst = bb_pop_lowest(&available)) >= 0) BB_OP(ORC_OP_LIST_STORE, 1), out[n++] = (uint16_t)((src << 8) | dst);
     }
     return n;
 }
@@ -317,10 +317,10 @@ static int oth_actions(const orc_state *s, uint16_t *out) {
     bb_t moves = oth_generate_moves(player, opponent);
     int n = 0;
     if (bb_count_ones(moves) == 0) {
-        out[n++] = ORC_OTHELLO_PASS;
+        BB_OP(ORC_OP_LIST_STORE, 1), out[n++] = ORC_OTHELLO_PASS;
     } else {
         int idx;
-        while ((idx = bb_pop_lowest(&moves)) >= 0) out[n++] = (uint16_t)idx;
+        while ((idx = bb_pop_lowest(&moves)) >= 0) BB_OP(ORC_OP_LIST_STORE, 1), out[n++] = (uint16_t)idx;
     }
     return n;
 }
@@ -423,7 +423,7 @@ static int hex_winner(const orc_state *s) {
 static int hex_actions(const orc_state *s, uint16_t *out) {
     bb_t legal = bb_not(bb_or(hex_bb(&s->board[0]), hex_bb(&s->board[2])));
     int n = 0, idx;
-    while ((idx = bb_pop_lowest(&legal)) >= 0) out[n++] = (uint16_t)idx;
+    while ((idx = bb_pop_lowest(&legal)) >= 0) BB_OP(ORC_OP_LIST_STORE, 1), out[n++] = (uint16_t)idx;
     return n;
 }
 

@@ -180,6 +180,11 @@ int orc_naive_hex_winner(const uint8_t occ0[121], const uint8_t occ1[121], int l
 int orc_stress_othello(uint64_t num_games, uint64_t *games_done, uint64_t *plies_done);
 int orc_stress_through(int game, uint64_t num_games, uint64_t *goal_wins, uint64_t *stuck_games);
 
+/* ---- operation counters (bitboard.h): live only in _build/liboracle_ops.so (-DORC_COUNT_OPS); single-threaded runs ---- */
+int orc_ops_enabled(void);
+void orc_ops_reset(void);
+void orc_ops_read(uint64_t *out /* [ORC_OP_KINDS] */);
+
 /* ---- the MCTS loop around the playout path (search.c): BASELINE.json config 1 on the CPU, and the checker of
  * the product's GPU-driven tree driver ---- */
 typedef struct {

@@ -35,6 +35,7 @@
  *   MAST greedy (random_best): r = mulhi32(x0, 16 n); i = r / 16; stride = PRIMES[r % 16]
  */
 #include "oracle.h"
+#include "bitboard.h"
 
 #include <math.h>
 #include <pthread.h>
@@ -75,6 +76,7 @@ uint32_t orc_draw(uint64_t seed, uint32_t leaf_id, uint32_t playout_id, uint32_t
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t out[4];
     orc_philox4x32_10(ctr, key, out);
+    BB_OP(ORC_OP_DRAW, 1);
     return out[ply & 3];
 }
 
@@ -83,6 +85,7 @@ void orc_draw_pair(uint64_t seed, uint32_t leaf_id, uint32_t playout_id, uint32_
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t out[4];
     orc_philox4x32_10(ctr, key, out);
+    BB_OP(ORC_OP_DRAW, 2);
     *x0 = out[2 * (ply & 1)];
     *x1 = out[2 * (ply & 1) + 1];
 }
@@ -244,6 +247,7 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
             }
             if (greedy) {
                 const orc_action_stat *tab = mast + (size_t)player * na;
+                BB_OP(ORC_OP_SCORE_EVAL, n);
                 for (int i = 0; i < n; ++i) score[i] = unigram_score(tab, action_id(game, available[i]));
                 if (d->policy == ORC_EPS_NST && prev >= 0 && d->bigram) { /* Nst::select_move, simulate.rs:898-930 */
                     const int S = orc_num_slots(game);
@@ -263,6 +267,7 @@ void orc_playout(const orc_batch_desc *d, const orc_state *leaf, uint32_t leaf_i
         own_prev[player] = action;
         if (trace && depth < d->max_trace) trace[depth] = action;
         orc_apply(game, &state, action);
+        BB_OP(ORC_OP_PLY, 1);
         ++depth;
     }
     rec->depth = depth;
@@ -555,4 +560,28 @@ void orc_random_positions(int game, uint64_t seed, uint32_t plies, uint32_t n, o
         orc_playout(&d, &init, 0, pid, NULL, NULL, &rec, &fin);
         if (rec.end_type == ORC_END_TURN_LIMIT && rec.depth == plies) out[got++] = fin;
     }
+}
+
+/* ---- operation counters of the counting build (bitboard.h) ---- */
+#ifdef ORC_COUNT_OPS
+uint64_t orc_ops[ORC_OP_KINDS];
+#endif
+int orc_ops_enabled(void) {
+#ifdef ORC_COUNT_OPS
+    return 1;
+#else
+    return 0;
+#endif
+}
+void orc_ops_reset(void) {
+#ifdef ORC_COUNT_OPS
+    memset(orc_ops, 0, sizeof orc_ops);
+#endif
+}
+void orc_ops_read(uint64_t *out /* [ORC_OP_KINDS] */) {
+#ifdef ORC_COUNT_OPS
+    memcpy(out, orc_ops, sizeof orc_ops);
+#else
+    memset(out, 0, sizeof(uint64_t) * ORC_OP_KINDS);
+#endif
 }

@@ -241,6 +241,7 @@ def playout_batch(
     want_bigram_delta=False,
     replies2: np.ndarray | None = None,
     want_final_tables=False,
+    _use_lib=None,
 ):
     """Runs n_leaves*k playouts.  Returns a dict with results (+ optional amaf / mast_delta / trace /
     records / final)."""
@@ -286,7 +287,7 @@ def playout_batch(
     if mast is not None:
         mast = np.ascontiguousarray(mast, dtype=STAT_DTYPE)
         assert mast.shape == (2, na)
-    rc = lib().orc_playout_batch(
+    rc = (_use_lib or lib()).orc_playout_batch(
         C.byref(d), _p(leaves), n, _p(mast), _p(results), _p(amaf), _p(delta), _p(trace), _p(rec), _p(final), threads
     )
     if rc != 0:
@@ -294,6 +295,46 @@ def playout_batch(
     return {"results": results, "amaf": amaf, "mast_delta": delta, "trace": trace, "records": rec, "final": final,
             "reply_order": reply_order, "reply_action": reply_action, "last_win": last_win, "bigram_delta": bigram_delta,
             "replies_final": replies_final, "replies2_final": replies2_final}
+
+
+OP_KINDS = ["logic64", "shift64", "popc64", "ctz64", "list_store", "draw", "score_eval", "ply", "flood_iter"]
+# 32-bit integer instructions charged per counted operation (a 64-bit logical / shift operation is two
+# 32-bit instructions, a 64-bit population count three, a random word 20 (Philox4x32-10 ~ 80 per four words), one MAST
+# score evaluation + comparison 8 (two wide multiplies and a compare per legal move); a list store and the lowest-bit
+# search are charged one and three)
+OP_WEIGHTS = {"logic64": 2, "shift64": 2, "popc64": 3, "ctz64": 3, "list_store": 1, "draw": 20, "score_eval": 8}
+_ops_lib = None
+
+
+def ops_lib() -> C.CDLL:
+    """The counting build of the oracle (liboracle_ops.so, -DORC_COUNT_OPS): same sources, operation counters live."""
+    global _ops_lib
+    if _ops_lib is None:
+        build()
+        L = C.CDLL(str(LIB_PATH.with_name("liboracle_ops.so")))
+        L.orc_playout_batch.argtypes = lib().orc_playout_batch.argtypes
+        L.orc_ops_read.argtypes = [C.c_void_p]
+        assert L.orc_ops_enabled() == 1
+        _ops_lib = L
+    return _ops_lib
+
+
+def count_ops(game, leaves, k, **kw) -> dict:
+    """Operation counts of the oracle (= the reference's arithmetic as its algorithm executes it) over one single-threaded
+    batch: raw counts per kind, plies, and `ops_per_ply` = sum(count * OP_WEIGHTS) / plies in 32-bit integer instructions."""
+    L = ops_lib()
+    L.orc_ops_reset()
+    kw["threads"] = 1
+    out = playout_batch(game, leaves, k, _use_lib=L, **kw)
+    raw = np.zeros(len(OP_KINDS), dtype=np.uint64)
+    L.orc_ops_read(_p(raw))
+    counts = {nm: int(v) for nm, v in zip(OP_KINDS, raw)}
+    plies = counts["ply"]
+    assert plies == int(out["results"]["sum_depth"].sum())
+    total = sum(counts[nm] * w for nm, w in OP_WEIGHTS.items())
+    return {"counts": counts, "plies": plies, "ops_per_ply": total / max(1, plies),
+            "legal_per_greedy_ply": None, "flood_iters_per_ply": counts["flood_iter"] / max(1, plies),
+            "list_stores_per_ply": counts["list_store"] / max(1, plies)}
 
 
 def search_cfg(game=0, *, iterations=1, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,

@@ -34,8 +34,13 @@ def _worker(rank, world, port, q):
         delta["visits"] = rng.integers(0, 50, size=(2, 64))
         delta["score"] = rng.integers(-50, 50, size=(2, 64))
         md = root_merge.merge_mast_delta(delta)
+        # the slot-space table bench.py exchanges every step ([2][192] for Breakthrough), summed as int32
+        slots = np.zeros((2, 192), dtype=STAT_DTYPE)
+        slots["visits"] = rng.integers(0, 4000, size=(2, 192))
+        slots["score"] = rng.integers(-4000, 4000, size=(2, 192))
+        msl = root_merge.merge_table_i32(slots)
         b, e = root_merge.shard_range(4097, rank, world)
-        q.put((rank, visits, scores, mv, ms, delta, md, (b, e)))
+        q.put((rank, visits, scores, mv, ms, delta, md, (b, e), slots, msl))
     finally:
         dist.destroy_process_group()
 
@@ -57,6 +62,9 @@ def test_world2_gloo_root_merge():
         assert (o[3] == v_sum).all() and (o[4] == s_sum).all()
         assert (o[6]["visits"] == outs[0][5]["visits"] + outs[1][5]["visits"]).all()
         assert (o[6]["score"] == outs[0][5]["score"] + outs[1][5]["score"]).all()
+        assert o[9].dtype == STAT_DTYPE and o[9].shape == (2, 192)
+        assert (o[9]["visits"] == outs[0][8]["visits"] + outs[1][8]["visits"]).all()
+        assert (o[9]["score"] == outs[0][8]["score"] + outs[1][8]["score"]).all()
     # shards are contiguous, disjoint and cover everything
     assert outs[0][7][0] == 0 and outs[0][7][1] == outs[1][7][0] and outs[1][7][1] == 4097
     # all ranks pick the same final action from the merged visits
