@@ -481,10 +481,10 @@ int validate(mr_ctx *ctx, const mr_batch_desc *d, bool has_mast, kernel_fn *fn_o
         return fail(ctx, MR_ERR_INVALID, "the bigram table was set for game %d, the batch is game %u", ctx->bigram_game, d->game);
     if ((d->flags & MR_WANT_TRACE) && d->max_trace == 0) return fail(ctx, MR_ERR_INVALID, "MR_WANT_TRACE needs max_trace > 0");
     uint32_t cap = 0;
-    // (the Hex fill-then-search kernel derives AMAF from board masks; every per-ply kernel uses the slot trace)
-    const bool hex_fast = d->game == MR_HEX11 && d->policy == MR_UNIFORM && !(d->flags & MR_WANT_MAST_DELTA);
-    const bool needs_scratch = (d->flags & MR_WANT_MAST_DELTA) || ((d->flags & MR_WANT_AMAF) && !hex_fast) ||
-                               policy_is_lgr((int)d->policy) || d->policy == MR_EPS_NST;
+    // (the Hex fill-then-search kernels derive AMAF and the MAST delta from board masks; every per-ply kernel uses the slot trace)
+    const bool hex_fast = d->game == MR_HEX11 && (d->policy == MR_UNIFORM || d->policy == MR_EPS_MAST);
+    const bool needs_scratch = ((d->flags & (MR_WANT_MAST_DELTA | MR_WANT_AMAF)) && !hex_fast) || policy_is_lgr((int)d->policy) ||
+                               d->policy == MR_EPS_NST;
     if (needs_scratch) {
         const uint32_t bound = kGames[d->game].depth_bound;
         cap = d->max_playout_depth ? d->max_playout_depth : bound;

@@ -15,8 +15,17 @@
 // The stop ply, winner, trace, final state and AMAF occurrences are exactly those of the per-ply loop.
 // Moves generated past the stop ply are discarded; they consume Philox words the reference would never
 // have drawn, which is unobservable because draws are keyed by (leaf, playout, ply).
+//
+// The same holds for EpsilonGreedy<Mast> (simulate.rs:538-570, 824-848): its pick looks at the position only through
+// the set of EMPTY cells (the legal actions) and at the frozen MAST table -- never at who is connected -- so the ply
+// sequence of an epsilon-MAST playout is independent of where the game ends, and fill-then-search applies unchanged
+// with the bit-sliced arg-max + random_best tie-break as the fill step (POLICY == MR_EPS_MAST; two Philox words per
+// ply, as in the per-ply kernels).  Every Hex cell is played at most once per playout and by a known player, so the
+// MAST delta (like the AMAF table) is "stones at the stop ply minus leaf stones", added without a trace.
+// The decisive / reply / n-gram policies do read connectivity or need traces: they run in hex_step.cuh.
 #pragma once
 
+#include "hex_step.cuh"
 #include "rollout_kernel.cuh"
 
 namespace mr {
@@ -28,20 +37,29 @@ struct HexLeafShared {
     uint32_t n_empty;
 };
 
-template <int FLAGS>
-__global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% measured */) hex_rollout_kernel(const KernelParams p) {
+#ifndef MR_HEX_MAST_BLOCKS
+#define MR_HEX_MAST_BLOCKS 6
+#endif
+template <int POLICY, int FLAGS>
+__global__ void __launch_bounds__(THREADS_PER_BLOCK, POLICY == MR_EPS_MAST ? MR_HEX_MAST_BLOCKS : 8 /* 64 registers: +3.7% measured */)
+    hex_rollout_kernel(const KernelParams p) {
     using H = Hex11;
     using B128 = H::B128;
+    static_assert(POLICY == MR_UNIFORM || POLICY == MR_EPS_MAST, "fill-then-search covers the policies that never read connectivity");
+    constexpr bool IS_MAST = POLICY == MR_EPS_MAST;
+    constexpr uint32_t WINDOW = IS_MAST ? 2u : 4u; // plies per Philox block
     constexpr bool WANT_AMAF = (FLAGS & MR_WANT_AMAF) != 0;
+    constexpr bool WANT_MAST = (FLAGS & MR_WANT_MAST_DELTA) != 0;
     constexpr bool WANT_TRACE = (FLAGS & MR_WANT_TRACE) != 0;
     constexpr bool WANT_FINAL = (FLAGS & MR_WANT_FINAL_STATE) != 0;
-    constexpr bool NEED_BOARDS = WANT_AMAF || WANT_FINAL; // both players' stones at the stop ply
+    constexpr bool NEED_BOARDS = WANT_AMAF || WANT_MAST || WANT_FINAL; // both players' stones at the stop ply
     constexpr B128 NC0 = H::inv(H::col_mask(0)), NC10 = H::inv(H::col_mask(10)), BM = H::board_mask();
 
     __shared__ __align__(16) mr_leaf s_leaf[WARPS_PER_BLOCK];
     __shared__ HexLeafShared s_hex[WARPS_PER_BLOCK];
     __shared__ uint8_t s_order[WARPS_PER_BLOCK][121][32]; // cell played at [ply][lane]
     __shared__ uint32_t s_amaf[WARPS_PER_BLOCK][WANT_AMAF ? 2 * H::NSLOTS : 1];
+    __shared__ uint32_t s_mast[WARPS_PER_BLOCK][WANT_MAST ? 2 * H::NSLOTS : 1];
     // s_nth[v][r] = position of the r-th set bit of the byte v: the last step of the fill phase's rank -> cell select
     __shared__ uint8_t s_nth[256][8];
     for (uint32_t v = threadIdx.x; v < 256u; v += THREADS_PER_BLOCK) {
@@ -59,9 +77,12 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
     HexLeafShared &sh = s_hex[warp];
     uint8_t(*order)[32] = s_order[warp];
     uint32_t *amaf_tab = s_amaf[warp];
-    uint32_t amaf_plies = 0;
+    uint32_t *mast_tab = s_mast[warp];
+    uint32_t amaf_plies = 0, mast_plies = 0;
     if (WANT_AMAF)
         for (uint32_t e = lane; e < 2u * H::NSLOTS; e += 32) amaf_tab[e] = 0;
+    if (WANT_MAST)
+        for (uint32_t e = lane; e < 2u * H::NSLOTS; e += 32) mast_tab[e] = 0;
     __syncwarp();
 
     unsigned long long grab_lo = 0, grab_hi = 0;
@@ -170,55 +191,108 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                 // ---- 1. fill: D plies, lock-step, no connectivity work ----
                 B128 full[2] = {sh.stones[0], sh.stones[1]};
                 uint32_t n_empty = E; // warp-uniform
-                for (uint32_t base = 0; base < D; base += 4) {
+                for (uint32_t base = 0; base < D; base += WINDOW) {
                     uint32_t r[4];
-                    philox4x32_10(leaf_id, pid, base >> 2, 0u, p.seed_lo, p.seed_hi, r);
+                    philox4x32_10(leaf_id, pid, IS_MAST ? base >> 1 : base >> 2, IS_MAST ? 1u : 0u, p.seed_lo, p.seed_hi, r);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (uint32_t j = 0; j < WINDOW; ++j) {
                         const uint32_t ply = base + j;
                         if (ply < D) { // warp-uniform
-                            uint32_t idx = __umulhi(r[j], n_empty);
+                            const uint32_t x0 = IS_MAST ? r[2u * j] : r[j];
+                            const uint32_t mover = (leaf_turn + ply) & 1u; // warp-uniform
+                            uint32_t idx = __umulhi(x0, n_empty);
                             const uint32_t e0 = ~(full[0].w[0] | full[1].w[0]);
                             const uint32_t e1 = ~(full[0].w[1] | full[1].w[1]);
                             const uint32_t e2 = ~(full[0].w[2] | full[1].w[2]);
                             const uint32_t e3 = ~(full[0].w[3] | full[1].w[3]) & 0x01ffffffu;
-                            const uint32_t c0 = __popc(e0), c1 = __popc(e1), c2 = __popc(e2);
-                            // the idx-th empty cell (ascending), branch-free: three compare-and-select steps pick the
-                            // word, SWAR prefix popcounts the byte, a table the bit.  (Measured against the 5-step binary
-                            // search it replaces: 8 % fewer instructions, 14.05 -> 13.82 ms.  The same word pick with
-                            // predicated IMADs: 14.02 ms; prefix POPCs of the word's low 1, 2, 3 bytes instead of the
-                            // SWAR counts: 13.92 ms.)
-                            uint32_t wbase = 0, word = e0;
-                            {
-                                const uint32_t p1 = c0, p2 = c0 + c1, p3 = p2 + c2;
-                                uint32_t sub = 0;
-                                if (idx >= p1) {
-                                    word = e1;
-                                    wbase = 32;
-                                    sub = p1;
+                            uint32_t cell = 0;
+                            bool have = false;
+                            if constexpr (IS_MAST) {
+                                // EpsilonGreedy (simulate.rs:538-570): explore iff x1 < floor(eps * 2^32), else Mast::select_move
+                                // (:824-848): bit-sliced arg-max over the empty cells (the two 64-bit halves of the board ride the
+                                // "kind" dimension of the rank planes), then random_best's visiting order (util.rs:135-163)
+                                const uint32_t x1 = r[2u * j + 1u];
+                                if (!(p.eps_enable && x1 <= p.eps_thr_m1)) {
+                                    uint64_t cand[2] = {mk64(e0, e1), mk64(e2, e3)};
+                                    mast_argmax<2>(cand, p.mast_planes[mover], p.mast_nbits[mover]);
+                                    const B128 c = B128{{lo32(cand[0]), hi32(cand[0]), lo32(cand[1]), hi32(cand[1])}};
+                                    const B128 empties = B128{{e0, e1, e2, e3}};
+                                    const uint32_t m = HexStep::count(c);
+                                    const uint32_t rr = __umulhi(x0, 16u * n_empty);
+                                    const uint32_t i0 = rr >> 4;
+                                    if (m == 1) {
+                                        cell = HexStep::first_cell(c);
+                                        have = true;
+                                    } else if (m == n_empty) {
+                                        idx = i0; // every empty cell is maximal: the first visited list position
+                                    } else if (m <= 8) {
+                                        const uint32_t invs = MR_STRIDE_INV[n_empty][rr & 15u], rcp = MR_RCP32[n_empty];
+                                        uint32_t best_j = 0xffffffffu;
+                                        B128 rest = c;
+                                        for (uint32_t q = 0; q < m; ++q) {
+                                            const uint32_t c0 = HexStep::first_cell(rest);
+                                            rest = H::bandn(rest, HexStep::cell_bit(c0));
+                                            const uint32_t jr = visiting_rank(HexStep::rank128(empties, c0), i0, n_empty, invs, rcp);
+                                            if (jr < best_j) {
+                                                best_j = jr;
+                                                cell = c0;
+                                            }
+                                        }
+                                        have = true;
+                                    } else {
+                                        const uint32_t stride = MR_STRIDE[n_empty][rr & 15u];
+                                        uint32_t i = i0;
+                                        for (uint32_t q = 0; q < n_empty; ++q) {
+                                            const uint32_t c0 = HexStep::select128(empties, i);
+                                            if (HexStep::has_cell(c, c0)) {
+                                                cell = c0;
+                                                break;
+                                            }
+                                            i += stride;
+                                            if (i >= n_empty) i -= n_empty;
+                                        }
+                                        have = true;
+                                    }
                                 }
-                                if (idx >= p2) {
-                                    word = e2;
-                                    wbase = 64;
-                                    sub = p2;
-                                }
-                                if (idx >= p3) {
-                                    word = e3;
-                                    wbase = 96;
-                                    sub = p3;
-                                }
-                                idx -= sub;
                             }
-                            uint32_t bc = word - ((word >> 1) & 0x55555555u);
-                            bc = (bc & 0x33333333u) + ((bc >> 2) & 0x33333333u);
-                            bc = (bc + (bc >> 4)) & 0x0f0f0f0fu;            // set bits per byte
-                            const uint32_t incl = bc * 0x01010101u;          // byte j: set bits of bytes 0..j
-                            // bit 7 of byte j is set iff incl_j > idx (incl_j + 127 - idx >= 128; no carry between bytes)
-                            const uint32_t hit = (incl + (0x7fu - idx) * 0x01010101u) & 0x80808080u;
-                            const uint32_t sh8 = ((uint32_t)__ffs((int)hit) - 1u) & ~7u; // 8 * (index of the byte)
-                            const uint32_t below = ((incl << 8) >> sh8) & 0xffu;         // set bits in the bytes before it
-                            const uint32_t cell = wbase + sh8 + s_nth[(word >> sh8) & 0xffu][idx - below];
-                            const uint32_t mover = (leaf_turn + ply) & 1u; // warp-uniform
+                            if (!have) {
+                                const uint32_t c0 = __popc(e0), c1 = __popc(e1), c2 = __popc(e2);
+                                // the idx-th empty cell (ascending), branch-free: three compare-and-select steps pick the
+                                // word, SWAR prefix popcounts the byte, a table the bit.  (Measured against the 5-step binary
+                                // search it replaces: 8 % fewer instructions, 14.05 -> 13.82 ms.  The same word pick with
+                                // predicated IMADs: 14.02 ms; prefix POPCs of the word's low 1, 2, 3 bytes instead of the
+                                // SWAR counts: 13.92 ms.)
+                                uint32_t wbase = 0, word = e0;
+                                {
+                                    const uint32_t p1 = c0, p2 = c0 + c1, p3 = p2 + c2;
+                                    uint32_t sub = 0;
+                                    if (idx >= p1) {
+                                        word = e1;
+                                        wbase = 32;
+                                        sub = p1;
+                                    }
+                                    if (idx >= p2) {
+                                        word = e2;
+                                        wbase = 64;
+                                        sub = p2;
+                                    }
+                                    if (idx >= p3) {
+                                        word = e3;
+                                        wbase = 96;
+                                        sub = p3;
+                                    }
+                                    idx -= sub;
+                                }
+                                uint32_t bc = word - ((word >> 1) & 0x55555555u);
+                                bc = (bc & 0x33333333u) + ((bc >> 2) & 0x33333333u);
+                                bc = (bc + (bc >> 4)) & 0x0f0f0f0fu;            // set bits per byte
+                                const uint32_t incl = bc * 0x01010101u;          // byte j: set bits of bytes 0..j
+                                // bit 7 of byte j is set iff incl_j > idx (incl_j + 127 - idx >= 128; no carry between bytes)
+                                const uint32_t hit = (incl + (0x7fu - idx) * 0x01010101u) & 0x80808080u;
+                                const uint32_t sh8 = ((uint32_t)__ffs((int)hit) - 1u) & ~7u; // 8 * (index of the byte)
+                                const uint32_t below = ((incl << 8) >> sh8) & 0xffu;         // set bits in the bytes before it
+                                cell = wbase + sh8 + s_nth[(word >> sh8) & 0xffu][idx - below];
+                            }
 #pragma unroll
                             for (int q = 0; q < 4; ++q) { // word q receives the bit iff 0 <= cell - 32 q < 32: a clamped shift
                                 const uint32_t add = shl_clamp(1u, cell - 32u * (uint32_t)q);
@@ -345,33 +419,44 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
                         out->pad[0] = out->pad[1] = 0;
                     }
                 }
-                if (WANT_AMAF) {
-                    if (p.amaf) {
-                        // occurrences = stones at the stop ply minus leaf stones (every cell is played at most
-                        // once); lane L owns cells L, L+32, L+64, L+96 of both players: no atomics
-                        __syncwarp();
-                        const uint32_t n_act = min(32u, pid_end - round);
-                        for (uint32_t f = 0; f < n_act; ++f) {
-                            const uint32_t d_f = __shfl_sync(FULL_MASK, depth, f);
-                            const int w_f = __shfl_sync(FULL_MASK, winner, f);
+                if ((WANT_AMAF && p.amaf) || (WANT_MAST && p.mast_delta)) {
+                    // occurrences = stones at the stop ply minus leaf stones (every cell is played at most
+                    // once); lane L owns cells L, L+32, L+64, L+96 of both players: no atomics.  The per-leaf AMAF table
+                    // (backprop.rs:619-640) and the batch-wide MAST delta (:857-870) count the same occurrences.
+                    __syncwarp();
+                    const uint32_t n_act = min(32u, pid_end - round);
+                    for (uint32_t f = 0; f < n_act; ++f) {
+                        const uint32_t d_f = __shfl_sync(FULL_MASK, depth, f);
+                        const int w_f = __shfl_sync(FULL_MASK, winner, f);
+                        if (WANT_AMAF && p.amaf) {
                             if (amaf_plies + d_f > STAT_FLUSH_PLIES) {
                                 flush_stat_table<H>(amaf_tab, p.amaf + (size_t)li * p.amaf_stride, lane, p.tables_in_slots);
                                 amaf_plies = 0;
                             }
                             amaf_plies += d_f;
+                        }
+                        if (WANT_MAST && p.mast_delta) {
+                            if (mast_plies + d_f > STAT_FLUSH_PLIES) {
+                                flush_stat_table<H>(mast_tab, p.mast_delta, lane, p.tables_in_slots);
+                                mast_plies = 0;
+                            }
+                            mast_plies += d_f;
+                        }
 #pragma unroll
-                            for (int pl = 0; pl < 2; ++pl) {
-                                const int u = w_f < 0 ? 0 : (w_f == pl ? 1 : -1);
-                                const uint32_t inc = 1u + ((uint32_t)u << 16);
+                        for (int pl = 0; pl < 2; ++pl) {
+                            const int u = w_f < 0 ? 0 : (w_f == pl ? 1 : -1);
+                            const uint32_t inc = 1u + ((uint32_t)u << 16);
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const uint32_t played = __shfl_sync(FULL_MASK, fin[pl].w[q], f) & ~sh.stones[pl].w[q];
-                                    if ((played >> lane) & 1u) amaf_tab[pl * H::NSLOTS + q * 32 + lane] += inc;
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t played = __shfl_sync(FULL_MASK, fin[pl].w[q], f) & ~sh.stones[pl].w[q];
+                                if ((played >> lane) & 1u) {
+                                    if (WANT_AMAF && p.amaf) amaf_tab[pl * H::NSLOTS + q * 32 + lane] += inc;
+                                    if (WANT_MAST && p.mast_delta) mast_tab[pl * H::NSLOTS + q * 32 + lane] += inc;
                                 }
                             }
                         }
-                        __syncwarp();
                     }
+                    __syncwarp();
                 }
                 __syncwarp();
             }
@@ -395,6 +480,8 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, 8 /* 64 registers: +3.7% me
             if (acc_depth) atomicAdd(reinterpret_cast<unsigned long long *>(&res->sum_depth), (unsigned long long)acc_depth);
         }
     }
+    // the MAST delta is batch-wide: it leaves shared memory when the warp runs out of tasks
+    if (WANT_MAST && p.mast_delta) flush_stat_table<H>(mast_tab, p.mast_delta, lane, p.tables_in_slots);
     batch_epilogue(p);
 }
 

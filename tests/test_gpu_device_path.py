@@ -111,3 +111,82 @@ def test_two_gpu_context_table_policies(game):
     # and the single-device tables are the oracle's literal ones
     ref = o.playout_batch(game, leaves, k, policy=o.EPS_LGR2, eps=0.1, seed=11, max_depth=200, want_final_tables=True, threads=o.host_threads())
     assert (mb.GpuRollout.apply_replies2(t2, a1.reply2_inserts, a_r1) == ref["replies2_final"]).all()
+
+
+@pytest.mark.parametrize("game,policy", [(o.BREAKTHROUGH, o.EPS_MAST), (o.KNIGHTTHROUGH, o.EPS_MAST), (o.HEX11, o.EPS_MAST), (o.HEX11, o.UNIFORM),
+                                         (o.CONNECT4, o.UNIFORM)])
+def test_tables_in_slot_space_equal_the_dense_tables(game, policy):
+    """MR_TABLES_IN_SLOTS: the AMAF tables and the MAST delta indexed by compact per-player action slot hold exactly the
+    dense tables' entries (host path and device-resident path), and nothing else."""
+    from mcts_b200.rollout import slots_to_dense
+
+    dev = torch.device("cuda", 0)
+    n, k = 40, 96
+    leaves = o.random_positions(game, 3, 10, n)
+    strat = mb.EpsilonGreedyMast(0.1) if policy == o.EPS_MAST else mb.Uniform()
+    with mb.GpuRollout(mb.Game(game), strat, seed=5, max_playout_depth=200) as g:
+        mast = o.playout_batch(game, leaves, 16, seed=1, max_depth=200, want_mast_delta=True)["mast_delta"] if policy == o.EPS_MAST else None
+        kw = dict(stats=mast, want_mast_delta=True, want_amaf=True, leaf_id_base=3)
+        dense = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, **kw)
+        slots = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, tables_in_slots=True, **kw)
+        ns = mb.rollout.num_slots(g.game)
+        assert slots.mast_delta.shape == (2, ns) and slots.amaf.shape == (n, 2, ns)
+        assert slots.results.tobytes() == dense.results.tobytes()
+        assert slots_to_dense(g.game, slots.mast_delta).tobytes() == dense.mast_delta.tobytes()
+        assert slots_to_dense(g.game, slots.amaf).tobytes() == dense.amaf.tobytes()
+        assert int(slots.mast_delta["visits"].sum()) == int(dense.mast_delta["visits"].sum()) == int(dense.results["sum_depth"].sum())
+        # device-resident path, slot space
+        if mast is not None:
+            g.set_mast(mast)
+        d_leaves = torch.from_numpy(leaves.view(np.uint8).reshape(-1).copy()).to(dev)
+        d_res = torch.zeros(n * 24, dtype=torch.uint8, device=dev)
+        d_delta = torch.zeros(2 * ns * 2, dtype=torch.int32, device=dev)
+        d_amaf = torch.zeros(n * 2 * ns * 2, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        g.launch_device(d_leaves.data_ptr(), d_res.data_ptr(), n, k, leaf_id_base=3, d_mast_delta=d_delta.data_ptr(), d_amaf=d_amaf.data_ptr(),
+                        tables_in_slots=True)
+        torch.cuda.synchronize()
+        assert d_delta.cpu().numpy().tobytes() == slots.mast_delta.tobytes()
+        assert d_amaf.cpu().numpy().tobytes() == slots.amaf.tobytes()
+
+
+def test_wait_returns_while_a_later_slot_is_still_running():
+    """Every slot has its own stream and completion signal: mr_wait(slot 0) must come back when slot 0's small batch is
+    done, not when the large batch submitted after it on slot 1 is (round 1 waited on one shared stream)."""
+    import time
+
+    leaves = mb.initial_state(mb.Game.OTHELLO)
+    small = np.repeat(leaves, 32)
+    big = np.repeat(leaves, 2048)
+    with mb.GpuRollout(mb.Game.OTHELLO, mb.Uniform(), seed=1) as g:
+        g.simulate_many(big, 1024)  # warm: buffers allocated, kernel loaded
+        g.simulate_many(small, 32)
+        torch.cuda.synchronize()
+        g.submit(small, 32, slot=0)
+        g.submit(big, 2048, slot=1)  # ~4 M playouts of 60 plies: tens of milliseconds
+        t0 = time.perf_counter()
+        r0 = g.wait(0)
+        t_small = time.perf_counter() - t0
+        r1 = g.wait(1)
+        t_big = time.perf_counter() - t0
+    assert int(r0.results["wins"].sum() + r0.results["draws"].sum()) == 32 * 32
+    assert int(r1.results["wins"].sum() + r1.results["draws"].sum()) == 2048 * 2048
+    assert t_big > 5e-3, t_big
+    assert t_small < 0.25 * t_big, (t_small, t_big)
+
+
+def test_four_slots_in_flight_are_independent_and_ordered_by_slot_only():
+    """MR_NUM_SLOTS batches submitted back to back, waited in reverse order: each slot returns its own batch's results,
+    bit-identical to the same batch run alone."""
+    game = o.BREAKTHROUGH
+    leaves = o.random_positions(game, 3, 10, 24)
+    mast = o.playout_batch(game, leaves, 16, seed=1, max_depth=200, want_mast_delta=True)["mast_delta"]
+    with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyMast(0.1), seed=5, max_playout_depth=200) as g:
+        alone = [g.simulate_many(leaves.view(mb.LEAF_DTYPE), 64 + 32 * s, stats=mast, want_mast_delta=True, leaf_id_base=100 * s) for s in range(4)]
+        for rep in range(3):  # the fused epilogue leaves the device buffers clean for the slot's next batch
+            for s in range(4):
+                g.submit(leaves.view(mb.LEAF_DTYPE), 64 + 32 * s, slot=s, stats=mast, want_mast_delta=True, leaf_id_base=100 * s)
+            for s in reversed(range(4)):
+                r = g.wait(s)
+                assert r.results.tobytes() == alone[s].results.tobytes(), (rep, s)
+                assert r.mast_delta.tobytes() == alone[s].mast_delta.tobytes(), (rep, s)
