@@ -157,20 +157,20 @@ def test_wait_returns_while_a_later_slot_is_still_running():
 
     leaves = mb.initial_state(mb.Game.OTHELLO)
     small = np.repeat(leaves, 32)
-    big = np.repeat(leaves, 2048)
+    big = np.repeat(leaves, 4096)
     with mb.GpuRollout(mb.Game.OTHELLO, mb.Uniform(), seed=1) as g:
-        g.simulate_many(big, 1024)  # warm: buffers allocated, kernel loaded
+        g.simulate_many(big, 256)  # warm: buffers allocated, kernel loaded
         g.simulate_many(small, 32)
         torch.cuda.synchronize()
         g.submit(small, 32, slot=0)
-        g.submit(big, 2048, slot=1)  # ~4 M playouts of 60 plies: tens of milliseconds
+        g.submit(big, 4096, slot=1)  # 2^24 playouts of 60 plies: ~18 ms
         t0 = time.perf_counter()
         r0 = g.wait(0)
         t_small = time.perf_counter() - t0
         r1 = g.wait(1)
         t_big = time.perf_counter() - t0
     assert int(r0.results["wins"].sum() + r0.results["draws"].sum()) == 32 * 32
-    assert int(r1.results["wins"].sum() + r1.results["draws"].sum()) == 2048 * 2048
+    assert int(r1.results["wins"].sum() + r1.results["draws"].sum()) == 4096 * 4096
     assert t_big > 5e-3, t_big
     assert t_small < 0.25 * t_big, (t_small, t_big)
 
