@@ -648,6 +648,51 @@ def test_win_rate_agrees_with_independent_cpu_rollouts():
         assert abs(p1 - p2) < z * se + 1e-9, (c, p1, p2)
 
 
+def wilson_interval(successes: float, total: int, z: float):
+    """mcts-bench/src/tournament.rs:98-111, restated."""
+    if total == 0:
+        return 0.0, 1.0
+    n = float(total)
+    p_hat = successes / n
+    z2 = z * z
+    denom = 1.0 + z2 / n
+    center = p_hat + z2 / (2.0 * n)
+    margin = z * np.sqrt(p_hat * (1.0 - p_hat) / n + z2 / (4.0 * n * n))
+    return max(0.0, (center - margin) / denom), min(1.0, (center + margin) / denom)
+
+
+@pytest.mark.parametrize("game,policy,k,max_depth", [
+    (o.CONNECT4, o.UNIFORM, 20000, 0),
+    (o.BREAKTHROUGH, o.EPS_MAST, 4000, 200),   # the headline policy: epsilon-greedy over a MAST table
+    (o.OTHELLO, o.DECISIVE_WIN, 4000, 0),      # BASELINE config 4's rollout policy
+])
+def test_root_child_win_rates_inside_wilson_intervals_of_cpu_rollouts(game, policy, k, max_depth):
+    """north_star's statistical parity: for every root child, the GPU's win rate (its own seeds) must lie inside the
+    Wilson 99.9 % interval (z = 3.29, `wilson_interval`, mcts-bench/src/tournament.rs:98-111) of the CPU oracle's
+    rollouts drawn with DIFFERENT seeds, and vice versa -- for two independent seed pairs.  (With ~20 children, two seed
+    pairs and two directions a correct engine trips a 99.9 % interval about once in twelve runs of this test by chance
+    alone; the seeds are fixed, so the outcome is deterministic.)"""
+    root = o.initial_state(game)
+    children = np.concatenate([o.apply(game, root, a) for a in o.generate_actions(game, root)])
+    mover = int(root["turn"][0])
+    strat = {o.UNIFORM: mb.Uniform(), o.EPS_MAST: mb.EpsilonGreedyMast(0.1), o.DECISIVE_WIN: mb.DecisiveMoveWin()}[policy]
+    mast = None
+    if policy == o.EPS_MAST:  # one table for both sides: the delta of a uniform batch
+        mast = o.playout_batch(game, children, 64, seed=77, max_depth=max_depth, want_mast_delta=True, threads=o.host_threads())["mast_delta"]
+    z = 3.29
+    for gpu_seed, cpu_seed in [(1, 2), (1001, 2002)]:
+        with mb.GpuRollout(mb.Game(game), strat, seed=gpu_seed, max_playout_depth=max_depth) as g:
+            got = g.simulate_many(children.view(mb.LEAF_DTYPE), k, stats=mast).results
+        ref = o.playout_batch(game, children, k, policy=policy, eps=0.1, max_depth=max_depth, seed=cpu_seed, mast=mast,
+                              threads=o.host_threads())["results"]
+        for c in range(len(children)):
+            wg, wc = int(got[c]["wins"][mover]), int(ref[c]["wins"][mover])
+            lo, hi = wilson_interval(wc, k, z)
+            assert lo <= wg / k <= hi, (c, "gpu rate outside the cpu interval", wg / k, lo, hi)
+            lo, hi = wilson_interval(wg, k, z)
+            assert lo <= wc / k <= hi, (c, "cpu rate outside the gpu interval", wc / k, lo, hi)
+
+
 def test_randomized_differential_sweep():
     """Seeded random batch shapes: game x policy x flags x (n, k) x leaf id base x depth cutoff, GPU vs oracle,
     every playout's trace, record, final state and every aggregate compared bit for bit."""

@@ -224,7 +224,8 @@ def test_othello_130452_replay():  # lib.rs:1171-1209
 def test_othello_symmetry_stress_sweep():
     """mcts-tests/tests/stress.rs:249-454 restated (same xorshift64* stream, seed 0xdead_beef_cafe_babe).
     The reference runs 100 000 games under `cargo test --test stress`; 4 000 here keeps the CPU suite
-    short (tests/test_oracle_stress_full.py holds the full-size run behind an env switch)."""
+    short (tests/test_oracle_stress_full.py holds the full-size run behind ORACLE_STRESS_FULL=1; profiles/oracle_stress_full_r02.txt
+    records it)."""
     games, plies = C.c_uint64(), C.c_uint64()
     rc = o.lib().orc_stress_othello(4000, C.byref(games), C.byref(plies))
     assert rc == 0, f"mismatch code {rc} in game {games.value}"
