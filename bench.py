@@ -10,8 +10,8 @@ under "per_game" / "depth_matrix" / "search".
 
   value  : whole-job playouts/s with the leaves already resident in HBM (device-timed, CUDA events
            on the launching stream, max over ranks)
-  e2e    : the same metric through the reference-facing C ABI calls (mr_submit + mr_wait, double-buffered
-           over two slots as the header describes) with HOST buffers: staging copy, H2D of the leaves,
+  e2e    : the same metric through the reference-facing C ABI calls (mr_submit + mr_wait over three of the
+           ABI's four slots, as the header describes) with HOST buffers: staging copy, H2D of the leaves,
            the MAST snapshot in the kernel parameters and the results + MAST delta written back to host
            memory inside the timed region
   N > 1  : one process per GPU (torchrun); every rank runs its own batch (weak scaling) and the ranks
@@ -462,17 +462,20 @@ def run_gpu(args):
             kw = dict(stats=mast, want_mast_delta=want_delta, want_amaf=w["amaf"], tables_in_slots=True)
 
             def e2e_pass(count, base):
-                g.submit(leaves, k, slot=0, leaf_id_base=root_merge.leaf_id_base(rank, world, base, n_leaves), **kw)
+                # three slots: while batch i's tables are merged over the ranks (a blocking NCCL round trip whose kernel
+                # only gets an SM when batch i+1's persistent kernel drains) batch i+2 is already queued behind i+1
+                for j in range(min(2, count)):
+                    g.submit(leaves, k, slot=j % 3, leaf_id_base=root_merge.leaf_id_base(rank, world, base + j, n_leaves), **kw)
                 merged = None
                 for i in range(count):
-                    if i + 1 < count:
-                        g.submit(leaves, k, slot=(i + 1) % 2, leaf_id_base=root_merge.leaf_id_base(rank, world, base + i + 1, n_leaves), **kw)
-                    r = g.wait(i % 2)
+                    if i + 2 < count:
+                        g.submit(leaves, k, slot=(i + 2) % 3, leaf_id_base=root_merge.leaf_id_base(rank, world, base + i + 2, n_leaves), **kw)
+                    r = g.wait(i % 3)
                     if dist is not None and want_delta:
                         merged = root_merge.merge_table_i32(r.mast_delta, device=dev)
                 return r, merged
 
-            e2e_pass(2, 5000)
+            e2e_pass(3, 5000)
             barrier()
             t0 = time.perf_counter()
             r, merged = e2e_pass(steps, 6000)
@@ -483,7 +486,7 @@ def run_gpu(args):
             h2d = n_leaves * 40 + 1536  # leaves + the kernel parameter block (holds the MAST rank planes)
             d2h = n_leaves * 24 + (2 * ns * 8 if want_delta else 0) + (n_leaves * 2 * ns * 8 if w["amaf"] else 0)
             out["e2e"] = {"value": world * n_leaves * k * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                          "how": "mr_submit / mr_wait with host buffers, two slots in flight" + ("; MAST delta merged over ranks by NCCL every step" if dist is not None and want_delta else "")}
+                          "how": "mr_submit / mr_wait with host buffers, three slots in flight" + ("; MAST delta merged over ranks by NCCL every step" if dist is not None and want_delta else "")}
             if dist is not None and want_delta:
                 # the merged table every rank ends with must be the sum of the ranks' own last tables
                 mine = torch.from_numpy(np.ascontiguousarray(r.mast_delta).view(np.int32).reshape(-1).copy()).to(dev)
