@@ -238,4 +238,21 @@ inline int action_id(int game, uint16_t a) {
     return a;
 }
 
+// compact per-player action slot (the index of the slot-space tables, include/mcts_rollout.h "N-gram Selection
+// Technique") of an action that IS legal for `player` -- the unchecked inline form of mr_action_slot for the driver's
+// expansion loop
+inline int action_slot(int game, int player, uint16_t a) {
+    if (game == MR_BREAKTHROUGH) {
+        const int src = a >> 8, dst = a & 0xff;
+        return src * 3 + (dst - src - (player ? 7 : -9));
+    }
+    if (game == MR_KNIGHTTHROUGH) {
+        static const int8_t kind_of_delta[35] = {0, -1, 1, -1, -1, -1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1,
+                                                 -1, -1, -1, -1, -1, 4, -1, -1, -1, 5, -1, -1, -1, -1, 6, -1, 7}; // delta + 17
+        const int src = a >> 8, dst = a & 0xff;
+        return src * 8 + kind_of_delta[dst - src + 17];
+    }
+    return a;
+}
+
 } // namespace mr_host

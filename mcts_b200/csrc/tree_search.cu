@@ -228,7 +228,7 @@ struct Tree {
         n.n_children = (uint16_t)cnt;
         for (int i = 0; i < cnt; ++i) {
             action.push_back(acts[i]);
-            slot.push_back((uint16_t)mr_action_slot(game, n.player, acts[i]));
+            slot.push_back((uint16_t)mr_host::action_slot(game, n.player, acts[i]));
             child.push_back(-1);
             edge.push_back(Stats());
             if (want_amaf_rows) amaf_row.push_back(AmafRow());
@@ -276,8 +276,8 @@ struct Search {
 
     // select/rave.rs:157-184 get_ref: the child itself when its incoming edge has total_visits >= threshold (decided in
     // best_child), else the nearest such node on the path, else the root
-    uint32_t grave_ref_ancestor(const std::vector<PathEntry> &path) const {
-        for (size_t i = path.size(); i-- > 1;) {
+    uint32_t grave_ref_ancestor(const std::vector<PathEntry> &path, size_t len) const {
+        for (size_t i = len; i-- > 1;) {
             const Stats &e = t.edge[t.nodes[path[i - 1].node].first + path[i].idx];
             if (e.visits + e.vloss >= d->grave_threshold) return path[i].node;
         }
@@ -291,12 +291,69 @@ struct Search {
         return t.edge[parent.first + me.idx];
     }
 
-    // select/mod.rs:343-386 with the strategies' scores
+    // ---- per-edge score cache ----
+    // Between two backprops the only statistics that change are the virtual losses of the edges a descent walks, so the
+    // score of every OTHER child of a node stays what it was when the node was last evaluated.  A node's children are
+    // scored in full on its first visit of an epoch (epoch = the number of backprop batches applied, bumped too whenever
+    // an edge crosses the GRAVE threshold, which changes reference nodes below it) and the walked edge is re-scored when
+    // its virtual loss changes; the arg-max then reads cached numbers.  The numbers are the ones a fresh evaluation
+    // would produce (same inputs, same formula), so the search is unchanged -- the oracle re-evaluates everything on
+    // every descent and the parity tests compare.  Off with transpositions: a shared node is reached along different
+    // edges, and the "current" statistics its scores depend on are the incoming edge's.
+    struct LevelCtx { // what scoring a child of one path node needs, kept per level of the current descent
+        double parent_log = 0.0;
+        int player = 0;
+        bool anc_done = false;
+        const GraveTable *anc_tab = nullptr;
+    };
+    std::vector<double> score_cache;  // per edge
+    std::vector<uint32_t> node_epoch; // per node: the epoch its children's cached scores belong to (0 = never)
+    uint32_t epoch = 1;
+    bool cache_ok = false;
+    std::vector<LevelCtx> lctx; // parallel to the path of the descent in progress
+
+    double edge_score(const std::vector<PathEntry> &path, size_t level, uint32_t ei, LevelCtx &c) {
+        const Stats &e = t.edge[ei];
+        uint32_t grave_n = 0;
+        double grave_q = 0.0;
+        if (d->select == MR_SELECT_GRAVE) {
+            // get_ref: the child itself once its edge has the threshold visits, else the nearest such ancestor --
+            // which is the same node for every child of this node, so it is resolved once per visit (anc_tab)
+            const bool own_ref = e.visits + e.vloss >= d->grave_threshold;
+            if (!own_ref && !c.anc_done) {
+                c.anc_tab = grave_of(t.nodes[grave_ref_ancestor(path, level + 1)], false);
+                c.anc_done = true;
+            }
+            if (const GraveTable *tab = own_ref ? grave_of(t.nodes[(uint32_t)t.child[ei]], false) : c.anc_tab) {
+                const size_t g = (size_t)c.player * S + t.slot[ei];
+                grave_n = tab->visits[g];
+                grave_q = (double)tab->score[g];
+            }
+        }
+        return created_child_score(d, e, t.want_amaf_rows ? &t.amaf_row[ei] : nullptr, c.player, c.parent_log, grave_n, grave_q);
+    }
+
+    // an edge's virtual loss changes from `before` to its current value: keep the cache exact
+    void edge_changed(const std::vector<PathEntry> &path, size_t level, uint32_t ei, uint32_t total_before) {
+        if (!cache_ok) return;
+        const Stats &e = t.edge[ei];
+        if (d->select == MR_SELECT_GRAVE && total_before < d->grave_threshold && e.visits + e.vloss >= d->grave_threshold) ++epoch;
+        if (t.child[ei] >= 0) score_cache[ei] = edge_score(path, level, ei, lctx[level]);
+    }
+
+    // select/mod.rs:343-386 with the strategies' scores; `path.back()` is the node, `lctx.back()` its context
     uint32_t best_child(const std::vector<PathEntry> &path, uint32_t descent) {
-        const Node &node = t.nodes[path.back().node];
+        const uint32_t node_id = path.back().node;
+        const Node &node = t.nodes[node_id];
+        const size_t level = path.size() - 1;
+        LevelCtx &c = lctx[level];
         const int player = node.player;
         const Stats &cur = current_stats(path);
         const double parent_log = std::log(std::max(1.0, (double)cur.visits)); // ucb.rs:34-37: without virtual loss
+        c.parent_log = parent_log;
+        c.player = player;
+        c.anc_done = false;
+        c.anc_tab = nullptr;
         const double unvisited_value = unvisited_child_score(d, cur, player, parent_log);
         const uint32_t n = node.n_children;
         const uint32_t r = mulhi32(philox_word0(d->seed, descent, (uint32_t)path.size() - 1, 0, 2), 16u * n);
@@ -316,37 +373,17 @@ struct Search {
                 if (j >= n) j -= n;
             }
         }
+        if (cache_ok && node_epoch[node_id] != epoch) { // first visit of this epoch: score every existing child once
+            for (uint32_t j = 0; j < n; ++j)
+                if (t.child[node.first + j] >= 0) score_cache[node.first + j] = edge_score(path, level, node.first + j, c);
+            node_epoch[node_id] = epoch;
+        }
         bool have = false;
         double best = 0.0;
         uint32_t best_i = i;
-        bool anc_done = false;
-        const GraveTable *anc_tab = nullptr;
-        const bool grave_sel = d->select == MR_SELECT_GRAVE;
         for (uint32_t k = 0; k < n; ++k) {
             const uint32_t ei = node.first + i;
-            double score;
-            if (t.child[ei] < 0) {
-                score = unvisited_value;
-            } else {
-                const Stats &e = t.edge[ei];
-                uint32_t grave_n = 0;
-                double grave_q = 0.0;
-                if (grave_sel) {
-                    // get_ref: the child itself once its edge has the threshold visits, else the nearest such ancestor --
-                    // which is the same node for every child of this node, so it is resolved once (anc_tab)
-                    const bool own_ref = e.visits + e.vloss >= d->grave_threshold;
-                    if (!own_ref && !anc_done) {
-                        anc_tab = grave_of(t.nodes[grave_ref_ancestor(path)], false);
-                        anc_done = true;
-                    }
-                    if (const GraveTable *tab = own_ref ? grave_of(t.nodes[(uint32_t)t.child[ei]], false) : anc_tab) {
-                        const size_t g = (size_t)player * S + t.slot[ei];
-                        grave_n = tab->visits[g];
-                        grave_q = (double)tab->score[g];
-                    }
-                }
-                score = created_child_score(d, e, t.want_amaf_rows ? &t.amaf_row[ei] : nullptr, player, parent_log, grave_n, grave_q);
-            }
+            const double score = t.child[ei] < 0 ? unvisited_value : (cache_ok ? score_cache[ei] : edge_score(path, level, ei, c));
             if (!have || score > best) {
                 have = true;
                 best = score;
@@ -361,9 +398,11 @@ struct Search {
     // search/shared.rs:569-736, with the in-flight trials counted by the expansion test (file header)
     void select(uint32_t descent, std::vector<PathEntry> &path) {
         path.clear();
+        lctx.clear();
         uint32_t cur = 0, incoming = 0;
         for (;;) {
             path.push_back({cur, incoming});
+            lctx.emplace_back();
             const Stats &cs = current_stats(path);
             // trials in flight through this node from OTHER descents: every gathered descent holds k virtual losses on
             // each of its edges (root_inflight for the root); this one has added 1 to the edge it just came down
@@ -373,12 +412,15 @@ struct Search {
             if (t.nodes[cur].status == UNEXPANDED) {
                 t.expand(cur);
                 if (t.nodes[cur].status == TERMINAL) return;
+                score_cache.resize(t.edge.size(), 0.0);
             }
             const uint32_t best = best_child(path, descent);
             incoming = best;
             const uint32_t ei = t.nodes[cur].first + best;
+            const uint32_t total_before = t.edge[ei].visits + t.edge[ei].vloss;
             t.edge[ei].vloss += 1; // one virtual loss per traversed edge
             if (t.child[ei] >= 0) {
+                edge_changed(path, path.size() - 1, ei, total_before);
                 cur = (uint32_t)t.child[ei];
             } else {
                 mr_leaf s = t.nodes[cur].state;
@@ -396,9 +438,12 @@ struct Search {
                     id = t.add_node(s);
                 }
                 t.child[ei] = (int32_t)id;
+                if (node_epoch.size() < t.nodes.size()) node_epoch.resize(t.nodes.size(), 0u);
+                edge_changed(path, path.size() - 1, ei, total_before);
                 cur = id;
                 if (d->expand_threshold > 0) {
                     path.push_back({cur, incoming});
+                    lctx.emplace_back();
                     return;
                 }
             }
@@ -407,7 +452,13 @@ struct Search {
 
     // shared.rs:787-805: k-1 extra virtual losses on every edge of the path; the root counts the k trials in flight
     void add_path_virtual_loss(const std::vector<PathEntry> &path, uint32_t k) {
-        for (size_t i = 1; i < path.size(); ++i) t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
+        if (k > 1)
+            for (size_t i = 1; i < path.size(); ++i) {
+                const uint32_t ei = t.nodes[path[i - 1].node].first + path[i].idx;
+                const uint32_t total_before = t.edge[ei].visits + t.edge[ei].vloss;
+                t.edge[ei].vloss += k - 1;
+                edge_changed(path, i - 1, ei, total_before);
+            }
         t.root_inflight += k;
     }
 
@@ -616,6 +667,8 @@ int run_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, Roo
     s.t.want_amaf_rows = desc->select == MR_SELECT_AMAF;
     s.t.add_node(*root);
     if (s.t.use_table) s.t.table.emplace(key_of(*root), 0u);
+    s.cache_ok = !s.t.use_table;
+    s.node_epoch.assign(1, 0u);
 
     const uint32_t B = desc->batch_leaves, k = desc->playouts_per_leaf;
     const bool want_amaf = desc->select == MR_SELECT_GRAVE || desc->select == MR_SELECT_AMAF;
@@ -720,6 +773,7 @@ int run_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, Roo
             if (rc != MR_OK) return rc;
         }
         const double t1 = now_s();
+        ++s.epoch; // statistics change: every cached child score is stale
         if (lgr) s.merge_replies(bb.paths, bb.nb, k, reply_upd, last_win);
         for (size_t i = 0; i < n_bigram; ++i) {
             s.bigram[i].visits += bigram_delta[i].visits;
