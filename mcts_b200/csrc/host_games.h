@@ -58,7 +58,26 @@ inline uint64_t oth_flips(uint64_t P, uint64_t O, int sq) {
             if (dr || dc) f |= oth_ray_flips(P, O, sq, dr, dc);
     return f;
 }
+// legal squares of the player P: an empty square at the far end of a run of opponent discs that starts next to an own
+// disc, in any of the eight directions (the move SET of othello/lib.rs:132-180; the set has no order).  Fill by repeated
+// shifts; the opponent board is cut to columns 1..6 for the directions that change column, so nothing wraps around a row.
 inline uint64_t oth_moves(uint64_t P, uint64_t O) {
+    const uint64_t inner = O & 0x7e7e7e7e7e7e7e7eull;
+    uint64_t m = 0;
+    const int shifts[4] = {1, 7, 9, 8};
+    for (int d = 0; d < 4; ++d) {
+        const int s = shifts[d];
+        const uint64_t M = s == 8 ? O : inner;
+        uint64_t up = M & (P << s), dn = M & (P >> s);
+        for (int i = 0; i < 5; ++i) {
+            up |= M & (up << s);
+            dn |= M & (dn >> s);
+        }
+        m |= (up << s) | (dn >> s);
+    }
+    return m & ~(P | O);
+}
+inline uint64_t oth_moves_by_scan(uint64_t P, uint64_t O) { // the definition, square by square (checked against the fill)
     uint64_t m = 0;
     const uint64_t empty = ~(P | O);
     for (int sq = 0; sq < 64; ++sq)
