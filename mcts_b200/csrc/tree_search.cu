@@ -337,7 +337,12 @@ struct Search {
     void edge_changed(const std::vector<PathEntry> &path, size_t level, uint32_t ei, uint32_t total_before) {
         if (!cache_ok) return;
         const Stats &e = t.edge[ei];
-        if (d->select == MR_SELECT_GRAVE && total_before < d->grave_threshold && e.visits + e.vloss >= d->grave_threshold) ++epoch;
+        // crossing the GRAVE threshold makes the child the reference node of everything BELOW it: cached scores in its
+        // subtree are stale (a child that has not been expanded has no subtree -- the common case, a fresh leaf whose
+        // first k trials already reach the threshold)
+        if (d->select == MR_SELECT_GRAVE && total_before < d->grave_threshold && e.visits + e.vloss >= d->grave_threshold &&
+            t.child[ei] >= 0 && t.nodes[(uint32_t)t.child[ei]].status == EXPANDED)
+            ++epoch;
         if (t.child[ei] >= 0) score_cache[ei] = edge_score(path, level, ei, lctx[level]);
     }
 
