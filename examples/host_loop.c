@@ -54,7 +54,7 @@ int main(void) {
         printf("leaf %u: black %ld  white %ld  draws %ld  mean depth %.2f\n", i, w0, w1, dr, (double)res[i].sum_depth / (double)k);
     }
 
-    /* ---- 2. a move: UCT (UCB1, c = sqrt 2), 64 leaves x 16 playouts per batch, pipelined over the two slots ---- */
+    /* ---- 2. a move: UCT (UCB1, c = sqrt 2), 64 leaves x 16 playouts per batch, four batches in flight (one per slot) ---- */
     mr_search_desc s;
     memset(&s, 0, sizeof s);
     s.game = MR_CONNECT4;
@@ -65,7 +65,7 @@ int main(void) {
     s.batch_leaves = 64;
     s.playouts_per_leaf = 16;
     s.expand_threshold = 1;
-    s.flags = MR_SEARCH_PIPELINED;
+    s.pipeline_depth = MR_NUM_SLOTS;
     s.exploration_c = 1.4142135623730951;
     s.seed = 7;
     uint16_t best = 0;

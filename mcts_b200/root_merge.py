@@ -74,6 +74,35 @@ def merge_table_i32(table: np.ndarray, device=None, group=None) -> np.ndarray:
     return out
 
 
+class PendingMerge:
+    """An all-reduce of a (visits, score) table in flight: `result()` waits for it and returns the merged table."""
+
+    def __init__(self, buf: torch.Tensor, work, like: np.ndarray):
+        self._buf, self._work, self._like = buf, work, like
+
+    def result(self) -> np.ndarray:
+        if self._work is not None:
+            self._work.wait()
+        out = np.empty_like(self._like)
+        out.view(np.int32).reshape(-1)[:] = self._buf.cpu().numpy()
+        return out
+
+
+def merge_table_i32_async(table: np.ndarray, device=None, group=None) -> PendingMerge:
+    """`merge_table_i32` without the wait: the host copies the table to the device, enqueues the all-reduce and goes on
+    (gather the next batch, submit it); `result()` collects the merged table one step later.  The table a batch plays
+    from is a batch stale by construction, so nothing needs the merged table any sooner -- and the ranks stop running
+    in lock-step through a blocking collective every step."""
+    like = np.ascontiguousarray(table)
+    buf = torch.from_numpy(like.view(np.int32).reshape(-1).copy())
+    if device is not None:
+        buf = buf.to(device, non_blocking=True)
+    work = None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return PendingMerge(buf, work, like)
+
+
 PRIMES = (14323, 18713, 19463, 30553, 33469, 45343, 50221, 51991, 53201, 56923, 64891, 72763, 74471, 81647, 92581, 94693)
 
 

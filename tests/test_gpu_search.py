@@ -370,3 +370,30 @@ def test_root_parallel_threads_equal_the_sum_of_independent_searches():
     assert (merged.children["visits"] == visits).all() and (merged.children["score"] == score).all()
     assert merged.playouts == n_thr * iters * k
     assert visits[list(merged.children["action"]).index(merged.best_action)] == visits.max()
+
+
+def test_search_argument_errors_are_codes_not_crashes():
+    """mr_search / mr_search_root_parallel validate their descriptors: bad arguments come back as MR_ERR_INVALID."""
+    import ctypes as C
+
+    from mcts_b200 import _lib
+    from mcts_b200._lib import MAX_ROOT_CHILDREN, ROOT_CHILD_DTYPE, SearchStats, ptr
+
+    L = _lib.load()
+    root = mb.initial_state(mb.Game.CONNECT4)
+    children = np.zeros(MAX_ROOT_CHILDREN, dtype=ROOT_CHILD_DTYPE)
+    best, n, st = C.c_uint16(), C.c_uint32(), SearchStats()
+    with mb.GpuSearch(mb.Game.CONNECT4, mb.Uniform(), max_iterations=64, batch_leaves=8, num_rollouts_per_leaf=4, seed=1) as s:
+        for field, value in [("pipeline_depth", 5), ("select", 9), ("rave_schedule", 3), ("batch_leaves", 0), ("max_iterations", 0), ("game", 7)]:
+            saved = getattr(s.desc, field)
+            setattr(s.desc, field, value)
+            rc = L.mr_search(s.rollout._h, C.byref(s.desc), ptr(root), C.byref(best), ptr(children), C.byref(n), C.byref(st))
+            setattr(s.desc, field, saved)
+            assert rc == 1, (field, rc)
+        handles = (C.c_void_p * 2)(s.rollout._h, None)
+        sts = (SearchStats * 2)()
+        assert L.mr_search_root_parallel(handles, 2, C.byref(s.desc), ptr(root), C.byref(best), ptr(children), C.byref(n), sts) == 1
+        assert L.mr_search_root_parallel(handles, 0, C.byref(s.desc), ptr(root), C.byref(best), ptr(children), C.byref(n), sts) == 1
+        # and the context is still usable afterwards
+        r = s.choose_action(root)
+        assert r.playouts == 64 * 4 and r.best_action in _legal_root_actions(o.CONNECT4)

@@ -39,6 +39,7 @@ def _worker(rank, world, port, q):
         slots["visits"] = rng.integers(0, 4000, size=(2, 192))
         slots["score"] = rng.integers(-4000, 4000, size=(2, 192))
         msl = root_merge.merge_table_i32(slots)
+        assert root_merge.merge_table_i32_async(slots).result().tobytes() == msl.tobytes()  # the deferred form of the same merge
         b, e = root_merge.shard_range(4097, rank, world)
         q.put((rank, visits, scores, mv, ms, delta, md, (b, e), slots, msl))
     finally:
