@@ -535,6 +535,10 @@ void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, co
     kp.max_depth = d->max_playout_depth ? d->max_playout_depth : 0xffffffffu;
     kp.seed_lo = (uint32_t)d->seed;
     kp.seed_hi = (uint32_t)(d->seed >> 32);
+    for (uint32_t r = 0; r < 10; ++r) {
+        kp.philox_keys[r][0] = kp.seed_lo + r * 0x9E3779B9u;
+        kp.philox_keys[r][1] = kp.seed_hi + r * 0xBB67AE85u;
+    }
     kp.leaf_id_base = d->leaf_id_base;
     // explore iff x1 < floor(eps * 2^32)
     double t = d->epsilon * 4294967296.0;
@@ -543,6 +547,14 @@ void fill_params(const mr_ctx *ctx, KernelParams &kp, const mr_batch_desc *d, co
     kp.eps_thr_m1 = thr > 0 ? (uint32_t)(thr - 1) : 0;
     kp.max_trace = d->max_trace;
     kp.trace_cap = trace_cap;
+    // the per-lane playout log (rollout_kernel.cuh) is a ring with room for a whole playout plus slack, so that a lane's
+    // log holds several playouts when it is drained; the LGR / NST kernels index the scratch by ply
+    kp.trace_rows = trace_cap;
+    if (trace_cap && !policy_is_lgr((int)d->policy) && d->policy != MR_EPS_NST) {
+        uint32_t rows = 512;
+        while (rows < trace_cap + trace_cap / 2u + 2u) rows <<= 1;
+        kp.trace_rows = rows;
+    }
     kp.grab_div = 2;
     kp.tables_in_slots = (d->flags & MR_TABLES_IN_SLOTS) ? 1u : 0u;
     kp.amaf_stride = 2u * (uint32_t)table_len(d);
@@ -572,7 +584,7 @@ int launch_on(mr_ctx *ctx, Device &dv, kernel_fn fn, KernelParams &kp, const Lau
     if (kp.grab_min < 32) kp.grab_min = 32;
     if (kp.grab_max < kp.grab_min) kp.grab_max = kp.grab_min;
     if (kp.trace_cap) {
-        const size_t need = (size_t)blocks * WARPS_PER_BLOCK * kp.trace_cap * 32u;
+        const size_t need = (size_t)blocks * WARPS_PER_BLOCK * kp.trace_rows * 32u;
         CUDA_TRY(ctx, dv.scratch[scratch_slot].reserve(need, false));
         kp.trace_scratch = dv.scratch[scratch_slot].d;
     }

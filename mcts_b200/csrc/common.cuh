@@ -57,6 +57,9 @@ struct KernelParams {
     uint32_t grab_div;           // grab = remaining / (grab_div * warps)
     uint32_t max_depth; // 0xffffffff = unlimited
     uint32_t seed_lo, seed_hi;
+    // the ten Philox round keys (seed_lo + r * W0, seed_hi + r * W1), computed on the host: the rounds read them as
+    // constant-bank operands of their LOP3s instead of bumping the key with an add per round
+    uint32_t philox_keys[10][2];
     uint32_t leaf_id_base;
     uint32_t eps_thr_m1; // explore iff eps_enable && x1 <= eps_thr_m1
     uint32_t eps_enable;
@@ -73,8 +76,9 @@ struct KernelParams {
     uint64_t mast_planes[2][MAST_KINDS][MAST_BITS];
     uint32_t mast_nbits[2];
     uint16_t mast_rank_small[2][8]; // Connect4: the same dense ranks, one per column, read directly
-    uint16_t *trace_scratch;   // [resident warps][trace_cap][32] u16, MAST-delta staging
+    uint16_t *trace_scratch;   // [resident warps][trace_rows][32] u16, MAST-delta / AMAF staging
     uint32_t trace_cap;
+    uint32_t trace_rows;       // rows of a warp's scratch: trace_cap (LGR / NST: one row per ply), else the per-lane log's ring size (a power of two)
     // Last Good Reply (MR_EPS_LGR): frozen reply table in, last-winning-occurrence stamps out
     const uint16_t *lgr_in;          // [2][NA]: 1 + compact code of the reply to the preceding action id, 0 = none
     unsigned long long *lgr_stamps;  // [2][NA]: ((g + 1) << 26) | ((4096 + ply) << 13) | reply action id, max-merged
@@ -135,6 +139,24 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
         c3 = l0;
         k0 += W0;
         k1 += W1;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+// the same block with the round keys precomputed (KernelParams::philox_keys)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&keys)[10][2],
+                                              uint32_t out[4]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(M0, c0), l0 = M0 * c0;
+        const uint32_t h1 = __umulhi(M1, c2), l1 = M1 * c2;
+        c0 = h1 ^ c1 ^ keys[r][0];
+        c1 = l1;
+        c2 = h0 ^ c3 ^ keys[r][1];
+        c3 = l0;
     }
     out[0] = c0;
     out[1] = c1;

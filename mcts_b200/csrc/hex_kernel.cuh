@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, POLICY == MR_EPS_MAST ? MR_
                 uint32_t n_empty = E; // warp-uniform
                 for (uint32_t base = 0; base < D; base += WINDOW) {
                     uint32_t r[4];
-                    philox4x32_10(leaf_id, pid, IS_MAST ? base >> 1 : base >> 2, IS_MAST ? 1u : 0u, p.seed_lo, p.seed_hi, r);
+                    philox4x32_10(leaf_id, pid, IS_MAST ? base >> 1 : base >> 2, IS_MAST ? 1u : 0u, p.philox_keys, r);
 #pragma unroll
                     for (uint32_t j = 0; j < WINDOW; ++j) {
                         const uint32_t ply = base + j;

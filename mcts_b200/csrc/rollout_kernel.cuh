@@ -31,6 +31,12 @@ __device__ __forceinline__ int end_code_to_outcome(int code) {
 
 constexpr uint32_t STAT_FLUSH_PLIES = 32000; // packed 16-bit fields: flush before any entry can overflow
 
+// A/B switch (the default is the measured winner)
+#ifndef MR_LOG_FLUSH
+#define MR_LOG_FLUSH 1 // per-lane playout log drained in bulk, instead of a flattened flush at every window boundary
+#endif
+constexpr uint32_t LOG_TRAILER = 0x8000u; // log entry: table index (player * NSLOTS + slot) or LOG_TRAILER | (utility of player 0 + 1)
+
 // per-warp packed table -> global (visits, score) table, one atomic per non-zero field
 template <class G>
 __device__ __forceinline__ void flush_stat_table(uint32_t *tab, mr_action_stat *out, uint32_t lane, uint32_t in_slots) {
@@ -65,6 +71,12 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
     constexpr bool PAIR_DRAWS = policy_uses_mast(POLICY) || IS_LGR; // two Philox words per ply
     constexpr bool NEED_SCRATCH = WANT_MAST || (WANT_AMAF && !G::MASK_AMAF) || IS_LGR || IS_NST; // per-lane slot trace
     constexpr int WINDOW = PAIR_DRAWS ? 2 : 4;
+    // MAST delta / AMAF occurrence tables without the reply / bigram side tables: every lane appends its moves (and, when a
+    // playout ends, a trailer with the outcome) to its own ring log in the scratch buffer; the logs are drained when a task
+    // ends or a lane could run out of room -- each lane walks its own log, which holds many playouts by then, so the lanes'
+    // trip counts are balanced and no prefix sum / owner search is needed (the LGR / NST tables need (playout id, ply) per
+    // entry and keep the flattened flush at every window boundary)
+    constexpr bool LOG_FLUSH = MR_LOG_FLUSH && NEED_SCRATCH && !IS_LGR && !IS_NST;
 
     __shared__ __align__(16) mr_leaf s_leaf[WARPS_PER_BLOCK];
     __shared__ typename G::Shared s_game[WARPS_PER_BLOCK];
@@ -78,7 +90,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
     typename G::Shared &sh = s_game[warp];
-    uint16_t *scratch = NEED_SCRATCH ? p.trace_scratch + (size_t)gwarp * p.trace_cap * 32u : nullptr;
+    uint16_t *scratch = NEED_SCRATCH ? p.trace_scratch + (size_t)gwarp * p.trace_rows * 32u : nullptr;
     uint32_t *mast_tab = s_mast[warp];
     uint32_t *amaf_tab = s_amaf[warp];
     unsigned long long *lgr_tab = s_lgr;
@@ -97,6 +109,10 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
 
     unsigned long long grab_lo = 0, grab_hi = 0; // the warp's current grab, relative to g_begin
     const unsigned long long work_total = p.g_end - p.g_begin;
+    // per-lane playout log (LOG_FLUSH): a ring of p.trace_rows entries per lane, lane-interleaved in the warp's scratch
+    uint32_t log_pos = 0, log_tail = 0; // entries [log_tail, log_pos) are not yet in the shared tables
+    const uint32_t log_mask = p.trace_rows - 1u;
+    const bool log_on = LOG_FLUSH && p.trace_rows != 0; // (the parity variant is compiled with every output and run with any subset)
     for (;;) {
         // ---- next task: the part of the current grab that lies inside one leaf ----
         if (grab_lo >= grab_hi) {
@@ -185,7 +201,7 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
         } else {
             G st;
             uint32_t pid = pid_begin + lane;
-            uint32_t next_pid = pid_begin + 32;
+            uint32_t next_pid = min(pid_begin + 32u, pid_end);
             bool idle = pid >= pid_end;
             bool alive = !idle;
             uint32_t depth = 0, win = 0;
@@ -198,9 +214,63 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
             // mover's colour, MAST table index, rank-bit loop and plane addresses derived from it) in uniform registers
             st.turn_u = __reduce_or_sync(FULL_MASK, leaf_turn & 1u);
 
+            // Drain the lanes' logs into the per-warp shared tables: every (action, player) occurrence adds visits += 1,
+            // score += utilities[player] (backprop.rs:619-640 GRAVE/AMAF, :857-870 GLOBAL/MAST).  A lane walks its own log
+            // BACKWARDS, so the trailer of a playout (its outcome) is met before its moves; the moves of a playout that is
+            // still running (the last min(depth, trace_cap) entries of a live lane) stay in the ring.
+            auto drain_logs = [&]() {
+                const uint32_t keep = alive ? min(depth, p.trace_cap) : 0u;
+                const uint32_t n = log_pos - log_tail - keep;
+                const uint32_t nmax = __reduce_max_sync(FULL_MASK, n);
+                const uint32_t top = log_pos - keep; // one past the newest entry to drain
+                const uint32_t off_mask = p.trace_rows * 32u - 1u;
+                uint32_t off = (((top - 1u) & log_mask) << 5) | lane; // element offset of the entry under the cursor
+                uint32_t inc0 = 1u, inc1 = 1u; // the packed (visits +1, score +-1) increments of the playout under the cursor
+                for (uint32_t base = 0; base < nmax; base += 256u) {
+                    const uint32_t lim = min(nmax, base + 256u);
+                    // (the packed 16-bit fields must not overflow: an entry receives at most 32 * 256 additions per chunk)
+                    if (WANT_MAST && p.mast_delta) {
+                        if (mast_plies + 32u * 256u > STAT_FLUSH_PLIES) {
+                            flush_stat_table<G>(mast_tab, p.mast_delta, lane, p.tables_in_slots);
+                            mast_plies = 0;
+                        }
+                        mast_plies += 32u * (lim - base);
+                    }
+                    if (WANT_AMAF && !G::MASK_AMAF && p.amaf) {
+                        if (amaf_plies + 32u * 256u > STAT_FLUSH_PLIES) {
+                            flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * p.amaf_stride, lane, p.tables_in_slots);
+                            amaf_plies = 0;
+                        }
+                        amaf_plies += 32u * (lim - base);
+                    }
+#pragma unroll 4
+                    for (uint32_t i = base; i < lim; ++i) {
+                        if (i < n) {
+                            const uint32_t e = scratch[off];
+                            off = (off - 32u) & off_mask;
+                            if (e & LOG_TRAILER) {
+                                const uint32_t u = (e & 3u) - 1u; // utility of player 0 (two's complement)
+                                inc0 = 1u + (u << 16);
+                                inc1 = 1u - (u << 16);
+                            } else {
+                                const uint32_t inc = e >= (uint32_t)G::NSLOTS ? inc1 : inc0;
+                                if (WANT_MAST && p.mast_delta) atomicAdd(&mast_tab[e], inc);
+                                if (WANT_AMAF && !G::MASK_AMAF && p.amaf) atomicAdd(&amaf_tab[e], inc);
+                            }
+                        }
+                    }
+                }
+                if (alive) {
+                    log_tail = top;
+                } else { // nothing of this lane is left in the ring: start over at row 0 (small, L2-resident footprint)
+                    log_pos = 0;
+                    log_tail = 0;
+                }
+            };
+
             for (;;) {
                 uint32_t r[4];
-                philox4x32_10(leaf_id, pid, win, PAIR_DRAWS ? 1u : 0u, p.seed_lo, p.seed_hi, r);
+                philox4x32_10(leaf_id, pid, win, PAIR_DRAWS ? 1u : 0u, p.philox_keys, r);
                 // the depth cutoff can only fire in a window that reaches max_depth: one test per window, not per ply
                 const bool near_cutoff = depth + (uint32_t)WINDOW > p.max_depth || p.max_depth < (uint32_t)WINDOW;
                 // one ply.  PAR is the ply's parity inside the window: a compile-time 0/1 when the window is
@@ -251,7 +321,13 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                                     if (depth < p.max_trace)
                                         p.trace[((size_t)li * p.k + pid) * p.max_trace + depth] = (uint16_t)action;
                                 }
-                                if (NEED_SCRATCH) {
+                                if constexpr (LOG_FLUSH) {
+                                    if (depth < p.trace_cap) {
+                                        const uint32_t pl = (st.turn_u ^ (par == 2 ? st.rt_parity : (uint32_t)par)) & 1u;
+                                        scratch[(log_pos & log_mask) * 32u + lane] = (uint16_t)(pl * (uint32_t)G::NSLOTS + slot);
+                                        ++log_pos;
+                                    }
+                                } else if (NEED_SCRATCH) {
                                     if (depth < p.trace_cap) scratch[depth * 32u + lane] = (uint16_t)slot;
                                 }
                                 ++depth;
@@ -317,8 +393,13 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                             p.rec[g] = rr;
                         }
                         if (WANT_FINAL && p.final_state) st.store_final(sh, &p.final_state[g], depth, e);
+                        if (log_on) { // the playout's trailer: utility of player 0, biased by one
+                            const uint32_t code = e == ST_WIN_P0 ? 2u : (e == ST_WIN_P1 ? 0u : 1u);
+                            scratch[(log_pos & log_mask) * 32u + lane] = (uint16_t)(LOG_TRAILER | code);
+                            ++log_pos;
+                        }
                     }
-                    if (NEED_SCRATCH) {
+                    if (NEED_SCRATCH && !LOG_FLUSH) {
                         // Statistics from the finished playouts' traces, FLATTENED over the warp: entry q of the
                         // concatenated traces belongs to the finished lane f with excl[f] <= q < incl[f].
                         // Every (action, player) occurrence: visits += 1, score += utilities[player]
@@ -429,10 +510,16 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                         }
                     }
                     const uint32_t rank = __popc(fin_mask & lanemask_lt());
+                    const uint32_t nfin = __popc(fin_mask);
+                    const uint32_t avail = pid_end - next_pid; // ids left in the task (next_pid <= pid_end)
+                    const bool got = fin && rank < avail;
+                    if (log_on) {
+                        // a lane starts a playout only with room for all of it (trace_cap moves and the trailer)
+                        if (__any_sync(FULL_MASK, got && log_pos - log_tail + p.trace_cap + 1u > p.trace_rows)) drain_logs();
+                    }
                     if (fin) {
-                        const uint32_t np = next_pid + rank;
-                        if (np < pid_end) {
-                            pid = np;
+                        if (got) {
+                            pid = next_pid + rank;
                             st.reset(sh);
                             alive = true;
                             depth = 0;
@@ -445,10 +532,11 @@ __global__ void __launch_bounds__(THREADS_PER_BLOCK, G::min_blocks(POLICY)) roll
                             idle = true;
                         }
                     }
-                    next_pid += __popc(fin_mask);
+                    next_pid += min(nfin, avail);
                     if (__all_sync(FULL_MASK, idle)) break;
                 }
             }
+            if (log_on) drain_logs(); // every lane is idle: the logs are emptied and restart at row 0
             // the AMAF table is per leaf: it leaves shared memory with the task
             if (WANT_AMAF && p.amaf) {
                 flush_stat_table<G>(amaf_tab, p.amaf + (size_t)li * p.amaf_stride, lane, p.tables_in_slots);
