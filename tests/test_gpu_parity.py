@@ -564,6 +564,31 @@ def test_full_size_properties(game):
         assert ref["results"][0].tobytes() == res[i].tobytes(), (o.GAME_NAMES[game], i)
 
 
+@pytest.mark.parametrize("game", [o.BREAKTHROUGH, o.KNIGHTTHROUGH, o.CONNECT4, o.OTHELLO, o.HEX11])
+@pytest.mark.parametrize("eps", [0.1, 0.0])
+def test_production_variants_match_the_oracle(game, eps):
+    """The kernel variants a search actually launches (MAST delta only, MAST delta + AMAF: no trace, no final state)
+    against the oracle's tables: every other parity test runs the traced variant, which is a different instantiation.
+    Tables and results must come out bit for bit the same, for table densities from "all ties" to "fully visited", a warm
+    table (scores of exactly 1 on the winning moves) and enough playouts per lane for the per-lane logs to be drained
+    more than once."""
+    leaves = _leaves(game, n_per=3)
+    warm = o.playout_batch(game, leaves, 64, seed=5, max_depth=200, want_mast_delta=True, threads=o.host_threads())["mast_delta"]
+    tables = [_random_mast(game, 7, 0.0), _random_mast(game, 8, 0.5), _random_mast(game, 9, 1.0), warm]
+    for t, mast in enumerate(tables):
+        k = 2400 if t == 3 else 160
+        for amaf in (False, True):
+            ref = o.playout_batch(game, leaves, k, policy=o.EPS_MAST, eps=eps, max_depth=200, seed=77 + t, mast=mast,
+                                  want_amaf=amaf, want_mast_delta=True, threads=o.host_threads())
+            with mb.GpuRollout(mb.Game(game), mb.EpsilonGreedyMast(eps), seed=77 + t, max_playout_depth=200) as g:
+                got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, stats=mast, want_amaf=amaf, want_mast_delta=True)
+            name = (o.GAME_NAMES[game], t, amaf)
+            assert got.results.tobytes() == ref["results"].tobytes(), name
+            assert got.mast_delta.tobytes() == ref["mast_delta"].tobytes(), name
+            if amaf:
+                assert got.amaf.tobytes() == ref["amaf"].tobytes(), name
+
+
 def test_headline_workload_at_full_size():
     """BASELINE.json configs[1] at its bench size (4096 leaves x 4096 playouts, epsilon-MAST, depth 200): conservation
     properties over the whole batch, the MAST delta's checksum, and bit-exact replay of sampled leaves by the oracle."""
