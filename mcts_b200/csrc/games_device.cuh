@@ -14,6 +14,8 @@
 //   store_final(sh, out, parity_after)  debug: lane state -> reference-layout mr_leaf
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mr {
@@ -416,6 +418,41 @@ struct Breakthrough : ThroughBase {
         return pos + (in_hi ? 32u : 0u);
     }
 
+    // random_best over FEW maximal actions (util.rs:147-161): the pick is the maximal action with the smallest visiting
+    // rank.  One 32-bit half of the board at a time (HI = sources 32..63; `before` = the legal actions of the sources in
+    // front of this half): the tied actions are as a rule the winning moves of ONE piece, all with score exactly 1
+    // (measured with an instrumented oracle: every one of the 12.5 % of plies with a small tie on the headline workload),
+    // so one half has the candidates and a 64-bit walk would do twice the work.  Cell by cell: the prefix count of the
+    // cell gives the visiting rank of its first kind, every further legal kind is one list position on, i.e. + inv
+    // (mod n) in visiting rank.  Returns the minimum of `best` and the packed keys (rank << 8 | source << 2 | kind).
+    template <bool HI>
+    __device__ static uint32_t half_tie(uint32_t best, const uint64_t cand[3], uint64_t W, uint64_t F, uint64_t S, uint64_t C,
+                                        uint32_t before, uint32_t n, uint32_t i0, uint32_t inv, uint32_t rcp) {
+        const uint32_t c0 = HI ? hi32(cand[0]) : lo32(cand[0]), c1 = HI ? hi32(cand[1]) : lo32(cand[1]);
+        const uint32_t c2 = HI ? hi32(cand[2]) : lo32(cand[2]);
+        const uint32_t w = HI ? hi32(W) : lo32(W), f = HI ? hi32(F) : lo32(F);
+        const uint32_t sw = HI ? hi32(S) : lo32(S), cw = HI ? hi32(C) : lo32(C);
+        for (uint32_t cells = c0 | c1 | c2; cells; cells &= cells - 1u) {
+            const uint32_t b = (uint32_t)__ffs((int)cells) - 1u;
+            const uint32_t below = (1u << b) - 1u;
+            const uint32_t i = before + (uint32_t)(__popc(sw & below) + 2 * __popc(cw & below));
+            const uint32_t key = ((HI ? 32u : 0u) + b) << 2;
+            uint32_t j = visiting_rank(i, i0, n, inv, rcp);
+            if ((c0 >> b) & 1u) best = min(best, (j << 8) | key);
+            if ((w >> b) & 1u) {
+                j += inv;
+                j = min(j, j - n); // j - n wraps to a huge value while j < n
+            }
+            if ((c1 >> b) & 1u) best = min(best, (j << 8) | key | 1u);
+            if ((f >> b) & 1u) {
+                j += inv;
+                j = min(j, j - n);
+            }
+            if ((c2 >> b) & 1u) best = min(best, (j << 8) | key | 2u);
+        }
+        return best;
+    }
+
     template <int POLICY, int PARITY>
     __device__ int step(const Shared &sh, uint32_t x0, uint32_t x1, const KernelParams &p, uint32_t &action, uint32_t &slot);
 };
@@ -601,28 +638,13 @@ __device__ int Breakthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, co
                 idx = i0;
                 idx_set = true;
             } else if (m <= 6) {
-                // few maximal actions: the pick is the one with the smallest visiting rank
+                // few maximal actions: the one with the smallest visiting rank (half_tie)
                 const uint32_t pk = r & 15u;
                 const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
-                // cell by cell (the tied actions are mostly the winning moves of ONE piece): the prefix count of the
-                // cell gives the visiting rank of its first kind, every further legal kind is one list position on, i.e.
-                // + inv (mod n) in visiting rank.  The minimum is taken over packed keys (rank << 8 | cell << 2 | kind).
+                const uint64_t cells = cand[0] | cand[1] | cand[2];
                 uint32_t best = 0xffffffffu;
-                const uint64_t legal_k[3] = {W, F, E};
-                for (uint64_t cells = cand[0] | cand[1] | cand[2]; cells; cells &= cells - 1) {
-                    const uint32_t s = (uint32_t)__ffsll((long long)cells) - 1u;
-                    const uint64_t bit = 1ull << s, below = bit - 1ull;
-                    const uint32_t i = __popcll(S & below) + 2u * __popcll(C & below);
-                    uint32_t j = visiting_rank(i, i0, n, inv, rcp);
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        if (cand[q] & bit) best = min(best, (j << 8) | (s << 2) | (uint32_t)q);
-                        if (legal_k[q] & bit) {
-                            j += inv;
-                            j = min(j, j - n); // j - n wraps to a huge value while j < n
-                        }
-                    }
-                }
+                if (lo32(cells)) best = half_tie<false>(best, cand, W, F, S, C, 0u, n, i0, inv, rcp);
+                if (hi32(cells)) best = half_tie<true>(best, cand, W, F, S, C, __popc(lo32(S)) + 2u * __popc(lo32(C)), n, i0, inv, rcp);
                 src = (best >> 2) & 63u;
                 dir = best & 3u;
                 have = true;
@@ -675,11 +697,6 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
     const uint32_t n = __popcll(B0) + 2u * __popcll(B1) + 4u * __popcll(B2) + 8u * __popcll(B3);
     if (n == 0) return ST_NO_ACTIONS;
 
-    // number of legal moves of cells strictly below `s`
-    auto count_below = [&](uint32_t s) -> uint32_t {
-        const uint64_t below = (1ull << s) - 1ull;
-        return __popcll(B0 & below) + 2u * __popcll(B1 & below) + 4u * __popcll(B2 & below) + 8u * __popcll(B3 & below);
-    };
     auto select_move = [&](uint32_t idx, uint32_t &kind) -> uint32_t {
         const uint32_t cl = __popc(lo32(B0)) + 2u * __popc(lo32(B1)) + 4u * __popc(lo32(B2)) + 8u * __popc(lo32(B3));
         const bool in_hi = idx >= cl;
@@ -813,22 +830,34 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
             } else if (m <= 6) {
                 const uint32_t pk = r & 15u;
                 const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
-                // as for Breakthrough: rank of the cell's first kind, + inv (mod n) per further legal kind, minimum over
-                // packed keys (rank << 9 | cell << 3 | kind)
+                // as for Breakthrough (half_tie): one 32-bit half of the board at a time -- the tied actions are as a
+                // rule the winning jumps of one knight -- rank of the cell's first kind, + inv (mod n) per further legal
+                // kind, minimum over packed keys (rank << 9 | cell << 3 | kind)
                 uint32_t best = 0xffffffffu;
-                for (uint64_t cells = any; cells; cells &= cells - 1) {
-                    const uint32_t s = (uint32_t)__ffsll((long long)cells) - 1u;
-                    const uint64_t bit = 1ull << s;
-                    uint32_t j = visiting_rank(count_below(s), i0, n, inv, rcp);
+                auto half = [&](auto HI_T, uint32_t before) {
+                    constexpr bool HI = decltype(HI_T)::value;
+                    const uint32_t b0 = HI ? hi32(B0) : lo32(B0), b1 = HI ? hi32(B1) : lo32(B1);
+                    const uint32_t b2 = HI ? hi32(B2) : lo32(B2), b3 = HI ? hi32(B3) : lo32(B3);
+                    for (uint32_t cells = HI ? hi32(any) : lo32(any); cells; cells &= cells - 1u) {
+                        const uint32_t b = (uint32_t)__ffs((int)cells) - 1u;
+                        const uint32_t below = (1u << b) - 1u;
+                        const uint32_t i = before + (uint32_t)(__popc(b0 & below) + 2 * __popc(b1 & below) + 4 * __popc(b2 & below) +
+                                                               8 * __popc(b3 & below));
+                        const uint32_t key = ((HI ? 32u : 0u) + b) << 3;
+                        uint32_t j = visiting_rank(i, i0, n, inv, rcp);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (cand[q] & bit) best = min(best, (j << 9) | (s << 3) | (uint32_t)q);
-                        if (M[q] & bit) {
-                            j += inv;
-                            j = min(j, j - n);
+                        for (int q = 0; q < 8; ++q) {
+                            if (((HI ? hi32(cand[q]) : lo32(cand[q])) >> b) & 1u) best = min(best, (j << 9) | key | (uint32_t)q);
+                            if (q < 7 && (((HI ? hi32(M[q]) : lo32(M[q])) >> b) & 1u)) {
+                                j += inv;
+                                j = min(j, j - n); // j - n wraps to a huge value while j < n
+                            }
                         }
                     }
-                }
+                };
+                if (lo32(any)) half(std::false_type{}, 0u);
+                if (hi32(any))
+                    half(std::true_type{}, __popc(lo32(B0)) + 2u * __popc(lo32(B1)) + 4u * __popc(lo32(B2)) + 8u * __popc(lo32(B3)));
                 src = (best >> 3) & 63u;
                 kind = best & 7u;
                 have = true;
