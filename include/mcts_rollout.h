@@ -349,11 +349,19 @@ enum mr_rave_schedule { MR_RAVE_HAND_SELECTED = 0, MR_RAVE_THRESHOLD = 1, MR_RAV
 enum mr_qinit { MR_QINIT_PARENT = 0, MR_QINIT_INFINITY = 1 };     /* node.rs:95-159 */
 /* MR_SEARCH_TRANSPOSITIONS: SearchConfig.use_transpositions -- a new child whose state is already in the
  * table reuses that node (search/shared.rs:412-436, table.rs); statistics stay on the edges.  The table is
- * keyed by the full 40-byte state record (exact, no Zobrist collisions); symmetry canonicalisation is not
- * applied. */
+ * keyed by the full 40-byte state record (exact, no Zobrist collisions); without MR_SEARCH_SYMMETRY no symmetry
+ * canonicalisation is applied. */
 /* MR_SEARCH_PIPELINED: two batches in flight (= pipeline_depth 2) -- batch N+1 is gathered (with batch N's virtual
  * losses still in place) and submitted before batch N's results are applied. */
-enum mr_search_flags { MR_SEARCH_TRANSPOSITIONS = 1, MR_SEARCH_PIPELINED = 2 };
+/* MR_SEARCH_SYMMETRY (implies MR_SEARCH_TRANSPOSITIONS; Othello, ignored for the other games): the table is keyed as the
+ * reference keys it -- by the position's canonical D4 orientation while at most SYMMETRY_PLY_LIMIT = 20 discs are on the
+ * board (games/othello/src/lib.rs:26, 436-443, 474-480), by the position itself later.  Every node but the root holds its
+ * action list in the canonical orientation (search/shared.rs:233-252); a descent carries the real state, translates each
+ * chosen action back through that state's symmetry (mcts/src/symmetry.rs:38-50, othello/lib.rs:658-665) and verifies a
+ * cached child against the real successor (shared.rs:382-405).  Playouts start from the real state.  Only with
+ * selection strategies and rollout policies that keep no action-keyed tables (UCB1 / UCB1-Tuned; uniform / decisive):
+ * MR_ERR_UNSUPPORTED otherwise. */
+enum mr_search_flags { MR_SEARCH_TRANSPOSITIONS = 1, MR_SEARCH_PIPELINED = 2, MR_SEARCH_SYMMETRY = 4 };
 
 typedef struct {
     uint32_t game;              /* mr_game */
@@ -407,6 +415,11 @@ typedef struct {
 int mr_generate_actions(int game, const mr_leaf *state, uint16_t *out /* [MR_MAX_ROOT_CHILDREN] */);
 int mr_apply(int game, mr_leaf *state, uint16_t action);
 int mr_terminal_status(int game, const mr_leaf *state); /* mr_outcome */
+/* Game::canonical_representation (game.rs; games/othello/src/lib.rs:618-646): writes the state in its canonical
+ * orientation and returns the index (0..7, game-core symmetry.rs:113-127 order) of the symmetry that maps the state onto
+ * it -- what MR_SEARCH_SYMMETRY keys the transposition table by.  Othello up to 20 discs; the identity (0, a plain
+ * copy) for everything else.  Negative on bad arguments. */
+int mr_canonical_representation(int game, const mr_leaf *state, mr_leaf *canonical_out);
 
 #define MR_MAX_ROOT_CHILDREN 256
 /* Runs one search from `root`; writes the chosen action (RobustChild: most visits, then expected score,

@@ -26,6 +26,7 @@ from .rollout import (
     apply,
     generate_actions,
     terminal_status,
+    canonical_representation,
     initial_state,
     make_leaf,
     num_actions,
@@ -35,5 +36,5 @@ __all__ = [
     "BatchResult", "DecisiveMove", "DecisiveMoveMast", "DecisiveMoveWin", "EndType", "EpsilonGreedyLgr", "EpsilonGreedyLgr2", "EpsilonGreedyLgr2Mast", "EpsilonGreedyMast", "EpsilonGreedyNst", "Game", "GpuRollout", "MastTable", "Outcome",
     "Policy", "Trial", "Uniform", "initial_state", "make_leaf", "num_actions", "LEAF_DTYPE", "RECORD_DTYPE",
     "RESULT_DTYPE", "STAT_DTYPE", "EXPORTS", "RolloutError", "load", "GpuSearch", "SearchResult", "choose_action_root_parallel", "apply",
-    "generate_actions", "terminal_status",
+    "generate_actions", "terminal_status", "canonical_representation",
 ]

@@ -134,6 +134,7 @@ EXPORTS = [
     "mr_generate_actions",
     "mr_apply",
     "mr_terminal_status",
+    "mr_canonical_representation",
 ]
 
 _lib = None
@@ -185,6 +186,7 @@ def load() -> C.CDLL:
     L.mr_generate_actions.argtypes = [i32, vp, vp]
     L.mr_apply.argtypes = [i32, vp, C.c_uint16]
     L.mr_terminal_status.argtypes = [i32, vp]
+    L.mr_canonical_representation.argtypes = [i32, vp, vp]
     L.mr_search.argtypes = [vp, C.POINTER(SearchDesc), vp, C.POINTER(C.c_uint16), vp, C.POINTER(u32), C.POINTER(SearchStats)]
     L.mr_set_kernel_timing.argtypes = [vp, i32]
     L.mr_search_root_parallel.argtypes = [C.POINTER(vp), i32, C.POINTER(SearchDesc), vp, C.POINTER(C.c_uint16), vp, C.POINTER(u32), C.POINTER(SearchStats)]

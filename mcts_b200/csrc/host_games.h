@@ -274,4 +274,68 @@ inline int action_slot(int game, int player, uint16_t a) {
     return a;
 }
 
+// ---- D4 symmetry of the 8x8 board (games/game-core/src/symmetry.rs:88-147, :357-374), word-parallel ----
+// Image k of a bitboard in the reference's order: identity, flip_cols, flip_rows, transpose, flip_rows o flip_cols,
+// transpose o flip_cols, transpose o flip_rows, transpose o flip_rows o flip_cols (a set square i moves to
+// index_symmetries(i)[k]; square = row * 8 + col).
+inline uint64_t flip_cols8(uint64_t x) { // col -> 7 - col: reverse the bits of every byte
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    return ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+}
+inline uint64_t flip_rows8(uint64_t x) { return __builtin_bswap64(x); } // row -> 7 - row: reverse the bytes
+inline uint64_t transpose8(uint64_t x) { // (row, col) -> (col, row): three delta swaps across the main diagonal
+    uint64_t t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;
+    x ^= t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull;
+    x ^= t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
+    return x ^ t ^ (t << 28);
+}
+inline uint64_t board_symmetry8(uint64_t x, int k) {
+    switch (k) {
+    case 0: return x;
+    case 1: return flip_cols8(x);
+    case 2: return flip_rows8(x);
+    case 3: return transpose8(x);
+    case 4: return flip_rows8(flip_cols8(x));
+    case 5: return transpose8(flip_cols8(x));
+    case 6: return transpose8(flip_rows8(x));
+    default: return transpose8(flip_rows8(flip_cols8(x)));
+    }
+}
+// the square whose image under symmetry k is `i` (symmetry.rs:134-147 invert_symmetry)
+inline int invert_symmetry8(int i, int k) {
+    auto fc = [](int v) { return (v & 56) | (7 - (v & 7)); };
+    auto fr = [](int v) { return (56 - (v & 56)) | (v & 7); };
+    auto tr = [](int v) { return ((v & 7) << 3) | (v >> 3); };
+    switch (k) {
+    case 0: return i;
+    case 1: return fc(i);
+    case 2: return fr(i);
+    case 3: return tr(i);
+    case 4: return fc(fr(i));
+    case 5: return fc(tr(i));
+    case 6: return fr(tr(i));
+    default: return fc(fr(tr(i)));
+    }
+}
+// Othello's canonical orientation (othello/lib.rs:26, 436-443, 618-646): up to SYMMETRY_PLY_LIMIT = 20 discs, the first
+// symmetry whose image of (black, white) is lexicographically minimal; past it the identity.  `canon` receives the
+// state in that orientation (turn and pass flag are not geometric).
+inline int othello_canonical(const mr_leaf &s, mr_leaf &canon) {
+    canon = s;
+    if (__builtin_popcountll(s.board[0] | s.board[1]) > 20) return 0;
+    int best = 0;
+    for (int k = 1; k < 8; ++k) {
+        const uint64_t b = board_symmetry8(s.board[0], k), w = board_symmetry8(s.board[1], k);
+        if (b < canon.board[0] || (b == canon.board[0] && w < canon.board[1])) {
+            best = k;
+            canon.board[0] = b;
+            canon.board[1] = w;
+        }
+    }
+    return best;
+}
+
 } // namespace mr_host

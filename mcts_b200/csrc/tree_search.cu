@@ -190,6 +190,7 @@ inline StateKey key_of(const mr_leaf &s) {
 struct Tree {
     int game;
     bool use_table = false;
+    bool symmetry = false; // MR_SEARCH_SYMMETRY: the table is keyed by Othello's canonical orientation (see Search::select)
     bool want_amaf_rows = false;
     std::unordered_map<StateKey, uint32_t, StateKeyHash> table; // use_transpositions: state -> node
     std::vector<Node> nodes;
@@ -400,14 +401,20 @@ struct Search {
         return best_i;
     }
 
-    // search/shared.rs:569-736, with the in-flight trials counted by the expansion test (file header)
-    void select(uint32_t descent, std::vector<PathEntry> &path) {
+    // search/shared.rs:569-736, with the in-flight trials counted by the expansion test (file header).  `leaf` receives
+    // the state the playouts start from.  With MR_SEARCH_SYMMETRY the descent carries the REAL state: every node but the
+    // root holds its state, and so its action list, in the canonical orientation (shared.rs:233-252), and a chosen action is
+    // translated back through the symmetry of the real state at that node (symmetry.rs:38-50 incoming_sym, othello/lib.rs:
+    // 658-665 invert_action) -- recomputed on every visit, because a shared node is reached in different orientations.
+    void select(uint32_t descent, std::vector<PathEntry> &path, mr_leaf &leaf) {
         path.clear();
         lctx.clear();
         uint32_t cur = 0, incoming = 0;
+        mr_leaf real = t.nodes[0].state;
         for (;;) {
             path.push_back({cur, incoming});
             lctx.emplace_back();
+            leaf = t.symmetry ? real : t.nodes[cur].state; // (for every return below)
             const Stats &cs = current_stats(path);
             // trials in flight through this node from OTHER descents: every gathered descent holds k virtual losses on
             // each of its edges (root_inflight for the root); this one has added 1 to the edge it just came down
@@ -424,12 +431,35 @@ struct Search {
             const uint32_t ei = t.nodes[cur].first + best;
             const uint32_t total_before = t.edge[ei].visits + t.edge[ei].vloss;
             t.edge[ei].vloss += 1; // one virtual loss per traversed edge
+            mr_leaf key; // MR_SEARCH_SYMMETRY: what the child node is keyed by
+            if (t.symmetry) {
+                uint16_t a = t.action[ei];
+                if (cur != 0 && a < 64) { // the root's list is literal; PASS maps to itself
+                    mr_leaf unused;
+                    a = (uint16_t)mr_host::invert_symmetry8((int)a, mr_host::othello_canonical(real, unused));
+                }
+                mr_host::apply(t.game, real, a);
+                mr_host::othello_canonical(real, key);
+            }
             if (t.child[ei] >= 0) {
                 edge_changed(path, path.size() - 1, ei, total_before);
                 cur = (uint32_t)t.child[ei];
+                // shared.rs:382-405 verified_child_id: the cached slot belongs to the orientation that created it; past
+                // the disc limit another orientation's child is a different node, found (or made) through the table
+                if (t.symmetry && !(key_of(t.nodes[cur].state) == key_of(key))) {
+                    auto it = t.table.find(key_of(key));
+                    if (it != t.table.end()) {
+                        cur = it->second;
+                    } else {
+                        cur = t.add_node(key);
+                        t.table.emplace(key_of(key), cur);
+                        if (node_epoch.size() < t.nodes.size()) node_epoch.resize(t.nodes.size(), 0u);
+                    }
+                }
             } else {
                 mr_leaf s = t.nodes[cur].state;
-                mr_host::apply(t.game, s, t.action[ei]);
+                if (t.symmetry) s = key;
+                else mr_host::apply(t.game, s, t.action[ei]);
                 uint32_t id;
                 if (t.use_table) { // resolve_child_id: reuse the node of an identical state (shared.rs:412-436)
                     auto it = t.table.find(key_of(s));
@@ -449,6 +479,7 @@ struct Search {
                 if (d->expand_threshold > 0) {
                     path.push_back({cur, incoming});
                     lctx.emplace_back();
+                    leaf = t.symmetry ? real : t.nodes[cur].state;
                     return;
                 }
             }
@@ -668,7 +699,8 @@ int run_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, Roo
     std::vector<mr_reply_update> reply_upd(lgr ? (size_t)2 * s.na : 0);
     std::vector<uint32_t> last_win(lgr ? (size_t)2 * desc->batch_leaves : 0);
     s.t.nodes.reserve(std::min<size_t>((size_t)desc->max_iterations + 16, (size_t)1 << 22)); // at most one new node per descent
-    s.t.use_table = (desc->flags & MR_SEARCH_TRANSPOSITIONS) != 0;
+    s.t.use_table = (desc->flags & (MR_SEARCH_TRANSPOSITIONS | MR_SEARCH_SYMMETRY)) != 0;
+    s.t.symmetry = (desc->flags & MR_SEARCH_SYMMETRY) != 0 && desc->game == MR_OTHELLO;
     s.t.want_amaf_rows = desc->select == MR_SELECT_AMAF;
     s.t.add_node(*root);
     if (s.t.use_table) s.t.table.emplace(key_of(*root), 0u);
@@ -715,9 +747,8 @@ int run_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, Roo
         bb.nb = nb;
         const double t0 = now_s();
         for (uint32_t b = 0; b < nb; ++b) {
-            s.select(first + b, bb.paths[b]);
+            s.select(first + b, bb.paths[b], bb.leaves[b]);
             s.add_path_virtual_loss(bb.paths[b], k);
-            bb.leaves[b] = s.t.nodes[bb.paths[b].back().node].state;
             if ((lgr || nst) && bb.paths[b].size() > 1) { // playout()'s prev_action: the last edge of the descent (shared.rs:763-778)
                 const std::vector<PathEntry> &path = bb.paths[b];
                 const Node &parent = s.t.nodes[path[path.size() - 2].node];
@@ -886,6 +917,13 @@ int check_desc(const mr_search_desc *desc) {
     if (desc->select > MR_SELECT_AMAF) return MR_ERR_INVALID;
     if (desc->rave_schedule > MR_RAVE_MIN_MSE) return MR_ERR_INVALID;
     if (desc->pipeline_depth > MR_NUM_SLOTS) return MR_ERR_INVALID;
+    if ((desc->flags & MR_SEARCH_SYMMETRY) && desc->game == MR_OTHELLO) {
+        // canonical nodes hold canonical actions: the action-keyed tables (MAST, replies, n-grams, AMAF / GRAVE) are
+        // written in the real orientation by the kernels and would need a per-path translation that is not built
+        const bool plain_policy = desc->policy == MR_UNIFORM || desc->policy == MR_DECISIVE_WIN || desc->policy == MR_DECISIVE_WINLOSS ||
+                                  desc->policy == MR_DECISIVE_WINLOSSDRAW || desc->policy == MR_DECISIVE_ANTI;
+        if (!plain_policy || desc->select > MR_SELECT_UCB1_TUNED) return MR_ERR_UNSUPPORTED;
+    }
     return MR_OK;
 }
 
@@ -915,6 +953,13 @@ extern "C" int mr_apply(int game, mr_leaf *state, uint16_t action) {
 extern "C" int mr_terminal_status(int game, const mr_leaf *state) {
     if (game < 0 || game >= MR_NUM_GAMES || !state) return -1;
     return mr_host::terminal_status(game, *state);
+}
+
+extern "C" int mr_canonical_representation(int game, const mr_leaf *state, mr_leaf *canonical_out) {
+    if (game < 0 || game >= MR_NUM_GAMES || !state || !canonical_out) return -1;
+    if (game == MR_OTHELLO) return mr_host::othello_canonical(*state, *canonical_out);
+    *canonical_out = *state;
+    return 0;
 }
 
 extern "C" int mr_search(mr_ctx *ctx, const mr_search_desc *desc, const mr_leaf *root, uint16_t *best_action,

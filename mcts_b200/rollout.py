@@ -111,6 +111,17 @@ def terminal_status(game: Game, state: np.ndarray) -> Outcome:
     return Outcome(_lib.load().mr_terminal_status(int(game), ptr(st)))
 
 
+def canonical_representation(game: Game, state: np.ndarray):
+    """Game::canonical_representation on a leaf record: (state in its canonical orientation, symmetry index 0..7).  Othello up
+    to 20 discs (games/othello/src/lib.rs:618-646); the identity for everything else."""
+    st = np.ascontiguousarray(state, dtype=LEAF_DTYPE)
+    out = st.copy()
+    sym = _lib.load().mr_canonical_representation(int(game), ptr(st), ptr(out))
+    if sym < 0:
+        raise ValueError("mr_canonical_representation: bad arguments")
+    return out, sym
+
+
 def num_actions(game: Game) -> int:
     return _lib.load().mr_num_actions(int(game))
 

@@ -42,18 +42,19 @@ class GpuSearch:
 
     def __init__(self, game: Game, strategy=None, *, max_iterations=10_000, batch_leaves=256, num_rollouts_per_leaf=1,
                  expand_threshold=1, max_playout_depth=0, exploration_constant=math.sqrt(2.0), select=SELECT_UCB1,
-                 q_init=QINIT_PARENT, use_transpositions=False, pipelined=False, pipeline_depth=0, grave_threshold=700,
+                 q_init=QINIT_PARENT, use_transpositions=False, canonical_symmetry=False, pipelined=False, pipeline_depth=0, grave_threshold=700,
                  rave_schedule=RAVE_HAND_SELECTED, rave_param=1000, rave_bias=0.0, amaf_alpha=1.0, seed=0, devices=1, num_threads=1):
         """`pipeline_depth` batches in flight (`pipelined=True` = 2).  `num_threads` > 1 = the reference's root-parallel
         search (SearchConfig.num_threads, search/parallel.rs:56-115): that many independent searchers of
         `max_iterations` iterations each, one host thread and one rollout context per searcher on the same device(s),
-        root-child totals merged."""
+        root-child totals merged.  `canonical_symmetry` (implies `use_transpositions`): the table is keyed by Othello's
+        canonical D4 orientation up to 20 discs, as the reference keys it (MR_SEARCH_SYMMETRY)."""
         self.rollout = GpuRollout(game, strategy or Uniform(), devices=devices, seed=seed, max_playout_depth=max_playout_depth)
         self.extra_rollouts = [GpuRollout(game, strategy or Uniform(), devices=devices, seed=seed, max_playout_depth=max_playout_depth)
                                for _ in range(max(1, int(num_threads)) - 1)]
         self.desc = SearchDesc(
             int(game), int(self.rollout.strategy.policy), select, q_init, max_iterations, batch_leaves,
-            num_rollouts_per_leaf, expand_threshold, max_playout_depth, (1 if use_transpositions else 0) | (2 if pipelined else 0), exploration_constant,
+            num_rollouts_per_leaf, expand_threshold, max_playout_depth, (1 if use_transpositions else 0) | (2 if pipelined else 0) | (4 if canonical_symmetry else 0), exploration_constant,
             float(getattr(self.rollout.strategy, "epsilon", 0.0)), int(seed) & 0xFFFFFFFFFFFFFFFF,
             grave_threshold, rave_schedule, rave_param, int(getattr(self.rollout.strategy, "backoff_threshold", 5)), float(amaf_alpha),
             float(rave_bias), int(pipeline_depth), 0,

@@ -201,7 +201,9 @@ typedef struct {
     int threads;                /* for the playouts of one batch */
     int pipeline_depth;         /* batches in flight (<= 1: none): batch n is gathered before the results of batches
                                    n - depth + 1 .. n - 1 are applied (deterministic order) */
-    int use_transpositions;     /* SearchConfig.use_transpositions: identical states share a node (shared.rs:412-436) */
+    int use_transpositions;     /* SearchConfig.use_transpositions: identical states share a node (shared.rs:412-436);
+                                   | 2: keyed as the reference keys Othello, by the canonical-symmetry image up to 20 discs
+                                   (othello/lib.rs:474-480), with the action translation of symmetry.rs:38-50 */
     double exploration_c;
     uint64_t eps_threshold;
     uint64_t seed;
@@ -233,6 +235,11 @@ typedef struct {
     uint16_t action, created;
     int64_t amaf_score[2];
 } orc_edge_stats;
+/* Game::canonical_representation (othello/lib.rs:618-646; the identity for the other games) and the D4 index maps of
+ * game-core symmetry.rs:113-147, exposed for the tests */
+int orc_canonical_representation(int game, const orc_state *s, orc_state *canon);
+int orc_symmetry_index(int i, int k);
+int orc_symmetry_invert(int i, int k);
 double orc_select_score(const orc_search_cfg *c, int player, const orc_edge_stats *current, const orc_edge_stats *child,
                         uint32_t grave_n, int64_t grave_q);
 int orc_kat_update_amaf(int game, const orc_state *root, const uint16_t *created, uint32_t n_created, uint16_t processed,

@@ -334,8 +334,95 @@ static uint32_t best_child(const tree_t *t, const sel_cfg *cfg, const entry_t *p
     return best_i;
 }
 
-/* shared.rs:569-736; returns the path length */
-static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t *path) {
+/* ---- canonical-symmetry transposition keys (Othello): games/othello/src/lib.rs:26, 425-480, 618-665 with the D4 index
+ * maps of games/game-core/src/symmetry.rs:88-147, restated square by square (the product's host rules use word-parallel
+ * flips, so the two are independent implementations) ---- */
+#define SYMMETRY_PLY_LIMIT 20 /* othello/lib.rs:26: discs on the board up to which states are canonicalised */
+
+static int sym_flip_cols(int i) { return (i / 8) * 8 + (7 - i % 8); }
+static int sym_flip_rows(int i) { return (7 - i / 8) * 8 + i % 8; }
+static int sym_transpose(int i) { return (i % 8) * 8 + i / 8; }
+
+/* symmetry.rs:113-127 index_symmetries(i)[k]: identity, flip_cols, flip_rows, transpose, flip_rows o flip_cols,
+ * transpose o flip_cols, transpose o flip_rows, transpose o flip_rows o flip_cols */
+static int sym_index(int i, int k) {
+    switch (k) {
+    case 0: return i;
+    case 1: return sym_flip_cols(i);
+    case 2: return sym_flip_rows(i);
+    case 3: return sym_transpose(i);
+    case 4: return sym_flip_rows(sym_flip_cols(i));
+    case 5: return sym_transpose(sym_flip_cols(i));
+    case 6: return sym_transpose(sym_flip_rows(i));
+    default: return sym_transpose(sym_flip_rows(sym_flip_cols(i)));
+    }
+}
+
+/* symmetry.rs:134-147 invert_symmetry */
+static int sym_invert(int i, int k) {
+    switch (k) {
+    case 0: return i;
+    case 1: return sym_flip_cols(i);
+    case 2: return sym_flip_rows(i);
+    case 3: return sym_transpose(i);
+    case 4: return sym_flip_cols(sym_flip_rows(i));
+    case 5: return sym_flip_cols(sym_transpose(i));
+    case 6: return sym_flip_rows(sym_transpose(i));
+    default: return sym_flip_cols(sym_flip_rows(sym_transpose(i)));
+    }
+}
+
+/* D4Symmetry::apply_to_bits: every set square moves to its image */
+static uint64_t sym_bits(uint64_t b, int k) {
+    uint64_t out = 0;
+    for (int i = 0; i < 64; ++i)
+        if ((b >> i) & 1ull) out |= 1ull << sym_index(i, k);
+    return out;
+}
+
+/* othello/lib.rs:436-443 canonical_symmetry: the FIRST symmetry whose image of (black, white) is lexicographically minimal */
+static int othello_canonical_symmetry(uint64_t black, uint64_t white) {
+    int best = 0;
+    uint64_t bb = black, bw = white;
+    for (int k = 1; k < 8; ++k) {
+        uint64_t b = sym_bits(black, k), w = sym_bits(white, k);
+        if (b < bb || (b == bb && w < bw)) {
+            best = k;
+            bb = b;
+            bw = w;
+        }
+    }
+    return best;
+}
+
+/* othello/lib.rs:618-646 canonical_representation: past the disc limit the state itself with the identity; else its
+ * canonical image and the symmetry that produced it */
+static int othello_canonical(const orc_state *s, orc_state *canon) {
+    *canon = *s;
+    if (__builtin_popcountll(s->board[0] | s->board[1]) > SYMMETRY_PLY_LIMIT) return 0;
+    int k = othello_canonical_symmetry(s->board[0], s->board[1]);
+    canon->board[0] = sym_bits(s->board[0], k);
+    canon->board[1] = sym_bits(s->board[1], k);
+    return k;
+}
+
+/* test hook: Game::canonical_representation (identity for every game but Othello); returns the symmetry index */
+int orc_canonical_representation(int game, const orc_state *s, orc_state *canon) {
+    if (game == ORC_OTHELLO) return othello_canonical(s, canon);
+    *canon = *s;
+    return 0;
+}
+/* test hooks: symmetry.rs:113-127 index_symmetries(i)[k] and :134-147 invert_symmetry(i, k) */
+int orc_symmetry_index(int i, int k) { return sym_index(i, k); }
+int orc_symmetry_invert(int i, int k) { return sym_invert(i, k); }
+
+/* shared.rs:569-736; returns the path length.  With `symmetry` (use_transpositions on a game with canonical keys) the
+ * descent carries the REAL state: a node's action list is in its canonical orientation (shared.rs:233-252) and every
+ * chosen action is translated back through the symmetry of the real state at that node (symmetry.rs:38-50 incoming_sym,
+ * node.rs real_action, othello/lib.rs:658-665 invert_action); the root's list is literal.  `leaf_state` receives the real
+ * state the playouts start from. */
+static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t *path, int symmetry, orc_state *leaf_state) {
+    orc_state real = t->nodes[0].state;
     int len = 0;
     uint32_t cur = 0, incoming = 0;
     for (;;) {
@@ -346,6 +433,7 @@ static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t 
         /* trials in flight through this node from other descents: k virtual losses per gathered descent on each of its
          * edges (root_inflight for the root); this descent has put 1 on the edge it just came down */
         uint64_t in_flight = len == 1 ? t->root_inflight : cs->vloss - 1u;
+        if (leaf_state) *leaf_state = symmetry ? real : t->nodes[cur].state; /* (for every return below) */
         if (t->nodes[cur].status == 2) return len;
         if ((uint64_t)cs->visits + in_flight < cfg->expand_threshold) return len;
         if (t->nodes[cur].status == 0) {
@@ -356,11 +444,25 @@ static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t 
         incoming = best;
         uint32_t slot = t->nodes[cur].first + best;
         t->edge[slot].vloss += 1;
+        orc_state key; /* what the child node is keyed by */
+        if (symmetry) {
+            uint16_t a = t->action[slot];
+            if (cur != 0 && a < 64) { /* PASS maps to itself (othello/lib.rs:650-652) */
+                orc_state unused;
+                a = (uint16_t)sym_invert((int)a, othello_canonical(&real, &unused));
+            }
+            orc_apply(t->game, &real, a);
+            othello_canonical(&real, &key);
+        }
         if (t->child[slot] >= 0) {
             cur = (uint32_t)t->child[slot];
+            /* shared.rs:382-405 verified_child_id: the cached slot belongs to whichever orientation created it; past the
+             * disc limit another orientation's child is a different node, found (or made) through the table */
+            if (symmetry && memcmp(&t->nodes[cur].state, &key, sizeof key) != 0) cur = table_resolve(t, &key);
         } else {
             orc_state s = t->nodes[cur].state;
-            orc_apply(t->game, &s, t->action[slot]);
+            if (symmetry) s = key;
+            else orc_apply(t->game, &s, t->action[slot]);
             uint32_t id = t->use_table ? table_resolve(t, &s) : add_node(t, &s);
             t->child[slot] = (int32_t)id;
             cur = id;
@@ -368,6 +470,7 @@ static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t 
                 path[len].node = cur;
                 path[len].idx = incoming;
                 ++len;
+                if (leaf_state) *leaf_state = symmetry ? real : t->nodes[cur].state;
                 return len;
             }
         }
@@ -414,7 +517,10 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
     tree_t t;
     memset(&t, 0, sizeof t);
     t.game = c->game;
-    t.use_table = c->use_transpositions;
+    t.use_table = c->use_transpositions != 0;
+    /* use_transpositions 2: the table is keyed as the reference keys it for Othello, by the canonical-symmetry image up to
+     * SYMMETRY_PLY_LIMIT discs (othello/lib.rs:474-480) */
+    const int symmetry = (c->use_transpositions & 2) != 0 && c->game == ORC_OTHELLO;
     if (t.use_table) table_resolve(&t, root);
     else add_node(&t, root);
     grave_t grave;
@@ -494,11 +600,10 @@ int orc_search(const orc_search_cfg *c, const orc_state *root, uint16_t *best_ac
             set_nb[slot] = nb;
             for (uint32_t b = 0; b < nb; ++b) {
                 entry_t *path = set_paths[slot] + (size_t)b * max_path;
-                set_plen[slot][b] = select_step(&t, &cfg, done + b, path);
+                set_plen[slot][b] = select_step(&t, &cfg, done + b, path, symmetry, &leaves[b]);
                 for (int i = 1; i < set_plen[slot][b]; ++i) /* add_path_virtual_loss(k - 1), shared.rs:787-805 */
                     t.edge[t.nodes[path[i - 1].node].first + path[i].idx].vloss += k - 1;
                 t.root_inflight += k; /* the k trials now in flight through the root */
-                leaves[b] = t.nodes[path[set_plen[slot][b] - 1].node].state;
                 if ((lgr || nst) && set_plen[slot][b] > 1) { /* playout()'s prev_action: the last edge of the descent */
                     int L = set_plen[slot][b];
                     leaves[b].prev_plus1 = (uint16_t)(t.action[t.nodes[path[L - 2].node].first + path[L - 1].idx] + 1);

@@ -337,12 +337,20 @@ def count_ops(game, leaves, k, **kw) -> dict:
             "list_stores_per_ply": counts["list_store"] / max(1, plies)}
 
 
+def canonical_representation(game, state):
+    """(canonical state, symmetry index) by the oracle's square-by-square restatement."""
+    st = np.ascontiguousarray(state, dtype=STATE_DTYPE).reshape(-1)[:1]
+    out = st.copy()
+    sym = lib().orc_canonical_representation(int(game), _p(st), _p(out))
+    return out, sym
+
+
 def search_cfg(game=0, *, iterations=1, batch_leaves=1, k=1, policy=UNIFORM, select=0, q_init=0, expand_threshold=1,
                max_depth=0, c=2.0 ** 0.5, eps=0.1, seed=0, threads=1, use_transpositions=False, grave_threshold=700,
-               rave_schedule=0, rave_param=1000, pipelined=False, pipeline_depth=0, amaf_alpha=1.0, nst_threshold=5, rave_bias=0.0):
+               rave_schedule=0, rave_param=1000, pipelined=False, pipeline_depth=0, amaf_alpha=1.0, nst_threshold=5, rave_bias=0.0, canonical_symmetry=False):
     depth = int(pipeline_depth) if pipeline_depth else (2 if pipelined else 1)
     return SearchCfg(game, policy, select, q_init, iterations, batch_leaves, k, expand_threshold, max_depth, threads,
-                     depth, int(use_transpositions), c, eps_threshold(eps), seed, grave_threshold, rave_schedule,
+                     depth, int(bool(use_transpositions)) | (3 if canonical_symmetry else 0), c, eps_threshold(eps), seed, grave_threshold, rave_schedule,
                      rave_param, amaf_alpha, nst_threshold, rave_bias)
 
 
