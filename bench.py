@@ -561,6 +561,9 @@ def run_gpu(args):
             "hex11_grave_amaf_search": [(mb.Game.HEX11, mb.Uniform(), 4096 * kk, 128, kk, 4, thr, dict(select=SELECT_GRAVE, q_init=QINIT_INFINITY, grave_threshold=700))
                                         for kk, thr in [(64, 1), (256, 1), (1024, 1), (256, 4)]],
             "othello_decisive_tt_search": [(mb.Game.OTHELLO, mb.DecisiveMoveWin(), 4096 * kk, 128, kk, 4, 1, dict(use_transpositions=True)) for kk in (64, 256)],
+            # the same with the table keyed as the reference keys it: canonical D4 orientation up to 20 discs (othello/lib.rs:474-480)
+            "othello_decisive_tt_canonical_symmetry_search": [(mb.Game.OTHELLO, mb.DecisiveMoveWin(), 4096 * 256, 128, 256, 4, 1,
+                                                               dict(use_transpositions=True, canonical_symmetry=True))],
         }
         for name, shapes in plans.items():
             rows = []

@@ -326,15 +326,24 @@ inline int invert_symmetry8(int i, int k) {
 inline int othello_canonical(const mr_leaf &s, mr_leaf &canon) {
     canon = s;
     if (__builtin_popcountll(s.board[0] | s.board[1]) > 20) return 0;
-    int best = 0;
-    for (int k = 1; k < 8; ++k) {
-        const uint64_t b = board_symmetry8(s.board[0], k), w = board_symmetry8(s.board[1], k);
-        if (b < canon.board[0] || (b == canon.board[0] && w < canon.board[1])) {
-            best = k;
-            canon.board[0] = b;
-            canon.board[1] = w;
-        }
+    // the eight images of both boards, sharing the intermediate flips (7 word-parallel transforms per board)
+    uint64_t img[2][8];
+    for (int c = 0; c < 2; ++c) {
+        const uint64_t x = s.board[c], fc = flip_cols8(x), fr = flip_rows8(x), rot = flip_rows8(fc);
+        img[c][0] = x;
+        img[c][1] = fc;
+        img[c][2] = fr;
+        img[c][3] = transpose8(x);
+        img[c][4] = rot;
+        img[c][5] = transpose8(fc);
+        img[c][6] = transpose8(fr);
+        img[c][7] = transpose8(rot);
     }
+    int best = 0;
+    for (int k = 1; k < 8; ++k)
+        if (img[0][k] < img[0][best] || (img[0][k] == img[0][best] && img[1][k] < img[1][best])) best = k;
+    canon.board[0] = img[0][best];
+    canon.board[1] = img[1][best];
     return best;
 }
 

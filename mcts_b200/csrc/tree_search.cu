@@ -411,6 +411,7 @@ struct Search {
         lctx.clear();
         uint32_t cur = 0, incoming = 0;
         mr_leaf real = t.nodes[0].state;
+        int real_sym = 0;
         for (;;) {
             path.push_back({cur, incoming});
             lctx.emplace_back();
@@ -434,12 +435,10 @@ struct Search {
             mr_leaf key; // MR_SEARCH_SYMMETRY: what the child node is keyed by
             if (t.symmetry) {
                 uint16_t a = t.action[ei];
-                if (cur != 0 && a < 64) { // the root's list is literal; PASS maps to itself
-                    mr_leaf unused;
-                    a = (uint16_t)mr_host::invert_symmetry8((int)a, mr_host::othello_canonical(real, unused));
-                }
+                // the root's list is literal; PASS maps to itself; real_sym = the symmetry of `real` at this node
+                if (cur != 0 && a < 64) a = (uint16_t)mr_host::invert_symmetry8((int)a, real_sym);
                 mr_host::apply(t.game, real, a);
-                mr_host::othello_canonical(real, key);
+                real_sym = mr_host::othello_canonical(real, key);
             }
             if (t.child[ei] >= 0) {
                 edge_changed(path, path.size() - 1, ei, total_before);

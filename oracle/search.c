@@ -423,6 +423,7 @@ int orc_symmetry_invert(int i, int k) { return sym_invert(i, k); }
  * state the playouts start from. */
 static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t *path, int symmetry, orc_state *leaf_state) {
     orc_state real = t->nodes[0].state;
+    int real_sym = 0;
     int len = 0;
     uint32_t cur = 0, incoming = 0;
     for (;;) {
@@ -447,12 +448,10 @@ static int select_step(tree_t *t, const sel_cfg *cfg, uint32_t descent, entry_t 
         orc_state key; /* what the child node is keyed by */
         if (symmetry) {
             uint16_t a = t->action[slot];
-            if (cur != 0 && a < 64) { /* PASS maps to itself (othello/lib.rs:650-652) */
-                orc_state unused;
-                a = (uint16_t)sym_invert((int)a, othello_canonical(&real, &unused));
-            }
+            /* PASS maps to itself (othello/lib.rs:650-652); real_sym = canonical_representation(real).1 at this node */
+            if (cur != 0 && a < 64) a = (uint16_t)sym_invert((int)a, real_sym);
             orc_apply(t->game, &real, a);
-            othello_canonical(&real, &key);
+            real_sym = othello_canonical(&real, &key);
         }
         if (t->child[slot] >= 0) {
             cur = (uint32_t)t->child[slot];
