@@ -581,7 +581,9 @@ def run_gpu(args):
         for label, strat in [("breakthrough_root_parallel_2p24_per_move", mb.EpsilonGreedyMast(0.1)),
                              ("breakthrough_root_parallel_2p24_uniform_per_move", mb.Uniform())]:
             try:
-                total, bl, kk, thr = 1 << 24, 256, 1024, 2
+                # (batch shape from tools/config5_probe.py on one B200: 2 searchers x 128 x 1024 at depth 4 7.2-7.6 ms per
+                # move, 256 x 1024 9.6 ms, 3 searchers x 128 x 1024 at depth 2 6.6 ms but 2^24 is not a multiple of 3)
+                total, bl, kk, thr = 1 << 24, 128, 1024, 2
                 iters = max(1, total // (world * thr * kk))
                 root = mb.initial_state(mb.Game.BREAKTHROUGH)
                 with mb.GpuSearch(mb.Game.BREAKTHROUGH, strat, max_iterations=iters, batch_leaves=bl, num_rollouts_per_leaf=kk,
