@@ -578,12 +578,15 @@ def run_gpu(args):
         # searcher threads per GPU, one GPU per rank, every searcher its own seed and tree; root-child totals merged
         # in-library over a rank's searchers and by one NCCL all-reduce over the ranks.  Strong scaling: 2^24 / (ranks x
         # searchers) playouts per searcher.  MAST and uniform rollouts.
-        for label, strat in [("breakthrough_root_parallel_2p24_per_move", mb.EpsilonGreedyMast(0.1)),
-                             ("breakthrough_root_parallel_2p24_uniform_per_move", mb.Uniform())]:
+        for label, strat, thr in [("breakthrough_root_parallel_2p24_per_move", mb.EpsilonGreedyMast(0.1), 2),
+                                  ("breakthrough_root_parallel_2p24_uniform_per_move", mb.Uniform(), 2),
+                                  ("breakthrough_root_parallel_2p24_one_searcher_per_rank", mb.EpsilonGreedyMast(0.1), 1)]:
             try:
-                # (batch shape from tools/config5_probe.py on one B200: 2 searchers x 128 x 1024 at depth 4 7.2-7.6 ms per
-                # move, 256 x 1024 9.6 ms, 3 searchers x 128 x 1024 at depth 2 6.6 ms but 2^24 is not a multiple of 3)
-                total, bl, kk, thr = 1 << 24, 128, 1024, 2
+                # (batch shape from tools/config5_probe.py on one B200: 2 searchers x 128 x 1024 at depth 4 7.2-9 ms per
+                # move depending on the box's host, 256 x 1024 9.6-10.5 ms; 3 searchers x 128 x 1024 at depth 2 are faster
+                # still but 2^24 is not a multiple of 3.  With 8 ranks a searcher's share is 1 024 descents: the third
+                # entry shows one searcher per rank.)
+                total, bl, kk = 1 << 24, 128, 1024
                 iters = max(1, total // (world * thr * kk))
                 root = mb.initial_state(mb.Game.BREAKTHROUGH)
                 with mb.GpuSearch(mb.Game.BREAKTHROUGH, strat, max_iterations=iters, batch_leaves=bl, num_rollouts_per_leaf=kk,
@@ -591,16 +594,24 @@ def run_gpu(args):
                     mb.choose_action_root_parallel(srch, root, device=dev, draw=3)
                     barrier()
                     t0 = time.perf_counter()
-                    reps = 3
+                    reps = 5
                     for _ in range(reps):
                         action, mv, _ms, lres = mb.choose_action_root_parallel(srch, root, device=dev, draw=3)
                     barrier()
                     dt = max_over_ranks((time.perf_counter() - t0) / reps)
+                    # where a move's time goes outside the tree driver: the search call alone, timed rank by rank without
+                    # the merge (the ranks are not synchronised between these calls)
+                    t1 = time.perf_counter()
+                    for _ in range(reps):
+                        srch.choose_action(root)
+                    dt_search = max_over_ranks((time.perf_counter() - t1) / reps)
+                    barrier()
                 entry = {
                     "playouts_per_move": world * thr * iters * kk, "seconds_per_move": dt, "playouts_per_s": world * thr * iters * kk / dt,
                     "merged_root_child_visits": int(mv.sum()), "root_child_visit_share": float(mv.sum()) / (world * thr * iters * kk),
                     "best_action": int(action), "ranks": world, "searcher_threads_per_rank": thr, "iterations_per_searcher": iters,
                     "batch_leaves": bl, "playouts_per_leaf": kk, "pipeline_depth": 4, "scaling": "strong",
+                    "seconds_search_call_only": dt_search,
                     "seconds_select": lres.seconds_select, "seconds_submit": lres.seconds_submit, "seconds_gpu_wait": lres.seconds_gpu,
                     "seconds_backprop": lres.seconds_backprop,
                     "merge": "root-child (visits, score) totals: summed over a rank's searchers in-library, one all-reduce over ranks per move",

@@ -92,8 +92,8 @@ for k in [b["config"]["workload"]] + list(b["per_game"].keys()):
         o = ops[k]
         L.append(f"| {k} | {o['ops_per_ply_reference_algorithm']:.0f} | {o['ops_per_ply_model_v1']:.0f} | {o['score_evals_per_ply']:.1f} | {o['flood_iters_per_ply']:.2f} | {o['mean_legal_actions']:.1f} |")
 L.append("\n`launches_r02.csv` is the ncu launch list of `bench.py --steps 3 --warmup 3 --headline-only --no-cpu-baseline`: per step one `rollout_kernel<Breakthrough, 1, 2>` "
-         "launch (3.5 ms) plus torch's result / delta memsets (2 us each) and the untimed 256 MiB L2 flush; the e2e arm's launches are the same kernel with the fused epilogue. "
+         "launch (3.3 ms) plus torch's result / delta memsets (2 us each) and the untimed 256 MiB L2 flush; the e2e arm's launches are the same kernel with the fused epilogue. "
          "`ncu_r02_<workload>.txt` are the `ncu --set full` summaries at bench size, `ncu_r02_breakthrough8x8_eps_mast_lines.txt` the per-source-line breakdown of the headline "
-         "kernel, `gputests_2gpu_r02.log` the GPU suite on a two-GPU box (226 passed, none skipped), `oracle_stress_full_r02.txt` the reference's 100 000-game Othello sweep at full size.\n")
+         "kernel, `gputests_2gpu_r02.log` the GPU suite on a two-GPU box (242 passed, none skipped), `oracle_stress_full_r02.txt` the reference's 100 000-game Othello sweep at full size.\n")
 (P / "SUMMARY_r02.md").write_text("\n".join(L) + "\n")
 print("\n".join(L))
