@@ -661,7 +661,6 @@ def run_gpu(args):
             "traffic_unit": ("bytes of DRAM per launch (ncu, one capture; it varies from a few MB to ~100 MB with what the L2 happens to evict); ~0.26 MB of it is "
                              "algorithmic (leaves in, results + MAST delta out), the rest is write-back of the per-lane u16 playout logs (2 B per ply, "
                              "re-written in place after every drain) -- at most ~30 GB/s of the 7.7 TB/s, not a bound"),
-                            "per-warp u16 trace scratch leaving L2 behind the 256 MiB flush -- 3 GB/s, not a bound",
             "ops_per_ply_model_v1": model_ops,
             "ops_per_ply_reference_algorithm": oe.get("ops_per_ply_reference_algorithm"),
             "measured": measured_counters(HEADLINE["name"], head["plies_per_s"] / world, head["int_peak"]),
