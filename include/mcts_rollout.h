@@ -449,6 +449,17 @@ typedef struct {
     uint16_t created;      /* (out) the child node exists */
     int64_t amaf_score[2];
 } mr_edge_stats;
+/* FlatMonteCarloStrategy::choose_action (mcts/src/strategies/flat_mc.rs:58-151) as ONE batch: every root child is a leaf
+ * with `samples_per_move` uniform playouts of at most `max_rollout_depth` moves (the reference's rollout loop never looks at
+ * the state its last move reaches: a playout with max_playout_depth = max_rollout_depth - 1 scored 0 at the cutoff); a
+ * child's value is the number of playouts the root's mover won, or with `use_ucb1` w / n + ucb1_c * ln(n) / n (:135); the
+ * pick is random_best (util.rs:135-163) with the combined draw `r` in [0, 16 n).  wins_out[MR_MAX_ROOT_CHILDREN] receives
+ * the wins per root action (generate_actions order), actions_out (nullable) the actions.  MR_ERR_INVALID for a root
+ * without actions (the reference panics). */
+int mr_flat_monte_carlo(mr_ctx *ctx, int game, const mr_leaf *root, uint32_t samples_per_move, uint32_t max_rollout_depth,
+                        int use_ucb1, double ucb1_c, uint32_t r, uint64_t seed, uint16_t *best_action, uint32_t *wins_out,
+                        uint16_t *actions_out, uint32_t *n_actions);
+
 /* The value `player` (the mover at the current node) assigns to one child: `current` = the statistics of the node being
  * left (root_stats, or the edge into it), `child` = the child's edge row, NULL = a child that does not exist yet
  * (unvisited_value).  grave_n / grave_q = the reference node's AMAF count and score sum for (player, action), used by

@@ -135,6 +135,7 @@ EXPORTS = [
     "mr_apply",
     "mr_terminal_status",
     "mr_canonical_representation",
+    "mr_flat_monte_carlo",
 ]
 
 _lib = None
@@ -187,6 +188,7 @@ def load() -> C.CDLL:
     L.mr_apply.argtypes = [i32, vp, C.c_uint16]
     L.mr_terminal_status.argtypes = [i32, vp]
     L.mr_canonical_representation.argtypes = [i32, vp, vp]
+    L.mr_flat_monte_carlo.argtypes = [vp, i32, vp, C.c_uint32, C.c_uint32, i32, C.c_double, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
     L.mr_search.argtypes = [vp, C.POINTER(SearchDesc), vp, C.POINTER(C.c_uint16), vp, C.POINTER(u32), C.POINTER(SearchStats)]
     L.mr_set_kernel_timing.argtypes = [vp, i32]
     L.mr_search_root_parallel.argtypes = [C.POINTER(vp), i32, C.POINTER(SearchDesc), vp, C.POINTER(C.c_uint16), vp, C.POINTER(u32), C.POINTER(SearchStats)]

@@ -1048,6 +1048,59 @@ extern "C" int mr_search_root_parallel(mr_ctx *const *ctxs, int n_searchers, con
 }
 
 // ---- known-answer hooks (include/mcts_rollout.h "Known-answer hooks") ----
+extern "C" int mr_flat_monte_carlo(mr_ctx *ctx, int game, const mr_leaf *root, uint32_t samples_per_move, uint32_t max_rollout_depth,
+                                   int use_ucb1, double ucb1_c, uint32_t r, uint64_t seed, uint16_t *best_action, uint32_t *wins_out,
+                                   uint16_t *actions_out, uint32_t *n_actions) {
+    if (!ctx || game < 0 || game >= MR_NUM_GAMES || !root || !best_action || !wins_out || !n_actions || samples_per_move == 0)
+        return MR_ERR_INVALID;
+    return guarded([&]() -> int {
+        uint16_t acts[MR_MAX_ROOT_CHILDREN];
+        const int cnt = mr_host::terminal_status(game, *root) == MR_NOT_TERMINAL ? mr_host::generate_actions(game, *root, acts) : 0;
+        if (cnt <= 0) return MR_ERR_INVALID; // flat_mc.rs:103-105 panics on a terminal state
+        const int player = root->turn;
+        std::vector<mr_leaf> leaves((size_t)cnt, *root);
+        for (int i = 0; i < cnt; ++i) {
+            mr_host::apply(game, leaves[(size_t)i], acts[i]);
+            leaves[(size_t)i].prev_action_plus1 = 0;
+            leaves[(size_t)i].prev2_action_plus1 = 0;
+        }
+        mr_batch_desc bd;
+        memset(&bd, 0, sizeof bd);
+        bd.game = (uint32_t)game;
+        bd.policy = MR_UNIFORM;
+        bd.n_leaves = (uint32_t)cnt;
+        bd.playouts_per_leaf = samples_per_move;
+        bd.max_playout_depth = max_rollout_depth > 1 ? max_rollout_depth - 1 : 1;
+        bd.seed = seed;
+        std::vector<mr_leaf_result> res((size_t)cnt);
+        const int rc = mr_playout_batch(ctx, &bd, leaves.data(), nullptr, res.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc != MR_OK) return rc;
+        // random_best over the children's values (util.rs:135-163): the first strict maximum in visiting order
+        const double n = (double)samples_per_move;
+        uint32_t i = (r / 16u) % (uint32_t)cnt, best_i = 0;
+        const uint32_t stride = kPrimes[r % 16u];
+        bool have = false;
+        double best = 0.0;
+        for (int k = 0; k < cnt; ++k) {
+            const double w = (double)res[i].wins[player];
+            const double v = use_ucb1 ? w / n + ucb1_c * (std::log(n) / n) : w;
+            if (!have || v > best) {
+                have = true;
+                best = v;
+                best_i = i;
+            }
+            i = (uint32_t)(((uint64_t)i + stride) % (uint32_t)cnt);
+        }
+        for (int k = 0; k < cnt; ++k) {
+            wins_out[k] = res[(size_t)k].wins[player];
+            if (actions_out) actions_out[k] = acts[k];
+        }
+        *n_actions = (uint32_t)cnt;
+        *best_action = acts[best_i];
+        return MR_OK;
+    });
+}
+
 extern "C" double mr_select_score(const mr_search_desc *desc, int player, const mr_edge_stats *current, const mr_edge_stats *child,
                                   uint32_t grave_n, int64_t grave_q) {
     if (!desc || !current || player < 0 || player > 1) return NAN;

@@ -159,33 +159,18 @@ def choose_action_root_parallel(search: GpuSearch, state: np.ndarray, *, device=
 
 def flat_monte_carlo(rollout: GpuRollout, state: np.ndarray, samples_per_move: int = 100, max_rollout_depth: int = 100,
                      ucb1: float | None = None, r: int = 0):
-    """FlatMonteCarloStrategy::choose_action (mcts/src/strategies/flat_mc.rs:58-151) as ONE GPU batch: every root
-    child is a leaf with `samples_per_move` uniform playouts.  The reference's rollout loop makes at most
-    `max_rollout_depth` moves and never checks the state reached by the last one, which is exactly a playout with
-    max_playout_depth = max_rollout_depth - 1 scored as 0 at the cutoff.  Returns (action, wins per root action).
-    `r` is the combined random_best draw in [0, 16 n)."""
-    from .rollout import apply, generate_actions
-    from .root_merge import PRIMES
-
-    game = rollout.game
+    """FlatMonteCarloStrategy::choose_action (mcts/src/strategies/flat_mc.rs:58-151) as ONE GPU batch through the C ABI
+    (`mr_flat_monte_carlo`): every root child is a leaf with `samples_per_move` uniform playouts.  The reference's rollout
+    loop makes at most `max_rollout_depth` moves and never checks the state reached by the last one, which is exactly a
+    playout with max_playout_depth = max_rollout_depth - 1 scored as 0 at the cutoff.  Returns (action, wins per root
+    action).  `r` is the combined random_best draw in [0, 16 n)."""
     st = np.ascontiguousarray(state, dtype=LEAF_DTYPE).reshape(-1)[:1]
-    player = int(st[0]["turn"])
-    actions = generate_actions(game, st)
-    if not actions:
+    wins = np.zeros(MAX_ROOT_CHILDREN, dtype=np.uint32)
+    best, n = C.c_uint16(), C.c_uint32()
+    rc = rollout.lib.mr_flat_monte_carlo(rollout._h, int(rollout.game), ptr(st), int(samples_per_move), int(max_rollout_depth),
+                                         0 if ucb1 is None else 1, 0.0 if ucb1 is None else float(ucb1), int(r), rollout.seed,
+                                         C.byref(best), ptr(wins), None, C.byref(n))
+    if rc == 1:  # MR_ERR_INVALID
         raise ValueError("flat_monte_carlo on a state without actions (the reference panics here)")
-    leaves = np.concatenate([apply(game, st, a) for a in actions])
-    saved, rollout.strategy = rollout.strategy, Uniform()
-    try:
-        res = rollout.simulate_many(leaves, samples_per_move, max_playout_depth=max(0, max_rollout_depth - 1) or 1).results
-    finally:
-        rollout.strategy = saved
-    wins = res["wins"][:, player].astype(np.int64)
-    n = float(samples_per_move)
-    score = wins / n + ucb1 * (math.log(n) / n) if ucb1 is not None else wins.astype(np.float64)
-    cnt = len(actions)
-    i, stride, best, best_i = (r // 16) % cnt, PRIMES[r % 16], None, 0
-    for _ in range(cnt):  # random_best (util.rs:135-163)
-        if best is None or score[i] > best:
-            best, best_i = score[i], i
-        i = (i + stride) % cnt
-    return actions[best_i], wins
+    rollout._check(rc)
+    return best.value, wins[: n.value].astype(np.int64)

@@ -237,6 +237,29 @@ def test_flat_monte_carlo_one_batch():
     assert action in acts and wins[acts.index(action)] == wins.max()
 
 
+def test_flat_monte_carlo_ucb1_and_error_paths():
+    """flat_mc.rs:135-149: with the UCB1 value w / n + c ln(n) / n every child has the same n, so the pick for a given draw
+    is the pick by wins; a terminal root is refused (the reference panics), as is a zero sample count."""
+    from mcts_b200.search import flat_monte_carlo
+
+    game = o.BREAKTHROUGH
+    s = o.random_positions(game, 4, 12, 1)
+    with mb.GpuRollout(mb.Game.BREAKTHROUGH, seed=9) as g:
+        for r in (0, 5, 123, 16 * 7 + 3):
+            a0, w0 = flat_monte_carlo(g, s.view(mb.LEAF_DTYPE), samples_per_move=200, max_rollout_depth=60, r=r)
+            a1, w1 = flat_monte_carlo(g, s.view(mb.LEAF_DTYPE), samples_per_move=200, max_rollout_depth=60, ucb1=0.7, r=r)
+            assert a0 == a1 and (w0 == w1).all()
+        acts = o.generate_actions(game, s)
+        leaves = np.concatenate([o.apply(game, s, a) for a in acts])
+        ref = o.playout_batch(game, leaves, 200, seed=9, max_depth=59)["results"]
+        assert (w0 == ref["wins"][:, int(s["turn"][0])]).all()
+        won = o.make_state([1 << 3, 1 << 60], turn=0, flag=1)  # a finished game (the winner flag set)
+        with pytest.raises(ValueError):
+            flat_monte_carlo(g, won.view(mb.LEAF_DTYPE), samples_per_move=10)
+        with pytest.raises(ValueError):
+            flat_monte_carlo(g, s.view(mb.LEAF_DTYPE), samples_per_move=0)
+
+
 def test_search_prefers_the_centre_in_connect4():
     with mb.GpuSearch(mb.Game.CONNECT4, max_iterations=20000, batch_leaves=128, num_rollouts_per_leaf=8, seed=3) as s:
         r = s.choose_action(mb.initial_state(mb.Game.CONNECT4))
