@@ -748,3 +748,34 @@ def test_randomized_differential_sweep():
         mast = _random_mast(game, case, float(rng.random())) if uses_mast else None
         _compare(game, policy, leaves, k, seed=int(rng.integers(1 << 62)), max_depth=cutoff, mast=mast,
                  eps=float(rng.choice([0.0, 0.1, 0.5])), leaf_id_base=int(rng.integers(1 << 20)), amaf=amaf, delta=delta)
+
+
+def test_randomized_sweep_of_the_production_variants():
+    """The same kind of seeded sweep over the kernel variants a search launches -- no trace, no final state: results only,
+    + AMAF, + MAST delta, + both -- with the aggregates compared bit for bit against the oracle (the traced sweep above
+    runs a different instantiation of every kernel).  MR_FUZZ_CASES / MR_FUZZ_SEED lengthen it."""
+    import os
+
+    rng = np.random.default_rng(int(os.environ.get("MR_FUZZ_SEED", "20260202")))
+    policies = [o.UNIFORM, o.EPS_MAST, o.DECISIVE_WIN, o.DECISIVE_MAST_WIN]
+    max_plies = {o.CONNECT4: 30, o.BREAKTHROUGH: 50, o.KNIGHTTHROUGH: 30, o.OTHELLO: 56, o.HEX11: 100}
+    for case in range(int(os.environ.get("MR_FUZZ_CASES", "40"))):
+        game = GAMES[case % 5]
+        policy = policies[int(rng.integers(len(policies)))]
+        n, k = int(rng.integers(1, 40)), int(rng.choice([1, 3, 32, 33, 100, 700, 2100]))
+        leaves = o.random_positions(game, 5000 + case, int(rng.integers(0, max_plies[game])), n)
+        amaf, delta = bool(rng.integers(2)), bool(rng.integers(2))
+        depth = int(rng.choice([0, 6, 60])) if not (amaf or delta) and game != o.KNIGHTTHROUGH else int(rng.choice([7, 60, 250]))
+        uses_mast = policy in (o.EPS_MAST, o.DECISIVE_MAST_WIN)
+        mast = _random_mast(game, case, float(rng.choice([0.0, 0.3, 0.9, 1.0]))) if uses_mast else None
+        eps, seed, base = float(rng.choice([0.0, 0.1, 0.5])), int(rng.integers(1 << 62)), int(rng.integers(1 << 20))
+        ref = o.playout_batch(game, leaves, k, policy=policy, eps=eps, max_depth=depth, seed=seed, leaf_id_base=base, mast=mast,
+                              want_amaf=amaf, want_mast_delta=delta, threads=o.host_threads())
+        with mb.GpuRollout(mb.Game(game), _strategy(policy, eps), seed=seed, max_playout_depth=depth) as g:
+            got = g.simulate_many(leaves.view(mb.LEAF_DTYPE), k, stats=mast, want_amaf=amaf, want_mast_delta=delta, leaf_id_base=base)
+        name = (case, o.GAME_NAMES[game], policy, n, k, depth, amaf, delta)
+        assert got.results.tobytes() == ref["results"].tobytes(), name
+        if amaf:
+            assert got.amaf.tobytes() == ref["amaf"].tobytes(), name
+        if delta:
+            assert got.mast_delta.tobytes() == ref["mast_delta"].tobytes(), name
