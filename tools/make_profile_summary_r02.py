@@ -79,10 +79,14 @@ if scal:
         n = d["n_gpus"]
         L.append(f"| {n} | {d['value']:.3e} | {d['ms_per_step']:.3f} | {d['value'] / (n * b['value']):.3f} | {d['e2e']['value']:.3e} | {d['e2e']['value'] / (n * b['e2e']['value']):.3f} | "
                  f"{'all ok' if all(d.get('self_check', {}).values()) else d.get('self_check')} |")
-        s5 = d["search"].get("breakthrough_root_parallel_2p24_per_move", {})
-        if "seconds_per_move" in s5:
-            L.append(f"|  | config 5 (2^24 playouts, one move, {s5['ranks']} ranks x {s5['searcher_threads_per_rank']} searchers): {s5['seconds_per_move'] * 1e3:.2f} ms, "
-                     f"{s5['playouts_per_s']:.3e} playouts/s, {s5['root_child_visit_share']:.4f} of the playouts below a root child | | | | | |")
+        for key in ("breakthrough_root_parallel_2p24_per_move", "breakthrough_root_parallel_2p24_one_searcher_per_rank"):
+            s5 = d["search"].get(key, {})
+            if "seconds_per_move" in s5:
+                one = b["search"].get("breakthrough_root_parallel_2p24_per_move", {}).get("seconds_per_move")
+                L.append(f"|  | config 5 (2^24 playouts, one move, {s5['ranks']} ranks x {s5['searcher_threads_per_rank']} searchers): {s5['seconds_per_move'] * 1e3:.2f} ms"
+                         + (f" ({one / s5['seconds_per_move']:.2f}x the one-GPU move)" if one else "") + f", {s5['playouts_per_s']:.3e} playouts/s, "
+                         f"{s5['root_child_visit_share']:.4f} of the playouts below a root child"
+                         + (f"; the search call alone {s5['seconds_search_call_only'] * 1e3:.2f} ms" if "seconds_search_call_only" in s5 else "") + " | | | | | |")
     L.append("")
 L.append("## Counted operations of the reference's arithmetic (instrumented oracle, `oracle_ops_r02.json`)\n")
 L.append("| workload | reference-algorithm ops/ply | model v1 ops/ply | MAST score evals/ply | flood iterations/ply | list stores/ply |")
