@@ -578,9 +578,14 @@ def run_gpu(args):
         # searcher threads per GPU, one GPU per rank, every searcher its own seed and tree; root-child totals merged
         # in-library over a rank's searchers and by one NCCL all-reduce over the ranks.  Strong scaling: 2^24 / (ranks x
         # searchers) playouts per searcher.  MAST and uniform rollouts.
-        for label, strat, thr in [("breakthrough_root_parallel_2p24_per_move", mb.EpsilonGreedyMast(0.1), 2),
-                                  ("breakthrough_root_parallel_2p24_uniform_per_move", mb.Uniform(), 2),
-                                  ("breakthrough_root_parallel_2p24_one_searcher_per_rank", mb.EpsilonGreedyMast(0.1), 1)]:
+        # searchers per rank: two while a searcher's share is large (1 or 2 ranks), one from 4 ranks on, where a share is
+        # <= 4 096 descents and a second searcher only adds skew in front of the move's all-reduce (measured both ways:
+        # the third entry is the other count)
+        thr_main = 2 if world <= 2 else 1
+        other = ("breakthrough_root_parallel_2p24_one_searcher_per_rank", 1) if thr_main == 2 else ("breakthrough_root_parallel_2p24_two_searchers_per_rank", 2)
+        for label, strat, thr in [("breakthrough_root_parallel_2p24_per_move", mb.EpsilonGreedyMast(0.1), thr_main),
+                                  ("breakthrough_root_parallel_2p24_uniform_per_move", mb.Uniform(), thr_main),
+                                  (other[0], mb.EpsilonGreedyMast(0.1), other[1])]:
             try:
                 # (batch shape from tools/config5_probe.py on one B200: 2 searchers x 128 x 1024 at depth 4 7.2-9 ms per
                 # move depending on the box's host, 256 x 1024 9.6-10.5 ms; 3 searchers x 128 x 1024 at depth 2 are faster

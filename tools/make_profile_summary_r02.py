@@ -79,7 +79,8 @@ if scal:
         n = d["n_gpus"]
         L.append(f"| {n} | {d['value']:.3e} | {d['ms_per_step']:.3f} | {d['value'] / (n * b['value']):.3f} | {d['e2e']['value']:.3e} | {d['e2e']['value'] / (n * b['e2e']['value']):.3f} | "
                  f"{'all ok' if all(d.get('self_check', {}).values()) else d.get('self_check')} |")
-        for key in ("breakthrough_root_parallel_2p24_per_move", "breakthrough_root_parallel_2p24_one_searcher_per_rank"):
+        for key in ("breakthrough_root_parallel_2p24_per_move", "breakthrough_root_parallel_2p24_one_searcher_per_rank",
+                    "breakthrough_root_parallel_2p24_two_searchers_per_rank"):
             s5 = d["search"].get(key, {})
             if "seconds_per_move" in s5:
                 one = b["search"].get("breakthrough_root_parallel_2p24_per_move", {}).get("seconds_per_move")
