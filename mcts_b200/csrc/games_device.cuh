@@ -710,17 +710,16 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
             const uint32_t cnt = __popc(b0 & m) + 2u * __popc(b1 & m) + 4u * __popc(b2 & m) + 8u * __popc(b3 & m);
             select_step(idx, pos, cnt, (uint32_t)step);
         }
-        // residual: idx-th set kind at this cell, kinds in ascending-dst order
-        uint32_t kk = 7;
-        bool found = false;
+        // residual: the idx-th set kind at this cell, kinds in ascending-dst order -- the cell's kinds as a byte, then a
+        // three-step rank/select over it
+        uint32_t kb = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t b = ((in_hi ? hi32(M[q]) : lo32(M[q])) >> pos) & 1u;
-            if (!found && b && idx == 0) {
-                kk = q;
-                found = true;
-            }
-            idx -= (found ? 0u : b);
+        for (int q = 0; q < 8; ++q) kb |= (((in_hi ? hi32(M[q]) : lo32(M[q])) >> pos) & 1u) << q;
+        uint32_t kk = 0;
+#pragma unroll
+        for (int step = 4; step >= 1; step >>= 1) {
+            const uint32_t cnt = __popc(kb & (((1u << step) - 1u) << kk));
+            select_step(idx, kk, cnt, (uint32_t)step);
         }
         kind = kk;
         return pos + (in_hi ? 32u : 0u);
@@ -808,20 +807,57 @@ __device__ int Knightthrough::step(const Shared &sh, uint32_t x0, uint32_t x1, c
         for (int q = 0; q < 8; ++q) cand[q] = M[q];
         if (POLICY == MR_EPS_NST) mast_argmax<8>(cand, nst_planes, nst_nbits);
         else mast_argmax<8>(cand, p.mast_planes[pl], p.mast_nbits[pl]);
-        uint32_t m = 0;
         uint64_t any = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            m += __popcll(cand[q]);
-            any |= cand[q];
-        }
-        if (m == 1) {
+        for (int q = 0; q < 8; ++q) any |= cand[q];
+        if ((any & (any - 1ull)) == 0ull) {
+            // Every maximal action starts from ONE cell -- the unique maximum, or (a quarter of the plies) the winning jumps
+            // of one knight tied at score 1: the cell's candidate kinds as a byte, no popcounts over the eight boards
             src = (uint32_t)__ffsll((long long)any) - 1u;
+            const bool hi = src >= 32u;
+            const uint32_t b = src & 31u;
+            uint32_t kb = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (cand[q]) kind = q;
-            have = true;
+            for (int q = 0; q < 8; ++q) kb |= (((hi ? hi32(cand[q]) : lo32(cand[q])) >> b) & 1u) << q;
+            if ((kb & (kb - 1u)) == 0u) {
+                kind = (uint32_t)__ffs((int)kb) - 1u;
+                have = true;
+            } else {
+                const uint32_t r = mulhi(x0, 16u * n);
+                const uint32_t i0 = r >> 4;
+                if ((uint32_t)__popc(kb) == n) { // the cell's jumps are all there is
+                    idx = i0;
+                    idx_set = true;
+                } else {
+                    // random_best among the cell's tied kinds: visiting rank of the cell's first action, + inv (mod n) per
+                    // further legal kind (as in the general loop below)
+                    const uint32_t pk = r & 15u;
+                    const uint32_t inv = MR_STRIDE_INV[n][pk], rcp = MR_RCP32[n];
+                    uint32_t lb = 0;
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) lb |= (((hi ? hi32(M[q]) : lo32(M[q])) >> b) & 1u) << q;
+                    const uint32_t below = (1u << b) - 1u;
+                    const uint32_t h0 = hi ? hi32(B0) : lo32(B0), h1 = hi ? hi32(B1) : lo32(B1);
+                    const uint32_t h2 = hi ? hi32(B2) : lo32(B2), h3 = hi ? hi32(B3) : lo32(B3);
+                    uint32_t i = (uint32_t)(__popc(h0 & below) + 2 * __popc(h1 & below) + 4 * __popc(h2 & below) + 8 * __popc(h3 & below));
+                    if (hi) i += __popc(lo32(B0)) + 2u * __popc(lo32(B1)) + 4u * __popc(lo32(B2)) + 8u * __popc(lo32(B3));
+                    uint32_t j = visiting_rank(i, i0, n, inv, rcp), best = 0xffffffffu;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if ((kb >> q) & 1u) best = min(best, (j << 3) | (uint32_t)q);
+                        if (q < 7 && ((lb >> q) & 1u)) {
+                            j += inv;
+                            j = min(j, j - n); // j - n wraps to a huge value while j < n
+                        }
+                    }
+                    kind = best & 7u;
+                    have = true;
+                }
+            }
         } else {
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m += __popcll(cand[q]);
             const uint32_t r = mulhi(x0, 16u * n);
             const uint32_t i0 = r >> 4;
             if (m == n) {
