@@ -77,7 +77,15 @@ int main(void) {
     for (uint32_t i = 0; i < n_children; ++i) visits += children[i].visits;
     printf("search: %llu playouts in %u batches, %llu nodes, best column %u (%u children, %llu child visits)\n",
            (unsigned long long)st.playouts, st.batches, (unsigned long long)st.nodes, best, n_children, (unsigned long long)visits);
+    /* ---- 3. the same decision by flat Monte Carlo (flat_mc.rs): every root child one leaf of one batch ---- */
+    uint16_t flat_best = 0, flat_actions[MR_MAX_ROOT_CHILDREN];
+    uint32_t flat_wins[MR_MAX_ROOT_CHILDREN], n_flat = 0;
+    CHECK(mr_flat_monte_carlo(ctx, MR_CONNECT4, &leaves[0], 4096, 100, 0, 0.0, 5, 7, &flat_best, flat_wins, flat_actions, &n_flat));
+    printf("flat MC: best column %u of %u (wins of 4096:", flat_best, n_flat);
+    for (uint32_t i = 0; i < n_flat; ++i) printf(" %u:%u", flat_actions[i], flat_wins[i]);
+    printf(")\n");
     printf("kernel launches: %llu\n", (unsigned long long)mr_kernel_launches(ctx));
     mr_destroy(ctx);
+    if (flat_best != 3) return 4;
     return best == 3 ? 0 : 2; /* the centre column is the right first move */
 }
