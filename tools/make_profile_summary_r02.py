@@ -99,6 +99,6 @@ for k in [b["config"]["workload"]] + list(b["per_game"].keys()):
 L.append("\n`launches_r02.csv` is the ncu launch list of `bench.py --steps 3 --warmup 3 --headline-only --no-cpu-baseline`: per step one `rollout_kernel<Breakthrough, 1, 2>` "
          "launch (3.3 ms) plus torch's result / delta memsets (2 us each) and the untimed 256 MiB L2 flush; the e2e arm's launches are the same kernel with the fused epilogue. "
          "`ncu_r02_<workload>.txt` are the `ncu --set full` summaries at bench size, `ncu_r02_breakthrough8x8_eps_mast_lines.txt` the per-source-line breakdown of the headline "
-         "kernel, `gputests_2gpu_r02.log` the GPU suite on a two-GPU box (242 passed, none skipped), `oracle_stress_full_r02.txt` the reference's 100 000-game Othello sweep at full size.\n")
+         "kernel, `gputests_2gpu_r02.log` the GPU suite on a two-GPU box (244 passed, none skipped), `oracle_stress_full_r02.txt` the reference's 100 000-game Othello sweep at full size.\n")
 (P / "SUMMARY_r02.md").write_text("\n".join(L) + "\n")
 print("\n".join(L))
